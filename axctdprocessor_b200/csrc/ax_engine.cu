@@ -1,0 +1,724 @@
+// ax_engine.cu -- kernels, host runtime and C ABI of the AXCTD engine (sm_100a).
+//
+// Built by __graft_entry__.build() with
+//   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+// The same translation unit compiles with g++ -x c++ -DAXCTD_EMU into the
+// test-only host emulation (tests/emu), which the product never loads.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "ax_proto.h"
+
+#ifndef AXCTD_EMU
+#include <cuda_runtime.h>
+#include "ax_kernels.cuh"
+#endif
+
+// ============================================================ launch plumbing
+#ifdef AXCTD_EMU
+typedef int axStream;
+#define AX_GLOBAL static
+#define AX_FOR_ITEM(n) for (int64_t item = 0; item < (n); ++item)
+#define AX_LAUNCH(eng, name, n, ...)                         \
+    do { if ((n) > 0) { name((int64_t)(n), __VA_ARGS__); (eng)->launches++; } } while (0)
+#else
+typedef cudaStream_t axStream;
+#define AX_GLOBAL __global__
+#define AX_FOR_ITEM(n) const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; if (item < (n))
+#define AX_LAUNCH(eng, name, n, ...)                                                                   \
+    do { if ((n) > 0) { const int64_t _n = (n); const int _b = 128;                                   \
+        name<<<(unsigned)((_n + _b - 1) / _b), _b, 0, (eng)->stream>>>(_n, __VA_ARGS__); (eng)->launches++; } } while (0)
+#endif
+
+AX_GLOBAL void k_init(int64_t n, AxWave w) {
+    AX_FOR_ITEM(n) {
+        AxState& st = w.st[item];
+        memset(&st, 0, sizeof(AxState));
+        st.ampl = -2147483647 - 1;
+        st.k0 = st.k2 = st.km = st.k1 = -1;
+        st.firstpulse400 = -1; st.profstartind = -1; st.firstpointtime = -1.0; st.mean7500 = ax_nan();
+        st.status_chunk = -1;
+        for (int q = 0; q < 3; ++q) st.header_chunk[q] = -1;
+        const AxCfg& c = w.cfg[w.drop[item].cfg];
+        st.scale = c.scale0;
+        for (int q = 0; q < 4; ++q) { st.zc_used[q] = c.zc[q]; st.tc_used[q] = c.tc[q]; st.cc_used[q] = c.cc[q]; }
+    }
+}
+AX_GLOBAL void k_inject(int64_t n, AxWave w) {     // test hook: pretend the first prediction was off by 3 samples
+    AX_FOR_ITEM(n) {
+        AxState& s = w.st[item];
+        if (s.sm_status >= 1 && s.n_chunks > s.k0 + 2) {
+            AxChunk* c = w.chunk + w.drop[item].chunk_base + s.k0;
+            c[0].spec_last += 3; c[1].s += 3; c[1].e += 3;
+        }
+    }
+}
+AX_GLOBAL void k_stats(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_stats_item(w, item); }
+AX_GLOBAL void k_stats_fin(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_stats_fin(w, item); }
+AX_GLOBAL void k_filter(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_filter_item(w, item); }
+AX_GLOBAL void k_scan(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_scan_item(w, item); }
+AX_GLOBAL void k_compact(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_compact_item(w, item); }
+AX_GLOBAL void k_tiles(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_tiles_item(w, item); }
+AX_GLOBAL void k_plan0(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_plan0_item(w, item); }
+AX_GLOBAL void k_tone_direct(int64_t n, AxWave w, int phase_b) { AX_FOR_ITEM(n) ax_tone_direct_item(w, item, phase_b); }
+AX_GLOBAL void k_sm(int64_t n, AxWave w, int phase_b) { AX_FOR_ITEM(n) ax_sm_item(w, item, phase_b); }
+AX_GLOBAL void k_chain(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_chain_item(w, item); }
+AX_GLOBAL void k_heads(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_head_item(w, item); }
+AX_GLOBAL void k_verify(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_verify_item(w, item); }
+AX_GLOBAL void k_plan_tones(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_plan_tones_item(w, item); }
+AX_GLOBAL void k_offsets(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_offsets_item(w, item); }
+AX_GLOBAL void k_emit(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_emit_item(w, item); }
+AX_GLOBAL void k_scale(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_scale_item(w, item); }
+AX_GLOBAL void k_bits(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_bits_item(w, item); }
+AX_GLOBAL void k_headers(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_header_item(w, item); }
+AX_GLOBAL void k_frames(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_frames_item(w, item); }
+AX_GLOBAL void k_calib(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_calib_item(w, item); }
+AX_GLOBAL void k_qc(int64_t n, AxWave w, double* scratch) { AX_FOR_ITEM(n) ax_qc_item(w, item, scratch); }
+
+// ============================================================ memory helpers
+struct axctd_engine {
+    int device = 0;
+    axStream stream = 0;
+    std::string err;
+    std::vector<AxCfg> cfgs;              // host copies (device pointers inside)
+    std::vector<void*> cfg_allocs;
+    AxCfg* d_cfg = nullptr;
+    int cfg_cap = 64;
+    int64_t launches = 0;
+    // options
+    int64_t opt_segment_len = 0;          // 0 = auto
+    int opt_exact_head = 0;               // 0 = auto from pole radius
+    double opt_guard = 1e-12;
+    int opt_force_exact = 0;
+    int opt_tone_direct = 0;
+    int opt_max_fixups = 64;
+    int opt_filter_variant = 0;
+    int opt_zc_div = 12;
+    int opt_inject_misspec = 0;           // test hook: corrupt the first prediction
+};
+
+#ifdef AXCTD_EMU
+static int ax_alloc(axctd_engine*, void** p, size_t bytes) { *p = calloc(bytes ? bytes : 1, 1); return *p ? 0 : 1; }
+static void ax_free(void* p) { free(p); }
+static int ax_h2d(axctd_engine*, void* d, const void* h, size_t b) { memcpy(d, h, b); return 0; }
+static int ax_d2h(axctd_engine*, void* h, const void* d, size_t b) { memcpy(h, d, b); return 0; }
+static int ax_zero(axctd_engine*, void* d, size_t b) { memset(d, 0, b); return 0; }
+static int ax_sync(axctd_engine*) { return 0; }
+#else
+static int ax_fail(axctd_engine* e, cudaError_t r, const char* what) {
+    if (r == cudaSuccess) return 0;
+    e->err = std::string(what) + ": " + cudaGetErrorString(r);
+    return 1;
+}
+static int ax_alloc(axctd_engine* e, void** p, size_t bytes) { return ax_fail(e, cudaMalloc(p, bytes ? bytes : 1), "cudaMalloc"); }
+static void ax_free(void* p) { if (p) cudaFree(p); }
+static int ax_h2d(axctd_engine* e, void* d, const void* h, size_t b) { return ax_fail(e, cudaMemcpyAsync(d, h, b, cudaMemcpyHostToDevice, e->stream), "H2D"); }
+static int ax_d2h(axctd_engine* e, void* h, const void* d, size_t b) { return ax_fail(e, cudaMemcpyAsync(h, d, b, cudaMemcpyDeviceToHost, e->stream), "D2H"); }
+static int ax_zero(axctd_engine* e, void* d, size_t b) { return ax_fail(e, cudaMemsetAsync(d, 0, b, e->stream), "memset"); }
+static int ax_sync(axctd_engine* e) { return ax_fail(e, cudaStreamSynchronize(e->stream), "sync"); }
+#endif
+
+struct axctd_batch {
+    axctd_engine* eng = nullptr;
+    int n = 0;
+    std::vector<AxDrop> drops;
+    std::vector<void*> allocs;
+    AxWave w;
+    int16_t* d_pcm = nullptr;
+    double* d_qc = nullptr;
+    int64_t pcm_total = 0, chunk_total = 0, edge_total = 0, frame_total = 0, zc_total = 0, tile_total = 0;
+    // host mirrors of the results
+    std::vector<AxState> st;
+    std::vector<AxChunk> chunk;
+    std::vector<axctd_frame> frame;
+    std::vector<axctd_drop_summary> summary;
+    bool ran = false, finished = false;
+    double ms_total = 0, ms_filter = 0, ms_tone = 0;
+#ifndef AXCTD_EMU
+    cudaEvent_t ev[6];
+#endif
+};
+
+template <typename T>
+static int ax_alloc_arr(axctd_batch* b, T** p, int64_t count) {
+    void* v = nullptr;
+    if (ax_alloc(b->eng, &v, (size_t)std::max<int64_t>(count, 1) * sizeof(T))) return 1;
+    b->allocs.push_back(v);
+    *p = (T*)v;
+    return 0;
+}
+
+// ============================================================ C ABI: engine
+extern "C" int axctd_abi_version(void) { return AXCTD_ABI_VERSION; }
+extern "C" int axctd_has_cuda(void) {
+#ifdef AXCTD_EMU
+    return 0;
+#else
+    return 1;
+#endif
+}
+
+extern "C" int axctd_struct_size(int which) {
+    switch (which) {
+        case 0: return (int)sizeof(axctd_config_desc);
+        case 1: return (int)sizeof(axctd_drop_summary);
+        case 2: return (int)sizeof(axctd_frame);
+        case 3: return (int)sizeof(axctd_chunk);
+    }
+    return -1;
+}
+
+extern "C" int axctd_engine_create(int device, axctd_engine** out) {
+    if (!out) return AXCTD_ERR_ARG;
+    axctd_engine* e = new axctd_engine();
+    e->device = device;
+#ifndef AXCTD_EMU
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        // no silent CPU path: the product needs a CUDA device
+        delete e; *out = nullptr; return AXCTD_ERR_CUDA;
+    }
+    if (ax_fail(e, cudaSetDevice(device), "cudaSetDevice") ||
+        ax_fail(e, cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking), "cudaStreamCreate")) {
+        delete e; *out = nullptr; return AXCTD_ERR_CUDA;
+    }
+#endif
+    void* p = nullptr;
+    if (ax_alloc(e, &p, sizeof(AxCfg) * e->cfg_cap)) { delete e; *out = nullptr; return AXCTD_ERR_CUDA; }
+    e->d_cfg = (AxCfg*)p;
+    *out = e;
+    return AXCTD_OK;
+}
+
+extern "C" void axctd_engine_destroy(axctd_engine* e) {
+    if (!e) return;
+    for (void* p : e->cfg_allocs) ax_free(p);
+    ax_free(e->d_cfg);
+#ifndef AXCTD_EMU
+    if (e->stream) cudaStreamDestroy(e->stream);
+#endif
+    delete e;
+}
+
+extern "C" const char* axctd_last_error(axctd_engine* e) { return e ? e->err.c_str() : "null engine"; }
+extern "C" int64_t axctd_engine_launch_count(axctd_engine* e) { return e ? e->launches : 0; }
+
+extern "C" int axctd_engine_set_option(axctd_engine* e, const char* name, double v) {
+    if (!e || !name) return AXCTD_ERR_ARG;
+    std::string s(name);
+    if (s == "segment_len") e->opt_segment_len = (int64_t)v;
+    else if (s == "exact_head") e->opt_exact_head = (int)v;
+    else if (s == "guard") e->opt_guard = v;
+    else if (s == "force_exact") e->opt_force_exact = (int)v;
+    else if (s == "tone_direct") e->opt_tone_direct = (int)v;
+    else if (s == "max_fixups") e->opt_max_fixups = (int)v;
+    else if (s == "filter_variant") e->opt_filter_variant = (int)v;
+    else if (s == "zc_div") e->opt_zc_div = std::max(2, (int)v);
+    else if (s == "inject_misspec") e->opt_inject_misspec = (int)v;
+    else return AXCTD_ERR_ARG;
+    return AXCTD_OK;
+}
+
+static int64_t ax_gcd(int64_t a, int64_t b) { while (b) { int64_t t = a % b; a = b; b = t; } return a; }
+
+template <typename T>
+static int ax_cfg_upload(axctd_engine* e, const T** dst, const T* src, size_t count) {
+    void* p = nullptr;
+    if (ax_alloc(e, &p, count * sizeof(T))) return 1;
+    e->cfg_allocs.push_back(p);
+    if (ax_h2d(e, p, src, count * sizeof(T))) return 1;
+    *dst = (const T*)p;
+    return 0;
+}
+
+extern "C" int axctd_config_create(axctd_engine* e, const axctd_config_desc* ds, int* config_id) {
+    if (!e || !ds || !config_id) return AXCTD_ERR_ARG;
+    if ((int)e->cfgs.size() >= e->cfg_cap) { e->err = "too many configs"; return AXCTD_ERR_CAPACITY; }
+    if (ds->n_sections < 1 || ds->n_sections > AX_MAXSEC || ds->bit_inset != 1 || ds->npcm < 1 ||
+        ds->bit_cs_len < ds->npcm + 1 || ds->n_power < 1 || ds->d_pcm < 1 || ds->chunk_len < 1 ||
+        !ds->bit_cs || !ds->tone_cs || !ds->temp_lut || !ds->hist_edges || !ds->hist_centers ||
+        ds->n_hist_edges < 3 || ds->n_hist_edges > 512) { e->err = "bad config"; return AXCTD_ERR_ARG; }
+    AxCfg c;
+    memset(&c, 0, sizeof(c));
+    c.fs = ds->fs;
+    c.fs2 = (int64_t)llround(2.0 * ds->fs);
+    c.n_power = ds->n_power; c.d_pcm = ds->d_pcm; c.npcm = ds->npcm; c.chunk_len = ds->chunk_len;
+    c.pad = ds->pad; c.inset = ds->bit_inset; c.bitrate = ds->bitrate; c.nsec = ds->n_sections;
+    for (int s = 0; s < AX_MAXSEC; ++s) for (int q = 0; q < 6; ++q) c.sos[s][q] = (s < c.nsec) ? ds->sos[s][q] : 0.0;
+    double r = ds->max_pole_radius;
+    if (!(r > 0.0 && r < 1.0)) { e->err = "max_pole_radius must be in (0,1)"; return AXCTD_ERR_ARG; }
+    // transient of a zero-state restart relative to the continuous filter decays like r^n:
+    // overlap until it is below 1e-19 of full scale (a few hundred times below fp64 epsilon)
+    int warm = (int)ceil(log(1e-19) / log(r));
+    warm = ((warm + 63) / 64) * 64;
+    if (warm < 256) warm = 256;
+    c.warm = warm;
+    c.head = e->opt_exact_head > 0 ? e->opt_exact_head : warm;
+    if (c.head < c.pad + 8) c.head = c.pad + 8;
+    c.rebase = ds->bit_cs_len - 1;
+    c.head_zc_cap = c.head / 4 + 64;
+    c.ybuf_len = c.head + c.npcm + 2;
+    const int64_t G = ax_gcd(c.n_power, c.d_pcm);
+    c.tone_G = (int)G; c.tone_nb = (int)(c.n_power / G); c.tone_stride = (int)(c.d_pcm / G);
+    c.min_r400 = ds->min_r400; c.min_dr7500 = ds->min_dr7500;
+    c.min_r400_inprof = ds->min_r400 / 2; c.min_dr7500_inprof = ds->min_dr7500 / 2;     // AXCTDprocessor.py:226,228
+    c.trig_from = ds->trigger_from_s; c.trig_to = ds->trigger_to_s; c.scale0 = ds->high_bit_scale0;
+    for (int q = 0; q < 4; ++q) { c.zc[q] = ds->zcoeff[q]; c.tc[q] = ds->tcoeff[q]; c.cc[q] = ds->ccoeff[q]; }
+    for (int q = 0; q < 2; ++q) { c.tlims[q] = ds->tlims[q]; c.slims[q] = ds->slims[q]; }
+    const double fs = ds->fs;
+    c.off_4p5 = (int64_t)(fs * 4.5); c.off_5p5 = (int64_t)(fs * 5.5);                     // :388-392
+    c.off_trig_from = (int64_t)(ds->trigger_from_s * fs); c.off_trig_to = (int64_t)(fs * ds->trigger_to_s);   // :397,404
+    c.h1s = (int64_t)(fs * 2.3); c.h1e = (int64_t)(fs * 3.3);                             // :447-448
+    c.h2s = (int64_t)(fs * 10.5); c.h2e = (int64_t)(fs * 14.8);                           // :451-452
+    c.h3s = (int64_t)(fs * 20); c.h3e = (int64_t)(fs * 24.5);                             // :455-456
+    c.half = (int64_t)(fs * 0.5);
+    const double* bc = ds->bit_cs + 4 * (size_t)c.rebase;      // e^{+j theta R}; store the conjugate
+    c.rot[0][0] = bc[0]; c.rot[0][1] = -bc[1]; c.rot[1][0] = bc[2]; c.rot[1][1] = -bc[3];
+    c.lut_len = ds->lut_len; c.n_hist_edges = ds->n_hist_edges;
+    if (ax_cfg_upload(e, &c.bit_cs, ds->bit_cs, 4 * (size_t)ds->bit_cs_len) ||
+        ax_cfg_upload(e, &c.tone_cs, ds->tone_cs, 6 * (size_t)ds->n_power) ||
+        ax_cfg_upload(e, &c.lut, ds->temp_lut, (size_t)ds->lut_len) ||
+        ax_cfg_upload(e, &c.hist_edges, ds->hist_edges, (size_t)ds->n_hist_edges) ||
+        ax_cfg_upload(e, &c.hist_centers, ds->hist_centers, (size_t)ds->n_hist_edges - 1)) return AXCTD_ERR_CUDA;
+    e->cfgs.push_back(c);
+    if (ax_h2d(e, e->d_cfg + (e->cfgs.size() - 1), &e->cfgs.back(), sizeof(AxCfg)) || ax_sync(e)) return AXCTD_ERR_CUDA;
+    *config_id = (int)e->cfgs.size() - 1;
+    return AXCTD_OK;
+}
+
+// ============================================================ C ABI: batch
+extern "C" void axctd_batch_destroy(axctd_batch* b) {
+    if (!b) return;
+#ifndef AXCTD_EMU
+    cudaStreamSynchronize(b->eng->stream);
+    for (int i = 0; i < 6; ++i) cudaEventDestroy(b->ev[i]);
+#endif
+    for (void* p : b->allocs) ax_free(p);
+    delete b;
+}
+
+extern "C" int axctd_batch_create(axctd_engine* e, int n_drops, const int64_t* n_samples, const int32_t* config_id,
+                                  axctd_batch** out) {
+    if (!e || n_drops <= 0 || !n_samples || !config_id || !out) return AXCTD_ERR_ARG;
+    axctd_batch* b = new axctd_batch();
+    b->eng = e; b->n = n_drops;
+    memset(&b->w, 0, sizeof(AxWave));
+#ifndef AXCTD_EMU
+    cudaSetDevice(e->device);
+    for (int i = 0; i < 6; ++i) cudaEventCreate(&b->ev[i]);
+#endif
+    int64_t total = 0;
+    int warm_max = 0, head_cap_max = 0, ybuf_max = 0, chunk_len_max = 0, blk_max = 1;
+    for (int d = 0; d < n_drops; ++d) {
+        if (config_id[d] < 0 || config_id[d] >= (int)e->cfgs.size() || n_samples[d] < 0 || n_samples[d] > 2000000000LL) {
+            e->err = "bad drop descriptor"; axctd_batch_destroy(b); return AXCTD_ERR_ARG;
+        }
+        const AxCfg& c = e->cfgs[config_id[d]];
+        total += n_samples[d];
+        warm_max = std::max(warm_max, c.warm);
+        head_cap_max = std::max(head_cap_max, c.head_zc_cap);
+        ybuf_max = std::max(ybuf_max, c.ybuf_len);
+        chunk_len_max = std::max(chunk_len_max, c.chunk_len);
+        if (ax_tone_blocked_ok(c)) blk_max = std::max(blk_max, (c.chunk_len / c.d_pcm + 2) * c.tone_stride + c.tone_nb);
+    }
+    if (e->opt_force_exact) { ybuf_max = chunk_len_max + 8; head_cap_max = chunk_len_max / 4 + 64; }
+    // segment length of the continuous pass: enough threads to fill the GPU, little warm-up waste
+    int64_t L = e->opt_segment_len;
+    if (L <= 0) {
+        L = 32768;
+        while (L > 2048 && total / L < 262144) L >>= 1;
+        while (L < 2 * (int64_t)warm_max) L <<= 1;
+    }
+    AxWave& w = b->w;
+    w.n_drops = n_drops; w.n_cfg = (int)e->cfgs.size(); w.cfg = e->d_cfg;
+    w.seg_len = (int32_t)L; w.seg_cap = (int32_t)(L / 8 + 32);
+    w.guard = e->opt_guard; w.tone_direct = e->opt_tone_direct; w.force_exact = e->opt_force_exact;
+    w.head_zc_cap_max = head_cap_max; w.ybuf_len_max = ybuf_max; w.blk_stride = blk_max;
+    b->drops.resize(n_drops);
+    int64_t pcm_off = 0, zc_off = 0, edge_off = 0;
+    int32_t seg_off = 0, slab_off = 0, tile_off = 0, chunk_off = 0, pw_off = 0, frame_off = 0;
+    for (int d = 0; d < n_drops; ++d) {
+        const AxCfg& c = e->cfgs[config_id[d]];
+        AxDrop& dr = b->drops[d];
+        const int64_t n = n_samples[d];
+        dr.pcm_off = pcm_off; dr.n = n; dr.cfg = config_id[d];
+        pcm_off += ((n + 63) / 64) * 64 + 64;
+        dr.seg_base = seg_off; dr.nseg = (int32_t)((n + L - 1) / L); seg_off += dr.nseg;
+        dr.slab_base = slab_off; dr.nslab = (int32_t)((n + AX_STAT_SLAB - 1) / AX_STAT_SLAB); slab_off += dr.nslab;
+        dr.zc_base = zc_off; dr.zc_cap = n / e->opt_zc_div + 4096; zc_off += dr.zc_cap + 8;
+        dr.tile_base = tile_off; dr.tile_cap = (int32_t)(dr.zc_cap / AX_TILE + 1); tile_off += dr.tile_cap;
+        dr.chunk_base = chunk_off; dr.chunk_cap = (int32_t)(2 * (n / c.chunk_len) + 16); chunk_off += dr.chunk_cap;
+        dr.edge_base = edge_off; dr.edge_cap = n / 24 + 8 * (int64_t)dr.chunk_cap; edge_off += dr.edge_cap + 64;
+        dr.pw_base = pw_off; dr.pw_cap = (int32_t)(n / c.d_pcm + 2 * (int64_t)dr.chunk_cap + 8); pw_off += dr.pw_cap;
+        dr.frame_base = frame_off; dr.frame_cap = (int32_t)(dr.edge_cap / 32 + 64); frame_off += dr.frame_cap;
+    }
+    b->pcm_total = pcm_off; b->zc_total = zc_off; b->tile_total = tile_off; b->chunk_total = chunk_off;
+    b->edge_total = edge_off; b->frame_total = frame_off;
+    w.nseg_total = seg_off; w.nslab_total = slab_off; w.pw_total = pw_off;
+    std::vector<int32_t> seg_drop(seg_off), slab_drop(slab_off);
+    for (int d = 0; d < n_drops; ++d) {
+        for (int s = 0; s < b->drops[d].nseg; ++s) seg_drop[b->drops[d].seg_base + s] = d;
+        for (int s = 0; s < b->drops[d].nslab; ++s) slab_drop[b->drops[d].slab_base + s] = d;
+    }
+    int bad = 0;
+    AxDrop* d_drop; int32_t* d_seg_drop; int32_t* d_slab_drop; AxState* d_st;
+    bad |= ax_alloc_arr(b, &d_drop, n_drops);
+    bad |= ax_alloc_arr(b, &d_st, n_drops);
+    bad |= ax_alloc_arr(b, &b->d_pcm, pcm_off + 64);
+    bad |= ax_alloc_arr(b, &d_seg_drop, seg_off);
+    bad |= ax_alloc_arr(b, &d_slab_drop, slab_off);
+    bad |= ax_alloc_arr(b, &w.seg_cnt, seg_off);
+    bad |= ax_alloc_arr(b, &w.seg_off, seg_off);
+    const int64_t rec_total = (int64_t)seg_off * w.seg_cap;
+    bad |= ax_alloc_arr(b, &w.rec_idx, rec_total);
+    bad |= ax_alloc_arr(b, &w.rec_a1, rec_total);
+    bad |= ax_alloc_arr(b, &w.rec_a2, rec_total);
+    bad |= ax_alloc_arr(b, &w.zc_idx, zc_off);
+    bad |= ax_alloc_arr(b, &w.zc_a1, zc_off);
+    bad |= ax_alloc_arr(b, &w.zc_a2, zc_off);
+    bad |= ax_alloc_arr(b, &w.tile_tab, (int64_t)tile_off * 4);
+    bad |= ax_alloc_arr(b, &w.chunk, chunk_off);
+    bad |= ax_alloc_arr(b, &w.head_idx, (int64_t)chunk_off * head_cap_max);
+    bad |= ax_alloc_arr(b, &w.head_a1, (int64_t)chunk_off * head_cap_max);
+    bad |= ax_alloc_arr(b, &w.head_a2, (int64_t)chunk_off * head_cap_max);
+    bad |= ax_alloc_arr(b, &w.ybuf, (int64_t)chunk_off * ybuf_max);
+    bad |= ax_alloc_arr(b, &w.pw_raw, 3 * (int64_t)pw_off);
+    bad |= ax_alloc_arr(b, &w.pw_sm, 3 * (int64_t)pw_off);
+    bad |= ax_alloc_arr(b, &w.r400, pw_off);
+    bad |= ax_alloc_arr(b, &w.r7500, pw_off);
+    bad |= ax_alloc_arr(b, &w.pw_ind, pw_off);
+    bad |= ax_alloc_arr(b, &w.blk, (int64_t)chunk_off * w.blk_stride * 6);
+    bad |= ax_alloc_arr(b, &w.edge_idx, edge_off);
+    bad |= ax_alloc_arr(b, &w.lvl400, edge_off);
+    bad |= ax_alloc_arr(b, &w.lvl7500, edge_off);
+    bad |= ax_alloc_arr(b, &w.bit, edge_off);
+    bad |= ax_alloc_arr(b, &w.a1, edge_off);
+    bad |= ax_alloc_arr(b, &w.a2, edge_off);
+    bad |= ax_alloc_arr(b, &w.conf, edge_off);
+    bad |= ax_alloc_arr(b, &w.frame, frame_off);
+    bad |= ax_alloc_arr(b, &b->d_qc, 2 * (int64_t)frame_off + 16);
+    bad |= ax_alloc_arr(b, &w.flags, 8);
+    if (bad) { axctd_batch_destroy(b); return AXCTD_ERR_CUDA; }
+    w.drop = d_drop; w.st = d_st; w.pcm = b->d_pcm; w.seg_drop = d_seg_drop; w.slab_drop = d_slab_drop;
+    bad |= ax_h2d(e, d_drop, b->drops.data(), sizeof(AxDrop) * n_drops);
+    bad |= ax_h2d(e, d_seg_drop, seg_drop.data(), sizeof(int32_t) * seg_off);
+    bad |= ax_h2d(e, d_slab_drop, slab_drop.data(), sizeof(int32_t) * slab_off);
+    bad |= ax_zero(e, b->d_pcm, sizeof(int16_t) * (pcm_off + 64));
+    bad |= ax_sync(e);
+    if (bad) { axctd_batch_destroy(b); return AXCTD_ERR_CUDA; }
+    b->st.resize(n_drops);
+    b->summary.resize(n_drops);
+    *out = b;
+    return AXCTD_OK;
+}
+
+extern "C" int axctd_batch_upload(axctd_batch* b, int drop, const int16_t* pcm, int64_t n) {
+    if (!b || drop < 0 || drop >= b->n || !pcm || n != b->drops[drop].n) return AXCTD_ERR_ARG;
+    if (ax_h2d(b->eng, b->d_pcm + b->drops[drop].pcm_off, pcm, sizeof(int16_t) * n)) return AXCTD_ERR_CUDA;
+    b->ran = false;
+    return AXCTD_OK;
+}
+
+extern "C" int axctd_batch_device_pcm(axctd_batch* b, int drop, void** dptr) {
+    if (!b || drop < 0 || drop >= b->n || !dptr) return AXCTD_ERR_ARG;
+    *dptr = (void*)(b->d_pcm + b->drops[drop].pcm_off);
+    return AXCTD_OK;
+}
+
+// ---- header text -> coefficients, metadata merge (host, python float semantics)
+// parse.py:277-278: int(chex[:9])/1E7 * 10**int(chex[9:]) with B->'+', D->'-'
+static bool ax_py_int(const char* s, int len, long long* out) {
+    int i = 0; int sign = 1;
+    if (i < len && (s[i] == '+' || s[i] == '-')) { if (s[i] == '-') sign = -1; ++i; }
+    if (i >= len) return false;
+    long long v = 0;
+    for (; i < len; ++i) { if (s[i] < '0' || s[i] > '9') return false; v = v * 10 + (s[i] - '0'); }
+    *out = sign * v;
+    return true;
+}
+static bool ax_coeff_from_frames(const uint16_t* f3, double* out) {
+    char hex[13];
+    snprintf(hex, sizeof(hex), "%04X%04X%04X", f3[0], f3[1], f3[2]);
+    for (int i = 0; i < 12; ++i) { if (hex[i] == 'B') hex[i] = '+'; else if (hex[i] == 'D') hex[i] = '-'; }
+    long long mant, ex;
+    if (!ax_py_int(hex, 9, &mant) || !ax_py_int(hex + 9, 3, &ex)) return false;
+    const double a = (double)mant / 1e7;
+    double p;
+    if (ex >= 0) { char buf[16]; snprintf(buf, sizeof(buf), "1e%lld", ex); p = strtod(buf, nullptr); }   // python int 10**ex -> float
+    else p = pow(10.0, (double)ex);                                                                    // python float pow
+    *out = a * p;
+    return true;
+}
+
+static void ax_merge_headers(const AxCfg& c, AxState& st, axctd_drop_summary& sm) {
+    // parse.py:187-192 defaults, then AXCTDprocessor.py:505-535
+    const double zd[4] = {1, 1, 1, 1}, td[4] = {0, 1, 0, 0};
+    for (int q = 0; q < 4; ++q) {
+        sm.zcoeff[q] = zd[q]; sm.tcoeff[q] = td[q]; sm.ccoeff[q] = td[q];
+        sm.zcoeff_valid[q] = sm.tcoeff_valid[q] = sm.ccoeff_valid[q] = 0;
+        st.zc_used[q] = c.zc[q]; st.tc_used[q] = c.tc[q]; st.cc_used[q] = c.cc[q];
+    }
+    bool any = false;
+    for (int slot = 0; slot < 2; ++slot) {
+        if (!st.header_parsed[slot]) continue;
+        any = true;
+        const uint8_t* cf = st.counter_found[slot];
+        const uint16_t* fd = st.frame_data[slot];
+        struct { int top; double* co; int32_t* va; } sets[3] = {
+            {33, sm.tcoeff, sm.tcoeff_valid}, {45, sm.ccoeff, sm.ccoeff_valid}, {21, sm.zcoeff, sm.zcoeff_valid}};
+        for (auto& S : sets) {
+            for (int i = 0; i < 4; ++i) {
+                const int f0 = S.top - 3 * i;                      // parse.py:258-270
+                if (cf[f0] && cf[f0 + 1] && cf[f0 + 2]) {
+                    double v;
+                    if (!ax_coeff_from_frames(fd + f0, &v)) { ax_raise(st, AXCTD_DROP_HEADER_VALUE, st.header_chunk[1 + slot]); return; }
+                    S.co[i] = v; S.va[i] = 1;
+                }
+            }
+        }
+    }
+    if (any) {                                                     // AXCTDprocessor.py:529-535
+        const int tv = sm.tcoeff_valid[0] + sm.tcoeff_valid[1] + sm.tcoeff_valid[2] + sm.tcoeff_valid[3];
+        const int cv = sm.ccoeff_valid[0] + sm.ccoeff_valid[1] + sm.ccoeff_valid[2] + sm.ccoeff_valid[3];
+        if (tv == 4) for (int q = 0; q < 4; ++q) st.tc_used[q] = sm.tcoeff[q];
+        if (cv == 4) for (int q = 0; q < 4; ++q) st.cc_used[q] = sm.ccoeff[q];
+        if (tv == 4) for (int q = 0; q < 4; ++q) st.zc_used[q] = sm.zcoeff[q];      // (sic) guarded by the T flag
+    }
+}
+
+#ifndef AXCTD_EMU
+#define AX_EVENT(b, i) cudaEventRecord((b)->ev[i], (b)->eng->stream)
+#else
+#define AX_EVENT(b, i) ((void)0)
+#endif
+
+static int ax_run_tones(axctd_batch* b, int phase_b) {
+    axctd_engine* e = b->eng;
+    AxWave& w = b->w;
+#ifndef AXCTD_EMU
+    if (!e->opt_tone_direct) {
+        bool all_blocked = true;
+        for (size_t ci = 0; ci < e->cfgs.size(); ++ci) {
+            const AxCfg& c = e->cfgs[ci];
+            const bool used = std::any_of(b->drops.begin(), b->drops.end(), [&](const AxDrop& d) { return d.cfg == (int)ci; });
+            if (!used) continue;
+            if (!ax_tone_blocked_ok(c)) { all_blocked = false; continue; }
+            ax_launch_tone_blocked(w, (int)ci, c, phase_b, (int)b->chunk_total, e->stream);
+            e->launches += 2;
+        }
+        if (all_blocked) return 0;
+        AX_LAUNCH(e, k_tone_direct, (int64_t)w.pw_total, w, phase_b + 2);   // only configs the blocked path skipped
+        return 0;
+    }
+#endif
+    AX_LAUNCH(e, k_tone_direct, (int64_t)w.pw_total, w, phase_b);
+    return 0;
+}
+
+extern "C" int axctd_batch_run_async(axctd_batch* b) {
+    if (!b) return AXCTD_ERR_ARG;
+    axctd_engine* e = b->eng;
+    AxWave& w = b->w;
+    const int n = b->n;
+#ifndef AXCTD_EMU
+    cudaSetDevice(e->device);
+#endif
+    b->finished = false;
+    AX_EVENT(b, 0);
+    if (ax_zero(e, w.flags, sizeof(int32_t) * 8)) return AXCTD_ERR_CUDA;
+    AX_LAUNCH(e, k_init, n, w);
+#ifndef AXCTD_EMU
+    ax_launch_stats(w, e->stream); e->launches++;
+#else
+    AX_LAUNCH(e, k_stats, (int64_t)w.nslab_total, w);
+#endif
+    AX_LAUNCH(e, k_stats_fin, n, w);
+    AX_EVENT(b, 1);
+    AX_LAUNCH(e, k_filter, (int64_t)w.nseg_total, w);
+    AX_EVENT(b, 2);
+    AX_LAUNCH(e, k_scan, n, w);
+    AX_LAUNCH(e, k_compact, (int64_t)w.nseg_total, w);
+    AX_LAUNCH(e, k_tiles, b->tile_total * 4, w);
+    AX_LAUNCH(e, k_plan0, n, w);
+    AX_EVENT(b, 3);
+    ax_run_tones(b, 0);
+    AX_EVENT(b, 4);
+    AX_LAUNCH(e, k_sm, n, w, 0);
+    // chunk chain: predict, recompute heads exactly, verify; repeat while repairs happen
+    int32_t flags[8];
+    for (int it = 0;; ++it) {
+        AX_LAUNCH(e, k_chain, n, w);
+        if (e->opt_inject_misspec && it == 0) AX_LAUNCH(e, k_inject, n, w);
+        AX_LAUNCH(e, k_heads, b->chunk_total, w);
+        AX_LAUNCH(e, k_verify, n, w);
+        if (ax_d2h(e, flags, w.flags, sizeof(flags)) || ax_sync(e)) return AXCTD_ERR_CUDA;
+        if (!flags[AX_FLAG_DIRTY]) break;
+        if (it >= e->opt_max_fixups) { e->err = "chunk chain did not converge"; return AXCTD_ERR_STATE; }
+        if (ax_zero(e, w.flags, sizeof(int32_t))) return AXCTD_ERR_CUDA;
+    }
+    AX_LAUNCH(e, k_plan_tones, n, w);
+    ax_run_tones(b, 1);
+    AX_LAUNCH(e, k_sm, n, w, 1);
+    AX_LAUNCH(e, k_offsets, n, w);
+    AX_LAUNCH(e, k_emit, b->chunk_total, w);
+    AX_LAUNCH(e, k_scale, n, w);
+    AX_LAUNCH(e, k_bits, b->chunk_total, w);
+    AX_LAUNCH(e, k_headers, 2 * (int64_t)n, w);
+    // header text -> calibration coefficients on the host (python float semantics)
+    if (ax_d2h(e, b->st.data(), w.st, sizeof(AxState) * n) || ax_sync(e)) return AXCTD_ERR_CUDA;
+    for (int d = 0; d < n; ++d) ax_merge_headers(e->cfgs[b->drops[d].cfg], b->st[d], b->summary[d]);
+    if (ax_h2d(e, w.st, b->st.data(), sizeof(AxState) * n)) return AXCTD_ERR_CUDA;
+    AX_LAUNCH(e, k_frames, n, w);
+    AX_LAUNCH(e, k_calib, b->frame_total, w);
+    AX_LAUNCH(e, k_qc, b->chunk_total, w, b->d_qc);
+    AX_EVENT(b, 5);
+    b->ran = true;
+    return AXCTD_OK;
+}
+
+extern "C" int axctd_batch_finish(axctd_batch* b) {
+    if (!b || !b->ran) return AXCTD_ERR_STATE;
+    if (b->finished) return AXCTD_OK;
+    axctd_engine* e = b->eng;
+    AxWave& w = b->w;
+    const int n = b->n;
+    b->chunk.resize(b->chunk_total);
+    if (ax_d2h(e, b->st.data(), w.st, sizeof(AxState) * n) ||
+        ax_d2h(e, b->chunk.data(), w.chunk, sizeof(AxChunk) * b->chunk_total) || ax_sync(e)) return AXCTD_ERR_CUDA;
+    b->frame.resize(b->frame_total);
+    for (int d = 0; d < n; ++d) {
+        const AxDrop& dr = b->drops[d];
+        const int64_t nf = b->st[d].n_frames;
+        if (nf > 0 && ax_d2h(e, b->frame.data() + dr.frame_base, w.frame + dr.frame_base, sizeof(axctd_frame) * nf)) return AXCTD_ERR_CUDA;
+    }
+    if (ax_sync(e)) return AXCTD_ERR_CUDA;
+#ifndef AXCTD_EMU
+    float ms = 0;
+    cudaEventElapsedTime(&ms, b->ev[0], b->ev[5]); b->ms_total = ms;
+    cudaEventElapsedTime(&ms, b->ev[1], b->ev[2]); b->ms_filter = ms;
+    cudaEventElapsedTime(&ms, b->ev[3], b->ev[4]); b->ms_tone = ms;
+#endif
+    for (int d = 0; d < n; ++d) {
+        const AxDrop& dr = b->drops[d];
+        const AxCfg& c = e->cfgs[dr.cfg];
+        AxState& st = b->st[d];
+        axctd_drop_summary& sm = b->summary[d];
+        if (st.n_uncertain > 0 && st.status == 0) { st.status = AXCTD_DROP_UNCERTAIN; }
+        sm.status = st.status; sm.status_chunk = st.status_chunk;
+        sm.numpoints = dr.n; sm.f_s = c.fs;
+        sm.firstpulse400 = st.firstpulse400; sm.profstartind = st.profstartind;
+        sm.firstpointtime = st.firstpointtime; sm.mean7500pwr = st.mean7500; sm.high_bit_scale = st.scale;
+        sm.n_chunks = st.n_chunks; sm.first_demod_chunk = st.k0; sm.profile_chunk = st.k2;
+        for (int q = 0; q < 3; ++q) { sm.header_read[q] = st.header_read[q]; sm.header_chunk[q] = st.header_chunk[q]; }
+        sm.n_bits = st.nbits_total; sm.n_edges = st.nedges_total; sm.n_power = st.pcount;
+        sm.n_frames = st.n_frames; sm.n_crossings = st.zc_count;
+        sm.n_uncertain = st.n_uncertain; sm.n_chain_fixups = st.n_fixups;
+        sm.pcm_sum = st.sum; sm.pcm_ampl = st.ampl;
+        memcpy(sm.frame_data, st.frame_data, sizeof(sm.frame_data));
+        memcpy(sm.counter_found, st.counter_found, sizeof(sm.counter_found));
+        sm.header_parsed[0] = st.header_parsed[0]; sm.header_parsed[1] = st.header_parsed[1];
+        for (int q = 0; q < 4; ++q) { sm.zcoeff_used[q] = st.zc_used[q]; sm.tcoeff_used[q] = st.tc_used[q]; sm.ccoeff_used[q] = st.cc_used[q]; }
+        int64_t rows = 0, hex = 0;
+        for (int k = 0; k < st.n_chunks && k < dr.chunk_cap; ++k) { rows += b->chunk[dr.chunk_base + k].n_rows; hex += b->chunk[dr.chunk_base + k].n_hex; }
+        sm.n_rows = rows; sm.n_hex = hex;
+    }
+    b->finished = true;
+    return AXCTD_OK;
+}
+
+extern "C" int axctd_batch_run(axctd_batch* b) {
+    int r = axctd_batch_run_async(b);
+    if (r) return r;
+    return axctd_batch_finish(b);
+}
+
+extern "C" int axctd_batch_timing(axctd_batch* b, double* total_ms, double* filter_ms, double* tone_ms) {
+    if (!b || !b->finished) return AXCTD_ERR_STATE;
+    if (total_ms) *total_ms = b->ms_total;
+    if (filter_ms) *filter_ms = b->ms_filter;
+    if (tone_ms) *tone_ms = b->ms_tone;
+    return AXCTD_OK;
+}
+
+extern "C" int axctd_batch_summary(axctd_batch* b, int drop, axctd_drop_summary* out) {
+    if (!b || !b->finished || drop < 0 || drop >= b->n || !out) return AXCTD_ERR_ARG;
+    *out = b->summary[drop];
+    return AXCTD_OK;
+}
+
+extern "C" int64_t axctd_batch_frames(axctd_batch* b, int drop, axctd_frame* out, int64_t cap) {
+    if (!b || !b->finished || drop < 0 || drop >= b->n) return -AXCTD_ERR_ARG;
+    const int64_t nf = b->st[drop].n_frames;
+    if (!out) return nf;
+    if (cap < nf) return -AXCTD_ERR_CAPACITY;
+    if (nf) memcpy(out, b->frame.data() + b->drops[drop].frame_base, sizeof(axctd_frame) * nf);
+    return nf;
+}
+
+extern "C" int64_t axctd_batch_chunks(axctd_batch* b, int drop, axctd_chunk* out, int64_t cap) {
+    if (!b || !b->finished || drop < 0 || drop >= b->n) return -AXCTD_ERR_ARG;
+    const AxState& st = b->st[drop];
+    const AxDrop& dr = b->drops[drop];
+    const int64_t nc = std::min<int64_t>(st.n_chunks, dr.chunk_cap);
+    if (!out) return nc;
+    if (cap < nc) return -AXCTD_ERR_CAPACITY;
+    for (int k = 0; k < nc; ++k) {
+        const AxChunk& c = b->chunk[dr.chunk_base + k];
+        axctd_chunk& o = out[k];
+        o.s = c.s; o.e = c.e; o.status = c.status; o.n_power_total = c.pw_off + c.np;
+        const bool dem = st.k0 >= 0 && k >= st.k0 && c.n_edges > 0;
+        o.n_bits = dem ? c.n_edges - 1 : -1;
+        o.first_edge = dem ? (int32_t)(c.first_edge - c.s) : -1; o.last_edge = dem ? (int32_t)(c.true_last - c.s) : -1;
+        o.n_head_edges = dem ? c.n_head_edges : 0;
+        o.n_rows = c.n_rows; o.n_hex = c.n_hex; o.scale = c.scale;
+    }
+    return nc;
+}
+
+extern "C" int64_t axctd_batch_bits(axctd_batch* b, int drop, uint8_t* bits, double* conf, int64_t cap) {
+    if (!b || !b->finished || drop < 0 || drop >= b->n) return -AXCTD_ERR_ARG;
+    const int64_t nb = b->st[drop].nbits_total;
+    if (!bits && !conf) return nb;
+    if (cap < nb) return -AXCTD_ERR_CAPACITY;
+    const int64_t base = b->drops[drop].edge_base;
+    // bits of chunk k sit at bit_off[k]: contiguous over the drop
+    if (bits && nb && ax_d2h(b->eng, bits, b->w.bit + base, (size_t)nb)) return -AXCTD_ERR_CUDA;
+    if (conf && nb && ax_d2h(b->eng, conf, b->w.conf + base, sizeof(double) * nb)) return -AXCTD_ERR_CUDA;
+    if (ax_sync(b->eng)) return -AXCTD_ERR_CUDA;
+    return nb;
+}
+
+extern "C" int64_t axctd_batch_edges(axctd_batch* b, int drop, int64_t* edges, double* r400, double* r7500, int64_t cap) {
+    if (!b || !b->finished || drop < 0 || drop >= b->n) return -AXCTD_ERR_ARG;
+    const int64_t ne = b->st[drop].nedges_total;
+    if (!edges && !r400 && !r7500) return ne;
+    if (cap < ne) return -AXCTD_ERR_CAPACITY;
+    const int64_t base = b->drops[drop].edge_base;
+    if (edges && ne) {
+        std::vector<int32_t> tmp(ne);
+        if (ax_d2h(b->eng, tmp.data(), b->w.edge_idx + base, sizeof(int32_t) * ne) || ax_sync(b->eng)) return -AXCTD_ERR_CUDA;
+        for (int64_t i = 0; i < ne; ++i) edges[i] = tmp[i];
+    }
+    if (r400 && ne && ax_d2h(b->eng, r400, b->w.lvl400 + base, sizeof(double) * ne)) return -AXCTD_ERR_CUDA;
+    if (r7500 && ne && ax_d2h(b->eng, r7500, b->w.lvl7500 + base, sizeof(double) * ne)) return -AXCTD_ERR_CUDA;
+    if (ax_sync(b->eng)) return -AXCTD_ERR_CUDA;
+    return ne;
+}
+
+extern "C" int64_t axctd_batch_power(axctd_batch* b, int drop, int64_t* power_inds, double* r400, double* r7500, int64_t cap) {
+    if (!b || !b->finished || drop < 0 || drop >= b->n) return -AXCTD_ERR_ARG;
+    const int64_t np = b->st[drop].pcount;
+    if (!power_inds && !r400 && !r7500) return np;
+    if (cap < np) return -AXCTD_ERR_CAPACITY;
+    const int64_t base = b->drops[drop].pw_base;
+    if (power_inds && np && ax_d2h(b->eng, power_inds, b->w.pw_ind + base, sizeof(int64_t) * np)) return -AXCTD_ERR_CUDA;
+    if (r400 && np && ax_d2h(b->eng, r400, b->w.r400 + base, sizeof(double) * np)) return -AXCTD_ERR_CUDA;
+    if (r7500 && np && ax_d2h(b->eng, r7500, b->w.r7500 + base, sizeof(double) * np)) return -AXCTD_ERR_CUDA;
+    if (ax_sync(b->eng)) return -AXCTD_ERR_CUDA;
+    return np;
+}

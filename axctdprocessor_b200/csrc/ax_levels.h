@@ -1,0 +1,350 @@
+// ax_levels.h -- tone powers, detection state machine, bit assembly.
+//
+//   ax_plan0_item      fixed chunk grid while status == 0            AXCTDprocessor.py:293-304, 332-333
+//   ax_plan_tones_item power_inds of the demodulated chunks          AXCTDprocessor.py:357
+//   ax_tone_direct     |sum x e^{j theta m}| at 400/7500/dead Hz     AXCTDprocessor.py:358-364
+//   ax_sm_item         smoothing, log ratios, pulse / tone detection AXCTDprocessor.py:367-408, demodulate.py:39-48
+//   ax_emit_item       bit edges, per-edge signal levels             AXCTDprocessor.py:413-429
+//   ax_scale_item      mark/space scale calibration                  AXCTDprocessor.py:459-468, demodulate.py:124-157
+//   ax_bits_item       bit decisions and confidence                  demodulate.py:109-114
+#pragma once
+#include "ax_dsp.h"
+
+AX_HD int32_t ax_grid_count(int64_t s, int64_t e, const AxCfg& c) {
+    const int64_t span = e - c.n_power - s;              // len(range(s, e - N_power, d_pcm))
+    return span > 0 ? (int32_t)((span + c.d_pcm - 1) / c.d_pcm) : 0;
+}
+
+AX_HDN inline void ax_plan0_item(const AxWave& w, int64_t d) {
+    const AxDrop& dr = w.drop[d];
+    const AxCfg& c = w.cfg[dr.cfg];
+    AxState& st = w.st[d];
+    AxChunk* ch = w.chunk + dr.chunk_base;
+    int k = 0;
+    int64_t s = 0;
+    int32_t pc = 0;
+    while (true) {
+        if (dr.n - s < 4 * (int64_t)c.n_power) break;
+        if (k >= dr.chunk_cap) { ax_raise(st, AXCTD_DROP_CAPACITY, k); w.flags[AX_FLAG_CAP] = 1; break; }
+        int64_t e = s + c.chunk_len;
+        if (e >= dr.n) e = dr.n - 1;
+        AxChunk& q = ch[k];
+        q.s = s; q.e = e; q.pw_off = pc; q.np = ax_grid_count(s, e, c);
+        q.n_edges = 0; q.n_head_edges = 0; q.err = 0; q.status = 0; q.n_rows = 0; q.n_hex = 0;
+        q.frame_begin = q.frame_end = 0; q.scale = c.scale0; q.mean7500 = ax_nan();
+        q.spec_last = q.true_last = -1; q.g_first = -1; q.q_last = -1; q.bit_off = q.edge_off = 0; q.first_edge = -1;
+        if (pc + q.np > dr.pw_cap) { ax_raise(st, AXCTD_DROP_CAPACITY, k); w.flags[AX_FLAG_CAP] = 1; break; }
+        for (int j = 0; j < q.np; ++j) w.pw_ind[dr.pw_base + pc + j] = s + (int64_t)j * c.d_pcm;
+        pc += q.np;
+        ++k;
+        s = e;
+    }
+    st.n_fixed = k;
+    st.n_chunks = k;
+}
+
+// After the chain is final: power grid of the chunks after the first demodulated one.
+AX_HDN inline void ax_plan_tones_item(const AxWave& w, int64_t d) {
+    const AxDrop& dr = w.drop[d];
+    AxState& st = w.st[d];
+    if (st.sm_status < 1) return;
+    const AxCfg& c = w.cfg[dr.cfg];
+    AxChunk* ch = w.chunk + dr.chunk_base;
+    int32_t pc = ch[st.k0].pw_off + ch[st.k0].np;
+    for (int k = st.k0 + 1; k < st.n_chunks; ++k) {
+        AxChunk& q = ch[k];
+        q.pw_off = pc; q.np = ax_grid_count(q.s, q.e, c);
+        q.status = 0; q.n_rows = 0; q.n_hex = 0; q.frame_begin = q.frame_end = 0; q.scale = c.scale0; q.mean7500 = ax_nan();
+        if (pc + q.np > dr.pw_cap) { ax_raise(st, AXCTD_DROP_CAPACITY, k); w.flags[AX_FLAG_CAP] = 1; q.np = 0; st.n_chunks = k; break; }
+        for (int j = 0; j < q.np; ++j) w.pw_ind[dr.pw_base + pc + j] = q.s + (int64_t)j * c.d_pcm;
+        pc += q.np;
+    }
+}
+
+// One power sample, straightforward evaluation (generic path; the CUDA build
+// uses the blocked kernel in ax_engine.cu whenever gcd(N_power, d_pcm) allows).
+AX_HDN inline void ax_tone_direct_item(const AxWave& w, int64_t slot, int phase_flags) {
+    const int phase_b = phase_flags & 1;
+    const int d = ax_find_owner(w.drop, w.n_drops, &AxDrop::pw_base, slot);
+    const AxDrop& dr = w.drop[d];
+    const AxState& st = w.st[d];
+    const AxCfg& c = w.cfg[dr.cfg];
+    if ((phase_flags & 2) && ax_tone_blocked_ok(c)) return;      // already done by the blocked kernel
+    if (st.status >= AXCTD_DROP_CAPACITY) return;
+    const int32_t i = (int32_t)(slot - dr.pw_base);
+    const AxChunk* ch = w.chunk + dr.chunk_base;
+    int32_t lo, hi;
+    if (!phase_b) { lo = 0; hi = st.n_fixed > 0 ? ch[st.n_fixed - 1].pw_off + ch[st.n_fixed - 1].np : 0; }
+    else {
+        if (st.sm_status < 1 || st.n_chunks <= st.k0 + 1) return;
+        lo = ch[st.k0].pw_off + ch[st.k0].np; hi = ch[st.n_chunks - 1].pw_off + ch[st.n_chunks - 1].np;
+    }
+    if (i < lo || i >= hi) return;
+    const int16_t* x = w.pcm + dr.pcm_off + w.pw_ind[slot];
+    const double kmul = st.inv_ampl, kadd = -(st.dc * st.inv_ampl);
+    double a[6] = {0, 0, 0, 0, 0, 0};
+    for (int m = 0; m < c.n_power; ++m) {
+        const double u = ax_fma((double)x[m], kmul, kadd);
+        const double* t6 = c.tone_cs + 6 * (int64_t)m;
+        for (int q = 0; q < 6; ++q) a[q] = ax_fma(u, t6[q], a[q]);
+    }
+    w.pw_raw[0 * (int64_t)w.pw_total + slot] = hypot(a[0], a[1]);
+    w.pw_raw[1 * (int64_t)w.pw_total + slot] = hypot(a[2], a[3]);
+    w.pw_raw[2 * (int64_t)w.pw_total + slot] = hypot(a[4], a[5]);
+}
+
+// numpy's pairwise summation for a contiguous float64 vector of n <= 128
+// (np.sum inside np.nanmean, AXCTDprocessor.py:393)
+AX_HD double ax_np_sum_small(const double* a, int n) {
+    if (n < 8) { double r = 0.0; for (int i = 0; i < n; ++i) r = ax_add(r, a[i]); return r; }
+    double r[8];
+    for (int q = 0; q < 8; ++q) r[q] = a[q];
+    int i = 8;
+    for (; i < n - (n % 8); i += 8) for (int q = 0; q < 8; ++q) r[q] = ax_add(r[q], a[i + q]);
+    double res = ax_add(ax_add(ax_add(r[0], r[1]), ax_add(r[2], r[3])), ax_add(ax_add(r[4], r[5]), ax_add(r[6], r[7])));
+    for (; i < n; ++i) res = ax_add(res, a[i]);
+    return res;
+}
+
+// Sequential per-drop state machine over run() iterations.  phase 0: fixed grid
+// until the 400 Hz pulse is found; phase 1: the demodulated chunks.
+AX_HDN inline void ax_sm_item(const AxWave& w, int64_t d, int phase_b) {
+    const AxDrop& dr = w.drop[d];
+    const AxCfg& c = w.cfg[dr.cfg];
+    AxState& st = w.st[d];
+    if (st.status != 0 && !phase_b) return;
+    AxChunk* ch = w.chunk + dr.chunk_base;
+    const int64_t PT = w.pw_total;
+    double* raw[3]; double* sm[3];
+    for (int f = 0; f < 3; ++f) { raw[f] = w.pw_raw + f * PT + dr.pw_base; sm[f] = w.pw_sm + f * PT + dr.pw_base; }
+    double* r400 = w.r400 + dr.pw_base; double* r7500 = w.r7500 + dr.pw_base;
+    const int64_t* pind = w.pw_ind + dr.pw_base;
+    const int kend = phase_b ? st.n_chunks : st.n_fixed;
+    if (phase_b && st.sm_status < 1) return;
+    for (int k = st.next_sm_chunk; k < kend; ++k) {
+        AxChunk& q = ch[k];
+        const int pstart = q.pw_off, np = q.np;
+        // demodulate.py:39-48 called with startind = pstart (AXCTDprocessor.py:367-369)
+        for (int f = 0; f < 3; ++f) {
+            for (int i = pstart; i < pstart + np; ++i) {
+                const int lo = (i < 5) ? 0 : i - 5;
+                double tot = 0.0; int cnt = 0;
+                for (int jj = lo; jj <= i; ++jj) {
+                    const double v = (jj < pstart) ? sm[f][jj] : raw[f][jj];
+                    if (!isnan(v)) { tot = ax_add(tot, v); ++cnt; }
+                }
+                sm[f][i] = cnt ? ax_div(tot, (double)cnt) : ax_nan();
+            }
+        }
+        for (int i = pstart; i < pstart + np; ++i) {                    // :370-371
+            r400[i] = log10(ax_div(sm[0][i], sm[2][i]));
+            r7500[i] = log10(ax_div(sm[1][i], sm[2][i]));
+        }
+        st.pcount = pstart + np;
+        if (st.sm_status == 0) {                                        // :375-380
+            for (int i = pstart; i < pstart + np; ++i) {
+                if (r400[i] >= c.min_r400) { st.firstpulse400 = pind[i]; st.sm_status = 1; st.k0 = k; break; }
+            }
+        }
+        if (st.sm_status >= 1 && st.pcount > 0) {
+            const int64_t last_ind = pind[st.pcount - 1];
+            const int64_t fp = st.firstpulse400;
+            if (last_ind >= fp + c.off_5p5 && isnan(st.mean7500)) {     // :388-393
+                int s75 = 0, e75 = 0; int64_t b1 = 0, b2 = 0;
+                for (int jj = 0; jj < st.pcount; ++jj) {
+                    int64_t d1 = fp + c.off_4p5 - pind[jj]; if (d1 < 0) d1 = -d1;
+                    int64_t d2 = fp + c.off_5p5 - pind[jj]; if (d2 < 0) d2 = -d2;
+                    if (jj == 0 || d1 < b1) { b1 = d1; s75 = jj; }
+                    if (jj == 0 || d2 < b2) { b2 = d2; e75 = jj; }
+                }
+                double buf[128]; int nb = 0, cnt = 0;
+                for (int jj = s75; jj < e75 && nb < 128; ++jj) { const double v = r7500[jj]; if (isnan(v)) buf[nb++] = 0.0; else { buf[nb++] = v; ++cnt; } }
+                st.mean7500 = cnt ? ax_div(ax_np_sum_small(buf, nb), (double)cnt) : ax_nan();
+                st.km = k;
+            }
+            if (last_ind > fp + c.off_trig_from) {                      // :397-408
+                if (!isnan(st.mean7500) && st.sm_status == 1) {
+                    for (int i = pstart; i < pstart + np; ++i) {
+                        if (ax_sub(r7500[i], st.mean7500) >= c.min_dr7500) { st.profstartind = pind[i]; st.sm_status = 2; st.k2 = k; break; }
+                    }
+                } else if (c.trig_to > 0 && last_ind >= fp + c.off_trig_to) {
+                    st.profstartind = fp + c.off_trig_to;
+                    if (st.sm_status != 2) st.k2 = k;
+                    st.sm_status = 2;
+                }
+                if (st.profstartind > 0 && st.firstpointtime <= 0) st.firstpointtime = ax_div((double)st.profstartind, c.fs);
+            }
+        }
+        q.mean7500 = st.mean7500;
+        q.status = st.sm_status;
+        st.next_sm_chunk = k + 1;
+        if (!phase_b && st.sm_status >= 1) break;      // hand over to the chunk chain
+    }
+    if (!phase_b) {
+        if (st.sm_status >= 1) { st.chain_from = st.k0; st.chain_end = 0; }
+        else { st.n_chunks = st.n_fixed; st.chain_end = 1; }
+    }
+}
+
+// bit / edge array offsets of every demodulated chunk
+AX_HDN inline void ax_offsets_item(const AxWave& w, int64_t d) {
+    const AxDrop& dr = w.drop[d];
+    AxState& st = w.st[d];
+    st.nbits_total = 0; st.nedges_total = 0;
+    if (st.sm_status < 1) return;
+    AxChunk* ch = w.chunk + dr.chunk_base;
+    int64_t nb = 0, ne = 0;
+    for (int k = st.k0; k < st.n_chunks; ++k) {
+        ch[k].bit_off = nb; ch[k].edge_off = ne;
+        if (ch[k].n_edges > 0) { nb += ch[k].n_edges - 1; ne += ch[k].n_edges; }
+    }
+    if (ne > dr.edge_cap) { ax_raise(st, AXCTD_DROP_CAPACITY, -1); w.flags[AX_FLAG_CAP] = 1; nb = 0; ne = 0; }
+    st.nbits_total = nb; st.nedges_total = ne;
+}
+
+// AXCTDprocessor.py:413-429: bit edges of one chunk and the signal level of the
+// nearest power sample of THIS chunk for every edge.
+AX_HDN inline void ax_emit_item(const AxWave& w, int64_t cg) {
+    const int d = ax_find_owner(w.drop, w.n_drops, &AxDrop::chunk_base, cg);
+    const AxDrop& dr = w.drop[d];
+    AxState& st = w.st[d];
+    const int k = (int)(cg - dr.chunk_base);
+    if (st.sm_status < 1 || k < st.k0 || k >= st.n_chunks || st.nedges_total == 0) return;
+    AxChunk& ch = w.chunk[cg];
+    if (ch.n_edges <= 0) return;
+    const AxCfg& c = w.cfg[dr.cfg];
+    const int32_t* zi = w.zc_idx + dr.zc_base;
+    const double* za1 = w.zc_a1 + dr.zc_base; const double* za2 = w.zc_a2 + dr.zc_base;
+    const int32_t* hz = w.head_idx + cg * (int64_t)w.head_zc_cap_max;
+    const double* ha1 = w.head_a1 + cg * (int64_t)w.head_zc_cap_max;
+    const double* ha2 = w.head_a2 + cg * (int64_t)w.head_zc_cap_max;
+    int32_t* eidx = w.edge_idx + dr.edge_base + ch.edge_off;
+    double* l400 = w.lvl400 + dr.edge_base + ch.edge_off;
+    double* l7500 = w.lvl7500 + dr.edge_base + ch.edge_off;
+    double* a1 = w.a1 + dr.edge_base + ch.bit_off;
+    double* a2 = w.a2 + dr.edge_base + ch.bit_off;
+    const double* r400 = w.r400 + dr.pw_base + ch.pw_off;
+    const double* r7500 = w.r7500 + dr.pw_base + ch.pw_off;
+    const int64_t br2 = 2 * (int64_t)c.bitrate;
+    int64_t pos = ch.g_first;
+    for (int t = 0; t < ch.n_edges; ++t) {
+        int64_t idx; double v1, v2;
+        if (t < ch.n_head_edges) { idx = ch.s + hz[t]; v1 = ha1[t]; v2 = ha2[t]; }
+        else {
+            idx = zi[pos]; v1 = za1[pos]; v2 = za2[pos];
+            if (t < ch.n_edges - 1) {
+                if (idx + c.inset + c.npcm > ch.e) ax_raise(st, AXCTD_DROP_SHORT_WINDOW, k);   // demodulate.py:100-101
+                pos = ax_next(zi, pos, c.fs2, br2);
+            }
+        }
+        eidx[t] = (int32_t)idx;
+        if (t < ch.n_edges - 1) { a1[t] = v1; a2[t] = v2; }
+        // np.argmin(np.abs(recent_pwrinds - ci)): nearest grid point, first on ties (:425,:428)
+        if (ch.np > 0) {
+            const int64_t off = idx - ch.s;
+            int64_t jj = off / c.d_pcm;
+            const int64_t rem = off - jj * c.d_pcm;
+            if (2 * rem > c.d_pcm) ++jj;
+            if (jj > ch.np - 1) jj = ch.np - 1;
+            if (jj < 0) jj = 0;
+            l400[t] = r400[jj];
+            l7500[t] = ax_sub(r7500[jj], ch.mean7500);
+        } else { l400[t] = ax_nan(); l7500[t] = ax_nan(); }
+    }
+}
+
+// first index j in [0,n) with I[j] >= v (-1 if none); last index with I[j] <= v (-1 if none).
+// I is only piecewise sorted (chunk joins overlap by a sample or two), so scan.
+AX_HD int64_t ax_first_ge(const int32_t* I, int64_t n, int64_t v) {
+    int64_t lo = ax_lower_bound(I, n, v);       // good guess; then make it exact
+    int64_t j = lo - 64; if (j < 0) j = 0;
+    for (; j < n; ++j) if ((int64_t)I[j] >= v) return j;
+    return -1;
+}
+AX_HD int64_t ax_last_le(const int32_t* I, int64_t n, int64_t v) {
+    int64_t hi = ax_upper_bound(I, n, v) + 64;
+    if (hi > n) hi = n;
+    for (int64_t j = hi - 1; j >= 0; --j) if ((int64_t)I[j] <= v) return j;
+    return -1;
+}
+AX_HD int64_t ax_first_gt(const int32_t* I, int64_t from, int64_t n, int64_t v) {
+    for (int64_t j = from; j < n; ++j) if ((int64_t)I[j] > v) return j;
+    return -1;
+}
+
+// AXCTDprocessor.py:459-468 + demodulate.py:124-157
+AX_HDN inline void ax_scale_item(const AxWave& w, int64_t d) {
+    const AxDrop& dr = w.drop[d];
+    const AxCfg& c = w.cfg[dr.cfg];
+    AxState& st = w.st[d];
+    st.scale = c.scale0; st.k1 = -1; st.header_read[0] = 0; st.header_chunk[0] = -1;
+    if (st.sm_status < 1 || st.nedges_total == 0) return;
+    AxChunk* ch = w.chunk + dr.chunk_base;
+    const int32_t* I = w.edge_idx + dr.edge_base;
+    const double* a1 = w.a1 + dr.edge_base; const double* a2 = w.a2 + dr.edge_base;
+    const int64_t firstbin = I[0];
+    const int64_t p1s = st.firstpulse400 + c.h1s, p1e = st.firstpulse400 + c.h1e;
+    const int klast = (st.k2 >= 0) ? st.k2 : st.n_chunks - 1;
+    for (int k = st.k0; k <= klast && k < st.n_chunks; ++k) {
+        if (ch[k].n_edges <= 0) continue;
+        const int64_t ni = ch[k].edge_off + ch[k].n_edges, nb = ch[k].bit_off + ch[k].n_edges - 1;
+        const int64_t lastbin = I[ni - 1];
+        if (!(firstbin <= p1s && lastbin >= p1e)) continue;
+        const int64_t a = ax_first_ge(I, ni, p1s - c.half), b = ax_last_le(I, ni, p1e + c.half);
+        if (a < 0 || b < 0) { ax_raise(st, AXCTD_DROP_TRIM_INDEX, k); return; }
+        int64_t hi = b < nb ? b : nb;
+        const int64_t npts = hi > a ? hi - a : 0;
+        const int nbins = c.n_hist_edges - 1;
+        int hist[512];
+        if (nbins > 512) { ax_raise(st, AXCTD_DROP_CAPACITY, k); return; }
+        for (int q = 0; q < nbins; ++q) hist[q] = 0;
+        const double* ed = c.hist_edges;
+        for (int64_t jj = a; jj < hi; ++jj) {
+            const double v = ax_div(ax_mul(a2[jj], c.scale0), a1[jj]);          // demodulate.py:102,110
+            if (!(v >= ed[0]) || v > ed[nbins]) continue;
+            int lo = 0, up = nbins + 1;                                          // first edge > v
+            while (lo < up) { int mid = (lo + up) >> 1; if (ed[mid] <= v) lo = mid + 1; else up = mid; }
+            int bin = lo - 1;
+            if (bin >= nbins) bin = nbins - 1;
+            hist[bin]++;
+        }
+        // cumulative percentage and centred slope, evaluated on the fly
+        double best = 0; int first = -1, last = -1;
+        int64_t cs = 0;
+        double cp[512];
+        for (int q = 0; q < nbins; ++q) { cs += hist[q]; cp[q] = ax_div((double)(100 * cs), (double)npts); }
+        const double* ctr = c.hist_centers;
+        for (int q = 0; q < nbins; ++q) {
+            if (!(cp[q] >= 30.0 && cp[q] <= 65.0)) continue;
+            double sl;
+            if (q == 0) sl = ax_div(ax_sub(cp[1], cp[0]), ax_sub(ctr[1], ctr[0]));
+            else if (q == nbins - 1) sl = ax_div(ax_sub(cp[q], cp[q - 1]), ax_sub(ctr[q], ctr[q - 1]));
+            else sl = ax_div(ax_sub(cp[q + 1], cp[q - 1]), ax_sub(ctr[q + 1], ctr[q - 1]));
+            if (first < 0 || sl < best) { best = sl; first = q; last = q; }
+            else if (sl == best) last = q;
+        }
+        if (first < 0) { ax_raise(st, AXCTD_DROP_SCALE_EMPTY, k); return; }
+        const double thr = ax_div(ax_add(ctr[first], ctr[last]), 2.0);
+        st.scale = ax_div(c.scale0, thr);
+        st.k1 = k; st.header_read[0] = 1; st.header_chunk[0] = k;
+        break;
+    }
+    for (int k = st.k0; k < st.n_chunks; ++k) ch[k].scale = (st.k1 >= 0 && k > st.k1) ? st.scale : c.scale0;
+}
+
+// demodulate.py:102,109-114
+AX_HDN inline void ax_bits_item(const AxWave& w, int64_t cg) {
+    const int d = ax_find_owner(w.drop, w.n_drops, &AxDrop::chunk_base, cg);
+    const AxDrop& dr = w.drop[d];
+    const AxState& st = w.st[d];
+    const int k = (int)(cg - dr.chunk_base);
+    if (st.sm_status < 1 || k < st.k0 || k >= st.n_chunks || st.nedges_total == 0) return;
+    const AxChunk& ch = w.chunk[cg];
+    const int64_t base = dr.edge_base + ch.bit_off;
+    for (int t = 0; t < ch.n_edges - 1; ++t) {
+        const double p1 = w.a1[base + t];
+        const double p2 = ax_mul(w.a2[base + t], ch.scale);
+        w.conf[base + t] = ax_div(p2, p1);
+        w.bit[base + t] = (p1 >= p2) ? 1 : 0;
+    }
+}

@@ -1,0 +1,269 @@
+// ax_proto.h -- protocol layer: header decode, frame sync + CRC, calibration, QC.
+//
+//   ax_header_item   header windows, trim_header, parse_header   AXCTDprocessor.py:472-501, parse.py:157-183, 197-245
+//   ax_frames_item   profile trim + greedy frame sync + CRC       AXCTDprocessor.py:540-557, 617-621, parse.py:41-92, 310-322
+//   ax_calib_item    LUT, C*60/4096, cubics, PSS-78, rounding, QC AXCTDprocessor.py:559-574, parse.py:103-134, 297-301
+//   ax_qc_item       per-iteration spike filter                   AXCTDprocessor.py:576-613
+#pragma once
+#include "ax_levels.h"
+
+// parse.py:310-322: remainder of the 32-bit word modulo x^6+x^5+x^2+1 is zero
+AX_HD bool ax_crc_ok(uint32_t wd) {
+#pragma unroll
+    for (int k = 0; k < 26; ++k) if (wd & (0x80000000u >> k)) wd ^= (0x65u << (25 - k));
+    return wd == 0;
+}
+
+AX_HD uint32_t ax_word32(const uint8_t* b) {
+    uint32_t wd = 0;
+    for (int i = 0; i < 32; ++i) wd = (wd << 1) | (b[i] ? 1u : 0u);
+    return wd;
+}
+
+// One header slot (0 = second transmission, 1 = third) of one drop.
+AX_HDN inline void ax_header_item(const AxWave& w, int64_t item) {
+    const int d = (int)(item >> 1), slot = (int)(item & 1);
+    const AxDrop& dr = w.drop[d];
+    const AxCfg& c = w.cfg[dr.cfg];
+    AxState& st = w.st[d];
+    st.header_read[1 + slot] = 0; st.header_chunk[1 + slot] = -1; st.header_parsed[slot] = 0;
+    for (int q = 0; q < 72; ++q) { st.frame_data[slot][q] = 0; st.counter_found[slot][q] = 0; }
+    if (st.sm_status < 1 || st.nedges_total == 0) return;
+    const AxChunk* ch = w.chunk + dr.chunk_base;
+    const int32_t* I = w.edge_idx + dr.edge_base;
+    const uint8_t* B = w.bit + dr.edge_base;
+    const int64_t ps = st.firstpulse400 + (slot ? c.h3s : c.h2s), pe = st.firstpulse400 + (slot ? c.h3e : c.h2e);
+    const int64_t firstbin = I[0];
+    const int klast = (st.k2 >= 0) ? st.k2 : st.n_chunks - 1;
+    for (int k = st.k0; k <= klast && k < st.n_chunks; ++k) {
+        if (ch[k].n_edges <= 0) continue;
+        const int64_t ni = ch[k].edge_off + ch[k].n_edges, nb = ch[k].bit_off + ch[k].n_edges - 1;
+        if (!(firstbin <= ps && (int64_t)I[ni - 1] >= pe)) continue;
+        const int64_t a = ax_first_ge(I, ni, ps - c.half), b = ax_last_le(I, ni, pe + c.half);
+        if (a < 0 || b < 0) { ax_raise(st, AXCTD_DROP_TRIM_INDEX, k); return; }
+        const int64_t hi = b < nb ? b : nb;
+        const int64_t n = hi > a ? hi - a : 0;
+        const uint8_t* bits = B + a;
+        // ---- trim_header, parse.py:157-183
+        int64_t last_pulse = 0; int ones25 = 0; int run = 0;
+        for (int64_t i = 0; i < n; ++i) {
+            const int bv = (i < 25) ? 1 : bits[i];
+            if (bv) { ++ones25; ++run; if (i > 10 && run >= 8) last_pulse = i; } else run = 0;
+            if (i > 24) {
+                const int back = (i - 25 < 25) ? 1 : bits[i - 25];
+                if (back) --ones25;
+                if (i >= 400 && ones25 <= 20) break;
+            }
+        }
+        int64_t hn = n - last_pulse;
+        if (hn > 32 * 75) hn = 32 * 75;
+        if (hn < 72 * 32) continue;                       // AXCTDprocessor.py:481: try again next iteration
+        // ---- parse_header, parse.py:197-245
+        int lastframe = -1; int64_t s = 0;
+        uint8_t fb[32];
+        while (lastframe < 71 && s < hn - 32) {
+            for (int q = 0; q < 32; ++q) { const int64_t p = last_pulse + s + q; fb[q] = (p < 25) ? 1 : bits[p]; }
+            if (!(fb[0] == 1 && fb[1] == 0) || !ax_crc_ok(ax_word32(fb))) { ++s; continue; }
+            int cur = 0;
+            if (fb[2] & fb[3] & fb[4] & fb[5] & fb[6]) { cur = (fb[7] << 2 | fb[8] << 1 | fb[9]) + 64; }
+            else { for (int q = 2; q < 10; ++q) cur = (cur << 1) | fb[q]; }
+            if (cur <= 71) {
+                st.counter_found[slot][cur] = 1; lastframe = cur;
+                uint16_t v = 0; for (int q = 10; q < 26; ++q) v = (uint16_t)((v << 1) | fb[q]);
+                st.frame_data[slot][cur] = v;
+            }
+            s += 32;
+        }
+        st.header_parsed[slot] = 1; st.header_read[1 + slot] = 1; st.header_chunk[1 + slot] = k;
+        return;
+    }
+}
+
+// Greedy frame synchronisation over the profile bits of one drop, grouped by
+// run() iteration exactly as the reference consumes its buffers.
+AX_HDN inline void ax_frames_item(const AxWave& w, int64_t d) {
+    const AxDrop& dr = w.drop[d];
+    const AxCfg& c = w.cfg[dr.cfg];
+    AxState& st = w.st[d];
+    st.n_frames = 0;
+    if (st.status != 0 || st.sm_status < 2 || st.k2 < 0 || st.nedges_total == 0) return;
+    AxChunk* ch = w.chunk + dr.chunk_base;
+    const int32_t* I = w.edge_idx + dr.edge_base;
+    const uint8_t* B = w.bit + dr.edge_base;
+    const double* l400 = w.lvl400 + dr.edge_base; const double* l7500 = w.lvl7500 + dr.edge_base;
+    axctd_frame* fr = w.frame + dr.frame_base;
+    const int64_t prof = st.profstartind;
+    int64_t cur = 0;
+    int32_t nf = 0;
+    for (int k = st.k2; k < st.n_chunks; ++k) {
+        ch[k].frame_begin = nf; ch[k].frame_end = nf;
+        if (ch[k].n_edges <= 0) continue;
+        const int64_t NI = ch[k].edge_off + ch[k].n_edges, NB = ch[k].bit_off + ch[k].n_edges - 1;
+        if (cur < NI && (int64_t)I[cur] <= prof) {                     // AXCTDprocessor.py:545-551
+            const int64_t f = ax_first_gt(I, cur, NI, prof);
+            if (f < 0) { ax_raise(st, AXCTD_DROP_TRIM_INDEX, k); return; }
+            cur = f;
+        }
+        const int64_t numbits = NB > cur ? NB - cur : 0;
+        int64_t s = 0;
+        while (s < numbits - 32) {                                     // parse.py:57-89
+            const int64_t p = cur + s;
+            bool ok = (B[p] == 1 && B[p + 1] == 0);
+            uint32_t wd = 0;
+            if (ok) { wd = ax_word32(B + p); ok = ax_crc_ok(wd) && (l7500[p] > 0.0); }
+            if (!ok) { ++s; continue; }
+            if (nf >= dr.frame_cap) { ax_raise(st, AXCTD_DROP_CAPACITY, k); w.flags[AX_FLAG_CAP] = 1; return; }
+            axctd_frame& f = fr[nf++];
+            f.edge_index = I[p]; f.word = wd; f.chunk = k;
+            f.time_raw = ax_div((double)((int64_t)I[p] - prof), c.fs);  // AXCTDprocessor.py:554
+            f.r400_raw = l400[p]; f.r7500_raw = l7500[p];
+            f.keep = 0; f.hex_returned = 0;
+            s += 32;
+        }
+        cur += s;                                                       // AXCTDprocessor.py:618-621
+        ch[k].frame_end = nf;
+    }
+    st.n_frames = nf;
+}
+
+// ---- PSS-78 (gsw_sp_from_c of GSW-C; reference parse.py:132) ----------------
+AX_HD double ax_sp_poly(double x, double ft) {
+    return 0.0080 + (-0.1692 + (25.3851 + (14.0941 + (-7.0261 + 2.7081 * x) * x) * x) * x) * x
+         + ft * (0.0005 + (-0.0056 + (-0.0066 + (-0.0375 + (0.0636 + -0.0144 * x) * x) * x) * x) * x);
+}
+AX_HD double ax_dsp_poly(double x, double ft) {
+    return -0.1692 + (2 * 25.3851 + (3 * 14.0941 + (4 * -7.0261 + 5 * 2.7081 * x) * x) * x) * x
+         + ft * (-0.0056 + (2 * -0.0066 + (3 * -0.0375 + (4 * 0.0636 + 5 * -0.0144 * x) * x) * x) * x);
+}
+AX_HD double ax_hill_ratio(double t) {
+    const double g0 = 2.641463563366498e-1, g1 = 2.007883247811176e-4, g2 = -4.107694432853053e-6,
+                 g3 = 8.401670882091225e-8, g4 = -1.711392021989210e-9, g5 = 3.374193893377380e-11,
+                 g6 = -5.923731174730784e-13, g7 = 8.057771569962299e-15, g8 = -7.054313817447962e-17,
+                 g9 = 2.859992717347235e-19;
+    const double t68 = t * 1.00024;
+    const double ft = (t68 - 15.0) / (1.0 + 0.0162 * (t68 - 15.0));
+    const double rtx0 = g0 + t68 * (g1 + t68 * (g2 + t68 * (g3 + t68 * (g4 + t68 * (g5 + t68 * (g6 + t68 * (g7 + t68 * (g8 + t68 * g9))))))));
+    double dsp = ax_dsp_poly(rtx0, ft);
+    const double sp_est = ax_sp_poly(rtx0, ft);
+    double rtx = rtx0 - (sp_est - 2.0) / dsp;
+    const double rtxm = 0.5 * (rtx + rtx0);
+    dsp = ax_dsp_poly(rtxm, ft);
+    rtx = rtx0 - (sp_est - 2.0) / dsp;
+    const double x = 400.0 * rtx * rtx, sq = 10.0 * rtx;
+    const double part1 = 1.0 + x * (1.5 + x), part2 = 1.0 + sq * (1.0 + sq * (1.0 + sq));
+    return 2.0 / (2.0 - 0.0080 / part1 - 0.0005 * ft / part2);
+}
+AX_HD double ax_sp_from_c(double C, double t, double p) {
+    const double t68 = t * 1.00024;
+    const double ft = (t68 - 15.0) / (1.0 + 0.0162 * (t68 - 15.0));
+    const double r = 0.023302418791070513 * C;
+    const double rt_lc = 0.6766097 + (2.00564e-2 + (1.104259e-4 + (-6.9698e-7 + 1.0031e-9 * t68) * t68) * t68) * t68;
+    const double rp = 1.0 + (p * (2.070e-5 + -6.370e-10 * p + 3.989e-15 * p * p))
+                          / (1.0 + 3.426e-2 * t68 + 4.464e-4 * t68 * t68 + (4.215e-1 + -3.107e-3 * t68) * r);
+    double rt = r / (rp * rt_lc);
+    if (rt < 0.0) rt = ax_nan();
+    const double rtx = sqrt(rt);
+    double sp = ax_sp_poly(rtx, ft);
+    if (sp < 2.0) {
+        const double x = 400.0 * rt, sq = 10.0 * rtx;
+        const double part1 = 1.0 + x * (1.5 + x), part2 = 1.0 + sq * (1.0 + sq * (1.0 + sq));
+        sp = ax_hill_ratio(t) * (sp - 0.0080 / part1 - 0.0005 * ft / part2);
+    }
+    if (sp < 0.0) sp = ax_nan();
+    return sp;
+}
+
+// parse.py:297-301: output = 0; output += c[i] * x**i
+AX_HD double ax_dataconvert(double x, const double* cf) {
+    double out = cf[0];                                   // 0 + c0 * x**0
+    out = ax_add(out, ax_mul(cf[1], x));
+    const double x2 = ax_mul(x, x);
+    out = ax_add(out, ax_mul(cf[2], x2));
+    out = ax_add(out, ax_mul(cf[3], ax_mul(x2, x)));
+    return out;
+}
+AX_HD double ax_round2(double v) { return ax_div(rint(ax_mul(v, 100.0)), 100.0); }   // np.round(v, 2)
+
+AX_HDN inline void ax_calib_item(const AxWave& w, int64_t fg) {
+    const int d = ax_find_owner(w.drop, w.n_drops, &AxDrop::frame_base, fg);
+    const AxDrop& dr = w.drop[d];
+    const AxState& st = w.st[d];
+    if (fg - dr.frame_base >= st.n_frames || st.status != 0) return;
+    const AxCfg& c = w.cfg[dr.cfg];
+    axctd_frame& f = w.frame[fg];
+    f.cint = (int32_t)((f.word >> 18) & 0xFFF);           // bits 2..13  (parse.py:107)
+    f.tint = (int32_t)((f.word >> 6) & 0xFFF);            // bits 14..25 (parse.py:106)
+    const double z = ax_dataconvert(f.time_raw, st.zc_used);                    // parse.py:117
+    const double tun = (f.tint >= 0 && f.tint <= c.lut_len - 1) ? c.lut[f.tint] : ax_nan();   // parse.py:120-123
+    const double cun = ax_div((double)(f.cint * 60), 4096.0);                   // parse.py:125
+    const double T = ax_dataconvert(tun, st.tc_used);
+    const double C = ax_dataconvert(cun, st.cc_used);
+    const double S = ax_sp_from_c(C, T, z);
+    f.depth_raw = z; f.temperature_raw = T; f.conductivity_raw = C; f.salinity_raw = S;
+    f.time_s = ax_round2(ax_add(f.time_raw, st.firstpointtime));                // AXCTDprocessor.py:560
+    f.depth = ax_round2(z); f.temperature = ax_round2(T); f.conductivity = ax_round2(C); f.salinity = ax_round2(S);
+    f.r400 = ax_round2(f.r400_raw); f.r7500 = ax_round2(f.r7500_raw);
+    const bool bad = f.r7500 < c.min_dr7500_inprof || f.r400 < c.min_r400_inprof || f.temperature < c.tlims[0]
+                  || f.temperature > c.tlims[1] || f.salinity < c.slims[0] || f.salinity > c.slims[1];   // :572-574
+    f.keep = bad ? 0 : 1;
+}
+
+// np.percentile(v, q) (method 'linear') on an ascending array without NaN
+AX_HD double ax_percentile_sorted(const double* v, int n, double q) {
+    const double virt = ax_mul((double)(n - 1), q);
+    int64_t prev = (int64_t)floor(virt), next = prev + 1;
+    if (virt >= (double)(n - 1)) { prev = n - 1; next = n - 1; }
+    if (virt < 0) { prev = 0; next = 0; }
+    const double gamma = ax_sub(virt, floor(virt));
+    const double a = v[prev], b = v[next];
+    const double diff = ax_sub(b, a);
+    double r = ax_add(a, ax_mul(diff, gamma));
+    if (gamma >= 0.5) r = ax_sub(b, ax_mul(diff, ax_sub(1.0, gamma)));
+    return r;
+}
+
+AX_HD void ax_sort_small(double* v, int n) {
+    for (int i = 1; i < n; ++i) { const double x = v[i]; int j = i - 1; while (j >= 0 && v[j] > x) { v[j + 1] = v[j]; --j; } v[j + 1] = x; }
+}
+
+// AXCTDprocessor.py:576-613 for the frames parsed in one iteration
+AX_HDN inline void ax_qc_item(const AxWave& w, int64_t cg, double* scratch) {
+    const int d = ax_find_owner(w.drop, w.n_drops, &AxDrop::chunk_base, cg);
+    const AxDrop& dr = w.drop[d];
+    const AxState& st = w.st[d];
+    const int k = (int)(cg - dr.chunk_base);
+    if (st.status != 0 || st.k2 < 0 || k < st.k2 || k >= st.n_chunks) return;
+    AxChunk& ch = w.chunk[cg];
+    ch.n_rows = 0; ch.n_hex = 0;
+    const int nfr = ch.frame_end - ch.frame_begin;
+    if (nfr <= 0) return;
+    axctd_frame* fr = w.frame + dr.frame_base + ch.frame_begin;
+    double* tv = scratch + 2 * ((int64_t)dr.frame_base + ch.frame_begin);
+    double* sv = tv + nfr;
+    int n = 0; bool tnan = false, snan = false;
+    for (int i = 0; i < nfr; ++i) if (fr[i].keep) {
+        tv[n] = fr[i].temperature; sv[n] = fr[i].salinity;
+        tnan |= isnan(tv[n]); snan |= isnan(sv[n]); ++n;
+    }
+    if (n == 0) return;
+    double Tlo = ax_nan(), Thi = ax_nan(), Slo = ax_nan(), Shi = ax_nan();
+    if (!tnan) {
+        ax_sort_small(tv, n);
+        const double m = ax_percentile_sorted(tv, n, 0.5);
+        Tlo = ax_sub(m, ax_mul(10.0, ax_sub(m, ax_percentile_sorted(tv, n, 0.15))));
+        Thi = ax_add(m, ax_mul(10.0, ax_sub(ax_percentile_sorted(tv, n, 0.85), m)));
+    }
+    if (!snan) {
+        ax_sort_small(sv, n);
+        const double m = ax_percentile_sorted(sv, n, 0.5);
+        Slo = ax_sub(m, ax_mul(10.0, ax_sub(m, ax_percentile_sorted(sv, n, 0.15))));
+        Shi = ax_add(m, ax_mul(10.0, ax_sub(ax_percentile_sorted(sv, n, 0.85), m)));
+    }
+    int rows = 0;
+    for (int i = 0; i < nfr; ++i) if (fr[i].keep) {
+        const double T = fr[i].temperature, S = fr[i].salinity;
+        if (T < Tlo || T > Thi || S < Slo || S > Shi) fr[i].keep = 0; else ++rows;
+    }
+    ch.n_rows = rows;
+    if (rows > 0) { ch.n_hex = nfr; for (int i = 0; i < nfr; ++i) fr[i].hex_returned = 1; }   // :611-612
+}

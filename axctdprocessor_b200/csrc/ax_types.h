@@ -1,0 +1,197 @@
+// ax_types.h -- device-side data model of the AXCTD engine.
+//
+// All per-batch state lives in flat device arrays described by AxWave; every
+// kernel receives the AxWave by value.  The same header compiles for the GPU
+// (nvcc) and, with -DAXCTD_EMU, for the test-only host emulation used to debug
+// the algorithm without a GPU (tests/emu; never loaded by the product).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include "../../include/axctd.h"
+
+#if defined(__CUDACC__) && !defined(AXCTD_EMU)
+#define AX_HD __host__ __device__ __forceinline__
+#define AX_HDN __host__ __device__
+#else
+#define AX_HD inline
+#define AX_HDN
+#endif
+
+// ---- IEEE operations that must never be contracted into FMAs -------------
+// (exact restatement of scipy's C sosfilt, which is compiled without FMA)
+AX_HD double ax_mul(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dmul_rn(a, b);
+#else
+    return a * b;   // host objects are built with -ffp-contract=off
+#endif
+}
+AX_HD double ax_add(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+AX_HD double ax_sub(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dadd_rn(a, -b);
+#else
+    return a - b;
+#endif
+}
+AX_HD double ax_div(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __ddiv_rn(a, b);
+#else
+    return a / b;
+#endif
+}
+AX_HD double ax_fma(double a, double b, double c) { return fma(a, b, c); }
+AX_HD double ax_nan() { return nan(""); }
+
+#define AX_TILE 64          // crossings per walk tile
+#define AX_MAXSEC AXCTD_MAX_SECTIONS
+#define AX_PEND 6           // pending bit-windows per thread in the filter pass
+#define AX_STAT_SLAB 16384  // samples per stats work item
+
+// Per rate-class constants (reference AXCTDprocessor.py:117-182, 212-262).
+struct AxCfg {
+    double fs;
+    int64_t fs2;                 // round(2*fs): the walk compares |d*2*bitrate - fs2| (demodulate.py:92)
+    int32_t n_power, d_pcm, npcm, chunk_len, pad, inset, bitrate, nsec;
+    double sos[AX_MAXSEC][6];
+    int32_t warm;                // warm-up overlap of the continuous filter pass (samples)
+    int32_t head;                // exact zero-state prefix recomputed per chunk (samples)
+    int32_t rebase;              // phase re-anchoring period of the bit-window prefix sums
+    int32_t head_zc_cap;         // crossings kept per exact head
+    int32_t ybuf_len;            // head + npcm + 2
+    int32_t tone_G, tone_nb, tone_stride;   // block decomposition of the tone windows
+    double min_r400, min_dr7500, min_r400_inprof, min_dr7500_inprof;
+    double trig_from, trig_to, scale0;
+    double zc[4], tc[4], cc[4], tlims[2], slims[2];
+    int64_t off_4p5, off_5p5, off_trig_from, off_trig_to;          // int(f_s*x)
+    int64_t h1s, h1e, h2s, h2e, h3s, h3e, half;                    // AXCTDprocessor.py:447-456
+    double rot[2][2];            // cos,sin of (-theta_f * rebase), f = mark, space
+    const double* bit_cs;        // [rebase+1][4]
+    const double* tone_cs;       // [n_power][6]
+    const double* lut;           // [lut_len]
+    const double* hist_edges;    // [n_hist_edges]
+    const double* hist_centers;  // [n_hist_edges-1]
+    int32_t lut_len, n_hist_edges;
+};
+
+struct AxDrop {
+    int64_t pcm_off, n;          // sample offset into the batch PCM buffer, sample count
+    int32_t cfg;
+    int32_t seg_base, nseg;      // segments of the continuous filter pass
+    int32_t slab_base, nslab;    // stats work items
+    int64_t zc_base, zc_cap;     // dense crossing arrays
+    int32_t tile_base, tile_cap;
+    int32_t chunk_base, chunk_cap;
+    int64_t edge_base, edge_cap; // bit / edge arrays
+    int32_t pw_base, pw_cap;     // power samples
+    int32_t frame_base, frame_cap;
+    int32_t pad0;
+};
+
+// One run() iteration (reference AXCTDprocessor.py:283-338).
+struct AxChunk {
+    int64_t s, e;                // demodbufferstartind, e
+    int64_t spec_last;           // last bit edge (global PCM index) predicted from the continuous pass
+    int64_t true_last;           // last bit edge with the exact zero-state head
+    int64_t g_first;             // dense ordinal of the first bit edge taken from the continuous pass, -1 if none
+    int64_t q_last;              // dense ordinal of the chunk's last usable crossing
+    int64_t bit_off, edge_off;   // offsets into the drop's bit / edge arrays
+    int64_t first_edge;          // first bit edge (global PCM index)
+    int32_t pw_off, np;          // power samples of this iteration
+    int32_t n_head_edges;        // bit edges found inside the exact head
+    int32_t n_edges;             // total bit edges (bits = n_edges - 1), 0 if not demodulated
+    int32_t status;              // self.status after the iteration
+    int32_t err;                 // AXCTD_DROP_* raised by this chunk
+    int32_t n_rows, n_hex;
+    int32_t frame_begin, frame_end;   // frames parsed in this iteration
+    double scale;
+    double mean7500;             // mean7500pwr in force when the chunk was demodulated (NaN before)
+};
+
+// Sequential per-drop state (the attributes of reference class AXCTD_Processor).
+struct AxState {
+    int32_t status, status_chunk;
+    int64_t sum;
+    int32_t ampl;
+    int32_t n_uncertain;
+    double dc, inv_ampl, ampl_d;
+    int64_t zc_count;
+    // state machine
+    int32_t sm_status;           // self.status
+    int32_t n_chunks;            // run() iterations
+    int32_t n_fixed;             // iterations of the fixed (status 0) grid that were planned
+    int32_t k0, k2, km;          // first demod chunk, profile chunk, chunk where mean7500pwr was set
+    int32_t pcount;              // len(power_inds)
+    int32_t next_sm_chunk;       // next iteration the level state machine will process
+    int64_t firstpulse400, profstartind;
+    double firstpointtime, mean7500;
+    // chain
+    int32_t chain_from;          // first chunk whose start is not yet final
+    int32_t chain_dirty;         // set by verify when a mis-speculation was repaired
+    int32_t n_fixups;
+    int32_t chain_end;           // chain finished (file end or error)
+    // demod bookkeeping
+    double scale;
+    int32_t k1;                  // iteration at the end of which the scale changed
+    int32_t header_read[3], header_chunk[3];
+    int64_t nbits_total, nedges_total;
+    int64_t n_frames, n_rows, n_hex;
+    int32_t header_parsed[2];
+    uint16_t frame_data[2][72];
+    uint8_t counter_found[2][72];
+    double zc_used[4], tc_used[4], cc_used[4];
+};
+
+struct AxWave {
+    int32_t n_drops, n_cfg;
+    const AxCfg* cfg;
+    const AxDrop* drop;
+    AxState* st;
+    const int16_t* pcm;
+    // continuous filter pass
+    int32_t seg_len, seg_cap, nseg_total, nslab_total;
+    const int32_t* seg_drop;     // segment -> drop
+    const int32_t* slab_drop;    // stats slab -> drop
+    int32_t* seg_cnt; int64_t* seg_off;
+    int32_t* rec_idx; double* rec_a1; double* rec_a2;       // [nseg_total * seg_cap]
+    int32_t* zc_idx; double* zc_a1; double* zc_a2;          // dense, per drop at zc_base
+    uint16_t* tile_tab;                                     // [tile][4]
+    // chunks
+    AxChunk* chunk;
+    int32_t* head_idx; double* head_a1; double* head_a2;    // [chunk][head_zc_cap_max]
+    double* ybuf;                                           // [chunk][ybuf_len_max]
+    int32_t head_zc_cap_max, ybuf_len_max;
+    // tone powers
+    double* pw_raw;              // [3][pw_total]
+    double* pw_sm;               // [3][pw_total]
+    double* r400; double* r7500; // [pw_total]
+    int64_t* pw_ind;             // [pw_total] power_inds
+    int32_t pw_total;
+    double* blk;                 // tone block sums scratch [chunk][blk_stride][6]
+    int32_t blk_stride, pad1;
+    // bits / edges
+    int32_t* edge_idx; double* lvl400; double* lvl7500;     // per edge
+    uint8_t* bit; double* a1; double* a2; double* conf;     // per bit
+    // frames
+    axctd_frame* frame;
+    double guard;
+    int32_t tone_direct;
+    int32_t force_exact;
+    int32_t* flags;              // [0] = any chain dirty, [1] = any capacity error
+};
+
+AX_HD bool ax_tone_blocked_ok(const AxCfg& c) { return c.tone_G >= 32 && c.tone_nb <= 16 && (int64_t)c.tone_G * 48 <= 160 * 1024; }
+
+#define AX_FLAG_DIRTY 0
+#define AX_FLAG_CAP 1
+
+AX_HD void ax_raise(AxState& st, int code, int chunk) {
+    if (st.status == 0) { st.status = code; st.status_chunk = chunk; }
+}

@@ -1,0 +1,204 @@
+/*
+ * axctd.h -- C ABI of the B200-native AXCTD demodulation / decoding engine.
+ *
+ * The reference (cdens/AXCTDprocessor) is pure Python and has no FFI of its
+ * own; the drop-in boundary is its Python API (class AXCTD_Processor,
+ * reference AXCTDprocessor.py:80-627, driven by processAXCTD.py:126-183).
+ * This header is the C boundary underneath the Python mirror of that API
+ * (axctdprocessor_b200/AXCTDprocessor.py): plain pointers and sizes, caller
+ * owns all host memory, every call returns an int status and never throws.
+ * One engine per GPU, one host thread per engine.
+ *
+ * Each entry point cites the reference code it replaces.
+ */
+#ifndef AXCTD_H
+#define AXCTD_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AXCTD_ABI_VERSION 1
+#define AXCTD_MAX_SECTIONS 6
+
+/* ---- return codes of API calls ---------------------------------------- */
+#define AXCTD_OK                 0
+#define AXCTD_ERR_CUDA           1   /* CUDA runtime error, see axctd_last_error */
+#define AXCTD_ERR_ARG            2
+#define AXCTD_ERR_CAPACITY       3   /* an internal capacity was exceeded */
+#define AXCTD_ERR_STATE          4
+
+/* ---- per-drop status (axctd_drop_summary.status) ---------------------- */
+/* Non-zero values >= 16 mirror the exception the reference would raise.   */
+#define AXCTD_DROP_OK                  0
+#define AXCTD_DROP_NO_CROSSING        16  /* IndexError, demodulate.py:85 */
+#define AXCTD_DROP_FLOAT_INDEX        17  /* TypeError after AXCTDprocessor.py:331 */
+#define AXCTD_DROP_SHORT_WINDOW       18  /* ValueError (broadcast), demodulate.py:101 */
+#define AXCTD_DROP_HEADER_VALUE       19  /* ValueError, parse.py:278 */
+#define AXCTD_DROP_SCALE_EMPTY        20  /* ValueError (min of empty), demodulate.py:149 */
+#define AXCTD_DROP_TRIM_INDEX         21  /* IndexError, AXCTDprocessor.py:546 / :462 */
+#define AXCTD_DROP_CAPACITY           32  /* engine capacity exceeded (not a reference error) */
+#define AXCTD_DROP_UNCERTAIN          33  /* a sign/threshold decision fell inside the guard band */
+#define AXCTD_DROP_CHAIN_DIVERGED     34  /* chunk-chain fix-up did not converge */
+
+/*
+ * Settings of one "rate class" (everything AXCTD_Processor derives from f_s
+ * and its settings dict): reference AXCTDprocessor.py:117-182 (constants),
+ * :187-208 (defaults), :212-262 (derived tables and the Butterworth SOS).
+ * Tables are computed by the host with numpy/scipy exactly as the reference
+ * does and passed as data.
+ */
+typedef struct axctd_config_desc {
+    double fs;                  /* effective sampling rate f_s (after any /2 decimation) */
+    int32_t n_power;            /* int(f_s/10)                      :153 */
+    int32_t d_pcm;              /* int(round(f_s/25))               :155 */
+    int32_t npcm;               /* N - 2*bit_inset                  :170-171 */
+    int32_t chunk_len;          /* int(refreshrate*f_s)             :222 */
+    int32_t pad;                /* demod_Npad = 100                 :158 */
+    int32_t bit_inset;          /* 1                                :165 */
+    int32_t bitrate;            /* 800                              :164 */
+    int32_t n_sections;         /* rows of sos (3 lowpass, 6 bandpass) :254-257 */
+    double sos[AXCTD_MAX_SECTIONS][6]; /* scipy.signal.butter(..., output='sos') */
+    double max_pole_radius;     /* largest |pole| of sos; sizes the warm-up overlap */
+    /* cos/sin tables computed by the host with numpy exactly as the reference does: */
+    const double* bit_cs;       /* [bit_cs_len][4] = cos(trig1), sin(trig1), cos(trig2), sin(trig2);
+                                   trig = 2*pi*n/f_s*f (:245-246), extended to n < bit_cs_len (> npcm) */
+    int32_t bit_cs_len;
+    int32_t reserved0;
+    const double* tone_cs;      /* [n_power][6] = cos,sin of theta400, theta7500, thetadead (:260-262) */
+    double min_r400;            /* settings['minr400']              :225 */
+    double min_dr7500;          /* settings['mindr7500']            :227 */
+    double trigger_from_s;      /* triggerrange[0] (30)             :250 */
+    double trigger_to_s;        /* triggerrange[1] (-1)             :250 */
+    double high_bit_scale0;     /* 1.5                              :161 */
+    double zcoeff[4], tcoeff[4], ccoeff[4];   /* defaults           :203-205 */
+    double tlims[2], slims[2];  /*                                  :207-208 */
+    const double* temp_lut;     /* [lut_len] parse.read_temp_LUT    parse.py:139 */
+    int32_t lut_len;
+    const double* hist_edges;   /* [n_hist_edges] np.arange(0,3,0.01)  demodulate.py:130 */
+    const double* hist_centers; /* [n_hist_edges-1]                    demodulate.py:132 */
+    int32_t n_hist_edges;
+    int32_t reserved;
+} axctd_config_desc;
+
+/* Result header of one drop: the scalar attributes processAXCTD.py:149-168 reads. */
+typedef struct axctd_drop_summary {
+    int32_t status;             /* AXCTD_DROP_* */
+    int32_t status_chunk;       /* chunk index where status was raised, or -1 */
+    int64_t numpoints;          /* len(audiostream)                 :91 */
+    double  f_s;
+    int64_t firstpulse400;      /* -1 if never found                :140,378 */
+    int64_t profstartind;       /* -1 if never triggered            :141,401 */
+    double  firstpointtime;
+    double  mean7500pwr;        /*                                  :393 */
+    double  high_bit_scale;     /* after header 1                   :467 */
+    int32_t n_chunks;           /* loop iterations of run()         :283 */
+    int32_t first_demod_chunk;  /* -1 if none */
+    int32_t profile_chunk;      /* iteration where status became 2, -1 if none */
+    int32_t header_read[3];     /* header1_read..header3_read       :122-124 */
+    int32_t header_chunk[3];
+    int64_t n_bits;             /* total demodulated bits (all chunks) */
+    int64_t n_edges;            /* total bit edges (n_bits + demod chunks) */
+    int64_t n_power;            /* len(power_inds) */
+    int64_t n_frames;           /* CRC-valid profile frames found */
+    int64_t n_rows;             /* rows surviving QC + spike filter */
+    int64_t n_hex;              /* hexframes returned to the caller (:612 quirk) */
+    int64_t n_crossings;        /* zero crossings of the continuous filter pass */
+    int32_t n_uncertain;        /* guard-band hits */
+    int32_t n_chain_fixups;     /* mis-speculated chunks repaired */
+    int64_t pcm_sum;            /* integer sum and max|x| of the int16 input (:55-56) */
+    int32_t pcm_ampl;
+    int32_t reserved;
+    /* header frames as decoded by parse_header (parse.py:197-285), slot 0 = header 2, 1 = header 3 */
+    uint16_t frame_data[2][72];
+    uint8_t  counter_found[2][72];
+    int32_t  header_parsed[2];  /* parse_header ran for that slot */
+    /* merged metadata after AXCTDprocessor.py:505-535 */
+    double  zcoeff[4], tcoeff[4], ccoeff[4];      /* metadata['?coeff'] */
+    int32_t zcoeff_valid[4], tcoeff_valid[4], ccoeff_valid[4];
+    double  zcoeff_used[4], tcoeff_used[4], ccoeff_used[4];   /* self.?coeff actually applied */
+} axctd_drop_summary;
+
+/* One profile frame (parse.py:41-92) with its calibrated values (parse.py:113-134). */
+typedef struct axctd_frame {
+    int64_t edge_index;         /* PCM index paired with the frame's first bit */
+    uint32_t word;              /* the 32 frame bits, MSB first (binListToHex) */
+    int32_t  chunk;             /* run() iteration that parsed it */
+    int32_t  cint, tint;        /* parse.py:106-107 */
+    int32_t  keep;              /* 1 if the row survives QC and the spike filter (:569-609) */
+    int32_t  hex_returned;      /* 1 if its hex string reaches self.hexframes (:612,:323) */
+    double time_s;              /* rounded, + firstpointtime        :560 */
+    double depth, temperature, conductivity, salinity;   /* rounded  :561-564 */
+    double r400, r7500;         /* rounded                          :565-566 */
+    double time_raw, depth_raw, temperature_raw, conductivity_raw, salinity_raw, r400_raw, r7500_raw;
+} axctd_frame;
+
+/* One run() iteration (AXCTDprocessor.py:283-338). */
+typedef struct axctd_chunk {
+    int64_t s, e;               /* demodbufferstartind, e           :293-304 */
+    int32_t status;             /* self.status after the iteration */
+    int32_t n_power_total;      /* len(power_inds) after the iteration */
+    int32_t n_bits;             /* bits demodulated in this iteration, -1 if none */
+    int32_t first_edge, last_edge;   /* chunk-relative, demodulate.py:85,104 */
+    int32_t n_head_edges;       /* edges taken from the exact zero-state recomputation */
+    int32_t n_rows, n_hex;
+    double  scale;              /* high_bit_scale used                :411 */
+} axctd_chunk;
+
+typedef struct axctd_engine axctd_engine;
+typedef struct axctd_batch  axctd_batch;
+
+/* ---- engine ----------------------------------------------------------- */
+int  axctd_abi_version(void);
+/* 1 if the library was built with the CUDA kernels (always for the product). */
+int  axctd_has_cuda(void);
+/* sizeof() of the ABI structs: 0 config_desc, 1 drop_summary, 2 frame, 3 chunk (binding self-check). */
+int  axctd_struct_size(int which);
+int  axctd_engine_create(int device, axctd_engine** out);
+void axctd_engine_destroy(axctd_engine* e);
+const char* axctd_last_error(axctd_engine* e);
+/* Tunables: "segment_len", "exact_head", "guard", "force_exact", "tone_direct",
+ * "tile", "max_fixups", "filter_variant".  Unknown names return AXCTD_ERR_ARG. */
+int  axctd_engine_set_option(axctd_engine* e, const char* name, double value);
+/* Number of kernels launched by the engine since creation (for bench.py). */
+int64_t axctd_engine_launch_count(axctd_engine* e);
+
+/* Replaces AXCTD_Processor.initialize_AXCTD_vars + load_AXCTD_settings
+ * (AXCTDprocessor.py:117-182, 212-262): copies the tables to the device. */
+int  axctd_config_create(axctd_engine* e, const axctd_config_desc* desc, int* config_id);
+
+/* ---- batch of independent drops --------------------------------------- */
+/* Allocates device storage for n_drops mono int16 recordings. */
+int  axctd_batch_create(axctd_engine* e, int n_drops, const int64_t* n_samples,
+                        const int32_t* config_id, axctd_batch** out);
+void axctd_batch_destroy(axctd_batch* b);
+/* Replaces the PCM part of readAXCTDwavfile (AXCTDprocessor.py:41-57): copies
+ * one drop's int16 samples host->device (stream ordered). */
+int  axctd_batch_upload(axctd_batch* b, int drop, const int16_t* pcm, int64_t n);
+/* Device pointer of a drop's PCM (for callers that fill it on the GPU). */
+int  axctd_batch_device_pcm(axctd_batch* b, int drop, void** dptr);
+/* Replaces AXCTD_Processor.run() (AXCTDprocessor.py:267-338) for every drop
+ * of the batch.  Blocks until the results are on the host. */
+int  axctd_batch_run(axctd_batch* b);
+/* Same, but returns after enqueueing the device work; pair with _finish. */
+int  axctd_batch_run_async(axctd_batch* b);
+int  axctd_batch_finish(axctd_batch* b);
+/* Device milliseconds of the last run (CUDA events on the engine stream),
+ * and of the dominant filter kernel inside it. */
+int  axctd_batch_timing(axctd_batch* b, double* total_ms, double* filter_ms, double* tone_ms);
+
+int  axctd_batch_summary(axctd_batch* b, int drop, axctd_drop_summary* out);
+/* Caller-owned buffers; each returns the number of items written or a
+ * negative AXCTD_ERR_* code.  cap is the buffer capacity in items. */
+int64_t axctd_batch_frames(axctd_batch* b, int drop, axctd_frame* out, int64_t cap);
+int64_t axctd_batch_chunks(axctd_batch* b, int drop, axctd_chunk* out, int64_t cap);
+int64_t axctd_batch_bits(axctd_batch* b, int drop, uint8_t* bits, double* conf, int64_t cap);
+int64_t axctd_batch_edges(axctd_batch* b, int drop, int64_t* edges, double* r400, double* r7500, int64_t cap);
+int64_t axctd_batch_power(axctd_batch* b, int drop, int64_t* power_inds, double* r400, double* r7500, int64_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AXCTD_H */
