@@ -75,12 +75,23 @@ class Chunk(C.Structure):
     ]
 
 
+class SynthDesc(C.Structure):
+    _fields_ = [
+        ("n_total", C.c_int64), ("n0", C.c_int64), ("tone_start", C.c_int64), ("fs", C.c_int64),
+        ("key1", C.c_uint64), ("key2", C.c_uint64),
+        ("nscale", C.c_double), ("gain", C.c_double), ("tone_amp", C.c_double),
+        ("sin_coef", C.c_double * 9),
+        ("bits", C.c_void_p), ("gate", C.c_void_p), ("parity", C.c_void_p), ("nslots", C.c_int64),
+    ]
+
+
 SYMBOLS = [
     "axctd_abi_version", "axctd_has_cuda", "axctd_struct_size", "axctd_engine_create", "axctd_engine_destroy", "axctd_last_error",
-    "axctd_engine_set_option", "axctd_engine_launch_count", "axctd_config_create", "axctd_batch_create",
+    "axctd_engine_set_option", "axctd_engine_set_stream", "axctd_engine_launch_count", "axctd_config_create", "axctd_batch_create",
     "axctd_batch_destroy", "axctd_batch_upload", "axctd_batch_device_pcm", "axctd_batch_run",
     "axctd_batch_run_async", "axctd_batch_finish", "axctd_batch_timing", "axctd_batch_summary",
     "axctd_batch_frames", "axctd_batch_chunks", "axctd_batch_bits", "axctd_batch_edges", "axctd_batch_power",
+    "axctd_synth_fill", "axctd_batch_download",
 ]
 
 
@@ -97,6 +108,7 @@ def bind(lib: C.CDLL) -> C.CDLL:
         "axctd_last_error": (C.c_char_p, [vp]),
         "axctd_engine_set_option": (i32, [vp, C.c_char_p, dbl]),
         "axctd_engine_launch_count": (i64, [vp]),
+        "axctd_engine_set_stream": (i32, [vp, vp]),
         "axctd_config_create": (i32, [vp, P(ConfigDesc), P(i32)]),
         "axctd_batch_create": (i32, [vp, i32, P(i64), P(C.c_int32), P(vp)]),
         "axctd_batch_destroy": (None, [vp]),
@@ -112,6 +124,8 @@ def bind(lib: C.CDLL) -> C.CDLL:
         "axctd_batch_bits": (i64, [vp, i32, vp, vp, i64]),
         "axctd_batch_edges": (i64, [vp, i32, vp, vp, vp, i64]),
         "axctd_batch_power": (i64, [vp, i32, vp, vp, vp, i64]),
+        "axctd_synth_fill": (i32, [vp, i32, P(SynthDesc)]),
+        "axctd_batch_download": (i32, [vp, i32, vp, i64]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "ax_proto.h"
+#include "ax_synth.h"
 
 #ifndef AXCTD_EMU
 #include <cuda_runtime.h>
@@ -78,12 +79,14 @@ AX_GLOBAL void k_bits(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_bits_item(w, item
 AX_GLOBAL void k_headers(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_header_item(w, item); }
 AX_GLOBAL void k_frames(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_frames_item(w, item); }
 AX_GLOBAL void k_calib(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_calib_item(w, item); }
+AX_GLOBAL void k_synth(int64_t n, AxSynth g) { AX_FOR_ITEM(n) ax_synth_item(g, item); }
 AX_GLOBAL void k_qc(int64_t n, AxWave w, double* scratch) { AX_FOR_ITEM(n) ax_qc_item(w, item, scratch); }
 
 // ============================================================ memory helpers
 struct axctd_engine {
     int device = 0;
     axStream stream = 0;
+    bool own_stream = true;
     std::string err;
     std::vector<AxCfg> cfgs;              // host copies (device pointers inside)
     std::vector<void*> cfg_allocs;
@@ -200,9 +203,21 @@ extern "C" void axctd_engine_destroy(axctd_engine* e) {
     for (void* p : e->cfg_allocs) ax_free(p);
     ax_free(e->d_cfg);
 #ifndef AXCTD_EMU
-    if (e->stream) cudaStreamDestroy(e->stream);
+    if (e->stream && e->own_stream) cudaStreamDestroy(e->stream);
 #endif
     delete e;
+}
+
+extern "C" int axctd_engine_set_stream(axctd_engine* e, void* cuda_stream) {
+    if (!e) return AXCTD_ERR_ARG;
+#ifndef AXCTD_EMU
+    if (e->stream && e->own_stream) { cudaStreamSynchronize(e->stream); cudaStreamDestroy(e->stream); }
+    e->stream = (cudaStream_t)cuda_stream;
+    e->own_stream = false;
+#else
+    (void)cuda_stream;
+#endif
+    return AXCTD_OK;
 }
 
 extern "C" const char* axctd_last_error(axctd_engine* e) { return e ? e->err.c_str() : "null engine"; }
@@ -721,4 +736,33 @@ extern "C" int64_t axctd_batch_power(axctd_batch* b, int drop, int64_t* power_in
     if (r7500 && np && ax_d2h(b->eng, r7500, b->w.r7500 + base, sizeof(double) * np)) return -AXCTD_ERR_CUDA;
     if (ax_sync(b->eng)) return -AXCTD_ERR_CUDA;
     return np;
+}
+
+// ============================================================ bench / test tooling
+extern "C" int axctd_synth_fill(axctd_batch* b, int drop, const axctd_synth_desc* ds) {
+    if (!b || !ds || drop < 0 || drop >= b->n || ds->n_total != b->drops[drop].n || !ds->bits || !ds->gate || !ds->parity) return AXCTD_ERR_ARG;
+    axctd_engine* e = b->eng;
+    AxSynth g;
+    g.n_total = ds->n_total; g.n0 = ds->n0; g.tone_start = ds->tone_start; g.fs = ds->fs;
+    g.key1 = ds->key1; g.key2 = ds->key2; g.nscale = ds->nscale; g.gain = ds->gain; g.tone_amp = ds->tone_amp;
+    for (int q = 0; q < 9; ++q) g.sin_coef[q] = ds->sin_coef[q];
+    g.nslots = ds->nslots;
+    uint8_t* dev = nullptr;
+    if (ax_alloc_arr(b, &dev, 3 * ds->nslots + 16)) return AXCTD_ERR_CUDA;
+    if (ax_h2d(e, dev, ds->bits, (size_t)ds->nslots) || ax_h2d(e, dev + ds->nslots, ds->gate, (size_t)ds->nslots) ||
+        ax_h2d(e, dev + 2 * ds->nslots, ds->parity, (size_t)ds->nslots)) return AXCTD_ERR_CUDA;
+    g.bits = dev; g.gate = dev + ds->nslots; g.par = dev + 2 * ds->nslots;
+    g.out = b->d_pcm + b->drops[drop].pcm_off;
+    int64_t launches_before = e->launches;
+    AX_LAUNCH(e, k_synth, ds->n_total, g);
+    e->launches = launches_before;          // tooling, not part of the decode path
+    if (ax_sync(e)) return AXCTD_ERR_CUDA;
+    b->ran = false;
+    return AXCTD_OK;
+}
+
+extern "C" int axctd_batch_download(axctd_batch* b, int drop, int16_t* pcm, int64_t n) {
+    if (!b || drop < 0 || drop >= b->n || !pcm || n != b->drops[drop].n) return AXCTD_ERR_ARG;
+    if (ax_d2h(b->eng, pcm, b->d_pcm + b->drops[drop].pcm_off, sizeof(int16_t) * n) || ax_sync(b->eng)) return AXCTD_ERR_CUDA;
+    return AXCTD_OK;
 }

@@ -186,6 +186,11 @@ class Engine:
         if self.lib.axctd_engine_set_option(self.h, name.encode(), float(value)) != 0:
             raise ValueError(f"unknown engine option {name}")
 
+    def set_stream(self, cuda_stream: int):
+        """Run on a caller-owned CUDA stream (e.g. torch.cuda.Stream().cuda_stream)."""
+        if self.lib.axctd_engine_set_stream(self.h, C.c_void_p(cuda_stream)) != 0:
+            raise RuntimeError("axctd_engine_set_stream failed")
+
     @property
     def launch_count(self) -> int:
         return int(self.lib.axctd_engine_launch_count(self.h))
@@ -299,6 +304,31 @@ class Batch:
             n = self.lib.axctd_batch_chunks(self.h, i, chunks.ctypes.data, len(chunks))
             chunks = chunks[:max(n, 0)]
         return DropResult(summary=s, frames=frames, chunks=chunks, config=self.configs[i])
+
+    def synth_fill(self, i: int, spec):
+        """bench / test tooling: generate synth.DropSpec ``spec`` directly in device memory."""
+        import synth
+        n_total, truth = synth.build_bitplan(spec)
+        assert n_total == self.n_samples[i], (n_total, self.n_samples[i])
+        par = np.zeros(len(truth.bits) + 1, dtype=np.int64)
+        np.cumsum(truth.bits, out=par[1:])
+        par = np.ascontiguousarray((par[:-1] & 1).astype(np.uint8))
+        bits = np.ascontiguousarray(truth.bits, dtype=np.uint8)
+        gate = np.ascontiguousarray(truth.gate, dtype=np.uint8)
+        d = _lib.SynthDesc()
+        d.n_total, d.n0, d.tone_start, d.fs = n_total, truth.n0, truth.tone_start_sample, spec.fs
+        d.key1, d.key2 = synth.stream_key(spec.seed, 1), synth.stream_key(spec.seed, 2)
+        d.nscale, d.gain, d.tone_amp = synth.noise_sigma(spec) / synth._IH8_SIGMA, synth.gain(spec), spec.tone_amp
+        for k in range(9):
+            d.sin_coef[k] = synth._SIN_COEF[k]
+        d.bits, d.gate, d.parity, d.nslots = bits.ctypes.data, gate.ctypes.data, par.ctypes.data, len(bits)
+        self._check(self.lib.axctd_synth_fill(self.h, i, C.byref(d)), "axctd_synth_fill")
+        return truth
+
+    def download(self, i: int) -> np.ndarray:
+        out = np.empty(self.n_samples[i], dtype=np.int16)
+        self._check(self.lib.axctd_batch_download(self.h, i, out.ctypes.data, out.size), "axctd_batch_download")
+        return out
 
     def bits(self, i: int):
         n = int(self.summary(i).n_bits)

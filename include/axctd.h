@@ -162,6 +162,9 @@ const char* axctd_last_error(axctd_engine* e);
 /* Tunables: "segment_len", "exact_head", "guard", "force_exact", "tone_direct",
  * "tile", "max_fixups", "filter_variant".  Unknown names return AXCTD_ERR_ARG. */
 int  axctd_engine_set_option(axctd_engine* e, const char* name, double value);
+/* Run all engine work on a caller-owned CUDA stream (cudaStream_t passed as void*), so that the
+ * caller can bracket it with its own events.  The engine does not take ownership. */
+int  axctd_engine_set_stream(axctd_engine* e, void* cuda_stream);
 /* Number of kernels launched by the engine since creation (for bench.py). */
 int64_t axctd_engine_launch_count(axctd_engine* e);
 
@@ -197,6 +200,23 @@ int64_t axctd_batch_chunks(axctd_batch* b, int drop, axctd_chunk* out, int64_t c
 int64_t axctd_batch_bits(axctd_batch* b, int drop, uint8_t* bits, double* conf, int64_t cap);
 int64_t axctd_batch_edges(axctd_batch* b, int drop, int64_t* edges, double* r400, double* r7500, int64_t cap);
 int64_t axctd_batch_power(axctd_batch* b, int drop, int64_t* power_inds, double* r400, double* r7500, int64_t cap);
+
+/* ---- bench / test tooling (not part of the reference's path) --------------
+ * Device-side twin of synth.py: fills one drop of the batch with a synthetic
+ * AXCTD recording (BASELINE.json configs) without staging it through the host. */
+typedef struct axctd_synth_desc {
+    int64_t n_total, n0, tone_start, fs;
+    uint64_t key1, key2;
+    double nscale, gain, tone_amp;
+    double sin_coef[9];
+    const uint8_t* bits;        /* [nslots] transmitted bit per 1/800 s slot */
+    const uint8_t* gate;        /* [nslots] carrier on/off */
+    const uint8_t* parity;      /* [nslots] parity of the ones before the slot */
+    int64_t nslots;
+} axctd_synth_desc;
+int  axctd_synth_fill(axctd_batch* b, int drop, const axctd_synth_desc* desc);
+/* Copy one drop's PCM device->host (to hand device-generated audio to the CPU baseline). */
+int  axctd_batch_download(axctd_batch* b, int drop, int16_t* pcm, int64_t n);
 
 #ifdef __cplusplus
 }

@@ -38,8 +38,12 @@ def mix64(x: np.ndarray) -> np.ndarray:
     return x ^ (x >> np.uint64(31))
 
 
+def stream_key(seed: int, stream: int) -> int:
+    return (seed * 0x632BE59BD9B4E019 + stream * 0xD1342543DE82EF95 + 0x1234567) & (2 ** 64 - 1)
+
+
 def hash_u64(seed: int, stream: int, idx: np.ndarray) -> np.ndarray:
-    key = np.uint64((seed * 0x632BE59BD9B4E019 + stream * 0xD1342543DE82EF95 + 0x1234567) & (2 ** 64 - 1))
+    key = np.uint64(stream_key(seed, stream))
     with np.errstate(over="ignore"):
         return mix64(mix64(idx.astype(np.uint64) * _GOLD + key) + key)
 

@@ -1,0 +1,93 @@
+"""Shared comparison of an engine result with a golden fixture or an oracle run."""
+import numpy as np
+
+
+def mono(pcm):
+    return np.ascontiguousarray(pcm[:, 0]) if pcm.ndim == 2 else pcm
+
+
+def run_engine(eng, pcm, fs, settings=None, triggerrange=None):
+    cfg = eng.config(fs, settings=settings, triggerrange=triggerrange)
+    b = eng.batch([len(pcm)], [cfg])
+    b.upload(0, pcm)
+    b.run()
+    out = dict(result=b.result(0), bits=b.bits(0), edges=b.edges(0), power=b.power(0), timing=b.timing())
+    b.close()
+    return out
+
+
+def frames_view(res):
+    fr = res.frames
+    kept = fr[fr["keep"] == 1]
+    hexr = ["%08x" % int(w) for w in fr["word"][fr["hex_returned"] == 1]]
+    return kept, hexr
+
+
+def check_against_golden(out, g, level_rtol=1e-9):
+    """Discrete outputs exact; calibrated values 1e-6 relative (north_star)."""
+    res, m = out["result"], g.meta
+    s = res.summary
+    assert s.status == 0, (s.status, s.status_chunk)
+    assert s.n_uncertain == 0
+    assert s.firstpulse400 == m["firstpulse400"] and s.profstartind == m["profstartind"]
+    assert s.numpoints == m["numpoints"]
+    assert abs(s.high_bit_scale - m["high_bit_scale"]) <= 1e-12 * m["high_bit_scale"]
+    bits, conf = out["bits"]
+    edges = out["edges"][0]
+    assert len(bits) == m["n_bits"] and np.array_equal(bits, g.bits), "bitstream"
+    assert len(edges) == m["n_edges"] and np.array_equal(edges, g.edges), "bit edges"
+    tr = g.trace()
+    assert len(tr) == len(res.chunks)
+    for k, (c, t) in enumerate(zip(res.chunks, tr)):
+        got = (c["s"], c["e"], c["status"], c["n_power_total"], c["n_bits"], c["first_edge"], c["last_edge"], c["n_rows"], c["n_hex"])
+        exp = (t["s"], t["e"], t["status"], t["n_power"], t["nbits"], t["first_edge"], t["last_edge"], t["nrows"], t["nhex"])
+        assert got == exp, (k, got, exp)
+    kept, hexr = frames_view(res)
+    assert hexr == g.hexframes, "hex frames"
+    for key, gk in (("time_s", "time"), ("depth", "depth"), ("temperature", "temperature"),
+                    ("conductivity", "conductivity"), ("salinity", "salinity")):
+        assert len(kept[key]) == len(g.z[gk]), gk
+        np.testing.assert_allclose(kept[key], g.z[gk], rtol=1e-6, atol=0, equal_nan=True, err_msg=gk)
+    for key, gk in (("r400", "r400_prof"), ("r7500", "r7500_prof")):
+        np.testing.assert_allclose(kept[key], g.z[gk], rtol=1e-4, atol=0, equal_nan=True, err_msg=gk)
+    p, r400, r7500 = out["power"]
+    assert np.array_equal(p, g.z["power_inds"])
+    np.testing.assert_allclose(r400, g.z["r400"].astype(np.float64), rtol=max(level_rtol, 1e-6 if g.z["r400"].dtype == np.float32 else 0), atol=1e-6 if g.z["r400"].dtype == np.float32 else 1e-11, equal_nan=True)
+    np.testing.assert_allclose(r7500, g.z["r7500"].astype(np.float64), rtol=max(level_rtol, 1e-6 if g.z["r7500"].dtype == np.float32 else 0), atol=1e-6 if g.z["r7500"].dtype == np.float32 else 1e-11, equal_nan=True)
+    if "conf" in g.z.files:
+        np.testing.assert_allclose(conf, g.z["conf"], rtol=1e-9, equal_nan=True)
+    # header metadata (exact)
+    from axctdprocessor_b200.AXCTDprocessor import header_metadata
+    for slot in range(2):
+        key = f"frame_data_{slot + 2}"
+        if key in m["metadata"]:
+            assert s.header_parsed[slot]
+            md = header_metadata(list(s.frame_data[slot]), list(s.counter_found[slot]))
+            assert md["frame_data"] == m["metadata"][key]
+            assert md["counter_found"] == m["metadata"][f"counter_found_{slot + 2}"]
+        else:
+            assert not s.header_parsed[slot]
+    assert list(s.tcoeff_used) == [float(x) for x in m["tcoeff"]]
+    assert list(s.ccoeff_used) == [float(x) for x in m["ccoeff"]]
+    assert list(s.zcoeff_used) == [float(x) for x in m["zcoeff"]]
+
+
+def check_against_oracle(out, op):
+    res = out["result"]
+    s = res.summary
+    assert s.status == 0, (s.status, s.status_chunk)
+    assert s.firstpulse400 == op.firstpulse400 and s.profstartind == op.profstartind
+    assert abs(s.high_bit_scale - op.high_bit_scale) <= 1e-12 * op.high_bit_scale
+    bits, conf = out["bits"]
+    assert np.array_equal(bits, np.asarray(op.all_bits, dtype=np.uint8)), "bitstream"
+    assert np.array_equal(out["edges"][0], np.asarray(op.all_edges, dtype=np.int64)), "bit edges"
+    assert len(res.chunks) == len(op.trace)
+    for c, t in zip(res.chunks, op.trace):
+        assert (c["s"], c["e"], c["status"], c["n_rows"], c["n_hex"]) == (t["s"], t["e"], t["status"], t["nrows"], t["nhex"])
+    kept, hexr = frames_view(res)
+    assert hexr == op.hexframes
+    for key, name in (("time_s", "time"), ("depth", "depth"), ("temperature", "temperature"),
+                      ("conductivity", "conductivity"), ("salinity", "salinity")):
+        np.testing.assert_allclose(kept[key], np.asarray(getattr(op, name), dtype=np.float64), rtol=1e-6, atol=0, equal_nan=True)
+    for key, name in (("r400", "r400_prof"), ("r7500", "r7500_prof")):
+        np.testing.assert_allclose(kept[key], np.asarray(getattr(op, name), dtype=np.float64), rtol=1e-4, atol=0, equal_nan=True)

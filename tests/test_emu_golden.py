@@ -1,0 +1,119 @@
+"""Host logic + kernel bodies (TEST-ONLY host emulation, tests/emu/README.md)
+against fixtures produced by the unmodified reference.  CPU only; the GPU
+versions of these checks are in test_gpu_parity.py."""
+import os
+
+import numpy as np
+import pytest
+
+from emu_util import emu_engine
+from golden_util import SMALL_CASES, Golden
+from parity_util import check_against_golden, mono, run_engine
+
+
+@pytest.fixture(scope="module")
+def eng():
+    e = emu_engine()
+    yield e
+    e.close()
+
+
+@pytest.mark.parametrize("name", SMALL_CASES)
+def test_emulated_engine_matches_reference(eng, name):
+    g = Golden(name)
+    out = run_engine(eng, mono(g.pcm()), g.spec.fs, settings=g.user_settings, triggerrange=g.triggerrange)
+    check_against_golden(out, g)
+
+
+def test_emulated_engine_full_size_config1(eng):
+    g = Golden("config1_720s")
+    out = run_engine(eng, g.pcm(), g.spec.fs)
+    check_against_golden(out, g)
+
+
+def test_chain_repair_loop_converges_to_same_answer():
+    g = Golden("g44_10db")
+    e = emu_engine(inject_misspec=1)
+    out = run_engine(e, g.pcm(), g.spec.fs)
+    assert out["result"].summary.n_chain_fixups >= 1
+    check_against_golden(out, g)
+    e.close()
+
+
+@pytest.mark.parametrize("opts", [dict(force_exact=1), dict(segment_len=4096), dict(exact_head=2048, segment_len=8192)])
+def test_decomposition_invariance(opts):
+    g = Golden("g48_25db")
+    e = emu_engine(**opts)
+    check_against_golden(run_engine(e, g.pcm(), g.spec.fs), g)
+    e.close()
+
+
+def test_device_generator_twin_matches_numpy(eng):
+    import synth
+    spec = synth.DropSpec(fs=48000, duration_s=20.0, seed=31, snr_db=15.0)
+    ref = synth.generate_drop(spec)
+    b = eng.batch([len(ref)], [eng.config(spec.fs)])
+    b.synth_fill(0, spec)
+    assert np.array_equal(b.download(0), ref)
+    b.close()
+
+
+def test_cli_mirror_writes_reference_output_file(eng, tmp_path, capsys):
+    import synth
+    from axctdprocessor_b200 import processAXCTD
+    g = Golden("g44_40db")
+    wav = tmp_path / "g44_40db.wav"
+    synth.write_wav(str(wav), g.pcm(), g.spec.fs)
+    out = tmp_path / "out.txt"
+    settings = {"triggerrange": [30, -1], "minR400": 2.0, "mindR7500": 1.5, "deadfreq": 3000.0, "pointsperloop": 100000,
+                "mark_space_freqs": [400.0, 800.0], "use_bandpass": False}
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        processAXCTD.processAXCTD("g44_40db.wav", str(out), [0, -1], settings, engine=eng)
+    finally:
+        os.chdir(cwd)
+    assert out.read_text() == g.meta["output_text"]
+    assert "Processing profile" in capsys.readouterr().out
+
+
+def test_cli_mirror_reproduces_reference_crashes(eng, tmp_path):
+    import synth
+    from axctdprocessor_b200 import AXCTDprocessor, processAXCTD
+    g = Golden("g44_nopulse")
+    wav = tmp_path / "n.wav"
+    synth.write_wav(str(wav), g.pcm(), g.spec.fs)
+    settings = {"triggerrange": [30, -1], "minR400": 2.0, "mindR7500": 1.5, "deadfreq": 3000.0, "pointsperloop": 100000,
+                "mark_space_freqs": [400.0, 800.0], "use_bandpass": False}
+    with pytest.raises(KeyError, match="zcoeff_default"):          # processAXCTD.py:165 as shipped
+        processAXCTD.processAXCTD(str(wav), str(tmp_path / "o.txt"), [0, -1], settings, engine=eng)
+    assert (tmp_path / "o.txt").read_text().endswith("Conversion equations:\n")      # partial file left behind
+    with pytest.raises(NameError):                                   # AXCTDprocessor.py:66 as shipped
+        AXCTDprocessor.AXCTD_Processor(str(wav), timerange=[5, -1], engine=eng)
+    # wired mode: defaults are printed, flags act
+    processAXCTD.processAXCTD(str(wav), str(tmp_path / "w.txt"), [0, -1], settings, mode="wired", engine=eng)
+    assert "(default)" in (tmp_path / "w.txt").read_text()
+
+
+def test_wired_cli_equals_reference_driven_by_internal_keys(eng, tmp_path):
+    import synth
+    from axctdprocessor_b200 import processAXCTD
+    g = Golden("g44_wired")
+    wav = tmp_path / "w.wav"
+    synth.write_wav(str(wav), g.pcm(), g.spec.fs)
+    us = g.user_settings
+    argv = ["-i", str(wav), "-o", str(tmp_path / "w.txt"), "--wired", "-p", str(us["minr400"]), "-t", str(us["mindr7500"]),
+            "-d", str(us["deadfreq"]), "-l", str(int(us["refreshrate"] * g.spec.fs)), "-a", str(g.triggerrange[0])]
+    import axctdprocessor_b200.AXCTDprocessor as A
+    old = A._default_engines.get(0)
+    A._default_engines[0] = eng
+    try:
+        processAXCTD.main(argv)
+    finally:
+        if old is None:
+            A._default_engines.pop(0, None)
+        else:
+            A._default_engines[0] = old
+    rows = [ln for ln in (tmp_path / "w.txt").read_text().splitlines() if ln[:8].strip().replace(".", "").isdigit() and "," in ln]
+    assert len(rows) == min(g.meta["n_rows"], g.meta["n_hexframes"])
+    assert [r.split(",")[1].strip() for r in rows] == g.hexframes[:len(rows)]
