@@ -82,16 +82,7 @@ AX_HDN inline void ax_stats_fin(const AxWave& w, int64_t d) {
 }
 
 // ------------------------------------------------------------------ filter
-// One biquad of the continuous pass (direct form II transposed as scipy's
-// _sosfilt, but with FMAs: this pass only has to agree with the exact
-// restart to ~1e-16 of peak; decisions inside `guard` of zero are flagged).
-AX_HD double ax_biquad_fma(double x, const double* c, double& z0, double& z1) {
-    double y = ax_fma(c[0], x, z0);
-    z0 = ax_fma(c[1], x, ax_fma(-c[4], y, z1));
-    z1 = ax_fma(c[2], x, -(c[5] * y));
-    return y;
-}
-// scipy/signal/_sosfilt.pyx order, no contraction:
+// scipy/signal/_sosfilt.pyx order, no contraction (used by the exact heads):
 //   y = b0*x + z0 ; z0 = (b1*x - a1*y) + z1 ; z1 = b2*x - a2*y
 AX_HD double ax_biquad_exact(double x, const double* c, double& z0, double& z1) {
     double y = ax_add(ax_mul(c[0], x), z0);
@@ -100,131 +91,193 @@ AX_HD double ax_biquad_exact(double x, const double* c, double& z0, double& z1) 
     return y;
 }
 
-struct AxPending {
-    double snap[AX_PEND][4];
-    int64_t tgt[AX_PEND];
-    int32_t idx[AX_PEND];
-    int n;
-};
-
-// Continuous filter over one segment (with warm-up overlap), emitting every
-// zero crossing i (sign(y[i]) != sign(y[i+1]), demodulate.py:77-79) together
-// with |sum y[i+1..i+npcm] e^{j theta_f m}| for the mark and space tones
-// (demodulate.py:99-102) via re-anchored prefix sums.
-template <int NSEC>
-AX_HDN inline void ax_filter_segment(const AxWave& w, int64_t seg) {
-    const int d = w.seg_drop[seg];
-    const AxDrop& dr = w.drop[d];
-    const AxCfg& c = w.cfg[dr.cfg];
-    AxState& st = w.st[d];
-    const int64_t L = w.seg_len;
-    const int64_t j = seg - dr.seg_base;
-    const int64_t seg_start = j * L;
-    int64_t seg_end = seg_start + L;
-    if (seg_end > dr.n) seg_end = dr.n;
-    int64_t n_begin = seg_start - c.warm;
-    if (n_begin < 0) n_begin = 0;
-    int64_t n_stop = seg_end + c.npcm;       // last window of this segment ends at seg_end-1+npcm
-    if (n_stop > dr.n) n_stop = dr.n;
-    const int16_t* x = w.pcm + dr.pcm_off;
-    const double kmul = st.inv_ampl, kadd = -(st.dc * st.inv_ampl);
-    double cf[NSEC][6];
-    double z[NSEC][2];
-    for (int s = 0; s < NSEC; ++s) {
-        for (int q = 0; q < 6; ++q) cf[s][q] = c.sos[s][q];
-        z[s][0] = 0.0; z[s][1] = 0.0;
+// every section b2 == b0, b1 == +-2*b0, and b0 == 1 except in section 0
+// (scipy.signal.butter(..., output='sos') for low- and band-pass)
+AX_HD bool ax_sos_is_butter(const AxCfg& c) {
+    for (int s = 0; s < c.nsec; ++s) {
+        const double b0 = c.sos[s][0], b1 = c.sos[s][1], b2 = c.sos[s][2];
+        if (b2 != b0 || (b1 != 2.0 * b0 && b1 != -2.0 * b0)) return false;
+        if (s > 0 && b0 != 1.0) return false;
     }
-    const int R = c.rebase, npcm = c.npcm;
-    const double* tab = c.bit_cs;
-    const double guard = w.guard;
-    double C0 = 0, C1 = 0, C2 = 0, C3 = 0;
-    AxPending pe;
-    pe.n = 0;
-    int m = 0, cnt = 0, unc = 0;
-    bool prev_neg = false, have_prev = false;
-    const int64_t slot = seg * (int64_t)w.seg_cap;
-    for (int64_t n = n_begin; n < n_stop; ++n) {
-        double u = ax_fma((double)x[n], kmul, kadd);
+    return true;
+}
+
+// Per-thread state of the continuous filter pass over one segment: the SOS
+// cascade (direct form II transposed as scipy's _sosfilt, with FMAs: this pass
+// only has to agree with the exact zero-state restart to ~1e-16 of peak, and
+// samples inside `guard` of zero are flagged), the zero-crossing detector
+// (demodulate.py:77-79) and, for every crossing i, |sum y[i+1..i+npcm] e^{j theta_f m}|
+// for the mark and space tones (demodulate.py:99-102) from re-anchored prefix sums.
+// BUTTER: 4 double-precision operations per section (5 in section 0, which also
+// absorbs the (x - mean)/max|x| normalisation of AXCTDprocessor.py:57).
+template <int NSEC, bool BUTTER>
+struct AxFilt {
+    double z0[NSEC], z1[NSEC], a1[NSEC], a2[NSEC];
+    double sg[NSEC];                 // BUTTER: b1/b0 = +-2
+    double b0[NSEC], b1[NSEC], b2[NSEC];   // general form
+    double k0, k1;
+    double C0, C1, C2, C3;
+    double snap[AX_PEND][4];
+    int32_t tgt[AX_PEND], idx[AX_PEND];
+    int32_t np, head, next_tgt, m, cnt, unc, R, npcm, cap;   // pending windows: ring in local memory
+    int32_t seg_start, seg_end;
+    bool prev_neg, have_prev;
+    double guard, rot00, rot01, rot10, rot11;
+    int32_t* rec_idx; double* rec_a1; double* rec_a2;
+
+    AX_HD void init(const AxCfg& c, const AxState& st, int32_t s0, int32_t s1, double guard_,
+                    int32_t* ri, double* r1, double* r2, int32_t cap_) {
+        const double kmul = st.inv_ampl, kadd = -(st.dc * st.inv_ampl);
 #pragma unroll
-        for (int s = 0; s < NSEC; ++s) u = ax_biquad_fma(u, cf[s], z[s][0], z[s][1]);
+        for (int s = 0; s < NSEC; ++s) {
+            z0[s] = 0.0; z1[s] = 0.0;
+            a1[s] = c.sos[s][4]; a2[s] = c.sos[s][5];
+            b0[s] = c.sos[s][0]; b1[s] = c.sos[s][1]; b2[s] = c.sos[s][2];
+            sg[s] = (c.sos[s][1] < 0.0) ? -2.0 : 2.0;
+        }
+        if (BUTTER) { k0 = c.sos[0][0] * kmul; k1 = c.sos[0][0] * kadd; } else { k0 = kmul; k1 = kadd; }
+        C0 = C1 = C2 = C3 = 0.0;
+        np = 0; head = 0; next_tgt = 0x7fffffff; m = 0; cnt = 0; unc = 0; R = c.rebase; npcm = c.npcm; cap = cap_;
+        seg_start = s0; seg_end = s1; prev_neg = false; have_prev = false; guard = guard_;
+        rot00 = c.rot[0][0]; rot01 = c.rot[0][1]; rot10 = c.rot[1][0]; rot11 = c.rot[1][1];
+        rec_idx = ri; rec_a1 = r1; rec_a2 = r2;
+    }
+
+    AX_HD double filter(double xd) {
+        if (BUTTER) {
+            double t = ax_fma(xd, k0, k1);
+#pragma unroll
+            for (int s = 0; s < NSEC; ++s) {
+                const double y = t + z0[s];
+                z0[s] = ax_fma(-a1[s], y, ax_fma(sg[s], t, z1[s]));
+                z1[s] = ax_fma(-a2[s], y, t);
+                t = y;
+            }
+            return t;
+        } else {
+            double u = ax_fma(xd, k0, k1);
+#pragma unroll
+            for (int s = 0; s < NSEC; ++s) {
+                const double y = ax_fma(b0[s], u, z0[s]);
+                z0[s] = ax_fma(b1[s], u, ax_fma(-a1[s], y, z1[s]));
+                z1[s] = ax_fma(b2[s], u, -(a2[s] * y));
+                u = y;
+            }
+            return u;
+        }
+    }
+
+    AX_HD void put(int32_t i, double v1, double v2) {
+        if (cnt < cap) { rec_idx[cnt] = i; rec_a1[cnt] = v1; rec_a2[cnt] = v2; }
+        ++cnt;
+    }
+    AX_HD void pop() {
+        head = (head + 1) & (AX_PEND - 1);
+        np--;
+        next_tgt = np > 0 ? tgt[head] : 0x7fffffff;
+    }
+
+    // one sample: n = index within the drop, xd = (double) int16 sample, tab = [R][4] cos/sin table
+    AX_HD void step(int32_t n, double xd, const double* tab) {
+        const double u = filter(xd);
         const bool neg = u < 0.0;
         if (have_prev && neg != prev_neg) {
-            const int64_t i = n - 1;
+            const int32_t i = n - 1;
             if (i >= seg_start && i < seg_end) {
-                if (pe.n == AX_PEND) {       // too many crossings inside one bit window: give up on the oldest
-                    if (cnt < w.seg_cap) { w.rec_idx[slot + cnt] = pe.idx[0]; w.rec_a1[slot + cnt] = ax_nan(); w.rec_a2[slot + cnt] = ax_nan(); }
-                    ++cnt; ++unc;
-                    for (int q = 1; q < AX_PEND; ++q) {
-                        for (int r = 0; r < 4; ++r) pe.snap[q - 1][r] = pe.snap[q][r];
-                        pe.tgt[q - 1] = pe.tgt[q]; pe.idx[q - 1] = pe.idx[q];
-                    }
-                    pe.n--;
-                }
-#pragma unroll
-                for (int q = 0; q < AX_PEND; ++q) if (q == pe.n) {
-                    pe.snap[q][0] = C0; pe.snap[q][1] = C1; pe.snap[q][2] = C2; pe.snap[q][3] = C3;
-                    pe.tgt[q] = i + npcm; pe.idx[q] = (int32_t)i;
-                }
-                pe.n++;
+                if (np == AX_PEND) { put(idx[head], ax_nan(), ax_nan()); ++unc; pop(); }   // cannot happen for a 1200 Hz band limit
+                const int q = (head + np) & (AX_PEND - 1);
+                snap[q][0] = C0; snap[q][1] = C1; snap[q][2] = C2; snap[q][3] = C3;
+                tgt[q] = i + npcm; idx[q] = i;
+                if (np == 0) next_tgt = i + npcm;
+                np++;
             }
         }
         const double* t4 = tab + 4 * m;
         C0 = ax_fma(u, t4[0], C0); C1 = ax_fma(u, t4[1], C1);
         C2 = ax_fma(u, t4[2], C2); C3 = ax_fma(u, t4[3], C3);
-        if (pe.n > 0 && pe.tgt[0] == n) {
-            const double a1 = hypot(C0 - pe.snap[0][0], C1 - pe.snap[0][1]);
-            const double a2 = hypot(C2 - pe.snap[0][2], C3 - pe.snap[0][3]);
-            if (cnt < w.seg_cap) { w.rec_idx[slot + cnt] = pe.idx[0]; w.rec_a1[slot + cnt] = a1; w.rec_a2[slot + cnt] = a2; }
-            ++cnt;
-#pragma unroll
-            for (int q = 1; q < AX_PEND; ++q) {
-                for (int r = 0; r < 4; ++r) pe.snap[q - 1][r] = pe.snap[q][r];
-                pe.tgt[q - 1] = pe.tgt[q]; pe.idx[q - 1] = pe.idx[q];
-            }
-            pe.n--;
+        if (next_tgt == n) {
+            put(idx[head], hypot(C0 - snap[head][0], C1 - snap[head][1]), hypot(C2 - snap[head][2], C3 - snap[head][3]));
+            pop();
         }
-        if (n >= seg_start && n < seg_end && fabs(u) < guard) ++unc;
+        if (fabs(u) < guard && n >= seg_start && n < seg_end) ++unc;
         if (++m == R) {
             // re-anchor the phase reference: snap' = -(C - snap) * e^{-j theta R}; C = 0
-#pragma unroll
-            for (int q = 0; q < AX_PEND; ++q) if (q < pe.n) {
-                double pr = C0 - pe.snap[q][0], pi = C1 - pe.snap[q][1];
-                pe.snap[q][0] = -(pr * c.rot[0][0] - pi * c.rot[0][1]);
-                pe.snap[q][1] = -(pr * c.rot[0][1] + pi * c.rot[0][0]);
-                pr = C2 - pe.snap[q][2]; pi = C3 - pe.snap[q][3];
-                pe.snap[q][2] = -(pr * c.rot[1][0] - pi * c.rot[1][1]);
-                pe.snap[q][3] = -(pr * c.rot[1][1] + pi * c.rot[1][0]);
+            for (int k = 0; k < np; ++k) {
+                const int q = (head + k) & (AX_PEND - 1);
+                double pr = C0 - snap[q][0], pi = C1 - snap[q][1];
+                snap[q][0] = -(pr * rot00 - pi * rot01);
+                snap[q][1] = -(pr * rot01 + pi * rot00);
+                pr = C2 - snap[q][2]; pi = C3 - snap[q][3];
+                snap[q][2] = -(pr * rot10 - pi * rot11);
+                snap[q][3] = -(pr * rot11 + pi * rot10);
             }
             C0 = C1 = C2 = C3 = 0.0;
             m = 0;
         }
         prev_neg = neg; have_prev = true;
     }
+
     // windows that run past the end of the recording can never be demodulated
-    for (int q = 0; q < pe.n; ++q) {
-        if (cnt < w.seg_cap) { w.rec_idx[slot + cnt] = pe.idx[q]; w.rec_a1[slot + cnt] = ax_nan(); w.rec_a2[slot + cnt] = ax_nan(); }
-        ++cnt;
+    AX_HD void finish() {
+        while (np > 0) { put(idx[head], ax_nan(), ax_nan()); pop(); }
     }
-    if (cnt > w.seg_cap) { w.flags[AX_FLAG_CAP] = 1; cnt = w.seg_cap; }
-    w.seg_cnt[seg] = cnt;
-    if (unc) AX_ATOMIC_ADD32(&st.n_uncertain, unc);
+};
+
+struct AxSegGeom { int64_t seg_start, seg_end, n_begin, n_stop; };
+AX_HD AxSegGeom ax_seg_geom(const AxDrop& dr, const AxCfg& c, int64_t L, int64_t j) {
+    AxSegGeom g;
+    g.seg_start = j * L;
+    g.seg_end = g.seg_start + L; if (g.seg_end > dr.n) g.seg_end = dr.n;
+    g.n_begin = g.seg_start - c.warm; if (g.n_begin < 0) g.n_begin = 0;
+    g.n_stop = g.seg_end + c.npcm; if (g.n_stop > dr.n) g.n_stop = dr.n;      // last window of the segment ends at seg_end-1+npcm
+    return g;
+}
+
+template <int NSEC, bool BUTTER>
+AX_HDN inline void ax_filter_segment(const AxWave& w, int64_t seg) {
+    const int d = w.seg_drop[seg];
+    const AxDrop& dr = w.drop[d];
+    const int64_t j = seg - dr.seg_base;
+    if (j >= dr.nseg) { w.seg_cnt[seg] = 0; return; }
+    const AxCfg& c = w.cfg[dr.cfg];
+    AxState& st = w.st[d];
+    const AxSegGeom g = ax_seg_geom(dr, c, w.seg_len, j);
+    const int16_t* x = w.pcm + dr.pcm_off;
+    const int64_t slot = seg * (int64_t)w.seg_cap;
+    AxFilt<NSEC, BUTTER> f;
+    f.init(c, st, (int32_t)g.seg_start, (int32_t)g.seg_end, w.guard, w.rec_idx + slot, w.rec_a1 + slot, w.rec_a2 + slot, w.seg_cap);
+    for (int64_t n = g.n_begin; n < g.n_stop; ++n) f.step((int32_t)n, (double)x[n], c.bit_cs);
+    f.finish();
+    if (f.cnt > w.seg_cap) { w.flags[AX_FLAG_CAP] = 1; f.cnt = w.seg_cap; }
+    w.seg_cnt[seg] = f.cnt;
+    if (f.unc) AX_ATOMIC_ADD32(&st.n_uncertain, f.unc);
 }
 
 AX_HDN inline void ax_filter_item(const AxWave& w, int64_t seg) {
-    const int nsec = w.cfg[w.drop[w.seg_drop[seg]].cfg].nsec;
-    if (nsec == 3) ax_filter_segment<3>(w, seg);
-    else if (nsec == 6) ax_filter_segment<6>(w, seg);
-    else if (nsec == 1) ax_filter_segment<1>(w, seg);
-    else if (nsec == 2) ax_filter_segment<2>(w, seg);
-    else if (nsec == 4) ax_filter_segment<4>(w, seg);
-    else ax_filter_segment<5>(w, seg);
+    const AxCfg& c = w.cfg[w.drop[w.seg_drop[seg]].cfg];
+    const bool bt = ax_sos_is_butter(c);
+    if (c.nsec == 3) { if (bt) ax_filter_segment<3, true>(w, seg); else ax_filter_segment<3, false>(w, seg); }
+    else if (c.nsec == 6) { if (bt) ax_filter_segment<6, true>(w, seg); else ax_filter_segment<6, false>(w, seg); }
+    else if (c.nsec == 1) ax_filter_segment<1, false>(w, seg);
+    else if (c.nsec == 2) ax_filter_segment<2, false>(w, seg);
+    else if (c.nsec == 4) ax_filter_segment<4, false>(w, seg);
+    else ax_filter_segment<5, false>(w, seg);
+}
+
+// exclusive scan of the crossing counts, stage 1: inside blocks of 128 segments
+AX_HDN inline void ax_scan_block_item(const AxWave& w, int64_t blk) {
+    int64_t off = 0;
+    const int64_t s0 = blk * 128;
+    for (int q = 0; q < 128; ++q) { w.seg_off[s0 + q] = off; off += w.seg_cnt[s0 + q]; }
+    w.blk_sum[blk] = off;
 }
 
 // exclusive scan of the per-segment crossing counts of one drop
 AX_HDN inline void ax_scan_item(const AxWave& w, int64_t d) {
     const AxDrop& dr = w.drop[d];
-    int64_t off = 0;
-    for (int s = 0; s < dr.nseg; ++s) { w.seg_off[dr.seg_base + s] = off; off += w.seg_cnt[dr.seg_base + s]; }
+    int64_t off = 0;                                   // stage 2: across the drop's blocks (seg_base is a multiple of 128)
+    const int nblk = (dr.nseg + 127) / 128, b0 = dr.seg_base / 128;
+    for (int q = 0; q < nblk; ++q) { const int64_t t = w.blk_sum[b0 + q]; w.blk_sum[b0 + q] = off; off += t; }
     w.st[d].zc_count = off;
     if (off > dr.zc_cap) { w.flags[AX_FLAG_CAP] = 1; w.st[d].zc_count = 0; ax_raise(w.st[d], AXCTD_DROP_CAPACITY, -1); }
 }
@@ -233,7 +286,7 @@ AX_HDN inline void ax_compact_item(const AxWave& w, int64_t seg) {
     const int d = w.seg_drop[seg];
     const AxDrop& dr = w.drop[d];
     if (w.st[d].zc_count == 0) return;
-    const int64_t src = seg * (int64_t)w.seg_cap, dst = dr.zc_base + w.seg_off[seg];
+    const int64_t src = seg * (int64_t)w.seg_cap, dst = dr.zc_base + w.seg_off[seg] + w.blk_sum[seg / 128];
     const int cnt = w.seg_cnt[seg];
     for (int q = 0; q < cnt; ++q) {
         w.zc_idx[dst + q] = w.rec_idx[src + q];
@@ -259,47 +312,116 @@ AX_HD int64_t ax_next(const int32_t* zi, int64_t pos, int64_t fs2, int64_t br2) 
     return pos + 1 + bj;
 }
 
-// tile_tab[(tile*4 + o)]: walk entering tile at offset o leaves it at offset
-// (tab & 3) of the next tile after (tab >> 2) steps; 0xFFFF = not available.
-AX_HDN inline void ax_tiles_item(const AxWave& w, int64_t item) {
-    const int64_t tg = item >> 2;
-    const int o = (int)(item & 3);
+// zc_nx[c] = ax_next(c) - c (1..4), 0 where the walk cannot step (fewer than four crossings follow)
+AX_HDN inline void ax_nx_item(const AxWave& w, int64_t zg) {
+    const int d = ax_find_owner(w.drop, w.n_drops, &AxDrop::zc_base, zg);
+    const AxDrop& dr = w.drop[d];
+    const int64_t pos = zg - dr.zc_base;
+    const int64_t M = w.st[d].zc_count;
+    if (pos >= M) return;
+    const AxCfg& c = w.cfg[dr.cfg];
+    w.zc_nx[zg] = (pos + 4 < M) ? (uint8_t)(ax_next(w.zc_idx + dr.zc_base, pos, c.fs2, 2 * (int64_t)c.bitrate) - pos) : (uint8_t)0;
+}
+
+// Per tile of AX_TILE crossings:
+//   zc_exit[c]       walk from crossing c leaves its tile at offset (x & 3) of the next tile after
+//                    (x >> 2) + 1 steps; 0xFF = not available
+//   tile_mask[t][o]  bit i set <=> crossing t*AX_TILE+i is visited by the walk entering the tile at offset o (0..3)
+AX_HDN inline void ax_tiles_item(const AxWave& w, int64_t tg) {
     const int d = ax_find_owner(w.drop, w.n_drops, &AxDrop::tile_base, tg);
     const AxDrop& dr = w.drop[d];
     const int64_t t = tg - dr.tile_base;
     if (t >= dr.tile_cap) return;
-    const AxCfg& c = w.cfg[dr.cfg];
     const int64_t M = w.st[d].zc_count;
-    const int32_t* zi = w.zc_idx + dr.zc_base;
-    int64_t pos = t * AX_TILE + o;
-    const int64_t limit = (t + 1) * AX_TILE;
-    int cnt = 0;
-    bool ok = pos < M;
-    while (ok && pos < limit) {
-        if (pos + 4 >= M) { ok = false; break; }
-        pos = ax_next(zi, pos, c.fs2, 2 * (int64_t)c.bitrate);
-        ++cnt;
+    const int64_t first = t * AX_TILE;
+    if (first >= M) return;
+    const uint8_t* nx = w.zc_nx + dr.zc_base;
+    uint8_t* ex = w.zc_exit + dr.zc_base;
+    const int64_t limit = first + AX_TILE;
+    const int64_t last = (limit < M ? limit : M) - 1;
+    for (int64_t c = last; c >= first; --c) {
+        const int stp = nx[c];
+        uint8_t v = 0xFF;
+        if (stp) {
+            const int64_t nxt = c + stp;
+            if (nxt >= limit) v = (uint8_t)(nxt - limit);
+            else if (ex[nxt] != 0xFF && (ex[nxt] >> 2) < 62) v = (uint8_t)(ex[nxt] + 4);      // one more step, same exit
+        }
+        ex[c] = v;
     }
-    w.tile_tab[tg * 4 + o] = ok ? (uint16_t)((pos - limit) | (cnt << 2)) : (uint16_t)0xFFFF;
+    for (int o = 0; o < 4; ++o) {
+        uint64_t mask = 0;
+        int64_t c = first + o;
+        while (c < limit && c < M) {
+            mask |= 1ull << (c - first);
+            if (!nx[c]) break;
+            c += nx[c];
+        }
+        w.tile_mask[tg * 4 + o] = mask;
+    }
+}
+
+AX_HD int ax_popc64(uint64_t v) {
+#ifdef __CUDA_ARCH__
+    return __popcll(v);
+#else
+    return __builtin_popcountll(v);
+#endif
+}
+AX_HD int ax_ctz64(uint64_t v) {
+#ifdef __CUDA_ARCH__
+    return __ffsll((long long)v) - 1;
+#else
+    return __builtin_ctzll(v);
+#endif
 }
 
 // Follow the walk from `pos` while pos <= qstop-5 (demodulate.py:90:
-// `while c < len(zerocrossings)-5`); returns the final ordinal.
-AX_HD int64_t ax_walk_end(const int32_t* zi, const uint16_t* tab, int64_t pos, int64_t qstop,
-                          int64_t fs2, int64_t br2, int64_t* steps) {
+// `while c < len(zerocrossings)-5`); returns the final ordinal and the number of steps.
+AX_HD int64_t ax_walk_end(const uint8_t* nx, const uint8_t* ex, const uint64_t* tmask, int64_t pos, int64_t qstop,
+                          int64_t* steps) {
     int64_t st = 0;
-    while (pos <= qstop - 5) {
-        const int64_t t = pos / AX_TILE;
-        const int o = (int)(pos - t * AX_TILE);
-        if (o < 4 && (t + 1) * AX_TILE - 1 <= qstop - 5) {
-            const uint16_t e = tab[t * 4 + o];
-            if (e != 0xFFFF) { st += e >> 2; pos = (t + 1) * AX_TILE + (e & 3); continue; }
+    const int64_t X = qstop - 4;                       // the walk stops at the first visited ordinal >= X
+    while (pos < X) {
+        const int64_t t = pos / AX_TILE, first = t * AX_TILE, limit = first + AX_TILE;
+        if (limit <= X) {                              // the stop point lies beyond this tile: leave it in one go
+            const uint8_t e = ex[pos];
+            if (e != 0xFF) { st += (e >> 2) + 1; pos = limit + (e & 3); continue; }
+        } else if (pos - first < 4) {                  // stop point inside this tile, entered at an offset with a mask
+            const uint64_t mask = tmask[t * 4 + (pos - first)];
+            const uint64_t ahead = mask & ~((1ull << (X - first)) - 1ull);
+            if (ahead) {
+                const int tb = ax_ctz64(ahead);
+                st += ax_popc64(mask & ((2ull << tb) - 1ull)) - 1;
+                pos = first + tb;
+                break;
+            }
+            const uint8_t e = ex[pos];
+            if (e != 0xFF) { st += (e >> 2) + 1; pos = limit + (e & 3); continue; }
         }
-        pos = ax_next(zi, pos, fs2, br2);
+        pos += nx[pos];                                // (nx > 0 is guaranteed while pos <= qstop-5)
         ++st;
     }
     *steps = st;
     return pos;
+}
+
+// first index in [0,n) with a[i] > v, searching outward from a guess
+AX_HD int64_t ax_upper_bound_from(const int32_t* a, int64_t n, int64_t v, int64_t guess) {
+    if (n <= 0) return 0;
+    if (guess < 0) guess = 0;
+    if (guess > n - 1) guess = n - 1;
+    int64_t lo, hi;                                    // invariant: a[lo-1] <= v (or lo == 0), a[hi] > v (or hi == n)
+    if ((int64_t)a[guess] <= v) {
+        int64_t step = 1; lo = guess + 1; hi = lo;
+        while (hi < n && (int64_t)a[hi] <= v) { lo = hi + 1; hi += step; step <<= 1; }
+        if (hi > n) hi = n;
+    } else {
+        int64_t step = 1; hi = guess; lo = guess;
+        while (lo > 0 && (int64_t)a[lo - 1] > v) { hi = lo - 1; lo -= step; step <<= 1; if (lo < 0) lo = 0; }
+    }
+    while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if ((int64_t)a[mid] <= v) lo = mid + 1; else hi = mid; }
+    return lo;
 }
 
 // ------------------------------------------------------------------ chunk chain
@@ -312,27 +434,33 @@ AX_HDN inline void ax_chain_item(const AxWave& w, int64_t d) {
     const AxCfg& c = w.cfg[dr.cfg];
     AxChunk* ch = w.chunk + dr.chunk_base;
     const int32_t* zi = w.zc_idx + dr.zc_base;
-    const uint16_t* tab = w.tile_tab + (int64_t)dr.tile_base * 4;
+    const uint8_t* nx = w.zc_nx + dr.zc_base;
+    const uint8_t* ex = w.zc_exit + dr.zc_base;
+    const uint64_t* tmask = w.tile_mask + (int64_t)dr.tile_base * 4;
     const int64_t M = st.zc_count;
     int k = st.chain_from;
     int64_t s;
     if (k == st.k0) s = ch[k].s;
     else s = ch[k - 1].true_last - 1 - c.pad;          // s + (last_edge - 1) - pad
+    int64_t entry = -1, span = (int64_t)c.chunk_len / 37;
     for (;; ++k) {
         if (dr.n - s < 4 * (int64_t)c.n_power) { st.n_chunks = k; break; }          // :295
         if (k >= dr.chunk_cap) { ax_raise(st, AXCTD_DROP_CAPACITY, k); w.flags[AX_FLAG_CAP] = 1; st.n_chunks = k; break; }
         int64_t e = s + c.chunk_len;                                               // :293
         if (e >= dr.n) e = dr.n - 1;                                               // :299-300
         ch[k].s = s; ch[k].e = e; ch[k].err = 0; ch[k].n_edges = 0; ch[k].spec_last = -1;
-        const int64_t entry = ax_lower_bound(zi, M, s + c.pad);
-        const int64_t q = ax_upper_bound(zi, M, e - 2) - 1;
+        if (entry < 0) entry = ax_lower_bound(zi, M, s + c.pad);
+        const int64_t q = ax_upper_bound_from(zi, M, e - 2, entry + span) - 1;
         if (entry > q) { st.n_chunks = k + 1; break; }
+        span = q - entry;
         int64_t steps;
-        const int64_t pos = ax_walk_end(zi, tab, entry, q, c.fs2, 2 * (int64_t)c.bitrate, &steps);
+        const int64_t pos = ax_walk_end(nx, ex, tmask, entry, q, &steps);
         ch[k].spec_last = zi[pos];
         const int64_t next_ind = zi[pos] - s - 1;                                  // demodulate.py:104
         if (next_ind <= c.pad) { st.n_chunks = k + 1; break; }                     // :330-331 handled by verify
         s = s + next_ind - c.pad;                                                  // :329
+        // next entry: first crossing with index >= s + pad = zi[pos] - 1
+        entry = (pos > 0 && (int64_t)zi[pos - 1] >= (int64_t)zi[pos] - 1) ? pos - 1 : pos;
     }
 }
 
@@ -377,7 +505,9 @@ AX_HDN inline void ax_head_item(const AxWave& w, int64_t cg) {
     }
     if (overflow) { ch.err = AXCTD_DROP_CAPACITY; return; }
     const int32_t* zi = w.zc_idx + dr.zc_base;
-    const uint16_t* tab = w.tile_tab + (int64_t)dr.tile_base * 4;
+    const uint8_t* nx = w.zc_nx + dr.zc_base;
+    const uint8_t* ex = w.zc_exit + dr.zc_base;
+    const uint64_t* tmask = w.tile_mask + (int64_t)dr.tile_base * 4;
     const int64_t M = st.zc_count;
     int64_t g0 = 0, q = -1, nc = 0;
     if (H < len) {
@@ -414,7 +544,7 @@ AX_HDN inline void ax_head_item(const AxWave& w, int64_t cg) {
         const int64_t pos = g0 + (cpos - nh);
         ch.g_first = pos;
         int64_t steps;
-        const int64_t endpos = ax_walk_end(zi, tab, pos, q, c.fs2, br2, &steps);
+        const int64_t endpos = ax_walk_end(nx, ex, tmask, pos, q, &steps);
         nedges += steps + 1;
         last = zi[endpos];
     }

@@ -62,11 +62,15 @@ AX_GLOBAL void k_inject(int64_t n, AxWave w) {     // test hook: pretend the fir
 AX_GLOBAL void k_stats(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_stats_item(w, item); }
 AX_GLOBAL void k_stats_fin(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_stats_fin(w, item); }
 AX_GLOBAL void k_filter(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_filter_item(w, item); }
+AX_GLOBAL void k_scan_block(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_scan_block_item(w, item); }
 AX_GLOBAL void k_scan(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_scan_item(w, item); }
 AX_GLOBAL void k_compact(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_compact_item(w, item); }
+AX_GLOBAL void k_nx(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_nx_item(w, item); }
 AX_GLOBAL void k_tiles(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_tiles_item(w, item); }
 AX_GLOBAL void k_plan0(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_plan0_item(w, item); }
 AX_GLOBAL void k_tone_direct(int64_t n, AxWave w, int phase_b) { AX_FOR_ITEM(n) ax_tone_direct_item(w, item, phase_b); }
+AX_GLOBAL void k_pwfill(int64_t n, AxWave w, int phase_b) { AX_FOR_ITEM(n) ax_pwfill_item(w, item, phase_b); }
+AX_GLOBAL void k_levels(int64_t n, AxWave w, int phase_b) { AX_FOR_ITEM(n) ax_levels_item(w, item, phase_b); }
 AX_GLOBAL void k_sm(int64_t n, AxWave w, int phase_b) { AX_FOR_ITEM(n) ax_sm_item(w, item, phase_b); }
 AX_GLOBAL void k_chain(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_chain_item(w, item); }
 AX_GLOBAL void k_heads(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_head_item(w, item); }
@@ -77,6 +81,8 @@ AX_GLOBAL void k_emit(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_emit_item(w, item
 AX_GLOBAL void k_scale(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_scale_item(w, item); }
 AX_GLOBAL void k_bits(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_bits_item(w, item); }
 AX_GLOBAL void k_headers(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_header_item(w, item); }
+AX_GLOBAL void k_pack(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_pack_item(w, item); }
+AX_GLOBAL void k_valid(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_valid_item(w, item); }
 AX_GLOBAL void k_frames(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_frames_item(w, item); }
 AX_GLOBAL void k_calib(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_calib_item(w, item); }
 AX_GLOBAL void k_synth(int64_t n, AxSynth g) { AX_FOR_ITEM(n) ax_synth_item(g, item); }
@@ -344,6 +350,7 @@ extern "C" int axctd_batch_create(axctd_engine* e, int n_drops, const int64_t* n
     if (e->opt_force_exact) { ybuf_max = chunk_len_max + 8; head_cap_max = chunk_len_max / 4 + 64; }
     // segment length of the continuous pass: enough threads to fill the GPU, little warm-up waste
     int64_t L = e->opt_segment_len;
+    if (L > 0) L = ((L + 63) / 64) * 64;
     if (L <= 0) {
         L = 32768;
         while (L > 2048 && total / L < 262144) L >>= 1;
@@ -363,12 +370,12 @@ extern "C" int axctd_batch_create(axctd_engine* e, int n_drops, const int64_t* n
         const int64_t n = n_samples[d];
         dr.pcm_off = pcm_off; dr.n = n; dr.cfg = config_id[d];
         pcm_off += ((n + 63) / 64) * 64 + 64;
-        dr.seg_base = seg_off; dr.nseg = (int32_t)((n + L - 1) / L); seg_off += dr.nseg;
+        dr.seg_base = seg_off; dr.nseg = (int32_t)((n + L - 1) / L); seg_off += ((dr.nseg + 127) / 128) * 128;
         dr.slab_base = slab_off; dr.nslab = (int32_t)((n + AX_STAT_SLAB - 1) / AX_STAT_SLAB); slab_off += dr.nslab;
         dr.zc_base = zc_off; dr.zc_cap = n / e->opt_zc_div + 4096; zc_off += dr.zc_cap + 8;
         dr.tile_base = tile_off; dr.tile_cap = (int32_t)(dr.zc_cap / AX_TILE + 1); tile_off += dr.tile_cap;
         dr.chunk_base = chunk_off; dr.chunk_cap = (int32_t)(2 * (n / c.chunk_len) + 16); chunk_off += dr.chunk_cap;
-        dr.edge_base = edge_off; dr.edge_cap = n / 24 + 8 * (int64_t)dr.chunk_cap; edge_off += dr.edge_cap + 64;
+        dr.edge_base = edge_off; dr.edge_cap = n / 24 + 8 * (int64_t)dr.chunk_cap; edge_off += ((dr.edge_cap + 64 + 63) / 64) * 64;
         dr.pw_base = pw_off; dr.pw_cap = (int32_t)(n / c.d_pcm + 2 * (int64_t)dr.chunk_cap + 8); pw_off += dr.pw_cap;
         dr.frame_base = frame_off; dr.frame_cap = (int32_t)(dr.edge_cap / 32 + 64); frame_off += dr.frame_cap;
     }
@@ -377,7 +384,7 @@ extern "C" int axctd_batch_create(axctd_engine* e, int n_drops, const int64_t* n
     w.nseg_total = seg_off; w.nslab_total = slab_off; w.pw_total = pw_off;
     std::vector<int32_t> seg_drop(seg_off), slab_drop(slab_off);
     for (int d = 0; d < n_drops; ++d) {
-        for (int s = 0; s < b->drops[d].nseg; ++s) seg_drop[b->drops[d].seg_base + s] = d;
+        for (int s = 0; s < ((b->drops[d].nseg + 127) / 128) * 128; ++s) seg_drop[b->drops[d].seg_base + s] = d;
         for (int s = 0; s < b->drops[d].nslab; ++s) slab_drop[b->drops[d].slab_base + s] = d;
     }
     int bad = 0;
@@ -389,6 +396,7 @@ extern "C" int axctd_batch_create(axctd_engine* e, int n_drops, const int64_t* n
     bad |= ax_alloc_arr(b, &d_slab_drop, slab_off);
     bad |= ax_alloc_arr(b, &w.seg_cnt, seg_off);
     bad |= ax_alloc_arr(b, &w.seg_off, seg_off);
+    bad |= ax_alloc_arr(b, &w.blk_sum, seg_off / 128 + 1);
     const int64_t rec_total = (int64_t)seg_off * w.seg_cap;
     bad |= ax_alloc_arr(b, &w.rec_idx, rec_total);
     bad |= ax_alloc_arr(b, &w.rec_a1, rec_total);
@@ -396,7 +404,9 @@ extern "C" int axctd_batch_create(axctd_engine* e, int n_drops, const int64_t* n
     bad |= ax_alloc_arr(b, &w.zc_idx, zc_off);
     bad |= ax_alloc_arr(b, &w.zc_a1, zc_off);
     bad |= ax_alloc_arr(b, &w.zc_a2, zc_off);
-    bad |= ax_alloc_arr(b, &w.tile_tab, (int64_t)tile_off * 4);
+    bad |= ax_alloc_arr(b, &w.zc_nx, zc_off);
+    bad |= ax_alloc_arr(b, &w.zc_exit, zc_off);
+    bad |= ax_alloc_arr(b, &w.tile_mask, (int64_t)tile_off * 4);
     bad |= ax_alloc_arr(b, &w.chunk, chunk_off);
     bad |= ax_alloc_arr(b, &w.head_idx, (int64_t)chunk_off * head_cap_max);
     bad |= ax_alloc_arr(b, &w.head_a1, (int64_t)chunk_off * head_cap_max);
@@ -415,6 +425,8 @@ extern "C" int axctd_batch_create(axctd_engine* e, int n_drops, const int64_t* n
     bad |= ax_alloc_arr(b, &w.a1, edge_off);
     bad |= ax_alloc_arr(b, &w.a2, edge_off);
     bad |= ax_alloc_arr(b, &w.conf, edge_off);
+    bad |= ax_alloc_arr(b, &w.bitw, edge_off / 32 + 4);
+    bad |= ax_alloc_arr(b, &w.validw, edge_off / 32 + 4);
     bad |= ax_alloc_arr(b, &w.frame, frame_off);
     bad |= ax_alloc_arr(b, &b->d_qc, 2 * (int64_t)frame_off + 16);
     bad |= ax_alloc_arr(b, &w.flags, 8);
@@ -554,18 +566,52 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
 #endif
     AX_LAUNCH(e, k_stats_fin, n, w);
     AX_EVENT(b, 1);
-    AX_LAUNCH(e, k_filter, (int64_t)w.nseg_total, w);
+#ifndef AXCTD_EMU
+    if (e->opt_filter_variant == 0) {
+        // staged kernel: one instantiation per (sections, form) in use; CTAs of other configs exit at once
+        int rebase_max = 1;
+        bool need[4] = {false, false, false, false};      // <3,butter> <6,butter> <3,general> <6,general>
+        bool generic = false;
+        for (const AxDrop& dr : b->drops) {
+            const AxCfg& c = e->cfgs[dr.cfg];
+            rebase_max = std::max(rebase_max, c.rebase);
+            const bool bt = ax_sos_is_butter(c);
+            if (c.nsec == 3) need[bt ? 0 : 2] = true; else if (c.nsec == 6) need[bt ? 1 : 3] = true; else generic = true;
+        }
+        if (generic || (size_t)rebase_max * 32 > 96 * 1024) { AX_LAUNCH(e, k_filter, (int64_t)w.nseg_total, w); }
+        else {
+            if (need[0]) { ax_launch_filter_variant<3, true>(w, rebase_max, e->stream); e->launches++; }
+            if (need[1]) { ax_launch_filter_variant<6, true>(w, rebase_max, e->stream); e->launches++; }
+            if (need[2]) { ax_launch_filter_variant<3, false>(w, rebase_max, e->stream); e->launches++; }
+            if (need[3]) { ax_launch_filter_variant<6, false>(w, rebase_max, e->stream); e->launches++; }
+        }
+    } else
+#endif
+    { AX_LAUNCH(e, k_filter, (int64_t)w.nseg_total, w); }
     AX_EVENT(b, 2);
+    AX_LAUNCH(e, k_scan_block, (int64_t)w.nseg_total / 128, w);
     AX_LAUNCH(e, k_scan, n, w);
     AX_LAUNCH(e, k_compact, (int64_t)w.nseg_total, w);
-    AX_LAUNCH(e, k_tiles, b->tile_total * 4, w);
+    AX_LAUNCH(e, k_nx, b->zc_total, w);
+    AX_LAUNCH(e, k_tiles, b->tile_total, w);
     AX_LAUNCH(e, k_plan0, n, w);
+    AX_LAUNCH(e, k_pwfill, b->chunk_total, w, 0);
     AX_EVENT(b, 3);
-    ax_run_tones(b, 0);
-    AX_EVENT(b, 4);
-    AX_LAUNCH(e, k_sm, n, w, 0);
-    // chunk chain: predict, recompute heads exactly, verify; repeat while repairs happen
     int32_t flags[8];
+    // 400 Hz pulse search on the fixed chunk grid, in rounds of chunks (most drops need one round)
+    for (int lo = 0, hi = 8;; lo = hi, hi = hi * 4) {
+        w.pa_lo = lo; w.pa_hi = hi;
+        ax_run_tones(b, 0);
+        AX_LAUNCH(e, k_levels, (int64_t)w.pw_total, w, 0);
+        AX_LAUNCH(e, k_sm, n, w, 0);
+        if (ax_d2h(e, flags, w.flags, sizeof(flags)) || ax_sync(e)) return AXCTD_ERR_CUDA;
+        if (!flags[AX_FLAG_MORE]) break;
+        flags[AX_FLAG_MORE] = 0;
+        if (ax_h2d(e, w.flags, flags, sizeof(flags))) return AXCTD_ERR_CUDA;
+        if (hi > (1 << 28)) break;
+    }
+    AX_EVENT(b, 4);
+    // chunk chain: predict, recompute heads exactly, verify; repeat while repairs happen
     for (int it = 0;; ++it) {
         AX_LAUNCH(e, k_chain, n, w);
         if (e->opt_inject_misspec && it == 0) AX_LAUNCH(e, k_inject, n, w);
@@ -577,18 +623,25 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
         if (ax_zero(e, w.flags, sizeof(int32_t))) return AXCTD_ERR_CUDA;
     }
     AX_LAUNCH(e, k_plan_tones, n, w);
+    AX_LAUNCH(e, k_pwfill, b->chunk_total, w, 1);
     ax_run_tones(b, 1);
+    AX_LAUNCH(e, k_levels, (int64_t)w.pw_total, w, 1);
     AX_LAUNCH(e, k_sm, n, w, 1);
     AX_LAUNCH(e, k_offsets, n, w);
     AX_LAUNCH(e, k_emit, b->chunk_total, w);
     AX_LAUNCH(e, k_scale, n, w);
-    AX_LAUNCH(e, k_bits, b->chunk_total, w);
+    AX_LAUNCH(e, k_bits, b->edge_total, w);
     AX_LAUNCH(e, k_headers, 2 * (int64_t)n, w);
     // header text -> calibration coefficients on the host (python float semantics)
     if (ax_d2h(e, b->st.data(), w.st, sizeof(AxState) * n) || ax_sync(e)) return AXCTD_ERR_CUDA;
     for (int d = 0; d < n; ++d) ax_merge_headers(e->cfgs[b->drops[d].cfg], b->st[d], b->summary[d]);
     if (ax_h2d(e, w.st, b->st.data(), sizeof(AxState) * n)) return AXCTD_ERR_CUDA;
-    AX_LAUNCH(e, k_frames, n, w);
+    AX_LAUNCH(e, k_pack, b->edge_total / 32, w);
+    AX_LAUNCH(e, k_valid, b->edge_total / 32, w);
+#ifndef AXCTD_EMU
+    if (e->opt_filter_variant == 0) { ax_launch_frames_warp(w, e->stream); e->launches++; } else
+#endif
+    { AX_LAUNCH(e, k_frames, n, w); }
     AX_LAUNCH(e, k_calib, b->frame_total, w);
     AX_LAUNCH(e, k_qc, b->chunk_total, w, b->d_qc);
     AX_EVENT(b, 5);

@@ -61,13 +61,116 @@ static inline void ax_launch_stats(const AxWave& w, cudaStream_t stream) {
     if (w.nslab_total > 0) k_stats_coalesced<<<w.nslab_total, 256, 0, stream>>>(w);
 }
 
+// ------------------------------------------------------------------ filter (staged)
+// One thread per segment, as ax_filter_segment, but the int16 samples reach the
+// threads through shared memory: each warp copies, with 16-byte cp.async, one
+// full 128-byte line (64 samples) per thread per stage, double buffered, and
+// every thread then reads its own row with conflict-free 128-bit LDS.  The
+// cos/sin table of the bit windows sits in shared memory as well (one config
+// per CTA: segment ranges are padded to multiples of 128 per drop).
+#define AX_FS_THREADS 128
+#define AX_FS_ROW 72                                  // 64 samples + 8 pad (144-byte row stride)
+#define AX_FS_STAGE (4 * 32 * AX_FS_ROW)              // int16 elements per stage
+
+__device__ __forceinline__ void ax_cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void ax_cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void ax_cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+template <int NSEC, bool BUTTER>
+__global__ void __launch_bounds__(AX_FS_THREADS) k_filter_staged(AxWave w) {
+    extern __shared__ __align__(16) unsigned char ax_smem[];
+    const int d = w.seg_drop[(int64_t)blockIdx.x * AX_FS_THREADS];
+    const AxDrop& dr = w.drop[d];
+    const AxCfg& c = w.cfg[dr.cfg];
+    if (c.nsec != NSEC || ax_sos_is_butter(c) != BUTTER) return;      // another instantiation handles this drop
+    AxState& st = w.st[d];
+    const int R = c.rebase;
+    double* tab = reinterpret_cast<double*>(ax_smem);                   // [R][4]
+    int16_t* stage = reinterpret_cast<int16_t*>(ax_smem + (size_t)R * 4 * sizeof(double));
+    for (int i = threadIdx.x; i < 4 * R; i += AX_FS_THREADS) tab[i] = c.bit_cs[i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t seg = (int64_t)blockIdx.x * AX_FS_THREADS + threadIdx.x;
+    const int64_t j = seg - dr.seg_base;
+    const bool active = j < dr.nseg;
+    AxSegGeom g;
+    g.seg_start = g.seg_end = g.n_begin = g.n_stop = 0;
+    if (active) g = ax_seg_geom(dr, c, w.seg_len, j);
+    const int T = active ? (int)((g.n_stop - g.n_begin + 63) >> 6) : 0;
+    int Tmax = T;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) Tmax = max(Tmax, __shfl_xor_sync(0xffffffffu, Tmax, o));
+    const unsigned long long xrow = (unsigned long long)(w.pcm + dr.pcm_off + g.n_begin);   // 16-byte aligned
+    const int64_t slot = seg * (int64_t)w.seg_cap;
+    AxFilt<NSEC, BUTTER> f;
+    f.init(c, st, (int32_t)g.seg_start, (int32_t)g.seg_end, w.guard, w.rec_idx + slot, w.rec_a1 + slot, w.rec_a2 + slot, w.seg_cap);
+    int16_t* wst = stage + warp * (32 * AX_FS_ROW);
+    const int prow = lane >> 3, piece = lane & 7;
+    // rows this lane helps to copy: r = i*4 + prow, i = 0..7
+    unsigned long long src[8];
+    int Tr[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        src[i] = __shfl_sync(0xffffffffu, xrow, i * 4 + prow) + (unsigned long long)piece * 16;
+        Tr[i] = __shfl_sync(0xffffffffu, T, i * 4 + prow);
+    }
+    auto issue = [&](int t, int s) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (t < Tr[i]) ax_cp_async16(wst + s * AX_FS_STAGE + (i * 4 + prow) * AX_FS_ROW + piece * 8,
+                                         reinterpret_cast<const void*>(src[i] + (unsigned long long)t * 128));
+        ax_cp_async_commit();
+    };
+    if (Tmax > 0) issue(0, 0);
+    for (int t = 0; t < Tmax; ++t) {
+        if (t + 1 < Tmax) { issue(t + 1, (t + 1) & 1); ax_cp_async_wait<1>(); } else ax_cp_async_wait<0>();
+        __syncwarp();
+        if (t < T) {
+            const int4* rp = reinterpret_cast<const int4*>(wst + (t & 1) * AX_FS_STAGE + lane * AX_FS_ROW);
+            int32_t n = (int32_t)g.n_begin + t * 64;
+            const int32_t n_stop = (int32_t)g.n_stop;
+#pragma unroll 1
+            for (int v = 0; v < 8; ++v) {
+                const int4 q = rp[v];
+                const int wd[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    const int lo = (short)(wd[h] & 0xFFFF), hi = wd[h] >> 16;
+                    if (n < n_stop) f.step(n, (double)lo, tab);
+                    ++n;
+                    if (n < n_stop) f.step(n, (double)hi, tab);
+                    ++n;
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (!active) { w.seg_cnt[seg] = 0; return; }
+    f.finish();
+    if (f.cnt > w.seg_cap) { w.flags[AX_FLAG_CAP] = 1; f.cnt = w.seg_cap; }
+    w.seg_cnt[seg] = f.cnt;
+    if (f.unc) atomicAdd(&st.n_uncertain, f.unc);
+}
+
+template <int NSEC, bool BUTTER>
+static inline void ax_launch_filter_variant(const AxWave& w, int rebase_max, cudaStream_t stream) {
+    const size_t smem = (size_t)rebase_max * 4 * sizeof(double) + 2 * AX_FS_STAGE * sizeof(int16_t);
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(k_filter_staged<NSEC, BUTTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr_set = true; }
+    k_filter_staged<NSEC, BUTTER><<<w.nseg_total / AX_FS_THREADS, AX_FS_THREADS, smem, stream>>>(w);
+}
+
 // ------------------------------------------------------------------ tones
 #define AX_TONE_WARPS 8
 #define AX_TONE_R 4          // blocks per warp pass (register blocking against the smem table)
 
-__device__ __forceinline__ bool ax_tone_chunk_active(const AxState& st, int k, int phase_b) {
-    if (!phase_b) return k < st.n_fixed;
-    return st.sm_status >= 1 && k > st.k0 && k < st.n_chunks;
+__device__ __forceinline__ bool ax_tone_chunk_active(const AxWave& w, const AxState& st, int k, int phase_b) {
+    int klo, khi;
+    return ax_level_range(w, st, phase_b, &klo, &khi) && k >= klo && k < khi;
 }
 
 __global__ void __launch_bounds__(AX_TONE_WARPS * 32)
@@ -92,7 +195,7 @@ k_tone_blocks(AxWave w, int cfg_id, int phase_b, int qpc, int chunk_total) {
         if (dr.cfg != cfg_id) continue;
         const AxState& st = w.st[d];
         const int k = (int)(cg - dr.chunk_base);
-        if (k >= dr.chunk_cap || st.status >= AXCTD_DROP_CAPACITY || !ax_tone_chunk_active(st, k, phase_b)) continue;
+        if (k >= dr.chunk_cap || st.status >= AXCTD_DROP_CAPACITY || !ax_tone_chunk_active(w, st, k, phase_b)) continue;
         const AxChunk& ch = w.chunk[cg];
         if (ch.np <= 0) continue;
         const int B = (ch.np - 1) * c.tone_stride + c.tone_nb;
@@ -148,9 +251,7 @@ __global__ void k_tone_combine(AxWave w, int cfg_id, int phase_b) {
     const int32_t i = (int32_t)(slot - dr.pw_base);
     const AxChunk* ch = w.chunk + dr.chunk_base;
     int klo, khi;                                         // active chunk range [klo, khi)
-    if (!phase_b) { klo = 0; khi = st.n_fixed; }
-    else { if (st.sm_status < 1) return; klo = st.k0 + 1; khi = st.n_chunks; }
-    if (khi <= klo) return;
+    if (!ax_level_range(w, st, phase_b, &klo, &khi)) return;
     if (i < ch[klo].pw_off || i >= ch[khi - 1].pw_off + ch[khi - 1].np) return;
     int lo = klo, hi = khi - 1;                           // last chunk with pw_off <= i
     while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (ch[mid].pw_off <= i) lo = mid; else hi = mid - 1; }
@@ -184,4 +285,68 @@ static inline void ax_launch_tone_blocked(const AxWave& w, int cfg_id, const AxC
     int grid = (int)std::min<int64_t>((total + AX_TONE_WARPS - 1) / AX_TONE_WARPS, 148 * 4);
     k_tone_blocks<<<grid, AX_TONE_WARPS * 32, smem, stream>>>(w, cfg_id, phase_b, qpc, chunk_total);
     k_tone_combine<<<(w.pw_total + 127) / 128, 128, 0, stream>>>(w, cfg_id, phase_b);
+}
+
+// ------------------------------------------------------------------ frame sync (warp per drop)
+// Same greedy scan as ax_frames_item (parse.py:57-89 over AXCTDprocessor.py's per-iteration buffers),
+// but one warp walks a drop: the 32 lanes fetch 1024 mask positions per load, so the chain of
+// dependent memory latencies is one per 32 frames instead of one per frame.  Control flow is
+// warp-uniform; lane 0 records the frame positions.
+__global__ void __launch_bounds__(128) k_frames_warp(AxWave w) {
+    const int d = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (d >= w.n_drops) return;
+    const int lane = threadIdx.x & 31;
+    const AxDrop& dr = w.drop[d];
+    AxState& st = w.st[d];
+    if (lane == 0) st.n_frames = 0;
+    if (st.status != 0 || st.sm_status < 2 || st.k2 < 0 || st.nedges_total == 0) return;
+    AxChunk* ch = w.chunk + dr.chunk_base;
+    const int32_t* I = w.edge_idx + dr.edge_base;
+    const uint32_t* vw = w.validw + dr.edge_base / 32;
+    const int64_t nwords = (st.nbits_total + 31) / 32;
+    axctd_frame* fr = w.frame + dr.frame_base;
+    const int64_t prof = st.profstartind;
+    int64_t cur = 0, wbase = -1;
+    uint32_t myword = 0;
+    int32_t nf = 0;
+    for (int k = st.k2; k < st.n_chunks; ++k) {
+        if (lane == 0) { ch[k].frame_begin = nf; ch[k].frame_end = nf; }
+        if (ch[k].n_edges <= 0) continue;
+        const int64_t NI = ch[k].edge_off + ch[k].n_edges, NB = ch[k].bit_off + ch[k].n_edges - 1;
+        if (cur < NI && (int64_t)I[cur] <= prof) {
+            const int64_t f = ax_first_gt(I, cur, NI, prof);
+            if (f < 0) { if (lane == 0) ax_raise(st, AXCTD_DROP_TRIM_INDEX, k); return; }
+            cur = f;
+        }
+        const int64_t limit = NB - 32;
+        int64_t p = cur;
+        while (p < limit) {
+            const int64_t wi = p >> 5;
+            if (wbase < 0 || wi < wbase || wi >= wbase + 32) {
+                wbase = wi;
+                myword = (wbase + lane < nwords) ? vw[wbase + lane] : 0u;
+            }
+            uint32_t v = myword;
+            const int64_t mine = wbase + lane;
+            if (mine < wi) v = 0u; else if (mine == wi) v &= ~((1u << (p & 31)) - 1u);
+            const unsigned ball = __ballot_sync(0xffffffffu, v != 0u);
+            if (ball == 0u) { p = (wbase + 32) << 5; if (p > limit) p = limit; continue; }
+            const int L = __ffs((int)ball) - 1;
+            const uint32_t vv = __shfl_sync(0xffffffffu, v, L);
+            const int64_t pos = ((wbase + L) << 5) + (__ffs((int)vv) - 1);
+            if (pos >= limit) { p = limit; break; }
+            if (nf >= dr.frame_cap) { if (lane == 0) { ax_raise(st, AXCTD_DROP_CAPACITY, k); w.flags[AX_FLAG_CAP] = 1; } return; }
+            if (lane == 0) { fr[nf].edge_index = pos; fr[nf].chunk = k; }
+            ++nf;
+            p = pos + 32;
+        }
+        if (p > cur) cur = p;                      // AXCTDprocessor.py:618-621
+        if (lane == 0) ch[k].frame_end = nf;
+    }
+    if (lane == 0) st.n_frames = nf;
+}
+
+static inline void ax_launch_frames_warp(const AxWave& w, cudaStream_t stream) {
+    const int warps_per_block = 4;
+    k_frames_warp<<<(w.n_drops + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, stream>>>(w);
 }

@@ -23,6 +23,7 @@ AX_HDN inline void ax_plan0_item(const AxWave& w, int64_t d) {
     int k = 0;
     int64_t s = 0;
     int32_t pc = 0;
+    int par = 1;
     while (true) {
         if (dr.n - s < 4 * (int64_t)c.n_power) break;
         if (k >= dr.chunk_cap) { ax_raise(st, AXCTD_DROP_CAPACITY, k); w.flags[AX_FLAG_CAP] = 1; break; }
@@ -34,13 +35,29 @@ AX_HDN inline void ax_plan0_item(const AxWave& w, int64_t d) {
         q.frame_begin = q.frame_end = 0; q.scale = c.scale0; q.mean7500 = ax_nan();
         q.spec_last = q.true_last = -1; q.g_first = -1; q.q_last = -1; q.bit_off = q.edge_off = 0; q.first_edge = -1;
         if (pc + q.np > dr.pw_cap) { ax_raise(st, AXCTD_DROP_CAPACITY, k); w.flags[AX_FLAG_CAP] = 1; break; }
-        for (int j = 0; j < q.np; ++j) w.pw_ind[dr.pw_base + pc + j] = s + (int64_t)j * c.d_pcm;
+        if (q.np < 10) par = 0;
         pc += q.np;
         ++k;
         s = e;
     }
     st.n_fixed = k;
     st.n_chunks = k;
+    st.par_levels = par;
+    st.searching = k > 0 ? 1 : 0;
+}
+
+// power_inds of one chunk (AXCTDprocessor.py:357)
+AX_HDN inline void ax_pwfill_item(const AxWave& w, int64_t cg, int phase_b) {
+    const int d = ax_find_owner(w.drop, w.n_drops, &AxDrop::chunk_base, cg);
+    const AxDrop& dr = w.drop[d];
+    const AxState& st = w.st[d];
+    const int k = (int)(cg - dr.chunk_base);
+    if (k >= dr.chunk_cap || st.status >= AXCTD_DROP_CAPACITY) return;
+    if (!phase_b) { if (k >= st.n_fixed) return; }
+    else if (st.sm_status < 1 || k <= st.k0 || k >= st.n_chunks) return;
+    const AxChunk& q = w.chunk[cg];
+    const AxCfg& c = w.cfg[dr.cfg];
+    for (int j = 0; j < q.np; ++j) w.pw_ind[dr.pw_base + q.pw_off + j] = q.s + (int64_t)j * c.d_pcm;
 }
 
 // After the chain is final: power grid of the chunks after the first demodulated one.
@@ -56,7 +73,7 @@ AX_HDN inline void ax_plan_tones_item(const AxWave& w, int64_t d) {
         q.pw_off = pc; q.np = ax_grid_count(q.s, q.e, c);
         q.status = 0; q.n_rows = 0; q.n_hex = 0; q.frame_begin = q.frame_end = 0; q.scale = c.scale0; q.mean7500 = ax_nan();
         if (pc + q.np > dr.pw_cap) { ax_raise(st, AXCTD_DROP_CAPACITY, k); w.flags[AX_FLAG_CAP] = 1; q.np = 0; st.n_chunks = k; break; }
-        for (int j = 0; j < q.np; ++j) w.pw_ind[dr.pw_base + pc + j] = q.s + (int64_t)j * c.d_pcm;
+        if (q.np < 10) st.par_levels = 0;
         pc += q.np;
     }
 }
@@ -74,7 +91,11 @@ AX_HDN inline void ax_tone_direct_item(const AxWave& w, int64_t slot, int phase_
     const int32_t i = (int32_t)(slot - dr.pw_base);
     const AxChunk* ch = w.chunk + dr.chunk_base;
     int32_t lo, hi;
-    if (!phase_b) { lo = 0; hi = st.n_fixed > 0 ? ch[st.n_fixed - 1].pw_off + ch[st.n_fixed - 1].np : 0; }
+    if (!phase_b) {
+        const int ka = w.pa_lo, kb = w.pa_hi < st.n_fixed ? w.pa_hi : st.n_fixed;
+        if (!st.searching || kb <= ka) return;
+        lo = ch[ka].pw_off; hi = ch[kb - 1].pw_off + ch[kb - 1].np;
+    }
     else {
         if (st.sm_status < 1 || st.n_chunks <= st.k0 + 1) return;
         lo = ch[st.k0].pw_off + ch[st.k0].np; hi = ch[st.n_chunks - 1].pw_off + ch[st.n_chunks - 1].np;
@@ -106,8 +127,59 @@ AX_HD double ax_np_sum_small(const double* a, int n) {
     return res;
 }
 
+// chunk range [klo, khi) whose power samples a levels / tone launch covers
+AX_HD bool ax_level_range(const AxWave& w, const AxState& st, int phase_b, int* klo, int* khi) {
+    if (!phase_b) {
+        *klo = w.pa_lo; *khi = w.pa_hi < st.n_fixed ? w.pa_hi : st.n_fixed;
+        return st.searching && *khi > *klo;
+    }
+    *klo = st.k0 + 1; *khi = st.n_chunks;
+    return st.sm_status >= 1 && *khi > *klo;
+}
+
+AX_HD double ax_nanmean_raw(const double* raw, int lo, int hi) {     // np.nanmean(raw[lo..hi]) (demodulate.py:44,46)
+    double tot = 0.0; int cnt = 0;
+    for (int j = lo; j <= hi; ++j) { const double v = raw[j]; if (!isnan(v)) { tot = ax_add(tot, v); ++cnt; } }
+    return cnt ? ax_div(tot, (double)cnt) : ax_nan();
+}
+
+// demodulate.py:39-48 + AXCTDprocessor.py:370-371 for ONE power sample.  The lagging box filter
+// re-reads entries smoothed by earlier calls only in the first five samples of a chunk; those
+// entries are themselves plain window means of raw values whenever the previous chunk holds at
+// least ten samples (st.par_levels), so every sample can be evaluated independently.
+AX_HDN inline void ax_levels_item(const AxWave& w, int64_t slot, int phase_b) {
+    const int d = ax_find_owner(w.drop, w.n_drops, &AxDrop::pw_base, slot);
+    const AxDrop& dr = w.drop[d];
+    const AxState& st = w.st[d];
+    if (!st.par_levels || st.status >= AXCTD_DROP_CAPACITY) return;
+    int klo, khi;
+    if (!ax_level_range(w, st, phase_b, &klo, &khi)) return;
+    const AxChunk* ch = w.chunk + dr.chunk_base;
+    const int i = (int)(slot - dr.pw_base);
+    if (i < ch[klo].pw_off || i >= ch[khi - 1].pw_off + ch[khi - 1].np) return;
+    int lo = klo, hi = khi - 1;                          // last chunk with pw_off <= i
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (ch[mid].pw_off <= i) lo = mid; else hi = mid - 1; }
+    const int pstart = ch[lo].pw_off;
+    const int64_t PT = w.pw_total;
+    double smv[3];
+    for (int f = 0; f < 3; ++f) {
+        const double* raw = w.pw_raw + f * PT + dr.pw_base;
+        const int wl = (i < 5) ? 0 : i - 5;
+        double tot = 0.0; int cnt = 0;
+        for (int j = wl; j <= i; ++j) {
+            const double v = (j >= pstart) ? raw[j] : ax_nanmean_raw(raw, j < 5 ? 0 : j - 5, j);
+            if (!isnan(v)) { tot = ax_add(tot, v); ++cnt; }
+        }
+        smv[f] = cnt ? ax_div(tot, (double)cnt) : ax_nan();
+        w.pw_sm[f * PT + slot] = smv[f];
+    }
+    w.r400[slot] = log10(ax_div(smv[0], smv[2]));
+    w.r7500[slot] = log10(ax_div(smv[1], smv[2]));
+}
+
 // Sequential per-drop state machine over run() iterations.  phase 0: fixed grid
-// until the 400 Hz pulse is found; phase 1: the demodulated chunks.
+// until the 400 Hz pulse is found (in rounds of chunks [pa_lo, pa_hi)); phase 1: the demodulated
+// chunks.  Smoothing is done here only for drops that cannot use ax_levels_item.
 AX_HDN inline void ax_sm_item(const AxWave& w, int64_t d, int phase_b) {
     const AxDrop& dr = w.drop[d];
     const AxCfg& c = w.cfg[dr.cfg];
@@ -119,26 +191,29 @@ AX_HDN inline void ax_sm_item(const AxWave& w, int64_t d, int phase_b) {
     for (int f = 0; f < 3; ++f) { raw[f] = w.pw_raw + f * PT + dr.pw_base; sm[f] = w.pw_sm + f * PT + dr.pw_base; }
     double* r400 = w.r400 + dr.pw_base; double* r7500 = w.r7500 + dr.pw_base;
     const int64_t* pind = w.pw_ind + dr.pw_base;
-    const int kend = phase_b ? st.n_chunks : st.n_fixed;
-    if (phase_b && st.sm_status < 1) return;
+    int klo, kend;
+    if (!ax_level_range(w, st, phase_b, &klo, &kend)) return;
+    const bool do_smooth = !st.par_levels;
     for (int k = st.next_sm_chunk; k < kend; ++k) {
         AxChunk& q = ch[k];
         const int pstart = q.pw_off, np = q.np;
-        // demodulate.py:39-48 called with startind = pstart (AXCTDprocessor.py:367-369)
-        for (int f = 0; f < 3; ++f) {
-            for (int i = pstart; i < pstart + np; ++i) {
-                const int lo = (i < 5) ? 0 : i - 5;
-                double tot = 0.0; int cnt = 0;
-                for (int jj = lo; jj <= i; ++jj) {
-                    const double v = (jj < pstart) ? sm[f][jj] : raw[f][jj];
-                    if (!isnan(v)) { tot = ax_add(tot, v); ++cnt; }
+        if (do_smooth) {
+            // demodulate.py:39-48 called with startind = pstart (AXCTDprocessor.py:367-369)
+            for (int f = 0; f < 3; ++f) {
+                for (int i = pstart; i < pstart + np; ++i) {
+                    const int lo = (i < 5) ? 0 : i - 5;
+                    double tot = 0.0; int cnt = 0;
+                    for (int jj = lo; jj <= i; ++jj) {
+                        const double v = (jj < pstart) ? sm[f][jj] : raw[f][jj];
+                        if (!isnan(v)) { tot = ax_add(tot, v); ++cnt; }
+                    }
+                    sm[f][i] = cnt ? ax_div(tot, (double)cnt) : ax_nan();
                 }
-                sm[f][i] = cnt ? ax_div(tot, (double)cnt) : ax_nan();
             }
-        }
-        for (int i = pstart; i < pstart + np; ++i) {                    // :370-371
-            r400[i] = log10(ax_div(sm[0][i], sm[2][i]));
-            r7500[i] = log10(ax_div(sm[1][i], sm[2][i]));
+            for (int i = pstart; i < pstart + np; ++i) {                    // :370-371
+                r400[i] = log10(ax_div(sm[0][i], sm[2][i]));
+                r7500[i] = log10(ax_div(sm[1][i], sm[2][i]));
+            }
         }
         st.pcount = pstart + np;
         if (st.sm_status == 0) {                                        // :375-380
@@ -181,8 +256,9 @@ AX_HDN inline void ax_sm_item(const AxWave& w, int64_t d, int phase_b) {
         if (!phase_b && st.sm_status >= 1) break;      // hand over to the chunk chain
     }
     if (!phase_b) {
-        if (st.sm_status >= 1) { st.chain_from = st.k0; st.chain_end = 0; }
-        else { st.n_chunks = st.n_fixed; st.chain_end = 1; }
+        if (st.sm_status >= 1) { st.chain_from = st.k0; st.chain_end = 0; st.searching = 0; }
+        else if (st.next_sm_chunk >= st.n_fixed) { st.n_chunks = st.n_fixed; st.chain_end = 1; st.searching = 0; }
+        else w.flags[AX_FLAG_MORE] = 1;                // another detection round is needed
     }
 }
 
@@ -225,7 +301,7 @@ AX_HDN inline void ax_emit_item(const AxWave& w, int64_t cg) {
     double* a2 = w.a2 + dr.edge_base + ch.bit_off;
     const double* r400 = w.r400 + dr.pw_base + ch.pw_off;
     const double* r7500 = w.r7500 + dr.pw_base + ch.pw_off;
-    const int64_t br2 = 2 * (int64_t)c.bitrate;
+    const uint8_t* nx = w.zc_nx + dr.zc_base;
     int64_t pos = ch.g_first;
     for (int t = 0; t < ch.n_edges; ++t) {
         int64_t idx; double v1, v2;
@@ -234,7 +310,7 @@ AX_HDN inline void ax_emit_item(const AxWave& w, int64_t cg) {
             idx = zi[pos]; v1 = za1[pos]; v2 = za2[pos];
             if (t < ch.n_edges - 1) {
                 if (idx + c.inset + c.npcm > ch.e) ax_raise(st, AXCTD_DROP_SHORT_WINDOW, k);   // demodulate.py:100-101
-                pos = ax_next(zi, pos, c.fs2, br2);
+                pos += nx[pos];
             }
         }
         eidx[t] = (int32_t)idx;
@@ -268,7 +344,9 @@ AX_HD int64_t ax_last_le(const int32_t* I, int64_t n, int64_t v) {
     return -1;
 }
 AX_HD int64_t ax_first_gt(const int32_t* I, int64_t from, int64_t n, int64_t v) {
-    for (int64_t j = from; j < n; ++j) if ((int64_t)I[j] > v) return j;
+    int64_t j = from + ax_upper_bound(I + from, n - from, v) - 64;     // good guess; then make it exact
+    if (j < from) j = from;
+    for (; j < n; ++j) if ((int64_t)I[j] > v) return j;
     return -1;
 }
 
@@ -277,7 +355,7 @@ AX_HDN inline void ax_scale_item(const AxWave& w, int64_t d) {
     const AxDrop& dr = w.drop[d];
     const AxCfg& c = w.cfg[dr.cfg];
     AxState& st = w.st[d];
-    st.scale = c.scale0; st.k1 = -1; st.header_read[0] = 0; st.header_chunk[0] = -1;
+    st.scale = c.scale0; st.k1 = -1; st.header_read[0] = 0; st.header_chunk[0] = -1; st.scale_switch_bit = st.nbits_total;
     if (st.sm_status < 1 || st.nedges_total == 0) return;
     AxChunk* ch = w.chunk + dr.chunk_base;
     const int32_t* I = w.edge_idx + dr.edge_base;
@@ -330,21 +408,19 @@ AX_HDN inline void ax_scale_item(const AxWave& w, int64_t d) {
         break;
     }
     for (int k = st.k0; k < st.n_chunks; ++k) ch[k].scale = (st.k1 >= 0 && k > st.k1) ? st.scale : c.scale0;
+    st.scale_switch_bit = (st.k1 >= 0 && st.k1 + 1 < st.n_chunks) ? ch[st.k1 + 1].bit_off : st.nbits_total;
 }
 
-// demodulate.py:102,109-114
-AX_HDN inline void ax_bits_item(const AxWave& w, int64_t cg) {
-    const int d = ax_find_owner(w.drop, w.n_drops, &AxDrop::chunk_base, cg);
+// demodulate.py:102,109-114 for one bit
+AX_HDN inline void ax_bits_item(const AxWave& w, int64_t slot) {
+    const int d = ax_find_owner(w.drop, w.n_drops, &AxDrop::edge_base, slot);
     const AxDrop& dr = w.drop[d];
     const AxState& st = w.st[d];
-    const int k = (int)(cg - dr.chunk_base);
-    if (st.sm_status < 1 || k < st.k0 || k >= st.n_chunks || st.nedges_total == 0) return;
-    const AxChunk& ch = w.chunk[cg];
-    const int64_t base = dr.edge_base + ch.bit_off;
-    for (int t = 0; t < ch.n_edges - 1; ++t) {
-        const double p1 = w.a1[base + t];
-        const double p2 = ax_mul(w.a2[base + t], ch.scale);
-        w.conf[base + t] = ax_div(p2, p1);
-        w.bit[base + t] = (p1 >= p2) ? 1 : 0;
-    }
+    const int64_t j = slot - dr.edge_base;
+    if (j >= st.nbits_total) return;
+    const double scale = (j >= st.scale_switch_bit) ? st.scale : w.cfg[dr.cfg].scale0;
+    const double p1 = w.a1[slot];
+    const double p2 = ax_mul(w.a2[slot], scale);
+    w.conf[slot] = ax_div(p2, p1);
+    w.bit[slot] = (p1 >= p2) ? 1 : 0;
 }

@@ -79,18 +79,85 @@ AX_HDN inline void ax_header_item(const AxWave& w, int64_t item) {
     }
 }
 
+// 32 demodulated bits -> one word, bit b of word i = bit 32*i + b of the drop's bitstream
+AX_HDN inline void ax_pack_item(const AxWave& w, int64_t wg) {
+    const int d = ax_find_owner(w.drop, w.n_drops, &AxDrop::edge_base, wg * 32);
+    const AxDrop& dr = w.drop[d];
+    const AxState& st = w.st[d];
+    const int64_t j0 = wg * 32 - dr.edge_base;             // edge_base is a multiple of 64
+    if (st.sm_status < 2 || j0 >= st.nbits_total) { w.bitw[wg] = 0; return; }
+    const uint8_t* B = w.bit + dr.edge_base;
+    uint32_t v = 0;
+    for (int q = 0; q < 32; ++q) if (j0 + q < st.nbits_total && B[j0 + q]) v |= 1u << q;
+    w.bitw[wg] = v;
+}
+
+AX_HD uint32_t ax_brev32(uint32_t v) {
+#ifdef __CUDA_ARCH__
+    return __brev(v);
+#else
+    v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
+    v = ((v >> 2) & 0x33333333u) | ((v & 0x33333333u) << 2);
+    v = ((v >> 4) & 0x0F0F0F0Fu) | ((v & 0x0F0F0F0Fu) << 4);
+    v = ((v >> 8) & 0x00FF00FFu) | ((v & 0x00FF00FFu) << 8);
+    return (v >> 16) | (v << 16);
+#endif
+}
+// the 32 bits starting at bit position p of the drop's bitstream, first bit in the MSB (binListToHex order)
+AX_HD uint32_t ax_frame_word(const uint32_t* bw, int64_t p) {
+    const int64_t wi = p >> 5; const int sh = (int)(p & 31);
+    const uint64_t two = (uint64_t)bw[wi] | ((uint64_t)bw[wi + 1] << 32);
+    return ax_brev32((uint32_t)(two >> sh));
+}
+
+// parse.py:68 for every start position: '10' header, CRC, r7500 > 0  ->  one mask bit per position
+AX_HDN inline void ax_valid_item(const AxWave& w, int64_t wg) {
+    const int d = ax_find_owner(w.drop, w.n_drops, &AxDrop::edge_base, wg * 32);
+    const AxDrop& dr = w.drop[d];
+    const AxState& st = w.st[d];
+    const int64_t j0 = wg * 32 - dr.edge_base;
+    if (st.sm_status < 2 || j0 >= st.nbits_total) { w.validw[wg] = 0; return; }
+    const uint32_t* bw = w.bitw + dr.edge_base / 32;
+    const double* l7500 = w.lvl7500 + dr.edge_base;
+    uint32_t v = 0;
+    for (int q = 0; q < 32; ++q) {
+        const int64_t p = j0 + q;
+        if (p + 32 > st.nbits_total) break;
+        const uint32_t wd = ax_frame_word(bw, p);
+        if ((wd >> 30) == 2u && ax_crc_ok(wd) && l7500[p] > 0.0) v |= 1u << q;
+    }
+    w.validw[wg] = v;
+}
+
+// next position >= p whose mask bit is set (or `limit` if none below limit)
+AX_HD int64_t ax_next_valid(const uint32_t* vw, int64_t p, int64_t limit) {
+    while (p < limit) {
+        const uint32_t v = vw[p >> 5] >> (p & 31);
+        if (v) {
+#ifdef __CUDA_ARCH__
+            const int z = __ffs((int)v) - 1;
+#else
+            const int z = __builtin_ctz(v);
+#endif
+            p += z;
+            return p < limit ? p : limit;
+        }
+        p = ((p >> 5) + 1) << 5;
+    }
+    return limit;
+}
+
 // Greedy frame synchronisation over the profile bits of one drop, grouped by
-// run() iteration exactly as the reference consumes its buffers.
+// run() iteration exactly as the reference consumes its buffers.  Only the frame
+// positions are recorded here; ax_calib_item fills the records in parallel.
 AX_HDN inline void ax_frames_item(const AxWave& w, int64_t d) {
     const AxDrop& dr = w.drop[d];
-    const AxCfg& c = w.cfg[dr.cfg];
     AxState& st = w.st[d];
     st.n_frames = 0;
     if (st.status != 0 || st.sm_status < 2 || st.k2 < 0 || st.nedges_total == 0) return;
     AxChunk* ch = w.chunk + dr.chunk_base;
     const int32_t* I = w.edge_idx + dr.edge_base;
-    const uint8_t* B = w.bit + dr.edge_base;
-    const double* l400 = w.lvl400 + dr.edge_base; const double* l7500 = w.lvl7500 + dr.edge_base;
+    const uint32_t* vw = w.validw + dr.edge_base / 32;
     axctd_frame* fr = w.frame + dr.frame_base;
     const int64_t prof = st.profstartind;
     int64_t cur = 0;
@@ -104,23 +171,17 @@ AX_HDN inline void ax_frames_item(const AxWave& w, int64_t d) {
             if (f < 0) { ax_raise(st, AXCTD_DROP_TRIM_INDEX, k); return; }
             cur = f;
         }
-        const int64_t numbits = NB > cur ? NB - cur : 0;
-        int64_t s = 0;
-        while (s < numbits - 32) {                                     // parse.py:57-89
-            const int64_t p = cur + s;
-            bool ok = (B[p] == 1 && B[p + 1] == 0);
-            uint32_t wd = 0;
-            if (ok) { wd = ax_word32(B + p); ok = ax_crc_ok(wd) && (l7500[p] > 0.0); }
-            if (!ok) { ++s; continue; }
+        const int64_t limit = NB - 32;                                 // parse.py:57 `while s < numbits - 32`
+        int64_t p = cur;
+        while (p < limit) {
+            p = ax_next_valid(vw, p, limit);
+            if (p >= limit) break;
             if (nf >= dr.frame_cap) { ax_raise(st, AXCTD_DROP_CAPACITY, k); w.flags[AX_FLAG_CAP] = 1; return; }
-            axctd_frame& f = fr[nf++];
-            f.edge_index = I[p]; f.word = wd; f.chunk = k;
-            f.time_raw = ax_div((double)((int64_t)I[p] - prof), c.fs);  // AXCTDprocessor.py:554
-            f.r400_raw = l400[p]; f.r7500_raw = l7500[p];
-            f.keep = 0; f.hex_returned = 0;
-            s += 32;
+            fr[nf].edge_index = p; fr[nf].chunk = k;                   // bit position; ax_calib_item resolves it
+            ++nf;
+            p += 32;
         }
-        cur += s;                                                       // AXCTDprocessor.py:618-621
+        if (p > cur) cur = p;                                          // AXCTDprocessor.py:618-621
         ch[k].frame_end = nf;
     }
     st.n_frames = nf;
@@ -191,6 +252,15 @@ AX_HDN inline void ax_calib_item(const AxWave& w, int64_t fg) {
     if (fg - dr.frame_base >= st.n_frames || st.status != 0) return;
     const AxCfg& c = w.cfg[dr.cfg];
     axctd_frame& f = w.frame[fg];
+    {   // the scan stored the bit position in edge_index: resolve word, PCM index, time and levels
+        const int64_t p = f.edge_index;
+        const int64_t ei = w.edge_idx[dr.edge_base + p];
+        f.word = ax_frame_word(w.bitw + dr.edge_base / 32, p);
+        f.edge_index = ei;
+        f.time_raw = ax_div((double)(ei - st.profstartind), c.fs);     // AXCTDprocessor.py:554
+        f.r400_raw = w.lvl400[dr.edge_base + p]; f.r7500_raw = w.lvl7500[dr.edge_base + p];
+        f.hex_returned = 0;
+    }
     f.cint = (int32_t)((f.word >> 18) & 0xFFF);           // bits 2..13  (parse.py:107)
     f.tint = (int32_t)((f.word >> 6) & 0xFFF);            // bits 14..25 (parse.py:106)
     const double z = ax_dataconvert(f.time_raw, st.zc_used);                    // parse.py:117

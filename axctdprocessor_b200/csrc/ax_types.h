@@ -52,7 +52,7 @@ AX_HD double ax_nan() { return nan(""); }
 
 #define AX_TILE 64          // crossings per walk tile
 #define AX_MAXSEC AXCTD_MAX_SECTIONS
-#define AX_PEND 6           // pending bit-windows per thread in the filter pass
+#define AX_PEND 8           // pending bit-windows per thread in the filter pass
 #define AX_STAT_SLAB 16384  // samples per stats work item
 
 // Per rate-class constants (reference AXCTDprocessor.py:117-182, 212-262).
@@ -140,6 +140,10 @@ struct AxState {
     // demod bookkeeping
     double scale;
     int32_t k1;                  // iteration at the end of which the scale changed
+    int32_t par_levels;          // 1: smoothing may be evaluated per power sample in parallel
+    int64_t scale_switch_bit;    // first bit decided with the calibrated scale
+    int32_t searching;           // still looking for the 400 Hz pulse on the fixed grid
+    int32_t pad2;
     int32_t header_read[3], header_chunk[3];
     int64_t nbits_total, nedges_total;
     int64_t n_frames, n_rows, n_hex;
@@ -159,10 +163,11 @@ struct AxWave {
     int32_t seg_len, seg_cap, nseg_total, nslab_total;
     const int32_t* seg_drop;     // segment -> drop
     const int32_t* slab_drop;    // stats slab -> drop
-    int32_t* seg_cnt; int64_t* seg_off;
+    int32_t* seg_cnt; int64_t* seg_off; int64_t* blk_sum;  // per segment / per block of 128 segments
     int32_t* rec_idx; double* rec_a1; double* rec_a2;       // [nseg_total * seg_cap]
     int32_t* zc_idx; double* zc_a1; double* zc_a2;          // dense, per drop at zc_base
-    uint16_t* tile_tab;                                     // [tile][4]
+    uint8_t* zc_nx; uint8_t* zc_exit;                       // per crossing: walk step, tile exit
+    uint64_t* tile_mask;                                    // [tile][4] visited masks
     // chunks
     AxChunk* chunk;
     int32_t* head_idx; double* head_a1; double* head_a2;    // [chunk][head_zc_cap_max]
@@ -179,10 +184,12 @@ struct AxWave {
     // bits / edges
     int32_t* edge_idx; double* lvl400; double* lvl7500;     // per edge
     uint8_t* bit; double* a1; double* a2; double* conf;     // per bit
+    uint32_t* bitw; uint32_t* validw;                       // packed bits / frame-candidate mask (32 per word)
     // frames
     axctd_frame* frame;
     double guard;
     int32_t tone_direct;
+    int32_t pa_lo, pa_hi;        // fixed-grid chunk range of the current detection round
     int32_t force_exact;
     int32_t* flags;              // [0] = any chain dirty, [1] = any capacity error
 };
@@ -191,6 +198,7 @@ AX_HD bool ax_tone_blocked_ok(const AxCfg& c) { return c.tone_G >= 32 && c.tone_
 
 #define AX_FLAG_DIRTY 0
 #define AX_FLAG_CAP 1
+#define AX_FLAG_MORE 2
 
 AX_HD void ax_raise(AxState& st, int code, int chunk) {
     if (st.status == 0) { st.status = code; st.status_chunk = chunk; }
