@@ -295,6 +295,26 @@ AX_HDN inline void ax_compact_item(const AxWave& w, int64_t seg) {
     }
 }
 
+// ------------------------------------------------------------------ fp64 point evaluation
+// y[n] of the continuous (zero state at the start of the recording) SOS cascade as a direct
+// convolution with its impulse response: sum_m h[m] * (x[n-m] - dc) / ampl.  Used to re-decide,
+// in double precision, single samples / windows where the fp32 pass is too close to call.
+// Returns the partial sum over taps m = lane, lane+nl, ...; the caller adds the partials and
+// finishes with ax_fir_finish.
+AX_HD double ax_fir_partial(const int16_t* x, int64_t n, const double* h, int K, int lane, int nl) {
+    const int64_t mmax = (n + 1 < (int64_t)K) ? n + 1 : (int64_t)K;
+    double acc = 0.0;
+    for (int64_t m = lane; m < mmax; m += nl) acc = ax_fma(h[m], (double)x[n - m], acc);
+    return acc;
+}
+AX_HD double ax_fir_finish(double sum, int64_t n, const AxCfg& c, const AxState& st) {
+    const int64_t mc = (n + 1 < (int64_t)c.fir_len) ? n : (int64_t)c.fir_len - 1;
+    return (sum - st.dc * c.fir_hc[mc]) * st.inv_ampl;
+}
+AX_HD double ax_fir_y64(const int16_t* x, int64_t n, const AxCfg& c, const AxState& st) {
+    return ax_fir_finish(ax_fir_partial(x, n, c.fir_h, c.fir_len, 0, 1), n, c, st);
+}
+
 // ------------------------------------------------------------------ walk
 // demodulate.py:91-92: among the next four crossings take the one closest to
 // one bit period later (first minimum).  |z - (z0 + fs/bitrate)| is compared

@@ -109,6 +109,8 @@ struct axctd_engine {
     int opt_filter_variant = 0;
     int opt_zc_div = 12;
     int opt_inject_misspec = 0;           // test hook: corrupt the first prediction
+    double opt_guard32 = 5e-5;            // fp32 filter pass guard band (of full scale)
+    int opt_bitfix_all = 0;               // test hook
 };
 
 #ifdef AXCTD_EMU
@@ -241,6 +243,8 @@ extern "C" int axctd_engine_set_option(axctd_engine* e, const char* name, double
     else if (s == "filter_variant") e->opt_filter_variant = (int)v;
     else if (s == "zc_div") e->opt_zc_div = std::max(2, (int)v);
     else if (s == "inject_misspec") e->opt_inject_misspec = (int)v;
+    else if (s == "guard32") e->opt_guard32 = v;
+    else if (s == "bitfix_all") e->opt_bitfix_all = (int)v;
     else return AXCTD_ERR_ARG;
     return AXCTD_OK;
 }
@@ -301,6 +305,26 @@ extern "C" int axctd_config_create(axctd_engine* e, const axctd_config_desc* ds,
     const double* bc = ds->bit_cs + 4 * (size_t)c.rebase;      // e^{+j theta R}; store the conjugate
     c.rot[0][0] = bc[0]; c.rot[0][1] = -bc[1]; c.rot[1][0] = bc[2]; c.rot[1][1] = -bc[3];
     c.lut_len = ds->lut_len; c.n_hist_edges = ds->n_hist_edges;
+    {   // impulse response of the cascade, long enough for the tail to fall below 1e-18
+        int K = (int)ceil(log(1e-18) / log(r)) + 64;
+        K = ((K + 31) / 32) * 32;
+        std::vector<long double> zz(2 * AX_MAXSEC, 0.0L);
+        std::vector<double> h(K), hc(K);
+        long double run = 0.0L;
+        for (int n = 0; n < K; ++n) {
+            long double u = (n == 0) ? 1.0L : 0.0L;
+            for (int q = 0; q < c.nsec; ++q) {
+                const long double b0 = c.sos[q][0], b1 = c.sos[q][1], b2 = c.sos[q][2], a1 = c.sos[q][4], a2 = c.sos[q][5];
+                const long double y = b0 * u + zz[2 * q];
+                zz[2 * q] = b1 * u - a1 * y + zz[2 * q + 1];
+                zz[2 * q + 1] = b2 * u - a2 * y;
+                u = y;
+            }
+            h[n] = (double)u; run += u; hc[n] = (double)run;
+        }
+        c.fir_len = K;
+        if (ax_cfg_upload(e, &c.fir_h, h.data(), (size_t)K) || ax_cfg_upload(e, &c.fir_hc, hc.data(), (size_t)K)) return AXCTD_ERR_CUDA;
+    }
     if (ax_cfg_upload(e, &c.bit_cs, ds->bit_cs, 4 * (size_t)ds->bit_cs_len) ||
         ax_cfg_upload(e, &c.tone_cs, ds->tone_cs, 6 * (size_t)ds->n_power) ||
         ax_cfg_upload(e, &c.lut, ds->temp_lut, (size_t)ds->lut_len) ||
@@ -360,6 +384,7 @@ extern "C" int axctd_batch_create(axctd_engine* e, int n_drops, const int64_t* n
     w.n_drops = n_drops; w.n_cfg = (int)e->cfgs.size(); w.cfg = e->d_cfg;
     w.seg_len = (int32_t)L; w.seg_cap = (int32_t)(L / 8 + 32);
     w.guard = e->opt_guard; w.tone_direct = e->opt_tone_direct; w.force_exact = e->opt_force_exact;
+    w.guard32 = (float)e->opt_guard32; w.bitfix_all = e->opt_bitfix_all;
     w.head_zc_cap_max = head_cap_max; w.ybuf_len_max = ybuf_max; w.blk_stride = blk_max;
     b->drops.resize(n_drops);
     int64_t pcm_off = 0, zc_off = 0, edge_off = 0;

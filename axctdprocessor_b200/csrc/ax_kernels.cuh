@@ -164,6 +164,237 @@ static inline void ax_launch_filter_variant(const AxWave& w, int rebase_max, cud
     k_filter_staged<NSEC, BUTTER><<<w.nseg_total / AX_FS_THREADS, AX_FS_THREADS, smem, stream>>>(w);
 }
 
+// ------------------------------------------------------------------ filter (fp32, fused)
+// The production filter pass.  B200's double-precision pipe is ~30x slower than the FP32 pipe,
+// so the streaming work runs in fp32 and double precision is spent only where a decision could
+// depend on it:
+//   phase 1 (one thread per segment): int16 -> Butterworth SOS cascade in fp32 (13 FMA-pipe
+//            operations per sample) -> y written to a per-thread row in shared memory;
+//   phase 2a (warp-cooperative): every sample with |y| < guard32 is re-evaluated in fp64 as a
+//            direct convolution with the cascade's impulse response (ax_fir_partial) and
+//            replaced, so that all signs used below are the exact filter's signs;
+//   phase 2b (warp-cooperative): zero crossings of the previous row (demodulate.py:77-79) and,
+//            for each, the mark / space single-bin DFT magnitudes of the following npcm samples
+//            (demodulate.py:99-102), 32 lanes over the window taps.
+// The PCM reaches shared memory through 16-byte cp.async copies, one full 128-byte line per
+// thread per stage, double buffered; y never leaves the SM.
+#define AX_F32_YROW 65                                 // floats per y row: 64 + 1 pad (conflict-free column access)
+
+template <int NSEC>
+__global__ void __launch_bounds__(AX_FS_THREADS, 2) k_filter32(AxWave w) {
+    extern __shared__ __align__(16) unsigned char ax_smem[];
+    const int d = w.seg_drop[(int64_t)blockIdx.x * AX_FS_THREADS];
+    const AxDrop& dr = w.drop[d];
+    const AxCfg& c = w.cfg[dr.cfg];
+    if (c.nsec != NSEC || !ax_sos_is_butter(c) || c.npcm > 64) return;
+    AxState& st = w.st[d];
+    float4* tabf = reinterpret_cast<float4*>(ax_smem);                             // [64] cos1,sin1,cos2,sin2
+    int16_t* stage = reinterpret_cast<int16_t*>(ax_smem + 64 * sizeof(float4));   // [2][4][32][72]
+    float* yrow = reinterpret_cast<float*>(ax_smem + 64 * sizeof(float4) + 2 * AX_FS_STAGE * sizeof(int16_t));   // [2][128][65]
+    int* count = reinterpret_cast<int*>(yrow + 2 * AX_FS_THREADS * AX_F32_YROW);   // [128]
+    const int npcm = c.npcm;
+    if (threadIdx.x < 64) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if ((int)threadIdx.x < npcm) {
+            const double* t4 = c.bit_cs + 4 * threadIdx.x;
+            v = make_float4((float)t4[0], (float)t4[1], (float)t4[2], (float)t4[3]);
+        }
+        tabf[threadIdx.x] = v;
+    }
+    count[threadIdx.x] = 0;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t seg = (int64_t)blockIdx.x * AX_FS_THREADS + threadIdx.x;
+    const int64_t j = seg - dr.seg_base;
+    const bool active = j < dr.nseg;
+    AxSegGeom g;
+    g.seg_start = g.seg_end = g.n_begin = g.n_stop = 0;
+    if (active) g = ax_seg_geom(dr, c, w.seg_len, j);
+    const int T = active ? (int)((g.n_stop - g.n_begin + 63) >> 6) : 0;
+    int Tmax = T;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) Tmax = max(Tmax, __shfl_xor_sync(0xffffffffu, Tmax, o));
+    const int16_t* xdrop = w.pcm + dr.pcm_off;
+    const unsigned long long xrow = (unsigned long long)(xdrop + g.n_begin);
+    // ---- fp32 cascade state (Butterworth form, see AxFilt)
+    float z0[NSEC], z1[NSEC], a1[NSEC], a2[NSEC], sg[NSEC];
+#pragma unroll
+    for (int s = 0; s < NSEC; ++s) {
+        z0[s] = 0.f; z1[s] = 0.f;
+        a1[s] = (float)c.sos[s][4]; a2[s] = (float)c.sos[s][5];
+        sg[s] = (c.sos[s][1] < 0.0) ? -2.f : 2.f;
+    }
+    const float k0 = (float)(c.sos[0][0] * st.inv_ampl), k1 = (float)(-(c.sos[0][0] * st.dc * st.inv_ampl));
+    const float G = w.guard32;
+    int16_t* wst = stage + warp * (32 * AX_FS_ROW);
+    float* wy = yrow + (warp * 32) * AX_F32_YROW;          // this warp's 32 rows inside one y buffer
+    const int prow = lane >> 3, piece = lane & 7;
+    unsigned long long src[8];
+    int Tr[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        src[i] = __shfl_sync(0xffffffffu, xrow, i * 4 + prow) + (unsigned long long)piece * 16;
+        Tr[i] = __shfl_sync(0xffffffffu, T, i * 4 + prow);
+    }
+    const int nb = (int)g.n_begin, nstop = (int)g.n_stop, sstart = (int)g.seg_start, send = (int)g.seg_end;
+    const int64_t slot0 = seg * (int64_t)w.seg_cap;
+    float errmax = 0.f;
+    int nre = 0;
+    if (Tmax > 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (0 < Tr[i]) ax_cp_async16(wst + (i * 4 + prow) * AX_FS_ROW + piece * 8, reinterpret_cast<const void*>(src[i]));
+        ax_cp_async_commit();
+    }
+    for (int t = 0; t <= Tmax; ++t) {
+        float* ycur = wy + (t & 1) * (AX_FS_THREADS * AX_F32_YROW);
+        float* yprev = wy + ((t & 1) ^ 1) * (AX_FS_THREADS * AX_F32_YROW);
+        if (t < Tmax) {
+            if (t + 1 < Tmax) {
+                const int s = (t + 1) & 1;
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (t + 1 < Tr[i]) ax_cp_async16(wst + s * AX_FS_STAGE + (i * 4 + prow) * AX_FS_ROW + piece * 8,
+                                                     reinterpret_cast<const void*>(src[i] + (unsigned long long)(t + 1) * 128));
+                ax_cp_async_commit();
+                ax_cp_async_wait<1>();
+            } else ax_cp_async_wait<0>();
+            __syncwarp();
+            // ---------------- phase 1: fp32 cascade over this thread's 64 samples
+            if (t < T) {
+                const int4* rp = reinterpret_cast<const int4*>(wst + (t & 1) * AX_FS_STAGE + lane * AX_FS_ROW);
+                float* yo = ycur + lane * AX_F32_YROW;
+#pragma unroll 1
+                for (int v = 0; v < 8; ++v) {
+                    const int4 q = rp[v];
+                    const int wd[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) {
+#pragma unroll
+                        for (int e2 = 0; e2 < 2; ++e2) {
+                            const int xi = e2 ? (wd[h] >> 16) : (int)(short)(wd[h] & 0xFFFF);
+                            float tt = fmaf((float)xi, k0, k1);
+#pragma unroll
+                            for (int s = 0; s < NSEC; ++s) {
+                                const float y = tt + z0[s];
+                                z0[s] = fmaf(-a1[s], y, fmaf(sg[s], tt, z1[s]));
+                                z1[s] = fmaf(-a2[s], y, tt);
+                                tt = y;
+                            }
+                            yo[v * 8 + h * 2 + e2] = tt;
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        // ---------------- phase 2: warp-cooperative, one thread-row at a time
+        for (int r = 0; r < 32; ++r) {
+            const int Tq = __shfl_sync(0xffffffffu, T, r);
+            if (Tq == 0) continue;
+            const int nbq = __shfl_sync(0xffffffffu, nb, r), nstopq = __shfl_sync(0xffffffffu, nstop, r);
+            const int sstartq = __shfl_sync(0xffffffffu, sstart, r), sendq = __shfl_sync(0xffffffffu, send, r);
+            float* yc = ycur + r * AX_F32_YROW;
+            float* yp = yprev + r * AX_F32_YROW;
+            // -------- 2a: fp64 re-evaluation of the samples of the current row that are too close to zero
+            if (t < Tq) {
+                const int base = nbq + 64 * t;
+#pragma unroll 1
+                for (int half = 0; half < 2; ++half) {
+                    const int p = half * 32 + lane, n = base + p;
+                    const float y = yc[p];
+                    const bool flag = (n < nstopq) && (n >= sstartq) && (n <= sendq) && (fabsf(y) < G);
+                    unsigned ball = __ballot_sync(0xffffffffu, flag);
+                    while (ball) {
+                        const int L = __ffs((int)ball) - 1;
+                        ball &= ball - 1;
+                        const int nf = base + half * 32 + L;
+                        double part = ax_fir_partial(xdrop, nf, c.fir_h, c.fir_len, lane, 32);
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+                        if (lane == 0) {
+                            const double y64 = ax_fir_finish(part, nf, c, st);
+                            const float old = yc[half * 32 + L];
+                            float fixed = (float)y64;
+                            if (fixed == 0.f && y64 != 0.0) fixed = copysignf(1e-37f, (float)(y64 < 0.0 ? -1.0 : 1.0));
+                            yc[half * 32 + L] = fixed;
+                            errmax = fmaxf(errmax, fabsf((float)(y64 - (double)old)));
+                            ++nre;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+            // -------- 2b: crossings of the previous row and their mark / space windows
+            if (t >= 1 && t - 1 < Tq) {
+                const int base = nbq + 64 * (t - 1);
+                const bool have_cur = t < Tq;
+#pragma unroll 1
+                for (int half = 0; half < 2; ++half) {
+                    const int p = half * 32 + lane, i = base + p;
+                    const float y0 = yp[p];
+                    const float y1 = (p < 63) ? yp[p + 1] : (have_cur ? yc[0] : 0.f);
+                    const bool ok = (i >= sstartq) && (i < sendq) && (i + 1 < nstopq);
+                    unsigned ball = __ballot_sync(0xffffffffu, ok && ((y0 < 0.f) != (y1 < 0.f)));
+                    while (ball) {
+                        const int L = __ffs((int)ball) - 1;
+                        ball &= ball - 1;
+                        const int pc = half * 32 + L;            // crossing position inside the previous row
+                        float sr1 = 0.f, si1 = 0.f, sr2 = 0.f, si2 = 0.f;
+                        bool complete = (base + pc + npcm < nstopq);
+#pragma unroll
+                        for (int rep = 0; rep < 2; ++rep) {
+                            const int m = rep * 32 + lane;
+                            if (m < npcm) {
+                                const int qpos = pc + 1 + m;
+                                const float yv = (qpos < 64) ? yp[qpos] : (have_cur ? yc[qpos - 64] : 0.f);
+                                const float4 tb = tabf[m];
+                                sr1 = fmaf(yv, tb.x, sr1); si1 = fmaf(yv, tb.y, si1);
+                                sr2 = fmaf(yv, tb.z, sr2); si2 = fmaf(yv, tb.w, si2);
+                            }
+                        }
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            sr1 += __shfl_xor_sync(0xffffffffu, sr1, o); si1 += __shfl_xor_sync(0xffffffffu, si1, o);
+                            sr2 += __shfl_xor_sync(0xffffffffu, sr2, o); si2 += __shfl_xor_sync(0xffffffffu, si2, o);
+                        }
+                        if (lane == 0) {
+                            const int cnt = count[warp * 32 + r];
+                            if (cnt < w.seg_cap) {
+                                const int64_t o = slot0 + (int64_t)(r - lane) * w.seg_cap + cnt;      // slot of thread-row r (lane == 0 here)
+                                w.rec_idx[o] = base + pc;
+                                w.rec_a1[o] = complete ? (double)sqrtf(sr1 * sr1 + si1 * si1) : ax_nan();
+                                w.rec_a2[o] = complete ? (double)sqrtf(sr2 * sr2 + si2 * si2) : ax_nan();
+                            }
+                            count[warp * 32 + r] = cnt + 1;
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+    __syncwarp();
+    if (active) {
+        int cnt = count[threadIdx.x];
+        if (cnt > w.seg_cap) { w.flags[AX_FLAG_CAP] = 1; cnt = w.seg_cap; }
+        w.seg_cnt[seg] = cnt;
+    } else w.seg_cnt[seg] = 0;
+    if (lane == 0 && nre > 0) {
+        atomicAdd(&st.n_recheck, nre);
+        atomicMax(&st.err32_bits, __float_as_int(errmax));
+    }
+}
+
+template <int NSEC>
+static inline void ax_launch_filter32(const AxWave& w, cudaStream_t stream) {
+    const size_t smem = 64 * sizeof(float4) + 2 * AX_FS_STAGE * sizeof(int16_t) +
+                        2 * AX_FS_THREADS * AX_F32_YROW * sizeof(float) + AX_FS_THREADS * sizeof(int);
+    static bool attr_set = false;
+    if (!attr_set) { cudaFuncSetAttribute(k_filter32<NSEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr_set = true; }
+    k_filter32<NSEC><<<w.nseg_total / AX_FS_THREADS, AX_FS_THREADS, smem, stream>>>(w);
+}
+
 // ------------------------------------------------------------------ tones
 #define AX_TONE_WARPS 8
 #define AX_TONE_R 4          // blocks per warp pass (register blocking against the smem table)

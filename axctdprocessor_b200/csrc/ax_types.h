@@ -78,6 +78,9 @@ struct AxCfg {
     const double* lut;           // [lut_len]
     const double* hist_edges;    // [n_hist_edges]
     const double* hist_centers;  // [n_hist_edges-1]
+    const double* fir_h;         // [fir_len] impulse response of the SOS cascade (fp64 re-evaluation of single samples)
+    const double* fir_hc;        // [fir_len] running sum of fir_h (response to the constant -dc/ampl term)
+    int32_t fir_len, pad_fir;
     int32_t lut_len, n_hist_edges;
 };
 
@@ -121,6 +124,8 @@ struct AxState {
     int64_t sum;
     int32_t ampl;
     int32_t n_uncertain;
+    int32_t n_recheck;           // samples re-evaluated in fp64 by the fp32 filter pass
+    int32_t err32_bits;          // max |y64 - y32| seen at re-evaluated samples (float bits)
     double dc, inv_ampl, ampl_d;
     int64_t zc_count;
     // state machine
@@ -188,6 +193,8 @@ struct AxWave {
     // frames
     axctd_frame* frame;
     double guard;
+    float guard32;               // fp32 filter pass: samples with |y| below this are re-evaluated in fp64
+    int32_t bitfix_all;          // test hook: re-evaluate every bit decision in fp64
     int32_t tone_direct;
     int32_t pa_lo, pa_hi;        // fixed-grid chunk range of the current detection round
     int32_t force_exact;
