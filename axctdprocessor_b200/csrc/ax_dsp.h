@@ -102,31 +102,87 @@ AX_HD bool ax_sos_is_butter(const AxCfg& c) {
     return true;
 }
 
-// Per-thread state of the continuous filter pass over one segment: the SOS
-// cascade (direct form II transposed as scipy's _sosfilt, with FMAs: this pass
-// only has to agree with the exact zero-state restart to ~1e-16 of peak, and
-// samples inside `guard` of zero are flagged), the zero-crossing detector
-// (demodulate.py:77-79) and, for every crossing i, |sum y[i+1..i+npcm] e^{j theta_f m}|
-// for the mark and space tones (demodulate.py:99-102) from re-anchored prefix sums.
-// BUTTER: 4 double-precision operations per section (5 in section 0, which also
-// absorbs the (x - mean)/max|x| normalisation of AXCTDprocessor.py:57).
+// ------------------------------------------------------------------ bit windows
+// demodulate.py:99-102: |sum_m y[i+1+m] e^{j theta_f m}| for the mark and space tones over the
+// npcm samples after crossing i.  Only the magnitude is used, so the phase reference is free:
+// the window is evaluated over the aligned quads of samples that cover it, tap k of the first
+// quad carrying e^{j theta_f k}, with the taps outside the window masked to zero.  The samples
+// are the float roundings of the double-precision filter output and the sums run in fp32 (eight
+// chains); a decision that this precision cannot make is re-made from ax_gwin_* in double.
+AX_HD int ax_win_quads(int npcm) { return (npcm + 6) >> 2; }     // quads covering offset o <= 3 plus npcm taps
+
+// yv[k], k < 4*ax_win_quads(npcm): samples of the aligned quads; o = (i + 1) & 3
+AX_HD void ax_window32(const float* yv, int o, int npcm, const AxWinTab& tab, float* a1, float* a2) {
+    float r1a = 0.f, i1a = 0.f, r2a = 0.f, i2a = 0.f, r1b = 0.f, i1b = 0.f, r2b = 0.f, i2b = 0.f;
+    const int nt = 4 * ax_win_quads(npcm);
+#pragma unroll
+    for (int k = 0; k < AX_WIN_TAPS; k += 2) {
+        if (k < nt) {
+            const float ya = (k >= o && k < o + npcm) ? yv[k] : 0.f;
+            const float yb = (k + 1 >= o && k + 1 < o + npcm) ? yv[k + 1] : 0.f;
+            r1a = fmaf(ya, tab.t[k].x, r1a); i1a = fmaf(ya, tab.t[k].y, i1a);
+            r2a = fmaf(ya, tab.t[k].z, r2a); i2a = fmaf(ya, tab.t[k].w, i2a);
+            r1b = fmaf(yb, tab.t[k + 1].x, r1b); i1b = fmaf(yb, tab.t[k + 1].y, i1b);
+            r2b = fmaf(yb, tab.t[k + 1].z, r2b); i2b = fmaf(yb, tab.t[k + 1].w, i2b);
+        }
+    }
+    const float r1 = r1a + r1b, i1 = i1a + i1b, r2 = r2a + r2b, i2 = i2a + i2b;
+    *a1 = sqrtf(fmaf(r1, r1, i1 * i1));
+    *a2 = sqrtf(fmaf(r2, r2, i2 * i2));
+}
+
+// The same two magnitudes in double precision, straight from the int16 samples: with h the
+// impulse response of the SOS cascade and u = (x - dc) / ampl,
+//   S_f(i) = sum_m e^{j theta_f m} y[i+1+m] = sum_{d >= 0} u[i + npcm - d] * G_f[d],
+//   G_f[d] = sum_m e^{j theta_f m} h[d - (npcm - 1 - m)]            (host, long double)
+// truncated at the sample q0 where the filter state was zero (the start of the recording or, for
+// the reference's per-chunk restart, the chunk start).  Partial sums over d = lane, lane+nl, ...
+AX_HD void ax_gwin_partial(const int16_t* x, int64_t i, int64_t q0, const AxCfg& c, int lane, int nl, double* acc) {
+    const int64_t n_end = i + c.npcm;
+    int64_t D = n_end - q0;
+    if (D > (int64_t)c.g_len - 1) D = (int64_t)c.g_len - 1;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    for (int64_t d = lane; d <= D; d += nl) {
+        const double xv = (double)x[n_end - d];
+        const double* g = c.gtab + 4 * d;
+        s0 = ax_fma(xv, g[0], s0); s1 = ax_fma(xv, g[1], s1); s2 = ax_fma(xv, g[2], s2); s3 = ax_fma(xv, g[3], s3);
+    }
+    acc[0] = s0; acc[1] = s1; acc[2] = s2; acc[3] = s3;
+}
+AX_HD void ax_gwin_finish(const double* acc, int64_t i, int64_t q0, const AxCfg& c, const AxState& st, double* a1, double* a2) {
+    int64_t D = i + c.npcm - q0;
+    if (D > (int64_t)c.g_len - 1) D = (int64_t)c.g_len - 1;
+    const double* gc = c.gcum + 4 * D;
+    double S[4];
+    for (int q = 0; q < 4; ++q) S[q] = (acc[q] - st.dc * gc[q]) * st.inv_ampl;
+    *a1 = hypot(S[0], S[1]);
+    *a2 = hypot(S[2], S[3]);
+}
+
+// Per-thread state of the continuous filter pass over one segment (generic form; the sm_100a
+// production kernel is k_demod_fused in ax_kernels.cuh, which computes the same values): the SOS
+// cascade (direct form II transposed as scipy's _sosfilt, with FMAs: this pass only has to agree
+// with the exact zero-state restart to ~1e-16 of peak, and samples inside `guard` of zero are
+// flagged), the zero-crossing detector (demodulate.py:77-79) and the float bit windows above.
+// BUTTER: 4 double-precision operations per section (5 in section 0, which also absorbs the
+// (x - mean)/max|x| normalisation of AXCTDprocessor.py:57).
 template <int NSEC, bool BUTTER>
 struct AxFilt {
     double z0[NSEC], z1[NSEC], a1[NSEC], a2[NSEC];
     double sg[NSEC];                 // BUTTER: b1/b0 = +-2
     double b0[NSEC], b1[NSEC], b2[NSEC];   // general form
     double k0, k1;
-    double C0, C1, C2, C3;
-    double snap[AX_PEND][4];
+    float yring[128];                // float filter output, index n & 127
     int32_t tgt[AX_PEND], idx[AX_PEND];
-    int32_t np, head, next_tgt, m, cnt, unc, R, npcm, cap;   // pending windows: ring in local memory
+    int32_t np, head, next_tgt, cnt, unc, npcm, cap;   // pending windows: ring in local memory
     int32_t seg_start, seg_end;
     bool prev_neg, have_prev;
-    double guard, rot00, rot01, rot10, rot11;
-    int32_t* rec_idx; double* rec_a1; double* rec_a2;
+    double guard;
+    const AxWinTab* tab;
+    int32_t* rec_idx; float* rec_a1; float* rec_a2;
 
     AX_HD void init(const AxCfg& c, const AxState& st, int32_t s0, int32_t s1, double guard_,
-                    int32_t* ri, double* r1, double* r2, int32_t cap_) {
+                    int32_t* ri, float* r1, float* r2, int32_t cap_) {
         const double kmul = st.inv_ampl, kadd = -(st.dc * st.inv_ampl);
 #pragma unroll
         for (int s = 0; s < NSEC; ++s) {
@@ -136,10 +192,10 @@ struct AxFilt {
             sg[s] = (c.sos[s][1] < 0.0) ? -2.0 : 2.0;
         }
         if (BUTTER) { k0 = c.sos[0][0] * kmul; k1 = c.sos[0][0] * kadd; } else { k0 = kmul; k1 = kadd; }
-        C0 = C1 = C2 = C3 = 0.0;
-        np = 0; head = 0; next_tgt = 0x7fffffff; m = 0; cnt = 0; unc = 0; R = c.rebase; npcm = c.npcm; cap = cap_;
+        for (int q = 0; q < 128; ++q) yring[q] = 0.f;
+        np = 0; head = 0; next_tgt = 0x7fffffff; cnt = 0; unc = 0; npcm = c.npcm; cap = cap_;
         seg_start = s0; seg_end = s1; prev_neg = false; have_prev = false; guard = guard_;
-        rot00 = c.rot[0][0]; rot01 = c.rot[0][1]; rot10 = c.rot[1][0]; rot11 = c.rot[1][1];
+        tab = &c.win_tab;
         rec_idx = ri; rec_a1 = r1; rec_a2 = r2;
     }
 
@@ -167,7 +223,7 @@ struct AxFilt {
         }
     }
 
-    AX_HD void put(int32_t i, double v1, double v2) {
+    AX_HD void put(int32_t i, float v1, float v2) {
         if (cnt < cap) { rec_idx[cnt] = i; rec_a1[cnt] = v1; rec_a2[cnt] = v2; }
         ++cnt;
     }
@@ -177,49 +233,39 @@ struct AxFilt {
         next_tgt = np > 0 ? tgt[head] : 0x7fffffff;
     }
 
-    // one sample: n = index within the drop, xd = (double) int16 sample, tab = [R][4] cos/sin table
-    AX_HD void step(int32_t n, double xd, const double* tab) {
+    // one sample: n = index within the drop, xd = (double) int16 sample
+    AX_HD void step(int32_t n, double xd) {
         const double u = filter(xd);
         const bool neg = u < 0.0;
         if (have_prev && neg != prev_neg) {
             const int32_t i = n - 1;
             if (i >= seg_start && i < seg_end) {
-                if (np == AX_PEND) { put(idx[head], ax_nan(), ax_nan()); ++unc; pop(); }   // cannot happen for a 1200 Hz band limit
+                if (np == AX_PEND) { put(idx[head], (float)ax_nan(), (float)ax_nan()); ++unc; pop(); }   // cannot happen for a 1200 Hz band limit
                 const int q = (head + np) & (AX_PEND - 1);
-                snap[q][0] = C0; snap[q][1] = C1; snap[q][2] = C2; snap[q][3] = C3;
                 tgt[q] = i + npcm; idx[q] = i;
                 if (np == 0) next_tgt = i + npcm;
                 np++;
             }
         }
-        const double* t4 = tab + 4 * m;
-        C0 = ax_fma(u, t4[0], C0); C1 = ax_fma(u, t4[1], C1);
-        C2 = ax_fma(u, t4[2], C2); C3 = ax_fma(u, t4[3], C3);
+        yring[n & 127] = (float)u;
         if (next_tgt == n) {
-            put(idx[head], hypot(C0 - snap[head][0], C1 - snap[head][1]), hypot(C2 - snap[head][2], C3 - snap[head][3]));
+            const int32_t i = idx[head];
+            const int32_t a = (i + 1) & ~3, o = (i + 1) & 3;
+            float yv[AX_WIN_TAPS];
+            const int nt = 4 * ax_win_quads(npcm);
+            for (int k = 0; k < nt; ++k) yv[k] = yring[(a + k) & 127];
+            float v1, v2;
+            ax_window32(yv, o, npcm, *tab, &v1, &v2);
+            put(i, v1, v2);
             pop();
         }
         if (fabs(u) < guard && n >= seg_start && n < seg_end) ++unc;
-        if (++m == R) {
-            // re-anchor the phase reference: snap' = -(C - snap) * e^{-j theta R}; C = 0
-            for (int k = 0; k < np; ++k) {
-                const int q = (head + k) & (AX_PEND - 1);
-                double pr = C0 - snap[q][0], pi = C1 - snap[q][1];
-                snap[q][0] = -(pr * rot00 - pi * rot01);
-                snap[q][1] = -(pr * rot01 + pi * rot00);
-                pr = C2 - snap[q][2]; pi = C3 - snap[q][3];
-                snap[q][2] = -(pr * rot10 - pi * rot11);
-                snap[q][3] = -(pr * rot11 + pi * rot10);
-            }
-            C0 = C1 = C2 = C3 = 0.0;
-            m = 0;
-        }
         prev_neg = neg; have_prev = true;
     }
 
     // windows that run past the end of the recording can never be demodulated
     AX_HD void finish() {
-        while (np > 0) { put(idx[head], ax_nan(), ax_nan()); pop(); }
+        while (np > 0) { put(idx[head], (float)ax_nan(), (float)ax_nan()); pop(); }
     }
 };
 
@@ -246,7 +292,7 @@ AX_HDN inline void ax_filter_segment(const AxWave& w, int64_t seg) {
     const int64_t slot = seg * (int64_t)w.seg_cap;
     AxFilt<NSEC, BUTTER> f;
     f.init(c, st, (int32_t)g.seg_start, (int32_t)g.seg_end, w.guard, w.rec_idx + slot, w.rec_a1 + slot, w.rec_a2 + slot, w.seg_cap);
-    for (int64_t n = g.n_begin; n < g.n_stop; ++n) f.step((int32_t)n, (double)x[n], c.bit_cs);
+    for (int64_t n = g.n_begin; n < g.n_stop; ++n) f.step((int32_t)n, (double)x[n]);
     f.finish();
     if (f.cnt > w.seg_cap) { w.flags[AX_FLAG_CAP] = 1; f.cnt = w.seg_cap; }
     w.seg_cnt[seg] = f.cnt;
@@ -293,26 +339,6 @@ AX_HDN inline void ax_compact_item(const AxWave& w, int64_t seg) {
         w.zc_a1[dst + q] = w.rec_a1[src + q];
         w.zc_a2[dst + q] = w.rec_a2[src + q];
     }
-}
-
-// ------------------------------------------------------------------ fp64 point evaluation
-// y[n] of the continuous (zero state at the start of the recording) SOS cascade as a direct
-// convolution with its impulse response: sum_m h[m] * (x[n-m] - dc) / ampl.  Used to re-decide,
-// in double precision, single samples / windows where the fp32 pass is too close to call.
-// Returns the partial sum over taps m = lane, lane+nl, ...; the caller adds the partials and
-// finishes with ax_fir_finish.
-AX_HD double ax_fir_partial(const int16_t* x, int64_t n, const double* h, int K, int lane, int nl) {
-    const int64_t mmax = (n + 1 < (int64_t)K) ? n + 1 : (int64_t)K;
-    double acc = 0.0;
-    for (int64_t m = lane; m < mmax; m += nl) acc = ax_fma(h[m], (double)x[n - m], acc);
-    return acc;
-}
-AX_HD double ax_fir_finish(double sum, int64_t n, const AxCfg& c, const AxState& st) {
-    const int64_t mc = (n + 1 < (int64_t)c.fir_len) ? n : (int64_t)c.fir_len - 1;
-    return (sum - st.dc * c.fir_hc[mc]) * st.inv_ampl;
-}
-AX_HD double ax_fir_y64(const int16_t* x, int64_t n, const AxCfg& c, const AxState& st) {
-    return ax_fir_finish(ax_fir_partial(x, n, c.fir_h, c.fir_len, 0, 1), n, c, st);
 }
 
 // ------------------------------------------------------------------ walk

@@ -79,7 +79,7 @@ AX_GLOBAL void k_plan_tones(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_plan_tones_
 AX_GLOBAL void k_offsets(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_offsets_item(w, item); }
 AX_GLOBAL void k_emit(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_emit_item(w, item); }
 AX_GLOBAL void k_scale(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_scale_item(w, item); }
-AX_GLOBAL void k_bits(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_bits_item(w, item); }
+AX_GLOBAL void k_bits(int64_t n, AxWave w, int phase) { AX_FOR_ITEM(n) ax_bits_item(w, item, phase); }
 AX_GLOBAL void k_headers(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_header_item(w, item); }
 AX_GLOBAL void k_pack(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_pack_item(w, item); }
 AX_GLOBAL void k_valid(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_valid_item(w, item); }
@@ -109,8 +109,9 @@ struct axctd_engine {
     int opt_filter_variant = 0;
     int opt_zc_div = 12;
     int opt_inject_misspec = 0;           // test hook: corrupt the first prediction
-    double opt_guard32 = 5e-5;            // fp32 filter pass guard band (of full scale)
-    int opt_bitfix_all = 0;               // test hook
+    double opt_bit_tol = 2e-5;            // fp32 bit windows: relative distance to a decision boundary that triggers
+    double opt_hist_tol = 2e-5;           //   the double-precision re-evaluation (bit decision / calibration histogram)
+    int opt_bitfix_all = 0;               // test hook: re-evaluate every window
 };
 
 #ifdef AXCTD_EMU
@@ -243,7 +244,8 @@ extern "C" int axctd_engine_set_option(axctd_engine* e, const char* name, double
     else if (s == "filter_variant") e->opt_filter_variant = (int)v;
     else if (s == "zc_div") e->opt_zc_div = std::max(2, (int)v);
     else if (s == "inject_misspec") e->opt_inject_misspec = (int)v;
-    else if (s == "guard32") e->opt_guard32 = v;
+    else if (s == "bit_tol") e->opt_bit_tol = v;
+    else if (s == "hist_tol") e->opt_hist_tol = v;
     else if (s == "bitfix_all") e->opt_bitfix_all = (int)v;
     else return AXCTD_ERR_ARG;
     return AXCTD_OK;
@@ -305,12 +307,16 @@ extern "C" int axctd_config_create(axctd_engine* e, const axctd_config_desc* ds,
     const double* bc = ds->bit_cs + 4 * (size_t)c.rebase;      // e^{+j theta R}; store the conjugate
     c.rot[0][0] = bc[0]; c.rot[0][1] = -bc[1]; c.rot[1][0] = bc[2]; c.rot[1][1] = -bc[3];
     c.lut_len = ds->lut_len; c.n_hist_edges = ds->n_hist_edges;
-    {   // impulse response of the cascade, long enough for the tail to fall below 1e-18
+    if (ds->bit_cs_len < AX_WIN_TAPS) { e->err = "bit_cs table shorter than 48 entries"; return AXCTD_ERR_ARG; }
+    for (int k = 0; k < AX_WIN_TAPS; ++k) {
+        const double* t4 = ds->bit_cs + 4 * (size_t)k;
+        c.win_tab.t[k].x = (float)t4[0]; c.win_tab.t[k].y = (float)t4[1]; c.win_tab.t[k].z = (float)t4[2]; c.win_tab.t[k].w = (float)t4[3];
+    }
+    {   // window responses G_f[d] = sum_m e^{j theta_f m} h[d - (npcm-1-m)] (ax_gwin_*): impulse response h of the
+        // cascade in long double, long enough for its tail to fall below 1e-18
         int K = (int)ceil(log(1e-18) / log(r)) + 64;
         K = ((K + 31) / 32) * 32;
-        std::vector<long double> zz(2 * AX_MAXSEC, 0.0L);
-        std::vector<double> h(K), hc(K);
-        long double run = 0.0L;
+        std::vector<long double> zz(2 * AX_MAXSEC, 0.0L), h(K);
         for (int n = 0; n < K; ++n) {
             long double u = (n == 0) ? 1.0L : 0.0L;
             for (int q = 0; q < c.nsec; ++q) {
@@ -320,10 +326,23 @@ extern "C" int axctd_config_create(axctd_engine* e, const axctd_config_desc* ds,
                 zz[2 * q + 1] = b2 * u - a2 * y;
                 u = y;
             }
-            h[n] = (double)u; run += u; hc[n] = (double)run;
+            h[n] = u;
         }
-        c.fir_len = K;
-        if (ax_cfg_upload(e, &c.fir_h, h.data(), (size_t)K) || ax_cfg_upload(e, &c.fir_hc, hc.data(), (size_t)K)) return AXCTD_ERR_CUDA;
+        const int GL = K + c.npcm - 1;
+        std::vector<double> g(4 * (size_t)GL), gc(4 * (size_t)GL);
+        long double run[4] = {0, 0, 0, 0};
+        for (int d = 0; d < GL; ++d) {
+            long double acc[4] = {0, 0, 0, 0};
+            for (int m = 0; m < c.npcm; ++m) {
+                const int k = d - (c.npcm - 1 - m);
+                if (k < 0 || k >= K) continue;
+                const double* t4 = ds->bit_cs + 4 * (size_t)m;
+                for (int q = 0; q < 4; ++q) acc[q] += (long double)t4[q] * h[k];
+            }
+            for (int q = 0; q < 4; ++q) { g[4 * (size_t)d + q] = (double)acc[q]; run[q] += acc[q]; gc[4 * (size_t)d + q] = (double)run[q]; }
+        }
+        c.g_len = GL;
+        if (ax_cfg_upload(e, &c.gtab, g.data(), g.size()) || ax_cfg_upload(e, &c.gcum, gc.data(), gc.size())) return AXCTD_ERR_CUDA;
     }
     if (ax_cfg_upload(e, &c.bit_cs, ds->bit_cs, 4 * (size_t)ds->bit_cs_len) ||
         ax_cfg_upload(e, &c.tone_cs, ds->tone_cs, 6 * (size_t)ds->n_power) ||
@@ -384,7 +403,7 @@ extern "C" int axctd_batch_create(axctd_engine* e, int n_drops, const int64_t* n
     w.n_drops = n_drops; w.n_cfg = (int)e->cfgs.size(); w.cfg = e->d_cfg;
     w.seg_len = (int32_t)L; w.seg_cap = (int32_t)(L / 8 + 32);
     w.guard = e->opt_guard; w.tone_direct = e->opt_tone_direct; w.force_exact = e->opt_force_exact;
-    w.guard32 = (float)e->opt_guard32; w.bitfix_all = e->opt_bitfix_all;
+    w.bit_tol = e->opt_bit_tol; w.hist_tol = e->opt_hist_tol; w.bitfix_all = e->opt_bitfix_all;
     w.head_zc_cap_max = head_cap_max; w.ybuf_len_max = ybuf_max; w.blk_stride = blk_max;
     b->drops.resize(n_drops);
     int64_t pcm_off = 0, zc_off = 0, edge_off = 0;
@@ -501,7 +520,7 @@ static bool ax_coeff_from_frames(const uint16_t* f3, double* out) {
     if (!ax_py_int(hex, 9, &mant) || !ax_py_int(hex + 9, 3, &ex)) return false;
     const double a = (double)mant / 1e7;
     double p;
-    if (ex >= 0) { char buf[16]; snprintf(buf, sizeof(buf), "1e%lld", ex); p = strtod(buf, nullptr); }   // python int 10**ex -> float
+    if (ex >= 0) { char buf[32]; snprintf(buf, sizeof(buf), "1e%lld", ex); p = strtod(buf, nullptr); }   // python int 10**ex -> float
     else p = pow(10.0, (double)ex);                                                                    // python float pow
     *out = a * p;
     return true;
@@ -592,24 +611,16 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
     AX_LAUNCH(e, k_stats_fin, n, w);
     AX_EVENT(b, 1);
 #ifndef AXCTD_EMU
-    if (e->opt_filter_variant == 0) {
-        // staged kernel: one instantiation per (sections, form) in use; CTAs of other configs exit at once
-        int rebase_max = 1;
-        bool need[4] = {false, false, false, false};      // <3,butter> <6,butter> <3,general> <6,general>
-        bool generic = false;
-        for (const AxDrop& dr : b->drops) {
-            const AxCfg& c = e->cfgs[dr.cfg];
-            rebase_max = std::max(rebase_max, c.rebase);
-            const bool bt = ax_sos_is_butter(c);
-            if (c.nsec == 3) need[bt ? 0 : 2] = true; else if (c.nsec == 6) need[bt ? 1 : 3] = true; else generic = true;
+    bool fused = e->opt_filter_variant == 0;
+    std::vector<int> used_cfg;
+    for (size_t ci = 0; ci < e->cfgs.size(); ++ci)
+        if (std::any_of(b->drops.begin(), b->drops.end(), [&](const AxDrop& d) { return d.cfg == (int)ci; })) {
+            used_cfg.push_back((int)ci);
+            if (!ax_demod_fused_ok(e->cfgs[ci])) fused = false;
         }
-        if (generic || (size_t)rebase_max * 32 > 96 * 1024) { AX_LAUNCH(e, k_filter, (int64_t)w.nseg_total, w); }
-        else {
-            if (need[0]) { ax_launch_filter_variant<3, true>(w, rebase_max, e->stream); e->launches++; }
-            if (need[1]) { ax_launch_filter_variant<6, true>(w, rebase_max, e->stream); e->launches++; }
-            if (need[2]) { ax_launch_filter_variant<3, false>(w, rebase_max, e->stream); e->launches++; }
-            if (need[3]) { ax_launch_filter_variant<6, false>(w, rebase_max, e->stream); e->launches++; }
-        }
+    if (fused) {
+        // one launch per rate class in use (CTAs of the other classes exit at once)
+        for (int ci : used_cfg) { ax_launch_demod_fused_any(w, e->cfgs[ci], ci, e->stream); e->launches++; }
     } else
 #endif
     { AX_LAUNCH(e, k_filter, (int64_t)w.nseg_total, w); }
@@ -654,8 +665,14 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
     AX_LAUNCH(e, k_sm, n, w, 1);
     AX_LAUNCH(e, k_offsets, n, w);
     AX_LAUNCH(e, k_emit, b->chunk_total, w);
+#ifndef AXCTD_EMU
+#define AX_BITS(phase) do { k_bits_warp<<<(unsigned)((b->edge_total + 127) / 128), 128, 0, e->stream>>>(w, b->edge_total, phase); e->launches++; } while (0)
+#else
+#define AX_BITS(phase) AX_LAUNCH(e, k_bits, b->edge_total, w, phase)
+#endif
+    AX_BITS(0);
     AX_LAUNCH(e, k_scale, n, w);
-    AX_LAUNCH(e, k_bits, b->edge_total, w);
+    AX_BITS(1);
     AX_LAUNCH(e, k_headers, 2 * (int64_t)n, w);
     // header text -> calibration coefficients on the host (python float semantics)
     if (ax_d2h(e, b->st.data(), w.st, sizeof(AxState) * n) || ax_sync(e)) return AXCTD_ERR_CUDA;
@@ -712,6 +729,7 @@ extern "C" int axctd_batch_finish(axctd_batch* b) {
         sm.n_frames = st.n_frames; sm.n_crossings = st.zc_count;
         sm.n_uncertain = st.n_uncertain; sm.n_chain_fixups = st.n_fixups;
         sm.pcm_sum = st.sum; sm.pcm_ampl = st.ampl;
+        sm.n_recheck = st.n_recheck; memcpy(&sm.win32_max_rel_err, &st.err32_bits, sizeof(float)); sm.reserved = 0;
         memcpy(sm.frame_data, st.frame_data, sizeof(sm.frame_data));
         memcpy(sm.counter_found, st.counter_found, sizeof(sm.counter_found));
         sm.header_parsed[0] = st.header_parsed[0]; sm.header_parsed[1] = st.header_parsed[1];

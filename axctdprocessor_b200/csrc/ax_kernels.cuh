@@ -61,16 +61,35 @@ static inline void ax_launch_stats(const AxWave& w, cudaStream_t stream) {
     if (w.nslab_total > 0) k_stats_coalesced<<<w.nslab_total, 256, 0, stream>>>(w);
 }
 
-// ------------------------------------------------------------------ filter (staged)
-// One thread per segment, as ax_filter_segment, but the int16 samples reach the
-// threads through shared memory: each warp copies, with 16-byte cp.async, one
-// full 128-byte line (64 samples) per thread per stage, double buffered, and
-// every thread then reads its own row with conflict-free 128-bit LDS.  The
-// cos/sin table of the bit windows sits in shared memory as well (one config
-// per CTA: segment ranges are padded to multiples of 128 per drop).
-#define AX_FS_THREADS 128
-#define AX_FS_ROW 72                                  // 64 samples + 8 pad (144-byte row stride)
-#define AX_FS_STAGE (4 * 32 * AX_FS_ROW)              // int16 elements per stage
+// ------------------------------------------------------------------ fused demodulation pass
+// k_demod_fused: int16 PCM -> normalise -> Butterworth SOS cascade (double) -> zero crossings
+// (demodulate.py:74-79) -> mark / space window magnitudes after every crossing (demodulate.py:99-102).
+//
+// Work decomposition: one lane per segment of seg_len samples (plus the warm-up overlap), 64 samples
+// ("a row") per iteration; a warp therefore advances 32 independent filter recurrences in lockstep.
+//   staging  each warp copies one 128-byte line per lane per stage with 16-byte cp.async (LDGSTS),
+//            double buffered, into lane-major rows that the owner reads back with conflict-free LDS.128;
+//   phase 1  the owner lane runs the cascade over its 64 samples (13 DFMA-pipe operations per sample for
+//            three sections), collects the sign bits in registers and stores the float roundings of y
+//            into its 128-sample ring in shared memory (STS.128, conflict free);
+//   phase 2  the crossings of the previous row are compacted across the warp and dealt to the lanes one
+//            each, so the 4*NPCM-FMA fp32 windows (ax_window32, phasors as constant-bank operands) run
+//            without divergence whatever the crossing density of the individual rows.
+// y never leaves the SM; the only global traffic is the int16 stream in and (index, |S1|, |S2|) per
+// crossing out.
+#define AX_FD_WARPS 4
+#define AX_FD_THREADS (AX_FD_WARPS * 32)
+#define AX_FD_ROW 72                                   // int16 per staged row: 64 samples + 8 pad (144-byte stride)
+#define AX_FD_STAGE (32 * AX_FD_ROW)                   // int16 per warp per stage
+#define AX_FD_YSTRIDE 132                              // floats per lane ring: 128 + 4 pad (33 quads: conflict-free STS.128)
+#define AX_FD_LIST 256                                 // crossings dealt per pass
+
+struct AxFdSmem {
+    int16_t stage[2][AX_FD_STAGE];
+    float yring[32 * AX_FD_YSTRIDE];
+    uint32_t list[AX_FD_LIST];
+    int32_t row_begin[32], row_stop[32];
+};
 
 __device__ __forceinline__ void ax_cp_async16(void* smem_dst, const void* gsrc) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -80,131 +99,17 @@ __device__ __forceinline__ void ax_cp_async_commit() { asm volatile("cp.async.co
 template <int N>
 __device__ __forceinline__ void ax_cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-template <int NSEC, bool BUTTER>
-__global__ void __launch_bounds__(AX_FS_THREADS) k_filter_staged(AxWave w) {
-    extern __shared__ __align__(16) unsigned char ax_smem[];
-    const int d = w.seg_drop[(int64_t)blockIdx.x * AX_FS_THREADS];
+template <int NSEC, int NPCM>
+__global__ void __launch_bounds__(AX_FD_THREADS, 2) k_demod_fused(const __grid_constant__ AxWave w, const __grid_constant__ AxWinTab tab, int cfg_id) {
+    extern __shared__ __align__(16) unsigned char ax_smem_raw[];
+    const int d = w.seg_drop[(int64_t)blockIdx.x * AX_FD_THREADS];
     const AxDrop& dr = w.drop[d];
-    const AxCfg& c = w.cfg[dr.cfg];
-    if (c.nsec != NSEC || ax_sos_is_butter(c) != BUTTER) return;      // another instantiation handles this drop
+    if (dr.cfg != cfg_id) return;                       // another launch handles this rate class
+    const AxCfg& c = w.cfg[cfg_id];
     AxState& st = w.st[d];
-    const int R = c.rebase;
-    double* tab = reinterpret_cast<double*>(ax_smem);                   // [R][4]
-    int16_t* stage = reinterpret_cast<int16_t*>(ax_smem + (size_t)R * 4 * sizeof(double));
-    for (int i = threadIdx.x; i < 4 * R; i += AX_FS_THREADS) tab[i] = c.bit_cs[i];
-    __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t seg = (int64_t)blockIdx.x * AX_FS_THREADS + threadIdx.x;
-    const int64_t j = seg - dr.seg_base;
-    const bool active = j < dr.nseg;
-    AxSegGeom g;
-    g.seg_start = g.seg_end = g.n_begin = g.n_stop = 0;
-    if (active) g = ax_seg_geom(dr, c, w.seg_len, j);
-    const int T = active ? (int)((g.n_stop - g.n_begin + 63) >> 6) : 0;
-    int Tmax = T;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) Tmax = max(Tmax, __shfl_xor_sync(0xffffffffu, Tmax, o));
-    const unsigned long long xrow = (unsigned long long)(w.pcm + dr.pcm_off + g.n_begin);   // 16-byte aligned
-    const int64_t slot = seg * (int64_t)w.seg_cap;
-    AxFilt<NSEC, BUTTER> f;
-    f.init(c, st, (int32_t)g.seg_start, (int32_t)g.seg_end, w.guard, w.rec_idx + slot, w.rec_a1 + slot, w.rec_a2 + slot, w.seg_cap);
-    int16_t* wst = stage + warp * (32 * AX_FS_ROW);
-    const int prow = lane >> 3, piece = lane & 7;
-    // rows this lane helps to copy: r = i*4 + prow, i = 0..7
-    unsigned long long src[8];
-    int Tr[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        src[i] = __shfl_sync(0xffffffffu, xrow, i * 4 + prow) + (unsigned long long)piece * 16;
-        Tr[i] = __shfl_sync(0xffffffffu, T, i * 4 + prow);
-    }
-    auto issue = [&](int t, int s) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-            if (t < Tr[i]) ax_cp_async16(wst + s * AX_FS_STAGE + (i * 4 + prow) * AX_FS_ROW + piece * 8,
-                                         reinterpret_cast<const void*>(src[i] + (unsigned long long)t * 128));
-        ax_cp_async_commit();
-    };
-    if (Tmax > 0) issue(0, 0);
-    for (int t = 0; t < Tmax; ++t) {
-        if (t + 1 < Tmax) { issue(t + 1, (t + 1) & 1); ax_cp_async_wait<1>(); } else ax_cp_async_wait<0>();
-        __syncwarp();
-        if (t < T) {
-            const int4* rp = reinterpret_cast<const int4*>(wst + (t & 1) * AX_FS_STAGE + lane * AX_FS_ROW);
-            int32_t n = (int32_t)g.n_begin + t * 64;
-            const int32_t n_stop = (int32_t)g.n_stop;
-#pragma unroll 1
-            for (int v = 0; v < 8; ++v) {
-                const int4 q = rp[v];
-                const int wd[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-                for (int h = 0; h < 4; ++h) {
-                    const int lo = (short)(wd[h] & 0xFFFF), hi = wd[h] >> 16;
-                    if (n < n_stop) f.step(n, (double)lo, tab);
-                    ++n;
-                    if (n < n_stop) f.step(n, (double)hi, tab);
-                    ++n;
-                }
-            }
-        }
-        __syncwarp();
-    }
-    if (!active) { w.seg_cnt[seg] = 0; return; }
-    f.finish();
-    if (f.cnt > w.seg_cap) { w.flags[AX_FLAG_CAP] = 1; f.cnt = w.seg_cap; }
-    w.seg_cnt[seg] = f.cnt;
-    if (f.unc) atomicAdd(&st.n_uncertain, f.unc);
-}
-
-template <int NSEC, bool BUTTER>
-static inline void ax_launch_filter_variant(const AxWave& w, int rebase_max, cudaStream_t stream) {
-    const size_t smem = (size_t)rebase_max * 4 * sizeof(double) + 2 * AX_FS_STAGE * sizeof(int16_t);
-    static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(k_filter_staged<NSEC, BUTTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr_set = true; }
-    k_filter_staged<NSEC, BUTTER><<<w.nseg_total / AX_FS_THREADS, AX_FS_THREADS, smem, stream>>>(w);
-}
-
-// ------------------------------------------------------------------ filter (fp32, fused)
-// The production filter pass.  B200's double-precision pipe is ~30x slower than the FP32 pipe,
-// so the streaming work runs in fp32 and double precision is spent only where a decision could
-// depend on it:
-//   phase 1 (one thread per segment): int16 -> Butterworth SOS cascade in fp32 (13 FMA-pipe
-//            operations per sample) -> y written to a per-thread row in shared memory;
-//   phase 2a (warp-cooperative): every sample with |y| < guard32 is re-evaluated in fp64 as a
-//            direct convolution with the cascade's impulse response (ax_fir_partial) and
-//            replaced, so that all signs used below are the exact filter's signs;
-//   phase 2b (warp-cooperative): zero crossings of the previous row (demodulate.py:77-79) and,
-//            for each, the mark / space single-bin DFT magnitudes of the following npcm samples
-//            (demodulate.py:99-102), 32 lanes over the window taps.
-// The PCM reaches shared memory through 16-byte cp.async copies, one full 128-byte line per
-// thread per stage, double buffered; y never leaves the SM.
-#define AX_F32_YROW 65                                 // floats per y row: 64 + 1 pad (conflict-free column access)
-
-template <int NSEC>
-__global__ void __launch_bounds__(AX_FS_THREADS, 2) k_filter32(AxWave w) {
-    extern __shared__ __align__(16) unsigned char ax_smem[];
-    const int d = w.seg_drop[(int64_t)blockIdx.x * AX_FS_THREADS];
-    const AxDrop& dr = w.drop[d];
-    const AxCfg& c = w.cfg[dr.cfg];
-    if (c.nsec != NSEC || !ax_sos_is_butter(c) || c.npcm > 64) return;
-    AxState& st = w.st[d];
-    float4* tabf = reinterpret_cast<float4*>(ax_smem);                             // [64] cos1,sin1,cos2,sin2
-    int16_t* stage = reinterpret_cast<int16_t*>(ax_smem + 64 * sizeof(float4));   // [2][4][32][72]
-    float* yrow = reinterpret_cast<float*>(ax_smem + 64 * sizeof(float4) + 2 * AX_FS_STAGE * sizeof(int16_t));   // [2][128][65]
-    int* count = reinterpret_cast<int*>(yrow + 2 * AX_FS_THREADS * AX_F32_YROW);   // [128]
-    const int npcm = c.npcm;
-    if (threadIdx.x < 64) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if ((int)threadIdx.x < npcm) {
-            const double* t4 = c.bit_cs + 4 * threadIdx.x;
-            v = make_float4((float)t4[0], (float)t4[1], (float)t4[2], (float)t4[3]);
-        }
-        tabf[threadIdx.x] = v;
-    }
-    count[threadIdx.x] = 0;
-    __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t seg = (int64_t)blockIdx.x * AX_FS_THREADS + threadIdx.x;
+    AxFdSmem& sm = reinterpret_cast<AxFdSmem*>(ax_smem_raw)[warp];
+    const int64_t seg = (int64_t)blockIdx.x * AX_FD_THREADS + threadIdx.x;
     const int64_t j = seg - dr.seg_base;
     const bool active = j < dr.nseg;
     AxSegGeom g;
@@ -215,19 +120,22 @@ __global__ void __launch_bounds__(AX_FS_THREADS, 2) k_filter32(AxWave w) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) Tmax = max(Tmax, __shfl_xor_sync(0xffffffffu, Tmax, o));
     const int16_t* xdrop = w.pcm + dr.pcm_off;
-    const unsigned long long xrow = (unsigned long long)(xdrop + g.n_begin);
-    // ---- fp32 cascade state (Butterworth form, see AxFilt)
-    float z0[NSEC], z1[NSEC], a1[NSEC], a2[NSEC], sg[NSEC];
+    const unsigned long long xrow = (unsigned long long)(xdrop + g.n_begin);      // 16-byte aligned
+    sm.row_begin[lane] = (int)g.n_begin; sm.row_stop[lane] = (int)g.n_stop;
+    // ---- cascade constants (Butterworth form, see AxFilt::filter)
+    double z0[NSEC], z1[NSEC], a1[NSEC], a2[NSEC], sg[NSEC];
 #pragma unroll
     for (int s = 0; s < NSEC; ++s) {
-        z0[s] = 0.f; z1[s] = 0.f;
-        a1[s] = (float)c.sos[s][4]; a2[s] = (float)c.sos[s][5];
-        sg[s] = (c.sos[s][1] < 0.0) ? -2.f : 2.f;
+        z0[s] = 0.0; z1[s] = 0.0;
+        a1[s] = -c.sos[s][4]; a2[s] = -c.sos[s][5];
+        sg[s] = (c.sos[s][1] < 0.0) ? -2.0 : 2.0;
     }
-    const float k0 = (float)(c.sos[0][0] * st.inv_ampl), k1 = (float)(-(c.sos[0][0] * st.dc * st.inv_ampl));
-    const float G = w.guard32;
-    int16_t* wst = stage + warp * (32 * AX_FS_ROW);
-    float* wy = yrow + (warp * 32) * AX_F32_YROW;          // this warp's 32 rows inside one y buffer
+    const double k0 = c.sos[0][0] * st.inv_ampl, k1 = c.sos[0][0] * -(st.dc * st.inv_ampl);
+    const unsigned guard_hi = (unsigned)__double2hiint(w.guard);
+    const int nb = (int)g.n_begin, nstop = (int)g.n_stop, sstart = (int)g.seg_start, send = (int)g.seg_end;
+    const int64_t slot0 = seg * (int64_t)w.seg_cap;
+    const int64_t wslot0 = (seg - lane) * (int64_t)w.seg_cap;       // slot of the warp's row 0
+    // rows this lane helps to stage: r = i*4 + prow, i = 0..7
     const int prow = lane >> 3, piece = lane & 7;
     unsigned long long src[8];
     int Tr[8];
@@ -236,163 +144,178 @@ __global__ void __launch_bounds__(AX_FS_THREADS, 2) k_filter32(AxWave w) {
         src[i] = __shfl_sync(0xffffffffu, xrow, i * 4 + prow) + (unsigned long long)piece * 16;
         Tr[i] = __shfl_sync(0xffffffffu, T, i * 4 + prow);
     }
-    const int nb = (int)g.n_begin, nstop = (int)g.n_stop, sstart = (int)g.seg_start, send = (int)g.seg_end;
-    const int64_t slot0 = seg * (int64_t)w.seg_cap;
-    float errmax = 0.f;
-    int nre = 0;
-    if (Tmax > 0) {
+    auto issue = [&](int t, int s) {
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-            if (0 < Tr[i]) ax_cp_async16(wst + (i * 4 + prow) * AX_FS_ROW + piece * 8, reinterpret_cast<const void*>(src[i]));
+            if (t < Tr[i]) ax_cp_async16(&sm.stage[s][(i * 4 + prow) * AX_FD_ROW + piece * 8],
+                                         reinterpret_cast<const void*>(src[i] + (unsigned long long)t * 128));
         ax_cp_async_commit();
-    }
+    };
+    unsigned long long Sprev = 0ull;        // sign bits of row t-1 (bit i = sample i negative)
+    int count = 0, unc = 0;
+    float* myring = sm.yring + lane * AX_FD_YSTRIDE;
+    __syncwarp();
+    if (Tmax > 0) issue(0, 0);
     for (int t = 0; t <= Tmax; ++t) {
-        float* ycur = wy + (t & 1) * (AX_FS_THREADS * AX_F32_YROW);
-        float* yprev = wy + ((t & 1) ^ 1) * (AX_FS_THREADS * AX_F32_YROW);
+        unsigned long long Scur = 0ull;
         if (t < Tmax) {
-            if (t + 1 < Tmax) {
-                const int s = (t + 1) & 1;
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    if (t + 1 < Tr[i]) ax_cp_async16(wst + s * AX_FS_STAGE + (i * 4 + prow) * AX_FS_ROW + piece * 8,
-                                                     reinterpret_cast<const void*>(src[i] + (unsigned long long)(t + 1) * 128));
-                ax_cp_async_commit();
-                ax_cp_async_wait<1>();
-            } else ax_cp_async_wait<0>();
+            if (t + 1 < Tmax) { issue(t + 1, (t + 1) & 1); ax_cp_async_wait<1>(); } else ax_cp_async_wait<0>();
             __syncwarp();
-            // ---------------- phase 1: fp32 cascade over this thread's 64 samples
+            // ---------------- phase 1: the cascade over this lane's 64 samples
             if (t < T) {
-                const int4* rp = reinterpret_cast<const int4*>(wst + (t & 1) * AX_FS_STAGE + lane * AX_FS_ROW);
-                float* yo = ycur + lane * AX_F32_YROW;
-#pragma unroll 1
-                for (int v = 0; v < 8; ++v) {
-                    const int4 q = rp[v];
-                    const int wd[4] = {q.x, q.y, q.z, q.w};
+                const int4* rp = reinterpret_cast<const int4*>(&sm.stage[t & 1][lane * AX_FD_ROW]);
+                float4* yo = reinterpret_cast<float4*>(myring + (t & 1) * 64);
+                unsigned minabs = 0x7fffffffu;
 #pragma unroll
-                    for (int h = 0; h < 4; ++h) {
+                for (int hw = 0; hw < 2; ++hw) {
+                    unsigned sb = 0u;
 #pragma unroll
-                        for (int e2 = 0; e2 < 2; ++e2) {
-                            const int xi = e2 ? (wd[h] >> 16) : (int)(short)(wd[h] & 0xFFFF);
-                            float tt = fmaf((float)xi, k0, k1);
+                    for (int v = 0; v < 4; ++v) {
+                        const int4 q = rp[hw * 4 + v];
+                        const int wd[4] = {q.x, q.y, q.z, q.w};
+                        float yf[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const int xi = (e & 1) ? (wd[e >> 1] >> 16) : (int)(short)(wd[e >> 1] & 0xFFFF);
+                            double tt = fma((double)xi, k0, k1);
 #pragma unroll
                             for (int s = 0; s < NSEC; ++s) {
-                                const float y = tt + z0[s];
-                                z0[s] = fmaf(-a1[s], y, fmaf(sg[s], tt, z1[s]));
-                                z1[s] = fmaf(-a2[s], y, tt);
+                                const double y = tt + z0[s];
+                                z0[s] = fma(a1[s], y, fma(sg[s], tt, z1[s]));
+                                z1[s] = fma(a2[s], y, tt);
                                 tt = y;
                             }
-                            yo[v * 8 + h * 2 + e2] = tt;
+                            const unsigned hi = (unsigned)__double2hiint(tt);
+                            sb = __funnelshift_l(hi, sb, 1);                 // MSB-first: sample 0 of this half ends at bit 31
+                            minabs = min(minabs, hi & 0x7fffffffu);
+                            yf[e] = (float)tt;
                         }
+                        yo[hw * 8 + v * 2] = make_float4(yf[0], yf[1], yf[2], yf[3]);
+                        yo[hw * 8 + v * 2 + 1] = make_float4(yf[4], yf[5], yf[6], yf[7]);
+                    }
+                    Scur |= (unsigned long long)__brev(sb) << (32 * hw);
+                }
+                // guard band: a filter output this close to zero cannot be signed reliably (AXCTD_DROP_UNCERTAIN)
+                if (minabs < guard_hi) {
+                    const int base = nb + 64 * t;
+                    for (int i = 0; i < 64; ++i) {
+                        const int n = base + i;
+                        if (n >= sstart && n < send && n < nstop && fabsf(myring[(t & 1) * 64 + i]) < (float)w.guard) ++unc;
                     }
                 }
             }
         }
         __syncwarp();
-        // ---------------- phase 2: warp-cooperative, one thread-row at a time
-        for (int r = 0; r < 32; ++r) {
-            const int Tq = __shfl_sync(0xffffffffu, T, r);
-            if (Tq == 0) continue;
-            const int nbq = __shfl_sync(0xffffffffu, nb, r), nstopq = __shfl_sync(0xffffffffu, nstop, r);
-            const int sstartq = __shfl_sync(0xffffffffu, sstart, r), sendq = __shfl_sync(0xffffffffu, send, r);
-            float* yc = ycur + r * AX_F32_YROW;
-            float* yp = yprev + r * AX_F32_YROW;
-            // -------- 2a: fp64 re-evaluation of the samples of the current row that are too close to zero
-            if (t < Tq) {
-                const int base = nbq + 64 * t;
-#pragma unroll 1
-                for (int half = 0; half < 2; ++half) {
-                    const int p = half * 32 + lane, n = base + p;
-                    const float y = yc[p];
-                    const bool flag = (n < nstopq) && (n >= sstartq) && (n <= sendq) && (fabsf(y) < G);
-                    unsigned ball = __ballot_sync(0xffffffffu, flag);
-                    while (ball) {
-                        const int L = __ffs((int)ball) - 1;
-                        ball &= ball - 1;
-                        const int nf = base + half * 32 + L;
-                        double part = ax_fir_partial(xdrop, nf, c.fir_h, c.fir_len, lane, 32);
+        // ---------------- phase 2: crossings of row t-1 and their windows
+        if (t >= 1) {
+            unsigned long long X = 0ull;
+            const int base = nb + 64 * (t - 1);
+            if (t - 1 < T) {
+                const unsigned long long nxt = (t < T) ? (Scur & 1ull) : ((Sprev >> 63) & 1ull);
+                X = Sprev ^ ((Sprev >> 1) | (nxt << 63));
+                int lo = sstart - base, hi = min(send, nstop - 1) - base;      // crossing i needs sample i+1
+                lo = max(lo, 0); hi = min(hi, 64);
+                unsigned long long m = 0ull;
+                if (hi > lo) m = ((hi >= 64) ? ~0ull : ((1ull << hi) - 1ull)) & ~((1ull << lo) - 1ull);
+                X &= m;
+            }
+            while (__any_sync(0xffffffffu, X != 0ull)) {
+                const int take = min(__popcll(X), AX_FD_LIST / 32);
+                int off = take;
 #pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-                        if (lane == 0) {
-                            const double y64 = ax_fir_finish(part, nf, c, st);
-                            const float old = yc[half * 32 + L];
-                            float fixed = (float)y64;
-                            if (fixed == 0.f && y64 != 0.0) fixed = copysignf(1e-37f, (float)(y64 < 0.0 ? -1.0 : 1.0));
-                            yc[half * 32 + L] = fixed;
-                            errmax = fmaxf(errmax, fabsf((float)(y64 - (double)old)));
-                            ++nre;
-                        }
+                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, off, o); if (lane >= o) off += v; }
+                const int total = __shfl_sync(0xffffffffu, off, 31);
+                off -= take;
+                for (int q = 0; q < take; ++q) {
+                    const int p = __ffsll((long long)X) - 1;
+                    X &= X - 1ull;
+                    sm.list[off + q] = (unsigned)p | ((unsigned)lane << 6) | ((unsigned)(count + q) << 11);
+                }
+                count += take;
+                __syncwarp();
+                for (int it = lane; it < total; it += 32) {
+                    const unsigned en = sm.list[it];
+                    const int p = (int)(en & 63u), r = (int)((en >> 6) & 31u), op = (int)(en >> 11);
+                    const int j0 = ((t - 1) & 1) * 64 + p + 1;           // ring position of the first window sample
+                    const int o = j0 & 3;
+                    const float4* rq = reinterpret_cast<const float4*>(sm.yring + r * AX_FD_YSTRIDE);
+                    constexpr int NQ = (NPCM + 6) >> 2;
+                    float yv[NQ * 4];
+#pragma unroll
+                    for (int k = 0; k < NQ; ++k) {
+                        const float4 v = rq[((j0 >> 2) + k) & 31];
+                        yv[4 * k] = v.x; yv[4 * k + 1] = v.y; yv[4 * k + 2] = v.z; yv[4 * k + 3] = v.w;
+                    }
+                    float m1, m2;
+                    ax_window32(yv, o, NPCM, tab, &m1, &m2);
+                    const int rb = sm.row_begin[r] + 64 * (t - 1);
+                    const bool complete = rb + p + NPCM < sm.row_stop[r];
+                    if (op < w.seg_cap) {
+                        const int64_t oi = wslot0 + (int64_t)r * w.seg_cap + op;
+                        w.rec_idx[oi] = rb + p;
+                        w.rec_a1[oi] = complete ? m1 : __int_as_float(0x7fc00000);
+                        w.rec_a2[oi] = complete ? m2 : __int_as_float(0x7fc00000);
                     }
                 }
                 __syncwarp();
             }
-            // -------- 2b: crossings of the previous row and their mark / space windows
-            if (t >= 1 && t - 1 < Tq) {
-                const int base = nbq + 64 * (t - 1);
-                const bool have_cur = t < Tq;
-#pragma unroll 1
-                for (int half = 0; half < 2; ++half) {
-                    const int p = half * 32 + lane, i = base + p;
-                    const float y0 = yp[p];
-                    const float y1 = (p < 63) ? yp[p + 1] : (have_cur ? yc[0] : 0.f);
-                    const bool ok = (i >= sstartq) && (i < sendq) && (i + 1 < nstopq);
-                    unsigned ball = __ballot_sync(0xffffffffu, ok && ((y0 < 0.f) != (y1 < 0.f)));
-                    while (ball) {
-                        const int L = __ffs((int)ball) - 1;
-                        ball &= ball - 1;
-                        const int pc = half * 32 + L;            // crossing position inside the previous row
-                        float sr1 = 0.f, si1 = 0.f, sr2 = 0.f, si2 = 0.f;
-                        bool complete = (base + pc + npcm < nstopq);
-#pragma unroll
-                        for (int rep = 0; rep < 2; ++rep) {
-                            const int m = rep * 32 + lane;
-                            if (m < npcm) {
-                                const int qpos = pc + 1 + m;
-                                const float yv = (qpos < 64) ? yp[qpos] : (have_cur ? yc[qpos - 64] : 0.f);
-                                const float4 tb = tabf[m];
-                                sr1 = fmaf(yv, tb.x, sr1); si1 = fmaf(yv, tb.y, si1);
-                                sr2 = fmaf(yv, tb.z, sr2); si2 = fmaf(yv, tb.w, si2);
-                            }
-                        }
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) {
-                            sr1 += __shfl_xor_sync(0xffffffffu, sr1, o); si1 += __shfl_xor_sync(0xffffffffu, si1, o);
-                            sr2 += __shfl_xor_sync(0xffffffffu, sr2, o); si2 += __shfl_xor_sync(0xffffffffu, si2, o);
-                        }
-                        if (lane == 0) {
-                            const int cnt = count[warp * 32 + r];
-                            if (cnt < w.seg_cap) {
-                                const int64_t o = slot0 + (int64_t)(r - lane) * w.seg_cap + cnt;      // slot of thread-row r (lane == 0 here)
-                                w.rec_idx[o] = base + pc;
-                                w.rec_a1[o] = complete ? (double)sqrtf(sr1 * sr1 + si1 * si1) : ax_nan();
-                                w.rec_a2[o] = complete ? (double)sqrtf(sr2 * sr2 + si2 * si2) : ax_nan();
-                            }
-                            count[warp * 32 + r] = cnt + 1;
-                        }
-                    }
-                }
-            }
         }
+        Sprev = Scur;
         __syncwarp();
     }
-    __syncwarp();
     if (active) {
-        int cnt = count[threadIdx.x];
-        if (cnt > w.seg_cap) { w.flags[AX_FLAG_CAP] = 1; cnt = w.seg_cap; }
-        w.seg_cnt[seg] = cnt;
+        if (count > w.seg_cap) { w.flags[AX_FLAG_CAP] = 1; count = w.seg_cap; }
+        w.seg_cnt[seg] = count;
+        if (unc) atomicAdd(&st.n_uncertain, unc);
     } else w.seg_cnt[seg] = 0;
-    if (lane == 0 && nre > 0) {
-        atomicAdd(&st.n_recheck, nre);
-        atomicMax(&st.err32_bits, __float_as_int(errmax));
-    }
+    (void)slot0;
 }
 
-template <int NSEC>
-static inline void ax_launch_filter32(const AxWave& w, cudaStream_t stream) {
-    const size_t smem = 64 * sizeof(float4) + 2 * AX_FS_STAGE * sizeof(int16_t) +
-                        2 * AX_FS_THREADS * AX_F32_YROW * sizeof(float) + AX_FS_THREADS * sizeof(int);
+template <int NSEC, int NPCM>
+static inline void ax_launch_demod_fused(const AxWave& w, const AxCfg& c, int cfg_id, cudaStream_t stream) {
+    const size_t smem = AX_FD_WARPS * sizeof(AxFdSmem);
     static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(k_filter32<NSEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attr_set = true; }
-    k_filter32<NSEC><<<w.nseg_total / AX_FS_THREADS, AX_FS_THREADS, smem, stream>>>(w);
+    if (!attr_set) { cudaFuncSetAttribute(k_demod_fused<NSEC, NPCM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+    k_demod_fused<NSEC, NPCM><<<w.nseg_total / AX_FD_THREADS, AX_FD_THREADS, smem, stream>>>(w, c.win_tab, cfg_id);
+}
+
+// true if the fused kernel has an instantiation for this rate class
+static inline bool ax_demod_fused_ok(const AxCfg& c) {
+    return ax_sos_is_butter(c) && (c.nsec == 3 || c.nsec == 6) && (c.npcm == 39 || c.npcm == 43) && c.inset == 1;
+}
+static inline void ax_launch_demod_fused_any(const AxWave& w, const AxCfg& c, int cfg_id, cudaStream_t stream) {
+    if (c.nsec == 3 && c.npcm == 39) ax_launch_demod_fused<3, 39>(w, c, cfg_id, stream);
+    else if (c.nsec == 3 && c.npcm == 43) ax_launch_demod_fused<3, 43>(w, c, cfg_id, stream);
+    else if (c.nsec == 6 && c.npcm == 39) ax_launch_demod_fused<6, 39>(w, c, cfg_id, stream);
+    else ax_launch_demod_fused<6, 43>(w, c, cfg_id, stream);
+}
+
+// ------------------------------------------------------------------ bit decisions with shared window sums
+// As ax_bits_item, but a window that needs double precision is summed by the whole warp.
+__global__ void __launch_bounds__(128) k_bits_warp(AxWave w, int64_t n, int phase) {
+    const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    AxBitFix fx;
+    fx.d = 0; fx.i = 0; fx.q0 = 0;
+    const bool need = slot < n && ax_bits_need(w, slot, phase, &fx);
+    unsigned ball = __ballot_sync(0xffffffffu, need);
+    while (ball) {
+        const int L = __ffs((int)ball) - 1;
+        ball &= ball - 1;
+        AxBitFix f;
+        f.d = __shfl_sync(0xffffffffu, fx.d, L);
+        f.i = __shfl_sync(0xffffffffu, fx.i, L);
+        f.q0 = __shfl_sync(0xffffffffu, fx.q0, L);
+        const AxDrop& dr = w.drop[f.d];
+        double acc[4];
+        ax_gwin_partial(w.pcm + dr.pcm_off, f.i, f.q0, w.cfg[dr.cfg], lane, 32, acc);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+        if (lane == L) ax_bits_fix(w, slot, f, acc);
+    }
+    if (phase == 1 && slot < n) ax_bits_decide(w, slot);
 }
 
 // ------------------------------------------------------------------ tones

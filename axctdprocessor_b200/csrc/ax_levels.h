@@ -290,7 +290,7 @@ AX_HDN inline void ax_emit_item(const AxWave& w, int64_t cg) {
     if (ch.n_edges <= 0) return;
     const AxCfg& c = w.cfg[dr.cfg];
     const int32_t* zi = w.zc_idx + dr.zc_base;
-    const double* za1 = w.zc_a1 + dr.zc_base; const double* za2 = w.zc_a2 + dr.zc_base;
+    const float* za1 = w.zc_a1 + dr.zc_base; const float* za2 = w.zc_a2 + dr.zc_base;
     const int32_t* hz = w.head_idx + cg * (int64_t)w.head_zc_cap_max;
     const double* ha1 = w.head_a1 + cg * (int64_t)w.head_zc_cap_max;
     const double* ha2 = w.head_a2 + cg * (int64_t)w.head_zc_cap_max;
@@ -411,8 +411,90 @@ AX_HDN inline void ax_scale_item(const AxWave& w, int64_t d) {
     st.scale_switch_bit = (st.k1 >= 0 && st.k1 + 1 < st.n_chunks) ? ch[st.k1 + 1].bit_off : st.nbits_total;
 }
 
-// demodulate.py:102,109-114 for one bit
-AX_HDN inline void ax_bits_item(const AxWave& w, int64_t slot) {
+// ---- bit decisions (demodulate.py:102,109-114) ------------------------------------------------
+// The mark / space magnitudes of the continuous pass carry fp32 accuracy (ax_window32).  Two
+// consumers make discrete decisions from them: the scale calibration bins conf into 0.01-wide
+// histogram bins (phase 0, before ax_scale_item) and the bit decision compares p1 with p2
+// (phase 1).  Whenever a value lies within the tolerance of such a boundary, the window is
+// re-evaluated in double precision from the int16 samples (ax_gwin_*) and replaced.
+
+// run() iteration that demodulated bit j of the drop
+AX_HD int ax_chunk_of_bit(const AxChunk* ch, int k0, int n_chunks, int64_t j) {
+    int lo = k0, hi = n_chunks - 1;                      // last chunk with bit_off <= j
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (ch[mid].bit_off <= j) lo = mid; else hi = mid - 1; }
+    return lo;
+}
+
+struct AxBitFix { int32_t d; int64_t i, q0; };
+
+// Does bit `slot` need a double-precision window in this phase?
+AX_HD bool ax_bits_need(const AxWave& w, int64_t slot, int phase, AxBitFix* fx) {
+    const int d = ax_find_owner(w.drop, w.n_drops, &AxDrop::edge_base, slot);
+    const AxDrop& dr = w.drop[d];
+    const AxState& st = w.st[d];
+    const int64_t j = slot - dr.edge_base;
+    if (j >= st.nbits_total || st.sm_status < 1) return false;
+    const AxCfg& c = w.cfg[dr.cfg];
+    const double p1 = w.a1[slot];
+    bool need = w.bitfix_all != 0;
+    int64_t ei = -1;
+    const AxChunk* ch = w.chunk + dr.chunk_base;
+    const int k = ax_chunk_of_bit(ch, st.k0, st.n_chunks, j);
+    const int64_t e = ch[k].edge_off + (j - ch[k].bit_off);
+    if (phase == 0) {
+        ei = w.edge_idx[dr.edge_base + e];
+        // header-1 calibration bits (AXCTDprocessor.py:459-466).  The reference pairs bit j with edge-list
+        // position j, which lags the bit's own edge by one entry per earlier iteration: keep a margin.
+        const int64_t mg = (int64_t)(64.0 * c.fs / c.bitrate);
+        const int64_t p1s = st.firstpulse400 + c.h1s - c.half - mg, p1e = st.firstpulse400 + c.h1e + c.half + mg;
+        if (ei < p1s || ei > p1e) return false;
+        if (!need) {
+            const double v = ax_div(ax_mul(w.a2[slot], c.scale0), p1);
+            const int nbins = c.n_hist_edges - 1;
+            const double* ed = c.hist_edges;
+            if (v <= ed[nbins] * 1.001) {
+                int lo = 0, up = nbins + 1;                  // first edge > v
+                while (lo < up) { const int mid = (lo + up) >> 1; if (ed[mid] <= v) lo = mid + 1; else up = mid; }
+                // conf = a2*s/a1 with both magnitudes good to hist_tol of the stronger one
+                const double a2v = w.a2[slot];
+                const double tol = w.hist_tol * ((p1 > a2v ? p1 : a2v) / p1) * (c.scale0 + v);
+                if (lo <= nbins && ed[lo] - v <= tol) need = true;
+                if (lo >= 1 && v - ed[lo - 1] <= tol) need = true;
+            }
+        }
+    } else if (!need) {
+        const double scale = (j >= st.scale_switch_bit) ? st.scale : c.scale0;
+        const double p2 = ax_mul(w.a2[slot], scale);
+        const double m = p1 > p2 ? p1 : p2;
+        need = fabs(p1 - p2) <= w.bit_tol * m;              // false for NaN
+    }
+    if (!need) return false;
+    if (ei < 0) ei = w.edge_idx[dr.edge_base + e];
+    fx->d = d; fx->i = ei; fx->q0 = ch[k].s;
+    return true;
+}
+
+// Replace the magnitudes of bit `slot` by the double-precision ones (acc = summed ax_gwin_partial).
+AX_HD void ax_bits_fix(const AxWave& w, int64_t slot, const AxBitFix& fx, const double* acc) {
+    const AxDrop& dr = w.drop[fx.d];
+    AxState& st = w.st[fx.d];
+    double e1, e2;
+    ax_gwin_finish(acc, fx.i, fx.q0, w.cfg[dr.cfg], st, &e1, &e2);
+    const double o1 = w.a1[slot], o2 = w.a2[slot];
+    // error of the fp32 magnitudes relative to the stronger of the two tones
+    double rel = fabs(o1 - e1) > fabs(o2 - e2) ? fabs(o1 - e1) : fabs(o2 - e2);
+    rel /= (e1 > e2 ? e1 : e2);
+    if (rel == rel) {
+        const float rf = (float)rel;
+        int32_t bits;
+        memcpy(&bits, &rf, sizeof(bits));
+        AX_ATOMIC_MAX32(&st.err32_bits, bits);
+    }
+    AX_ATOMIC_ADD32(&st.n_recheck, 1);
+    w.a1[slot] = e1; w.a2[slot] = e2;
+}
+
+AX_HD void ax_bits_decide(const AxWave& w, int64_t slot) {
     const int d = ax_find_owner(w.drop, w.n_drops, &AxDrop::edge_base, slot);
     const AxDrop& dr = w.drop[d];
     const AxState& st = w.st[d];
@@ -423,4 +505,16 @@ AX_HDN inline void ax_bits_item(const AxWave& w, int64_t slot) {
     const double p2 = ax_mul(w.a2[slot], scale);
     w.conf[slot] = ax_div(p2, p1);
     w.bit[slot] = (p1 >= p2) ? 1 : 0;
+}
+
+// one thread does everything (generic form; the CUDA build shares the window sum across a warp)
+AX_HDN inline void ax_bits_item(const AxWave& w, int64_t slot, int phase) {
+    AxBitFix fx;
+    if (ax_bits_need(w, slot, phase, &fx)) {
+        const AxDrop& dr = w.drop[fx.d];
+        double acc[4];
+        ax_gwin_partial(w.pcm + dr.pcm_off, fx.i, fx.q0, w.cfg[dr.cfg], 0, 1, acc);
+        ax_bits_fix(w, slot, fx, acc);
+    }
+    if (phase == 1) ax_bits_decide(w, slot);
 }

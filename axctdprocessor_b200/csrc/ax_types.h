@@ -7,6 +7,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 #include "../../include/axctd.h"
 
 #if defined(__CUDACC__) && !defined(AXCTD_EMU)
@@ -55,6 +56,11 @@ AX_HD double ax_nan() { return nan(""); }
 #define AX_PEND 8           // pending bit-windows per thread in the filter pass
 #define AX_STAT_SLAB 16384  // samples per stats work item
 
+// fp32 phasor table of the bit windows (ax_window32): cos, sin of theta_mark * k and theta_space * k
+#define AX_WIN_TAPS 48
+struct alignas(16) AxF4 { float x, y, z, w; };
+struct AxWinTab { AxF4 t[AX_WIN_TAPS]; };
+
 // Per rate-class constants (reference AXCTDprocessor.py:117-182, 212-262).
 struct AxCfg {
     double fs;
@@ -78,10 +84,11 @@ struct AxCfg {
     const double* lut;           // [lut_len]
     const double* hist_edges;    // [n_hist_edges]
     const double* hist_centers;  // [n_hist_edges-1]
-    const double* fir_h;         // [fir_len] impulse response of the SOS cascade (fp64 re-evaluation of single samples)
-    const double* fir_hc;        // [fir_len] running sum of fir_h (response to the constant -dc/ampl term)
-    int32_t fir_len, pad_fir;
+    const double* gtab;          // [g_len][4] mark/space window responses: |S_f(i)| = |sum_d u[i+npcm-d] * G_f[d]| (ax_gwin_*)
+    const double* gcum;          // [g_len][4] running sums of gtab (response to the constant -dc/ampl term)
+    int32_t g_len, pad_g;
     int32_t lut_len, n_hist_edges;
+    AxWinTab win_tab;
 };
 
 struct AxDrop {
@@ -124,8 +131,8 @@ struct AxState {
     int64_t sum;
     int32_t ampl;
     int32_t n_uncertain;
-    int32_t n_recheck;           // samples re-evaluated in fp64 by the fp32 filter pass
-    int32_t err32_bits;          // max |y64 - y32| seen at re-evaluated samples (float bits)
+    int32_t n_recheck;           // bit windows re-evaluated in double precision (ax_gwin_*)
+    int32_t err32_bits;          // max relative |a32 - a64| / a64 seen at re-evaluated windows (float bits)
     double dc, inv_ampl, ampl_d;
     int64_t zc_count;
     // state machine
@@ -169,8 +176,8 @@ struct AxWave {
     const int32_t* seg_drop;     // segment -> drop
     const int32_t* slab_drop;    // stats slab -> drop
     int32_t* seg_cnt; int64_t* seg_off; int64_t* blk_sum;  // per segment / per block of 128 segments
-    int32_t* rec_idx; double* rec_a1; double* rec_a2;       // [nseg_total * seg_cap]
-    int32_t* zc_idx; double* zc_a1; double* zc_a2;          // dense, per drop at zc_base
+    int32_t* rec_idx; float* rec_a1; float* rec_a2;         // [nseg_total * seg_cap]
+    int32_t* zc_idx; float* zc_a1; float* zc_a2;            // dense, per drop at zc_base
     uint8_t* zc_nx; uint8_t* zc_exit;                       // per crossing: walk step, tile exit
     uint64_t* tile_mask;                                    // [tile][4] visited masks
     // chunks
@@ -193,8 +200,10 @@ struct AxWave {
     // frames
     axctd_frame* frame;
     double guard;
-    float guard32;               // fp32 filter pass: samples with |y| below this are re-evaluated in fp64
-    int32_t bitfix_all;          // test hook: re-evaluate every bit decision in fp64
+    double bit_tol;              // |p1 - p2| <= bit_tol * max(p1, p2): the bit is re-decided from a double-precision window
+    double hist_tol;             // conf within hist_tol (relative) of a histogram bin edge: re-evaluated before the scale calibration
+    int32_t bitfix_all;          // test hook: re-evaluate every bit window in double precision
+    int32_t pad3;
     int32_t tone_direct;
     int32_t pa_lo, pa_hi;        // fixed-grid chunk range of the current detection round
     int32_t force_exact;

@@ -110,6 +110,8 @@ typedef struct axctd_drop_summary {
     int32_t n_chain_fixups;     /* mis-speculated chunks repaired */
     int64_t pcm_sum;            /* integer sum and max|x| of the int16 input (:55-56) */
     int32_t pcm_ampl;
+    int32_t n_recheck;          /* fp32 bit windows re-evaluated in double precision (decision within tolerance) */
+    float   win32_max_rel_err;  /* largest relative |fp32 - fp64| window magnitude difference seen at those */
     int32_t reserved;
     /* header frames as decoded by parse_header (parse.py:197-285), slot 0 = header 2, 1 = header 3 */
     uint16_t frame_data[2][72];
@@ -159,8 +161,9 @@ int  axctd_struct_size(int which);
 int  axctd_engine_create(int device, axctd_engine** out);
 void axctd_engine_destroy(axctd_engine* e);
 const char* axctd_last_error(axctd_engine* e);
-/* Tunables: "segment_len", "exact_head", "guard", "force_exact", "tone_direct",
- * "tile", "max_fixups", "filter_variant".  Unknown names return AXCTD_ERR_ARG. */
+/* Tunables: "segment_len", "exact_head", "guard", "force_exact", "tone_direct", "max_fixups",
+ * "filter_variant", "zc_div", "bit_tol", "hist_tol", "bitfix_all", "inject_misspec".
+ * Unknown names return AXCTD_ERR_ARG. */
 int  axctd_engine_set_option(axctd_engine* e, const char* name, double value);
 /* Run all engine work on a caller-owned CUDA stream (cudaStream_t passed as void*), so that the
  * caller can bracket it with its own events.  The engine does not take ownership. */

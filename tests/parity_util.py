@@ -2,6 +2,9 @@
 import numpy as np
 
 
+CONF_RTOL = 5e-6
+
+
 def mono(pcm):
     return np.ascontiguousarray(pcm[:, 0]) if pcm.ndim == 2 else pcm
 
@@ -55,7 +58,10 @@ def check_against_golden(out, g, level_rtol=1e-9):
     np.testing.assert_allclose(r400, g.z["r400"].astype(np.float64), rtol=max(level_rtol, 1e-6 if g.z["r400"].dtype == np.float32 else 0), atol=1e-6 if g.z["r400"].dtype == np.float32 else 1e-11, equal_nan=True)
     np.testing.assert_allclose(r7500, g.z["r7500"].astype(np.float64), rtol=max(level_rtol, 1e-6 if g.z["r7500"].dtype == np.float32 else 0), atol=1e-6 if g.z["r7500"].dtype == np.float32 else 1e-11, equal_nan=True)
     if "conf" in g.z.files:
-        np.testing.assert_allclose(conf, g.z["conf"], rtol=1e-9, equal_nan=True)
+        # the mark / space windows are summed in fp32 (decisions near a boundary are re-made in double)
+        # (fp32 error is relative to the stronger tone: conf = a2*s/a1 moves by ~1e-6 * (s + conf) * max(a1,a2)/a1)
+        np.testing.assert_allclose(conf, g.z["conf"], rtol=CONF_RTOL, atol=CONF_RTOL, equal_nan=True)
+        assert s.win32_max_rel_err < 2e-6, s.win32_max_rel_err
     # header metadata (exact)
     from axctdprocessor_b200.AXCTDprocessor import header_metadata
     for slot in range(2):

@@ -40,11 +40,24 @@ def test_chain_repair_loop_converges_to_same_answer():
     e.close()
 
 
-@pytest.mark.parametrize("opts", [dict(force_exact=1), dict(segment_len=4096), dict(exact_head=2048, segment_len=8192)])
+@pytest.mark.parametrize("opts", [dict(force_exact=1), dict(segment_len=4096), dict(exact_head=2048, segment_len=8192),
+                                  dict(bit_tol=1e-3, hist_tol=1e-3)])
 def test_decomposition_invariance(opts):
     g = Golden("g48_25db")
     e = emu_engine(**opts)
     check_against_golden(run_engine(e, g.pcm(), g.spec.fs), g)
+    e.close()
+
+
+def test_double_precision_windows_reproduce_reference_confidence():
+    """bitfix_all: every mark/space window comes from ax_gwin_* (double, straight from the int16
+    samples, truncated at the chunk start): conf then agrees with the reference to fp64 round-off."""
+    g = Golden("g44_10db")
+    e = emu_engine(bitfix_all=1)
+    out = run_engine(e, g.pcm(), g.spec.fs)
+    check_against_golden(out, g)
+    np.testing.assert_allclose(out["bits"][1], g.z["conf"], rtol=1e-9, equal_nan=True)
+    assert out["result"].summary.n_recheck >= g.meta["n_bits"]
     e.close()
 
 

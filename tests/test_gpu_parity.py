@@ -124,7 +124,8 @@ def test_batch_equals_single_drops(eng):
 
 
 @pytest.mark.parametrize("opts", [dict(tone_direct=1), dict(force_exact=1), dict(inject_misspec=1),
-                                  dict(segment_len=4096), dict(segment_len=32768), dict(filter_variant=1)])
+                                  dict(segment_len=4096), dict(segment_len=32768), dict(filter_variant=1),
+                                  dict(bitfix_all=1), dict(bit_tol=1e-3, hist_tol=1e-3)])
 def test_kernel_variants_agree_with_reference(opts):
     g = Golden("g48_25db")
     e = _engine(**opts)
@@ -132,6 +133,9 @@ def test_kernel_variants_agree_with_reference(opts):
     if "inject_misspec" in opts:
         assert out["result"].summary.n_chain_fixups >= 1
     check_against_golden(out, g)
+    if "bitfix_all" in opts:        # every window re-evaluated in double: conf agrees with the reference to fp64 round-off
+        np.testing.assert_allclose(out["bits"][1], g.z["conf"], rtol=1e-9, equal_nan=True)
+        assert out["result"].summary.n_recheck >= g.meta["n_bits"]
     e.close()
 
 
