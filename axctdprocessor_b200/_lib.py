@@ -47,7 +47,7 @@ class DropSummary(C.Structure):
         ("n_frames", C.c_int64), ("n_rows", C.c_int64), ("n_hex", C.c_int64), ("n_crossings", C.c_int64),
         ("n_uncertain", C.c_int32), ("n_chain_fixups", C.c_int32),
         ("pcm_sum", C.c_int64), ("pcm_ampl", C.c_int32), ("n_recheck", C.c_int32),
-        ("win32_max_rel_err", C.c_float), ("reserved", C.c_int32),
+        ("win32_max_rel_err", C.c_float), ("n_frame_respec", C.c_int32),
         ("frame_data", (C.c_uint16 * 72) * 2), ("counter_found", (C.c_uint8 * 72) * 2),
         ("header_parsed", C.c_int32 * 2),
         ("zcoeff", C.c_double * 4), ("tcoeff", C.c_double * 4), ("ccoeff", C.c_double * 4),

@@ -370,9 +370,8 @@ AX_HDN inline void ax_nx_item(const AxWave& w, int64_t zg) {
 }
 
 // Per tile of AX_TILE crossings:
-//   zc_exit[c]       walk from crossing c leaves its tile at offset (x & 3) of the next tile after
-//                    (x >> 2) + 1 steps; 0xFF = not available
 //   tile_mask[t][o]  bit i set <=> crossing t*AX_TILE+i is visited by the walk entering the tile at offset o (0..3)
+//   tile_map[t]      byte o = offset (0..3) at which that walk enters the next tile, 0xFF if it stops inside
 AX_HDN inline void ax_tiles_item(const AxWave& w, int64_t tg) {
     const int d = ax_find_owner(w.drop, w.n_drops, &AxDrop::tile_base, tg);
     const AxDrop& dr = w.drop[d];
@@ -382,29 +381,22 @@ AX_HDN inline void ax_tiles_item(const AxWave& w, int64_t tg) {
     const int64_t first = t * AX_TILE;
     if (first >= M) return;
     const uint8_t* nx = w.zc_nx + dr.zc_base;
-    uint8_t* ex = w.zc_exit + dr.zc_base;
     const int64_t limit = first + AX_TILE;
-    const int64_t last = (limit < M ? limit : M) - 1;
-    for (int64_t c = last; c >= first; --c) {
-        const int stp = nx[c];
-        uint8_t v = 0xFF;
-        if (stp) {
-            const int64_t nxt = c + stp;
-            if (nxt >= limit) v = (uint8_t)(nxt - limit);
-            else if (ex[nxt] != 0xFF && (ex[nxt] >> 2) < 62) v = (uint8_t)(ex[nxt] + 4);      // one more step, same exit
-        }
-        ex[c] = v;
-    }
+    uint32_t map = 0;
     for (int o = 0; o < 4; ++o) {
         uint64_t mask = 0;
+        uint32_t ex = 0xFF;
         int64_t c = first + o;
-        while (c < limit && c < M) {
+        while (c < M) {
+            if (c >= limit) { ex = (uint32_t)(c - limit); break; }
             mask |= 1ull << (c - first);
             if (!nx[c]) break;
             c += nx[c];
         }
         w.tile_mask[tg * 4 + o] = mask;
+        map |= ex << (8 * o);
     }
+    w.tile_map[tg] = map;
 }
 
 AX_HD int ax_popc64(uint64_t v) {
@@ -422,28 +414,87 @@ AX_HD int ax_ctz64(uint64_t v) {
 #endif
 }
 
+// ---- the canonical walk -------------------------------------------------------------------------
+// The greedy walk of every demodulated chunk starts at (or right beside) the crossing where the
+// previous chunk's walk ended, so apart from the exact heads all chunks of a drop travel along ONE
+// walk: the one that starts at the first usable crossing of the first demodulated chunk.  Its visited
+// set is stored as one 64-bit mask per tile (cmask) with the running count of visited crossings
+// before each tile (crank).  A walk that starts elsewhere is stepped explicitly until it lands on
+// a canonical crossing; from there "where does it stop" and "how many steps" are two lookups.
+//
+// First tile of one drop: returns the state (offset into the next tile, 4 = stopped) and fills
+// cmask[t0] for the walk that starts at ordinal `entry`.
+AX_HD int ax_canon_first_tile(const uint8_t* nx, int64_t M, int64_t entry, uint64_t* mask_out) {
+    const int64_t first = (entry / AX_TILE) * AX_TILE, limit = first + AX_TILE;
+    uint64_t mask = 0;
+    int state = 4;
+    int64_t c = entry;
+    while (c < M) {
+        if (c >= limit) { state = (int)(c - limit); break; }
+        mask |= 1ull << (c - first);
+        if (!nx[c]) break;
+        c += nx[c];
+    }
+    *mask_out = mask;
+    return state;
+}
+AX_HD int ax_map_apply(uint32_t map, int state) {
+    if (state >= 4) return 4;
+    const uint32_t e = (map >> (8 * state)) & 0xFFu;
+    return e == 0xFFu ? 4 : (int)e;
+}
+
+// generic (sequential) form of the canonical-walk tables of one drop; the CUDA build uses k_canon_block
+AX_HDN inline void ax_canon_item(const AxWave& w, int64_t d) {
+    const AxDrop& dr = w.drop[d];
+    AxState& st = w.st[d];
+    if (st.status != 0 || st.sm_status < 1) return;
+    const AxCfg& c = w.cfg[dr.cfg];
+    const int64_t M = st.zc_count;
+    const int64_t ntile = (M + AX_TILE - 1) / AX_TILE;
+    uint64_t* cmask = w.cmask + dr.tile_base;
+    int32_t* crank = w.crank + dr.tile_base;
+    const int64_t entry = ax_lower_bound(w.zc_idx + dr.zc_base, M, w.chunk[dr.chunk_base + st.k0].s + c.pad);
+    const int64_t t0 = entry / AX_TILE;
+    for (int64_t t = 0; t < ntile && t < t0; ++t) { cmask[t] = 0; crank[t] = 0; }
+    if (entry >= M) return;
+    uint64_t m0;
+    int state = ax_canon_first_tile(w.zc_nx + dr.zc_base, M, entry, &m0);
+    cmask[t0] = m0; crank[t0] = 0;
+    int32_t rank = ax_popc64(m0);
+    for (int64_t t = t0 + 1; t < ntile; ++t) {
+        const uint64_t m = state < 4 ? w.tile_mask[(dr.tile_base + t) * 4 + state] : 0ull;
+        cmask[t] = m; crank[t] = rank;
+        rank += ax_popc64(m);
+        state = ax_map_apply(w.tile_map[dr.tile_base + t], state);
+    }
+}
+
+// number of canonical crossings with ordinal < pos
+AX_HD int64_t ax_canon_rank(const uint64_t* cmask, const int32_t* crank, int64_t pos) {
+    const int64_t t = pos / AX_TILE;
+    return (int64_t)crank[t] + ax_popc64(cmask[t] & ((1ull << (pos - t * AX_TILE)) - 1ull));
+}
+
 // Follow the walk from `pos` while pos <= qstop-5 (demodulate.py:90:
 // `while c < len(zerocrossings)-5`); returns the final ordinal and the number of steps.
-AX_HD int64_t ax_walk_end(const uint8_t* nx, const uint8_t* ex, const uint64_t* tmask, int64_t pos, int64_t qstop,
-                          int64_t* steps) {
+// *merge (optional): ordinal at which the walk joined the canonical walk, -1 if it ended before.
+AX_HD int64_t ax_walk_end(const uint8_t* nx, const uint64_t* cmask, const int32_t* crank, int64_t pos, int64_t qstop,
+                          int64_t* steps, int64_t* merge = nullptr) {
     int64_t st = 0;
+    if (merge) *merge = -1;
     const int64_t X = qstop - 4;                       // the walk stops at the first visited ordinal >= X
     while (pos < X) {
-        const int64_t t = pos / AX_TILE, first = t * AX_TILE, limit = first + AX_TILE;
-        if (limit <= X) {                              // the stop point lies beyond this tile: leave it in one go
-            const uint8_t e = ex[pos];
-            if (e != 0xFF) { st += (e >> 2) + 1; pos = limit + (e & 3); continue; }
-        } else if (pos - first < 4) {                  // stop point inside this tile, entered at an offset with a mask
-            const uint64_t mask = tmask[t * 4 + (pos - first)];
-            const uint64_t ahead = mask & ~((1ull << (X - first)) - 1ull);
-            if (ahead) {
-                const int tb = ax_ctz64(ahead);
-                st += ax_popc64(mask & ((2ull << tb) - 1ull)) - 1;
-                pos = first + tb;
-                break;
-            }
-            const uint8_t e = ex[pos];
-            if (e != 0xFF) { st += (e >> 2) + 1; pos = limit + (e & 3); continue; }
+        const int64_t t = pos / AX_TILE;
+        if ((cmask[t] >> (pos - t * AX_TILE)) & 1ull) {  // on the canonical walk: jump
+            if (merge) *merge = pos;
+            int64_t tx = X / AX_TILE;
+            uint64_t m = cmask[tx] & ~((1ull << (X - tx * AX_TILE)) - 1ull);
+            while (!m) m = cmask[++tx];                 // (the canonical walk passes every ordinal range [X, X+3] with X <= M-5)
+            const int64_t endp = tx * AX_TILE + ax_ctz64(m);
+            st += ax_canon_rank(cmask, crank, endp) - ax_canon_rank(cmask, crank, pos);
+            pos = endp;
+            break;
         }
         pos += nx[pos];                                // (nx > 0 is guaranteed while pos <= qstop-5)
         ++st;
@@ -481,8 +532,8 @@ AX_HDN inline void ax_chain_item(const AxWave& w, int64_t d) {
     AxChunk* ch = w.chunk + dr.chunk_base;
     const int32_t* zi = w.zc_idx + dr.zc_base;
     const uint8_t* nx = w.zc_nx + dr.zc_base;
-    const uint8_t* ex = w.zc_exit + dr.zc_base;
-    const uint64_t* tmask = w.tile_mask + (int64_t)dr.tile_base * 4;
+    const uint64_t* cmask = w.cmask + dr.tile_base;
+    const int32_t* crank = w.crank + dr.tile_base;
     const int64_t M = st.zc_count;
     int k = st.chain_from;
     int64_t s;
@@ -500,7 +551,7 @@ AX_HDN inline void ax_chain_item(const AxWave& w, int64_t d) {
         if (entry > q) { st.n_chunks = k + 1; break; }
         span = q - entry;
         int64_t steps;
-        const int64_t pos = ax_walk_end(nx, ex, tmask, entry, q, &steps);
+        const int64_t pos = ax_walk_end(nx, cmask, crank, entry, q, &steps);
         ch[k].spec_last = zi[pos];
         const int64_t next_ind = zi[pos] - s - 1;                                  // demodulate.py:104
         if (next_ind <= c.pad) { st.n_chunks = k + 1; break; }                     // :330-331 handled by verify
@@ -532,6 +583,7 @@ AX_HDN inline void ax_head_item(const AxWave& w, int64_t cg) {
     double* ha1 = w.head_a1 + cg * (int64_t)w.head_zc_cap_max;
     double* ha2 = w.head_a2 + cg * (int64_t)w.head_zc_cap_max;
     ch.err = 0; ch.n_edges = 0; ch.n_head_edges = 0; ch.g_first = -1; ch.true_last = -1; ch.q_last = -1; ch.first_edge = -1;
+    ch.merge_pos = -1; ch.n_pre = 0;
     if (ny > w.ybuf_len_max) { ch.err = AXCTD_DROP_CAPACITY; return; }
     {   // demodulate.py:74 on AXCTDprocessor.py:57 samples
         double z[AX_MAXSEC][2];
@@ -552,8 +604,8 @@ AX_HDN inline void ax_head_item(const AxWave& w, int64_t cg) {
     if (overflow) { ch.err = AXCTD_DROP_CAPACITY; return; }
     const int32_t* zi = w.zc_idx + dr.zc_base;
     const uint8_t* nx = w.zc_nx + dr.zc_base;
-    const uint8_t* ex = w.zc_exit + dr.zc_base;
-    const uint64_t* tmask = w.tile_mask + (int64_t)dr.tile_base * 4;
+    const uint64_t* cmask = w.cmask + dr.tile_base;
+    const int32_t* crank = w.crank + dr.tile_base;
     const int64_t M = st.zc_count;
     int64_t g0 = 0, q = -1, nc = 0;
     if (H < len) {
@@ -589,10 +641,13 @@ AX_HDN inline void ax_head_item(const AxWave& w, int64_t cg) {
     if (!done) {
         const int64_t pos = g0 + (cpos - nh);
         ch.g_first = pos;
-        int64_t steps;
-        const int64_t endpos = ax_walk_end(nx, ex, tmask, pos, q, &steps);
+        int64_t steps, merge;
+        const int64_t endpos = ax_walk_end(nx, cmask, crank, pos, q, &steps, &merge);
         nedges += steps + 1;
         last = zi[endpos];
+        // edges pos .. (explicit steps) .. merge .. (canonical crossings) .. endpos
+        ch.merge_pos = merge;
+        ch.n_pre = (int32_t)(merge < 0 ? steps + 1 : steps - (ax_canon_rank(cmask, crank, endpos) - ax_canon_rank(cmask, crank, merge)));
     }
     ch.n_head_edges = nhe;
     ch.n_edges = (int32_t)nedges;

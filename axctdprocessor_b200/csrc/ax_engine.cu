@@ -25,8 +25,10 @@
 typedef int axStream;
 #define AX_GLOBAL static
 #define AX_FOR_ITEM(n) for (int64_t item = 0; item < (n); ++item)
+#define AX_FOR_ITEM1(n) for (int64_t item = 0; item < (n); ++item)
 #define AX_LAUNCH(eng, name, n, ...)                         \
     do { if ((n) > 0) { name((int64_t)(n), __VA_ARGS__); (eng)->launches++; } } while (0)
+#define AX_LAUNCH1 AX_LAUNCH
 #else
 typedef cudaStream_t axStream;
 #define AX_GLOBAL __global__
@@ -34,6 +36,10 @@ typedef cudaStream_t axStream;
 #define AX_LAUNCH(eng, name, n, ...)                                                                   \
     do { if ((n) > 0) { const int64_t _n = (n); const int _b = 128;                                   \
         name<<<(unsigned)((_n + _b - 1) / _b), _b, 0, (eng)->stream>>>(_n, __VA_ARGS__); (eng)->launches++; } } while (0)
+// sequential per-drop work: one item per CTA (its own SM, no divergence between the items of a warp)
+#define AX_FOR_ITEM1(n) const int64_t item = blockIdx.x; if (threadIdx.x == 0 && item < (n))
+#define AX_LAUNCH1(eng, name, n, ...)                                                                  \
+    do { if ((n) > 0) { name<<<(unsigned)(n), 32, 0, (eng)->stream>>>((int64_t)(n), __VA_ARGS__); (eng)->launches++; } } while (0)
 #endif
 
 AX_GLOBAL void k_init(int64_t n, AxWave w) {
@@ -63,27 +69,30 @@ AX_GLOBAL void k_stats(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_stats_item(w, it
 AX_GLOBAL void k_stats_fin(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_stats_fin(w, item); }
 AX_GLOBAL void k_filter(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_filter_item(w, item); }
 AX_GLOBAL void k_scan_block(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_scan_block_item(w, item); }
-AX_GLOBAL void k_scan(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_scan_item(w, item); }
+AX_GLOBAL void k_scan(int64_t n, AxWave w) { AX_FOR_ITEM1(n) ax_scan_item(w, item); }
 AX_GLOBAL void k_compact(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_compact_item(w, item); }
 AX_GLOBAL void k_nx(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_nx_item(w, item); }
 AX_GLOBAL void k_tiles(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_tiles_item(w, item); }
-AX_GLOBAL void k_plan0(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_plan0_item(w, item); }
+AX_GLOBAL void k_plan0(int64_t n, AxWave w) { AX_FOR_ITEM1(n) ax_plan0_item(w, item); }
 AX_GLOBAL void k_tone_direct(int64_t n, AxWave w, int phase_b) { AX_FOR_ITEM(n) ax_tone_direct_item(w, item, phase_b); }
 AX_GLOBAL void k_pwfill(int64_t n, AxWave w, int phase_b) { AX_FOR_ITEM(n) ax_pwfill_item(w, item, phase_b); }
 AX_GLOBAL void k_levels(int64_t n, AxWave w, int phase_b) { AX_FOR_ITEM(n) ax_levels_item(w, item, phase_b); }
-AX_GLOBAL void k_sm(int64_t n, AxWave w, int phase_b) { AX_FOR_ITEM(n) ax_sm_item(w, item, phase_b); }
-AX_GLOBAL void k_chain(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_chain_item(w, item); }
+AX_GLOBAL void k_sm(int64_t n, AxWave w, int phase_b) { AX_FOR_ITEM1(n) ax_sm_item(w, item, phase_b); }
+AX_GLOBAL void k_canon(int64_t n, AxWave w) { AX_FOR_ITEM1(n) ax_canon_item(w, item); }
+AX_GLOBAL void k_chain(int64_t n, AxWave w) { AX_FOR_ITEM1(n) ax_chain_item(w, item); }
 AX_GLOBAL void k_heads(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_head_item(w, item); }
-AX_GLOBAL void k_verify(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_verify_item(w, item); }
-AX_GLOBAL void k_plan_tones(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_plan_tones_item(w, item); }
-AX_GLOBAL void k_offsets(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_offsets_item(w, item); }
+AX_GLOBAL void k_verify(int64_t n, AxWave w) { AX_FOR_ITEM1(n) ax_verify_item(w, item); }
+AX_GLOBAL void k_plan_tones(int64_t n, AxWave w) { AX_FOR_ITEM1(n) ax_plan_tones_item(w, item); }
+AX_GLOBAL void k_offsets(int64_t n, AxWave w) { AX_FOR_ITEM1(n) ax_offsets_item(w, item); }
 AX_GLOBAL void k_emit(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_emit_item(w, item); }
-AX_GLOBAL void k_scale(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_scale_item(w, item); }
+AX_GLOBAL void k_scale(int64_t n, AxWave w) { AX_FOR_ITEM1(n) ax_scale_item(w, item); }
 AX_GLOBAL void k_bits(int64_t n, AxWave w, int phase) { AX_FOR_ITEM(n) ax_bits_item(w, item, phase); }
-AX_GLOBAL void k_headers(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_header_item(w, item); }
+AX_GLOBAL void k_headers(int64_t n, AxWave w) { AX_FOR_ITEM1(n) ax_header_item(w, item); }
 AX_GLOBAL void k_pack(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_pack_item(w, item); }
 AX_GLOBAL void k_valid(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_valid_item(w, item); }
-AX_GLOBAL void k_frames(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_frames_item(w, item); }
+AX_GLOBAL void k_frames_spec(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_frames_spec_item(w, item); }
+AX_GLOBAL void k_frames_chain(int64_t n, AxWave w) { AX_FOR_ITEM1(n) ax_frames_chain_item(w, item); }
+AX_GLOBAL void k_frames_write(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_frames_write_item(w, item); }
 AX_GLOBAL void k_calib(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_calib_item(w, item); }
 AX_GLOBAL void k_synth(int64_t n, AxSynth g) { AX_FOR_ITEM(n) ax_synth_item(g, item); }
 AX_GLOBAL void k_qc(int64_t n, AxWave w, double* scratch) { AX_FOR_ITEM(n) ax_qc_item(w, item, scratch); }
@@ -449,8 +458,10 @@ extern "C" int axctd_batch_create(axctd_engine* e, int n_drops, const int64_t* n
     bad |= ax_alloc_arr(b, &w.zc_a1, zc_off);
     bad |= ax_alloc_arr(b, &w.zc_a2, zc_off);
     bad |= ax_alloc_arr(b, &w.zc_nx, zc_off);
-    bad |= ax_alloc_arr(b, &w.zc_exit, zc_off);
     bad |= ax_alloc_arr(b, &w.tile_mask, (int64_t)tile_off * 4);
+    bad |= ax_alloc_arr(b, &w.tile_map, tile_off);
+    bad |= ax_alloc_arr(b, &w.cmask, (int64_t)tile_off + 8);
+    bad |= ax_alloc_arr(b, &w.crank, (int64_t)tile_off + 8);
     bad |= ax_alloc_arr(b, &w.chunk, chunk_off);
     bad |= ax_alloc_arr(b, &w.head_idx, (int64_t)chunk_off * head_cap_max);
     bad |= ax_alloc_arr(b, &w.head_a1, (int64_t)chunk_off * head_cap_max);
@@ -626,11 +637,17 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
     { AX_LAUNCH(e, k_filter, (int64_t)w.nseg_total, w); }
     AX_EVENT(b, 2);
     AX_LAUNCH(e, k_scan_block, (int64_t)w.nseg_total / 128, w);
-    AX_LAUNCH(e, k_scan, n, w);
+    AX_LAUNCH1(e, k_scan, n, w);
+#ifndef AXCTD_EMU
+    k_compact_warp<<<(unsigned)(((int64_t)w.nseg_total * 32 + 255) / 256), 256, 0, e->stream>>>(w);
+    k_nx_grid<<<dim3(148, (unsigned)n), 256, 0, e->stream>>>(w);
+    e->launches += 2;
+#else
     AX_LAUNCH(e, k_compact, (int64_t)w.nseg_total, w);
     AX_LAUNCH(e, k_nx, b->zc_total, w);
+#endif
     AX_LAUNCH(e, k_tiles, b->tile_total, w);
-    AX_LAUNCH(e, k_plan0, n, w);
+    AX_LAUNCH1(e, k_plan0, n, w);
     AX_LAUNCH(e, k_pwfill, b->chunk_total, w, 0);
     AX_EVENT(b, 3);
     int32_t flags[8];
@@ -639,7 +656,7 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
         w.pa_lo = lo; w.pa_hi = hi;
         ax_run_tones(b, 0);
         AX_LAUNCH(e, k_levels, (int64_t)w.pw_total, w, 0);
-        AX_LAUNCH(e, k_sm, n, w, 0);
+        AX_LAUNCH1(e, k_sm, n, w, 0);
         if (ax_d2h(e, flags, w.flags, sizeof(flags)) || ax_sync(e)) return AXCTD_ERR_CUDA;
         if (!flags[AX_FLAG_MORE]) break;
         flags[AX_FLAG_MORE] = 0;
@@ -647,43 +664,51 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
         if (hi > (1 << 28)) break;
     }
     AX_EVENT(b, 4);
-    // chunk chain: predict, recompute heads exactly, verify; repeat while repairs happen
+    // chunk chain: canonical walk tables, then predict, recompute heads exactly, verify; repeat while repairs happen
+#ifndef AXCTD_EMU
+    k_canon_block<<<n, AX_CANON_THREADS, 0, e->stream>>>(w); e->launches++;
+#else
+    AX_LAUNCH1(e, k_canon, n, w);
+#endif
     for (int it = 0;; ++it) {
-        AX_LAUNCH(e, k_chain, n, w);
+        AX_LAUNCH1(e, k_chain, n, w);
         if (e->opt_inject_misspec && it == 0) AX_LAUNCH(e, k_inject, n, w);
         AX_LAUNCH(e, k_heads, b->chunk_total, w);
-        AX_LAUNCH(e, k_verify, n, w);
+        AX_LAUNCH1(e, k_verify, n, w);
         if (ax_d2h(e, flags, w.flags, sizeof(flags)) || ax_sync(e)) return AXCTD_ERR_CUDA;
         if (!flags[AX_FLAG_DIRTY]) break;
         if (it >= e->opt_max_fixups) { e->err = "chunk chain did not converge"; return AXCTD_ERR_STATE; }
         if (ax_zero(e, w.flags, sizeof(int32_t))) return AXCTD_ERR_CUDA;
     }
-    AX_LAUNCH(e, k_plan_tones, n, w);
+    AX_LAUNCH1(e, k_plan_tones, n, w);
     AX_LAUNCH(e, k_pwfill, b->chunk_total, w, 1);
     ax_run_tones(b, 1);
     AX_LAUNCH(e, k_levels, (int64_t)w.pw_total, w, 1);
-    AX_LAUNCH(e, k_sm, n, w, 1);
-    AX_LAUNCH(e, k_offsets, n, w);
-    AX_LAUNCH(e, k_emit, b->chunk_total, w);
+    AX_LAUNCH1(e, k_sm, n, w, 1);
+    AX_LAUNCH1(e, k_offsets, n, w);
 #ifndef AXCTD_EMU
-#define AX_BITS(phase) do { k_bits_warp<<<(unsigned)((b->edge_total + 127) / 128), 128, 0, e->stream>>>(w, b->edge_total, phase); e->launches++; } while (0)
+    k_emit_chunk<<<(unsigned)b->chunk_total, 128, 0, e->stream>>>(w); e->launches++;
+#else
+    AX_LAUNCH(e, k_emit, b->chunk_total, w);
+#endif
+#ifndef AXCTD_EMU
+#define AX_BITS(phase) do { k_bits_chunk<<<(unsigned)b->chunk_total, 128, 0, e->stream>>>(w, phase); e->launches++; } while (0)
 #else
 #define AX_BITS(phase) AX_LAUNCH(e, k_bits, b->edge_total, w, phase)
 #endif
     AX_BITS(0);
-    AX_LAUNCH(e, k_scale, n, w);
+    AX_LAUNCH1(e, k_scale, n, w);
     AX_BITS(1);
-    AX_LAUNCH(e, k_headers, 2 * (int64_t)n, w);
+    AX_LAUNCH1(e, k_headers, 2 * (int64_t)n, w);
     // header text -> calibration coefficients on the host (python float semantics)
     if (ax_d2h(e, b->st.data(), w.st, sizeof(AxState) * n) || ax_sync(e)) return AXCTD_ERR_CUDA;
     for (int d = 0; d < n; ++d) ax_merge_headers(e->cfgs[b->drops[d].cfg], b->st[d], b->summary[d]);
     if (ax_h2d(e, w.st, b->st.data(), sizeof(AxState) * n)) return AXCTD_ERR_CUDA;
     AX_LAUNCH(e, k_pack, b->edge_total / 32, w);
     AX_LAUNCH(e, k_valid, b->edge_total / 32, w);
-#ifndef AXCTD_EMU
-    if (e->opt_filter_variant == 0) { ax_launch_frames_warp(w, e->stream); e->launches++; } else
-#endif
-    { AX_LAUNCH(e, k_frames, n, w); }
+    AX_LAUNCH(e, k_frames_spec, b->chunk_total, w);
+    AX_LAUNCH1(e, k_frames_chain, n, w);
+    AX_LAUNCH(e, k_frames_write, b->chunk_total, w);
     AX_LAUNCH(e, k_calib, b->frame_total, w);
     AX_LAUNCH(e, k_qc, b->chunk_total, w, b->d_qc);
     AX_EVENT(b, 5);
@@ -729,7 +754,7 @@ extern "C" int axctd_batch_finish(axctd_batch* b) {
         sm.n_frames = st.n_frames; sm.n_crossings = st.zc_count;
         sm.n_uncertain = st.n_uncertain; sm.n_chain_fixups = st.n_fixups;
         sm.pcm_sum = st.sum; sm.pcm_ampl = st.ampl;
-        sm.n_recheck = st.n_recheck; memcpy(&sm.win32_max_rel_err, &st.err32_bits, sizeof(float)); sm.reserved = 0;
+        sm.n_recheck = st.n_recheck; memcpy(&sm.win32_max_rel_err, &st.err32_bits, sizeof(float)); sm.n_frame_respec = st.n_frame_respec;
         memcpy(sm.frame_data, st.frame_data, sizeof(sm.frame_data));
         memcpy(sm.counter_found, st.counter_found, sizeof(sm.counter_found));
         sm.header_parsed[0] = st.header_parsed[0]; sm.header_parsed[1] = st.header_parsed[1];

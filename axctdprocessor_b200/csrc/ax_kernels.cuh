@@ -291,31 +291,186 @@ static inline void ax_launch_demod_fused_any(const AxWave& w, const AxCfg& c, in
 }
 
 // ------------------------------------------------------------------ bit decisions with shared window sums
-// As ax_bits_item, but a window that needs double precision is summed by the whole warp.
-__global__ void __launch_bounds__(128) k_bits_warp(AxWave w, int64_t n, int phase) {
-    const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// As ax_bits_item, one CTA per run() iteration (no per-bit searches); a window that needs double
+// precision is summed by the whole warp.
+__global__ void __launch_bounds__(128) k_bits_chunk(AxWave w, int phase) {
+    const int64_t cg = blockIdx.x;
+    const int d = ax_find_owner(w.drop, w.n_drops, &AxDrop::chunk_base, cg);
+    const AxDrop& dr = w.drop[d];
+    const AxState& st = w.st[d];
+    const int k = (int)(cg - dr.chunk_base);
+    if (st.sm_status < 1 || st.nedges_total == 0 || k < st.k0 || k >= st.n_chunks || k >= dr.chunk_cap) return;
+    const AxChunk& ch = w.chunk[cg];
+    const int nb = ch.n_edges - 1;
+    if (nb <= 0) return;
     const int lane = threadIdx.x & 31;
-    AxBitFix fx;
-    fx.d = 0; fx.i = 0; fx.q0 = 0;
-    const bool need = slot < n && ax_bits_need(w, slot, phase, &fx);
-    unsigned ball = __ballot_sync(0xffffffffu, need);
-    while (ball) {
-        const int L = __ffs((int)ball) - 1;
-        ball &= ball - 1;
-        AxBitFix f;
-        f.d = __shfl_sync(0xffffffffu, fx.d, L);
-        f.i = __shfl_sync(0xffffffffu, fx.i, L);
-        f.q0 = __shfl_sync(0xffffffffu, fx.q0, L);
-        const AxDrop& dr = w.drop[f.d];
-        double acc[4];
-        ax_gwin_partial(w.pcm + dr.pcm_off, f.i, f.q0, w.cfg[dr.cfg], lane, 32, acc);
+    const int64_t slot0 = dr.edge_base + ch.bit_off;
+    for (int jb = threadIdx.x - lane; jb < nb; jb += blockDim.x) {       // warp-uniform trip count
+        const int mine = jb + lane;
+        const int64_t slot = slot0 + mine;
+        AxBitFix fx;
+        fx.d = 0; fx.i = 0; fx.q0 = 0;
+        const bool need = mine < nb && ax_bits_need(w, d, k, slot, phase, &fx);
+        unsigned ball = __ballot_sync(0xffffffffu, need);
+        while (ball) {
+            const int L = __ffs((int)ball) - 1;
+            ball &= ball - 1;
+            AxBitFix f;
+            f.d = d;
+            f.i = __shfl_sync(0xffffffffu, fx.i, L);
+            f.q0 = __shfl_sync(0xffffffffu, fx.q0, L);
+            double acc[4];
+            ax_gwin_partial(w.pcm + dr.pcm_off, f.i, f.q0, w.cfg[dr.cfg], lane, 32, acc);
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
+            for (int q = 0; q < 4; ++q)
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
-        if (lane == L) ax_bits_fix(w, slot, f, acc);
+                for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+            if (lane == L) ax_bits_fix(w, slot, f, acc);
+        }
+        if (phase == 1 && mine < nb) ax_bits_decide(w, d, slot);
     }
-    if (phase == 1 && slot < n) ax_bits_decide(w, slot);
+}
+
+// ------------------------------------------------------------------ bit edges (CTA per run() iteration)
+// ax_emit_item with one thread per edge: the continuous part of a chunk's walk is read off the
+// canonical walk by rank (ax_emit_canon_pos); only the few edges stepped explicitly before the walk
+// joins it are produced by one thread.
+__global__ void __launch_bounds__(128) k_emit_chunk(AxWave w) {
+    const int64_t cg = blockIdx.x;
+    const int d = ax_find_owner(w.drop, w.n_drops, &AxDrop::chunk_base, cg);
+    const AxDrop& dr = w.drop[d];
+    AxState& st = w.st[d];
+    const int k = (int)(cg - dr.chunk_base);
+    if (!ax_emit_active(w, dr, st, k)) return;
+    AxChunk& ch = w.chunk[cg];
+    const int ne = ch.n_edges;
+    if (ne <= 0) return;
+    const AxCfg& c = w.cfg[dr.cfg];
+    const int nhe = ch.n_head_edges, npre = ch.n_pre;
+    const bool merged = ch.merge_pos >= 0;
+    for (int t = threadIdx.x; t < ne; t += blockDim.x) {
+        if (t < nhe) ax_emit_edge(w, dr, st, c, ch, cg, k, t, 0);
+        else if (t >= nhe + npre) { if (merged) ax_emit_edge(w, dr, st, c, ch, cg, k, t, ax_emit_canon_pos(w, dr, ch, t)); }
+        else if (t == nhe) {
+            const uint8_t* nx = w.zc_nx + dr.zc_base;
+            int64_t pos = ch.g_first;
+            for (int q = 0; q < npre; ++q) { ax_emit_edge(w, dr, st, c, ch, cg, k, nhe + q, pos); if (q < npre - 1) pos += nx[pos]; }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ dense crossing arrays
+// ax_compact_item with a warp per segment (coalesced), and the walk steps (ax_nx_item) with a 2-D grid.
+__global__ void __launch_bounds__(256) k_compact_warp(AxWave w) {
+    const int64_t seg = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (seg >= w.nseg_total) return;
+    const int lane = threadIdx.x & 31;
+    const int d = w.seg_drop[seg];
+    const AxDrop& dr = w.drop[d];
+    if (w.st[d].zc_count == 0) return;
+    const int64_t src = seg * (int64_t)w.seg_cap, dst = dr.zc_base + w.seg_off[seg] + w.blk_sum[seg / 128];
+    const int cnt = w.seg_cnt[seg];
+    for (int q = lane; q < cnt; q += 32) {
+        w.zc_idx[dst + q] = w.rec_idx[src + q];
+        w.zc_a1[dst + q] = w.rec_a1[src + q];
+        w.zc_a2[dst + q] = w.rec_a2[src + q];
+    }
+}
+
+__global__ void __launch_bounds__(256) k_nx_grid(AxWave w) {
+    const int d = blockIdx.y;
+    const AxDrop& dr = w.drop[d];
+    const int64_t M = w.st[d].zc_count;
+    const AxCfg& c = w.cfg[dr.cfg];
+    const int32_t* zi = w.zc_idx + dr.zc_base;
+    for (int64_t pos = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pos < M; pos += (int64_t)gridDim.x * blockDim.x)
+        w.zc_nx[dr.zc_base + pos] = (pos + 4 < M) ? (uint8_t)(ax_next(zi, pos, c.fs2, 2 * (int64_t)c.bitrate) - pos) : (uint8_t)0;
+}
+
+// ------------------------------------------------------------------ canonical walk tables (block per drop)
+// Same result as ax_canon_item.  The per-tile exit maps compose associatively, so each thread folds a
+// contiguous range of tiles into one 4-state map, the ranges are chained through shared memory, and a
+// second sweep writes the visited masks and the running counts.
+#define AX_CANON_THREADS 256
+__global__ void __launch_bounds__(AX_CANON_THREADS) k_canon_block(AxWave w) {
+    const int d = blockIdx.x;
+    const AxDrop& dr = w.drop[d];
+    const AxState& st = w.st[d];
+    if (st.status != 0 || st.sm_status < 1) return;
+    const AxCfg& c = w.cfg[dr.cfg];
+    const int64_t M = st.zc_count;
+    const int ntile = (int)((M + AX_TILE - 1) / AX_TILE);
+    uint64_t* cmask = w.cmask + dr.tile_base;
+    int32_t* crank = w.crank + dr.tile_base;
+    const uint64_t* tmask = w.tile_mask + (int64_t)dr.tile_base * 4;
+    const uint32_t* tmap = w.tile_map + dr.tile_base;
+    __shared__ int64_t s_entry;
+    __shared__ int s_state[AX_CANON_THREADS + 1];
+    __shared__ uint32_t s_map[AX_CANON_THREADS];
+    __shared__ int s_cnt[AX_CANON_THREADS + 1];
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        const int64_t entry = ax_lower_bound(w.zc_idx + dr.zc_base, M, w.chunk[dr.chunk_base + st.k0].s + c.pad);
+        s_entry = entry;
+        if (entry < M) {
+            uint64_t m0;
+            s_state[0] = ax_canon_first_tile(w.zc_nx + dr.zc_base, M, entry, &m0);
+            const int t0 = (int)(entry / AX_TILE);
+            cmask[t0] = m0; crank[t0] = 0;
+            s_cnt[0] = ax_popc64(m0);
+        }
+    }
+    __syncthreads();
+    const int64_t entry = s_entry;
+    const int t0 = (int)(entry / AX_TILE);
+    for (int t = tid; t < ntile && t < t0; t += AX_CANON_THREADS) { cmask[t] = 0; crank[t] = 0; }
+    if (entry >= M) return;
+    const int nrest = ntile - (t0 + 1);
+    const int per = (nrest + AX_CANON_THREADS - 1) / AX_CANON_THREADS;
+    const int ta = min(t0 + 1 + tid * per, ntile), tb = min(ta + per, ntile);
+    {   // fold my range into one map
+        uint32_t f = 0x03020100u;
+        for (int t = ta; t < tb; ++t) {
+            const uint32_t m = tmap[t];
+            uint32_t g = 0;
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+                const uint32_t sI = (f >> (8 * o)) & 0xFFu;
+                const uint32_t e = sI < 4u ? ((m >> (8 * sI)) & 0xFFu) : 0xFFu;
+                g |= e << (8 * o);
+            }
+            f = g;
+        }
+        s_map[tid] = f;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int state = s_state[0];
+        for (int i = 0; i < AX_CANON_THREADS; ++i) {
+            s_state[i] = state;
+            state = ax_map_apply(s_map[i], state);
+        }
+    }
+    __syncthreads();
+    int state = s_state[tid];
+    int local = 0;
+    for (int t = ta; t < tb; ++t) {
+        const uint64_t m = state < 4 ? tmask[(int64_t)t * 4 + state] : 0ull;
+        cmask[t] = m; crank[t] = local;
+        local += __popcll(m);
+        state = ax_map_apply(tmap[t], state);
+    }
+    const int first_cnt = s_cnt[0];
+    __syncthreads();
+    s_cnt[tid + 1] = local;
+    __syncthreads();
+    if (tid == 0) {
+        int run = first_cnt;
+        for (int i = 0; i < AX_CANON_THREADS; ++i) { const int v = s_cnt[i + 1]; s_cnt[i + 1] = run; run += v; }
+    }
+    __syncthreads();
+    const int base = s_cnt[tid + 1];
+    for (int t = ta; t < tb; ++t) crank[t] += base;
 }
 
 // ------------------------------------------------------------------ tones
@@ -441,66 +596,3 @@ static inline void ax_launch_tone_blocked(const AxWave& w, int cfg_id, const AxC
     k_tone_combine<<<(w.pw_total + 127) / 128, 128, 0, stream>>>(w, cfg_id, phase_b);
 }
 
-// ------------------------------------------------------------------ frame sync (warp per drop)
-// Same greedy scan as ax_frames_item (parse.py:57-89 over AXCTDprocessor.py's per-iteration buffers),
-// but one warp walks a drop: the 32 lanes fetch 1024 mask positions per load, so the chain of
-// dependent memory latencies is one per 32 frames instead of one per frame.  Control flow is
-// warp-uniform; lane 0 records the frame positions.
-__global__ void __launch_bounds__(128) k_frames_warp(AxWave w) {
-    const int d = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    if (d >= w.n_drops) return;
-    const int lane = threadIdx.x & 31;
-    const AxDrop& dr = w.drop[d];
-    AxState& st = w.st[d];
-    if (lane == 0) st.n_frames = 0;
-    if (st.status != 0 || st.sm_status < 2 || st.k2 < 0 || st.nedges_total == 0) return;
-    AxChunk* ch = w.chunk + dr.chunk_base;
-    const int32_t* I = w.edge_idx + dr.edge_base;
-    const uint32_t* vw = w.validw + dr.edge_base / 32;
-    const int64_t nwords = (st.nbits_total + 31) / 32;
-    axctd_frame* fr = w.frame + dr.frame_base;
-    const int64_t prof = st.profstartind;
-    int64_t cur = 0, wbase = -1;
-    uint32_t myword = 0;
-    int32_t nf = 0;
-    for (int k = st.k2; k < st.n_chunks; ++k) {
-        if (lane == 0) { ch[k].frame_begin = nf; ch[k].frame_end = nf; }
-        if (ch[k].n_edges <= 0) continue;
-        const int64_t NI = ch[k].edge_off + ch[k].n_edges, NB = ch[k].bit_off + ch[k].n_edges - 1;
-        if (cur < NI && (int64_t)I[cur] <= prof) {
-            const int64_t f = ax_first_gt(I, cur, NI, prof);
-            if (f < 0) { if (lane == 0) ax_raise(st, AXCTD_DROP_TRIM_INDEX, k); return; }
-            cur = f;
-        }
-        const int64_t limit = NB - 32;
-        int64_t p = cur;
-        while (p < limit) {
-            const int64_t wi = p >> 5;
-            if (wbase < 0 || wi < wbase || wi >= wbase + 32) {
-                wbase = wi;
-                myword = (wbase + lane < nwords) ? vw[wbase + lane] : 0u;
-            }
-            uint32_t v = myword;
-            const int64_t mine = wbase + lane;
-            if (mine < wi) v = 0u; else if (mine == wi) v &= ~((1u << (p & 31)) - 1u);
-            const unsigned ball = __ballot_sync(0xffffffffu, v != 0u);
-            if (ball == 0u) { p = (wbase + 32) << 5; if (p > limit) p = limit; continue; }
-            const int L = __ffs((int)ball) - 1;
-            const uint32_t vv = __shfl_sync(0xffffffffu, v, L);
-            const int64_t pos = ((wbase + L) << 5) + (__ffs((int)vv) - 1);
-            if (pos >= limit) { p = limit; break; }
-            if (nf >= dr.frame_cap) { if (lane == 0) { ax_raise(st, AXCTD_DROP_CAPACITY, k); w.flags[AX_FLAG_CAP] = 1; } return; }
-            if (lane == 0) { fr[nf].edge_index = pos; fr[nf].chunk = k; }
-            ++nf;
-            p = pos + 32;
-        }
-        if (p > cur) cur = p;                      // AXCTDprocessor.py:618-621
-        if (lane == 0) ch[k].frame_end = nf;
-    }
-    if (lane == 0) st.n_frames = nf;
-}
-
-static inline void ax_launch_frames_warp(const AxWave& w, cudaStream_t stream) {
-    const int warps_per_block = 4;
-    k_frames_warp<<<(w.n_drops + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, stream>>>(w);
-}

@@ -280,52 +280,68 @@ AX_HDN inline void ax_offsets_item(const AxWave& w, int64_t d) {
 
 // AXCTDprocessor.py:413-429: bit edges of one chunk and the signal level of the
 // nearest power sample of THIS chunk for every edge.
+// One edge: t < n_head_edges comes from the exact head, otherwise `pos` is its dense crossing ordinal.
+AX_HD void ax_emit_edge(const AxWave& w, const AxDrop& dr, AxState& st, const AxCfg& c, AxChunk& ch, int64_t cg, int k, int t, int64_t pos) {
+    int64_t idx; double v1, v2;
+    if (t < ch.n_head_edges) {
+        idx = ch.s + w.head_idx[cg * (int64_t)w.head_zc_cap_max + t];
+        v1 = w.head_a1[cg * (int64_t)w.head_zc_cap_max + t]; v2 = w.head_a2[cg * (int64_t)w.head_zc_cap_max + t];
+    } else {
+        idx = w.zc_idx[dr.zc_base + pos]; v1 = w.zc_a1[dr.zc_base + pos]; v2 = w.zc_a2[dr.zc_base + pos];
+        if (t < ch.n_edges - 1 && idx + c.inset + c.npcm > ch.e) ax_raise(st, AXCTD_DROP_SHORT_WINDOW, k);   // demodulate.py:100-101
+    }
+    const int64_t eo = dr.edge_base + ch.edge_off + t;
+    w.edge_idx[eo] = (int32_t)idx;
+    if (t < ch.n_edges - 1) { w.a1[dr.edge_base + ch.bit_off + t] = v1; w.a2[dr.edge_base + ch.bit_off + t] = v2; }
+    // np.argmin(np.abs(recent_pwrinds - ci)): nearest grid point, first on ties (:425,:428)
+    if (ch.np > 0) {
+        const int64_t off = idx - ch.s;
+        int64_t jj = off / c.d_pcm;
+        const int64_t rem = off - jj * c.d_pcm;
+        if (2 * rem > c.d_pcm) ++jj;
+        if (jj > ch.np - 1) jj = ch.np - 1;
+        if (jj < 0) jj = 0;
+        w.lvl400[eo] = w.r400[dr.pw_base + ch.pw_off + jj];
+        w.lvl7500[eo] = ax_sub(w.r7500[dr.pw_base + ch.pw_off + jj], ch.mean7500);
+    } else { w.lvl400[eo] = ax_nan(); w.lvl7500[eo] = ax_nan(); }
+}
+
+// position of the (r+1)-th set bit of m (r < popcount(m))
+AX_HD int ax_select64(uint64_t m, int r) {
+    for (int q = 0; q < r; ++q) m &= m - 1ull;
+    return ax_ctz64(m);
+}
+
+// dense ordinal of edge t >= n_head_edges + n_pre of a chunk: the (t - n_head_edges - n_pre)-th canonical crossing from merge_pos
+AX_HD int64_t ax_emit_canon_pos(const AxWave& w, const AxDrop& dr, const AxChunk& ch, int t) {
+    const uint64_t* cmask = w.cmask + dr.tile_base;
+    const int32_t* crank = w.crank + dr.tile_base;
+    const int64_t r = ax_canon_rank(cmask, crank, ch.merge_pos) + (t - ch.n_head_edges - ch.n_pre);
+    int64_t lo = ch.merge_pos / AX_TILE, hi = (ch.q_last) / AX_TILE;       // last tile with crank <= r
+    while (lo < hi) { const int64_t mid = (lo + hi + 1) >> 1; if ((int64_t)crank[mid] <= r) lo = mid; else hi = mid - 1; }
+    return lo * AX_TILE + ax_select64(cmask[lo], (int)(r - crank[lo]));
+}
+
+AX_HD bool ax_emit_active(const AxWave& w, const AxDrop& dr, const AxState& st, int k) {
+    return !(st.sm_status < 1 || k < st.k0 || k >= st.n_chunks || k >= dr.chunk_cap || st.nedges_total == 0);
+}
+
+// generic form: one thread per chunk (the CUDA build uses k_emit_chunk, one thread per edge)
 AX_HDN inline void ax_emit_item(const AxWave& w, int64_t cg) {
     const int d = ax_find_owner(w.drop, w.n_drops, &AxDrop::chunk_base, cg);
     const AxDrop& dr = w.drop[d];
     AxState& st = w.st[d];
     const int k = (int)(cg - dr.chunk_base);
-    if (st.sm_status < 1 || k < st.k0 || k >= st.n_chunks || st.nedges_total == 0) return;
+    if (!ax_emit_active(w, dr, st, k)) return;
     AxChunk& ch = w.chunk[cg];
     if (ch.n_edges <= 0) return;
     const AxCfg& c = w.cfg[dr.cfg];
-    const int32_t* zi = w.zc_idx + dr.zc_base;
-    const float* za1 = w.zc_a1 + dr.zc_base; const float* za2 = w.zc_a2 + dr.zc_base;
-    const int32_t* hz = w.head_idx + cg * (int64_t)w.head_zc_cap_max;
-    const double* ha1 = w.head_a1 + cg * (int64_t)w.head_zc_cap_max;
-    const double* ha2 = w.head_a2 + cg * (int64_t)w.head_zc_cap_max;
-    int32_t* eidx = w.edge_idx + dr.edge_base + ch.edge_off;
-    double* l400 = w.lvl400 + dr.edge_base + ch.edge_off;
-    double* l7500 = w.lvl7500 + dr.edge_base + ch.edge_off;
-    double* a1 = w.a1 + dr.edge_base + ch.bit_off;
-    double* a2 = w.a2 + dr.edge_base + ch.bit_off;
-    const double* r400 = w.r400 + dr.pw_base + ch.pw_off;
-    const double* r7500 = w.r7500 + dr.pw_base + ch.pw_off;
     const uint8_t* nx = w.zc_nx + dr.zc_base;
     int64_t pos = ch.g_first;
     for (int t = 0; t < ch.n_edges; ++t) {
-        int64_t idx; double v1, v2;
-        if (t < ch.n_head_edges) { idx = ch.s + hz[t]; v1 = ha1[t]; v2 = ha2[t]; }
-        else {
-            idx = zi[pos]; v1 = za1[pos]; v2 = za2[pos];
-            if (t < ch.n_edges - 1) {
-                if (idx + c.inset + c.npcm > ch.e) ax_raise(st, AXCTD_DROP_SHORT_WINDOW, k);   // demodulate.py:100-101
-                pos += nx[pos];
-            }
-        }
-        eidx[t] = (int32_t)idx;
-        if (t < ch.n_edges - 1) { a1[t] = v1; a2[t] = v2; }
-        // np.argmin(np.abs(recent_pwrinds - ci)): nearest grid point, first on ties (:425,:428)
-        if (ch.np > 0) {
-            const int64_t off = idx - ch.s;
-            int64_t jj = off / c.d_pcm;
-            const int64_t rem = off - jj * c.d_pcm;
-            if (2 * rem > c.d_pcm) ++jj;
-            if (jj > ch.np - 1) jj = ch.np - 1;
-            if (jj < 0) jj = 0;
-            l400[t] = r400[jj];
-            l7500[t] = ax_sub(r7500[jj], ch.mean7500);
-        } else { l400[t] = ax_nan(); l7500[t] = ax_nan(); }
+        if (t >= ch.n_head_edges + ch.n_pre && ch.merge_pos >= 0) pos = ax_emit_canon_pos(w, dr, ch, t);
+        ax_emit_edge(w, dr, st, c, ch, cg, k, t, pos);
+        if (t >= ch.n_head_edges && t < ch.n_head_edges + ch.n_pre - 1) pos += nx[pos];
     }
 }
 
@@ -427,20 +443,17 @@ AX_HD int ax_chunk_of_bit(const AxChunk* ch, int k0, int n_chunks, int64_t j) {
 
 struct AxBitFix { int32_t d; int64_t i, q0; };
 
-// Does bit `slot` need a double-precision window in this phase?
-AX_HD bool ax_bits_need(const AxWave& w, int64_t slot, int phase, AxBitFix* fx) {
-    const int d = ax_find_owner(w.drop, w.n_drops, &AxDrop::edge_base, slot);
+// Does bit `slot` (bit j of drop d, demodulated by iteration k) need a double-precision window in this phase?
+AX_HD bool ax_bits_need(const AxWave& w, int d, int k, int64_t slot, int phase, AxBitFix* fx) {
     const AxDrop& dr = w.drop[d];
     const AxState& st = w.st[d];
     const int64_t j = slot - dr.edge_base;
-    if (j >= st.nbits_total || st.sm_status < 1) return false;
     const AxCfg& c = w.cfg[dr.cfg];
     const double p1 = w.a1[slot];
     bool need = w.bitfix_all != 0;
     int64_t ei = -1;
-    const AxChunk* ch = w.chunk + dr.chunk_base;
-    const int k = ax_chunk_of_bit(ch, st.k0, st.n_chunks, j);
-    const int64_t e = ch[k].edge_off + (j - ch[k].bit_off);
+    const AxChunk& ch = w.chunk[dr.chunk_base + k];
+    const int64_t e = ch.edge_off + (j - ch.bit_off);
     if (phase == 0) {
         ei = w.edge_idx[dr.edge_base + e];
         // header-1 calibration bits (AXCTDprocessor.py:459-466).  The reference pairs bit j with edge-list
@@ -470,7 +483,7 @@ AX_HD bool ax_bits_need(const AxWave& w, int64_t slot, int phase, AxBitFix* fx) 
     }
     if (!need) return false;
     if (ei < 0) ei = w.edge_idx[dr.edge_base + e];
-    fx->d = d; fx->i = ei; fx->q0 = ch[k].s;
+    fx->d = d; fx->i = ei; fx->q0 = ch.s;
     return true;
 }
 
@@ -494,12 +507,10 @@ AX_HD void ax_bits_fix(const AxWave& w, int64_t slot, const AxBitFix& fx, const 
     w.a1[slot] = e1; w.a2[slot] = e2;
 }
 
-AX_HD void ax_bits_decide(const AxWave& w, int64_t slot) {
-    const int d = ax_find_owner(w.drop, w.n_drops, &AxDrop::edge_base, slot);
+AX_HD void ax_bits_decide(const AxWave& w, int d, int64_t slot) {
     const AxDrop& dr = w.drop[d];
     const AxState& st = w.st[d];
     const int64_t j = slot - dr.edge_base;
-    if (j >= st.nbits_total) return;
     const double scale = (j >= st.scale_switch_bit) ? st.scale : w.cfg[dr.cfg].scale0;
     const double p1 = w.a1[slot];
     const double p2 = ax_mul(w.a2[slot], scale);
@@ -509,12 +520,18 @@ AX_HD void ax_bits_decide(const AxWave& w, int64_t slot) {
 
 // one thread does everything (generic form; the CUDA build shares the window sum across a warp)
 AX_HDN inline void ax_bits_item(const AxWave& w, int64_t slot, int phase) {
+    const int d = ax_find_owner(w.drop, w.n_drops, &AxDrop::edge_base, slot);
+    const AxDrop& dr0 = w.drop[d];
+    const AxState& st = w.st[d];
+    const int64_t j = slot - dr0.edge_base;
+    if (j >= st.nbits_total || st.sm_status < 1) return;
+    const int k = ax_chunk_of_bit(w.chunk + dr0.chunk_base, st.k0, st.n_chunks, j);
     AxBitFix fx;
-    if (ax_bits_need(w, slot, phase, &fx)) {
+    if (ax_bits_need(w, d, k, slot, phase, &fx)) {
         const AxDrop& dr = w.drop[fx.d];
         double acc[4];
         ax_gwin_partial(w.pcm + dr.pcm_off, fx.i, fx.q0, w.cfg[dr.cfg], 0, 1, acc);
         ax_bits_fix(w, slot, fx, acc);
     }
-    if (phase == 1) ax_bits_decide(w, slot);
+    if (phase == 1) ax_bits_decide(w, d, slot);
 }

@@ -147,44 +147,121 @@ AX_HD int64_t ax_next_valid(const uint32_t* vw, int64_t p, int64_t limit) {
     return limit;
 }
 
-// Greedy frame synchronisation over the profile bits of one drop, grouped by
-// run() iteration exactly as the reference consumes its buffers.  Only the frame
-// positions are recorded here; ax_calib_item fills the records in parallel.
-AX_HDN inline void ax_frames_item(const AxWave& w, int64_t d) {
+// ---- greedy frame synchronisation (parse.py:57-89 over AXCTDprocessor.py's per-iteration buffers) ----
+// The scan of iteration k is a function of one integer, the bit position `cur` where the previous
+// iteration stopped: profile trim (AXCTDprocessor.py:545-551), then candidate by candidate up to
+// limit = NB - 32 (parse.py:57), consuming the scanned bits (:618-621).  ax_frames_scan is that
+// function; fr != nullptr records the frame positions.
+//   returns 0, or AXCTD_DROP_TRIM_INDEX / AXCTD_DROP_CAPACITY
+AX_HD int ax_frames_scan(const AxWave& w, const AxDrop& dr, const AxState& st, const AxChunk& ch, int k, int64_t cur,
+                         axctd_frame* fr, int32_t room, int32_t* cnt_out, int64_t* cur_out) {
+    const int32_t* I = w.edge_idx + dr.edge_base;
+    const uint32_t* vw = w.validw + dr.edge_base / 32;
+    const int64_t NI = ch.edge_off + ch.n_edges, NB = ch.bit_off + ch.n_edges - 1;
+    int32_t nf = 0;
+    if (cur < NI && (int64_t)I[cur] <= st.profstartind) {              // AXCTDprocessor.py:545-551
+        const int64_t f = ax_first_gt(I, cur, NI, st.profstartind);
+        if (f < 0) return AXCTD_DROP_TRIM_INDEX;
+        cur = f;
+    }
+    const int64_t limit = NB - 32;                                     // parse.py:57 `while s < numbits - 32`
+    int64_t p = cur;
+    while (p < limit) {
+        p = ax_next_valid(vw, p, limit);
+        if (p >= limit) break;
+        if (nf >= room) return AXCTD_DROP_CAPACITY;
+        if (fr) { fr[nf].edge_index = p; fr[nf].chunk = k; }           // bit position; ax_calib_item resolves it
+        ++nf;
+        p += 32;
+    }
+    if (p > cur) cur = p;                                              // AXCTDprocessor.py:618-621
+    *cnt_out = nf; *cur_out = cur;
+    return 0;
+}
+
+// Speculative scan of one iteration: the scans lock onto the frame grid, so a scan started a few
+// frames before the end of the previous iteration's bits arrives at this iteration with the same
+// `cur` as the true one (checked, and repaired if not, by ax_frames_chain_item).
+#define AX_FRAME_WARM 256
+AX_HDN inline void ax_frames_spec_item(const AxWave& w, int64_t cg) {
+    const int d = ax_find_owner(w.drop, w.n_drops, &AxDrop::chunk_base, cg);
+    const AxDrop& dr = w.drop[d];
+    const AxState& st = w.st[d];
+    const int k = (int)(cg - dr.chunk_base);
+    if (st.status != 0 || st.sm_status < 2 || st.k2 < 0 || st.nedges_total == 0 || k < st.k2 || k >= st.n_chunks || k >= dr.chunk_cap) return;
+    AxChunk* chs = w.chunk + dr.chunk_base;
+    AxChunk& ch = chs[k];
+    ch.scan_from = -1; ch.scan_cnt = 0; ch.scan_end = -1;
+    if (ch.n_edges <= 0) return;
+    int kp = k - 1;
+    while (kp >= st.k2 && chs[kp].n_edges <= 0) --kp;
+    int64_t cur = 0;
+    if (kp >= st.k2) {
+        const AxChunk& pc = chs[kp];
+        const int64_t plimit = pc.bit_off + pc.n_edges - 1 - 32;
+        const uint32_t* vw = w.validw + dr.edge_base / 32;
+        int64_t p = plimit - AX_FRAME_WARM;
+        if (p < 0) p = 0;
+        cur = p;
+        while (p < plimit) {
+            p = ax_next_valid(vw, p, plimit);
+            if (p >= plimit) break;
+            p += 32;
+        }
+        if (p > cur) cur = p;
+    }
+    int32_t cnt; int64_t cend;
+    if (ax_frames_scan(w, dr, st, ch, k, cur, nullptr, 0x7fffffff, &cnt, &cend) != 0) return;       // left to the chain pass
+    ch.scan_from = cur; ch.scan_cnt = cnt; ch.scan_end = cend;
+}
+
+// Sequential pass over the iterations of one drop: accept the speculative scans whose start matches,
+// redo the others, assign the frame ranges.
+AX_HDN inline void ax_frames_chain_item(const AxWave& w, int64_t d) {
     const AxDrop& dr = w.drop[d];
     AxState& st = w.st[d];
     st.n_frames = 0;
     if (st.status != 0 || st.sm_status < 2 || st.k2 < 0 || st.nedges_total == 0) return;
     AxChunk* ch = w.chunk + dr.chunk_base;
-    const int32_t* I = w.edge_idx + dr.edge_base;
-    const uint32_t* vw = w.validw + dr.edge_base / 32;
-    axctd_frame* fr = w.frame + dr.frame_base;
-    const int64_t prof = st.profstartind;
     int64_t cur = 0;
     int32_t nf = 0;
     for (int k = st.k2; k < st.n_chunks; ++k) {
         ch[k].frame_begin = nf; ch[k].frame_end = nf;
         if (ch[k].n_edges <= 0) continue;
-        const int64_t NI = ch[k].edge_off + ch[k].n_edges, NB = ch[k].bit_off + ch[k].n_edges - 1;
-        if (cur < NI && (int64_t)I[cur] <= prof) {                     // AXCTDprocessor.py:545-551
-            const int64_t f = ax_first_gt(I, cur, NI, prof);
-            if (f < 0) { ax_raise(st, AXCTD_DROP_TRIM_INDEX, k); return; }
-            cur = f;
+        if (ch[k].scan_from != cur) {                                   // mis-speculated (or first) iteration
+            int32_t cnt; int64_t cend;
+            const int err = ax_frames_scan(w, dr, st, ch[k], k, cur, nullptr, 0x7fffffff, &cnt, &cend);
+            if (err) { ax_raise(st, err, k); return; }
+            ch[k].scan_from = cur; ch[k].scan_cnt = cnt; ch[k].scan_end = cend;
+            st.n_frame_respec++;
         }
-        const int64_t limit = NB - 32;                                 // parse.py:57 `while s < numbits - 32`
-        int64_t p = cur;
-        while (p < limit) {
-            p = ax_next_valid(vw, p, limit);
-            if (p >= limit) break;
-            if (nf >= dr.frame_cap) { ax_raise(st, AXCTD_DROP_CAPACITY, k); w.flags[AX_FLAG_CAP] = 1; return; }
-            fr[nf].edge_index = p; fr[nf].chunk = k;                   // bit position; ax_calib_item resolves it
-            ++nf;
-            p += 32;
-        }
-        if (p > cur) cur = p;                                          // AXCTDprocessor.py:618-621
+        if (nf + ch[k].scan_cnt > dr.frame_cap) { ax_raise(st, AXCTD_DROP_CAPACITY, k); w.flags[AX_FLAG_CAP] = 1; return; }
+        nf += ch[k].scan_cnt;
         ch[k].frame_end = nf;
+        cur = ch[k].scan_end;
     }
     st.n_frames = nf;
+}
+
+// Record the frame positions of one iteration (its true start is known now).
+AX_HDN inline void ax_frames_write_item(const AxWave& w, int64_t cg) {
+    const int d = ax_find_owner(w.drop, w.n_drops, &AxDrop::chunk_base, cg);
+    const AxDrop& dr = w.drop[d];
+    const AxState& st = w.st[d];
+    const int k = (int)(cg - dr.chunk_base);
+    if (st.status != 0 || st.n_frames == 0 || st.k2 < 0 || k < st.k2 || k >= st.n_chunks || k >= dr.chunk_cap) return;
+    const AxChunk& ch = w.chunk[cg];
+    if (ch.n_edges <= 0 || ch.frame_end <= ch.frame_begin) return;
+    int32_t cnt; int64_t cend;
+    ax_frames_scan(w, dr, st, ch, k, ch.scan_from, w.frame + dr.frame_base + ch.frame_begin, ch.frame_end - ch.frame_begin, &cnt, &cend);
+}
+
+// generic one-thread form of the three passes (reference order)
+AX_HDN inline void ax_frames_item(const AxWave& w, int64_t d) {
+    const AxDrop& dr = w.drop[d];
+    for (int k = 0; k < dr.chunk_cap; ++k) ax_frames_spec_item(w, dr.chunk_base + k);
+    ax_frames_chain_item(w, d);
+    for (int k = 0; k < dr.chunk_cap; ++k) ax_frames_write_item(w, dr.chunk_base + k);
 }
 
 // ---- PSS-78 (gsw_sp_from_c of GSW-C; reference parse.py:132) ----------------

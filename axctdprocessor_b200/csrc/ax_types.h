@@ -114,6 +114,10 @@ struct AxChunk {
     int64_t q_last;              // dense ordinal of the chunk's last usable crossing
     int64_t bit_off, edge_off;   // offsets into the drop's bit / edge arrays
     int64_t first_edge;          // first bit edge (global PCM index)
+    int64_t merge_pos;           // dense ordinal where the chunk's walk joins the canonical walk, -1 if it never does
+    int32_t n_pre, pad_pre;      // edges of the continuous part before merge_pos (stepped explicitly)
+    int64_t scan_from, scan_end; // frame scan of this iteration: bit position it starts from / leaves to the next one
+    int32_t scan_cnt, pad_scan;  // frames it finds
     int32_t pw_off, np;          // power samples of this iteration
     int32_t n_head_edges;        // bit edges found inside the exact head
     int32_t n_edges;             // total bit edges (bits = n_edges - 1), 0 if not demodulated
@@ -159,6 +163,7 @@ struct AxState {
     int32_t header_read[3], header_chunk[3];
     int64_t nbits_total, nedges_total;
     int64_t n_frames, n_rows, n_hex;
+    int32_t n_frame_respec, pad4; // iterations whose speculative frame scan had to be redone
     int32_t header_parsed[2];
     uint16_t frame_data[2][72];
     uint8_t counter_found[2][72];
@@ -178,8 +183,9 @@ struct AxWave {
     int32_t* seg_cnt; int64_t* seg_off; int64_t* blk_sum;  // per segment / per block of 128 segments
     int32_t* rec_idx; float* rec_a1; float* rec_a2;         // [nseg_total * seg_cap]
     int32_t* zc_idx; float* zc_a1; float* zc_a2;            // dense, per drop at zc_base
-    uint8_t* zc_nx; uint8_t* zc_exit;                       // per crossing: walk step, tile exit
-    uint64_t* tile_mask;                                    // [tile][4] visited masks
+    uint8_t* zc_nx;                                         // per crossing: walk step
+    uint64_t* tile_mask; uint32_t* tile_map;                // [tile][4] visited masks, [tile] exit offsets (ax_tiles_item)
+    uint64_t* cmask; int32_t* crank;                        // [tile] canonical walk: visited mask, visited count before the tile
     // chunks
     AxChunk* chunk;
     int32_t* head_idx; double* head_a1; double* head_a2;    // [chunk][head_zc_cap_max]

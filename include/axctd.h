@@ -112,7 +112,7 @@ typedef struct axctd_drop_summary {
     int32_t pcm_ampl;
     int32_t n_recheck;          /* fp32 bit windows re-evaluated in double precision (decision within tolerance) */
     float   win32_max_rel_err;  /* largest relative |fp32 - fp64| window magnitude difference seen at those */
-    int32_t reserved;
+    int32_t n_frame_respec;     /* iterations whose speculative frame scan started from the wrong bit and was redone */
     /* header frames as decoded by parse_header (parse.py:197-285), slot 0 = header 2, 1 = header 3 */
     uint16_t frame_data[2][72];
     uint8_t  counter_found[2][72];
