@@ -76,6 +76,8 @@ AX_HDN inline void ax_stats_item(const AxWave& w, int64_t slab) {
 
 AX_HDN inline void ax_stats_fin(const AxWave& w, int64_t d) {
     AxState& st = w.st[d];
+    // min / max decide np.max(np.abs(x)) unless a sample equals -32768 (then st.ampl holds the exact rescan)
+    if (st.vmin != 0x7fffffff && st.vmin > -32768) st.ampl = st.vmax > -st.vmin ? st.vmax : -st.vmin;
     st.dc = ax_div((double)st.sum, (double)w.drop[d].n);
     st.ampl_d = (double)st.ampl;
     st.inv_ampl = ax_div(1.0, st.ampl_d);

@@ -46,7 +46,7 @@ AX_GLOBAL void k_init(int64_t n, AxWave w) {
     AX_FOR_ITEM(n) {
         AxState& st = w.st[item];
         memset(&st, 0, sizeof(AxState));
-        st.ampl = -2147483647 - 1;
+        st.ampl = -2147483647 - 1; st.vmax = -2147483647 - 1; st.vmin = 0x7fffffff;
         st.k0 = st.k2 = st.km = st.k1 = -1;
         st.firstpulse400 = -1; st.profstartind = -1; st.firstpointtime = -1.0; st.mean7500 = ax_nan();
         st.status_chunk = -1;
@@ -75,6 +75,8 @@ AX_GLOBAL void k_nx(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_nx_item(w, item); }
 AX_GLOBAL void k_tiles(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_tiles_item(w, item); }
 AX_GLOBAL void k_plan0(int64_t n, AxWave w) { AX_FOR_ITEM1(n) ax_plan0_item(w, item); }
 AX_GLOBAL void k_tone_direct(int64_t n, AxWave w, int phase_b) { AX_FOR_ITEM(n) ax_tone_direct_item(w, item, phase_b); }
+AX_GLOBAL void k_toneblock(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_toneblock_item(w, item); }
+AX_GLOBAL void k_tonewin(int64_t n, AxWave w, int phase_b) { AX_FOR_ITEM(n) ax_tonewin_item(w, item, phase_b); }
 AX_GLOBAL void k_pwfill(int64_t n, AxWave w, int phase_b) { AX_FOR_ITEM(n) ax_pwfill_item(w, item, phase_b); }
 AX_GLOBAL void k_levels(int64_t n, AxWave w, int phase_b) { AX_FOR_ITEM(n) ax_levels_item(w, item, phase_b); }
 AX_GLOBAL void k_sm(int64_t n, AxWave w, int phase_b) { AX_FOR_ITEM1(n) ax_sm_item(w, item, phase_b); }
@@ -104,6 +106,7 @@ struct axctd_engine {
     bool own_stream = true;
     std::string err;
     std::vector<AxCfg> cfgs;              // host copies (device pointers inside)
+    std::vector<AxToneTab> tone_tabs;     // per config: phasors of one tone block (kernel parameter)
     std::vector<void*> cfg_allocs;
     AxCfg* d_cfg = nullptr;
     int cfg_cap = 64;
@@ -152,6 +155,7 @@ struct axctd_batch {
     AxWave w;
     int16_t* d_pcm = nullptr;
     double* d_qc = nullptr;
+    int64_t tb_total = 0;
     int64_t pcm_total = 0, chunk_total = 0, edge_total = 0, frame_total = 0, zc_total = 0, tile_total = 0;
     // host mirrors of the results
     std::vector<AxState> st;
@@ -301,6 +305,17 @@ extern "C" int axctd_config_create(axctd_engine* e, const axctd_config_desc* ds,
     c.ybuf_len = c.head + c.npcm + 2;
     const int64_t G = ax_gcd(c.n_power, c.d_pcm);
     c.tone_G = (int)G; c.tone_nb = (int)(c.n_power / G); c.tone_stride = (int)(c.d_pcm / G);
+    AxToneTab ttab;
+    memset(&ttab, 0, sizeof(ttab));
+    {
+        long double ts[6] = {0, 0, 0, 0, 0, 0};
+        for (int m = 0; m < c.n_power; ++m)
+            for (int q = 0; q < 6; ++q) {
+                ts[q] += (long double)ds->tone_cs[6 * (size_t)m + q];
+                if (m < AX_TB) ttab.t[m][q] = ds->tone_cs[6 * (size_t)m + q];
+            }
+        for (int q = 0; q < 6; ++q) c.tone_tsum[q] = (double)ts[q];
+    }
     c.min_r400 = ds->min_r400; c.min_dr7500 = ds->min_dr7500;
     c.min_r400_inprof = ds->min_r400 / 2; c.min_dr7500_inprof = ds->min_dr7500 / 2;     // AXCTDprocessor.py:226,228
     c.trig_from = ds->trigger_from_s; c.trig_to = ds->trigger_to_s; c.scale0 = ds->high_bit_scale0;
@@ -359,6 +374,7 @@ extern "C" int axctd_config_create(axctd_engine* e, const axctd_config_desc* ds,
         ax_cfg_upload(e, &c.hist_edges, ds->hist_edges, (size_t)ds->n_hist_edges) ||
         ax_cfg_upload(e, &c.hist_centers, ds->hist_centers, (size_t)ds->n_hist_edges - 1)) return AXCTD_ERR_CUDA;
     e->cfgs.push_back(c);
+    e->tone_tabs.push_back(ttab);
     if (ax_h2d(e, e->d_cfg + (e->cfgs.size() - 1), &e->cfgs.back(), sizeof(AxCfg)) || ax_sync(e)) return AXCTD_ERR_CUDA;
     *config_id = (int)e->cfgs.size() - 1;
     return AXCTD_OK;
@@ -386,7 +402,7 @@ extern "C" int axctd_batch_create(axctd_engine* e, int n_drops, const int64_t* n
     for (int i = 0; i < 6; ++i) cudaEventCreate(&b->ev[i]);
 #endif
     int64_t total = 0;
-    int warm_max = 0, head_cap_max = 0, ybuf_max = 0, chunk_len_max = 0, blk_max = 1;
+    int warm_max = 0, head_cap_max = 0, ybuf_max = 0, chunk_len_max = 0;
     for (int d = 0; d < n_drops; ++d) {
         if (config_id[d] < 0 || config_id[d] >= (int)e->cfgs.size() || n_samples[d] < 0 || n_samples[d] > 2000000000LL) {
             e->err = "bad drop descriptor"; axctd_batch_destroy(b); return AXCTD_ERR_ARG;
@@ -397,7 +413,6 @@ extern "C" int axctd_batch_create(axctd_engine* e, int n_drops, const int64_t* n
         head_cap_max = std::max(head_cap_max, c.head_zc_cap);
         ybuf_max = std::max(ybuf_max, c.ybuf_len);
         chunk_len_max = std::max(chunk_len_max, c.chunk_len);
-        if (ax_tone_blocked_ok(c)) blk_max = std::max(blk_max, (c.chunk_len / c.d_pcm + 2) * c.tone_stride + c.tone_nb);
     }
     if (e->opt_force_exact) { ybuf_max = chunk_len_max + 8; head_cap_max = chunk_len_max / 4 + 64; }
     // segment length of the continuous pass: enough threads to fill the GPU, little warm-up waste
@@ -413,9 +428,10 @@ extern "C" int axctd_batch_create(axctd_engine* e, int n_drops, const int64_t* n
     w.seg_len = (int32_t)L; w.seg_cap = (int32_t)(L / 8 + 32);
     w.guard = e->opt_guard; w.tone_direct = e->opt_tone_direct; w.force_exact = e->opt_force_exact;
     w.bit_tol = e->opt_bit_tol; w.hist_tol = e->opt_hist_tol; w.bitfix_all = e->opt_bitfix_all;
-    w.head_zc_cap_max = head_cap_max; w.ybuf_len_max = ybuf_max; w.blk_stride = blk_max;
+    w.head_zc_cap_max = head_cap_max; w.ybuf_len_max = ybuf_max;
     b->drops.resize(n_drops);
-    int64_t pcm_off = 0, zc_off = 0, edge_off = 0;
+    int64_t pcm_off = 0, zc_off = 0, edge_off = 0, tb_off = 0;
+    int32_t ntb_max = 0;
     int32_t seg_off = 0, slab_off = 0, tile_off = 0, chunk_off = 0, pw_off = 0, frame_off = 0;
     for (int d = 0; d < n_drops; ++d) {
         const AxCfg& c = e->cfgs[config_id[d]];
@@ -425,6 +441,7 @@ extern "C" int axctd_batch_create(axctd_engine* e, int n_drops, const int64_t* n
         pcm_off += ((n + 63) / 64) * 64 + 64;
         dr.seg_base = seg_off; dr.nseg = (int32_t)((n + L - 1) / L); seg_off += ((dr.nseg + 127) / 128) * 128;
         dr.slab_base = slab_off; dr.nslab = (int32_t)((n + AX_STAT_SLAB - 1) / AX_STAT_SLAB); slab_off += dr.nslab;
+        dr.tb_base = tb_off; dr.ntb = (int32_t)(n / AX_TB); tb_off += dr.ntb; ntb_max = std::max(ntb_max, (int32_t)((n + AX_TB - 1) / AX_TB));
         dr.zc_base = zc_off; dr.zc_cap = n / e->opt_zc_div + 4096; zc_off += dr.zc_cap + 8;
         dr.tile_base = tile_off; dr.tile_cap = (int32_t)(dr.zc_cap / AX_TILE + 1); tile_off += dr.tile_cap;
         dr.chunk_base = chunk_off; dr.chunk_cap = (int32_t)(2 * (n / c.chunk_len) + 16); chunk_off += dr.chunk_cap;
@@ -434,7 +451,8 @@ extern "C" int axctd_batch_create(axctd_engine* e, int n_drops, const int64_t* n
     }
     b->pcm_total = pcm_off; b->zc_total = zc_off; b->tile_total = tile_off; b->chunk_total = chunk_off;
     b->edge_total = edge_off; b->frame_total = frame_off;
-    w.nseg_total = seg_off; w.nslab_total = slab_off; w.pw_total = pw_off;
+    w.nseg_total = seg_off; w.nslab_total = slab_off; w.pw_total = pw_off; w.ntb_max = ntb_max;
+    b->tb_total = tb_off;
     std::vector<int32_t> seg_drop(seg_off), slab_drop(slab_off);
     for (int d = 0; d < n_drops; ++d) {
         for (int s = 0; s < ((b->drops[d].nseg + 127) / 128) * 128; ++s) seg_drop[b->drops[d].seg_base + s] = d;
@@ -472,7 +490,7 @@ extern "C" int axctd_batch_create(axctd_engine* e, int n_drops, const int64_t* n
     bad |= ax_alloc_arr(b, &w.r400, pw_off);
     bad |= ax_alloc_arr(b, &w.r7500, pw_off);
     bad |= ax_alloc_arr(b, &w.pw_ind, pw_off);
-    bad |= ax_alloc_arr(b, &w.blk, (int64_t)chunk_off * w.blk_stride * 6);
+    bad |= ax_alloc_arr(b, &w.tb_sum, tb_off * 6 + 8);
     bad |= ax_alloc_arr(b, &w.edge_idx, edge_off);
     bad |= ax_alloc_arr(b, &w.lvl400, edge_off);
     bad |= ax_alloc_arr(b, &w.lvl7500, edge_off);
@@ -582,22 +600,18 @@ static void ax_merge_headers(const AxCfg& c, AxState& st, axctd_drop_summary& sm
 static int ax_run_tones(axctd_batch* b, int phase_b) {
     axctd_engine* e = b->eng;
     AxWave& w = b->w;
-#ifndef AXCTD_EMU
     if (!e->opt_tone_direct) {
         bool all_blocked = true;
-        for (size_t ci = 0; ci < e->cfgs.size(); ++ci) {
-            const AxCfg& c = e->cfgs[ci];
-            const bool used = std::any_of(b->drops.begin(), b->drops.end(), [&](const AxDrop& d) { return d.cfg == (int)ci; });
-            if (!used) continue;
-            if (!ax_tone_blocked_ok(c)) { all_blocked = false; continue; }
-            ax_launch_tone_blocked(w, (int)ci, c, phase_b, (int)b->chunk_total, e->stream);
-            e->launches += 2;
-        }
+        for (const AxDrop& dr : b->drops) if (!ax_tone_blocked_ok(e->cfgs[dr.cfg])) all_blocked = false;
+#ifndef AXCTD_EMU
+        if (w.pw_total > 0) { k_tone_windows<<<(unsigned)(((int64_t)w.pw_total * 32 + 255) / 256), 256, 0, e->stream>>>(w, phase_b); e->launches++; }
+#else
+        AX_LAUNCH(e, k_tonewin, (int64_t)w.pw_total, w, phase_b);
+#endif
         if (all_blocked) return 0;
         AX_LAUNCH(e, k_tone_direct, (int64_t)w.pw_total, w, phase_b + 2);   // only configs the blocked path skipped
         return 0;
     }
-#endif
     AX_LAUNCH(e, k_tone_direct, (int64_t)w.pw_total, w, phase_b);
     return 0;
 }
@@ -615,9 +629,17 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
     if (ax_zero(e, w.flags, sizeof(int32_t) * 8)) return AXCTD_ERR_CUDA;
     AX_LAUNCH(e, k_init, n, w);
 #ifndef AXCTD_EMU
-    ax_launch_stats(w, e->stream); e->launches++;
+    {   // one pass over the PCM: statistics and the tone block sums, one launch per rate class in use
+        for (size_t ci = 0; ci < e->cfgs.size(); ++ci) {
+            if (!std::any_of(b->drops.begin(), b->drops.end(), [&](const AxDrop& d) { return d.cfg == (int)ci; })) continue;
+            k_stats_tones<<<dim3((unsigned)((w.ntb_max + AX_ST_THREADS - 1) / AX_ST_THREADS), (unsigned)n), AX_ST_THREADS, 0, e->stream>>>(w, e->tone_tabs[ci], (int)ci);
+            e->launches++;
+        }
+        if (w.nslab_total > 0) { k_stats_wrap<<<w.nslab_total, 256, 0, e->stream>>>(w); e->launches++; }
+    }
 #else
     AX_LAUNCH(e, k_stats, (int64_t)w.nslab_total, w);
+    AX_LAUNCH(e, k_toneblock, b->tb_total, w);
 #endif
     AX_LAUNCH(e, k_stats_fin, n, w);
     AX_EVENT(b, 1);

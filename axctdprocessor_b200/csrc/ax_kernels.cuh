@@ -1,64 +1,162 @@
 // ax_kernels.cuh -- CUDA-only cooperative kernels (sm_100a).
 //
-//   k_stats_coalesced   int16 sum / max|x| with 128-bit loads (AXCTDprocessor.py:55-56)
-//   k_tone_blocks       400 / 7500 / dead-frequency single-bin DFTs by gcd(N_power, d_pcm)
-//                       blocks with the cos/sin table staged in shared memory
-//                       (AXCTDprocessor.py:358-364)
-//   k_tone_combine      5 rotated block sums -> one 0.1 s window magnitude
+//   k_stats_tones     one PCM pass: sum / min / max of the int16 samples (AXCTDprocessor.py:55-56) and the
+//                     400 / 7500 / dead-frequency DFT sums of every aligned 256-sample block (:358-364)
+//   k_tone_windows    0.1 s window magnitudes from the block sums and the ragged ends
+//   k_demod_fused     SOS cascade, zero crossings, mark / space windows (demodulate.py:74-102)
+//   k_compact_warp / k_nx_grid / k_canon_block   dense crossing arrays, walk steps, canonical walk tables
+//   k_emit_chunk / k_bits_chunk                  bit edges and bit decisions, one CTA per run() iteration
 #pragma once
 #include <cuda_runtime.h>
 #include "ax_proto.h"
 
-// ------------------------------------------------------------------ stats
-__global__ void __launch_bounds__(256) k_stats_coalesced(AxWave w) {
+__device__ __forceinline__ void ax_cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void ax_cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void ax_cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// ------------------------------------------------------------------ stats (exact |x| semantics, fallback)
+// np.max(np.abs(int16)) wraps abs(-32768) to -32768 (AXCTDprocessor.py:56).  k_stats_tones tracks min and max,
+// which decide max|x| unless a sample equals -32768; only then this kernel rescans the drop.
+__global__ void __launch_bounds__(256) k_stats_wrap(AxWave w) {
     const int64_t slab = blockIdx.x;
     const int d = w.slab_drop[slab];
+    if (w.st[d].vmin != -32768) return;
     const AxDrop& dr = w.drop[d];
     const int64_t j = slab - dr.slab_base;
     const int64_t a = j * AX_STAT_SLAB;
     int64_t b = a + AX_STAT_SLAB;
     if (b > dr.n) b = dr.n;
-    const int16_t* x = w.pcm + dr.pcm_off + a;          // 128-byte aligned
-    const int cnt = (int)(b - a);
-    const int nvec = cnt >> 3;
-    long long sum = 0;
+    const int16_t* x = w.pcm + dr.pcm_off + a;
     int mx = -32768;
-    const uint4* xv = reinterpret_cast<const uint4*>(x);
-    for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
-        const uint4 q = __ldg(xv + v);
-        const unsigned wds[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            const int lo = (short)(wds[t] & 0xFFFFu), hi = (short)(wds[t] >> 16);
-            sum += lo + hi;
-            const int alo = (lo == -32768) ? -32768 : abs(lo), ahi = (hi == -32768) ? -32768 : abs(hi);
-            mx = max(mx, max(alo, ahi));
-        }
-    }
-    for (int t = (nvec << 3) + threadIdx.x; t < cnt; t += blockDim.x) {
+    for (int t = threadIdx.x; t < (int)(b - a); t += blockDim.x) {
         const int v = x[t];
-        sum += v;
         mx = max(mx, (v == -32768) ? -32768 : abs(v));
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(&w.st[d].ampl, mx);
+}
+
+// ------------------------------------------------------------------ stats + tone block sums (one PCM pass)
+// Sum, min and max of the int16 samples (AXCTDprocessor.py:55-56) and, for every aligned block of AX_TB
+// samples, the raw 400 / 7500 / dead-frequency DFT sums (ax_toneblock_item; AXCTDprocessor.py:358-364).
+// One lane per tone block; the samples are staged as in k_demod_fused (16-byte cp.async, one 128-byte
+// line per lane per stage) and the phasors are constant-bank operands of the DFMAs.
+#define AX_ST_THREADS 128
+__global__ void __launch_bounds__(AX_ST_THREADS) k_stats_tones(const __grid_constant__ AxWave w, const __grid_constant__ AxToneTab tab, int cfg_id) {
+    __shared__ __align__(16) int16_t stage_all[AX_ST_THREADS / 32][2][32 * 72];
+    const int d = blockIdx.y;
+    const AxDrop& dr = w.drop[d];
+    if (dr.cfg != cfg_id) return;
+    const int64_t nblk = (dr.n + AX_TB - 1) / AX_TB;
+    if ((int64_t)blockIdx.x * AX_ST_THREADS >= nblk) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int16_t (*stage)[32 * 72] = stage_all[warp];
+    const int64_t jb = (int64_t)blockIdx.x * AX_ST_THREADS + threadIdx.x;
+    const bool active = jb < nblk;
+    const int64_t n0 = jb * AX_TB;
+    const int T = active ? (int)min((int64_t)4, (dr.n - n0 + 63) >> 6) : 0;
+    const unsigned long long xrow = (unsigned long long)(w.pcm + dr.pcm_off + n0);
+    const int prow = lane >> 3, piece = lane & 7;
+    unsigned long long src[8];
+    int Tr[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        src[i] = __shfl_sync(0xffffffffu, xrow, i * 4 + prow) + (unsigned long long)piece * 16;
+        Tr[i] = __shfl_sync(0xffffffffu, T, i * 4 + prow);
+    }
+    auto issue = [&](int t, int s) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (t < Tr[i]) ax_cp_async16(&stage[s][(i * 4 + prow) * 72 + piece * 8], reinterpret_cast<const void*>(src[i] + (unsigned long long)t * 128));
+        ax_cp_async_commit();
+    };
+    double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    long long sum = 0;
+    int mx2 = (int)0x80008000, mn2 = 0x7fff7fff;        // packed int16 max / min
+    issue(0, 0);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        if (r + 1 < 4) { issue(r + 1, (r + 1) & 1); ax_cp_async_wait<1>(); } else ax_cp_async_wait<0>();
+        __syncwarp();
+        if (r < T) {
+            const int4* rp = reinterpret_cast<const int4*>(&stage[r & 1][lane * 72]);
+            const int nvalid = (int)min((int64_t)64, dr.n - (n0 + 64 * r));
+            if (nvalid == 64) {
+                int s32 = 0;
+#pragma unroll
+                for (int v = 0; v < 8; ++v) {
+                    const int4 q = rp[v];
+                    const int wd[4] = {q.x, q.y, q.z, q.w};
+                    mx2 = (int)__vimax3_s16x2((unsigned)mx2, (unsigned)wd[0], (unsigned)wd[1]);
+                    mx2 = (int)__vimax3_s16x2((unsigned)mx2, (unsigned)wd[2], (unsigned)wd[3]);
+                    mn2 = (int)__vimin3_s16x2((unsigned)mn2, (unsigned)wd[0], (unsigned)wd[1]);
+                    mn2 = (int)__vimin3_s16x2((unsigned)mn2, (unsigned)wd[2], (unsigned)wd[3]);
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) {
+                        s32 = __dp2a_lo(wd[h], 0x0101, s32);
+                        const double x0 = (double)(int)(short)(wd[h] & 0xFFFF), x1 = (double)(wd[h] >> 16);
+                        const int m = 64 * r + v * 8 + h * 2;
+#pragma unroll
+                        for (int q6 = 0; q6 < 6; ++q6) acc[q6] = fma(x0, tab.t[m][q6], acc[q6]);
+#pragma unroll
+                        for (int q6 = 0; q6 < 6; ++q6) acc[q6] = fma(x1, tab.t[m + 1][q6], acc[q6]);
+                    }
+                }
+                sum += s32;
+            } else {                                   // ragged end of the recording: statistics only
+                const int16_t* xs = &stage[r & 1][lane * 72];
+                for (int i = 0; i < nvalid; ++i) {
+                    const int v = xs[i];
+                    sum += v;
+                    const int pk = (v & 0xFFFF) | (v << 16);
+                    mx2 = (int)__vimax3_s16x2((unsigned)mx2, (unsigned)pk, (unsigned)pk);
+                    mn2 = (int)__vimin3_s16x2((unsigned)mn2, (unsigned)pk, (unsigned)pk);
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (active && jb < dr.ntb) {
+        double* out = w.tb_sum + (dr.tb_base + jb) * 6;
+#pragma unroll
+        for (int q6 = 0; q6 < 6; ++q6) out[q6] = acc[q6];
+    }
+    int mx = max((int)(short)(mx2 & 0xFFFF), mx2 >> 16), mn = min((int)(short)(mn2 & 0xFFFF), mn2 >> 16);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         sum += __shfl_xor_sync(0xffffffffu, sum, o);
         mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
     }
-    __shared__ long long ssum[8];
-    __shared__ int smx[8];
-    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane == 0) { ssum[wid] = sum; smx[wid] = mx; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int q = 1; q < 8; ++q) { sum += ssum[q]; mx = max(mx, smx[q]); }
+    if (lane == 0) {
         atomicAdd((unsigned long long*)&w.st[d].sum, (unsigned long long)sum);
-        atomicMax(&w.st[d].ampl, mx);
+        atomicMax(&w.st[d].vmax, mx);
+        atomicMin(&w.st[d].vmin, mn);
     }
 }
 
-static inline void ax_launch_stats(const AxWave& w, cudaStream_t stream) {
-    if (w.nslab_total > 0) k_stats_coalesced<<<w.nslab_total, 256, 0, stream>>>(w);
+// One warp per power sample: ragged ends + block sums (ax_tonewin_partial), then the magnitudes.
+__global__ void __launch_bounds__(256) k_tone_windows(AxWave w, int phase_b) {
+    const int64_t slot = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (slot >= w.pw_total) return;
+    const int lane = threadIdx.x & 31;
+    int d;
+    if (!ax_tone_slot_active(w, slot, phase_b, &d)) return;
+    const AxDrop& dr = w.drop[d];
+    const AxCfg& c = w.cfg[dr.cfg];
+    if (!ax_tone_blocked_ok(c)) return;
+    double a[6];
+    ax_tonewin_partial(w, dr, c, w.pw_ind[slot], lane, 32, a);
+#pragma unroll
+    for (int q = 0; q < 6; ++q)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a[q] += __shfl_xor_sync(0xffffffffu, a[q], o);
+    if (lane == 0) ax_tonewin_finish(w, c, w.st[d], slot, a);
 }
 
 // ------------------------------------------------------------------ fused demodulation pass
@@ -91,13 +189,6 @@ struct AxFdSmem {
     int32_t row_begin[32], row_stop[32];
 };
 
-__device__ __forceinline__ void ax_cp_async16(void* smem_dst, const void* gsrc) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc));
-}
-__device__ __forceinline__ void ax_cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void ax_cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
 template <int NSEC, int NPCM>
 __global__ void __launch_bounds__(AX_FD_THREADS, 2) k_demod_fused(const __grid_constant__ AxWave w, const __grid_constant__ AxWinTab tab, int cfg_id) {
@@ -471,128 +562,5 @@ __global__ void __launch_bounds__(AX_CANON_THREADS) k_canon_block(AxWave w) {
     __syncthreads();
     const int base = s_cnt[tid + 1];
     for (int t = ta; t < tb; ++t) crank[t] += base;
-}
-
-// ------------------------------------------------------------------ tones
-#define AX_TONE_WARPS 8
-#define AX_TONE_R 4          // blocks per warp pass (register blocking against the smem table)
-
-__device__ __forceinline__ bool ax_tone_chunk_active(const AxWave& w, const AxState& st, int k, int phase_b) {
-    int klo, khi;
-    return ax_level_range(w, st, phase_b, &klo, &khi) && k >= klo && k < khi;
-}
-
-__global__ void __launch_bounds__(AX_TONE_WARPS * 32)
-k_tone_blocks(AxWave w, int cfg_id, int phase_b, int qpc, int chunk_total) {
-    extern __shared__ double tab[];                      // [6][G]
-    const AxCfg& c = w.cfg[cfg_id];
-    const int G = c.tone_G;
-    for (int i = threadIdx.x; i < 6 * G; i += blockDim.x) {
-        const int q = i / G, m = i - q * G;
-        tab[i] = c.tone_cs[6 * (int64_t)m + q];
-    }
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int64_t gw = (int64_t)blockIdx.x * AX_TONE_WARPS + (threadIdx.x >> 5);
-    const int64_t nw = (int64_t)gridDim.x * AX_TONE_WARPS;
-    const int64_t total = (int64_t)chunk_total * qpc;
-    for (int64_t item = gw; item < total; item += nw) {
-        const int64_t cg = item / qpc;
-        const int quad = (int)(item - cg * qpc);
-        const int d = ax_find_owner(w.drop, w.n_drops, &AxDrop::chunk_base, cg);
-        const AxDrop& dr = w.drop[d];
-        if (dr.cfg != cfg_id) continue;
-        const AxState& st = w.st[d];
-        const int k = (int)(cg - dr.chunk_base);
-        if (k >= dr.chunk_cap || st.status >= AXCTD_DROP_CAPACITY || !ax_tone_chunk_active(w, st, k, phase_b)) continue;
-        const AxChunk& ch = w.chunk[cg];
-        if (ch.np <= 0) continue;
-        const int B = (ch.np - 1) * c.tone_stride + c.tone_nb;
-        const int b0 = quad * AX_TONE_R;
-        if (b0 >= B) continue;
-        const int16_t* x = w.pcm + dr.pcm_off + ch.s + (int64_t)b0 * G;
-        const double kmul = st.inv_ampl, kadd = -(st.dc * st.inv_ampl);
-        double acc[AX_TONE_R][6];
-#pragma unroll
-        for (int r = 0; r < AX_TONE_R; ++r)
-#pragma unroll
-            for (int q = 0; q < 6; ++q) acc[r][q] = 0.0;
-        const int nblk = min(AX_TONE_R, B - b0);
-        for (int m = lane; m < G; m += 32) {
-            double t[6];
-#pragma unroll
-            for (int q = 0; q < 6; ++q) t[q] = tab[q * G + m];
-#pragma unroll
-            for (int r = 0; r < AX_TONE_R; ++r) {
-                if (r < nblk) {
-                    const double u = fma((double)x[(int64_t)r * G + m], kmul, kadd);
-#pragma unroll
-                    for (int q = 0; q < 6; ++q) acc[r][q] = fma(u, t[q], acc[r][q]);
-                }
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < AX_TONE_R; ++r)
-#pragma unroll
-            for (int q = 0; q < 6; ++q) {
-                double v = acc[r][q];
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                acc[r][q] = v;
-            }
-        if (lane == 0) {
-            double* out = w.blk + ((int64_t)cg * w.blk_stride + b0) * 6;
-            for (int r = 0; r < nblk; ++r)
-                for (int q = 0; q < 6; ++q) out[r * 6 + q] = acc[r][q];
-        }
-    }
-}
-
-__global__ void k_tone_combine(AxWave w, int cfg_id, int phase_b) {
-    const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot >= w.pw_total) return;
-    const int d = ax_find_owner(w.drop, w.n_drops, &AxDrop::pw_base, slot);
-    const AxDrop& dr = w.drop[d];
-    if (dr.cfg != cfg_id) return;
-    const AxState& st = w.st[d];
-    if (st.status >= AXCTD_DROP_CAPACITY) return;
-    const AxCfg& c = w.cfg[cfg_id];
-    const int32_t i = (int32_t)(slot - dr.pw_base);
-    const AxChunk* ch = w.chunk + dr.chunk_base;
-    int klo, khi;                                         // active chunk range [klo, khi)
-    if (!ax_level_range(w, st, phase_b, &klo, &khi)) return;
-    if (i < ch[klo].pw_off || i >= ch[khi - 1].pw_off + ch[khi - 1].np) return;
-    int lo = klo, hi = khi - 1;                           // last chunk with pw_off <= i
-    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (ch[mid].pw_off <= i) lo = mid; else hi = mid - 1; }
-    const int k = lo;
-    const int jw = i - ch[k].pw_off;
-    if (jw >= ch[k].np) return;
-    const double* S = w.blk + ((int64_t)(dr.chunk_base + k) * w.blk_stride + (int64_t)jw * c.tone_stride) * 6;
-    double re[3] = {0, 0, 0}, im[3] = {0, 0, 0};
-    for (int q = 0; q < c.tone_nb; ++q) {
-        const double* rot = c.tone_cs + 6 * (int64_t)q * c.tone_G;     // e^{j theta_f G q}
-#pragma unroll
-        for (int f = 0; f < 3; ++f) {
-            const double sr = S[q * 6 + 2 * f], si = S[q * 6 + 2 * f + 1];
-            const double cr = rot[2 * f], sn = rot[2 * f + 1];
-            re[f] += sr * cr - si * sn;
-            im[f] += sr * sn + si * cr;
-        }
-    }
-#pragma unroll
-    for (int f = 0; f < 3; ++f) w.pw_raw[f * (int64_t)w.pw_total + slot] = hypot(re[f], im[f]);
-}
-
-static inline void ax_launch_tone_blocked(const AxWave& w, int cfg_id, const AxCfg& c, int phase_b, int chunk_total,
-                                          cudaStream_t stream) {
-    const int qpc = (w.blk_stride + AX_TONE_R - 1) / AX_TONE_R;
-    const int64_t total = (int64_t)chunk_total * qpc;
-    if (total <= 0 || w.pw_total <= 0) return;
-    const size_t smem = (size_t)6 * c.tone_G * sizeof(double);
-    static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(k_tone_blocks, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
-    int grid = (int)std::min<int64_t>((total + AX_TONE_WARPS - 1) / AX_TONE_WARPS, 148 * 4);
-    k_tone_blocks<<<grid, AX_TONE_WARPS * 32, smem, stream>>>(w, cfg_id, phase_b, qpc, chunk_total);
-    k_tone_combine<<<(w.pw_total + 127) / 128, 128, 0, stream>>>(w, cfg_id, phase_b);
 }
 

@@ -78,29 +78,39 @@ AX_HDN inline void ax_plan_tones_item(const AxWave& w, int64_t d) {
     }
 }
 
-// One power sample, straightforward evaluation (generic path; the CUDA build
-// uses the blocked kernel in ax_engine.cu whenever gcd(N_power, d_pcm) allows).
-AX_HDN inline void ax_tone_direct_item(const AxWave& w, int64_t slot, int phase_flags) {
-    const int phase_b = phase_flags & 1;
+// Is power sample `slot` part of the current tone launch?  (phase 0: detection round on the fixed grid,
+// phase 1: the demodulated chunks after the first)
+AX_HD bool ax_tone_slot_active(const AxWave& w, int64_t slot, int phase_b, int* d_out) {
     const int d = ax_find_owner(w.drop, w.n_drops, &AxDrop::pw_base, slot);
     const AxDrop& dr = w.drop[d];
     const AxState& st = w.st[d];
-    const AxCfg& c = w.cfg[dr.cfg];
-    if ((phase_flags & 2) && ax_tone_blocked_ok(c)) return;      // already done by the blocked kernel
-    if (st.status >= AXCTD_DROP_CAPACITY) return;
+    *d_out = d;
+    if (st.status >= AXCTD_DROP_CAPACITY) return false;
     const int32_t i = (int32_t)(slot - dr.pw_base);
     const AxChunk* ch = w.chunk + dr.chunk_base;
     int32_t lo, hi;
     if (!phase_b) {
         const int ka = w.pa_lo, kb = w.pa_hi < st.n_fixed ? w.pa_hi : st.n_fixed;
-        if (!st.searching || kb <= ka) return;
+        if (!st.searching || kb <= ka) return false;
         lo = ch[ka].pw_off; hi = ch[kb - 1].pw_off + ch[kb - 1].np;
     }
     else {
-        if (st.sm_status < 1 || st.n_chunks <= st.k0 + 1) return;
+        if (st.sm_status < 1 || st.n_chunks <= st.k0 + 1) return false;
         lo = ch[st.k0].pw_off + ch[st.k0].np; hi = ch[st.n_chunks - 1].pw_off + ch[st.n_chunks - 1].np;
     }
-    if (i < lo || i >= hi) return;
+    return i >= lo && i < hi;
+}
+
+// One power sample, straightforward evaluation of AXCTDprocessor.py:358-364 (option "tone_direct";
+// the production path is ax_toneblock_item + ax_tonewin_item, which reads the PCM once).
+AX_HDN inline void ax_tone_direct_item(const AxWave& w, int64_t slot, int phase_flags) {
+    const int phase_b = phase_flags & 1;
+    int d;
+    if (!ax_tone_slot_active(w, slot, phase_b, &d)) return;
+    const AxDrop& dr = w.drop[d];
+    const AxState& st = w.st[d];
+    const AxCfg& c = w.cfg[dr.cfg];
+    if ((phase_flags & 2) && ax_tone_blocked_ok(c)) return;      // already done by the blocked path
     const int16_t* x = w.pcm + dr.pcm_off + w.pw_ind[slot];
     const double kmul = st.inv_ampl, kadd = -(st.dc * st.inv_ampl);
     double a[6] = {0, 0, 0, 0, 0, 0};
@@ -112,6 +122,74 @@ AX_HDN inline void ax_tone_direct_item(const AxWave& w, int64_t slot, int phase_
     w.pw_raw[0 * (int64_t)w.pw_total + slot] = hypot(a[0], a[1]);
     w.pw_raw[1 * (int64_t)w.pw_total + slot] = hypot(a[2], a[3]);
     w.pw_raw[2 * (int64_t)w.pw_total + slot] = hypot(a[4], a[5]);
+}
+
+// ---- tone powers from aligned block sums --------------------------------------------------------
+// |sum_m u[c+m] e^{j theta m}| does not depend on the phase reference, so the window [c, c+N) is split at
+// the AX_TB-aligned block boundaries: B_f[j] = sum_{m<AX_TB} x[AX_TB*j+m] e^{j theta_f m} is computed once
+// per block of raw samples in the same pass that takes the mean and max|x| (no chunk start is known
+// yet), and a window is  sum_j e^{j theta_f (AX_TB*j - c)} B_f[j]  plus its two ragged ends, normalised
+// afterwards: sum_m (x-dc)/ampl e^{j theta m} = (S_x - dc * T_f) / ampl with T_f = sum_m e^{j theta_f m}.
+AX_HDN inline void ax_toneblock_item(const AxWave& w, int64_t tbg) {
+    const int d = ax_find_owner(w.drop, w.n_drops, &AxDrop::tb_base, tbg);
+    const AxDrop& dr = w.drop[d];
+    const int64_t j = tbg - dr.tb_base;
+    if (j >= dr.ntb) return;
+    const AxCfg& c = w.cfg[dr.cfg];
+    const int16_t* x = w.pcm + dr.pcm_off + j * AX_TB;
+    double a[6] = {0, 0, 0, 0, 0, 0};
+    for (int m = 0; m < AX_TB; ++m) {
+        const double xd = (double)x[m];
+        const double* t6 = c.tone_cs + 6 * (int64_t)m;
+        for (int q = 0; q < 6; ++q) a[q] = ax_fma(xd, t6[q], a[q]);
+    }
+    for (int q = 0; q < 6; ++q) w.tb_sum[tbg * 6 + q] = a[q];
+}
+
+// partial sums of one window over the terms i = lane, lane+nl, ... (ragged-end samples first, then blocks)
+AX_HD void ax_tonewin_partial(const AxWave& w, const AxDrop& dr, const AxCfg& c, int64_t cstart, int lane, int nl, double* a) {
+    const int16_t* x = w.pcm + dr.pcm_off;
+    const int64_t cend = cstart + c.n_power;
+    int64_t j0 = (cstart + AX_TB - 1) / AX_TB, j1 = cend / AX_TB;       // full blocks j0 .. j1-1
+    if (j1 > dr.ntb) j1 = dr.ntb;
+    if (j1 < j0) j1 = j0;
+    const int64_t head_n = j0 * AX_TB - cstart;                          // samples before the first full block
+    const int64_t tail0 = j1 * AX_TB;                                    // first sample after the last full block
+    const int64_t tail_n = cend - tail0;
+    for (int q = 0; q < 6; ++q) a[q] = 0.0;
+    for (int64_t i = lane; i < head_n + tail_n; i += nl) {
+        const int64_t n = i < head_n ? cstart + i : tail0 + (i - head_n);
+        const double xd = (double)x[n];
+        const double* t6 = c.tone_cs + 6 * (n - cstart);
+        for (int q = 0; q < 6; ++q) a[q] = ax_fma(xd, t6[q], a[q]);
+    }
+    for (int64_t j = j0 + lane; j < j1; j += nl) {
+        const double* B = w.tb_sum + (dr.tb_base + j) * 6;
+        const double* r = c.tone_cs + 6 * (j * AX_TB - cstart);         // e^{j theta_f (AX_TB*j - c)}
+        for (int f = 0; f < 3; ++f) {
+            const double br = B[2 * f], bi = B[2 * f + 1], cr = r[2 * f], sn = r[2 * f + 1];
+            a[2 * f] = ax_fma(br, cr, ax_fma(-bi, sn, a[2 * f]));
+            a[2 * f + 1] = ax_fma(br, sn, ax_fma(bi, cr, a[2 * f + 1]));
+        }
+    }
+}
+AX_HD void ax_tonewin_finish(const AxWave& w, const AxCfg& c, const AxState& st, int64_t slot, const double* a) {
+    for (int f = 0; f < 3; ++f) {
+        const double re = (a[2 * f] - st.dc * c.tone_tsum[2 * f]) * st.inv_ampl;
+        const double im = (a[2 * f + 1] - st.dc * c.tone_tsum[2 * f + 1]) * st.inv_ampl;
+        w.pw_raw[f * (int64_t)w.pw_total + slot] = hypot(re, im);
+    }
+}
+// generic one-thread form (the CUDA build sums a window with a warp: k_tone_windows)
+AX_HDN inline void ax_tonewin_item(const AxWave& w, int64_t slot, int phase_b) {
+    int d;
+    if (!ax_tone_slot_active(w, slot, phase_b, &d)) return;
+    const AxDrop& dr = w.drop[d];
+    const AxCfg& c = w.cfg[dr.cfg];
+    if (!ax_tone_blocked_ok(c)) return;
+    double a[6];
+    ax_tonewin_partial(w, dr, c, w.pw_ind[slot], 0, 1, a);
+    ax_tonewin_finish(w, c, w.st[d], slot, a);
 }
 
 // numpy's pairwise summation for a contiguous float64 vector of n <= 128

@@ -55,6 +55,7 @@ AX_HD double ax_nan() { return nan(""); }
 #define AX_MAXSEC AXCTD_MAX_SECTIONS
 #define AX_PEND 8           // pending bit-windows per thread in the filter pass
 #define AX_STAT_SLAB 16384  // samples per stats work item
+#define AX_TB 256           // samples per tone block (ax_toneblock_item)
 
 // fp32 phasor table of the bit windows (ax_window32): cos, sin of theta_mark * k and theta_space * k
 #define AX_WIN_TAPS 48
@@ -88,6 +89,7 @@ struct AxCfg {
     const double* gcum;          // [g_len][4] running sums of gtab (response to the constant -dc/ampl term)
     int32_t g_len, pad_g;
     int32_t lut_len, n_hist_edges;
+    double tone_tsum[6];         // sum over the whole window of tone_cs (response to the constant -dc/ampl term)
     AxWinTab win_tab;
 };
 
@@ -96,6 +98,7 @@ struct AxDrop {
     int32_t cfg;
     int32_t seg_base, nseg;      // segments of the continuous filter pass
     int32_t slab_base, nslab;    // stats work items
+    int64_t tb_base; int32_t ntb, pad_tb;   // tone blocks: floor(n / AX_TB) full blocks
     int64_t zc_base, zc_cap;     // dense crossing arrays
     int32_t tile_base, tile_cap;
     int32_t chunk_base, chunk_cap;
@@ -133,6 +136,7 @@ struct AxChunk {
 struct AxState {
     int32_t status, status_chunk;
     int64_t sum;
+    int32_t vmax, vmin;          // max / min sample (k_stats_tones); vmin stays INT_MAX on the generic path
     int32_t ampl;
     int32_t n_uncertain;
     int32_t n_recheck;           // bit windows re-evaluated in double precision (ax_gwin_*)
@@ -197,8 +201,8 @@ struct AxWave {
     double* r400; double* r7500; // [pw_total]
     int64_t* pw_ind;             // [pw_total] power_inds
     int32_t pw_total;
-    double* blk;                 // tone block sums scratch [chunk][blk_stride][6]
-    int32_t blk_stride, pad1;
+    double* tb_sum;              // [tb_total][6] raw-sample tone sums of every aligned block of AX_TB samples
+    int32_t ntb_max, pad1;
     // bits / edges
     int32_t* edge_idx; double* lvl400; double* lvl7500;     // per edge
     uint8_t* bit; double* a1; double* a2; double* conf;     // per bit
@@ -216,7 +220,9 @@ struct AxWave {
     int32_t* flags;              // [0] = any chain dirty, [1] = any capacity error
 };
 
-AX_HD bool ax_tone_blocked_ok(const AxCfg& c) { return c.tone_G >= 32 && c.tone_nb <= 16 && (int64_t)c.tone_G * 48 <= 160 * 1024; }
+// cos, sin of theta400, theta7500, thetadead for the AX_TB taps of a tone block (kernel parameter of k_stats_tones)
+struct AxToneTab { double t[AX_TB][6]; };
+AX_HD bool ax_tone_blocked_ok(const AxCfg& c) { return c.n_power >= 2 * AX_TB; }
 
 #define AX_FLAG_DIRTY 0
 #define AX_FLAG_CAP 1
