@@ -268,7 +268,7 @@ class AXCTD_Processor:
                 self.ccoeff = self.metadata["ccoeff"]
             if sum(self.metadata["tcoeff_valid"]) == 4:     # (sic) AXCTDprocessor.py:534
                 self.zcoeff = self.metadata["zcoeff"]
-        fr = res.frames
+        fr = res.table()
         kept = fr[fr["keep"] == 1]
         self.time = list(kept["time_s"])
         self.r400_prof = list(kept["r400"])

@@ -76,6 +76,17 @@ class Chunk(C.Structure):
     ]
 
 
+class Row(C.Structure):
+    _fields_ = [
+        ("word", C.c_uint32), ("flags", C.c_int32),
+        ("time_c", C.c_int32), ("depth_c", C.c_int32), ("temperature_c", C.c_int32), ("conductivity_c", C.c_int32),
+        ("salinity_c", C.c_int32), ("r400_c", C.c_int32), ("r7500_c", C.c_int32),
+    ]
+
+
+ROW_KEEP, ROW_HEX, ROW_WIDE, ROW_NAN = 1, 2, 4, -2147483648
+
+
 class SynthDesc(C.Structure):
     _fields_ = [
         ("n_total", C.c_int64), ("n0", C.c_int64), ("tone_start", C.c_int64), ("fs", C.c_int64),
@@ -91,7 +102,7 @@ SYMBOLS = [
     "axctd_engine_set_option", "axctd_engine_set_stream", "axctd_engine_launch_count", "axctd_config_create", "axctd_batch_create",
     "axctd_batch_destroy", "axctd_batch_upload", "axctd_batch_device_pcm", "axctd_batch_run",
     "axctd_batch_run_async", "axctd_batch_finish", "axctd_batch_timing", "axctd_batch_summary",
-    "axctd_batch_frames", "axctd_batch_chunks", "axctd_batch_bits", "axctd_batch_edges", "axctd_batch_power",
+    "axctd_batch_rows", "axctd_batch_frames", "axctd_batch_chunks", "axctd_batch_bits", "axctd_batch_edges", "axctd_batch_power",
     "axctd_synth_fill", "axctd_batch_download",
 ]
 
@@ -120,6 +131,7 @@ def bind(lib: C.CDLL) -> C.CDLL:
         "axctd_batch_finish": (i32, [vp]),
         "axctd_batch_timing": (i32, [vp, P(dbl), P(dbl), P(dbl)]),
         "axctd_batch_summary": (i32, [vp, i32, P(DropSummary)]),
+        "axctd_batch_rows": (i64, [vp, i32, vp, i64]),
         "axctd_batch_frames": (i64, [vp, i32, vp, i64]),
         "axctd_batch_chunks": (i64, [vp, i32, vp, i64]),
         "axctd_batch_bits": (i64, [vp, i32, vp, vp, i64]),
@@ -132,7 +144,7 @@ def bind(lib: C.CDLL) -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    for which, st in enumerate((ConfigDesc, DropSummary, Frame, Chunk)):
+    for which, st in enumerate((ConfigDesc, DropSummary, Frame, Chunk, Row)):
         if lib.axctd_struct_size(which) != C.sizeof(st):
             raise ImportError(f"ABI struct size mismatch for {st.__name__}: "
                               f"{lib.axctd_struct_size(which)} != {C.sizeof(st)}")

@@ -98,6 +98,8 @@ AX_GLOBAL void k_frames_write(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_frames_wr
 AX_GLOBAL void k_calib(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_calib_item(w, item); }
 AX_GLOBAL void k_synth(int64_t n, AxSynth g) { AX_FOR_ITEM(n) ax_synth_item(g, item); }
 AX_GLOBAL void k_qc(int64_t n, AxWave w, double* scratch) { AX_FOR_ITEM(n) ax_qc_item(w, item, scratch); }
+AX_GLOBAL void k_rows(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_row_item(w, item); }
+AX_GLOBAL void k_chunkout(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_chunkout_item(w, item); }
 
 // ============================================================ memory helpers
 struct axctd_engine {
@@ -147,6 +149,14 @@ static int ax_zero(axctd_engine* e, void* d, size_t b) { return ax_fail(e, cudaM
 static int ax_sync(axctd_engine* e) { return ax_fail(e, cudaStreamSynchronize(e->stream), "sync"); }
 #endif
 
+#ifdef AXCTD_EMU
+static void* ax_host_alloc(size_t bytes) { return calloc(bytes ? bytes : 1, 1); }
+static void ax_host_free(void* p) { free(p); }
+#else
+static void* ax_host_alloc(size_t bytes) { void* p = nullptr; return cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) == cudaSuccess ? p : nullptr; }
+static void ax_host_free(void* p) { if (p) cudaFreeHost(p); }
+#endif
+
 struct axctd_batch {
     axctd_engine* eng = nullptr;
     int n = 0;
@@ -157,10 +167,11 @@ struct axctd_batch {
     double* d_qc = nullptr;
     int64_t tb_total = 0;
     int64_t pcm_total = 0, chunk_total = 0, edge_total = 0, frame_total = 0, zc_total = 0, tile_total = 0;
-    // host mirrors of the results
+    // host mirrors of the results (pinned: the result download is part of every step)
     std::vector<AxState> st;
-    std::vector<AxChunk> chunk;
-    std::vector<axctd_frame> frame;
+    AxState* h_st = nullptr;
+    axctd_row* h_row = nullptr;           // [frame_total], a drop's rows at frame_base
+    axctd_chunk* h_chunk = nullptr;       // [chunk_total]
     std::vector<axctd_drop_summary> summary;
     bool ran = false, finished = false;
     double ms_total = 0, ms_filter = 0, ms_tone = 0;
@@ -194,6 +205,7 @@ extern "C" int axctd_struct_size(int which) {
         case 1: return (int)sizeof(axctd_drop_summary);
         case 2: return (int)sizeof(axctd_frame);
         case 3: return (int)sizeof(axctd_chunk);
+        case 4: return (int)sizeof(axctd_row);
     }
     return -1;
 }
@@ -388,6 +400,7 @@ extern "C" void axctd_batch_destroy(axctd_batch* b) {
     for (int i = 0; i < 6; ++i) cudaEventDestroy(b->ev[i]);
 #endif
     for (void* p : b->allocs) ax_free(p);
+    ax_host_free(b->h_st); ax_host_free(b->h_row); ax_host_free(b->h_chunk);
     delete b;
 }
 
@@ -501,6 +514,12 @@ extern "C" int axctd_batch_create(axctd_engine* e, int n_drops, const int64_t* n
     bad |= ax_alloc_arr(b, &w.bitw, edge_off / 32 + 4);
     bad |= ax_alloc_arr(b, &w.validw, edge_off / 32 + 4);
     bad |= ax_alloc_arr(b, &w.frame, frame_off);
+    bad |= ax_alloc_arr(b, &w.row, frame_off);
+    bad |= ax_alloc_arr(b, &w.chunk_out, chunk_off);
+    b->h_st = (AxState*)ax_host_alloc(sizeof(AxState) * (size_t)n_drops);
+    b->h_row = (axctd_row*)ax_host_alloc(sizeof(axctd_row) * (size_t)frame_off);
+    b->h_chunk = (axctd_chunk*)ax_host_alloc(sizeof(axctd_chunk) * (size_t)chunk_off);
+    if (!b->h_st || !b->h_row || !b->h_chunk) bad = 1;
     bad |= ax_alloc_arr(b, &b->d_qc, 2 * (int64_t)frame_off + 16);
     bad |= ax_alloc_arr(b, &w.flags, 8);
     if (bad) { axctd_batch_destroy(b); return AXCTD_ERR_CUDA; }
@@ -604,7 +623,27 @@ static int ax_run_tones(axctd_batch* b, int phase_b) {
         bool all_blocked = true;
         for (const AxDrop& dr : b->drops) if (!ax_tone_blocked_ok(e->cfgs[dr.cfg])) all_blocked = false;
 #ifndef AXCTD_EMU
-        if (w.pw_total > 0) { k_tone_windows<<<(unsigned)(((int64_t)w.pw_total * 32 + 255) / 256), 256, 0, e->stream>>>(w, phase_b); e->launches++; }
+        {   // per-drop power-sample range this launch can touch: detection rounds only cover chunks [pa_lo, pa_hi) of the fixed grid
+            int i_lo = 0, i_hi = 0;
+            for (const AxDrop& dr : b->drops) {
+                const AxCfg& c = e->cfgs[dr.cfg];
+                const int per = c.chunk_len / c.d_pcm + 2;
+                i_hi = std::max(i_hi, phase_b ? dr.pw_cap : (int)std::min<int64_t>((int64_t)w.pa_hi * per, dr.pw_cap));
+            }
+            if (!phase_b) {
+                i_lo = 0x7fffffff;
+                for (const AxDrop& dr : b->drops) {
+                    const AxCfg& c = e->cfgs[dr.cfg];
+                    const int span = c.chunk_len - c.n_power;
+                    const int per_min = span > 0 ? span / c.d_pcm : 0;          // a full fixed-grid chunk holds at least this many
+                    i_lo = std::min(i_lo, (int)std::min<int64_t>((int64_t)w.pa_lo * per_min, dr.pw_cap));
+                }
+            }
+            if (i_hi > i_lo) {
+                k_tone_windows<<<dim3((unsigned)(((int64_t)(i_hi - i_lo) * 32 + 255) / 256), (unsigned)b->n), 256, 0, e->stream>>>(w, phase_b, i_lo, i_hi);
+                e->launches++;
+            }
+        }
 #else
         AX_LAUNCH(e, k_tonewin, (int64_t)w.pw_total, w, phase_b);
 #endif
@@ -733,6 +772,8 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
     AX_LAUNCH(e, k_frames_write, b->chunk_total, w);
     AX_LAUNCH(e, k_calib, b->frame_total, w);
     AX_LAUNCH(e, k_qc, b->chunk_total, w, b->d_qc);
+    AX_LAUNCH(e, k_rows, b->frame_total, w);
+    AX_LAUNCH(e, k_chunkout, b->chunk_total, w);
     AX_EVENT(b, 5);
     b->ran = true;
     return AXCTD_OK;
@@ -744,14 +785,14 @@ extern "C" int axctd_batch_finish(axctd_batch* b) {
     axctd_engine* e = b->eng;
     AxWave& w = b->w;
     const int n = b->n;
-    b->chunk.resize(b->chunk_total);
-    if (ax_d2h(e, b->st.data(), w.st, sizeof(AxState) * n) ||
-        ax_d2h(e, b->chunk.data(), w.chunk, sizeof(AxChunk) * b->chunk_total) || ax_sync(e)) return AXCTD_ERR_CUDA;
-    b->frame.resize(b->frame_total);
+    if (ax_d2h(e, b->h_st, w.st, sizeof(AxState) * n) || ax_sync(e)) return AXCTD_ERR_CUDA;
+    memcpy(b->st.data(), b->h_st, sizeof(AxState) * n);
     for (int d = 0; d < n; ++d) {
         const AxDrop& dr = b->drops[d];
-        const int64_t nf = b->st[d].n_frames;
-        if (nf > 0 && ax_d2h(e, b->frame.data() + dr.frame_base, w.frame + dr.frame_base, sizeof(axctd_frame) * nf)) return AXCTD_ERR_CUDA;
+        const int64_t nf = b->st[d].status == 0 ? b->st[d].n_frames : 0;
+        const int64_t nc = std::min<int64_t>(b->st[d].n_chunks, dr.chunk_cap);
+        if (nf > 0 && ax_d2h(e, b->h_row + dr.frame_base, w.row + dr.frame_base, sizeof(axctd_row) * nf)) return AXCTD_ERR_CUDA;
+        if (nc > 0 && ax_d2h(e, b->h_chunk + dr.chunk_base, w.chunk_out + dr.chunk_base, sizeof(axctd_chunk) * nc)) return AXCTD_ERR_CUDA;
     }
     if (ax_sync(e)) return AXCTD_ERR_CUDA;
 #ifndef AXCTD_EMU
@@ -782,7 +823,7 @@ extern "C" int axctd_batch_finish(axctd_batch* b) {
         sm.header_parsed[0] = st.header_parsed[0]; sm.header_parsed[1] = st.header_parsed[1];
         for (int q = 0; q < 4; ++q) { sm.zcoeff_used[q] = st.zc_used[q]; sm.tcoeff_used[q] = st.tc_used[q]; sm.ccoeff_used[q] = st.cc_used[q]; }
         int64_t rows = 0, hex = 0;
-        for (int k = 0; k < st.n_chunks && k < dr.chunk_cap; ++k) { rows += b->chunk[dr.chunk_base + k].n_rows; hex += b->chunk[dr.chunk_base + k].n_hex; }
+        for (int k = 0; k < st.n_chunks && k < dr.chunk_cap; ++k) { rows += b->h_chunk[dr.chunk_base + k].n_rows; hex += b->h_chunk[dr.chunk_base + k].n_hex; }
         sm.n_rows = rows; sm.n_hex = hex;
     }
     b->finished = true;
@@ -809,32 +850,31 @@ extern "C" int axctd_batch_summary(axctd_batch* b, int drop, axctd_drop_summary*
     return AXCTD_OK;
 }
 
+extern "C" int64_t axctd_batch_rows(axctd_batch* b, int drop, axctd_row* out, int64_t cap) {
+    if (!b || !b->finished || drop < 0 || drop >= b->n) return -AXCTD_ERR_ARG;
+    const int64_t nf = b->st[drop].status == 0 ? b->st[drop].n_frames : 0;
+    if (!out) return nf;
+    if (cap < nf) return -AXCTD_ERR_CAPACITY;
+    if (nf) memcpy(out, b->h_row + b->drops[drop].frame_base, sizeof(axctd_row) * nf);
+    return nf;
+}
+
 extern "C" int64_t axctd_batch_frames(axctd_batch* b, int drop, axctd_frame* out, int64_t cap) {
     if (!b || !b->finished || drop < 0 || drop >= b->n) return -AXCTD_ERR_ARG;
     const int64_t nf = b->st[drop].n_frames;
     if (!out) return nf;
     if (cap < nf) return -AXCTD_ERR_CAPACITY;
-    if (nf) memcpy(out, b->frame.data() + b->drops[drop].frame_base, sizeof(axctd_frame) * nf);
+    if (nf && (ax_d2h(b->eng, out, b->w.frame + b->drops[drop].frame_base, sizeof(axctd_frame) * nf) || ax_sync(b->eng))) return -AXCTD_ERR_CUDA;
     return nf;
 }
 
 extern "C" int64_t axctd_batch_chunks(axctd_batch* b, int drop, axctd_chunk* out, int64_t cap) {
     if (!b || !b->finished || drop < 0 || drop >= b->n) return -AXCTD_ERR_ARG;
-    const AxState& st = b->st[drop];
     const AxDrop& dr = b->drops[drop];
-    const int64_t nc = std::min<int64_t>(st.n_chunks, dr.chunk_cap);
+    const int64_t nc = std::min<int64_t>(b->st[drop].n_chunks, dr.chunk_cap);
     if (!out) return nc;
     if (cap < nc) return -AXCTD_ERR_CAPACITY;
-    for (int k = 0; k < nc; ++k) {
-        const AxChunk& c = b->chunk[dr.chunk_base + k];
-        axctd_chunk& o = out[k];
-        o.s = c.s; o.e = c.e; o.status = c.status; o.n_power_total = c.pw_off + c.np;
-        const bool dem = st.k0 >= 0 && k >= st.k0 && c.n_edges > 0;
-        o.n_bits = dem ? c.n_edges - 1 : -1;
-        o.first_edge = dem ? (int32_t)(c.first_edge - c.s) : -1; o.last_edge = dem ? (int32_t)(c.true_last - c.s) : -1;
-        o.n_head_edges = dem ? c.n_head_edges : 0;
-        o.n_rows = c.n_rows; o.n_hex = c.n_hex; o.scale = c.scale;
-    }
+    if (nc) memcpy(out, b->h_chunk + dr.chunk_base, sizeof(axctd_chunk) * nc);
     return nc;
 }
 

@@ -141,22 +141,36 @@ __global__ void __launch_bounds__(AX_ST_THREADS) k_stats_tones(const __grid_cons
 }
 
 // One warp per power sample: ragged ends + block sums (ax_tonewin_partial), then the magnitudes.
-__global__ void __launch_bounds__(256) k_tone_windows(AxWave w, int phase_b) {
-    const int64_t slot = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (slot >= w.pw_total) return;
-    const int lane = threadIdx.x & 31;
-    int d;
-    if (!ax_tone_slot_active(w, slot, phase_b, &d)) return;
+// grid = (warps over the per-drop power-sample range [i_lo, i_hi), drop)
+__global__ void __launch_bounds__(256) k_tone_windows(AxWave w, int phase_b, int i_lo, int i_hi) {
+    const int d = blockIdx.y;
     const AxDrop& dr = w.drop[d];
+    const AxState& st = w.st[d];
+    if (st.status >= AXCTD_DROP_CAPACITY) return;
     const AxCfg& c = w.cfg[dr.cfg];
     if (!ax_tone_blocked_ok(c)) return;
+    const int32_t i = i_lo + (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (i >= i_hi || i >= dr.pw_cap) return;
+    const AxChunk* ch = w.chunk + dr.chunk_base;
+    int32_t lo, hi;
+    if (!phase_b) {
+        const int ka = w.pa_lo, kb = w.pa_hi < st.n_fixed ? w.pa_hi : st.n_fixed;
+        if (!st.searching || kb <= ka) return;
+        lo = ch[ka].pw_off; hi = ch[kb - 1].pw_off + ch[kb - 1].np;
+    } else {
+        if (st.sm_status < 1 || st.n_chunks <= st.k0 + 1) return;
+        lo = ch[st.k0].pw_off + ch[st.k0].np; hi = ch[st.n_chunks - 1].pw_off + ch[st.n_chunks - 1].np;
+    }
+    if (i < lo || i >= hi) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t slot = (int64_t)dr.pw_base + i;
     double a[6];
     ax_tonewin_partial(w, dr, c, w.pw_ind[slot], lane, 32, a);
 #pragma unroll
     for (int q = 0; q < 6; ++q)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) a[q] += __shfl_xor_sync(0xffffffffu, a[q], o);
-    if (lane == 0) ax_tonewin_finish(w, c, w.st[d], slot, a);
+    if (lane == 0) ax_tonewin_finish(w, c, st, slot, a);
 }
 
 // ------------------------------------------------------------------ fused demodulation pass
@@ -423,9 +437,10 @@ __global__ void __launch_bounds__(128) k_bits_chunk(AxWave w, int phase) {
 }
 
 // ------------------------------------------------------------------ bit edges (CTA per run() iteration)
-// ax_emit_item with one thread per edge: the continuous part of a chunk's walk is read off the
-// canonical walk by rank (ax_emit_canon_pos); only the few edges stepped explicitly before the walk
-// joins it are produced by one thread.
+// ax_emit_item in parallel: head edges one per thread; the continuous part of the chunk's walk is read
+// off the canonical walk tile by tile (a warp per tile, a lane per crossing: the edge number is the tile's
+// running count plus the popcount below the lane's bit, no search); only the few edges stepped
+// explicitly before the walk joins the canonical one are produced by one thread.
 __global__ void __launch_bounds__(128) k_emit_chunk(AxWave w) {
     const int64_t cg = blockIdx.x;
     const int d = ax_find_owner(w.drop, w.n_drops, &AxDrop::chunk_base, cg);
@@ -438,14 +453,31 @@ __global__ void __launch_bounds__(128) k_emit_chunk(AxWave w) {
     if (ne <= 0) return;
     const AxCfg& c = w.cfg[dr.cfg];
     const int nhe = ch.n_head_edges, npre = ch.n_pre;
-    const bool merged = ch.merge_pos >= 0;
-    for (int t = threadIdx.x; t < ne; t += blockDim.x) {
-        if (t < nhe) ax_emit_edge(w, dr, st, c, ch, cg, k, t, 0);
-        else if (t >= nhe + npre) { if (merged) ax_emit_edge(w, dr, st, c, ch, cg, k, t, ax_emit_canon_pos(w, dr, ch, t)); }
-        else if (t == nhe) {
-            const uint8_t* nx = w.zc_nx + dr.zc_base;
-            int64_t pos = ch.g_first;
-            for (int q = 0; q < npre; ++q) { ax_emit_edge(w, dr, st, c, ch, cg, k, nhe + q, pos); if (q < npre - 1) pos += nx[pos]; }
+    for (int t = threadIdx.x; t < nhe; t += blockDim.x) ax_emit_edge(w, dr, st, c, ch, cg, k, t, 0);
+    if (threadIdx.x == 0 && npre > 0) {
+        const uint8_t* nx = w.zc_nx + dr.zc_base;
+        int64_t pos = ch.g_first;
+        for (int q = 0; q < npre; ++q) { ax_emit_edge(w, dr, st, c, ch, cg, k, nhe + q, pos); if (q < npre - 1) pos += nx[pos]; }
+    }
+    if (ch.merge_pos < 0) return;
+    const uint64_t* cmask = w.cmask + dr.tile_base;
+    const int32_t* crank = w.crank + dr.tile_base;
+    const int64_t mp = ch.merge_pos;
+    const int64_t t0 = mp / AX_TILE, t1 = ch.q_last / AX_TILE;
+    const int64_t r0 = ax_canon_rank(cmask, crank, mp) - (nhe + npre);       // edge number = canonical rank - r0
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int64_t tt = t0 + warp; tt <= t1; tt += blockDim.x >> 5) {
+        uint64_t m = cmask[tt];
+        if (tt == t0) m &= ~((1ull << (mp - t0 * AX_TILE)) - 1ull);
+        const int64_t base = (int64_t)crank[tt] - r0;
+        if (base >= ne) break;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int bit = lane + 32 * h;
+            if ((m >> bit) & 1ull) {
+                const int64_t t = base + __popcll(cmask[tt] & ((1ull << bit) - 1ull));
+                if (t < ne) ax_emit_edge(w, dr, st, c, ch, cg, k, (int)t, tt * AX_TILE + bit);
+            }
         }
     }
 }

@@ -414,3 +414,42 @@ AX_HDN inline void ax_qc_item(const AxWave& w, int64_t cg, double* scratch) {
     ch.n_rows = rows;
     if (rows > 0) { ch.n_hex = nfr; for (int i = 0; i < nfr; ++i) fr[i].hex_returned = 1; }   // :611-612
 }
+
+// ---- results as they leave the device ---------------------------------------------------------
+AX_HD int32_t ax_centi(double v, int32_t* flags) {                 // v is already np.round(v, 2)
+    if (isnan(v)) return AXCTD_ROW_NAN;
+    const double q = rint(ax_mul(v, 100.0));
+    if (!(fabs(q) < 2147483000.0) || ax_div(q, 100.0) != v) { *flags |= AXCTD_ROW_WIDE; return 0; }
+    return (int32_t)q;
+}
+AX_HDN inline void ax_row_item(const AxWave& w, int64_t fg) {
+    const int d = ax_find_owner(w.drop, w.n_drops, &AxDrop::frame_base, fg);
+    const AxDrop& dr = w.drop[d];
+    const AxState& st = w.st[d];
+    if (fg - dr.frame_base >= st.n_frames || st.status != 0) return;
+    const axctd_frame& f = w.frame[fg];
+    axctd_row r;
+    r.word = f.word;
+    int32_t fl = (f.keep ? AXCTD_ROW_KEEP : 0) | (f.hex_returned ? AXCTD_ROW_HEX : 0);
+    r.time_c = ax_centi(f.time_s, &fl); r.depth_c = ax_centi(f.depth, &fl); r.temperature_c = ax_centi(f.temperature, &fl);
+    r.conductivity_c = ax_centi(f.conductivity, &fl); r.salinity_c = ax_centi(f.salinity, &fl);
+    r.r400_c = ax_centi(f.r400, &fl); r.r7500_c = ax_centi(f.r7500, &fl);
+    r.flags = fl;
+    w.row[fg] = r;
+}
+AX_HDN inline void ax_chunkout_item(const AxWave& w, int64_t cg) {
+    const int d = ax_find_owner(w.drop, w.n_drops, &AxDrop::chunk_base, cg);
+    const AxDrop& dr = w.drop[d];
+    const AxState& st = w.st[d];
+    const int k = (int)(cg - dr.chunk_base);
+    if (k >= st.n_chunks || k >= dr.chunk_cap) return;
+    const AxChunk& c = w.chunk[cg];
+    axctd_chunk o;
+    o.s = c.s; o.e = c.e; o.status = c.status; o.n_power_total = c.pw_off + c.np;
+    const bool dem = st.k0 >= 0 && k >= st.k0 && c.n_edges > 0;
+    o.n_bits = dem ? c.n_edges - 1 : -1;
+    o.first_edge = dem ? (int32_t)(c.first_edge - c.s) : -1; o.last_edge = dem ? (int32_t)(c.true_last - c.s) : -1;
+    o.n_head_edges = dem ? c.n_head_edges : 0;
+    o.n_rows = c.n_rows; o.n_hex = c.n_hex; o.scale = c.scale;
+    w.chunk_out[cg] = o;
+}

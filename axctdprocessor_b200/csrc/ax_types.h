@@ -209,6 +209,8 @@ struct AxWave {
     uint32_t* bitw; uint32_t* validw;                       // packed bits / frame-candidate mask (32 per word)
     // frames
     axctd_frame* frame;
+    axctd_row* row;              // [frame_total] compact results (ax_row_item)
+    axctd_chunk* chunk_out;      // [chunk_total] public per-iteration records (ax_chunkout_item)
     double guard;
     double bit_tol;              // |p1 - p2| <= bit_tol * max(p1, p2): the bit is re-decided from a double-precision window
     double hist_tol;             // conf within hist_tol (relative) of a histogram bin edge: re-evaluated before the scale calibration

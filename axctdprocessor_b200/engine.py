@@ -125,12 +125,38 @@ class RateConfig:
         return self
 
 
+TABLE_DT = np.dtype([("word", np.uint32), ("keep", np.int32), ("hex_returned", np.int32), ("time_s", np.float64),
+                     ("depth", np.float64), ("temperature", np.float64), ("conductivity", np.float64),
+                     ("salinity", np.float64), ("r400", np.float64), ("r7500", np.float64)])
+
+
 @dataclass
 class DropResult:
     summary: _lib.DropSummary
-    frames: np.ndarray          # structured array of axctd_frame
+    rows: np.ndarray            # structured array of axctd_row (compact: rounded values as integer hundredths)
     chunks: np.ndarray          # structured array of axctd_chunk
     config: RateConfig
+    frames: np.ndarray = None   # structured array of axctd_frame (full records; fetched with full=True)
+
+    def table(self) -> np.ndarray:
+        """Per-frame results as the reference exposes them (rounded doubles): from the compact rows,
+        q / 100.0 being bit-identical to np.round(v, 2); from the full records if a value did not fit."""
+        out = np.zeros(len(self.rows), dtype=TABLE_DT)
+        if len(self.rows) and (self.rows["flags"] & _lib.ROW_WIDE).any():
+            if self.frames is None:
+                raise RuntimeError("a value exceeds the compact row range: fetch the result with full=True")
+            for k in TABLE_DT.names:
+                out[k] = self.frames[k]
+            return out
+        out["word"] = self.rows["word"]
+        out["keep"] = (self.rows["flags"] & _lib.ROW_KEEP) != 0
+        out["hex_returned"] = (self.rows["flags"] & _lib.ROW_HEX) != 0
+        for k in ("time_s", "depth", "temperature", "conductivity", "salinity", "r400", "r7500"):
+            q = self.rows[{"time_s": "time_c"}.get(k, k + "_c")]
+            v = q / 100.0
+            v[q == _lib.ROW_NAN] = np.nan
+            out[k] = v
+        return out
 
     @property
     def status(self):
@@ -148,6 +174,7 @@ def _np_dtype(struct):
 
 FRAME_DT = _np_dtype(_lib.Frame)
 CHUNK_DT = _np_dtype(_lib.Chunk)
+ROW_DT = _np_dtype(_lib.Row)
 
 
 class Engine:
@@ -293,17 +320,26 @@ class Batch:
         self._check(self.lib.axctd_batch_summary(self.h, i, C.byref(s)), "axctd_batch_summary")
         return s
 
-    def result(self, i: int) -> DropResult:
+    def result(self, i: int, full: bool = True) -> DropResult:
+        """Results of drop i.  full=False skips the device->host copy of the full per-frame records
+        (unrounded values): the compact rows already hold everything the reference's API exposes."""
         s = self.summary(i)
-        frames = np.zeros(max(int(s.n_frames), 0), dtype=FRAME_DT)
-        if len(frames):
-            n = self.lib.axctd_batch_frames(self.h, i, frames.ctypes.data, len(frames))
-            assert n == len(frames), n
+        nrow = int(self.lib.axctd_batch_rows(self.h, i, None, 0))
+        rows = np.zeros(max(nrow, 0), dtype=ROW_DT)
+        if len(rows):
+            n = self.lib.axctd_batch_rows(self.h, i, rows.ctypes.data, len(rows))
+            assert n == len(rows), n
         chunks = np.zeros(max(int(s.n_chunks), 0), dtype=CHUNK_DT)
         if len(chunks):
             n = self.lib.axctd_batch_chunks(self.h, i, chunks.ctypes.data, len(chunks))
             chunks = chunks[:max(n, 0)]
-        return DropResult(summary=s, frames=frames, chunks=chunks, config=self.configs[i])
+        frames = None
+        if full:
+            frames = np.zeros(max(int(s.n_frames), 0), dtype=FRAME_DT)
+            if len(frames):
+                n = self.lib.axctd_batch_frames(self.h, i, frames.ctypes.data, len(frames))
+                assert n == len(frames), n
+        return DropResult(summary=s, rows=rows, chunks=chunks, config=self.configs[i], frames=frames)
 
     def synth_fill(self, i: int, spec):
         """bench / test tooling: generate synth.DropSpec ``spec`` directly in device memory."""

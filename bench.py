@@ -261,8 +261,8 @@ def run_native(args):
         b.run()
         out_bytes = 0
         for i in range(len(specs)):
-            r = b.result(i)
-            out_bytes += r.frames.nbytes + r.chunks.nbytes + 2048
+            r = b.result(i, full=False)
+            out_bytes += r.rows.nbytes + r.chunks.nbytes + 2048
         return out_bytes
 
     d2h_bytes = e2e_step()

@@ -137,6 +137,19 @@ typedef struct axctd_frame {
     double time_raw, depth_raw, temperature_raw, conductivity_raw, salinity_raw, r400_raw, r7500_raw;
 } axctd_frame;
 
+/* Compact result record of one profile frame: what AXCTD_Processor exposes per frame (the lists extended at
+ * AXCTDprocessor.py:315-323), with the np.round(v, 2) values (:559-566) carried as integer hundredths
+ * q = rint(100 v), so that q / 100.0 on the host is bit-identical to the rounded double. */
+#define AXCTD_ROW_KEEP 1            /* row survives QC and the spike filter (:569-609) */
+#define AXCTD_ROW_HEX  2            /* its hex string reaches self.hexframes (:612) */
+#define AXCTD_ROW_WIDE 4            /* a value does not fit the int32 hundredths: fetch the drop with axctd_batch_frames */
+#define AXCTD_ROW_NAN  (-2147483647 - 1)
+typedef struct axctd_row {
+    uint32_t word;              /* the 32 frame bits, MSB first */
+    int32_t  flags;             /* AXCTD_ROW_* */
+    int32_t  time_c, depth_c, temperature_c, conductivity_c, salinity_c, r400_c, r7500_c;
+} axctd_row;
+
 /* One run() iteration (AXCTDprocessor.py:283-338). */
 typedef struct axctd_chunk {
     int64_t s, e;               /* demodbufferstartind, e           :293-304 */
@@ -156,7 +169,7 @@ typedef struct axctd_batch  axctd_batch;
 int  axctd_abi_version(void);
 /* 1 if the library was built with the CUDA kernels (always for the product). */
 int  axctd_has_cuda(void);
-/* sizeof() of the ABI structs: 0 config_desc, 1 drop_summary, 2 frame, 3 chunk (binding self-check). */
+/* sizeof() of the ABI structs: 0 config_desc, 1 drop_summary, 2 frame, 3 chunk, 4 row (binding self-check). */
 int  axctd_struct_size(int which);
 int  axctd_engine_create(int device, axctd_engine** out);
 void axctd_engine_destroy(axctd_engine* e);
@@ -198,6 +211,9 @@ int  axctd_batch_timing(axctd_batch* b, double* total_ms, double* filter_ms, dou
 int  axctd_batch_summary(axctd_batch* b, int drop, axctd_drop_summary* out);
 /* Caller-owned buffers; each returns the number of items written or a
  * negative AXCTD_ERR_* code.  cap is the buffer capacity in items. */
+/* Compact per-frame results (downloaded by axctd_batch_finish into pinned host memory). */
+int64_t axctd_batch_rows(axctd_batch* b, int drop, axctd_row* out, int64_t cap);
+/* Full per-frame records including the unrounded values (copied device->host on demand). */
 int64_t axctd_batch_frames(axctd_batch* b, int drop, axctd_frame* out, int64_t cap);
 int64_t axctd_batch_chunks(axctd_batch* b, int drop, axctd_chunk* out, int64_t cap);
 int64_t axctd_batch_bits(axctd_batch* b, int drop, uint8_t* bits, double* conf, int64_t cap);

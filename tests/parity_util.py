@@ -21,6 +21,10 @@ def run_engine(eng, pcm, fs, settings=None, triggerrange=None):
 
 def frames_view(res):
     fr = res.frames
+    tab = res.table()                       # compact rows (integer hundredths) must reproduce the rounded doubles exactly
+    assert len(tab) == len(fr)
+    for k in tab.dtype.names:
+        np.testing.assert_array_equal(tab[k], fr[k], err_msg=k)
     kept = fr[fr["keep"] == 1]
     hexr = ["%08x" % int(w) for w in fr["word"][fr["hex_returned"] == 1]]
     return kept, hexr
