@@ -385,6 +385,12 @@ extern "C" int axctd_config_create(axctd_engine* e, const axctd_config_desc* ds,
         ax_cfg_upload(e, &c.lut, ds->temp_lut, (size_t)ds->lut_len) ||
         ax_cfg_upload(e, &c.hist_edges, ds->hist_edges, (size_t)ds->n_hist_edges) ||
         ax_cfg_upload(e, &c.hist_centers, ds->hist_centers, (size_t)ds->n_hist_edges - 1)) return AXCTD_ERR_CUDA;
+    {
+        std::vector<double> soa(6 * (size_t)c.n_power);
+        for (int m = 0; m < c.n_power; ++m)
+            for (int q = 0; q < 6; ++q) soa[(size_t)q * c.n_power + m] = ds->tone_cs[6 * (size_t)m + q];
+        if (ax_cfg_upload(e, &c.tone_soa, soa.data(), soa.size())) return AXCTD_ERR_CUDA;
+    }
     e->cfgs.push_back(c);
     e->tone_tabs.push_back(ttab);
     if (ax_h2d(e, e->d_cfg + (e->cfgs.size() - 1), &e->cfgs.back(), sizeof(AxCfg)) || ax_sync(e)) return AXCTD_ERR_CUDA;
@@ -758,7 +764,11 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
 #define AX_BITS(phase) AX_LAUNCH(e, k_bits, b->edge_total, w, phase)
 #endif
     AX_BITS(0);
+#ifndef AXCTD_EMU
+    k_scale_block<<<n, 128, 0, e->stream>>>(w); e->launches++;
+#else
     AX_LAUNCH1(e, k_scale, n, w);
+#endif
     AX_BITS(1);
     AX_LAUNCH1(e, k_headers, 2 * (int64_t)n, w);
     // header text -> calibration coefficients on the host (python float semantics)
@@ -771,7 +781,10 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
     AX_LAUNCH1(e, k_frames_chain, n, w);
     AX_LAUNCH(e, k_frames_write, b->chunk_total, w);
     AX_LAUNCH(e, k_calib, b->frame_total, w);
-    AX_LAUNCH(e, k_qc, b->chunk_total, w, b->d_qc);
+#ifndef AXCTD_EMU
+    if (e->opt_filter_variant == 0) { k_qc_warp<<<(unsigned)((b->chunk_total + 3) / 4), 128, 0, e->stream>>>(w, b->d_qc); e->launches++; } else
+#endif
+    { AX_LAUNCH(e, k_qc, b->chunk_total, w, b->d_qc); }
     AX_LAUNCH(e, k_rows, b->frame_total, w);
     AX_LAUNCH(e, k_chunkout, b->chunk_total, w);
     AX_EVENT(b, 5);

@@ -408,6 +408,11 @@ __global__ void __launch_bounds__(128) k_bits_chunk(AxWave w, int phase) {
     const AxChunk& ch = w.chunk[cg];
     const int nb = ch.n_edges - 1;
     if (nb <= 0) return;
+    if (phase == 0) {        // only the header-1 calibration window matters (same bounds as ax_bits_need)
+        const AxCfg& c = w.cfg[dr.cfg];
+        const int64_t mg = (int64_t)(64.0 * c.fs / c.bitrate);
+        if (ch.e < st.firstpulse400 + c.h1s - c.half - mg || ch.s > st.firstpulse400 + c.h1e + c.half + mg) return;
+    }
     const int lane = threadIdx.x & 31;
     const int64_t slot0 = dr.edge_base + ch.bit_off;
     for (int jb = threadIdx.x - lane; jb < nb; jb += blockDim.x) {       // warp-uniform trip count
@@ -480,6 +485,129 @@ __global__ void __launch_bounds__(128) k_emit_chunk(AxWave w) {
             }
         }
     }
+}
+
+// ------------------------------------------------------------------ scale calibration (CTA per drop)
+// ax_scale_item with the histogram filled by the whole CTA (shared-memory atomics).
+__global__ void __launch_bounds__(128) k_scale_block(AxWave w) {
+    const int d = blockIdx.x;
+    const AxDrop& dr = w.drop[d];
+    const AxCfg& c = w.cfg[dr.cfg];
+    AxState& st = w.st[d];
+    __shared__ int s_hist[512];
+    __shared__ int s_found, s_k;
+    __shared__ int64_t s_a, s_hi;
+    const int nbins = c.n_hist_edges - 1;
+    if (threadIdx.x == 0) {
+        ax_scale_reset(w, d);
+        int k = -1; int64_t a = 0, hi = 0;
+        int found = 0;
+        if (st.sm_status >= 1 && st.nedges_total != 0) {
+            found = ax_scale_find(w, d, &k, &a, &hi);
+            if (found < 0) ax_raise(st, -found, k);
+            else if (found && nbins > 512) { ax_raise(st, AXCTD_DROP_CAPACITY, k); found = -1; }
+        } else found = -1;
+        s_found = found; s_k = k; s_a = a; s_hi = hi;
+    }
+    for (int q = threadIdx.x; q < 512; q += blockDim.x) s_hist[q] = 0;
+    __syncthreads();
+    if (s_found < 0) return;
+    if (s_found) {
+        const double* a1 = w.a1 + dr.edge_base; const double* a2 = w.a2 + dr.edge_base;
+        for (int64_t jj = s_a + threadIdx.x; jj < s_hi; jj += blockDim.x) {
+            const int bin = ax_scale_bin(c, ax_div(ax_mul(a2[jj], c.scale0), a1[jj]));
+            if (bin >= 0) atomicAdd(&s_hist[bin], 1);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double thr;
+            if (!ax_scale_threshold(c, s_hist, s_hi > s_a ? s_hi - s_a : 0, &thr)) { ax_raise(st, AXCTD_DROP_SCALE_EMPTY, s_k); s_found = -1; }
+            else { st.scale = ax_div(c.scale0, thr); st.k1 = s_k; st.header_read[0] = 1; st.header_chunk[0] = s_k; }
+        }
+        __syncthreads();
+        if (s_found < 0) return;
+    }
+    ax_scale_spread(w, d, threadIdx.x, blockDim.x);
+}
+
+// ------------------------------------------------------------------ spike filter (warp per run() iteration)
+// ax_qc_item with the percentiles taken by rank counting across the warp (up to 64 kept rows per
+// iteration, two per lane); larger iterations fall back to the one-thread form.
+// ranks (0-based, ties broken by position: slot 0 of lane j is entry j, slot 1 is entry j + 32) of this lane's two entries
+__device__ __forceinline__ void ax_warp_ranks(double v0, double v1, bool has0, bool has1, int lane, int* r0_out, int* r1_out) {
+    int r0 = 0, r1 = 0;
+    for (int j = 0; j < 32; ++j) {
+        const double u0 = __shfl_sync(0xffffffffu, v0, j), u1 = __shfl_sync(0xffffffffu, v1, j);
+        const bool h0 = __shfl_sync(0xffffffffu, (int)has0, j), h1 = __shfl_sync(0xffffffffu, (int)has1, j);
+        if (h0) { r0 += (u0 < v0) || (u0 == v0 && j < lane); r1 += (u0 < v1) || (u0 == v1); }
+        if (h1) { r0 += (u1 < v0); r1 += (u1 < v1) || (u1 == v1 && j < lane); }
+    }
+    *r0_out = r0; *r1_out = r1;
+}
+__device__ __forceinline__ double ax_warp_kth(double v0, double v1, bool has0, bool has1, int r0, int r1, int kth) {
+    const unsigned b0 = __ballot_sync(0xffffffffu, has0 && r0 == kth), b1 = __ballot_sync(0xffffffffu, has1 && r1 == kth);
+    if (b0) return __shfl_sync(0xffffffffu, v0, __ffs((int)b0) - 1);
+    return __shfl_sync(0xffffffffu, v1, __ffs((int)b1) - 1);
+}
+__device__ __forceinline__ double ax_warp_percentile(double v0, double v1, bool has0, bool has1, int r0, int r1, int n, double q) {
+    const double virt = ax_mul((double)(n - 1), q);                  // ax_percentile_sorted
+    int prev = (int)floor(virt), next = prev + 1;
+    if (virt >= (double)(n - 1)) { prev = n - 1; next = n - 1; }
+    if (virt < 0) { prev = 0; next = 0; }
+    const double gamma = ax_sub(virt, floor(virt));
+    const double a = ax_warp_kth(v0, v1, has0, has1, r0, r1, prev), b = ax_warp_kth(v0, v1, has0, has1, r0, r1, next);
+    const double diff = ax_sub(b, a);
+    double r = ax_add(a, ax_mul(diff, gamma));
+    if (gamma >= 0.5) r = ax_sub(b, ax_mul(diff, ax_sub(1.0, gamma)));
+    return r;
+}
+__global__ void __launch_bounds__(128) k_qc_warp(AxWave w, double* scratch) {
+    const int64_t cg = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (cg >= gridDim.x * (int64_t)(blockDim.x >> 5)) return;
+    const int d = ax_find_owner(w.drop, w.n_drops, &AxDrop::chunk_base, cg);
+    const AxDrop& dr = w.drop[d];
+    const AxState& st = w.st[d];
+    const int k = (int)(cg - dr.chunk_base);
+    if (k >= dr.chunk_cap || st.status != 0 || st.k2 < 0 || k < st.k2 || k >= st.n_chunks) return;
+    AxChunk& ch = w.chunk[cg];
+    const int nfr = ch.frame_end - ch.frame_begin;
+    if (nfr > 64) { if (lane == 0) ax_qc_item(w, cg, scratch); return; }
+    if (lane == 0) { ch.n_rows = 0; ch.n_hex = 0; }
+    if (nfr <= 0) return;
+    axctd_frame* fr = w.frame + dr.frame_base + ch.frame_begin;
+    const int i0 = lane, i1 = lane + 32;
+    const bool has0 = i0 < nfr && fr[i0].keep, has1 = i1 < nfr && fr[i1].keep;
+    const double T0 = has0 ? fr[i0].temperature : 0.0, T1 = has1 ? fr[i1].temperature : 0.0;
+    const double S0 = has0 ? fr[i0].salinity : 0.0, S1 = has1 ? fr[i1].salinity : 0.0;
+    const int n = __popc(__ballot_sync(0xffffffffu, has0)) + __popc(__ballot_sync(0xffffffffu, has1));
+    if (n == 0) return;
+    const bool tnan = __any_sync(0xffffffffu, (has0 && isnan(T0)) || (has1 && isnan(T1)));
+    const bool snan = __any_sync(0xffffffffu, (has0 && isnan(S0)) || (has1 && isnan(S1)));
+    double Tlo = ax_nan(), Thi = ax_nan(), Slo = ax_nan(), Shi = ax_nan();
+    int r0, r1;
+    if (!tnan) {
+        ax_warp_ranks(T0, T1, has0, has1, lane, &r0, &r1);
+        const double m = ax_warp_percentile(T0, T1, has0, has1, r0, r1, n, 0.5);
+        Tlo = ax_sub(m, ax_mul(10.0, ax_sub(m, ax_warp_percentile(T0, T1, has0, has1, r0, r1, n, 0.15))));
+        Thi = ax_add(m, ax_mul(10.0, ax_sub(ax_warp_percentile(T0, T1, has0, has1, r0, r1, n, 0.85), m)));
+    }
+    if (!snan) {
+        ax_warp_ranks(S0, S1, has0, has1, lane, &r0, &r1);
+        const double m = ax_warp_percentile(S0, S1, has0, has1, r0, r1, n, 0.5);
+        Slo = ax_sub(m, ax_mul(10.0, ax_sub(m, ax_warp_percentile(S0, S1, has0, has1, r0, r1, n, 0.15))));
+        Shi = ax_add(m, ax_mul(10.0, ax_sub(ax_warp_percentile(S0, S1, has0, has1, r0, r1, n, 0.85), m)));
+    }
+    const bool k0 = has0 && !(T0 < Tlo || T0 > Thi || S0 < Slo || S0 > Shi);
+    const bool k1 = has1 && !(T1 < Tlo || T1 > Thi || S1 < Slo || S1 > Shi);
+    if (has0 && !k0) fr[i0].keep = 0;
+    if (has1 && !k1) fr[i1].keep = 0;
+    const int rows = __popc(__ballot_sync(0xffffffffu, k0)) + __popc(__ballot_sync(0xffffffffu, k1));
+    if (rows > 0) {                                                    // :611-612
+        if (i0 < nfr) fr[i0].hex_returned = 1;
+        if (i1 < nfr) fr[i1].hex_returned = 1;
+    }
+    if (lane == 0) { ch.n_rows = rows; ch.n_hex = rows > 0 ? nfr : 0; }
 }
 
 // ------------------------------------------------------------------ dense crossing arrays

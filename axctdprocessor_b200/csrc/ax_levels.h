@@ -160,8 +160,8 @@ AX_HD void ax_tonewin_partial(const AxWave& w, const AxDrop& dr, const AxCfg& c,
     for (int64_t i = lane; i < head_n + tail_n; i += nl) {
         const int64_t n = i < head_n ? cstart + i : tail0 + (i - head_n);
         const double xd = (double)x[n];
-        const double* t6 = c.tone_cs + 6 * (n - cstart);
-        for (int q = 0; q < 6; ++q) a[q] = ax_fma(xd, t6[q], a[q]);
+        const double* t1 = c.tone_soa + (n - cstart);
+        for (int q = 0; q < 6; ++q) a[q] = ax_fma(xd, t1[(int64_t)q * c.n_power], a[q]);
     }
     for (int64_t j = j0 + lane; j < j1; j += nl) {
         const double* B = w.tb_sum + (dr.tb_base + j) * 6;
@@ -444,16 +444,15 @@ AX_HD int64_t ax_first_gt(const int32_t* I, int64_t from, int64_t n, int64_t v) 
     return -1;
 }
 
-// AXCTDprocessor.py:459-468 + demodulate.py:124-157
-AX_HDN inline void ax_scale_item(const AxWave& w, int64_t d) {
+// ---- mark/space scale calibration: AXCTDprocessor.py:459-468 + demodulate.py:124-157 ----------
+// Which iteration reads header 1, and which bit positions [a, hi) feed the histogram.
+//   returns 1 found, 0 not (yet) available, <0 = -AXCTD_DROP_* error (chunk in *k_out)
+AX_HD int ax_scale_find(const AxWave& w, int d, int* k_out, int64_t* a_out, int64_t* hi_out) {
     const AxDrop& dr = w.drop[d];
     const AxCfg& c = w.cfg[dr.cfg];
-    AxState& st = w.st[d];
-    st.scale = c.scale0; st.k1 = -1; st.header_read[0] = 0; st.header_chunk[0] = -1; st.scale_switch_bit = st.nbits_total;
-    if (st.sm_status < 1 || st.nedges_total == 0) return;
-    AxChunk* ch = w.chunk + dr.chunk_base;
+    const AxState& st = w.st[d];
+    const AxChunk* ch = w.chunk + dr.chunk_base;
     const int32_t* I = w.edge_idx + dr.edge_base;
-    const double* a1 = w.a1 + dr.edge_base; const double* a2 = w.a2 + dr.edge_base;
     const int64_t firstbin = I[0];
     const int64_t p1s = st.firstpulse400 + c.h1s, p1e = st.firstpulse400 + c.h1e;
     const int klast = (st.k2 >= 0) ? st.k2 : st.n_chunks - 1;
@@ -463,46 +462,85 @@ AX_HDN inline void ax_scale_item(const AxWave& w, int64_t d) {
         const int64_t lastbin = I[ni - 1];
         if (!(firstbin <= p1s && lastbin >= p1e)) continue;
         const int64_t a = ax_first_ge(I, ni, p1s - c.half), b = ax_last_le(I, ni, p1e + c.half);
-        if (a < 0 || b < 0) { ax_raise(st, AXCTD_DROP_TRIM_INDEX, k); return; }
-        int64_t hi = b < nb ? b : nb;
-        const int64_t npts = hi > a ? hi - a : 0;
+        *k_out = k;
+        if (a < 0 || b < 0) return -AXCTD_DROP_TRIM_INDEX;
+        *a_out = a; *hi_out = b < nb ? b : nb;
+        return 1;
+    }
+    return 0;
+}
+// np.histogram bin of v for edges ed[0..nbins] (last bin closed), -1 if outside
+AX_HD int ax_scale_bin(const AxCfg& c, double v) {
+    const int nbins = c.n_hist_edges - 1;
+    const double* ed = c.hist_edges;
+    if (!(v >= ed[0]) || v > ed[nbins]) return -1;
+    int lo = 0, up = nbins + 1;                                          // first edge > v
+    while (lo < up) { int mid = (lo + up) >> 1; if (ed[mid] <= v) lo = mid + 1; else up = mid; }
+    int bin = lo - 1;
+    if (bin >= nbins) bin = nbins - 1;
+    return bin;
+}
+// demodulate.py:136-153: cumulative percentage, centred slope, flattest stretch inside 30..65 %
+AX_HD bool ax_scale_threshold(const AxCfg& c, const int* hist, int64_t npts, double* thr) {
+    const int nbins = c.n_hist_edges - 1;
+    double best = 0; int first = -1, last = -1;
+    int64_t cs = 0;
+    double cp[512];
+    for (int q = 0; q < nbins; ++q) { cs += hist[q]; cp[q] = ax_div((double)(100 * cs), (double)npts); }
+    const double* ctr = c.hist_centers;
+    for (int q = 0; q < nbins; ++q) {
+        if (!(cp[q] >= 30.0 && cp[q] <= 65.0)) continue;
+        double sl;
+        if (q == 0) sl = ax_div(ax_sub(cp[1], cp[0]), ax_sub(ctr[1], ctr[0]));
+        else if (q == nbins - 1) sl = ax_div(ax_sub(cp[q], cp[q - 1]), ax_sub(ctr[q], ctr[q - 1]));
+        else sl = ax_div(ax_sub(cp[q + 1], cp[q - 1]), ax_sub(ctr[q + 1], ctr[q - 1]));
+        if (first < 0 || sl < best) { best = sl; first = q; last = q; }
+        else if (sl == best) last = q;
+    }
+    if (first < 0) return false;
+    *thr = ax_div(ax_add(ctr[first], ctr[last]), 2.0);
+    return true;
+}
+AX_HD void ax_scale_reset(const AxWave& w, int d) {
+    AxState& st = w.st[d];
+    st.scale = w.cfg[w.drop[d].cfg].scale0; st.k1 = -1; st.header_read[0] = 0; st.header_chunk[0] = -1; st.scale_switch_bit = st.nbits_total;
+}
+// per-iteration scale and the first bit decided with the calibrated one; chunks k = first, first+step, ...
+AX_HD void ax_scale_spread(const AxWave& w, int d, int first, int step) {
+    const AxDrop& dr = w.drop[d];
+    AxState& st = w.st[d];
+    AxChunk* ch = w.chunk + dr.chunk_base;
+    const double s0 = w.cfg[dr.cfg].scale0;
+    for (int k = st.k0 + first; k < st.n_chunks; k += step) ch[k].scale = (st.k1 >= 0 && k > st.k1) ? st.scale : s0;
+    if (first == 0) st.scale_switch_bit = (st.k1 >= 0 && st.k1 + 1 < st.n_chunks) ? ch[st.k1 + 1].bit_off : st.nbits_total;
+}
+
+// generic one-thread form (the CUDA build fills the histogram with a CTA: k_scale_block)
+AX_HDN inline void ax_scale_item(const AxWave& w, int64_t d) {
+    const AxDrop& dr = w.drop[d];
+    const AxCfg& c = w.cfg[dr.cfg];
+    AxState& st = w.st[d];
+    ax_scale_reset(w, (int)d);
+    if (st.sm_status < 1 || st.nedges_total == 0) return;
+    int k = -1; int64_t a = 0, hi = 0;
+    const int found = ax_scale_find(w, (int)d, &k, &a, &hi);
+    if (found < 0) { ax_raise(st, -found, k); return; }
+    if (found) {
         const int nbins = c.n_hist_edges - 1;
         int hist[512];
         if (nbins > 512) { ax_raise(st, AXCTD_DROP_CAPACITY, k); return; }
         for (int q = 0; q < nbins; ++q) hist[q] = 0;
-        const double* ed = c.hist_edges;
+        const double* a1 = w.a1 + dr.edge_base; const double* a2 = w.a2 + dr.edge_base;
         for (int64_t jj = a; jj < hi; ++jj) {
-            const double v = ax_div(ax_mul(a2[jj], c.scale0), a1[jj]);          // demodulate.py:102,110
-            if (!(v >= ed[0]) || v > ed[nbins]) continue;
-            int lo = 0, up = nbins + 1;                                          // first edge > v
-            while (lo < up) { int mid = (lo + up) >> 1; if (ed[mid] <= v) lo = mid + 1; else up = mid; }
-            int bin = lo - 1;
-            if (bin >= nbins) bin = nbins - 1;
-            hist[bin]++;
+            const int bin = ax_scale_bin(c, ax_div(ax_mul(a2[jj], c.scale0), a1[jj]));          // demodulate.py:102,110
+            if (bin >= 0) hist[bin]++;
         }
-        // cumulative percentage and centred slope, evaluated on the fly
-        double best = 0; int first = -1, last = -1;
-        int64_t cs = 0;
-        double cp[512];
-        for (int q = 0; q < nbins; ++q) { cs += hist[q]; cp[q] = ax_div((double)(100 * cs), (double)npts); }
-        const double* ctr = c.hist_centers;
-        for (int q = 0; q < nbins; ++q) {
-            if (!(cp[q] >= 30.0 && cp[q] <= 65.0)) continue;
-            double sl;
-            if (q == 0) sl = ax_div(ax_sub(cp[1], cp[0]), ax_sub(ctr[1], ctr[0]));
-            else if (q == nbins - 1) sl = ax_div(ax_sub(cp[q], cp[q - 1]), ax_sub(ctr[q], ctr[q - 1]));
-            else sl = ax_div(ax_sub(cp[q + 1], cp[q - 1]), ax_sub(ctr[q + 1], ctr[q - 1]));
-            if (first < 0 || sl < best) { best = sl; first = q; last = q; }
-            else if (sl == best) last = q;
-        }
-        if (first < 0) { ax_raise(st, AXCTD_DROP_SCALE_EMPTY, k); return; }
-        const double thr = ax_div(ax_add(ctr[first], ctr[last]), 2.0);
+        double thr;
+        if (!ax_scale_threshold(c, hist, hi > a ? hi - a : 0, &thr)) { ax_raise(st, AXCTD_DROP_SCALE_EMPTY, k); return; }
         st.scale = ax_div(c.scale0, thr);
         st.k1 = k; st.header_read[0] = 1; st.header_chunk[0] = k;
-        break;
     }
-    for (int k = st.k0; k < st.n_chunks; ++k) ch[k].scale = (st.k1 >= 0 && k > st.k1) ? st.scale : c.scale0;
-    st.scale_switch_bit = (st.k1 >= 0 && st.k1 + 1 < st.n_chunks) ? ch[st.k1 + 1].bit_off : st.nbits_total;
+    ax_scale_spread(w, (int)d, 0, 1);
 }
 
 // ---- bit decisions (demodulate.py:102,109-114) ------------------------------------------------

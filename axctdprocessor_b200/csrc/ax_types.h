@@ -82,6 +82,7 @@ struct AxCfg {
     double rot[2][2];            // cos,sin of (-theta_f * rebase), f = mark, space
     const double* bit_cs;        // [rebase+1][4]
     const double* tone_cs;       // [n_power][6]
+    const double* tone_soa;      // [6][n_power] the same table, one array per component (coalesced reads in ax_tonewin_partial)
     const double* lut;           // [lut_len]
     const double* hist_edges;    // [n_hist_edges]
     const double* hist_centers;  // [n_hist_edges-1]
