@@ -114,7 +114,7 @@ AX_HD bool ax_sos_is_butter(const AxCfg& c) {
 AX_HD int ax_win_quads(int npcm) { return (npcm + 6) >> 2; }     // quads covering offset o <= 3 plus npcm taps
 
 // yv[k], k < 4*ax_win_quads(npcm): samples of the aligned quads; o = (i + 1) & 3
-AX_HD void ax_window32(const float* yv, int o, int npcm, const AxWinTab& tab, float* a1, float* a2) {
+AX_HD void ax_window32(const float* yv, int o, int npcm, const AxF4* tab, float* a1, float* a2) {
     float r1a = 0.f, i1a = 0.f, r2a = 0.f, i2a = 0.f, r1b = 0.f, i1b = 0.f, r2b = 0.f, i2b = 0.f;
     const int nt = 4 * ax_win_quads(npcm);
 #pragma unroll
@@ -122,10 +122,11 @@ AX_HD void ax_window32(const float* yv, int o, int npcm, const AxWinTab& tab, fl
         if (k < nt) {
             const float ya = (k >= o && k < o + npcm) ? yv[k] : 0.f;
             const float yb = (k + 1 >= o && k + 1 < o + npcm) ? yv[k + 1] : 0.f;
-            r1a = fmaf(ya, tab.t[k].x, r1a); i1a = fmaf(ya, tab.t[k].y, i1a);
-            r2a = fmaf(ya, tab.t[k].z, r2a); i2a = fmaf(ya, tab.t[k].w, i2a);
-            r1b = fmaf(yb, tab.t[k + 1].x, r1b); i1b = fmaf(yb, tab.t[k + 1].y, i1b);
-            r2b = fmaf(yb, tab.t[k + 1].z, r2b); i2b = fmaf(yb, tab.t[k + 1].w, i2b);
+            const AxF4 ta = tab[k], tb = tab[k + 1];                   // 16-byte broadcast loads (shared memory in k_demod_fused)
+            r1a = fmaf(ya, ta.x, r1a); i1a = fmaf(ya, ta.y, i1a);
+            r2a = fmaf(ya, ta.z, r2a); i2a = fmaf(ya, ta.w, i2a);
+            r1b = fmaf(yb, tb.x, r1b); i1b = fmaf(yb, tb.y, i1b);
+            r2b = fmaf(yb, tb.z, r2b); i2b = fmaf(yb, tb.w, i2b);
         }
     }
     const float r1 = r1a + r1b, i1 = i1a + i1b, r2 = r2a + r2b, i2 = i2a + i2b;
@@ -257,7 +258,7 @@ struct AxFilt {
             const int nt = 4 * ax_win_quads(npcm);
             for (int k = 0; k < nt; ++k) yv[k] = yring[(a + k) & 127];
             float v1, v2;
-            ax_window32(yv, o, npcm, *tab, &v1, &v2);
+            ax_window32(yv, o, npcm, tab->t, &v1, &v2);
             put(i, v1, v2);
             pop();
         }
@@ -590,10 +591,14 @@ AX_HDN inline void ax_head_item(const AxWave& w, int64_t cg) {
     {   // demodulate.py:74 on AXCTDprocessor.py:57 samples
         double z[AX_MAXSEC][2];
         for (int q = 0; q < AX_MAXSEC; ++q) { z[q][0] = 0.0; z[q][1] = 0.0; }
-        for (int64_t n = 0; n < ny; ++n) {
-            double u = ax_div(ax_sub((double)x[n], st.dc), st.ampl_d);
-            for (int q = 0; q < c.nsec; ++q) u = ax_biquad_exact(u, c.sos[q], z[q][0], z[q][1]);
-            yb[n] = u;
+        for (int64_t n0 = 0; n0 < ny; n0 += 16) {         // samples fetched 16 at a time, ahead of the dependent filter chain
+            int xs[16];
+            for (int i = 0; i < 16; ++i) xs[i] = (n0 + i < ny) ? (int)x[n0 + i] : 0;
+            for (int i = 0; i < 16 && n0 + i < ny; ++i) {
+                double u = ax_div(ax_sub((double)xs[i], st.dc), st.ampl_d);
+                for (int q = 0; q < c.nsec; ++q) u = ax_biquad_exact(u, c.sos[q], z[q][0], z[q][1]);
+                yb[n0 + i] = u;
+            }
         }
     }
     int nh = 0;

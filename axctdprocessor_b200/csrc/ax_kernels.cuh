@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(256) k_tone_windows(AxWave w, int phase_b, int
 //            three sections), collects the sign bits in registers and stores the float roundings of y
 //            into its 128-sample ring in shared memory (STS.128, conflict free);
 //   phase 2  the crossings of the previous row are compacted across the warp and dealt to the lanes one
-//            each, so the 4*NPCM-FMA fp32 windows (ax_window32, phasors as constant-bank operands) run
+//            each, so the 4*NPCM-FMA fp32 windows (ax_window32, phasors broadcast from shared memory) run
 //            without divergence whatever the crossing density of the individual rows.
 // y never leaves the SM; the only global traffic is the int16 stream in and (index, |S1|, |S2|) per
 // crossing out.
@@ -197,6 +197,7 @@ __global__ void __launch_bounds__(256) k_tone_windows(AxWave w, int phase_b, int
 #define AX_FD_LIST 256                                 // crossings dealt per pass
 
 struct AxFdSmem {
+    AxF4 tab[AX_WIN_TAPS];                             // phasors of the bit windows (per warp copy: no CTA barrier needed)
     int16_t stage[2][AX_FD_STAGE];
     float yring[32 * AX_FD_YSTRIDE];
     uint32_t list[AX_FD_LIST];
@@ -227,6 +228,7 @@ __global__ void __launch_bounds__(AX_FD_THREADS, 2) k_demod_fused(const __grid_c
     const int16_t* xdrop = w.pcm + dr.pcm_off;
     const unsigned long long xrow = (unsigned long long)(xdrop + g.n_begin);      // 16-byte aligned
     sm.row_begin[lane] = (int)g.n_begin; sm.row_stop[lane] = (int)g.n_stop;
+    for (int k = lane; k < AX_WIN_TAPS; k += 32) sm.tab[k] = tab.t[k];
     // ---- cascade constants (Butterworth form, see AxFilt::filter)
     double z0[NSEC], z1[NSEC], a1[NSEC], a2[NSEC], sg[NSEC];
 #pragma unroll
@@ -236,7 +238,7 @@ __global__ void __launch_bounds__(AX_FD_THREADS, 2) k_demod_fused(const __grid_c
         sg[s] = (c.sos[s][1] < 0.0) ? -2.0 : 2.0;
     }
     const double k0 = c.sos[0][0] * st.inv_ampl, k1 = c.sos[0][0] * -(st.dc * st.inv_ampl);
-    const unsigned guard_hi = (unsigned)__double2hiint(w.guard);
+    const float guard_f = (float)w.guard;
     const int nb = (int)g.n_begin, nstop = (int)g.n_stop, sstart = (int)g.seg_start, send = (int)g.seg_end;
     const int64_t slot0 = seg * (int64_t)w.seg_cap;
     const int64_t wslot0 = (seg - lane) * (int64_t)w.seg_cap;       // slot of the warp's row 0
@@ -270,7 +272,7 @@ __global__ void __launch_bounds__(AX_FD_THREADS, 2) k_demod_fused(const __grid_c
             if (t < T) {
                 const int4* rp = reinterpret_cast<const int4*>(&sm.stage[t & 1][lane * AX_FD_ROW]);
                 float4* yo = reinterpret_cast<float4*>(myring + (t & 1) * 64);
-                unsigned minabs = 0x7fffffffu;
+                float minabs = 1e30f;
 #pragma unroll
                 for (int hw = 0; hw < 2; ++hw) {
                     unsigned sb = 0u;
@@ -290,10 +292,9 @@ __global__ void __launch_bounds__(AX_FD_THREADS, 2) k_demod_fused(const __grid_c
                                 z1[s] = fma(a2[s], y, tt);
                                 tt = y;
                             }
-                            const unsigned hi = (unsigned)__double2hiint(tt);
-                            sb = __funnelshift_l(hi, sb, 1);                 // MSB-first: sample 0 of this half ends at bit 31
-                            minabs = min(minabs, hi & 0x7fffffffu);
+                            sb = __funnelshift_l((unsigned)__double2hiint(tt), sb, 1);   // MSB-first: sample 0 of this half ends at bit 31
                             yf[e] = (float)tt;
+                            minabs = fminf(minabs, fabsf(yf[e]));
                         }
                         yo[hw * 8 + v * 2] = make_float4(yf[0], yf[1], yf[2], yf[3]);
                         yo[hw * 8 + v * 2 + 1] = make_float4(yf[4], yf[5], yf[6], yf[7]);
@@ -301,11 +302,11 @@ __global__ void __launch_bounds__(AX_FD_THREADS, 2) k_demod_fused(const __grid_c
                     Scur |= (unsigned long long)__brev(sb) << (32 * hw);
                 }
                 // guard band: a filter output this close to zero cannot be signed reliably (AXCTD_DROP_UNCERTAIN)
-                if (minabs < guard_hi) {
+                if (minabs < guard_f) {
                     const int base = nb + 64 * t;
                     for (int i = 0; i < 64; ++i) {
                         const int n = base + i;
-                        if (n >= sstart && n < send && n < nstop && fabsf(myring[(t & 1) * 64 + i]) < (float)w.guard) ++unc;
+                        if (n >= sstart && n < send && n < nstop && fabsf(myring[(t & 1) * 64 + i]) < guard_f) ++unc;
                     }
                 }
             }
@@ -352,7 +353,7 @@ __global__ void __launch_bounds__(AX_FD_THREADS, 2) k_demod_fused(const __grid_c
                         yv[4 * k] = v.x; yv[4 * k + 1] = v.y; yv[4 * k + 2] = v.z; yv[4 * k + 3] = v.w;
                     }
                     float m1, m2;
-                    ax_window32(yv, o, NPCM, tab, &m1, &m2);
+                    ax_window32(yv, o, NPCM, sm.tab, &m1, &m2);
                     const int rb = sm.row_begin[r] + 64 * (t - 1);
                     const bool complete = rb + p + NPCM < sm.row_stop[r];
                     if (op < w.seg_cap) {

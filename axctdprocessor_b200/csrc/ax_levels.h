@@ -149,28 +149,37 @@ AX_HDN inline void ax_toneblock_item(const AxWave& w, int64_t tbg) {
 // partial sums of one window over the terms i = lane, lane+nl, ... (ragged-end samples first, then blocks)
 AX_HD void ax_tonewin_partial(const AxWave& w, const AxDrop& dr, const AxCfg& c, int64_t cstart, int lane, int nl, double* a) {
     const int16_t* x = w.pcm + dr.pcm_off;
-    const int64_t cend = cstart + c.n_power;
+    const int np = c.n_power;
+    const int64_t cend = cstart + np;
     int64_t j0 = (cstart + AX_TB - 1) / AX_TB, j1 = cend / AX_TB;       // full blocks j0 .. j1-1
     if (j1 > dr.ntb) j1 = dr.ntb;
     if (j1 < j0) j1 = j0;
-    const int64_t head_n = j0 * AX_TB - cstart;                          // samples before the first full block
-    const int64_t tail0 = j1 * AX_TB;                                    // first sample after the last full block
-    const int64_t tail_n = cend - tail0;
-    for (int q = 0; q < 6; ++q) a[q] = 0.0;
-    for (int64_t i = lane; i < head_n + tail_n; i += nl) {
-        const int64_t n = i < head_n ? cstart + i : tail0 + (i - head_n);
-        const double xd = (double)x[n];
-        const double* t1 = c.tone_soa + (n - cstart);
-        for (int q = 0; q < 6; ++q) a[q] = ax_fma(xd, t1[(int64_t)q * c.n_power], a[q]);
+    const int head_n = (int)(j0 * AX_TB - cstart);                       // samples before the first full block
+    const int tail_off = (int)(j1 * AX_TB - cstart);                     // window offset of the first sample after the last full block
+    const double* t0 = c.tone_soa; const double* t1 = t0 + np; const double* t2 = t1 + np;
+    const double* t3 = t2 + np; const double* t4 = t3 + np; const double* t5 = t4 + np;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, a4 = 0.0, a5 = 0.0;
+    const int16_t* xw = x + cstart;
+    for (int m = lane; m < head_n; m += nl) {
+        const double xd = (double)xw[m];
+        a0 = ax_fma(xd, t0[m], a0); a1 = ax_fma(xd, t1[m], a1); a2 = ax_fma(xd, t2[m], a2);
+        a3 = ax_fma(xd, t3[m], a3); a4 = ax_fma(xd, t4[m], a4); a5 = ax_fma(xd, t5[m], a5);
     }
-    for (int64_t j = j0 + lane; j < j1; j += nl) {
-        const double* B = w.tb_sum + (dr.tb_base + j) * 6;
-        const double* r = c.tone_cs + 6 * (j * AX_TB - cstart);         // e^{j theta_f (AX_TB*j - c)}
-        for (int f = 0; f < 3; ++f) {
-            const double br = B[2 * f], bi = B[2 * f + 1], cr = r[2 * f], sn = r[2 * f + 1];
-            a[2 * f] = ax_fma(br, cr, ax_fma(-bi, sn, a[2 * f]));
-            a[2 * f + 1] = ax_fma(br, sn, ax_fma(bi, cr, a[2 * f + 1]));
-        }
+    for (int m = tail_off + lane; m < np; m += nl) {
+        const double xd = (double)xw[m];
+        a0 = ax_fma(xd, t0[m], a0); a1 = ax_fma(xd, t1[m], a1); a2 = ax_fma(xd, t2[m], a2);
+        a3 = ax_fma(xd, t3[m], a3); a4 = ax_fma(xd, t4[m], a4); a5 = ax_fma(xd, t5[m], a5);
+    }
+    a[0] = a0; a[1] = a1; a[2] = a2; a[3] = a3; a[4] = a4; a[5] = a5;
+    const int nblk = (int)(j1 - j0);
+    const double* B0 = w.tb_sum + (dr.tb_base + j0) * 6;
+    for (int jj = lane; jj < nblk; jj += nl) {
+        const double* B = B0 + 6 * jj;
+        const int m = head_n + jj * AX_TB;                               // e^{j theta_f (AX_TB*j - c)}
+        const double br0 = B[0], bi0 = B[1], br1 = B[2], bi1 = B[3], br2 = B[4], bi2 = B[5];
+        a[0] = ax_fma(br0, t0[m], ax_fma(-bi0, t1[m], a[0])); a[1] = ax_fma(br0, t1[m], ax_fma(bi0, t0[m], a[1]));
+        a[2] = ax_fma(br1, t2[m], ax_fma(-bi1, t3[m], a[2])); a[3] = ax_fma(br1, t3[m], ax_fma(bi1, t2[m], a[3]));
+        a[4] = ax_fma(br2, t4[m], ax_fma(-bi2, t5[m], a[4])); a[5] = ax_fma(br2, t5[m], ax_fma(bi2, t4[m], a[5]));
     }
 }
 AX_HD void ax_tonewin_finish(const AxWave& w, const AxCfg& c, const AxState& st, int64_t slot, const double* a) {
