@@ -67,14 +67,23 @@ def _first_channel(snd):
     raise Exception("Too many dimensions for an audio file!")
 
 
+class RawPCM(np.ndarray):
+    """int16 samples as read from the WAV file.  ``decimate`` = 2 marks a recording above 50 kHz: the
+    engine halves it on the GPU (reference AXCTDprocessor.py:60-62), and ``len()`` / f_s of the
+    processor refer to the halved signal as in the reference."""
+    decimate = 1
+
+
 def readAXCTDwavfile(inputfile, timerange):
     """Reference AXCTDprocessor.py:38-73.  Returns the RAW first-channel int16
-    samples and f_s: normalisation ((x-mean)/max|x|, :55-57) happens on the GPU.
+    samples and f_s: normalisation ((x-mean)/max|x|, :55-57) and the /2 decimation of
+    recordings above 50 kHz (:60-62, f_s becomes the float f_s/2) happen on the GPU.
     As shipped, any positive time bound raises NameError (:65-70)."""
     fs, snd = read_wav_pcm16(inputfile)
-    audiostream = _first_channel(snd)
+    audiostream = _first_channel(snd).view(RawPCM)
     if fs > 50000:                                       # :60-62
-        raise NotImplementedError("recordings above 50 kHz need the /2 decimation path (not built yet)")
+        audiostream.decimate = 2
+        fs /= 2
     if timerange[1] > 0 or timerange[0] > 0:
         raise NameError("name 'self' is not defined")    # :66 / :69
     return audiostream, fs
@@ -127,16 +136,19 @@ class AXCTD_Processor:
         if mode == "wired":
             fs, snd = read_wav_pcm16(audiofile)
             a = _first_channel(snd)
-            if fs > 50000:
-                raise NotImplementedError("recordings above 50 kHz need the /2 decimation path (not built yet)")
             if timerange[1] > 0:
                 a = a[:int(fs * timerange[1])]
             if timerange[0] > 0:
                 a = a[int(fs * timerange[0]):]
-            self.audiostream, self.f_s = np.ascontiguousarray(a), fs
+            a = np.ascontiguousarray(a).view(RawPCM)
+            if fs > 50000:
+                a.decimate = 2
+                fs /= 2
+            self.audiostream, self.f_s = a, fs
         else:
             self.audiostream, self.f_s = readAXCTDwavfile(audiofile, timerange)
-        self.numpoints = len(self.audiostream)
+        self._decimate = int(getattr(self.audiostream, "decimate", 1))
+        self.numpoints = (len(self.audiostream) + 1) // 2 if self._decimate == 2 else len(self.audiostream)
         self.init_default_AXCTD_settings()
         for csetting in user_settings:
             self.settings[csetting] = user_settings[csetting]          # :95-96 (verbatim overlay)
@@ -212,8 +224,8 @@ class AXCTD_Processor:
         self.status = 0
         eng = self._engine or default_engine(self._device)
         cfg = eng.config(self.f_s, settings=self._engine_settings(), triggerrange=self.triggerrange,
-                         temp_lut=np.asarray(self.tempLUT, dtype=np.float64))
-        b = eng.batch([self.numpoints], [cfg])
+                         temp_lut=np.asarray(self.tempLUT, dtype=np.float64), decimate=self._decimate)
+        b = eng.batch([len(self.audiostream)], [cfg])
         try:
             b.upload(0, self.audiostream)
             b.run()

@@ -31,7 +31,10 @@ class ConfigDesc(C.Structure):
         ("tlims", C.c_double * 2), ("slims", C.c_double * 2),
         ("temp_lut", C.POINTER(C.c_double)), ("lut_len", C.c_int32),
         ("hist_edges", C.POINTER(C.c_double)), ("hist_centers", C.POINTER(C.c_double)),
-        ("n_hist_edges", C.c_int32), ("reserved", C.c_int32),
+        ("n_hist_edges", C.c_int32),
+        ("decimate", C.c_int32), ("decim_sections", C.c_int32), ("decim_padlen", C.c_int32),
+        ("decim_sos", (C.c_double * 6) * MAX_SECTIONS), ("decim_zi", (C.c_double * 2) * MAX_SECTIONS),
+        ("decim_pole_radius", C.c_double),
     ]
 
 

@@ -60,7 +60,7 @@ AX_HDN inline void ax_stats_item(const AxWave& w, int64_t slab) {
     const AxDrop& dr = w.drop[d];
     int64_t j = slab - dr.slab_base;
     int64_t a = j * AX_STAT_SLAB, b = a + AX_STAT_SLAB;
-    if (b > dr.n) b = dr.n;
+    if (b > dr.n_raw) b = dr.n_raw;
     const int16_t* x = w.pcm + dr.pcm_off;
     int64_t sum = 0;
     int mx = -32768;
@@ -78,7 +78,7 @@ AX_HDN inline void ax_stats_fin(const AxWave& w, int64_t d) {
     AxState& st = w.st[d];
     // min / max decide np.max(np.abs(x)) unless a sample equals -32768 (then st.ampl holds the exact rescan)
     if (st.vmin != 0x7fffffff && st.vmin > -32768) st.ampl = st.vmax > -st.vmin ? st.vmax : -st.vmin;
-    st.dc = ax_div((double)st.sum, (double)w.drop[d].n);
+    st.dc = ax_div((double)st.sum, (double)w.drop[d].n_raw);
     st.ampl_d = (double)st.ampl;
     st.inv_ampl = ax_div(1.0, st.ampl_d);
 }
@@ -140,13 +140,13 @@ AX_HD void ax_window32(const float* yv, int o, int npcm, const AxF4* tab, float*
 //   G_f[d] = sum_m e^{j theta_f m} h[d - (npcm - 1 - m)]            (host, long double)
 // truncated at the sample q0 where the filter state was zero (the start of the recording or, for
 // the reference's per-chunk restart, the chunk start).  Partial sums over d = lane, lane+nl, ...
-AX_HD void ax_gwin_partial(const int16_t* x, int64_t i, int64_t q0, const AxCfg& c, int lane, int nl, double* acc) {
+AX_HD void ax_gwin_partial(const AxSrc& x, int64_t i, int64_t q0, const AxCfg& c, int lane, int nl, double* acc) {
     const int64_t n_end = i + c.npcm;
     int64_t D = n_end - q0;
     if (D > (int64_t)c.g_len - 1) D = (int64_t)c.g_len - 1;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     for (int64_t d = lane; d <= D; d += nl) {
-        const double xv = (double)x[n_end - d];
+        const double xv = ax_get(x, n_end - d);
         const double* g = c.gtab + 4 * d;
         s0 = ax_fma(xv, g[0], s0); s1 = ax_fma(xv, g[1], s1); s2 = ax_fma(xv, g[2], s2); s3 = ax_fma(xv, g[3], s3);
     }
@@ -291,11 +291,11 @@ AX_HDN inline void ax_filter_segment(const AxWave& w, int64_t seg) {
     const AxCfg& c = w.cfg[dr.cfg];
     AxState& st = w.st[d];
     const AxSegGeom g = ax_seg_geom(dr, c, w.seg_len, j);
-    const int16_t* x = w.pcm + dr.pcm_off;
+    const AxSrc x = ax_src(w, dr);
     const int64_t slot = seg * (int64_t)w.seg_cap;
     AxFilt<NSEC, BUTTER> f;
     f.init(c, st, (int32_t)g.seg_start, (int32_t)g.seg_end, w.guard, w.rec_idx + slot, w.rec_a1 + slot, w.rec_a2 + slot, w.seg_cap);
-    for (int64_t n = g.n_begin; n < g.n_stop; ++n) f.step((int32_t)n, (double)x[n]);
+    for (int64_t n = g.n_begin; n < g.n_stop; ++n) f.step((int32_t)n, ax_get(x, n));
     f.finish();
     if (f.cnt > w.seg_cap) { w.flags[AX_FLAG_CAP] = 1; f.cnt = w.seg_cap; }
     w.seg_cnt[seg] = f.cnt;
@@ -303,6 +303,7 @@ AX_HDN inline void ax_filter_segment(const AxWave& w, int64_t seg) {
 }
 
 AX_HDN inline void ax_filter_item(const AxWave& w, int64_t seg) {
+    if (w.only_xf && w.drop[w.seg_drop[seg]].xf_off < 0) return;      // the fused kernel filtered the int16 drops
     const AxCfg& c = w.cfg[w.drop[w.seg_drop[seg]].cfg];
     const bool bt = ax_sos_is_butter(c);
     if (c.nsec == 3) { if (bt) ax_filter_segment<3, true>(w, seg); else ax_filter_segment<3, false>(w, seg); }
@@ -577,7 +578,7 @@ AX_HDN inline void ax_head_item(const AxWave& w, int64_t cg) {
     const AxCfg& c = w.cfg[dr.cfg];
     AxChunk& ch = w.chunk[cg];
     const int64_t s = ch.s, e = ch.e, len = e - s;
-    const int16_t* x = w.pcm + dr.pcm_off + s;
+    const AxSrc x = ax_src(w, dr);
     const int64_t H = (w.force_exact || c.head > len) ? len : c.head;
     int64_t ny = H + c.npcm + 2;
     if (ny > len) ny = len;
@@ -592,10 +593,10 @@ AX_HDN inline void ax_head_item(const AxWave& w, int64_t cg) {
         double z[AX_MAXSEC][2];
         for (int q = 0; q < AX_MAXSEC; ++q) { z[q][0] = 0.0; z[q][1] = 0.0; }
         for (int64_t n0 = 0; n0 < ny; n0 += 16) {         // samples fetched 16 at a time, ahead of the dependent filter chain
-            int xs[16];
-            for (int i = 0; i < 16; ++i) xs[i] = (n0 + i < ny) ? (int)x[n0 + i] : 0;
+            double xs[16];
+            for (int i = 0; i < 16; ++i) xs[i] = (n0 + i < ny) ? ax_get(x, s + n0 + i) : 0.0;
             for (int i = 0; i < 16 && n0 + i < ny; ++i) {
-                double u = ax_div(ax_sub((double)xs[i], st.dc), st.ampl_d);
+                double u = ax_div(ax_sub(xs[i], st.dc), st.ampl_d);
                 for (int q = 0; q < c.nsec; ++q) u = ax_biquad_exact(u, c.sos[q], z[q][0], z[q][1]);
                 yb[n0 + i] = u;
             }
@@ -709,4 +710,70 @@ AX_HDN inline void ax_verify_item(const AxWave& w, int64_t d) {
     }
     st.chain_from = st.n_chunks;
     st.chain_end = 1;
+}
+
+// ------------------------------------------------------------------ /2 decimation (AXCTDprocessor.py:60-62)
+// scipy.signal.decimate(pcm, 2) = sosfiltfilt(cheby1(8, 0.05, 0.4, 'sos'), pcm)[::2]: odd extension by padlen
+// samples, forward pass from the state zi*ext[0], backward pass over the reversed forward output from
+// zi*(its first value), padding stripped, every second sample kept.  Both passes are cut into segments
+// that start `dwarm` samples early from zero state (the recursion forgets its start like r^n; the very
+// first segment of each pass starts from scipy's exact initial state).
+AX_HD double ax_decim_ext(const AxWave& w, const AxDrop& dr, const AxCfg& c, const AxState& st, int64_t e) {
+    const int16_t* x = w.pcm + dr.pcm_off;
+    const int64_t N = dr.n_raw, P = c.dpad;
+#define AX_U(n) ax_div(ax_sub((double)x[(n)], st.dc), st.ampl_d)
+    if (e < P) return ax_sub(ax_mul(2.0, AX_U(0)), AX_U(P - e));                 // 2 x[0] - x[P-e]
+    if (e < P + N) return AX_U(e - P);
+    return ax_sub(ax_mul(2.0, AX_U(N - 1)), AX_U(N - 2 - (e - P - N)));         // 2 x[N-1] - x[N-2-i]
+#undef AX_U
+}
+AX_HD double ax_decim_step(const AxCfg& c, double u, double (*z)[2]) {
+    for (int q = 0; q < c.dnsec; ++q) {
+        const double* k = c.dsos[q];
+        const double y = ax_fma(k[0], u, z[q][0]);
+        z[q][0] = ax_fma(k[1], u, ax_fma(-k[4], y, z[q][1]));
+        z[q][1] = ax_fma(k[2], u, -(k[5] * y));
+        u = y;
+    }
+    return u;
+}
+// pass 0: forward over the extended recording -> w.fwd; pass 1: backward over w.fwd -> w.xf (even samples)
+AX_HDN inline void ax_decim_item(const AxWave& w, int64_t sg, int pass) {
+    const int d = ax_find_owner(w.drop, w.n_drops, &AxDrop::dseg_base, sg);
+    const AxDrop& dr = w.drop[d];
+    const int64_t j = sg - dr.dseg_base;
+    if (dr.xf_off < 0 || j >= dr.ndseg) return;
+    const AxCfg& c = w.cfg[dr.cfg];
+    const AxState& st = w.st[d];
+    const int64_t E = dr.n_raw + 2 * (int64_t)c.dpad;
+    const int64_t e0 = j * w.dseg_len;
+    int64_t e1 = e0 + w.dseg_len; if (e1 > E) e1 = E;
+    int64_t start = e0 - c.dwarm; if (start < 0) start = 0;
+    double* fwd = w.fwd + dr.fwd_off;
+    double z[AX_MAXSEC][2];
+    for (int q = 0; q < AX_MAXSEC; ++q) { z[q][0] = 0.0; z[q][1] = 0.0; }
+    if (start == 0) {
+        const double x0 = pass == 0 ? ax_decim_ext(w, dr, c, st, 0) : fwd[E - 1];
+        for (int q = 0; q < c.dnsec; ++q) { z[q][0] = ax_mul(c.dzi[q][0], x0); z[q][1] = ax_mul(c.dzi[q][1], x0); }
+    }
+    if (pass == 0) {
+        for (int64_t e = start; e < e1; ++e) {
+            const double y = ax_decim_step(c, ax_decim_ext(w, dr, c, st, e), z);
+            if (e >= e0) fwd[e] = y;
+        }
+    } else {
+        double* xf = w.xf + dr.xf_off;
+        for (int64_t e = start; e < e1; ++e) {
+            const double y = ax_decim_step(c, fwd[E - 1 - e], z);
+            const int64_t m = (E - 1 - e) - c.dpad;                   // index in the unpadded recording
+            if (e >= e0 && m >= 0 && m < dr.n_raw && (m & 1) == 0) xf[m >> 1] = y;
+        }
+    }
+}
+// downstream kernels see an already normalised signal
+AX_HDN inline void ax_decim_fin(const AxWave& w, int64_t d) {
+    if (w.drop[d].xf_off < 0) return;
+    AxState& st = w.st[d];
+    st.dc_raw = st.dc; st.ampl_raw = st.ampl_d;
+    st.dc = 0.0; st.inv_ampl = 1.0; st.ampl_d = 1.0;
 }

@@ -98,6 +98,8 @@ AX_GLOBAL void k_frames_write(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_frames_wr
 AX_GLOBAL void k_calib(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_calib_item(w, item); }
 AX_GLOBAL void k_synth(int64_t n, AxSynth g) { AX_FOR_ITEM(n) ax_synth_item(g, item); }
 AX_GLOBAL void k_qc(int64_t n, AxWave w, double* scratch) { AX_FOR_ITEM(n) ax_qc_item(w, item, scratch); }
+AX_GLOBAL void k_decim(int64_t n, AxWave w, int pass) { AX_FOR_ITEM(n) ax_decim_item(w, item, pass); }
+AX_GLOBAL void k_decim_fin(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_decim_fin(w, item); }
 AX_GLOBAL void k_rows(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_row_item(w, item); }
 AX_GLOBAL void k_chunkout(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_chunkout_item(w, item); }
 
@@ -165,7 +167,7 @@ struct axctd_batch {
     AxWave w;
     int16_t* d_pcm = nullptr;
     double* d_qc = nullptr;
-    int64_t tb_total = 0;
+    int64_t tb_total = 0, dseg_total = 0;
     int64_t pcm_total = 0, chunk_total = 0, edge_total = 0, frame_total = 0, zc_total = 0, tile_total = 0;
     // host mirrors of the results (pinned: the result download is part of every step)
     std::vector<AxState> st;
@@ -317,6 +319,18 @@ extern "C" int axctd_config_create(axctd_engine* e, const axctd_config_desc* ds,
     c.ybuf_len = c.head + c.npcm + 2;
     const int64_t G = ax_gcd(c.n_power, c.d_pcm);
     c.tone_G = (int)G; c.tone_nb = (int)(c.n_power / G); c.tone_stride = (int)(c.d_pcm / G);
+    c.decimate = ds->decimate == 2 ? 2 : 1;
+    if (c.decimate == 2) {
+        if (ds->decim_sections < 1 || ds->decim_sections > AX_MAXSEC || ds->decim_padlen < 1 ||
+            !(ds->decim_pole_radius > 0.0 && ds->decim_pole_radius < 1.0)) { e->err = "bad decimator description"; return AXCTD_ERR_ARG; }
+        c.dnsec = ds->decim_sections; c.dpad = ds->decim_padlen;
+        int dw = (int)ceil(log(1e-19) / log(ds->decim_pole_radius));
+        c.dwarm = ((dw + 63) / 64) * 64;
+        for (int q = 0; q < c.dnsec; ++q) {
+            for (int i = 0; i < 6; ++i) c.dsos[q][i] = ds->decim_sos[q][i];
+            c.dzi[q][0] = ds->decim_zi[q][0]; c.dzi[q][1] = ds->decim_zi[q][1];
+        }
+    }
     AxToneTab ttab;
     memset(&ttab, 0, sizeof(ttab));
     {
@@ -449,18 +463,30 @@ extern "C" int axctd_batch_create(axctd_engine* e, int n_drops, const int64_t* n
     w.bit_tol = e->opt_bit_tol; w.hist_tol = e->opt_hist_tol; w.bitfix_all = e->opt_bitfix_all;
     w.head_zc_cap_max = head_cap_max; w.ybuf_len_max = ybuf_max;
     b->drops.resize(n_drops);
-    int64_t pcm_off = 0, zc_off = 0, edge_off = 0, tb_off = 0;
-    int32_t ntb_max = 0;
+    int64_t pcm_off = 0, zc_off = 0, edge_off = 0, tb_off = 0, xf_off = 0, fwd_off = 0;
+    int32_t ntb_max = 0, dseg_off = 0;
+    const int64_t DL = 8192;                       // samples per decimation segment
+    w.dseg_len = (int32_t)DL;
     int32_t seg_off = 0, slab_off = 0, tile_off = 0, chunk_off = 0, pw_off = 0, frame_off = 0;
     for (int d = 0; d < n_drops; ++d) {
         const AxCfg& c = e->cfgs[config_id[d]];
         AxDrop& dr = b->drops[d];
-        const int64_t n = n_samples[d];
-        dr.pcm_off = pcm_off; dr.n = n; dr.cfg = config_id[d];
-        pcm_off += ((n + 63) / 64) * 64 + 64;
+        const int64_t n_raw = n_samples[d];
+        const bool dec = c.decimate == 2;
+        const int64_t n = dec ? (n_raw + 1) / 2 : n_raw;              // len(y[::2])
+        dr.pcm_off = pcm_off; dr.n = n; dr.n_raw = n_raw; dr.cfg = config_id[d];
+        pcm_off += ((n_raw + 63) / 64) * 64 + 64;
+        dr.xf_off = -1; dr.fwd_off = -1; dr.dseg_base = dseg_off; dr.ndseg = 0;
+        if (dec) {
+            if (n_raw < 2 * (int64_t)c.dpad + 2) { e->err = "recording too short to decimate"; axctd_batch_destroy(b); return AXCTD_ERR_ARG; }
+            const int64_t E = n_raw + 2 * (int64_t)c.dpad;
+            dr.xf_off = xf_off; xf_off += ((n + 63) / 64) * 64 + 64;
+            dr.fwd_off = fwd_off; fwd_off += E + 8;
+            dr.ndseg = (int32_t)((E + DL - 1) / DL); dseg_off += dr.ndseg;
+        }
         dr.seg_base = seg_off; dr.nseg = (int32_t)((n + L - 1) / L); seg_off += ((dr.nseg + 127) / 128) * 128;
-        dr.slab_base = slab_off; dr.nslab = (int32_t)((n + AX_STAT_SLAB - 1) / AX_STAT_SLAB); slab_off += dr.nslab;
-        dr.tb_base = tb_off; dr.ntb = (int32_t)(n / AX_TB); tb_off += dr.ntb; ntb_max = std::max(ntb_max, (int32_t)((n + AX_TB - 1) / AX_TB));
+        dr.slab_base = slab_off; dr.nslab = (int32_t)((n_raw + AX_STAT_SLAB - 1) / AX_STAT_SLAB); slab_off += dr.nslab;
+        dr.tb_base = tb_off; dr.ntb = (int32_t)(n / AX_TB); tb_off += dr.ntb; ntb_max = std::max(ntb_max, (int32_t)((n_raw + AX_TB - 1) / AX_TB));
         dr.zc_base = zc_off; dr.zc_cap = n / e->opt_zc_div + 4096; zc_off += dr.zc_cap + 8;
         dr.tile_base = tile_off; dr.tile_cap = (int32_t)(dr.zc_cap / AX_TILE + 1); tile_off += dr.tile_cap;
         dr.chunk_base = chunk_off; dr.chunk_cap = (int32_t)(2 * (n / c.chunk_len) + 16); chunk_off += dr.chunk_cap;
@@ -471,7 +497,7 @@ extern "C" int axctd_batch_create(axctd_engine* e, int n_drops, const int64_t* n
     b->pcm_total = pcm_off; b->zc_total = zc_off; b->tile_total = tile_off; b->chunk_total = chunk_off;
     b->edge_total = edge_off; b->frame_total = frame_off;
     w.nseg_total = seg_off; w.nslab_total = slab_off; w.pw_total = pw_off; w.ntb_max = ntb_max;
-    b->tb_total = tb_off;
+    b->tb_total = tb_off; b->dseg_total = dseg_off;
     std::vector<int32_t> seg_drop(seg_off), slab_drop(slab_off);
     for (int d = 0; d < n_drops; ++d) {
         for (int s = 0; s < ((b->drops[d].nseg + 127) / 128) * 128; ++s) seg_drop[b->drops[d].seg_base + s] = d;
@@ -484,6 +510,8 @@ extern "C" int axctd_batch_create(axctd_engine* e, int n_drops, const int64_t* n
     bad |= ax_alloc_arr(b, &b->d_pcm, pcm_off + 64);
     bad |= ax_alloc_arr(b, &d_seg_drop, seg_off);
     bad |= ax_alloc_arr(b, &d_slab_drop, slab_off);
+    bad |= ax_alloc_arr(b, &w.xf, xf_off + 8);
+    bad |= ax_alloc_arr(b, &w.fwd, fwd_off + 8);
     bad |= ax_alloc_arr(b, &w.seg_cnt, seg_off);
     bad |= ax_alloc_arr(b, &w.seg_off, seg_off);
     bad |= ax_alloc_arr(b, &w.blk_sum, seg_off / 128 + 1);
@@ -509,6 +537,8 @@ extern "C" int axctd_batch_create(axctd_engine* e, int n_drops, const int64_t* n
     bad |= ax_alloc_arr(b, &w.r400, pw_off);
     bad |= ax_alloc_arr(b, &w.r7500, pw_off);
     bad |= ax_alloc_arr(b, &w.pw_ind, pw_off);
+    bad |= ax_alloc_arr(b, &w.tone_rng, 2 * (int64_t)n_drops);
+    bad |= ax_alloc_arr(b, &w.tone_acc, 6 * (int64_t)pw_off);
     bad |= ax_alloc_arr(b, &w.tb_sum, tb_off * 6 + 8);
     bad |= ax_alloc_arr(b, &w.edge_idx, edge_off);
     bad |= ax_alloc_arr(b, &w.lvl400, edge_off);
@@ -543,7 +573,7 @@ extern "C" int axctd_batch_create(axctd_engine* e, int n_drops, const int64_t* n
 }
 
 extern "C" int axctd_batch_upload(axctd_batch* b, int drop, const int16_t* pcm, int64_t n) {
-    if (!b || drop < 0 || drop >= b->n || !pcm || n != b->drops[drop].n) return AXCTD_ERR_ARG;
+    if (!b || drop < 0 || drop >= b->n || !pcm || n != b->drops[drop].n_raw) return AXCTD_ERR_ARG;
     if (ax_h2d(b->eng, b->d_pcm + b->drops[drop].pcm_off, pcm, sizeof(int16_t) * n)) return AXCTD_ERR_CUDA;
     b->ran = false;
     return AXCTD_OK;
@@ -646,8 +676,10 @@ static int ax_run_tones(axctd_batch* b, int phase_b) {
                 }
             }
             if (i_hi > i_lo) {
-                k_tone_windows<<<dim3((unsigned)(((int64_t)(i_hi - i_lo) * 32 + 255) / 256), (unsigned)b->n), 256, 0, e->stream>>>(w, phase_b, i_lo, i_hi);
-                e->launches++;
+                k_tone_range<<<(b->n + 127) / 128, 128, 0, e->stream>>>(w, phase_b);
+                k_tone_windows<<<dim3((unsigned)(((int64_t)(i_hi - i_lo) * 32 + 255) / 256), (unsigned)b->n), 256, 0, e->stream>>>(w, i_lo, i_hi);
+                k_tone_mag<<<dim3((unsigned)((i_hi - i_lo + 127) / 128), (unsigned)b->n), 128, 0, e->stream>>>(w, i_lo, i_hi);
+                e->launches += 3;
             }
         }
 #else
@@ -684,9 +716,22 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
     }
 #else
     AX_LAUNCH(e, k_stats, (int64_t)w.nslab_total, w);
-    AX_LAUNCH(e, k_toneblock, b->tb_total, w);
 #endif
     AX_LAUNCH(e, k_stats_fin, n, w);
+    const bool any_dec = b->dseg_total > 0;
+    if (any_dec) {       // recordings above 50 kHz: halve them on the device (AXCTDprocessor.py:60-62)
+        AX_LAUNCH(e, k_decim, b->dseg_total, w, 0);
+        AX_LAUNCH(e, k_decim, b->dseg_total, w, 1);
+        AX_LAUNCH(e, k_decim_fin, n, w);
+#ifndef AXCTD_EMU
+        w.only_xf = 1;
+        AX_LAUNCH(e, k_toneblock, b->tb_total, w);
+        w.only_xf = 0;
+#endif
+    }
+#ifdef AXCTD_EMU
+    AX_LAUNCH(e, k_toneblock, b->tb_total, w);
+#endif
     AX_EVENT(b, 1);
 #ifndef AXCTD_EMU
     bool fused = e->opt_filter_variant == 0;
@@ -699,6 +744,7 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
     if (fused) {
         // one launch per rate class in use (CTAs of the other classes exit at once)
         for (int ci : used_cfg) { ax_launch_demod_fused_any(w, e->cfgs[ci], ci, e->stream); e->launches++; }
+        if (any_dec) { w.only_xf = 1; AX_LAUNCH(e, k_filter, (int64_t)w.nseg_total, w); w.only_xf = 0; }
     } else
 #endif
     { AX_LAUNCH(e, k_filter, (int64_t)w.nseg_total, w); }
@@ -936,7 +982,7 @@ extern "C" int64_t axctd_batch_power(axctd_batch* b, int drop, int64_t* power_in
 
 // ============================================================ bench / test tooling
 extern "C" int axctd_synth_fill(axctd_batch* b, int drop, const axctd_synth_desc* ds) {
-    if (!b || !ds || drop < 0 || drop >= b->n || ds->n_total != b->drops[drop].n || !ds->bits || !ds->gate || !ds->parity) return AXCTD_ERR_ARG;
+    if (!b || !ds || drop < 0 || drop >= b->n || ds->n_total != b->drops[drop].n_raw || !ds->bits || !ds->gate || !ds->parity) return AXCTD_ERR_ARG;
     axctd_engine* e = b->eng;
     AxSynth g;
     g.n_total = ds->n_total; g.n0 = ds->n0; g.tone_start = ds->tone_start; g.fs = ds->fs;
@@ -958,7 +1004,7 @@ extern "C" int axctd_synth_fill(axctd_batch* b, int drop, const axctd_synth_desc
 }
 
 extern "C" int axctd_batch_download(axctd_batch* b, int drop, int16_t* pcm, int64_t n) {
-    if (!b || drop < 0 || drop >= b->n || !pcm || n != b->drops[drop].n) return AXCTD_ERR_ARG;
+    if (!b || drop < 0 || drop >= b->n || !pcm || n != b->drops[drop].n_raw) return AXCTD_ERR_ARG;
     if (ax_d2h(b->eng, pcm, b->d_pcm + b->drops[drop].pcm_off, sizeof(int16_t) * n) || ax_sync(b->eng)) return AXCTD_ERR_CUDA;
     return AXCTD_OK;
 }

@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(256) k_stats_wrap(AxWave w) {
     const int64_t j = slab - dr.slab_base;
     const int64_t a = j * AX_STAT_SLAB;
     int64_t b = a + AX_STAT_SLAB;
-    if (b > dr.n) b = dr.n;
+    if (b > dr.n_raw) b = dr.n_raw;
     const int16_t* x = w.pcm + dr.pcm_off + a;
     int mx = -32768;
     for (int t = threadIdx.x; t < (int)(b - a); t += blockDim.x) {
@@ -52,14 +52,15 @@ __global__ void __launch_bounds__(AX_ST_THREADS) k_stats_tones(const __grid_cons
     const int d = blockIdx.y;
     const AxDrop& dr = w.drop[d];
     if (dr.cfg != cfg_id) return;
-    const int64_t nblk = (dr.n + AX_TB - 1) / AX_TB;
+    const int64_t nsamp = dr.n_raw;                  // statistics are taken over the recording as uploaded
+    const int64_t nblk = (nsamp + AX_TB - 1) / AX_TB;
     if ((int64_t)blockIdx.x * AX_ST_THREADS >= nblk) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int16_t (*stage)[32 * 72] = stage_all[warp];
     const int64_t jb = (int64_t)blockIdx.x * AX_ST_THREADS + threadIdx.x;
     const bool active = jb < nblk;
     const int64_t n0 = jb * AX_TB;
-    const int T = active ? (int)min((int64_t)4, (dr.n - n0 + 63) >> 6) : 0;
+    const int T = active ? (int)min((int64_t)4, (nsamp - n0 + 63) >> 6) : 0;
     const unsigned long long xrow = (unsigned long long)(w.pcm + dr.pcm_off + n0);
     const int prow = lane >> 3, piece = lane & 7;
     unsigned long long src[8];
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(AX_ST_THREADS) k_stats_tones(const __grid_cons
         __syncwarp();
         if (r < T) {
             const int4* rp = reinterpret_cast<const int4*>(&stage[r & 1][lane * 72]);
-            const int nvalid = (int)min((int64_t)64, dr.n - (n0 + 64 * r));
+            const int nvalid = (int)min((int64_t)64, nsamp - (n0 + 64 * r));
             if (nvalid == 64) {
                 int s32 = 0;
 #pragma unroll
@@ -121,7 +122,7 @@ __global__ void __launch_bounds__(AX_ST_THREADS) k_stats_tones(const __grid_cons
         }
         __syncwarp();
     }
-    if (active && jb < dr.ntb) {
+    if (active && jb < dr.ntb && dr.xf_off < 0) {      // (a decimating drop takes its block sums from the halved signal)
         double* out = w.tb_sum + (dr.tb_base + jb) * 6;
 #pragma unroll
         for (int q6 = 0; q6 < 6; ++q6) out[q6] = acc[q6];
@@ -140,37 +141,65 @@ __global__ void __launch_bounds__(AX_ST_THREADS) k_stats_tones(const __grid_cons
     }
 }
 
-// One warp per power sample: ragged ends + block sums (ax_tonewin_partial), then the magnitudes.
-// grid = (warps over the per-drop power-sample range [i_lo, i_hi), drop)
-__global__ void __launch_bounds__(256) k_tone_windows(AxWave w, int phase_b, int i_lo, int i_hi) {
-    const int d = blockIdx.y;
+// ------------------------------------------------------------------ tone window magnitudes
+// Per-drop power-sample range [lo, hi) of a tone launch (the range test of ax_tone_slot_active, once per drop).
+__global__ void k_tone_range(AxWave w, int phase_b) {
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= w.n_drops) return;
     const AxDrop& dr = w.drop[d];
     const AxState& st = w.st[d];
-    if (st.status >= AXCTD_DROP_CAPACITY) return;
-    const AxCfg& c = w.cfg[dr.cfg];
-    if (!ax_tone_blocked_ok(c)) return;
-    const int32_t i = i_lo + (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    if (i >= i_hi || i >= dr.pw_cap) return;
-    const AxChunk* ch = w.chunk + dr.chunk_base;
-    int32_t lo, hi;
-    if (!phase_b) {
-        const int ka = w.pa_lo, kb = w.pa_hi < st.n_fixed ? w.pa_hi : st.n_fixed;
-        if (!st.searching || kb <= ka) return;
-        lo = ch[ka].pw_off; hi = ch[kb - 1].pw_off + ch[kb - 1].np;
-    } else {
-        if (st.sm_status < 1 || st.n_chunks <= st.k0 + 1) return;
-        lo = ch[st.k0].pw_off + ch[st.k0].np; hi = ch[st.n_chunks - 1].pw_off + ch[st.n_chunks - 1].np;
+    int32_t lo = 0, hi = 0;
+    if (st.status < AXCTD_DROP_CAPACITY && ax_tone_blocked_ok(w.cfg[dr.cfg])) {
+        const AxChunk* ch = w.chunk + dr.chunk_base;
+        if (!phase_b) {
+            const int ka = w.pa_lo, kb = w.pa_hi < st.n_fixed ? w.pa_hi : st.n_fixed;
+            if (st.searching && kb > ka) { lo = ch[ka].pw_off; hi = ch[kb - 1].pw_off + ch[kb - 1].np; }
+        } else if (st.sm_status >= 1 && st.n_chunks > st.k0 + 1) {
+            lo = ch[st.k0].pw_off + ch[st.k0].np; hi = ch[st.n_chunks - 1].pw_off + ch[st.n_chunks - 1].np;
+        }
     }
-    if (i < lo || i >= hi) return;
+    w.tone_rng[2 * d] = lo; w.tone_rng[2 * d + 1] = hi;
+}
+
+__device__ __forceinline__ void ax_warp_sum6(double* a, int lane) {
+    // after this call lane 0 holds the sums of components 0..2 in a[0..2], lane 16 those of 3..5 in a[0..2]
+    const bool hi = lane >= 16;
+    double keep[3], send[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) { keep[q] = hi ? a[3 + q] : a[q]; send[q] = hi ? a[q] : a[3 + q]; }
+#pragma unroll
+    for (int q = 0; q < 3; ++q) keep[q] += __shfl_xor_sync(0xffffffffu, send[q], 16);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) keep[q] += __shfl_xor_sync(0xffffffffu, keep[q], o);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) a[q] = keep[q];
+}
+
+// One warp per power sample: ragged ends + block sums (ax_tonewin_partial); the six sums go to tone_acc and
+// k_tone_mag turns them into magnitudes with one thread per power sample.
+// grid = (warps over the per-drop power-sample range [i_lo, i_hi), drop)
+__global__ void __launch_bounds__(256) k_tone_windows(AxWave w, int i_lo, int i_hi) {
+    const int d = blockIdx.y;
+    const int32_t i = i_lo + (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (i >= i_hi || i < w.tone_rng[2 * d] || i >= w.tone_rng[2 * d + 1]) return;
+    const AxDrop& dr = w.drop[d];
+    const AxCfg& c = w.cfg[dr.cfg];
     const int lane = threadIdx.x & 31;
     const int64_t slot = (int64_t)dr.pw_base + i;
     double a[6];
     ax_tonewin_partial(w, dr, c, w.pw_ind[slot], lane, 32, a);
-#pragma unroll
-    for (int q = 0; q < 6; ++q)
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) a[q] += __shfl_xor_sync(0xffffffffu, a[q], o);
-    if (lane == 0) ax_tonewin_finish(w, c, st, slot, a);
+    ax_warp_sum6(a, lane);
+    if ((lane & 15) == 0) { double* o = w.tone_acc + slot * 6 + (lane ? 3 : 0); o[0] = a[0]; o[1] = a[1]; o[2] = a[2]; }
+}
+__global__ void __launch_bounds__(128) k_tone_mag(AxWave w, int i_lo, int i_hi) {
+    const int d = blockIdx.y;
+    const int32_t i = i_lo + (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (i >= i_hi || i < w.tone_rng[2 * d] || i >= w.tone_rng[2 * d + 1]) return;
+    const AxDrop& dr = w.drop[d];
+    const int64_t slot = (int64_t)dr.pw_base + i;
+    ax_tonewin_finish(w, w.cfg[dr.cfg], w.st[d], slot, w.tone_acc + slot * 6);
 }
 
 // ------------------------------------------------------------------ fused demodulation pass
@@ -210,7 +239,7 @@ __global__ void __launch_bounds__(AX_FD_THREADS, 2) k_demod_fused(const __grid_c
     extern __shared__ __align__(16) unsigned char ax_smem_raw[];
     const int d = w.seg_drop[(int64_t)blockIdx.x * AX_FD_THREADS];
     const AxDrop& dr = w.drop[d];
-    if (dr.cfg != cfg_id) return;                       // another launch handles this rate class
+    if (dr.cfg != cfg_id || dr.xf_off >= 0) return;     // another launch handles this rate class / the generic kernel the halved signals
     const AxCfg& c = w.cfg[cfg_id];
     AxState& st = w.st[d];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -431,7 +460,7 @@ __global__ void __launch_bounds__(128) k_bits_chunk(AxWave w, int phase) {
             f.i = __shfl_sync(0xffffffffu, fx.i, L);
             f.q0 = __shfl_sync(0xffffffffu, fx.q0, L);
             double acc[4];
-            ax_gwin_partial(w.pcm + dr.pcm_off, f.i, f.q0, w.cfg[dr.cfg], lane, 32, acc);
+            ax_gwin_partial(ax_src(w, dr), f.i, f.q0, w.cfg[dr.cfg], lane, 32, acc);
 #pragma unroll
             for (int q = 0; q < 4; ++q)
 #pragma unroll

@@ -111,11 +111,12 @@ AX_HDN inline void ax_tone_direct_item(const AxWave& w, int64_t slot, int phase_
     const AxState& st = w.st[d];
     const AxCfg& c = w.cfg[dr.cfg];
     if ((phase_flags & 2) && ax_tone_blocked_ok(c)) return;      // already done by the blocked path
-    const int16_t* x = w.pcm + dr.pcm_off + w.pw_ind[slot];
+    const AxSrc x = ax_src(w, dr);
+    const int64_t c0 = w.pw_ind[slot];
     const double kmul = st.inv_ampl, kadd = -(st.dc * st.inv_ampl);
     double a[6] = {0, 0, 0, 0, 0, 0};
     for (int m = 0; m < c.n_power; ++m) {
-        const double u = ax_fma((double)x[m], kmul, kadd);
+        const double u = ax_fma(ax_get(x, c0 + m), kmul, kadd);
         const double* t6 = c.tone_cs + 6 * (int64_t)m;
         for (int q = 0; q < 6; ++q) a[q] = ax_fma(u, t6[q], a[q]);
     }
@@ -134,12 +135,12 @@ AX_HDN inline void ax_toneblock_item(const AxWave& w, int64_t tbg) {
     const int d = ax_find_owner(w.drop, w.n_drops, &AxDrop::tb_base, tbg);
     const AxDrop& dr = w.drop[d];
     const int64_t j = tbg - dr.tb_base;
-    if (j >= dr.ntb) return;
+    if (j >= dr.ntb || (w.only_xf && dr.xf_off < 0)) return;       // (k_stats_tones already did the int16 drops)
     const AxCfg& c = w.cfg[dr.cfg];
-    const int16_t* x = w.pcm + dr.pcm_off + j * AX_TB;
+    const AxSrc x = ax_src(w, dr);
     double a[6] = {0, 0, 0, 0, 0, 0};
     for (int m = 0; m < AX_TB; ++m) {
-        const double xd = (double)x[m];
+        const double xd = ax_get(x, j * AX_TB + m);
         const double* t6 = c.tone_cs + 6 * (int64_t)m;
         for (int q = 0; q < 6; ++q) a[q] = ax_fma(xd, t6[q], a[q]);
     }
@@ -148,7 +149,7 @@ AX_HDN inline void ax_toneblock_item(const AxWave& w, int64_t tbg) {
 
 // partial sums of one window over the terms i = lane, lane+nl, ... (ragged-end samples first, then blocks)
 AX_HD void ax_tonewin_partial(const AxWave& w, const AxDrop& dr, const AxCfg& c, int64_t cstart, int lane, int nl, double* a) {
-    const int16_t* x = w.pcm + dr.pcm_off;
+    const AxSrc x = ax_src(w, dr);
     const int np = c.n_power;
     const int64_t cend = cstart + np;
     int64_t j0 = (cstart + AX_TB - 1) / AX_TB, j1 = cend / AX_TB;       // full blocks j0 .. j1-1
@@ -159,14 +160,13 @@ AX_HD void ax_tonewin_partial(const AxWave& w, const AxDrop& dr, const AxCfg& c,
     const double* t0 = c.tone_soa; const double* t1 = t0 + np; const double* t2 = t1 + np;
     const double* t3 = t2 + np; const double* t4 = t3 + np; const double* t5 = t4 + np;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, a4 = 0.0, a5 = 0.0;
-    const int16_t* xw = x + cstart;
     for (int m = lane; m < head_n; m += nl) {
-        const double xd = (double)xw[m];
+        const double xd = ax_get(x, cstart + m);
         a0 = ax_fma(xd, t0[m], a0); a1 = ax_fma(xd, t1[m], a1); a2 = ax_fma(xd, t2[m], a2);
         a3 = ax_fma(xd, t3[m], a3); a4 = ax_fma(xd, t4[m], a4); a5 = ax_fma(xd, t5[m], a5);
     }
     for (int m = tail_off + lane; m < np; m += nl) {
-        const double xd = (double)xw[m];
+        const double xd = ax_get(x, cstart + m);
         a0 = ax_fma(xd, t0[m], a0); a1 = ax_fma(xd, t1[m], a1); a2 = ax_fma(xd, t2[m], a2);
         a3 = ax_fma(xd, t3[m], a3); a4 = ax_fma(xd, t4[m], a4); a5 = ax_fma(xd, t5[m], a5);
     }
@@ -655,7 +655,7 @@ AX_HDN inline void ax_bits_item(const AxWave& w, int64_t slot, int phase) {
     if (ax_bits_need(w, d, k, slot, phase, &fx)) {
         const AxDrop& dr = w.drop[fx.d];
         double acc[4];
-        ax_gwin_partial(w.pcm + dr.pcm_off, fx.i, fx.q0, w.cfg[dr.cfg], 0, 1, acc);
+        ax_gwin_partial(ax_src(w, dr), fx.i, fx.q0, w.cfg[dr.cfg], 0, 1, acc);
         ax_bits_fix(w, slot, fx, acc);
     }
     if (phase == 1) ax_bits_decide(w, d, slot);

@@ -91,11 +91,17 @@ struct AxCfg {
     int32_t g_len, pad_g;
     int32_t lut_len, n_hist_edges;
     double tone_tsum[6];         // sum over the whole window of tone_cs (response to the constant -dc/ampl term)
+    // /2 decimation (AXCTDprocessor.py:60-62): forward-backward Chebyshev SOS with odd padding
+    int32_t decimate, dnsec, dpad, dwarm;
+    double dsos[AX_MAXSEC][6], dzi[AX_MAXSEC][2];
     AxWinTab win_tab;
 };
 
 struct AxDrop {
-    int64_t pcm_off, n;          // sample offset into the batch PCM buffer, sample count
+    int64_t pcm_off, n;          // sample offset into the batch PCM buffer, sample count (after any decimation)
+    int64_t n_raw;               // samples of the recording as uploaded
+    int64_t xf_off, fwd_off;     // decimating drops: offsets of the halved signal / forward-pass scratch (doubles), else -1
+    int32_t dseg_base, ndseg;    // segments of the two decimation passes
     int32_t cfg;
     int32_t seg_base, nseg;      // segments of the continuous filter pass
     int32_t slab_base, nslab;    // stats work items
@@ -143,6 +149,7 @@ struct AxState {
     int32_t n_recheck;           // bit windows re-evaluated in double precision (ax_gwin_*)
     int32_t err32_bits;          // max relative |a32 - a64| / a64 seen at re-evaluated windows (float bits)
     double dc, inv_ampl, ampl_d;
+    double dc_raw, ampl_raw;     // decimating drops: statistics of the raw recording (dc / ampl above become 0 / 1)
     int64_t zc_count;
     // state machine
     int32_t sm_status;           // self.status
@@ -181,6 +188,8 @@ struct AxWave {
     const AxDrop* drop;
     AxState* st;
     const int16_t* pcm;
+    double* xf; double* fwd;     // decimated recordings (already normalised) and the forward-pass scratch
+    int32_t dseg_len, only_xf;   // decimation segment length; only_xf: generic sample-stream kernels skip int16 drops
     // continuous filter pass
     int32_t seg_len, seg_cap, nseg_total, nslab_total;
     const int32_t* seg_drop;     // segment -> drop
@@ -201,6 +210,8 @@ struct AxWave {
     double* pw_sm;               // [3][pw_total]
     double* r400; double* r7500; // [pw_total]
     int64_t* pw_ind;             // [pw_total] power_inds
+    int32_t* tone_rng;           // [n_drops][2] power-sample range the current tone launch evaluates (k_tone_range)
+    double* tone_acc;            // [pw_total][6] window sums before normalisation (k_tone_windows -> k_tone_mag)
     int32_t pw_total;
     double* tb_sum;              // [tb_total][6] raw-sample tone sums of every aligned block of AX_TB samples
     int32_t ntb_max, pad1;
@@ -225,7 +236,18 @@ struct AxWave {
 
 // cos, sin of theta400, theta7500, thetadead for the AX_TB taps of a tone block (kernel parameter of k_stats_tones)
 struct AxToneTab { double t[AX_TB][6]; };
+// the samples of one drop: int16 as uploaded, or the halved double-precision signal
+struct AxSrc { const int16_t* x; const double* xf; };
+AX_HD double ax_get(const AxSrc& s, int64_t n) { return s.xf ? s.xf[n] : (double)s.x[n]; }
+
 AX_HD bool ax_tone_blocked_ok(const AxCfg& c) { return c.n_power >= 2 * AX_TB; }
+
+AX_HD AxSrc ax_src(const AxWave& w, const AxDrop& dr) {
+    AxSrc s;
+    s.x = w.pcm + dr.pcm_off;
+    s.xf = dr.xf_off >= 0 ? w.xf + dr.xf_off : nullptr;
+    return s;
+}
 
 #define AX_FLAG_DIRTY 0
 #define AX_FLAG_CAP 1

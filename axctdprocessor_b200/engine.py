@@ -66,13 +66,14 @@ class RateConfig:
     desc: _lib.ConfigDesc = None
     keep: list = field(default_factory=list)
     config_id: int = -1
+    decimate: int = 1            # 2: the recording is above 50 kHz and is halved on the device (fs is already f_s/2)
 
     def key(self):
         s = self.settings
         return (float(self.fs), float(s["minr400"]), float(s["mindr7500"]), float(s["deadfreq"]),
                 tuple(float(x) for x in s["mark_space_freqs"]), bool(s["usebandpass"]), float(s["refreshrate"]),
                 tuple(self.triggerrange), tuple(s["zcoeff_axctd"]), tuple(s["tcoeff_axctd"]), tuple(s["ccoeff_axctd"]),
-                tuple(s["tlims_axctd"]), tuple(s["slims_axctd"]), self.temp_lut.tobytes())
+                tuple(s["tlims_axctd"]), tuple(s["slims_axctd"]), self.temp_lut.tobytes(), int(self.decimate))
 
     def build(self):
         f_s, st = self.fs, self.settings
@@ -121,6 +122,18 @@ class RateConfig:
             d.tlims[i] = float(st["tlims_axctd"][i]); d.slims[i] = float(st["slims_axctd"][i])
         d.temp_lut, d.lut_len = _dptr(lut), len(lut)
         d.hist_edges, d.hist_centers, d.n_hist_edges = _dptr(edges), _dptr(centers), len(edges)
+        d.decimate = int(self.decimate)
+        if self.decimate == 2:                                           # AXCTDprocessor.py:60-62 -> scipy.signal.decimate(pcm, 2)
+            dsos = np.ascontiguousarray(signal.cheby1(8, 0.05, 0.8 / 2, output="sos"), dtype=np.float64)
+            dzi = signal.sosfilt_zi(dsos)
+            d.decim_sections = dsos.shape[0]
+            ntheta = 2 * dsos.shape[0] + 1 - min((dsos[:, 2] == 0).sum(), (dsos[:, 5] == 0).sum())
+            d.decim_padlen = int(3 * ntheta)                             # sosfiltfilt's default padlen
+            for i in range(dsos.shape[0]):
+                for j in range(6):
+                    d.decim_sos[i][j] = float(dsos[i, j])
+                d.decim_zi[i][0], d.decim_zi[i][1] = float(dzi[i, 0]), float(dzi[i, 1])
+            d.decim_pole_radius = float(max(np.abs(np.roots([1.0, r[4], r[5]])).max() for r in dsos))
         self.desc = d
         return self
 
@@ -222,7 +235,9 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.axctd_engine_launch_count(self.h))
 
-    def config(self, fs, settings=None, triggerrange=None, temp_lut=None) -> RateConfig:
+    def config(self, fs, settings=None, triggerrange=None, temp_lut=None, decimate=1) -> RateConfig:
+        """Rate class for recordings of effective rate ``fs``.  decimate=2: the batch receives the raw
+        recording sampled at 2*fs and halves it on the device first."""
         st = {k: (list(v) if isinstance(v, list) else v) for k, v in DEFAULT_SETTINGS.items()}
         for k, v in (settings or {}).items():
             st[k] = v
@@ -231,7 +246,7 @@ class Engine:
                 self._temp_lut = load_temp_lut()
             temp_lut = self._temp_lut
         rc = RateConfig(fs=fs, settings=st, triggerrange=list(triggerrange) if triggerrange is not None else [30, -1],
-                        temp_lut=np.asarray(temp_lut, dtype=np.float64))
+                        temp_lut=np.asarray(temp_lut, dtype=np.float64), decimate=int(decimate))
         key = rc.key()
         if key in self._configs:
             return self._configs[key]

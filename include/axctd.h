@@ -80,7 +80,14 @@ typedef struct axctd_config_desc {
     const double* hist_edges;   /* [n_hist_edges] np.arange(0,3,0.01)  demodulate.py:130 */
     const double* hist_centers; /* [n_hist_edges-1]                    demodulate.py:132 */
     int32_t n_hist_edges;
-    int32_t reserved;
+    /* /2 decimation of recordings above 50 kHz (AXCTDprocessor.py:60-62): scipy.signal.decimate(pcm, 2) =
+     * sosfiltfilt(cheby1(8, 0.05, 0.4, output='sos'), pcm)[::2] with odd padding; fs above is then f_s/2. */
+    int32_t decimate;           /* 0 / 1: none, 2: the batch is given the raw recording and halves it on the device */
+    int32_t decim_sections;     /* rows of decim_sos (4) */
+    int32_t decim_padlen;       /* sosfiltfilt's default padlen (27) */
+    double  decim_sos[AXCTD_MAX_SECTIONS][6];
+    double  decim_zi[AXCTD_MAX_SECTIONS][2];   /* scipy.signal.sosfilt_zi(decim_sos) */
+    double  decim_pole_radius;  /* largest |pole| of decim_sos; sizes the warm-up overlap of the segmented passes */
 } axctd_config_desc;
 
 /* Result header of one drop: the scalar attributes processAXCTD.py:149-168 reads. */
@@ -189,7 +196,8 @@ int64_t axctd_engine_launch_count(axctd_engine* e);
 int  axctd_config_create(axctd_engine* e, const axctd_config_desc* desc, int* config_id);
 
 /* ---- batch of independent drops --------------------------------------- */
-/* Allocates device storage for n_drops mono int16 recordings. */
+/* Allocates device storage for n_drops mono int16 recordings (n_samples counts the RAW samples; a drop whose
+ * config has decimate == 2 is halved on the device and reports numpoints = ceil(n/2)). */
 int  axctd_batch_create(axctd_engine* e, int n_drops, const int64_t* n_samples,
                         const int32_t* config_id, axctd_batch** out);
 void axctd_batch_destroy(axctd_batch* b);

@@ -10,7 +10,10 @@ def mono(pcm):
 
 
 def run_engine(eng, pcm, fs, settings=None, triggerrange=None):
-    cfg = eng.config(fs, settings=settings, triggerrange=triggerrange)
+    if fs > 50000:          # AXCTDprocessor.py:60-62: the engine halves the recording on the device
+        cfg = eng.config(fs / 2, settings=settings, triggerrange=triggerrange, decimate=2)
+    else:
+        cfg = eng.config(fs, settings=settings, triggerrange=triggerrange)
     b = eng.batch([len(pcm)], [cfg])
     b.upload(0, pcm)
     b.run()

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from emu_util import emu_engine
-from golden_util import SMALL_CASES, Golden
+from golden_util import DECIM_CASES, SMALL_CASES, Golden
 from parity_util import check_against_golden, mono, run_engine
 
 
@@ -18,7 +18,7 @@ def eng():
     e.close()
 
 
-@pytest.mark.parametrize("name", SMALL_CASES)
+@pytest.mark.parametrize("name", SMALL_CASES + DECIM_CASES)
 def test_emulated_engine_matches_reference(eng, name):
     g = Golden(name)
     out = run_engine(eng, mono(g.pcm()), g.spec.fs, settings=g.user_settings, triggerrange=g.triggerrange)
@@ -88,6 +88,22 @@ def test_cli_mirror_writes_reference_output_file(eng, tmp_path, capsys):
         os.chdir(cwd)
     assert out.read_text() == g.meta["output_text"]
     assert "Processing profile" in capsys.readouterr().out
+
+
+def test_cli_mirror_decimates_recordings_above_50khz(eng, tmp_path):
+    import synth
+    from axctdprocessor_b200 import processAXCTD
+    g = Golden("g96_decim")
+    synth.write_wav(str(tmp_path / "g96_decim.wav"), g.pcm(), g.spec.fs)
+    settings = {"triggerrange": [30, -1], "minR400": 2.0, "mindR7500": 1.5, "deadfreq": 3000.0, "pointsperloop": 100000,
+                "mark_space_freqs": [400.0, 800.0], "use_bandpass": False}
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        processAXCTD.processAXCTD("g96_decim.wav", "out.txt", [0, -1], settings, engine=eng)
+    finally:
+        os.chdir(cwd)
+    assert (tmp_path / "out.txt").read_text() == g.meta["output_text"]
 
 
 def test_cli_mirror_reproduces_reference_crashes(eng, tmp_path):

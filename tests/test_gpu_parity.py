@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 import synth
-from golden_util import FULL_CASES, SMALL_CASES, Golden
+from golden_util import DECIM_CASES, FULL_CASES, SMALL_CASES, Golden
 from parity_util import check_against_golden, check_against_oracle, frames_view, mono, run_engine
 
 pytestmark = pytest.mark.gpu
@@ -32,7 +32,7 @@ def _engine(**opts):
     return e
 
 
-@pytest.mark.parametrize("name", SMALL_CASES)
+@pytest.mark.parametrize("name", SMALL_CASES + DECIM_CASES)
 def test_matches_reference_small(eng, name):
     g = Golden(name)
     out = run_engine(eng, mono(g.pcm()), g.spec.fs, settings=g.user_settings, triggerrange=g.triggerrange)
@@ -87,6 +87,20 @@ def test_cli_output_file_is_byte_exact(tmp_path):
     os.chdir(tmp_path)
     try:
         processAXCTD.main(["-i", "g44_40db.wav", "-o", "out.txt"])
+    finally:
+        os.chdir(cwd)
+    assert (tmp_path / "out.txt").read_text() == g.meta["output_text"]
+
+
+def test_cli_decimated_recording_is_byte_exact(tmp_path):
+    """96 kHz recording: halved on the device (AXCTDprocessor.py:60-62); f_s prints as 48000.0."""
+    from axctdprocessor_b200 import processAXCTD
+    g = Golden("g96_decim")
+    synth.write_wav(str(tmp_path / "g96_decim.wav"), g.pcm(), g.spec.fs)
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        processAXCTD.main(["-i", "g96_decim.wav", "-o", "out.txt"])
     finally:
         os.chdir(cwd)
     assert (tmp_path / "out.txt").read_text() == g.meta["output_text"]
