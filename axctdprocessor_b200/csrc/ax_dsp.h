@@ -565,6 +565,42 @@ AX_HDN inline void ax_chain_item(const AxWave& w, int64_t d) {
     }
 }
 
+// Zero-state restart of the SOS cascade over the first ny samples of a chunk (scipy's operation order),
+// coefficients and state in registers, samples fetched 16 at a time ahead of the dependent chain.
+template <int NSEC>
+AX_HD void ax_head_filter(const AxSrc& x, int64_t s, int64_t ny, const AxCfg& c, const AxState& st, double* yb) {
+    double k[NSEC][5], z[NSEC][2];
+#pragma unroll
+    for (int q = 0; q < NSEC; ++q) {
+        const bool on = q < c.nsec;               // (sections beyond nsec pass the signal through: b0 = 1, rest 0)
+        k[q][0] = on ? c.sos[q][0] : 1.0; k[q][1] = on ? c.sos[q][1] : 0.0; k[q][2] = on ? c.sos[q][2] : 0.0;
+        k[q][3] = on ? c.sos[q][4] : 0.0; k[q][4] = on ? c.sos[q][5] : 0.0;
+        z[q][0] = 0.0; z[q][1] = 0.0;
+    }
+    const double dc = st.dc, ampl = st.ampl_d;
+    for (int64_t n0 = 0; n0 < ny; n0 += 16) {
+        double xs[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) xs[i] = (n0 + i < ny) ? ax_get(x, s + n0 + i) : 0.0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            if (n0 + i < ny) {
+                double u = ax_div(ax_sub(xs[i], dc), ampl);
+#pragma unroll
+                for (int q = 0; q < NSEC; ++q) {
+                    if (NSEC != AX_MAXSEC || q < c.nsec) {
+                        const double y = ax_add(ax_mul(k[q][0], u), z[q][0]);
+                        z[q][0] = ax_add(ax_sub(ax_mul(k[q][1], u), ax_mul(k[q][3], y)), z[q][1]);
+                        z[q][1] = ax_sub(ax_mul(k[q][2], u), ax_mul(k[q][4], y));
+                        u = y;
+                    }
+                }
+                yb[n0 + i] = u;
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------ exact head
 // Recompute the first `head` samples of a chunk from zero filter state with
 // scipy's exact operation order, find its crossings and bit edges, then join
@@ -589,19 +625,10 @@ AX_HDN inline void ax_head_item(const AxWave& w, int64_t cg) {
     ch.err = 0; ch.n_edges = 0; ch.n_head_edges = 0; ch.g_first = -1; ch.true_last = -1; ch.q_last = -1; ch.first_edge = -1;
     ch.merge_pos = -1; ch.n_pre = 0;
     if (ny > w.ybuf_len_max) { ch.err = AXCTD_DROP_CAPACITY; return; }
-    {   // demodulate.py:74 on AXCTDprocessor.py:57 samples
-        double z[AX_MAXSEC][2];
-        for (int q = 0; q < AX_MAXSEC; ++q) { z[q][0] = 0.0; z[q][1] = 0.0; }
-        for (int64_t n0 = 0; n0 < ny; n0 += 16) {         // samples fetched 16 at a time, ahead of the dependent filter chain
-            double xs[16];
-            for (int i = 0; i < 16; ++i) xs[i] = (n0 + i < ny) ? ax_get(x, s + n0 + i) : 0.0;
-            for (int i = 0; i < 16 && n0 + i < ny; ++i) {
-                double u = ax_div(ax_sub(xs[i], st.dc), st.ampl_d);
-                for (int q = 0; q < c.nsec; ++q) u = ax_biquad_exact(u, c.sos[q], z[q][0], z[q][1]);
-                yb[n0 + i] = u;
-            }
-        }
-    }
+    // demodulate.py:74 on AXCTDprocessor.py:57 samples
+    if (c.nsec == 3) ax_head_filter<3>(x, s, ny, c, st, yb);
+    else if (c.nsec == 6) ax_head_filter<6>(x, s, ny, c, st, yb);
+    else ax_head_filter<AX_MAXSEC>(x, s, ny, c, st, yb);
     int nh = 0;
     bool overflow = false;
     for (int64_t i = c.pad; i <= H - 2; ++i) {                 // demodulate.py:77-82

@@ -32,6 +32,13 @@ METRIC = "audio_seconds_decoded_per_second"
 UNIT = "x_realtime"
 
 
+def workload_config(drops, duration, total_samples):
+    return {"workload": f"BASELINE config 4 share: {drops} drops/GPU x {duration:.0f} s, 44.1/48 kHz alternating, "
+                        f"SNR 40/25/10 dB, device-generated (synth.py twin), default 1200 Hz lowpass",
+            "drops_per_gpu": drops, "samples_per_gpu": total_samples, "sharding": "by drop, no collective",
+            "cache": "inputs (%.1f GB per GPU) larger than L2" % (2e-9 * total_samples)}
+
+
 def drop_specs(n_drops, duration_s, rank):
     return [synth.DropSpec(fs=(44100, 48000)[i % 2], duration_s=duration_s, seed=100000 * (rank + 1) + i,
                            snr_db=(40.0, 25.0, 10.0)[i % 3]) for i in range(n_drops)]
@@ -154,10 +161,12 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"config4 share: 12-min synthetic AXCTD drops, 44.1/48 kHz alternating; CPU arm decodes a "
-                                   f"bounded sample of {cores} x {dur:.0f} s drops per step"},
+            "config": workload_config(args.drops, args.duration,
+                                      sum(int(round(sp.duration_s * sp.fs)) for sp in drop_specs(args.drops, args.duration, 0))),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{cores} drops x {dur:.0f} s per step, one process per core, oracle/axctd_oracle.py"},
+                             "sample": f"bounded sample of the workload: {cores} of its drops x {dur:.0f} s per step, one process "
+                                       f"per host core, oracle/axctd_oracle.py (numpy port of the reference's path; the reference "
+                                       f"itself is Python and cannot travel to the GPU box)"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -277,10 +286,7 @@ def run_native(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"BASELINE config 4 share: {args.drops} drops/GPU x {args.duration:.0f} s, 44.1/48 kHz alternating, "
-                                   f"SNR 40/25/10 dB, device-generated (synth.py twin), default 1200 Hz lowpass",
-                       "drops_per_gpu": args.drops, "samples_per_gpu": total_samples, "sharding": "by drop, no collective",
-                       "cache": "inputs (%.1f GB per GPU) larger than L2" % (2e-9 * total_samples)},
+            "config": workload_config(args.drops, args.duration, total_samples),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(d2h_bytes),
                     "steps": args.e2e_steps, "note": "pinned host PCM -> axctd_batch_upload -> run -> results to host, wall clock"},
