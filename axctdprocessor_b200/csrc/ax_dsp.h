@@ -10,7 +10,7 @@
 //                                  per-bit mark/space single-bin DFTs   demodulate.py:74-79, 99-102
 //   ax_tiles_item / ax_walk_end    greedy bit-edge walk                 demodulate.py:85-93
 //   ax_chain_item                  chunk chain s_k                      AXCTDprocessor.py:293-333
-//   ax_head_item                   exact zero-state restart per chunk   demodulate.py:74 (sosfilt zero state)
+//   ax_headfilt_item / ax_headwalk_item   zero-state restart per chunk  demodulate.py:74 (sosfilt zero state)
 #pragma once
 #include "ax_types.h"
 
@@ -565,78 +565,79 @@ AX_HDN inline void ax_chain_item(const AxWave& w, int64_t d) {
     }
 }
 
-// Zero-state restart of the SOS cascade over the first ny samples of a chunk (scipy's operation order),
-// coefficients and state in registers, samples fetched 16 at a time ahead of the dependent chain.
-template <int NSEC>
-AX_HD void ax_head_filter(const AxSrc& x, int64_t s, int64_t ny, const AxCfg& c, const AxState& st, double* yb) {
-    double k[NSEC][5], z[NSEC][2];
-#pragma unroll
-    for (int q = 0; q < NSEC; ++q) {
-        const bool on = q < c.nsec;               // (sections beyond nsec pass the signal through: b0 = 1, rest 0)
-        k[q][0] = on ? c.sos[q][0] : 1.0; k[q][1] = on ? c.sos[q][1] : 0.0; k[q][2] = on ? c.sos[q][2] : 0.0;
-        k[q][3] = on ? c.sos[q][4] : 0.0; k[q][4] = on ? c.sos[q][5] : 0.0;
-        z[q][0] = 0.0; z[q][1] = 0.0;
-    }
-    const double dc = st.dc, ampl = st.ampl_d;
-    for (int64_t n0 = 0; n0 < ny; n0 += 16) {
-        double xs[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) xs[i] = (n0 + i < ny) ? ax_get(x, s + n0 + i) : 0.0;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            if (n0 + i < ny) {
-                double u = ax_div(ax_sub(xs[i], dc), ampl);
-#pragma unroll
-                for (int q = 0; q < NSEC; ++q) {
-                    if (NSEC != AX_MAXSEC || q < c.nsec) {
-                        const double y = ax_add(ax_mul(k[q][0], u), z[q][0]);
-                        z[q][0] = ax_add(ax_sub(ax_mul(k[q][1], u), ax_mul(k[q][3], y)), z[q][1]);
-                        z[q][1] = ax_sub(ax_mul(k[q][2], u), ax_mul(k[q][4], y));
-                        u = y;
-                    }
-                }
-                yb[n0 + i] = u;
-            }
-        }
-    }
+// ------------------------------------------------------------------ chunk heads
+// The reference restarts its filter from zero state at every chunk start (demodulate.py:74 on the chunk
+// slice).  Past the first `head` samples that restart is indistinguishable from the continuous pass; the
+// head itself is filtered again from zero state, with the same arithmetic as the continuous pass
+// (AxFilt / k_demod_fused in head mode), giving the crossings pad <= i <= H-2 (demodulate.py:77-82) and
+// their windows.
+struct AxHeadGeom { int64_t s, len, H, ny; bool active; };
+AX_HD AxHeadGeom ax_head_geom(const AxWave& w, const AxDrop& dr, const AxState& st, const AxCfg& c, const AxChunk& ch, int k) {
+    AxHeadGeom g;
+    g.active = !(st.status != 0 || st.sm_status < 1 || k < st.chain_from || k >= st.n_chunks || k >= dr.chunk_cap);
+    g.s = ch.s; g.len = ch.e - ch.s;
+    g.H = (w.force_exact || c.head > g.len) ? g.len : c.head;
+    g.ny = g.H + c.npcm + 2;
+    if (g.ny > g.len) g.ny = g.len;
+    return g;
 }
 
-// ------------------------------------------------------------------ exact head
-// Recompute the first `head` samples of a chunk from zero filter state with
-// scipy's exact operation order, find its crossings and bit edges, then join
-// the precomputed continuous crossings.
-AX_HDN inline void ax_head_item(const AxWave& w, int64_t cg) {
+// generic form of the head filter (the CUDA build runs k_demod_fused<.., HEAD> for the rate classes it
+// is instantiated for; `only_rest`: skip those)
+template <int NSEC, bool BUTTER>
+AX_HDN inline void ax_headfilt_run(const AxWave& w, int64_t cg, const AxDrop& dr, const AxCfg& c, AxState& st, const AxHeadGeom& g) {
+    int32_t* hz = w.head_idx + cg * (int64_t)w.head_zc_cap_max;
+    float* ha1 = w.head_a1 + cg * (int64_t)w.head_zc_cap_max;
+    float* ha2 = w.head_a2 + cg * (int64_t)w.head_zc_cap_max;
+    const AxSrc x = ax_src(w, dr);
+    AxFilt<NSEC, BUTTER> f;
+    f.init(c, st, (int32_t)(g.s + c.pad), (int32_t)(g.s + g.H - 1), w.guard, hz, ha1, ha2, w.head_zc_cap_max);
+    for (int64_t n = g.s; n < g.s + g.ny; ++n) f.step((int32_t)n, ax_get(x, n));
+    f.finish();
+    const int cnt = f.cnt > w.head_zc_cap_max ? -1 : f.cnt;
+    for (int q = 0; q < cnt; ++q) hz[q] -= (int32_t)g.s;               // chunk-relative
+    w.head_cnt[cg] = cnt;
+    if (f.unc) AX_ATOMIC_ADD32(&st.n_uncertain, f.unc);
+}
+AX_HDN inline void ax_headfilt_item(const AxWave& w, int64_t cg, int only_rest) {
     const int d = ax_find_owner(w.drop, w.n_drops, &AxDrop::chunk_base, cg);
     const AxDrop& dr = w.drop[d];
     AxState& st = w.st[d];
     const int k = (int)(cg - dr.chunk_base);
-    if (st.status != 0 || st.sm_status < 1 || k < st.chain_from || k >= st.n_chunks || k >= dr.chunk_cap) return;
+    if (k >= dr.chunk_cap) return;
+    const AxCfg& c = w.cfg[dr.cfg];
+    const AxHeadGeom g = ax_head_geom(w, dr, st, c, w.chunk[cg], k);
+    if (!g.active) return;
+    const bool bt = ax_sos_is_butter(c);
+    if (only_rest && bt && (c.nsec == 3 || c.nsec == 6) && (c.npcm == 39 || c.npcm == 43) && c.inset == 1 && dr.xf_off < 0) return;
+    if (c.nsec == 3) { if (bt) ax_headfilt_run<3, true>(w, cg, dr, c, st, g); else ax_headfilt_run<3, false>(w, cg, dr, c, st, g); }
+    else if (c.nsec == 6) { if (bt) ax_headfilt_run<6, true>(w, cg, dr, c, st, g); else ax_headfilt_run<6, false>(w, cg, dr, c, st, g); }
+    else if (c.nsec == 1) ax_headfilt_run<1, false>(w, cg, dr, c, st, g);
+    else if (c.nsec == 2) ax_headfilt_run<2, false>(w, cg, dr, c, st, g);
+    else if (c.nsec == 4) ax_headfilt_run<4, false>(w, cg, dr, c, st, g);
+    else ax_headfilt_run<5, false>(w, cg, dr, c, st, g);
+}
+
+// Bit edges of the head (greedy walk over its crossings, demodulate.py:85-93), then join the
+// precomputed continuous crossings.
+AX_HDN inline void ax_headwalk_item(const AxWave& w, int64_t cg) {
+    const int d = ax_find_owner(w.drop, w.n_drops, &AxDrop::chunk_base, cg);
+    const AxDrop& dr = w.drop[d];
+    AxState& st = w.st[d];
+    const int k = (int)(cg - dr.chunk_base);
+    if (k >= dr.chunk_cap) return;
     const AxCfg& c = w.cfg[dr.cfg];
     AxChunk& ch = w.chunk[cg];
-    const int64_t s = ch.s, e = ch.e, len = e - s;
-    const AxSrc x = ax_src(w, dr);
-    const int64_t H = (w.force_exact || c.head > len) ? len : c.head;
-    int64_t ny = H + c.npcm + 2;
-    if (ny > len) ny = len;
-    double* yb = w.ybuf + cg * (int64_t)w.ybuf_len_max;
+    const AxHeadGeom g = ax_head_geom(w, dr, st, c, ch, k);
+    if (!g.active) return;
+    const int64_t s = g.s, e = ch.e, len = g.len, H = g.H;
     int32_t* hz = w.head_idx + cg * (int64_t)w.head_zc_cap_max;
-    double* ha1 = w.head_a1 + cg * (int64_t)w.head_zc_cap_max;
-    double* ha2 = w.head_a2 + cg * (int64_t)w.head_zc_cap_max;
+    float* ha1 = w.head_a1 + cg * (int64_t)w.head_zc_cap_max;
+    float* ha2 = w.head_a2 + cg * (int64_t)w.head_zc_cap_max;
     ch.err = 0; ch.n_edges = 0; ch.n_head_edges = 0; ch.g_first = -1; ch.true_last = -1; ch.q_last = -1; ch.first_edge = -1;
     ch.merge_pos = -1; ch.n_pre = 0;
-    if (ny > w.ybuf_len_max) { ch.err = AXCTD_DROP_CAPACITY; return; }
-    // demodulate.py:74 on AXCTDprocessor.py:57 samples
-    if (c.nsec == 3) ax_head_filter<3>(x, s, ny, c, st, yb);
-    else if (c.nsec == 6) ax_head_filter<6>(x, s, ny, c, st, yb);
-    else ax_head_filter<AX_MAXSEC>(x, s, ny, c, st, yb);
-    int nh = 0;
-    bool overflow = false;
-    for (int64_t i = c.pad; i <= H - 2; ++i) {                 // demodulate.py:77-82
-        if ((yb[i] < 0.0) != (yb[i + 1] < 0.0)) {
-            if (nh < w.head_zc_cap_max) hz[nh++] = (int32_t)i; else overflow = true;
-        }
-    }
-    if (overflow) { ch.err = AXCTD_DROP_CAPACITY; return; }
+    const int nh = w.head_cnt[cg];
+    if (nh < 0) { ch.err = AXCTD_DROP_CAPACITY; return; }
     const int32_t* zi = w.zc_idx + dr.zc_base;
     const uint8_t* nx = w.zc_nx + dr.zc_base;
     const uint64_t* cmask = w.cmask + dr.tile_base;
@@ -659,7 +660,8 @@ AX_HDN inline void ax_head_item(const AxWave& w, int64_t cg) {
     bool done = false;
     int64_t last = -1;
     while (cpos < nh) {
-        hz[nhe++] = hz[cpos];                                  // bit edge inside the head
+        hz[nhe] = hz[cpos]; ha1[nhe] = ha1[cpos]; ha2[nhe] = ha2[cpos];   // bit edge inside the head
+        ++nhe;
         if (!(cpos < total - 5)) { last = s + hz[nhe - 1]; done = true; break; }
         const int64_t c0 = s + hz[cpos];
         int64_t best = 0; int bj = 0;
@@ -687,25 +689,9 @@ AX_HDN inline void ax_head_item(const AxWave& w, int64_t cg) {
     ch.n_head_edges = nhe;
     ch.n_edges = (int32_t)nedges;
     ch.true_last = last;
-    // demodulate.py:99-102 for the head edges (all but the chunk's final edge)
-    for (int t = 0; t < nhe; ++t) {
-        const int64_t e0 = hz[t];
-        const bool is_last = (t == nedges - 1);
-        if (e0 + c.inset + c.npcm > len) {
-            ha1[t] = ax_nan(); ha2[t] = ax_nan();
-            if (!is_last) ch.err = AXCTD_DROP_SHORT_WINDOW;
-            continue;
-        }
-        double sr1 = 0, si1 = 0, sr2 = 0, si2 = 0;
-        for (int mI = 0; mI < c.npcm; ++mI) {
-            const double y = yb[e0 + c.inset + mI];
-            const double* t4 = c.bit_cs + 4 * mI;
-            sr1 = ax_fma(y, t4[0], sr1); si1 = ax_fma(y, t4[1], si1);
-            sr2 = ax_fma(y, t4[2], sr2); si2 = ax_fma(y, t4[3], si2);
-        }
-        ha1[t] = hypot(sr1, si1);
-        ha2[t] = hypot(sr2, si2);
-    }
+    // demodulate.py:100-101: a window that runs past the chunk end cannot be summed (only the final edge needs none)
+    for (int t = 0; t < nhe; ++t)
+        if (hz[t] + c.inset + c.npcm > len && t != nedges - 1) ch.err = AXCTD_DROP_SHORT_WINDOW;
 }
 
 // Compare the prediction with the exact result; repair the chain on mismatch.

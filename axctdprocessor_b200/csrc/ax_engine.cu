@@ -82,7 +82,8 @@ AX_GLOBAL void k_levels(int64_t n, AxWave w, int phase_b) { AX_FOR_ITEM(n) ax_le
 AX_GLOBAL void k_sm(int64_t n, AxWave w, int phase_b) { AX_FOR_ITEM1(n) ax_sm_item(w, item, phase_b); }
 AX_GLOBAL void k_canon(int64_t n, AxWave w) { AX_FOR_ITEM1(n) ax_canon_item(w, item); }
 AX_GLOBAL void k_chain(int64_t n, AxWave w) { AX_FOR_ITEM1(n) ax_chain_item(w, item); }
-AX_GLOBAL void k_heads(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_head_item(w, item); }
+AX_GLOBAL void k_headfilt(int64_t n, AxWave w, int only_rest) { AX_FOR_ITEM(n) ax_headfilt_item(w, item, only_rest); }
+AX_GLOBAL void k_headwalk(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_headwalk_item(w, item); }
 AX_GLOBAL void k_verify(int64_t n, AxWave w) { AX_FOR_ITEM1(n) ax_verify_item(w, item); }
 AX_GLOBAL void k_plan_tones(int64_t n, AxWave w) { AX_FOR_ITEM1(n) ax_plan_tones_item(w, item); }
 AX_GLOBAL void k_offsets(int64_t n, AxWave w) { AX_FOR_ITEM1(n) ax_offsets_item(w, item); }
@@ -531,7 +532,7 @@ extern "C" int axctd_batch_create(axctd_engine* e, int n_drops, const int64_t* n
     bad |= ax_alloc_arr(b, &w.head_idx, (int64_t)chunk_off * head_cap_max);
     bad |= ax_alloc_arr(b, &w.head_a1, (int64_t)chunk_off * head_cap_max);
     bad |= ax_alloc_arr(b, &w.head_a2, (int64_t)chunk_off * head_cap_max);
-    bad |= ax_alloc_arr(b, &w.ybuf, (int64_t)chunk_off * ybuf_max);
+    bad |= ax_alloc_arr(b, &w.head_cnt, chunk_off);
     bad |= ax_alloc_arr(b, &w.pw_raw, 3 * (int64_t)pw_off);
     bad |= ax_alloc_arr(b, &w.pw_sm, 3 * (int64_t)pw_off);
     bad |= ax_alloc_arr(b, &w.r400, pw_off);
@@ -743,7 +744,7 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
         }
     if (fused) {
         // one launch per rate class in use (CTAs of the other classes exit at once)
-        for (int ci : used_cfg) { ax_launch_demod_fused_any(w, e->cfgs[ci], ci, e->stream); e->launches++; }
+        for (int ci : used_cfg) { ax_launch_demod_fused_any<false>(w, e->cfgs[ci], ci, 0, e->stream); e->launches++; }
         if (any_dec) { w.only_xf = 1; AX_LAUNCH(e, k_filter, (int64_t)w.nseg_total, w); w.only_xf = 0; }
     } else
 #endif
@@ -786,7 +787,19 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
     for (int it = 0;; ++it) {
         AX_LAUNCH1(e, k_chain, n, w);
         if (e->opt_inject_misspec && it == 0) AX_LAUNCH(e, k_inject, n, w);
-        AX_LAUNCH(e, k_heads, b->chunk_total, w);
+#ifndef AXCTD_EMU
+        if (e->opt_filter_variant == 0) {
+            // heads of the rate classes the fused kernel is instantiated for; the generic form takes the rest
+            bool rest = any_dec;
+            for (int ci : used_cfg) {
+                if (ax_demod_fused_ok(e->cfgs[ci])) { ax_launch_demod_fused_any<true>(w, e->cfgs[ci], ci, b->chunk_total, e->stream); e->launches++; }
+                else rest = true;
+            }
+            if (rest) AX_LAUNCH(e, k_headfilt, b->chunk_total, w, 1);
+        } else
+#endif
+        { AX_LAUNCH(e, k_headfilt, b->chunk_total, w, 0); }
+        AX_LAUNCH(e, k_headwalk, b->chunk_total, w);
         AX_LAUNCH1(e, k_verify, n, w);
         if (ax_d2h(e, flags, w.flags, sizeof(flags)) || ax_sync(e)) return AXCTD_ERR_CUDA;
         if (!flags[AX_FLAG_DIRTY]) break;

@@ -230,33 +230,61 @@ struct AxFdSmem {
     int16_t stage[2][AX_FD_STAGE];
     float yring[32 * AX_FD_YSTRIDE];
     uint32_t list[AX_FD_LIST];
-    int32_t row_begin[32], row_stop[32];
+    int32_t row_begin[32], row_stop[32], row_aux[32];
 };
 
 
-template <int NSEC, int NPCM>
-__global__ void __launch_bounds__(AX_FD_THREADS, 2) k_demod_fused(const __grid_constant__ AxWave w, const __grid_constant__ AxWinTab tab, int cfg_id) {
+// HEAD = false: lane = segment of the continuous pass.  HEAD = true: lane = run() iteration, filtered from
+// zero state at the chunk start over its first head + npcm + 2 samples (ax_headfilt_item); the lane's
+// stream starts at the chunk start rounded down to 8 samples (16-byte staging) and the samples before the
+// chunk start enter the cascade as zeros, which leaves its state at zero.
+template <int NSEC, int NPCM, bool HEAD>
+__global__ void __launch_bounds__(AX_FD_THREADS, 2) k_demod_fused(const __grid_constant__ AxWave w, const __grid_constant__ AxWinTab tab, int cfg_id, int64_t n_items) {
     extern __shared__ __align__(16) unsigned char ax_smem_raw[];
-    const int d = w.seg_drop[(int64_t)blockIdx.x * AX_FD_THREADS];
-    const AxDrop& dr = w.drop[d];
-    if (dr.cfg != cfg_id || dr.xf_off >= 0) return;     // another launch handles this rate class / the generic kernel the halved signals
-    const AxCfg& c = w.cfg[cfg_id];
-    AxState& st = w.st[d];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     AxFdSmem& sm = reinterpret_cast<AxFdSmem*>(ax_smem_raw)[warp];
     const int64_t seg = (int64_t)blockIdx.x * AX_FD_THREADS + threadIdx.x;
-    const int64_t j = seg - dr.seg_base;
-    const bool active = j < dr.nseg;
+    int d;
+    bool active;
     AxSegGeom g;
     g.seg_start = g.seg_end = g.n_begin = g.n_stop = 0;
-    if (active) g = ax_seg_geom(dr, c, w.seg_len, j);
+    int skip = 0;                                       // HEAD: samples of row 0 that lie before the chunk start
+    int64_t chunk_s = 0;
+    if (!HEAD) {
+        d = w.seg_drop[(int64_t)blockIdx.x * AX_FD_THREADS];
+        const AxDrop& dr0 = w.drop[d];
+        if (dr0.cfg != cfg_id || dr0.xf_off >= 0) return;   // another launch handles this rate class / the generic kernel the halved signals
+        const int64_t j = seg - dr0.seg_base;
+        active = j < dr0.nseg;
+        if (active) g = ax_seg_geom(dr0, w.cfg[cfg_id], w.seg_len, j);
+    } else {
+        const int64_t cg = seg < n_items ? seg : n_items - 1;
+        d = ax_find_owner(w.drop, w.n_drops, &AxDrop::chunk_base, cg);
+        const AxDrop& dr0 = w.drop[d];
+        const int k = (int)(cg - dr0.chunk_base);
+        active = seg < n_items && k < dr0.chunk_cap && dr0.cfg == cfg_id && dr0.xf_off < 0;
+        if (active) {
+            const AxHeadGeom hg = ax_head_geom(w, dr0, w.st[d], w.cfg[cfg_id], w.chunk[cg], k);
+            active = hg.active;
+            if (active) {
+                chunk_s = hg.s;
+                g.n_begin = hg.s & ~(int64_t)7; skip = (int)(hg.s - g.n_begin);
+                g.n_stop = hg.s + hg.ny;
+                g.seg_start = hg.s + w.cfg[cfg_id].pad; g.seg_end = hg.s + hg.H - 1;
+            }
+        }
+        if (!__any_sync(0xffffffffu, active)) { if (seg < n_items && !active) { /* nothing to do for this warp */ } return; }
+    }
+    const AxDrop& dr = w.drop[d];
+    const AxCfg& c = w.cfg[cfg_id];
+    AxState& st = w.st[d];
     const int T = active ? (int)((g.n_stop - g.n_begin + 63) >> 6) : 0;
     int Tmax = T;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) Tmax = max(Tmax, __shfl_xor_sync(0xffffffffu, Tmax, o));
     const int16_t* xdrop = w.pcm + dr.pcm_off;
     const unsigned long long xrow = (unsigned long long)(xdrop + g.n_begin);      // 16-byte aligned
-    sm.row_begin[lane] = (int)g.n_begin; sm.row_stop[lane] = (int)g.n_stop;
+    sm.row_begin[lane] = (int)g.n_begin; sm.row_stop[lane] = (int)g.n_stop; sm.row_aux[lane] = (int)chunk_s;
     for (int k = lane; k < AX_WIN_TAPS; k += 32) sm.tab[k] = tab.t[k];
     // ---- cascade constants (Butterworth form, see AxFilt::filter)
     double z0[NSEC], z1[NSEC], a1[NSEC], a2[NSEC], sg[NSEC];
@@ -269,8 +297,8 @@ __global__ void __launch_bounds__(AX_FD_THREADS, 2) k_demod_fused(const __grid_c
     const double k0 = c.sos[0][0] * st.inv_ampl, k1 = c.sos[0][0] * -(st.dc * st.inv_ampl);
     const float guard_f = (float)w.guard;
     const int nb = (int)g.n_begin, nstop = (int)g.n_stop, sstart = (int)g.seg_start, send = (int)g.seg_end;
-    const int64_t slot0 = seg * (int64_t)w.seg_cap;
-    const int64_t wslot0 = (seg - lane) * (int64_t)w.seg_cap;       // slot of the warp's row 0
+    const int out_cap = HEAD ? w.head_zc_cap_max : w.seg_cap;
+    const int64_t wslot0 = (seg - lane) * (int64_t)out_cap;          // output slot of the warp's row 0
     // rows this lane helps to stage: r = i*4 + prow, i = 0..7
     const int prow = lane >> 3, piece = lane & 7;
     unsigned long long src[8];
@@ -314,6 +342,7 @@ __global__ void __launch_bounds__(AX_FD_THREADS, 2) k_demod_fused(const __grid_c
                         for (int e = 0; e < 8; ++e) {
                             const int xi = (e & 1) ? (wd[e >> 1] >> 16) : (int)(short)(wd[e >> 1] & 0xFFFF);
                             double tt = fma((double)xi, k0, k1);
+                            if (HEAD && t == 0 && hw * 32 + v * 8 + e < skip) tt = 0.0;      // before the chunk start: keeps the state at zero
 #pragma unroll
                             for (int s = 0; s < NSEC; ++s) {
                                 const double y = tt + z0[s];
@@ -385,11 +414,17 @@ __global__ void __launch_bounds__(AX_FD_THREADS, 2) k_demod_fused(const __grid_c
                     ax_window32(yv, o, NPCM, sm.tab, &m1, &m2);
                     const int rb = sm.row_begin[r] + 64 * (t - 1);
                     const bool complete = rb + p + NPCM < sm.row_stop[r];
-                    if (op < w.seg_cap) {
-                        const int64_t oi = wslot0 + (int64_t)r * w.seg_cap + op;
-                        w.rec_idx[oi] = rb + p;
-                        w.rec_a1[oi] = complete ? m1 : __int_as_float(0x7fc00000);
-                        w.rec_a2[oi] = complete ? m2 : __int_as_float(0x7fc00000);
+                    if (op < out_cap) {
+                        const int64_t oi = wslot0 + (int64_t)r * out_cap + op;
+                        if (!HEAD) {
+                            w.rec_idx[oi] = rb + p;
+                            w.rec_a1[oi] = complete ? m1 : __int_as_float(0x7fc00000);
+                            w.rec_a2[oi] = complete ? m2 : __int_as_float(0x7fc00000);
+                        } else {
+                            w.head_idx[oi] = rb + p - sm.row_aux[r];         // chunk-relative
+                            w.head_a1[oi] = complete ? m1 : __int_as_float(0x7fc00000);
+                            w.head_a2[oi] = complete ? m2 : __int_as_float(0x7fc00000);
+                        }
                     }
                 }
                 __syncwarp();
@@ -398,31 +433,38 @@ __global__ void __launch_bounds__(AX_FD_THREADS, 2) k_demod_fused(const __grid_c
         Sprev = Scur;
         __syncwarp();
     }
-    if (active) {
-        if (count > w.seg_cap) { w.flags[AX_FLAG_CAP] = 1; count = w.seg_cap; }
-        w.seg_cnt[seg] = count;
+    if (!HEAD) {
+        if (active) {
+            if (count > w.seg_cap) { w.flags[AX_FLAG_CAP] = 1; count = w.seg_cap; }
+            w.seg_cnt[seg] = count;
+            if (unc) atomicAdd(&st.n_uncertain, unc);
+        } else w.seg_cnt[seg] = 0;
+    } else if (active) {
+        w.head_cnt[seg] = count > out_cap ? -1 : count;
         if (unc) atomicAdd(&st.n_uncertain, unc);
-    } else w.seg_cnt[seg] = 0;
-    (void)slot0;
+    }
 }
 
-template <int NSEC, int NPCM>
-static inline void ax_launch_demod_fused(const AxWave& w, const AxCfg& c, int cfg_id, cudaStream_t stream) {
+template <int NSEC, int NPCM, bool HEAD>
+static inline void ax_launch_demod_fused(const AxWave& w, const AxCfg& c, int cfg_id, int64_t n_items, cudaStream_t stream) {
     const size_t smem = AX_FD_WARPS * sizeof(AxFdSmem);
     static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(k_demod_fused<NSEC, NPCM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
-    k_demod_fused<NSEC, NPCM><<<w.nseg_total / AX_FD_THREADS, AX_FD_THREADS, smem, stream>>>(w, c.win_tab, cfg_id);
+    if (!attr_set) { cudaFuncSetAttribute(k_demod_fused<NSEC, NPCM, HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+    const int64_t items = HEAD ? n_items : (int64_t)w.nseg_total;
+    if (items <= 0) return;
+    k_demod_fused<NSEC, NPCM, HEAD><<<(unsigned)((items + AX_FD_THREADS - 1) / AX_FD_THREADS), AX_FD_THREADS, smem, stream>>>(w, c.win_tab, cfg_id, items);
 }
 
 // true if the fused kernel has an instantiation for this rate class
 static inline bool ax_demod_fused_ok(const AxCfg& c) {
     return ax_sos_is_butter(c) && (c.nsec == 3 || c.nsec == 6) && (c.npcm == 39 || c.npcm == 43) && c.inset == 1;
 }
-static inline void ax_launch_demod_fused_any(const AxWave& w, const AxCfg& c, int cfg_id, cudaStream_t stream) {
-    if (c.nsec == 3 && c.npcm == 39) ax_launch_demod_fused<3, 39>(w, c, cfg_id, stream);
-    else if (c.nsec == 3 && c.npcm == 43) ax_launch_demod_fused<3, 43>(w, c, cfg_id, stream);
-    else if (c.nsec == 6 && c.npcm == 39) ax_launch_demod_fused<6, 39>(w, c, cfg_id, stream);
-    else ax_launch_demod_fused<6, 43>(w, c, cfg_id, stream);
+template <bool HEAD>
+static inline void ax_launch_demod_fused_any(const AxWave& w, const AxCfg& c, int cfg_id, int64_t n_items, cudaStream_t stream) {
+    if (c.nsec == 3 && c.npcm == 39) ax_launch_demod_fused<3, 39, HEAD>(w, c, cfg_id, n_items, stream);
+    else if (c.nsec == 3 && c.npcm == 43) ax_launch_demod_fused<3, 43, HEAD>(w, c, cfg_id, n_items, stream);
+    else if (c.nsec == 6 && c.npcm == 39) ax_launch_demod_fused<6, 39, HEAD>(w, c, cfg_id, n_items, stream);
+    else ax_launch_demod_fused<6, 43, HEAD>(w, c, cfg_id, n_items, stream);
 }
 
 // ------------------------------------------------------------------ bit decisions with shared window sums

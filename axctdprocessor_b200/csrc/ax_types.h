@@ -202,8 +202,8 @@ struct AxWave {
     uint64_t* cmask; int32_t* crank;                        // [tile] canonical walk: visited mask, visited count before the tile
     // chunks
     AxChunk* chunk;
-    int32_t* head_idx; double* head_a1; double* head_a2;    // [chunk][head_zc_cap_max]
-    double* ybuf;                                           // [chunk][ybuf_len_max]
+    int32_t* head_idx; float* head_a1; float* head_a2;      // [chunk][head_zc_cap_max] crossings of the zero-state heads
+    int32_t* head_cnt;                                      // [chunk] how many (-1: did not fit)
     int32_t head_zc_cap_max, ybuf_len_max;
     // tone powers
     double* pw_raw;              // [3][pw_total]
