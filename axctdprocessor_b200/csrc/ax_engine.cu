@@ -129,6 +129,7 @@ struct axctd_engine {
     double opt_bit_tol = 2e-5;            // fp32 bit windows: relative distance to a decision boundary that triggers
     double opt_hist_tol = 2e-5;           //   the double-precision re-evaluation (bit decision / calibration histogram)
     int opt_bitfix_all = 0;               // test hook: re-evaluate every window
+    int opt_rows32 = 0;                   // fused kernel with 32-sample rows (12 warps per SM)
 };
 
 #ifdef AXCTD_EMU
@@ -272,6 +273,7 @@ extern "C" int axctd_engine_set_option(axctd_engine* e, const char* name, double
     else if (s == "filter_variant") e->opt_filter_variant = (int)v;
     else if (s == "zc_div") e->opt_zc_div = std::max(2, (int)v);
     else if (s == "inject_misspec") e->opt_inject_misspec = (int)v;
+    else if (s == "rows32") e->opt_rows32 = (int)v;
     else if (s == "bit_tol") e->opt_bit_tol = v;
     else if (s == "hist_tol") e->opt_hist_tol = v;
     else if (s == "bitfix_all") e->opt_bitfix_all = (int)v;
@@ -744,7 +746,7 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
         }
     if (fused) {
         // one launch per rate class in use (CTAs of the other classes exit at once)
-        for (int ci : used_cfg) { ax_launch_demod_fused_any<false>(w, e->cfgs[ci], ci, 0, e->stream); e->launches++; }
+        for (int ci : used_cfg) { ax_launch_demod_fused_any<false>(w, e->cfgs[ci], ci, 0, e->stream, e->opt_rows32); e->launches++; }
         if (any_dec) { w.only_xf = 1; AX_LAUNCH(e, k_filter, (int64_t)w.nseg_total, w); w.only_xf = 0; }
     } else
 #endif
@@ -792,7 +794,7 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
             // heads of the rate classes the fused kernel is instantiated for; the generic form takes the rest
             bool rest = any_dec;
             for (int ci : used_cfg) {
-                if (ax_demod_fused_ok(e->cfgs[ci])) { ax_launch_demod_fused_any<true>(w, e->cfgs[ci], ci, b->chunk_total, e->stream); e->launches++; }
+                if (ax_demod_fused_ok(e->cfgs[ci])) { ax_launch_demod_fused_any<true>(w, e->cfgs[ci], ci, b->chunk_total, e->stream, e->opt_rows32); e->launches++; }
                 else rest = true;
             }
             if (rest) AX_LAUNCH(e, k_headfilt, b->chunk_total, w, 1);

@@ -188,6 +188,9 @@ def run_native(args):
     stream = torch.cuda.Stream()
     eng = engine.Engine(local)
     eng.set_stream(stream.cuda_stream)
+    for kv in args.opt:
+        name, val = kv.split("=")
+        eng.set_option(name, float(val))
     specs = drop_specs(args.drops, args.duration, rank)
     cfg = {fs: eng.config(fs) for fs in (44100, 48000)}
     n = [int(round(s.duration_s * s.fs)) for s in specs]
@@ -272,6 +275,8 @@ def run_native(args):
         if not h:
             continue
         eh = engine.Engine(local)
+        for kv in args.opt:
+            eh.set_option(kv.split("=")[0], float(kv.split("=")[1]))
         cfgh = {fs: eh.config(fs) for fs in (44100, 48000)}
         engs.append(eh)
         bats.append((eh.batch([n[i] for i in h], [cfgh[specs[i].fs] for i in h]), h))
@@ -359,6 +364,7 @@ def main():
     ap.add_argument("--cpu-procs", type=int, default=0)
     ap.add_argument("--cpu-duration", type=float, default=720.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="engine option name=value (A/B experiments)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
