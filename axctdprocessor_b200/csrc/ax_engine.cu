@@ -130,6 +130,7 @@ struct axctd_engine {
     double opt_hist_tol = 2e-5;           //   the double-precision re-evaluation (bit decision / calibration histogram)
     int opt_bitfix_all = 0;               // test hook: re-evaluate every window
     int opt_rows32 = 0;                   // fused kernel with 32-sample rows (12 warps per SM)
+    int opt_scan_only = 0;                // tone levels only (segmentation of long recordings): skip the demodulation pass
 };
 
 #ifdef AXCTD_EMU
@@ -274,6 +275,7 @@ extern "C" int axctd_engine_set_option(axctd_engine* e, const char* name, double
     else if (s == "zc_div") e->opt_zc_div = std::max(2, (int)v);
     else if (s == "inject_misspec") e->opt_inject_misspec = (int)v;
     else if (s == "rows32") e->opt_rows32 = (int)v;
+    else if (s == "scan_only") e->opt_scan_only = (int)v;
     else if (s == "bit_tol") e->opt_bit_tol = v;
     else if (s == "hist_tol") e->opt_hist_tol = v;
     else if (s == "bitfix_all") e->opt_bitfix_all = (int)v;
@@ -736,6 +738,8 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
     AX_LAUNCH(e, k_toneblock, b->tb_total, w);
 #endif
     AX_EVENT(b, 1);
+    const bool scan_only = e->opt_scan_only != 0;     // tone levels only: no crossings are produced
+    if (scan_only) { if (ax_zero(e, w.seg_cnt, sizeof(int32_t) * (size_t)w.nseg_total)) return AXCTD_ERR_CUDA; }
 #ifndef AXCTD_EMU
     bool fused = e->opt_filter_variant == 0;
     std::vector<int> used_cfg;
@@ -744,11 +748,14 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
             used_cfg.push_back((int)ci);
             if (!ax_demod_fused_ok(e->cfgs[ci])) fused = false;
         }
-    if (fused) {
+    if (scan_only) {
+    } else if (fused) {
         // one launch per rate class in use (CTAs of the other classes exit at once)
         for (int ci : used_cfg) { ax_launch_demod_fused_any<false>(w, e->cfgs[ci], ci, 0, e->stream, e->opt_rows32); e->launches++; }
         if (any_dec) { w.only_xf = 1; AX_LAUNCH(e, k_filter, (int64_t)w.nseg_total, w); w.only_xf = 0; }
     } else
+#else
+    if (!scan_only)
 #endif
     { AX_LAUNCH(e, k_filter, (int64_t)w.nseg_total, w); }
     AX_EVENT(b, 2);

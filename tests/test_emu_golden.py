@@ -146,3 +146,29 @@ def test_wired_cli_equals_reference_driven_by_internal_keys(eng, tmp_path):
     rows = [ln for ln in (tmp_path / "w.txt").read_text().splitlines() if ln[:8].strip().replace(".", "").isdigit() and "," in ln]
     assert len(rows) == min(g.meta["n_rows"], g.meta["n_hexframes"])
     assert [r.split(",")[1].strip() for r in rows] == g.hexframes[:len(rows)]
+
+
+def test_multi_drop_recording_is_cut_and_decoded_per_drop(eng):
+    """Three drops back to back in one recording: the segmentation driver finds them from the engine's
+    400 Hz level and every segment decodes exactly as the oracle decodes that segment on its own."""
+    import synth
+    from axctdprocessor_b200 import segment
+    from oracle import axctd_oracle as ao
+    from parity_util import check_against_oracle
+    specs = [synth.DropSpec(fs=44100, duration_s=52.0 + 3 * i, seed=400 + i, snr_db=30.0 - 8 * i) for i in range(3)]
+    pcm = np.concatenate([synth.generate_drop(s) for s in specs])
+    out = segment.process_recording(eng, pcm, 44100)
+    assert len(out) == 3
+    bounds = np.cumsum([0] + [int(round(s.duration_s * s.fs)) for s in specs])
+    for i, (a, b, res) in enumerate(out):
+        assert abs(a - bounds[i]) < 0.3 * 44100 or i == 0          # cut ~5 s before the pulse = start of the drop's lead-in
+        assert res.status == 0
+        seg = pcm[a:b]
+        cfg = eng.config(44100)
+        bt = eng.batch([len(seg)], [cfg])
+        bt.upload(0, seg)
+        bt.run()
+        full = dict(result=bt.result(0), bits=bt.bits(0), edges=bt.edges(0), power=bt.power(0))
+        bt.close()
+        check_against_oracle(full, ao.process_pcm(seg, 44100))
+        assert np.array_equal(res.rows["word"], full["result"].rows["word"])

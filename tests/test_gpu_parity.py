@@ -181,3 +181,23 @@ def test_full_size_round_trip_property(eng):
 def test_smoke_entry_point():
     import __graft_entry__ as ge
     ge.smoke()
+
+
+def test_multi_drop_recording_is_cut_and_decoded_per_drop(eng):
+    """BASELINE config 3 in miniature: several drops in one recording (also at 96 kHz, halved on the device).
+    The segmentation driver cuts it from the engine's own 400 Hz level; every segment decodes exactly as
+    the oracle decodes that segment on its own."""
+    from axctdprocessor_b200 import segment
+    from oracle import axctd_oracle as ao
+    for fs, dec in ((44100, 1), (96000, 2)):
+        specs = [synth.DropSpec(fs=fs, duration_s=52.0 + 3 * i, seed=500 + i, snr_db=30.0 - 8 * i) for i in range(3)]
+        pcm = np.concatenate([synth.generate_drop(s) for s in specs])
+        out = segment.process_recording(eng, pcm, fs / dec, decimate=dec)
+        assert len(out) == 3
+        for a, b, res in out:
+            assert res.status == 0
+            seg = pcm[a:b]
+            full = run_engine(eng, seg, fs)
+            op = ao.process_pcm(seg, fs)
+            check_against_oracle(full, op)
+            assert np.array_equal(res.rows["word"], full["result"].rows["word"])
