@@ -346,6 +346,8 @@ extern "C" int axctd_config_create(axctd_engine* e, const axctd_config_desc* ds,
                 if (m < AX_TB) ttab.t[m][q] = ds->tone_cs[6 * (size_t)m + q];
             }
         for (int q = 0; q < 6; ++q) c.tone_tsum[q] = (double)ts[q];
+        for (int j = 0; j < AX_TONE_ROT; ++j)
+            for (int q = 0; q < 6; ++q) c.tone_rot[j][q] = (j * AX_TB < c.n_power) ? ds->tone_cs[6 * (size_t)(j * AX_TB) + q] : 0.0;
     }
     c.min_r400 = ds->min_r400; c.min_dr7500 = ds->min_dr7500;
     c.min_r400_inprof = ds->min_r400 / 2; c.min_dr7500_inprof = ds->min_dr7500 / 2;     // AXCTDprocessor.py:226,228

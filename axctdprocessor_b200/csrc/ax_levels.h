@@ -171,15 +171,22 @@ AX_HD void ax_tonewin_partial(const AxWave& w, const AxDrop& dr, const AxCfg& c,
         a3 = ax_fma(xd, t3[m], a3); a4 = ax_fma(xd, t4[m], a4); a5 = ax_fma(xd, t5[m], a5);
     }
     a[0] = a0; a[1] = a1; a[2] = a2; a[3] = a3; a[4] = a4; a[5] = a5;
+    // block j sits m = head_n + AX_TB*jj samples into the window: e^{j theta m} = e^{j theta head_n} * e^{j theta AX_TB jj}
+    // (one broadcast row of the table and a small per-config table instead of a scattered table row per block)
     const int nblk = (int)(j1 - j0);
     const double* B0 = w.tb_sum + (dr.tb_base + j0) * 6;
+    double eh[6];
+    for (int q = 0; q < 6; ++q) eh[q] = c.tone_soa[(int64_t)q * np + head_n];
     for (int jj = lane; jj < nblk; jj += nl) {
         const double* B = B0 + 6 * jj;
-        const int m = head_n + jj * AX_TB;                               // e^{j theta_f (AX_TB*j - c)}
-        const double br0 = B[0], bi0 = B[1], br1 = B[2], bi1 = B[3], br2 = B[4], bi2 = B[5];
-        a[0] = ax_fma(br0, t0[m], ax_fma(-bi0, t1[m], a[0])); a[1] = ax_fma(br0, t1[m], ax_fma(bi0, t0[m], a[1]));
-        a[2] = ax_fma(br1, t2[m], ax_fma(-bi1, t3[m], a[2])); a[3] = ax_fma(br1, t3[m], ax_fma(bi1, t2[m], a[3]));
-        a[4] = ax_fma(br2, t4[m], ax_fma(-bi2, t5[m], a[4])); a[5] = ax_fma(br2, t5[m], ax_fma(bi2, t4[m], a[5]));
+        const double* R = c.tone_rot[jj];
+        for (int f = 0; f < 3; ++f) {
+            const double cr = ax_fma(eh[2 * f], R[2 * f], -(eh[2 * f + 1] * R[2 * f + 1]));
+            const double sn = ax_fma(eh[2 * f], R[2 * f + 1], eh[2 * f + 1] * R[2 * f]);
+            const double br = B[2 * f], bi = B[2 * f + 1];
+            a[2 * f] = ax_fma(br, cr, ax_fma(-bi, sn, a[2 * f]));
+            a[2 * f + 1] = ax_fma(br, sn, ax_fma(bi, cr, a[2 * f + 1]));
+        }
     }
 }
 AX_HD void ax_tonewin_finish(const AxWave& w, const AxCfg& c, const AxState& st, int64_t slot, const double* a) {

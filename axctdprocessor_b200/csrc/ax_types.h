@@ -56,6 +56,7 @@ AX_HD double ax_nan() { return nan(""); }
 #define AX_PEND 8           // pending bit-windows per thread in the filter pass
 #define AX_STAT_SLAB 16384  // samples per stats work item
 #define AX_TB 256           // samples per tone block (ax_toneblock_item)
+#define AX_TONE_ROT 24      // most tone blocks a window can span
 
 // fp32 phasor table of the bit windows (ax_window32): cos, sin of theta_mark * k and theta_space * k
 #define AX_WIN_TAPS 48
@@ -91,6 +92,7 @@ struct AxCfg {
     int32_t g_len, pad_g;
     int32_t lut_len, n_hist_edges;
     double tone_tsum[6];         // sum over the whole window of tone_cs (response to the constant -dc/ampl term)
+    double tone_rot[AX_TONE_ROT][6];   // tone_cs rows AX_TB * j: phasors that carry a tone block sum j blocks into a window
     // /2 decimation (AXCTDprocessor.py:60-62): forward-backward Chebyshev SOS with odd padding
     int32_t decimate, dnsec, dpad, dwarm;
     double dsos[AX_MAXSEC][6], dzi[AX_MAXSEC][2];
@@ -240,7 +242,7 @@ struct AxToneTab { double t[AX_TB][6]; };
 struct AxSrc { const int16_t* x; const double* xf; };
 AX_HD double ax_get(const AxSrc& s, int64_t n) { return s.xf ? s.xf[n] : (double)s.x[n]; }
 
-AX_HD bool ax_tone_blocked_ok(const AxCfg& c) { return c.n_power >= 2 * AX_TB; }
+AX_HD bool ax_tone_blocked_ok(const AxCfg& c) { return c.n_power >= 2 * AX_TB && c.n_power / AX_TB < AX_TONE_ROT; }
 
 AX_HD AxSrc ax_src(const AxWave& w, const AxDrop& dr) {
     AxSrc s;
