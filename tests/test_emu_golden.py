@@ -172,3 +172,30 @@ def test_multi_drop_recording_is_cut_and_decoded_per_drop(eng):
         bt.close()
         check_against_oracle(full, ao.process_pcm(seg, 44100))
         assert np.array_equal(res.rows["word"], full["result"].rows["word"])
+
+
+@pytest.mark.parametrize("case", ["clipped", "too_short", "one_chunk"])
+def test_edge_inputs_match_oracle(eng, case):
+    """Ingest edge cases: a sample at -32768 (np.abs wraps, AXCTDprocessor.py:56), a recording shorter than
+    4*N_power (run() never iterates, :295) and one that holds a single iteration."""
+    import synth
+    from oracle import axctd_oracle as ao
+    from parity_util import check_against_oracle
+    spec = synth.DropSpec(fs=44100, duration_s=48.0, seed=77, snr_db=25.0)
+    pcm = synth.generate_drop(spec).copy()
+    if case == "clipped":
+        pcm[1000] = -32768
+        pcm[2000:2010] = -32768
+    elif case == "too_short":
+        pcm = pcm[:17000]
+    else:
+        pcm = pcm[:60000]
+    out = run_engine(eng, pcm, spec.fs)
+    op = ao.process_pcm(pcm, spec.fs)
+    s = out["result"].summary
+    assert s.pcm_ampl == int(np.max(np.abs(pcm)))          # (wraps exactly like the reference's int16 abs)
+    assert s.n_chunks == len(op.trace)
+    if case == "clipped":
+        check_against_oracle(out, op)
+    else:
+        assert s.status == 0 and s.n_bits == 0 and s.n_frames == 0 and s.firstpulse400 == -1

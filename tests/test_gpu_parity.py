@@ -201,3 +201,29 @@ def test_multi_drop_recording_is_cut_and_decoded_per_drop(eng):
             op = ao.process_pcm(seg, fs)
             check_against_oracle(full, op)
             assert np.array_equal(res.rows["word"], full["result"].rows["word"])
+
+
+@pytest.mark.parametrize("case", ["clipped", "too_short", "one_chunk"])
+def test_edge_inputs_match_oracle(eng, case):
+    """Ingest edge cases on the CUDA path: a sample at -32768 (np.abs wraps, AXCTDprocessor.py:56; exercises
+    k_stats_wrap), a recording shorter than 4*N_power (:295) and one that holds a single iteration."""
+    from oracle import axctd_oracle as ao
+    spec = synth.DropSpec(fs=44100, duration_s=48.0, seed=77, snr_db=25.0)
+    pcm = synth.generate_drop(spec).copy()
+    if case == "clipped":
+        pcm[1000] = -32768
+        pcm[2000:2010] = -32768
+    elif case == "too_short":
+        pcm = pcm[:17000]
+    else:
+        pcm = pcm[:60000]
+    out = run_engine(eng, pcm, spec.fs)
+    op = ao.process_pcm(pcm, spec.fs)
+    s = out["result"].summary
+    assert s.pcm_ampl == int(np.max(np.abs(pcm)))
+    assert s.pcm_sum == int(pcm.astype(np.int64).sum())
+    assert s.n_chunks == len(op.trace)
+    if case == "clipped":
+        check_against_oracle(out, op)
+    else:
+        assert s.status == 0 and s.n_bits == 0 and s.n_frames == 0 and s.firstpulse400 == -1
