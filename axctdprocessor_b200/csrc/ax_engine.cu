@@ -283,7 +283,6 @@ extern "C" int axctd_engine_set_option(axctd_engine* e, const char* name, double
     return AXCTD_OK;
 }
 
-static int64_t ax_gcd(int64_t a, int64_t b) { while (b) { int64_t t = a % b; a = b; b = t; } return a; }
 
 template <typename T>
 static int ax_cfg_upload(axctd_engine* e, const T** dst, const T* src, size_t count) {
@@ -319,11 +318,7 @@ extern "C" int axctd_config_create(axctd_engine* e, const axctd_config_desc* ds,
     c.warm = warm;
     c.head = e->opt_exact_head > 0 ? e->opt_exact_head : warm;
     if (c.head < c.pad + 8) c.head = c.pad + 8;
-    c.rebase = ds->bit_cs_len - 1;
     c.head_zc_cap = c.head / 4 + 64;
-    c.ybuf_len = c.head + c.npcm + 2;
-    const int64_t G = ax_gcd(c.n_power, c.d_pcm);
-    c.tone_G = (int)G; c.tone_nb = (int)(c.n_power / G); c.tone_stride = (int)(c.d_pcm / G);
     c.decimate = ds->decimate == 2 ? 2 : 1;
     if (c.decimate == 2) {
         if (ds->decim_sections < 1 || ds->decim_sections > AX_MAXSEC || ds->decim_padlen < 1 ||
@@ -361,8 +356,6 @@ extern "C" int axctd_config_create(axctd_engine* e, const axctd_config_desc* ds,
     c.h2s = (int64_t)(fs * 10.5); c.h2e = (int64_t)(fs * 14.8);                           // :451-452
     c.h3s = (int64_t)(fs * 20); c.h3e = (int64_t)(fs * 24.5);                             // :455-456
     c.half = (int64_t)(fs * 0.5);
-    const double* bc = ds->bit_cs + 4 * (size_t)c.rebase;      // e^{+j theta R}; store the conjugate
-    c.rot[0][0] = bc[0]; c.rot[0][1] = -bc[1]; c.rot[1][0] = bc[2]; c.rot[1][1] = -bc[3];
     c.lut_len = ds->lut_len; c.n_hist_edges = ds->n_hist_edges;
     if (ds->bit_cs_len < AX_WIN_TAPS) { e->err = "bit_cs table shorter than 48 entries"; return AXCTD_ERR_ARG; }
     for (int k = 0; k < AX_WIN_TAPS; ++k) {
@@ -401,8 +394,7 @@ extern "C" int axctd_config_create(axctd_engine* e, const axctd_config_desc* ds,
         c.g_len = GL;
         if (ax_cfg_upload(e, &c.gtab, g.data(), g.size()) || ax_cfg_upload(e, &c.gcum, gc.data(), gc.size())) return AXCTD_ERR_CUDA;
     }
-    if (ax_cfg_upload(e, &c.bit_cs, ds->bit_cs, 4 * (size_t)ds->bit_cs_len) ||
-        ax_cfg_upload(e, &c.tone_cs, ds->tone_cs, 6 * (size_t)ds->n_power) ||
+    if (ax_cfg_upload(e, &c.tone_cs, ds->tone_cs, 6 * (size_t)ds->n_power) ||
         ax_cfg_upload(e, &c.lut, ds->temp_lut, (size_t)ds->lut_len) ||
         ax_cfg_upload(e, &c.hist_edges, ds->hist_edges, (size_t)ds->n_hist_edges) ||
         ax_cfg_upload(e, &c.hist_centers, ds->hist_centers, (size_t)ds->n_hist_edges - 1)) return AXCTD_ERR_CUDA;
@@ -442,7 +434,7 @@ extern "C" int axctd_batch_create(axctd_engine* e, int n_drops, const int64_t* n
     for (int i = 0; i < 6; ++i) cudaEventCreate(&b->ev[i]);
 #endif
     int64_t total = 0;
-    int warm_max = 0, head_cap_max = 0, ybuf_max = 0, chunk_len_max = 0;
+    int warm_max = 0, head_cap_max = 0, chunk_len_max = 0;
     for (int d = 0; d < n_drops; ++d) {
         if (config_id[d] < 0 || config_id[d] >= (int)e->cfgs.size() || n_samples[d] < 0 || n_samples[d] > 2000000000LL) {
             e->err = "bad drop descriptor"; axctd_batch_destroy(b); return AXCTD_ERR_ARG;
@@ -451,10 +443,9 @@ extern "C" int axctd_batch_create(axctd_engine* e, int n_drops, const int64_t* n
         total += n_samples[d];
         warm_max = std::max(warm_max, c.warm);
         head_cap_max = std::max(head_cap_max, c.head_zc_cap);
-        ybuf_max = std::max(ybuf_max, c.ybuf_len);
         chunk_len_max = std::max(chunk_len_max, c.chunk_len);
     }
-    if (e->opt_force_exact) { ybuf_max = chunk_len_max + 8; head_cap_max = chunk_len_max / 4 + 64; }
+    if (e->opt_force_exact) head_cap_max = chunk_len_max / 4 + 64;
     // segment length of the continuous pass: enough threads to fill the GPU, little warm-up waste
     int64_t L = e->opt_segment_len;
     if (L > 0) L = ((L + 63) / 64) * 64;
@@ -468,7 +459,7 @@ extern "C" int axctd_batch_create(axctd_engine* e, int n_drops, const int64_t* n
     w.seg_len = (int32_t)L; w.seg_cap = (int32_t)(L / 8 + 32);
     w.guard = e->opt_guard; w.tone_direct = e->opt_tone_direct; w.force_exact = e->opt_force_exact;
     w.bit_tol = e->opt_bit_tol; w.hist_tol = e->opt_hist_tol; w.bitfix_all = e->opt_bitfix_all;
-    w.head_zc_cap_max = head_cap_max; w.ybuf_len_max = ybuf_max;
+    w.head_zc_cap_max = head_cap_max;
     b->drops.resize(n_drops);
     int64_t pcm_off = 0, zc_off = 0, edge_off = 0, tb_off = 0, xf_off = 0, fwd_off = 0;
     int32_t ntb_max = 0, dseg_off = 0;

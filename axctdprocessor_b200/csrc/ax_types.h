@@ -71,17 +71,12 @@ struct AxCfg {
     double sos[AX_MAXSEC][6];
     int32_t warm;                // warm-up overlap of the continuous filter pass (samples)
     int32_t head;                // exact zero-state prefix recomputed per chunk (samples)
-    int32_t rebase;              // phase re-anchoring period of the bit-window prefix sums
-    int32_t head_zc_cap;         // crossings kept per exact head
-    int32_t ybuf_len;            // head + npcm + 2
-    int32_t tone_G, tone_nb, tone_stride;   // block decomposition of the tone windows
+    int32_t head_zc_cap;         // crossings kept per chunk head
     double min_r400, min_dr7500, min_r400_inprof, min_dr7500_inprof;
     double trig_from, trig_to, scale0;
     double zc[4], tc[4], cc[4], tlims[2], slims[2];
     int64_t off_4p5, off_5p5, off_trig_from, off_trig_to;          // int(f_s*x)
     int64_t h1s, h1e, h2s, h2e, h3s, h3e, half;                    // AXCTDprocessor.py:447-456
-    double rot[2][2];            // cos,sin of (-theta_f * rebase), f = mark, space
-    const double* bit_cs;        // [rebase+1][4]
     const double* tone_cs;       // [n_power][6]
     const double* tone_soa;      // [6][n_power] the same table, one array per component (coalesced reads in ax_tonewin_partial)
     const double* lut;           // [lut_len]
@@ -206,7 +201,7 @@ struct AxWave {
     AxChunk* chunk;
     int32_t* head_idx; float* head_a1; float* head_a2;      // [chunk][head_zc_cap_max] crossings of the zero-state heads
     int32_t* head_cnt;                                      // [chunk] how many (-1: did not fit)
-    int32_t head_zc_cap_max, ybuf_len_max;
+    int32_t head_zc_cap_max, pad_head;
     // tone powers
     double* pw_raw;              // [3][pw_total]
     double* pw_sm;               // [3][pw_total]
