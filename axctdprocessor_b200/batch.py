@@ -68,3 +68,59 @@ def gather_results(local: dict, world_size: int, rank: int, all_gather_object: C
     for part in bucket:
         merged.update(part)
     return merged
+
+
+class PipelinedDecoder:
+    """Ingest pipeline for a stream of batches on one GPU.
+
+    Two engines (two CUDA streams) take alternate batches: ``submit`` enqueues the host->device copy of a
+    batch on its engine's stream and returns at once, ``collect`` runs the decode of the oldest submitted
+    batch and returns its results, so the copy of batch i+1 overlaps the decode of batch i.  Host buffers
+    should be pinned (e.g. ``torch.empty(..).pin_memory()``) for the copies to be asynchronous."""
+
+    def __init__(self, device: int = 0, slots: int = 2, engine_options=None, engine_factory=None):
+        from . import engine as _engine
+        make = engine_factory or (lambda: _engine.Engine(device))      # (tests inject the host emulation here)
+        self.engines = [make() for _ in range(slots)]
+        for e in self.engines:
+            for k, v in (engine_options or {}).items():
+                e.set_option(k, v)
+        self._batches = [None] * slots          # (key, Batch) cached per slot: same shapes reuse the allocation
+        self._pending = []                      # slots in submission order
+        self._next = 0
+
+    def close(self):
+        for kb in self._batches:
+            if kb:
+                kb[1].close()
+        for e in self.engines:
+            e.close()
+        self._batches, self.engines = [], []
+
+    def submit(self, host_ptrs, n_samples, fs_list, settings=None, triggerrange=None):
+        """Enqueue one batch: host_ptrs[i] = address of n_samples[i] int16 samples at rate fs_list[i]."""
+        slot = self._next
+        self._next = (self._next + 1) % len(self.engines)
+        if slot in self._pending:
+            raise RuntimeError("collect() the oldest batch before submitting more than `slots` batches")
+        eng = self.engines[slot]
+        key = (tuple(int(x) for x in n_samples), tuple(float(f) for f in fs_list), repr(settings), repr(triggerrange))
+        cached = self._batches[slot]
+        if cached is None or cached[0] != key:
+            if cached:
+                cached[1].close()
+            cfgs = [eng.config(fs, settings=settings, triggerrange=triggerrange) for fs in fs_list]
+            cached = (key, eng.batch(list(n_samples), cfgs))
+            self._batches[slot] = cached
+        b = cached[1]
+        for i, (p, n) in enumerate(zip(host_ptrs, n_samples)):
+            b.upload_ptr(i, int(p), int(n))
+        self._pending.append(slot)
+        return slot
+
+    def collect(self, full: bool = False):
+        """Decode the oldest submitted batch and return its DropResults."""
+        slot = self._pending.pop(0)
+        b = self._batches[slot][1]
+        b.run()
+        return [b.result(i, full=full) for i in range(b.n)]

@@ -199,3 +199,41 @@ def test_edge_inputs_match_oracle(eng, case):
         check_against_oracle(out, op)
     else:
         assert s.status == 0 and s.n_bits == 0 and s.n_frames == 0 and s.firstpulse400 == -1
+
+
+def test_random_batch_matches_oracle(eng):
+    """Four drops of mixed rate / SNR / length decoded as one batch, each compared with the oracle."""
+    import synth
+    from oracle import axctd_oracle as ao
+    from parity_util import check_against_oracle
+    rng = np.random.default_rng(2025)
+    specs = [synth.DropSpec(fs=int(rng.choice([44100, 48000])), duration_s=float(rng.uniform(45.0, 60.0)), seed=800 + i,
+                            snr_db=float(rng.uniform(6.0, 40.0)), tone_after_pulse_s=float(rng.uniform(30.5, 36.0)))
+             for i in range(4)]
+    pcms = [synth.generate_drop(s) for s in specs]
+    b = eng.batch([len(p) for p in pcms], [eng.config(s.fs) for s in specs])
+    for i, p in enumerate(pcms):
+        b.upload(i, p)
+    b.run()
+    outs = [dict(result=b.result(i), bits=b.bits(i), edges=b.edges(i), power=b.power(i)) for i in range(len(specs))]
+    b.close()
+    for s, p, out in zip(specs, pcms, outs):
+        check_against_oracle(out, ao.process_pcm(p, s.fs))
+
+
+def test_pipelined_decoder_returns_the_same_results(eng):
+    """batch.PipelinedDecoder (two engines taking alternate batches) against a plain batch."""
+    import synth
+    from axctdprocessor_b200 import batch as axbatch
+    specs = [synth.DropSpec(fs=(44100, 48000)[i % 2], duration_s=46.0, seed=900 + i, snr_db=20.0) for i in range(4)]
+    pcms = [np.ascontiguousarray(synth.generate_drop(s)) for s in specs]
+    ref = axbatch.process_drops(eng, pcms, [s.fs for s in specs])
+    pipe = axbatch.PipelinedDecoder(slots=2, engine_factory=emu_engine)
+    groups = [[0, 1], [2, 3]]
+    pipe.submit([pcms[i].ctypes.data for i in groups[0]], [len(pcms[i]) for i in groups[0]], [specs[i].fs for i in groups[0]])
+    pipe.submit([pcms[i].ctypes.data for i in groups[1]], [len(pcms[i]) for i in groups[1]], [specs[i].fs for i in groups[1]])
+    got = pipe.collect() + pipe.collect()
+    pipe.close()
+    for r, g in zip(ref, got):
+        assert r.status == 0 and g.status == 0
+        assert np.array_equal(r.rows, g.rows)

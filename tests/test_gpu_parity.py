@@ -227,3 +227,21 @@ def test_edge_inputs_match_oracle(eng, case):
         check_against_oracle(out, op)
     else:
         assert s.status == 0 and s.n_bits == 0 and s.n_frames == 0 and s.firstpulse400 == -1
+
+
+def test_random_batch_matches_oracle(eng):
+    """Twelve drops of mixed rate / SNR / length decoded as one batch, each compared with the oracle."""
+    from oracle import axctd_oracle as ao
+    rng = np.random.default_rng(2024)
+    specs = [synth.DropSpec(fs=int(rng.choice([44100, 48000])), duration_s=float(rng.uniform(45.0, 70.0)), seed=700 + i,
+                            snr_db=float(rng.uniform(6.0, 40.0)), tone_after_pulse_s=float(rng.uniform(30.5, 36.0)))
+             for i in range(12)]
+    pcms = [synth.generate_drop(s) for s in specs]
+    b = eng.batch([len(p) for p in pcms], [eng.config(s.fs) for s in specs])
+    for i, p in enumerate(pcms):
+        b.upload(i, p)
+    b.run()
+    outs = [dict(result=b.result(i), bits=b.bits(i), edges=b.edges(i), power=b.power(i)) for i in range(len(specs))]
+    b.close()
+    for s, p, out in zip(specs, pcms, outs):
+        check_against_oracle(out, ao.process_pcm(p, s.fs))
