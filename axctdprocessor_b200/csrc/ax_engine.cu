@@ -787,7 +787,10 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
     AX_LAUNCH1(e, k_canon, n, w);
 #endif
     for (int it = 0;; ++it) {
-        AX_LAUNCH1(e, k_chain, n, w);
+#ifndef AXCTD_EMU
+        if (e->opt_filter_variant == 0) { k_chain_warp<<<n, 32, 0, e->stream>>>(w); e->launches++; } else
+#endif
+        { AX_LAUNCH1(e, k_chain, n, w); }
         if (e->opt_inject_misspec && it == 0) AX_LAUNCH(e, k_inject, n, w);
 #ifndef AXCTD_EMU
         if (e->opt_filter_variant == 0) {
@@ -802,18 +805,27 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
 #endif
         { AX_LAUNCH(e, k_headfilt, b->chunk_total, w, 0); }
         AX_LAUNCH(e, k_headwalk, b->chunk_total, w);
-        AX_LAUNCH1(e, k_verify, n, w);
+#ifndef AXCTD_EMU
+        if (e->opt_filter_variant == 0) { k_verify_warp<<<n, 32, 0, e->stream>>>(w); e->launches++; } else
+#endif
+        { AX_LAUNCH1(e, k_verify, n, w); }
         if (ax_d2h(e, flags, w.flags, sizeof(flags)) || ax_sync(e)) return AXCTD_ERR_CUDA;
         if (!flags[AX_FLAG_DIRTY]) break;
         if (it >= e->opt_max_fixups) { e->err = "chunk chain did not converge"; return AXCTD_ERR_STATE; }
         if (ax_zero(e, w.flags, sizeof(int32_t))) return AXCTD_ERR_CUDA;
     }
-    AX_LAUNCH1(e, k_plan_tones, n, w);
+#ifndef AXCTD_EMU
+    if (e->opt_filter_variant == 0) { k_plan_tones_warp<<<n, 32, 0, e->stream>>>(w); e->launches++; } else
+#endif
+    { AX_LAUNCH1(e, k_plan_tones, n, w); }
     AX_LAUNCH(e, k_pwfill, b->chunk_total, w, 1);
     ax_run_tones(b, 1);
     AX_LAUNCH(e, k_levels, (int64_t)w.pw_total, w, 1);
     AX_LAUNCH1(e, k_sm, n, w, 1);
-    AX_LAUNCH1(e, k_offsets, n, w);
+#ifndef AXCTD_EMU
+    if (e->opt_filter_variant == 0) { k_offsets_warp<<<n, 32, 0, e->stream>>>(w); e->launches++; } else
+#endif
+    { AX_LAUNCH1(e, k_offsets, n, w); }
 #ifndef AXCTD_EMU
     k_emit_chunk<<<(unsigned)b->chunk_total, 128, 0, e->stream>>>(w); e->launches++;
 #else

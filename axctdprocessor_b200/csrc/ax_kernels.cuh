@@ -812,6 +812,179 @@ __global__ void __launch_bounds__(128) k_emit_chunk(AxWave w) {
     }
 }
 
+// ------------------------------------------------------------------ per-drop bookkeeping, one warp per drop
+// Same results as ax_verify_item / ax_offsets_item / ax_plan_tones_item / ax_chain_item; the loops over the
+// run() iterations of a drop advance 32 iterations per step (ballot / scan), and the chain uses the lanes to
+// fetch the handful of table entries each step needs in one round instead of one dependent load after another.
+__device__ __forceinline__ int ax_warp_excl_scan(int v, int lane, int* total) {
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    *total = __shfl_sync(0xffffffffu, x, 31);
+    return x - v;
+}
+
+__global__ void __launch_bounds__(32) k_verify_warp(AxWave w) {
+    const int d = blockIdx.x, lane = threadIdx.x;
+    AxState& st = w.st[d];
+    if (st.status != 0 || st.sm_status < 1 || st.chain_end) return;
+    const AxDrop& dr = w.drop[d];
+    const AxCfg& c = w.cfg[dr.cfg];
+    AxChunk* ch = w.chunk + dr.chunk_base;
+    const int k0 = st.chain_from, k1 = st.n_chunks;
+    __syncwarp();
+    if (lane == 0) st.chain_dirty = 0;
+    for (int kb = k0; kb < k1; kb += 32) {
+        const int k = kb + lane;
+        int code = 0;                                   // 1 error, 2 start index would become a float, 3 mis-speculated
+        if (k < k1) {
+            if (ch[k].err) code = 1;
+            else if (ch[k].true_last - ch[k].s - 1 <= c.pad) code = 2;
+            else if (ch[k].true_last != ch[k].spec_last) code = 3;
+        }
+        const unsigned ball = __ballot_sync(0xffffffffu, code != 0);
+        if (ball) {
+            if (lane == __ffs((int)ball) - 1) {         // the first iteration that stops the scan, as the sequential form
+                if (code == 1) { ax_raise(st, ch[k].err, k); st.n_chunks = k + 1; st.chain_from = k + 1; st.chain_end = 1; }
+                else if (code == 2) {
+                    const double sf = (double)ch[k].s + c.fs / (double)c.bitrate;       // AXCTDprocessor.py:331
+                    if (!((double)dr.n - sf < 4.0 * c.n_power)) ax_raise(st, AXCTD_DROP_FLOAT_INDEX, k + 1);
+                    st.n_chunks = k + 1; st.chain_from = k + 1; st.chain_end = 1;
+                } else { st.n_fixups++; st.chain_from = k + 1; st.chain_dirty = 1; w.flags[AX_FLAG_DIRTY] = 1; }
+            }
+            return;
+        }
+    }
+    if (lane == 0) { st.chain_from = st.n_chunks; st.chain_end = 1; }
+}
+
+__global__ void __launch_bounds__(32) k_offsets_warp(AxWave w) {
+    const int d = blockIdx.x, lane = threadIdx.x;
+    const AxDrop& dr = w.drop[d];
+    AxState& st = w.st[d];
+    if (st.sm_status < 1) { if (lane == 0) { st.nbits_total = 0; st.nedges_total = 0; } return; }
+    AxChunk* ch = w.chunk + dr.chunk_base;
+    const int k0 = st.k0, k1 = st.n_chunks;
+    int64_t nb = 0, ne = 0;
+    for (int kb = k0; kb < k1; kb += 32) {
+        const int k = kb + lane;
+        const int n = (k < k1 && ch[k].n_edges > 0) ? ch[k].n_edges : 0;
+        int tot_e, tot_b;
+        const int pe = ax_warp_excl_scan(n, lane, &tot_e);
+        const int pb = ax_warp_excl_scan(n > 0 ? n - 1 : 0, lane, &tot_b);
+        if (k < k1) { ch[k].bit_off = nb + pb; ch[k].edge_off = ne + pe; }
+        nb += tot_b; ne += tot_e;
+    }
+    if (lane == 0) {
+        if (ne > dr.edge_cap) { ax_raise(st, AXCTD_DROP_CAPACITY, -1); w.flags[AX_FLAG_CAP] = 1; nb = 0; ne = 0; }
+        st.nbits_total = nb; st.nedges_total = ne;
+    }
+}
+
+__global__ void __launch_bounds__(32) k_plan_tones_warp(AxWave w) {
+    const int d = blockIdx.x, lane = threadIdx.x;
+    const AxDrop& dr = w.drop[d];
+    AxState& st = w.st[d];
+    if (st.sm_status < 1) return;
+    const AxCfg& c = w.cfg[dr.cfg];
+    AxChunk* ch = w.chunk + dr.chunk_base;
+    const int k0 = st.k0 + 1, k1 = st.n_chunks;
+    int32_t pc = ch[st.k0].pw_off + ch[st.k0].np;
+    bool small = false;
+    for (int kb = k0; kb < k1; kb += 32) {
+        const int k = kb + lane;
+        const int np = k < k1 ? ax_grid_count(ch[k].s, ch[k].e, c) : 0;
+        int tot;
+        const int pre = ax_warp_excl_scan(np, lane, &tot);
+        const bool over = k < k1 && pc + pre + np > dr.pw_cap;
+        const unsigned ball = __ballot_sync(0xffffffffu, over);
+        const int stop = ball ? __ffs((int)ball) - 1 : 32;      // first lane whose samples do not fit
+        if (k < k1 && lane <= stop) {
+            AxChunk& q = ch[k];
+            q.pw_off = pc + pre; q.np = lane == stop ? 0 : np;
+            q.status = 0; q.n_rows = 0; q.n_hex = 0; q.frame_begin = q.frame_end = 0; q.scale = c.scale0; q.mean7500 = ax_nan();
+            if (lane < stop && np < 10) small = true;
+        }
+        if (ball) {
+            if (lane == stop) { ax_raise(st, AXCTD_DROP_CAPACITY, k); w.flags[AX_FLAG_CAP] = 1; st.n_chunks = k; }
+            break;
+        }
+        pc += tot;
+    }
+    if (__any_sync(0xffffffffu, small) && lane == 0) st.par_levels = 0;
+}
+
+// ax_chain_item with the lanes fetching in parallel.  Per run() iteration three rounds of loads: the crossings
+// around the predicted end of the chunk (lane i looks at ordinal guess-16+i), the canonical masks of the tiles
+// that can hold the stopping crossing, and the two crossing indices that fix the next start.
+__global__ void __launch_bounds__(32) k_chain_warp(AxWave w) {
+    const int d = blockIdx.x, lane = threadIdx.x;
+    AxState& st = w.st[d];
+    if (st.status != 0 || st.sm_status < 1 || st.chain_end) return;
+    const AxDrop& dr = w.drop[d];
+    const AxCfg& c = w.cfg[dr.cfg];
+    AxChunk* ch = w.chunk + dr.chunk_base;
+    const int32_t* zi = w.zc_idx + dr.zc_base;
+    const uint8_t* nx = w.zc_nx + dr.zc_base;
+    const uint64_t* cmask = w.cmask + dr.tile_base;
+    const int64_t M = st.zc_count;
+    int k = st.chain_from;
+    int64_t s;
+    if (k == st.k0) s = ch[k].s;
+    else s = ch[k - 1].true_last - 1 - c.pad;
+    int64_t entry = -1, span = (int64_t)c.chunk_len / 37;
+    int n_chunks_out = -1;
+    for (;; ++k) {
+        if (dr.n - s < 4 * (int64_t)c.n_power) { n_chunks_out = k; break; }
+        if (k >= dr.chunk_cap) { if (lane == 0) { ax_raise(st, AXCTD_DROP_CAPACITY, k); w.flags[AX_FLAG_CAP] = 1; } n_chunks_out = k; break; }
+        int64_t e = s + c.chunk_len;
+        if (e >= dr.n) e = dr.n - 1;
+        if (lane == 0) { ch[k].s = s; ch[k].e = e; ch[k].err = 0; ch[k].n_edges = 0; ch[k].spec_last = -1; }
+        if (entry < 0) entry = ax_lower_bound(zi, M, s + c.pad);            // (all lanes: same result)
+        // ---- q = last ordinal with zi <= e-2: look at 32 ordinals around the guess
+        int64_t q;
+        {
+            const int64_t g0 = entry + span - 15;
+            const int64_t mine = g0 + lane;
+            const bool le = mine < 0 ? true : (mine >= M ? false : (int64_t)zi[mine] <= e - 2);
+            const unsigned ball = __ballot_sync(0xffffffffu, le);
+            if (ball != 0u && ball != 0xffffffffu) q = g0 + (31 - __clz((int)ball));        // zi is ascending: le is a prefix
+            else q = ax_upper_bound_from(zi, M, e - 2, entry + span) - 1;
+        }
+        if (entry > q) { n_chunks_out = k + 1; break; }
+        span = q - entry;
+        // ---- where the walk stops (ax_walk_end without the step count)
+        const int64_t X = q - 4;
+        int64_t pos = entry;
+        while (pos < X) {
+            const int64_t t = pos / AX_TILE, tx = X / AX_TILE;
+            // lanes 0,1,2: masks of the entry tile and of the two tiles that can hold the stop
+            const int64_t tl = lane == 0 ? t : tx + (lane - 1);
+            const uint64_t mv = (lane < 3) ? cmask[tl] : 0ull;
+            const uint64_t m_t = __shfl_sync(0xffffffffu, mv, 0), m_x = __shfl_sync(0xffffffffu, mv, 1), m_x1 = __shfl_sync(0xffffffffu, mv, 2);
+            if ((m_t >> (pos - t * AX_TILE)) & 1ull) {                       // on the canonical walk: jump
+                uint64_t m = m_x & ~((1ull << (X - tx * AX_TILE)) - 1ull);
+                int64_t tt = tx;
+                if (!m) { m = m_x1; tt = tx + 1; }
+                while (!m) m = cmask[++tt];
+                pos = tt * AX_TILE + ax_ctz64(m);
+                break;
+            }
+            pos += nx[pos];
+        }
+        // ---- the crossing indices that fix the next start
+        const int64_t pl = pos - (lane & 1);
+        const int32_t zv = (lane < 2 && pl >= 0) ? zi[pl] : 0;
+        const int64_t zpos = __shfl_sync(0xffffffffu, zv, 0), zprev = __shfl_sync(0xffffffffu, zv, 1);
+        if (lane == 0) ch[k].spec_last = zpos;
+        const int64_t next_ind = zpos - s - 1;                               // demodulate.py:104
+        if (next_ind <= c.pad) { n_chunks_out = k + 1; break; }
+        s = s + next_ind - c.pad;
+        entry = (pos > 0 && zprev >= zpos - 1) ? pos - 1 : pos;
+    }
+    if (lane == 0) st.n_chunks = n_chunks_out;
+}
+
 // ------------------------------------------------------------------ scale calibration (CTA per drop)
 // ax_scale_item with the histogram filled by the whole CTA (shared-memory atomics).
 __global__ void __launch_bounds__(128) k_scale_block(AxWave w) {
