@@ -81,13 +81,13 @@ class Chunk(C.Structure):
 
 class Row(C.Structure):
     _fields_ = [
-        ("word", C.c_uint32), ("flags", C.c_int32),
-        ("time_c", C.c_int32), ("depth_c", C.c_int32), ("temperature_c", C.c_int32), ("conductivity_c", C.c_int32),
-        ("salinity_c", C.c_int32), ("r400_c", C.c_int32), ("r7500_c", C.c_int32),
+        ("word", C.c_uint32), ("time_c", C.c_int32), ("depth_c", C.c_int32),
+        ("temperature_c", C.c_int16), ("conductivity_c", C.c_int16), ("salinity_c", C.c_int16),
+        ("r400_c", C.c_int16), ("r7500_c", C.c_int16), ("flags", C.c_uint16),
     ]
 
 
-ROW_KEEP, ROW_HEX, ROW_WIDE, ROW_NAN = 1, 2, 4, -2147483648
+ROW_KEEP, ROW_HEX, ROW_WIDE, ROW_NAN, ROW_NAN16 = 1, 2, 4, -2147483648, -32768
 
 
 class SynthDesc(C.Structure):

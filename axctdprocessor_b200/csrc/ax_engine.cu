@@ -851,7 +851,10 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
     AX_LAUNCH(e, k_pack, b->edge_total / 32, w);
     AX_LAUNCH(e, k_valid, b->edge_total / 32, w);
     AX_LAUNCH(e, k_frames_spec, b->chunk_total, w);
-    AX_LAUNCH1(e, k_frames_chain, n, w);
+#ifndef AXCTD_EMU
+    if (e->opt_filter_variant == 0) { k_frames_chain_warp<<<n, 32, 0, e->stream>>>(w); e->launches++; } else
+#endif
+    { AX_LAUNCH1(e, k_frames_chain, n, w); }
     AX_LAUNCH(e, k_frames_write, b->chunk_total, w);
     AX_LAUNCH(e, k_calib, b->frame_total, w);
 #ifndef AXCTD_EMU

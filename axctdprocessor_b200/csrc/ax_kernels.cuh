@@ -985,6 +985,69 @@ __global__ void __launch_bounds__(32) k_chain_warp(AxWave w) {
     if (lane == 0) st.n_chunks = n_chunks_out;
 }
 
+// ax_frames_chain_item, 32 run() iterations per step: a speculative scan is right when it started where the
+// previous non-empty iteration's scan ended; the first one that did not is redone by one lane (rare), after
+// which the group is retried from the next iteration.
+__global__ void __launch_bounds__(32) k_frames_chain_warp(AxWave w) {
+    const int d = blockIdx.x, lane = threadIdx.x;
+    const AxDrop& dr = w.drop[d];
+    AxState& st = w.st[d];
+    if (lane == 0) st.n_frames = 0;
+    if (st.status != 0 || st.sm_status < 2 || st.k2 < 0 || st.nedges_total == 0) return;
+    AxChunk* ch = w.chunk + dr.chunk_base;
+    const int k1 = st.n_chunks;
+    int64_t cur = 0;
+    int32_t nf = 0;
+    int kb = st.k2;
+    while (kb < k1) {
+        const int k = kb + lane;
+        const bool in = k < k1;
+        const bool ne = in && ch[k].n_edges > 0;
+        const int64_t sfrom = ne ? ch[k].scan_from : 0, send = ne ? ch[k].scan_end : 0;
+        const int cnt = ne ? ch[k].scan_cnt : 0;
+        const unsigned nem = __ballot_sync(0xffffffffu, ne);
+        const unsigned below = nem & ((1u << lane) - 1u);
+        const int prev = below ? 31 - __clz((int)below) : -1;
+        const int64_t pend = __shfl_sync(0xffffffffu, send, prev < 0 ? 0 : prev);
+        const int64_t expect = prev < 0 ? cur : pend;
+        const unsigned bad = __ballot_sync(0xffffffffu, ne && sfrom != expect);
+        const int nok = bad ? __ffs((int)bad) - 1 : 32;          // lanes [0, nok) are consistent
+        int tot;
+        const int pre = ax_warp_excl_scan(lane < nok ? cnt : 0, lane, &tot);
+        const unsigned over = __ballot_sync(0xffffffffu, in && lane < nok && nf + pre + cnt > dr.frame_cap);
+        if (over) {
+            if (lane == __ffs((int)over) - 1) { ax_raise(st, AXCTD_DROP_CAPACITY, k); w.flags[AX_FLAG_CAP] = 1; }
+            return;
+        }
+        if (in && lane < nok) { ch[k].frame_begin = nf + pre; ch[k].frame_end = nf + pre + cnt; }
+        nf += tot;
+        {   // carry: end of the last non-empty consistent iteration
+            const unsigned okne = nem & (nok >= 32 ? 0xffffffffu : ((1u << nok) - 1u));
+            if (okne) cur = __shfl_sync(0xffffffffu, send, 31 - __clz((int)okne));
+        }
+        if (nok >= 32) { kb += 32; continue; }
+        // iteration kb + nok started from the wrong bit: redo its scan from the true start
+        const int kk = kb + nok;
+        int err = 0;
+        int32_t c2 = 0; int64_t e2 = 0;
+        if (lane == 0) {
+            err = ax_frames_scan(w, dr, st, ch[kk], kk, cur, nullptr, 0x7fffffff, &c2, &e2);
+            if (err) ax_raise(st, err, kk);
+            else {
+                ch[kk].scan_from = cur; ch[kk].scan_cnt = c2; ch[kk].scan_end = e2; st.n_frame_respec++;
+                if (nf + c2 > dr.frame_cap) { ax_raise(st, AXCTD_DROP_CAPACITY, kk); w.flags[AX_FLAG_CAP] = 1; err = 1; }
+                else { ch[kk].frame_begin = nf; ch[kk].frame_end = nf + c2; }
+            }
+        }
+        err = __shfl_sync(0xffffffffu, err, 0);
+        if (err) return;
+        nf += __shfl_sync(0xffffffffu, c2, 0);
+        cur = __shfl_sync(0xffffffffu, e2, 0);
+        kb = kk + 1;
+    }
+    if (lane == 0) st.n_frames = nf;
+}
+
 // ------------------------------------------------------------------ scale calibration (CTA per drop)
 // ax_scale_item with the histogram filled by the whole CTA (shared-memory atomics).
 __global__ void __launch_bounds__(128) k_scale_block(AxWave w) {

@@ -416,10 +416,10 @@ AX_HDN inline void ax_qc_item(const AxWave& w, int64_t cg, double* scratch) {
 }
 
 // ---- results as they leave the device ---------------------------------------------------------
-AX_HD int32_t ax_centi(double v, int32_t* flags) {                 // v is already np.round(v, 2)
-    if (isnan(v)) return AXCTD_ROW_NAN;
+AX_HD int32_t ax_centi(double v, int32_t* flags, bool narrow) {    // v is already np.round(v, 2)
+    if (isnan(v)) return narrow ? AXCTD_ROW_NAN16 : AXCTD_ROW_NAN;
     const double q = rint(ax_mul(v, 100.0));
-    if (!(fabs(q) < 2147483000.0) || ax_div(q, 100.0) != v) { *flags |= AXCTD_ROW_WIDE; return 0; }
+    if (!(fabs(q) < (narrow ? 32767.0 : 2147483000.0)) || ax_div(q, 100.0) != v) { *flags |= AXCTD_ROW_WIDE; return 0; }
     return (int32_t)q;
 }
 AX_HDN inline void ax_row_item(const AxWave& w, int64_t fg) {
@@ -431,10 +431,11 @@ AX_HDN inline void ax_row_item(const AxWave& w, int64_t fg) {
     axctd_row r;
     r.word = f.word;
     int32_t fl = (f.keep ? AXCTD_ROW_KEEP : 0) | (f.hex_returned ? AXCTD_ROW_HEX : 0);
-    r.time_c = ax_centi(f.time_s, &fl); r.depth_c = ax_centi(f.depth, &fl); r.temperature_c = ax_centi(f.temperature, &fl);
-    r.conductivity_c = ax_centi(f.conductivity, &fl); r.salinity_c = ax_centi(f.salinity, &fl);
-    r.r400_c = ax_centi(f.r400, &fl); r.r7500_c = ax_centi(f.r7500, &fl);
-    r.flags = fl;
+    r.time_c = ax_centi(f.time_s, &fl, false); r.depth_c = ax_centi(f.depth, &fl, false);
+    r.temperature_c = (int16_t)ax_centi(f.temperature, &fl, true); r.conductivity_c = (int16_t)ax_centi(f.conductivity, &fl, true);
+    r.salinity_c = (int16_t)ax_centi(f.salinity, &fl, true);
+    r.r400_c = (int16_t)ax_centi(f.r400, &fl, true); r.r7500_c = (int16_t)ax_centi(f.r7500, &fl, true);
+    r.flags = (uint16_t)fl;
     w.row[fg] = r;
 }
 AX_HDN inline void ax_chunkout_item(const AxWave& w, int64_t cg) {

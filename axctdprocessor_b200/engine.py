@@ -167,7 +167,7 @@ class DropResult:
         for k in ("time_s", "depth", "temperature", "conductivity", "salinity", "r400", "r7500"):
             q = self.rows[{"time_s": "time_c"}.get(k, k + "_c")]
             v = q / 100.0
-            v[q == _lib.ROW_NAN] = np.nan
+            v[q == (_lib.ROW_NAN if q.dtype == np.int32 else _lib.ROW_NAN16)] = np.nan
             out[k] = v
         return out
 

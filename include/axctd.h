@@ -150,11 +150,13 @@ typedef struct axctd_frame {
 #define AXCTD_ROW_KEEP 1            /* row survives QC and the spike filter (:569-609) */
 #define AXCTD_ROW_HEX  2            /* its hex string reaches self.hexframes (:612) */
 #define AXCTD_ROW_WIDE 4            /* a value does not fit the int32 hundredths: fetch the drop with axctd_batch_frames */
-#define AXCTD_ROW_NAN  (-2147483647 - 1)
-typedef struct axctd_row {
+#define AXCTD_ROW_NAN  (-2147483647 - 1)   /* 32-bit fields */
+#define AXCTD_ROW_NAN16 (-32768)          /* 16-bit fields */
+typedef struct axctd_row {      /* 24 bytes */
     uint32_t word;              /* the 32 frame bits, MSB first */
-    int32_t  flags;             /* AXCTD_ROW_* */
-    int32_t  time_c, depth_c, temperature_c, conductivity_c, salinity_c, r400_c, r7500_c;
+    int32_t  time_c, depth_c;   /* hundredths of a second / metre */
+    int16_t  temperature_c, conductivity_c, salinity_c, r400_c, r7500_c;
+    uint16_t flags;             /* AXCTD_ROW_* */
 } axctd_row;
 
 /* One run() iteration (AXCTDprocessor.py:283-338). */

@@ -237,3 +237,27 @@ def test_pipelined_decoder_returns_the_same_results(eng):
     for r, g in zip(ref, got):
         assert r.status == 0 and g.status == 0
         assert np.array_equal(r.rows, g.rows)
+
+
+def test_values_outside_the_compact_row_range_fall_back_to_full_records(eng):
+    """A header that announces an absurd depth slope: depth * 100 no longer fits the compact row's int32, the
+    row is flagged AXCTD_ROW_WIDE and table() takes the values from the full frame records instead."""
+    import synth
+    from axctdprocessor_b200 import _lib, engine
+    from oracle import axctd_oracle as ao
+    spec = synth.DropSpec(fs=44100, duration_s=47.0, seed=950, snr_db=30.0, zcoeff=(0.72, 5.0e8, 0.0, 0.0))
+    pcm = synth.generate_drop(spec)
+    cfg = eng.config(spec.fs)
+    b = eng.batch([len(pcm)], [cfg])
+    b.upload(0, pcm)
+    b.run()
+    full, lean = b.result(0, full=True), b.result(0, full=False)
+    b.close()
+    assert (full.rows["flags"] & _lib.ROW_WIDE).any()
+    tab = full.table()
+    op = ao.process_pcm(pcm, spec.fs)
+    kept = tab[tab["keep"] == 1]
+    np.testing.assert_allclose(kept["depth"], np.asarray(op.depth), rtol=1e-6)
+    assert kept["depth"].max() > 2.2e7
+    with pytest.raises(RuntimeError):
+        lean.table()
