@@ -941,12 +941,17 @@ __global__ void __launch_bounds__(32) k_chain_warp(AxWave w) {
         if (e >= dr.n) e = dr.n - 1;
         if (lane == 0) { ch[k].s = s; ch[k].e = e; ch[k].err = 0; ch[k].n_edges = 0; ch[k].spec_last = -1; }
         if (entry < 0) entry = ax_lower_bound(zi, M, s + c.pad);            // (all lanes: same result)
-        // ---- q = last ordinal with zi <= e-2: look at 32 ordinals around the guess
+        // ---- one round of loads: the 32 crossings around the predicted end of the chunk, and (lanes 0..2) the
+        // canonical masks of the entry tile and of the two tiles that should hold the stopping crossing
+        const int64_t g0 = entry + span - 15;
+        const int64_t mine = g0 + lane;
+        const int32_t zmine = (mine >= 0 && mine < M) ? zi[mine] : 0;
+        const int64_t tg = (entry + span - 4) / AX_TILE;                        // predicted tile of X
+        const int64_t tl = lane == 0 ? entry / AX_TILE : tg + (lane - 1);
+        const uint64_t mv = (lane < 3 && tl >= 0) ? cmask[tl] : 0ull;
         int64_t q;
         {
-            const int64_t g0 = entry + span - 15;
-            const int64_t mine = g0 + lane;
-            const bool le = mine < 0 ? true : (mine >= M ? false : (int64_t)zi[mine] <= e - 2);
+            const bool le = mine < 0 ? true : (mine >= M ? false : (int64_t)zmine <= e - 2);
             const unsigned ball = __ballot_sync(0xffffffffu, le);
             if (ball != 0u && ball != 0xffffffffu) q = g0 + (31 - __clz((int)ball));        // zi is ascending: le is a prefix
             else q = ax_upper_bound_from(zi, M, e - 2, entry + span) - 1;
@@ -956,12 +961,18 @@ __global__ void __launch_bounds__(32) k_chain_warp(AxWave w) {
         // ---- where the walk stops (ax_walk_end without the step count)
         const int64_t X = q - 4;
         int64_t pos = entry;
+        bool first = true;
         while (pos < X) {
             const int64_t t = pos / AX_TILE, tx = X / AX_TILE;
-            // lanes 0,1,2: masks of the entry tile and of the two tiles that can hold the stop
-            const int64_t tl = lane == 0 ? t : tx + (lane - 1);
-            const uint64_t mv = (lane < 3) ? cmask[tl] : 0ull;
-            const uint64_t m_t = __shfl_sync(0xffffffffu, mv, 0), m_x = __shfl_sync(0xffffffffu, mv, 1), m_x1 = __shfl_sync(0xffffffffu, mv, 2);
+            uint64_t m_t, m_x, m_x1;
+            if (first && tx == tg) {                                           // the prefetched masks are the right ones
+                m_t = __shfl_sync(0xffffffffu, mv, 0); m_x = __shfl_sync(0xffffffffu, mv, 1); m_x1 = __shfl_sync(0xffffffffu, mv, 2);
+            } else {
+                const int64_t tl2 = lane == 0 ? t : tx + (lane - 1);
+                const uint64_t mv2 = (lane < 3) ? cmask[tl2] : 0ull;
+                m_t = __shfl_sync(0xffffffffu, mv2, 0); m_x = __shfl_sync(0xffffffffu, mv2, 1); m_x1 = __shfl_sync(0xffffffffu, mv2, 2);
+            }
+            first = false;
             if ((m_t >> (pos - t * AX_TILE)) & 1ull) {                       // on the canonical walk: jump
                 uint64_t m = m_x & ~((1ull << (X - tx * AX_TILE)) - 1ull);
                 int64_t tt = tx;
@@ -972,10 +983,16 @@ __global__ void __launch_bounds__(32) k_chain_warp(AxWave w) {
             }
             pos += nx[pos];
         }
-        // ---- the crossing indices that fix the next start
-        const int64_t pl = pos - (lane & 1);
-        const int32_t zv = (lane < 2 && pl >= 0) ? zi[pl] : 0;
-        const int64_t zpos = __shfl_sync(0xffffffffu, zv, 0), zprev = __shfl_sync(0xffffffffu, zv, 1);
+        // ---- the crossing indices that fix the next start: from the window when they are in it
+        int64_t zpos, zprev;
+        if (pos - 1 >= g0 && pos < g0 + 32 && pos - 1 >= 0 && pos < M) {
+            zpos = __shfl_sync(0xffffffffu, zmine, (int)(pos - g0));
+            zprev = __shfl_sync(0xffffffffu, zmine, (int)(pos - 1 - g0));
+        } else {
+            const int64_t pl = pos - (lane & 1);
+            const int32_t zv = (lane < 2 && pl >= 0) ? zi[pl] : 0;
+            zpos = __shfl_sync(0xffffffffu, zv, 0); zprev = __shfl_sync(0xffffffffu, zv, 1);
+        }
         if (lane == 0) ch[k].spec_last = zpos;
         const int64_t next_ind = zpos - s - 1;                               // demodulate.py:104
         if (next_ind <= c.pad) { n_chunks_out = k + 1; break; }
