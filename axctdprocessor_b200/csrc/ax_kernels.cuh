@@ -213,24 +213,22 @@ __global__ void __launch_bounds__(128) k_tone_mag(AxWave w, int i_lo, int i_hi) 
 //   phase 1  the owner lane runs the cascade over its 64 samples (13 DFMA-pipe operations per sample for
 //            three sections), collects the sign bits in registers and stores the float roundings of y
 //            into its 128-sample ring in shared memory (STS.128, conflict free);
-//   phase 2  the crossings of the previous row are compacted across the warp and dealt to the lanes one
-//            each, so the 4*NPCM-FMA fp32 windows (ax_window32, phasors broadcast from shared memory) run
-//            without divergence whatever the crossing density of the individual rows.
+//   phase 2  every lane takes the crossings of its previous row one after the other and sums their 4*NPCM-FMA
+//            fp32 windows (ax_window32, phasors broadcast from shared memory) from its own ring; the warp
+//            iterates as often as its busiest lane has crossings (dealing the crossings evenly across the
+//            lanes was measured slower: the compaction cost more than the idle lanes).
 // y never leaves the SM; the only global traffic is the int16 stream in and (index, |S1|, |S2|) per
 // crossing out.
 #define AX_FD_WARPS 4
 #define AX_FD_THREADS (AX_FD_WARPS * 32)
 #define AX_FD_ROW 72                                   // int16 per staged row: 64 samples + 8 pad (144-byte stride)
 #define AX_FD_STAGE (32 * AX_FD_ROW)                   // int16 per warp per stage
-#define AX_FD_YSTRIDE 132                              // floats per lane ring: 128 + 4 pad (33 quads: conflict-free STS.128)
-#define AX_FD_LIST 256                                 // crossings dealt per pass
+#define AX_FD_RINGQ 32                                 // quads (4 samples) per lane ring: two rows
 
 struct AxFdSmem {
     AxF4 tab[AX_WIN_TAPS];                             // phasors of the bit windows (per warp copy: no CTA barrier needed)
     int16_t stage[2][AX_FD_STAGE];
-    float yring[32 * AX_FD_YSTRIDE];
-    uint32_t list[AX_FD_LIST];
-    int32_t row_begin[32], row_stop[32], row_aux[32];
+    float4 yring[AX_FD_RINGQ * 32];                    // [quad][lane]: every lane reads and writes only its own 16-byte column (no bank conflicts)
 };
 
 
@@ -284,7 +282,6 @@ __global__ void __launch_bounds__(AX_FD_THREADS, 2) k_demod_fused(const __grid_c
     for (int o = 16; o > 0; o >>= 1) Tmax = max(Tmax, __shfl_xor_sync(0xffffffffu, Tmax, o));
     const int16_t* xdrop = w.pcm + dr.pcm_off;
     const unsigned long long xrow = (unsigned long long)(xdrop + g.n_begin);      // 16-byte aligned
-    sm.row_begin[lane] = (int)g.n_begin; sm.row_stop[lane] = (int)g.n_stop; sm.row_aux[lane] = (int)chunk_s;
     for (int k = lane; k < AX_WIN_TAPS; k += 32) sm.tab[k] = tab.t[k];
     // ---- cascade constants (Butterworth form, see AxFilt::filter)
     double z0[NSEC], z1[NSEC], a1[NSEC], a2[NSEC], sg[NSEC];
@@ -317,7 +314,7 @@ __global__ void __launch_bounds__(AX_FD_THREADS, 2) k_demod_fused(const __grid_c
     };
     unsigned long long Sprev = 0ull;        // sign bits of row t-1 (bit i = sample i negative)
     int count = 0, unc = 0;
-    float* myring = sm.yring + lane * AX_FD_YSTRIDE;
+    float4* myring = sm.yring + lane;                // quad q of this lane's ring: myring[32 * q]
     __syncwarp();
     if (Tmax > 0) issue(0, 0);
     for (int t = 0; t <= Tmax; ++t) {
@@ -328,7 +325,7 @@ __global__ void __launch_bounds__(AX_FD_THREADS, 2) k_demod_fused(const __grid_c
             // ---------------- phase 1: the cascade over this lane's 64 samples
             if (t < T) {
                 const int4* rp = reinterpret_cast<const int4*>(&sm.stage[t & 1][lane * AX_FD_ROW]);
-                float4* yo = reinterpret_cast<float4*>(myring + (t & 1) * 64);
+                float4* yo = myring + (t & 1) * (16 * 32);
                 float minabs = 1e30f;
                 // The sections run skewed by one sample each (section s works on sample n - s), so every step
                 // holds NSEC independent recurrences; per sample the arithmetic is exactly AxFilt::filter's.
@@ -359,7 +356,7 @@ __global__ void __launch_bounds__(AX_FD_THREADS, 2) k_demod_fused(const __grid_c
                                 const float f = (float)y;
                                 yf[m & 3] = f;
                                 minabs = fminf(minabs, fabsf(f));
-                                if ((m & 3) == 3) yo[m >> 2] = make_float4(yf[0], yf[1], yf[2], yf[3]);
+                                if ((m & 3) == 3) yo[32 * (m >> 2)] = make_float4(yf[0], yf[1], yf[2], yf[3]);
                                 if ((m & 31) == 31) { Scur |= (unsigned long long)__brev(sb) << (m & 32); sb = 0u; }
                             }
                         }
@@ -370,7 +367,8 @@ __global__ void __launch_bounds__(AX_FD_THREADS, 2) k_demod_fused(const __grid_c
                     const int base = nb + 64 * t;
                     for (int i = 0; i < 64; ++i) {
                         const int n = base + i;
-                        if (n >= sstart && n < send && n < nstop && fabsf(myring[(t & 1) * 64 + i]) < guard_f) ++unc;
+                        if (n >= sstart && n < send && n < nstop &&
+                            fabsf(reinterpret_cast<const float*>(&yo[32 * (i >> 2)])[i & 3]) < guard_f) ++unc;
                     }
                 }
             }
@@ -389,51 +387,40 @@ __global__ void __launch_bounds__(AX_FD_THREADS, 2) k_demod_fused(const __grid_c
                 if (hi > lo) m = ((hi >= 64) ? ~0ull : ((1ull << hi) - 1ull)) & ~((1ull << lo) - 1ull);
                 X &= m;
             }
+            // every lane works through the crossings of its own row (its own ring: no exchange, no barrier);
+            // the warp iterates as often as its busiest lane has crossings
             while (__any_sync(0xffffffffu, X != 0ull)) {
-                const int take = min(__popcll(X), AX_FD_LIST / 32);
-                int off = take;
+                const bool has = X != 0ull;
+                const int p = has ? __ffsll((long long)X) - 1 : 0;
+                if (has) X &= X - 1ull;
+                const int j0 = ((t - 1) & 1) * 64 + p + 1;           // ring position of the first window sample
+                const int o = j0 & 3;
+                constexpr int NQ = (NPCM + 6) >> 2;
+                float yv[NQ * 4];
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, off, o); if (lane >= o) off += v; }
-                const int total = __shfl_sync(0xffffffffu, off, 31);
-                off -= take;
-                for (int q = 0; q < take; ++q) {
-                    const int p = __ffsll((long long)X) - 1;
-                    X &= X - 1ull;
-                    sm.list[off + q] = (unsigned)p | ((unsigned)lane << 6) | ((unsigned)(count + q) << 11);
+                for (int k = 0; k < NQ; ++k) {
+                    const float4 v = myring[32 * (((j0 >> 2) + k) & (AX_FD_RINGQ - 1))];
+                    yv[4 * k] = v.x; yv[4 * k + 1] = v.y; yv[4 * k + 2] = v.z; yv[4 * k + 3] = v.w;
                 }
-                count += take;
-                __syncwarp();
-                for (int it = lane; it < total; it += 32) {
-                    const unsigned en = sm.list[it];
-                    const int p = (int)(en & 63u), r = (int)((en >> 6) & 31u), op = (int)(en >> 11);
-                    const int j0 = ((t - 1) & 1) * 64 + p + 1;           // ring position of the first window sample
-                    const int o = j0 & 3;
-                    const float4* rq = reinterpret_cast<const float4*>(sm.yring + r * AX_FD_YSTRIDE);
-                    constexpr int NQ = (NPCM + 6) >> 2;
-                    float yv[NQ * 4];
-#pragma unroll
-                    for (int k = 0; k < NQ; ++k) {
-                        const float4 v = rq[((j0 >> 2) + k) & 31];
-                        yv[4 * k] = v.x; yv[4 * k + 1] = v.y; yv[4 * k + 2] = v.z; yv[4 * k + 3] = v.w;
-                    }
-                    float m1, m2;
-                    ax_window32(yv, o, NPCM, sm.tab, &m1, &m2);
-                    const int rb = sm.row_begin[r] + 64 * (t - 1);
-                    const bool complete = rb + p + NPCM < sm.row_stop[r];
-                    if (op < out_cap) {
-                        const int64_t oi = wslot0 + (int64_t)r * out_cap + op;
+                float m1, m2;
+                ax_window32(yv, o, NPCM, sm.tab, &m1, &m2);
+                if (has) {
+                    const int idx = base + p;
+                    const bool complete = idx + NPCM < nstop;
+                    if (count < out_cap) {
+                        const int64_t oi = wslot0 + (int64_t)lane * out_cap + count;
                         if (!HEAD) {
-                            w.rec_idx[oi] = rb + p;
+                            w.rec_idx[oi] = idx;
                             w.rec_a1[oi] = complete ? m1 : __int_as_float(0x7fc00000);
                             w.rec_a2[oi] = complete ? m2 : __int_as_float(0x7fc00000);
                         } else {
-                            w.head_idx[oi] = rb + p - sm.row_aux[r];         // chunk-relative
+                            w.head_idx[oi] = idx - (int)chunk_s;             // chunk-relative
                             w.head_a1[oi] = complete ? m1 : __int_as_float(0x7fc00000);
                             w.head_a2[oi] = complete ? m2 : __int_as_float(0x7fc00000);
                         }
                     }
+                    ++count;
                 }
-                __syncwarp();
             }
         }
         Sprev = Scur;
