@@ -124,3 +124,102 @@ class PipelinedDecoder:
         b = self._batches[slot][1]
         b.run()
         return [b.result(i, full=full) for i in range(b.n)]
+
+
+class ConcurrentDecoder:
+    """A resident batch decoded as ``shards`` sub-batches on as many engines (CUDA streams), each driven by
+    its own host thread (drops are independent, so a GPU's share can be cut further).
+
+    One engine's decode is a chain of about 45 launches with a few host round trips; most of its kernels are
+    small and latency bound (chunk chain, frame sync, calibration ...) and its results travel to the host at
+    the end.  With two sub-batches in flight those parts run underneath the other sub-batch's big kernels.
+    The engines take turns with the demodulation pass itself (``heavy_chain`` engine option), which fills the
+    GPU alone.  Drops are dealt round-robin (sub-batch k takes drops k, k + shards, ...)."""
+
+    def __init__(self, device: int, n_samples, fs_list, shards: int = 2, engine_options=None, settings=None,
+                 triggerrange=None, engine_factory=None, streams=None):
+        from concurrent.futures import ThreadPoolExecutor
+        from . import engine as _engine
+        n = len(n_samples)
+        shards = max(1, min(int(shards), n))
+        make = engine_factory or (lambda: _engine.Engine(device))      # (tests inject the host emulation here)
+        self.parts = [list(range(k, n, shards)) for k in range(shards)]
+        self.where = {}
+        for k, part in enumerate(self.parts):
+            for j, i in enumerate(part):
+                self.where[i] = (k, j)
+        self.engines = [make() for _ in range(shards)]
+        self.batches = []
+        for k, eng in enumerate(self.engines):
+            if streams is not None:
+                eng.set_stream(streams[k])
+            for name, v in (engine_options or {}).items():
+                eng.set_option(name, v)
+            cfgs = [eng.config(fs_list[i], settings=settings, triggerrange=triggerrange) for i in self.parts[k]]
+            self.batches.append(eng.batch([int(n_samples[i]) for i in self.parts[k]], cfgs))
+        self.n = n
+        self._pool = ThreadPoolExecutor(max_workers=shards)
+
+    def close(self):
+        if getattr(self, "_pool", None):
+            self._pool.shutdown(wait=True)
+            self._pool = None
+        for b in getattr(self, "batches", []):
+            b.close()
+        for e in getattr(self, "engines", []):
+            e.close()
+        self.batches, self.engines = [], []
+
+    def batch_of(self, i: int):
+        """(sub-batch, index inside it) holding drop i."""
+        k, j = self.where[i]
+        return self.batches[k], j
+
+    def upload(self, i: int, pcm):
+        b, j = self.batch_of(i)
+        b.upload(j, pcm)
+
+    def upload_ptr(self, i: int, host_ptr: int, n: int):
+        b, j = self.batch_of(i)
+        b.upload_ptr(j, host_ptr, n)
+
+    def synth_fill(self, i: int, spec):
+        b, j = self.batch_of(i)
+        b.synth_fill(j, spec)
+
+    def download(self, i: int):
+        b, j = self.batch_of(i)
+        return b.download(j)
+
+    def run(self, steps: int = 1, before=None, after=None):
+        """Decode every sub-batch ``steps`` times, all sub-batches concurrently.  ``before(k)`` / ``after(k)``
+        run in sub-batch k's thread around its steps (bench.py records its CUDA events there).  Returns the
+        per-step timings of every sub-batch."""
+        def work(k):
+            b = self.batches[k]
+            out = []
+            if before:
+                before(k)
+            for _ in range(steps):
+                b.run()
+                out.append(b.timing())
+            if after:
+                after(k)
+            return out
+        futs = [self._pool.submit(work, k) for k in range(len(self.batches))]
+        return [f.result() for f in futs]
+
+    def summary(self, i: int):
+        b, j = self.batch_of(i)
+        return b.summary(j)
+
+    def result(self, i: int, full: bool = True):
+        b, j = self.batch_of(i)
+        return b.result(j, full=full)
+
+    def results(self, full: bool = True) -> list:
+        return [self.result(i, full=full) for i in range(self.n)]
+
+    @property
+    def launch_count(self) -> int:
+        return sum(e.launch_count for e in self.engines)

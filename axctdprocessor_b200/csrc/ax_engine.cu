@@ -129,7 +129,8 @@ struct axctd_engine {
     double opt_bit_tol = 2e-5;            // fp32 bit windows: relative distance to a decision boundary that triggers
     double opt_hist_tol = 2e-5;           //   the double-precision re-evaluation (bit decision / calibration histogram)
     int opt_bitfix_all = 0;               // test hook: re-evaluate every window
-    int opt_rows32 = 0;                   // fused kernel with 32-sample rows (12 warps per SM)
+    int opt_ws = 0;                       // warp-specialised fused kernel (k_demod_ws)
+    int opt_heavy_chain = 1;              // engines of one process take turns with the demodulation pass (see ax_heavy_*)
     int opt_scan_only = 0;                // tone levels only (segmentation of long recordings): skip the demodulation pass
 };
 
@@ -274,7 +275,8 @@ extern "C" int axctd_engine_set_option(axctd_engine* e, const char* name, double
     else if (s == "filter_variant") e->opt_filter_variant = (int)v;
     else if (s == "zc_div") e->opt_zc_div = std::max(2, (int)v);
     else if (s == "inject_misspec") e->opt_inject_misspec = (int)v;
-    else if (s == "rows32") e->opt_rows32 = (int)v;
+    else if (s == "ws") e->opt_ws = (int)v;
+    else if (s == "heavy_chain") e->opt_heavy_chain = (int)v;
     else if (s == "scan_only") e->opt_scan_only = (int)v;
     else if (s == "bit_tol") e->opt_bit_tol = v;
     else if (s == "hist_tol") e->opt_hist_tol = v;
@@ -450,8 +452,25 @@ extern "C" int axctd_batch_create(axctd_engine* e, int n_drops, const int64_t* n
     int64_t L = e->opt_segment_len;
     if (L > 0) L = ((L + 63) / 64) * 64;
     if (L <= 0) {
-        L = 32768;
-        while (L > 2048 && total / L < 262144) L >>= 1;
+        // Every lane of the demodulation pass does the same amount of work, so the pass runs in waves of
+        // (SMs x 8 warps x 32) segments: take the number of waves that segments of about 8192 samples need (warm-up
+        // overlap near 1/8) and then the shortest segment length whose padded segment count still fits them.
+        int sms = 148;
+#ifndef AXCTD_EMU
+        { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, e->device) == cudaSuccess && v > 0) sms = v; }
+#endif
+        const int64_t lanes = (int64_t)sms * 8 * 32;
+        auto nseg_for = [&](int64_t len) {
+            int64_t s = 0;
+            for (int d = 0; d < n_drops; ++d) {
+                const int64_t nd = e->cfgs[config_id[d]].decimate == 2 ? (n_samples[d] + 1) / 2 : n_samples[d];
+                s += (((nd + len - 1) / len + 127) / 128) * 128;
+            }
+            return s;
+        };
+        const int64_t waves = std::max<int64_t>(1, (total + 8192 * lanes - 1) / (8192 * lanes));
+        L = 2048;
+        while (L < 16384 && nseg_for(L) > waves * lanes) L += 64;
         while (L < 2 * (int64_t)warm_max) L <<= 1;
     }
     AxWave& w = b->w;
@@ -646,7 +665,30 @@ static void ax_merge_headers(const AxCfg& c, AxState& st, axctd_drop_summary& sm
 
 #ifndef AXCTD_EMU
 #define AX_EVENT(b, i) cudaEventRecord((b)->ev[i], (b)->eng->stream)
+// Several engines (streams) of one process may decode sub-batches concurrently (batch.ConcurrentDecoder): their
+// small latency-bound kernels and result downloads overlap each other's big kernels.  The demodulation pass fills
+// the GPU by itself, so two of them side by side only stretch each other; every engine therefore waits for the
+// pass most recently enqueued by another engine on the same device before it starts its own.
+#include <mutex>
+static std::mutex g_heavy_mu;
+static cudaEvent_t g_heavy_ev[64];
+static bool g_heavy_have[64];
+static const axctd_engine* g_heavy_owner[64];
+static void ax_heavy_begin(axctd_engine* e) {
+    if (!e->opt_heavy_chain || e->device < 0 || e->device >= 64) return;
+    g_heavy_mu.lock();
+    if (g_heavy_have[e->device] && g_heavy_owner[e->device] != e) cudaStreamWaitEvent(e->stream, g_heavy_ev[e->device], 0);
+}
+static void ax_heavy_end(axctd_engine* e) {
+    if (!e->opt_heavy_chain || e->device < 0 || e->device >= 64) return;
+    if (!g_heavy_have[e->device]) { cudaEventCreateWithFlags(&g_heavy_ev[e->device], cudaEventDisableTiming); g_heavy_have[e->device] = true; }
+    cudaEventRecord(g_heavy_ev[e->device], e->stream);
+    g_heavy_owner[e->device] = e;
+    g_heavy_mu.unlock();
+}
 #else
+#define ax_heavy_begin(e) ((void)0)
+#define ax_heavy_end(e) ((void)0)
 #define AX_EVENT(b, i) ((void)0)
 #endif
 
@@ -730,9 +772,10 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
 #ifdef AXCTD_EMU
     AX_LAUNCH(e, k_toneblock, b->tb_total, w);
 #endif
+    ax_heavy_begin(e);
     AX_EVENT(b, 1);
     const bool scan_only = e->opt_scan_only != 0;     // tone levels only: no crossings are produced
-    if (scan_only) { if (ax_zero(e, w.seg_cnt, sizeof(int32_t) * (size_t)w.nseg_total)) return AXCTD_ERR_CUDA; }
+    if (scan_only) { if (ax_zero(e, w.seg_cnt, sizeof(int32_t) * (size_t)w.nseg_total)) { ax_heavy_end(e); return AXCTD_ERR_CUDA; } }
 #ifndef AXCTD_EMU
     bool fused = e->opt_filter_variant == 0;
     std::vector<int> used_cfg;
@@ -744,7 +787,7 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
     if (scan_only) {
     } else if (fused) {
         // one launch per rate class in use (CTAs of the other classes exit at once)
-        for (int ci : used_cfg) { ax_launch_demod_fused_any<false>(w, e->cfgs[ci], ci, 0, e->stream, e->opt_rows32); e->launches++; }
+        for (int ci : used_cfg) { ax_launch_demod_fused_any<false>(w, e->cfgs[ci], ci, 0, e->stream, e->opt_ws); e->launches++; }
         if (any_dec) { w.only_xf = 1; AX_LAUNCH(e, k_filter, (int64_t)w.nseg_total, w); w.only_xf = 0; }
     } else
 #else
@@ -752,6 +795,7 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
 #endif
     { AX_LAUNCH(e, k_filter, (int64_t)w.nseg_total, w); }
     AX_EVENT(b, 2);
+    ax_heavy_end(e);
     AX_LAUNCH(e, k_scan_block, (int64_t)w.nseg_total / 128, w);
     AX_LAUNCH1(e, k_scan, n, w);
 #ifndef AXCTD_EMU
@@ -797,7 +841,7 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
             // heads of the rate classes the fused kernel is instantiated for; the generic form takes the rest
             bool rest = any_dec;
             for (int ci : used_cfg) {
-                if (ax_demod_fused_ok(e->cfgs[ci])) { ax_launch_demod_fused_any<true>(w, e->cfgs[ci], ci, b->chunk_total, e->stream, e->opt_rows32); e->launches++; }
+                if (ax_demod_fused_ok(e->cfgs[ci])) { ax_launch_demod_fused_any<true>(w, e->cfgs[ci], ci, b->chunk_total, e->stream, e->opt_ws); e->launches++; }
                 else rest = true;
             }
             if (rest) AX_LAUNCH(e, k_headfilt, b->chunk_total, w, 1);

@@ -438,46 +438,72 @@ __global__ void __launch_bounds__(AX_FD_THREADS, 2) k_demod_fused(const __grid_c
     }
 }
 
-// ------------------------------------------------------------------ fused demodulation pass, 32-sample rows
-// Same computation as k_demod_fused with half the row length: a 96-sample ring per lane and 64-byte staging
-// rows bring the shared memory down to 18.2 KB per warp (three 4-warp CTAs per SM), and the loops are kept
-// rolled enough to fit 168 registers.  After row t the crossings whose NPCM-sample window has just become
-// complete are handled: stream positions 32(t-2)+OFF .. +31 with OFF = 64 - NPCM (rows t-2 and t-1).
-#define AX_F3_RS 32
-#define AX_F3_ROW 40                                   // int16 per staged row: 32 samples + 8 pad (80-byte stride)
-#define AX_F3_STAGE (32 * AX_F3_ROW)
-#define AX_F3_RQ 24                                    // quads per lane ring (3 rows)
-#define AX_F3_YSTRIDE 100                              // floats per lane ring: 96 + 4 pad (25 quads: conflict-free STS.128)
-#define AX_F3_LIST 64
-struct AxF3Warp {
-    int16_t stage[2][AX_F3_STAGE];
-    float yring[32 * AX_F3_YSTRIDE];
-    uint32_t list[AX_F3_LIST];
-    int32_t row_begin[32], row_stop[32], row_aux[32];
+// ------------------------------------------------------------------ fused demodulation pass, warp-specialised
+// k_demod_ws: the computation of k_demod_fused split over two kinds of warps so that the FP64 cascade and the
+// FP32 windows overlap instead of alternating.  A CTA holds AX_WS_PAIRS pairs of warps; pair p owns 32
+// segments (lane = segment in both warps):
+//   filter warp  stages its lanes' int16 rows (32 samples, 16-byte cp.async, double buffered), runs the skewed
+//                SOS cascade, stores the float roundings of y into the pair's ring in shared memory
+//                ([quad][lane], four rows deep) and the row's sign word, then arrives on full[row & 3];
+//   window warp  waits on full[u & 3], takes the crossings of row u-2 (their windows end inside row u), sums
+//                the windows from the ring exactly as k_demod_fused does, writes the crossing records and
+//                arrives on free[(u-2) & 3], which the filter warp waits on before it overwrites that slot.
+// The filter warp may run one row ahead of the window warp; with two CTAs per SM every scheduler holds two
+// filter warps (six independent DFMA chains) and two window warps.
+#define AX_WS_PAIRS 4
+#define AX_WS_THREADS (AX_WS_PAIRS * 64)
+#define AX_WS_RS 32                                    // samples per row
+#define AX_WS_ROW 40                                   // int16 per staged row: 32 samples + 8 pad (80-byte stride: conflict-free LDS.128)
+#define AX_WS_STAGE (32 * AX_WS_ROW)
+#define AX_WS_SLOTS 4                                  // ring rows per lane
+#define AX_WS_RINGQ (AX_WS_SLOTS * AX_WS_RS / 4)       // quads per lane ring
+struct AxWsPair {
+    int16_t stage[2][AX_WS_STAGE];
+    float4 yring[AX_WS_RINGQ * 32];                    // [quad][lane]
+    uint32_t signs[AX_WS_SLOTS][32];                   // bit i = sample i of the row is negative
+    unsigned long long full[AX_WS_SLOTS], freeb[AX_WS_SLOTS];
 };
-struct AxF3Smem {
+struct AxWsSmem {
     AxF4 tab[AX_WIN_TAPS];
-    AxF3Warp wp[AX_FD_WARPS];
+    AxWsPair pr[AX_WS_PAIRS];
 };
+__device__ __forceinline__ unsigned ax_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ax_mbar_init(unsigned long long* b, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(ax_smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void ax_mbar_arrive(unsigned long long* b) {
+    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"(ax_smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void ax_mbar_wait(unsigned long long* b, unsigned parity) {
+    const unsigned a = ax_smem_u32(b);
+    unsigned ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    } while (!ok);
+}
 
 template <int NSEC, int NPCM, bool HEAD>
-__global__ void __launch_bounds__(AX_FD_THREADS, 3) k_demod_fused32(const __grid_constant__ AxWave w, const __grid_constant__ AxWinTab tab, int cfg_id, int64_t n_items) {
-    static_assert(NPCM >= 34 && NPCM <= 45, "window length outside the range this kernel is laid out for");
+__global__ void __launch_bounds__(AX_WS_THREADS, 2) k_demod_ws(const __grid_constant__ AxWave w, const __grid_constant__ AxWinTab tab, int cfg_id, int64_t n_items) {
+    static_assert(NPCM + 2 <= 2 * AX_WS_RS, "window must end inside the row after next");
     extern __shared__ __align__(16) unsigned char ax_smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    AxF3Smem& smem = *reinterpret_cast<AxF3Smem*>(ax_smem_raw);
-    AxF3Warp& sm = smem.wp[warp];
-    const int64_t seg = (int64_t)blockIdx.x * AX_FD_THREADS + threadIdx.x;
+    const int pair = warp % AX_WS_PAIRS;
+    const bool is_filter = warp < AX_WS_PAIRS;
+    AxWsSmem& smem = *reinterpret_cast<AxWsSmem*>(ax_smem_raw);
+    AxWsPair& sm = smem.pr[pair];
+    const int64_t seg0 = (int64_t)blockIdx.x * (AX_WS_PAIRS * 32);
+    const int64_t seg = seg0 + pair * 32 + lane;
     int d;
     bool active;
     AxSegGeom g;
     g.seg_start = g.seg_end = g.n_begin = g.n_stop = 0;
-    int skip = 0;
+    int skip = 0;                                       // HEAD: samples of row 0 that lie before the chunk start
     int64_t chunk_s = 0;
     if (!HEAD) {
-        d = w.seg_drop[(int64_t)blockIdx.x * AX_FD_THREADS];
+        d = w.seg_drop[seg0];
         const AxDrop& dr0 = w.drop[d];
-        if (dr0.cfg != cfg_id || dr0.xf_off >= 0) return;
+        if (dr0.cfg != cfg_id || dr0.xf_off >= 0) return;   // another launch handles this rate class / the generic kernel the halved signals
         const int64_t j = seg - dr0.seg_base;
         active = j < dr0.nseg;
         if (active) g = ax_seg_geom(dr0, w.cfg[cfg_id], w.seg_len, j);
@@ -501,183 +527,184 @@ __global__ void __launch_bounds__(AX_FD_THREADS, 3) k_demod_fused32(const __grid
     }
     const AxCfg& c = w.cfg[cfg_id];
     AxState& st = w.st[d];
-    for (int k = threadIdx.x; k < AX_WIN_TAPS; k += AX_FD_THREADS) smem.tab[k] = tab.t[k];
-    const int T = active ? (int)((g.n_stop - g.n_begin + AX_F3_RS - 1) / AX_F3_RS) : 0;
+    for (int k = threadIdx.x; k < AX_WIN_TAPS; k += AX_WS_THREADS) smem.tab[k] = tab.t[k];
+    if (is_filter && lane < 2 * AX_WS_SLOTS) ax_mbar_init(lane < AX_WS_SLOTS ? &sm.full[lane] : &sm.freeb[lane - AX_WS_SLOTS], 32u);
+    const int T = active ? (int)((g.n_stop - g.n_begin + AX_WS_RS - 1) / AX_WS_RS) : 0;
     int Tmax = T;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) Tmax = max(Tmax, __shfl_xor_sync(0xffffffffu, Tmax, o));
-    const unsigned long long xrow = (unsigned long long)(w.pcm + w.drop[d].pcm_off + g.n_begin);   // 16-byte aligned
-    sm.row_begin[lane] = (int)g.n_begin; sm.row_stop[lane] = (int)g.n_stop; sm.row_aux[lane] = (int)chunk_s;
-    double z0[NSEC], z1[NSEC], a1[NSEC], a2[NSEC], sg[NSEC];
-#pragma unroll
-    for (int s = 0; s < NSEC; ++s) {
-        z0[s] = 0.0; z1[s] = 0.0;
-        a1[s] = -c.sos[s][4]; a2[s] = -c.sos[s][5];
-        sg[s] = (c.sos[s][1] < 0.0) ? -2.0 : 2.0;
-    }
-    const double k0 = c.sos[0][0] * st.inv_ampl, k1 = c.sos[0][0] * -(st.dc * st.inv_ampl);
-    const float guard_f = (float)w.guard;
     const int nb = (int)g.n_begin, nstop = (int)g.n_stop, sstart = (int)g.seg_start, send = (int)g.seg_end;
-    const int out_cap = HEAD ? w.head_zc_cap_max : w.seg_cap;
-    const int64_t wslot0 = (seg - lane) * (int64_t)out_cap;
-    // rows this lane helps to stage: r = i*8 + prow, i = 0..3 (four 16-byte pieces per row)
-    const int prow = lane >> 2, piece = lane & 3;
-    constexpr int OFF = 64 - NPCM;
-    unsigned S1 = 0u, S2 = 0u;              // sign bits of rows t-1 and t-2 (bit i = sample i negative)
-    int count = 0, unc = 0;
-    float* myring = sm.yring + lane * AX_F3_YSTRIDE;
+    float4* myring = sm.yring + lane;                // quad q of this lane's ring: myring[32 * q]
     __syncthreads();
-    auto issue = [&](int t, int s) {
+    if (is_filter) {
+        // ------------------------------------------------------------ filter warp
+        const unsigned long long xrow = (unsigned long long)(w.pcm + w.drop[d].pcm_off + g.n_begin);   // 16-byte aligned
+        double z0[NSEC], z1[NSEC], a1[NSEC], a2[NSEC], sg[NSEC];
+#pragma unroll
+        for (int s = 0; s < NSEC; ++s) {
+            z0[s] = 0.0; z1[s] = 0.0;
+            a1[s] = -c.sos[s][4]; a2[s] = -c.sos[s][5];
+            sg[s] = (c.sos[s][1] < 0.0) ? -2.0 : 2.0;
+        }
+        const double k0 = c.sos[0][0] * st.inv_ampl, k1 = c.sos[0][0] * -(st.dc * st.inv_ampl);
+        const float guard_f = (float)w.guard;
+        // rows this lane helps to stage: r = i*8 + prow, i = 0..3 (four 16-byte pieces per row)
+        const int prow = lane >> 2, piece = lane & 3;
+        unsigned long long src[4];
+        int Tr[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const unsigned long long src = __shfl_sync(0xffffffffu, xrow, i * 8 + prow) + (unsigned long long)piece * 16;
-            const int Tr = __shfl_sync(0xffffffffu, T, i * 8 + prow);
-            if (t < Tr) ax_cp_async16(&sm.stage[s][(i * 8 + prow) * AX_F3_ROW + piece * 8],
-                                      reinterpret_cast<const void*>(src + (unsigned long long)t * (2 * AX_F3_RS)));
+            src[i] = __shfl_sync(0xffffffffu, xrow, i * 8 + prow) + (unsigned long long)piece * 16;
+            Tr[i] = __shfl_sync(0xffffffffu, T, i * 8 + prow);
         }
-        ax_cp_async_commit();
-    };
-    if (Tmax > 0) issue(0, 0);
-    for (int t = 0; t < Tmax + 2; ++t) {
-        unsigned S0 = (S1 >> 31) ? 0xffffffffu : 0u;     // past the end: repeat the last sign (no crossing)
-        if (t < Tmax) {
+        auto issue = [&](int t, int s) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (t < Tr[i]) ax_cp_async16(&sm.stage[s][(i * 8 + prow) * AX_WS_ROW + piece * 8],
+                                             reinterpret_cast<const void*>(src[i] + (unsigned long long)t * (2 * AX_WS_RS)));
+            ax_cp_async_commit();
+        };
+        int unc = 0;
+        if (Tmax > 0) issue(0, 0);
+        for (int t = 0; t < Tmax; ++t) {
             if (t + 1 < Tmax) { issue(t + 1, (t + 1) & 1); ax_cp_async_wait<1>(); } else ax_cp_async_wait<0>();
             __syncwarp();
+            if (t >= AX_WS_SLOTS) ax_mbar_wait(&sm.freeb[t & (AX_WS_SLOTS - 1)], (unsigned)(((t - AX_WS_SLOTS) / AX_WS_SLOTS) & 1));
+            unsigned S = 0u;
             if (t < T) {
-                const int4* rp = reinterpret_cast<const int4*>(&sm.stage[t & 1][lane * AX_F3_ROW]);
-                float4* yo = reinterpret_cast<float4*>(myring + (t % 3) * AX_F3_RS);
+                const int4* rp = reinterpret_cast<const int4*>(&sm.stage[t & 1][lane * AX_WS_ROW]);
+                float4* yo = myring + (t & (AX_WS_SLOTS - 1)) * (8 * 32);
                 float minabs = 1e30f;
+                // The sections run skewed by one sample each (section s works on sample n - s), so every step
+                // holds NSEC independent recurrences; per sample the arithmetic is exactly AxFilt::filter's.
+                double pipe[NSEC];
+                int4 q = rp[0];
                 unsigned sb = 0u;
-#pragma unroll 1
-                for (int v = 0; v < 4; ++v) {
-                    const int4 q = rp[v];
-                    const int wd[4] = {q.x, q.y, q.z, q.w};
-                    float yf[8];
+                float yf[4];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const int xi = (e & 1) ? (wd[e >> 1] >> 16) : (int)(short)(wd[e >> 1] & 0xFFFF);
-                        double tt = fma((double)xi, k0, k1);
-                        if (HEAD && t == 0 && v * 8 + e < skip) tt = 0.0;
+                for (int n = 0; n < AX_WS_RS + NSEC - 1; ++n) {
 #pragma unroll
-                        for (int s = 0; s < NSEC; ++s) {
+                    for (int s = NSEC - 1; s >= 0; --s) {
+                        const int m = n - s;         // sample this section handles in this step
+                        if (m >= 0 && m < AX_WS_RS) {
+                            double tt;
+                            if (s == 0) {
+                                if ((m & 7) == 0 && m > 0) q = rp[m >> 3];
+                                const int wdv = ((m & 7) >> 1) == 0 ? q.x : ((m & 7) >> 1) == 1 ? q.y : ((m & 7) >> 1) == 2 ? q.z : q.w;
+                                const int xi = (m & 1) ? (wdv >> 16) : (int)(short)(wdv & 0xFFFF);
+                                tt = fma((double)xi, k0, k1);
+                                if (HEAD && t == 0 && m < skip) tt = 0.0;      // before the chunk start: keeps the state at zero
+                            } else tt = pipe[s];
                             const double y = tt + z0[s];
                             z0[s] = fma(a1[s], y, fma(sg[s], tt, z1[s]));
                             z1[s] = fma(a2[s], y, tt);
-                            tt = y;
+                            if (s < NSEC - 1) pipe[s + 1] = y;
+                            else {
+                                sb = __funnelshift_l((unsigned)__double2hiint(y), sb, 1);   // MSB-first: sample 0 ends at bit 31
+                                const float f = (float)y;
+                                yf[m & 3] = f;
+                                minabs = fminf(minabs, fabsf(f));
+                                if ((m & 3) == 3) yo[32 * (m >> 2)] = make_float4(yf[0], yf[1], yf[2], yf[3]);
+                            }
                         }
-                        sb = __funnelshift_l((unsigned)__double2hiint(tt), sb, 1);
-                        yf[e] = (float)tt;
-                        minabs = fminf(minabs, fabsf(yf[e]));
                     }
-                    yo[v * 2] = make_float4(yf[0], yf[1], yf[2], yf[3]);
-                    yo[v * 2 + 1] = make_float4(yf[4], yf[5], yf[6], yf[7]);
                 }
-                S0 = __brev(sb);
+                S = __brev(sb);
+                // guard band: a filter output this close to zero cannot be signed reliably (AXCTD_DROP_UNCERTAIN)
                 if (minabs < guard_f) {
-                    const int base = nb + AX_F3_RS * t;
-                    for (int i = 0; i < AX_F3_RS; ++i) {
+                    const int base = nb + AX_WS_RS * t;
+                    for (int i = 0; i < AX_WS_RS; ++i) {
                         const int n = base + i;
-                        if (n >= sstart && n < send && n < nstop && fabsf(myring[(t % 3) * AX_F3_RS + i]) < guard_f) ++unc;
+                        if (n >= sstart && n < send && n < nstop &&
+                            fabsf(reinterpret_cast<const float*>(&yo[32 * (i >> 2)])[i & 3]) < guard_f) ++unc;
                     }
                 }
+            }
+            sm.signs[t & (AX_WS_SLOTS - 1)][lane] = S;
+            ax_mbar_arrive(&sm.full[t & (AX_WS_SLOTS - 1)]);
+            __syncwarp();                                // the stage buffer t & 1 is rewritten by issue(t + 2)
+        }
+        if (active && unc) atomicAdd(&st.n_uncertain, unc);
+        return;
+    }
+    // ---------------------------------------------------------------- window warp
+    const int out_cap = HEAD ? w.head_zc_cap_max : w.seg_cap;
+    const int64_t oslot = seg * (int64_t)out_cap;
+    int count = 0;
+    for (int u = 2; u < Tmax + 2; ++u) {
+        const int r = u - 2;                            // row whose crossings are due
+        {
+            const int rw = min(u, Tmax - 1);            // newest row the windows of row r can reach
+            ax_mbar_wait(&sm.full[rw & (AX_WS_SLOTS - 1)], (unsigned)((rw / AX_WS_SLOTS) & 1));
+        }
+        unsigned X = 0u;
+        const int base = nb + AX_WS_RS * r;
+        if (r < T) {
+            const unsigned S = sm.signs[r & (AX_WS_SLOTS - 1)][lane];
+            const unsigned nxt = (r + 1 < T) ? (sm.signs[(r + 1) & (AX_WS_SLOTS - 1)][lane] & 1u) : (S >> 31);
+            X = S ^ ((S >> 1) | (nxt << 31));
+            int lo = sstart - base, hi = min(send, nstop - 1) - base;      // crossing i needs sample i+1
+            lo = max(lo, 0); hi = min(hi, 32);
+            unsigned m = 0u;
+            if (hi > lo) m = ((hi >= 32) ? 0xffffffffu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
+            X &= m;
+        }
+        // every lane works through the crossings of its own row (its own ring column: no exchange);
+        // the warp iterates as often as its busiest lane has crossings
+        while (__any_sync(0xffffffffu, X != 0u)) {
+            const bool has = X != 0u;
+            const int p = has ? __ffs((int)X) - 1 : 0;
+            if (has) X &= X - 1u;
+            const int j0 = (r & (AX_WS_SLOTS - 1)) * AX_WS_RS + p + 1;     // ring position of the first window sample
+            const int o = j0 & 3;
+            constexpr int NQ = (NPCM + 6) >> 2;
+            float yv[NQ * 4];
+#pragma unroll
+            for (int k = 0; k < NQ; ++k) {
+                const float4 v = myring[32 * (((j0 >> 2) + k) & (AX_WS_RINGQ - 1))];
+                yv[4 * k] = v.x; yv[4 * k + 1] = v.y; yv[4 * k + 2] = v.z; yv[4 * k + 3] = v.w;
+            }
+            float m1, m2;
+            ax_window32(yv, o, NPCM, smem.tab, &m1, &m2);
+            if (has) {
+                const int idx = base + p;
+                const bool complete = idx + NPCM < nstop;
+                if (count < out_cap) {
+                    const int64_t oi = oslot + count;
+                    if (!HEAD) {
+                        w.rec_idx[oi] = idx;
+                        w.rec_a1[oi] = complete ? m1 : __int_as_float(0x7fc00000);
+                        w.rec_a2[oi] = complete ? m2 : __int_as_float(0x7fc00000);
+                    } else {
+                        w.head_idx[oi] = idx - (int)chunk_s;             // chunk-relative
+                        w.head_a1[oi] = complete ? m1 : __int_as_float(0x7fc00000);
+                        w.head_a2[oi] = complete ? m2 : __int_as_float(0x7fc00000);
+                    }
+                }
+                ++count;
             }
         }
-        __syncwarp();
-        if (t >= 1) {
-            const int pbase = AX_F3_RS * (t - 2) + OFF;              // stream position of bit 0 (negative positions are masked)
-            unsigned X = __funnelshift_r(S2, S1, OFF) ^ __funnelshift_r(S2, S1, OFF + 1);
-            {
-                int lo = sstart - (nb + pbase), hi = min(send, nstop - 1) - (nb + pbase);      // crossing i needs sample i+1
-                lo = max(lo, 0); hi = min(hi, 32);
-                unsigned m = 0u;
-                if (hi > lo) m = ((hi >= 32) ? 0xffffffffu : ((1u << hi) - 1u)) & ~((1u << lo) - 1u);
-                X &= m;
-                if (!active) X = 0u;
-            }
-            while (__any_sync(0xffffffffu, X != 0u)) {
-                const int take = min(__popc(X), AX_F3_LIST / 32);
-                int off = take;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, off, o); if (lane >= o) off += v; }
-                const int total = __shfl_sync(0xffffffffu, off, 31);
-                off -= take;
-                for (int q = 0; q < take; ++q) {
-                    const int p = __ffs((int)X) - 1;
-                    X &= X - 1u;
-                    sm.list[off + q] = (unsigned)p | ((unsigned)lane << 5) | ((unsigned)(count + q) << 10);
-                }
-                count += take;
-                __syncwarp();
-                for (int it = lane; it < total; it += 32) {
-                    const unsigned en = sm.list[it];
-                    const int p = (int)(en & 31u), r = (int)((en >> 5) & 31u), op = (int)(en >> 10);
-                    const int P1 = pbase + p + 1;                    // stream position of the first window sample
-                    const int o = P1 & 3;
-                    int q0 = (P1 >> 2) % AX_F3_RQ;
-                    const float4* rq = reinterpret_cast<const float4*>(sm.yring + r * AX_F3_YSTRIDE);
-                    constexpr int NQ = (NPCM + 6) >> 2;
-                    // ax_window32, one quad at a time (same order of operations)
-                    float r1a = 0.f, i1a = 0.f, r2a = 0.f, i2a = 0.f, r1b = 0.f, i1b = 0.f, r2b = 0.f, i2b = 0.f;
-#pragma unroll 2
-                    for (int k = 0; k < NQ; ++k) {
-                        const float4 v = rq[q0];
-                        q0 = (q0 + 1 == AX_F3_RQ) ? 0 : q0 + 1;
-                        const float yq[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                        for (int h = 0; h < 4; h += 2) {
-                            const int kk = 4 * k + h;
-                            const float ya = (kk >= o && kk < o + NPCM) ? yq[h] : 0.f;
-                            const float yb = (kk + 1 >= o && kk + 1 < o + NPCM) ? yq[h + 1] : 0.f;
-                            const AxF4 ta = smem.tab[kk], tb = smem.tab[kk + 1];
-                            r1a = fmaf(ya, ta.x, r1a); i1a = fmaf(ya, ta.y, i1a);
-                            r2a = fmaf(ya, ta.z, r2a); i2a = fmaf(ya, ta.w, i2a);
-                            r1b = fmaf(yb, tb.x, r1b); i1b = fmaf(yb, tb.y, i1b);
-                            r2b = fmaf(yb, tb.z, r2b); i2b = fmaf(yb, tb.w, i2b);
-                        }
-                    }
-                    const float r1 = r1a + r1b, i1 = i1a + i1b, r2 = r2a + r2b, i2 = i2a + i2b;
-                    const float m1 = sqrtf(fmaf(r1, r1, i1 * i1)), m2 = sqrtf(fmaf(r2, r2, i2 * i2));
-                    const int idx = sm.row_begin[r] + pbase + p;
-                    const bool complete = idx + NPCM < sm.row_stop[r];
-                    if (op < out_cap) {
-                        const int64_t oi = wslot0 + (int64_t)r * out_cap + op;
-                        if (!HEAD) {
-                            w.rec_idx[oi] = idx;
-                            w.rec_a1[oi] = complete ? m1 : __int_as_float(0x7fc00000);
-                            w.rec_a2[oi] = complete ? m2 : __int_as_float(0x7fc00000);
-                        } else {
-                            w.head_idx[oi] = idx - sm.row_aux[r];
-                            w.head_a1[oi] = complete ? m1 : __int_as_float(0x7fc00000);
-                            w.head_a2[oi] = complete ? m2 : __int_as_float(0x7fc00000);
-                        }
-                    }
-                }
-                __syncwarp();
-            }
-        }
-        S2 = S1; S1 = S0;
-        __syncwarp();
+        ax_mbar_arrive(&sm.freeb[r & (AX_WS_SLOTS - 1)]);
     }
     if (!HEAD) {
         if (active) {
             if (count > w.seg_cap) { w.flags[AX_FLAG_CAP] = 1; count = w.seg_cap; }
             w.seg_cnt[seg] = count;
-            if (unc) atomicAdd(&st.n_uncertain, unc);
         } else w.seg_cnt[seg] = 0;
     } else if (active) {
         w.head_cnt[seg] = count > out_cap ? -1 : count;
-        if (unc) atomicAdd(&st.n_uncertain, unc);
     }
 }
 
 template <int NSEC, int NPCM, bool HEAD>
-static inline void ax_launch_demod_fused32(const AxWave& w, const AxCfg& c, int cfg_id, int64_t n_items, cudaStream_t stream) {
-    const size_t smem = sizeof(AxF3Smem);
+static inline void ax_launch_demod_ws(const AxWave& w, const AxCfg& c, int cfg_id, int64_t n_items, cudaStream_t stream) {
+    const size_t smem = sizeof(AxWsSmem);
     static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(k_demod_fused32<NSEC, NPCM, HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+    if (!attr_set) { cudaFuncSetAttribute(k_demod_ws<NSEC, NPCM, HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
     const int64_t items = HEAD ? n_items : (int64_t)w.nseg_total;
     if (items <= 0) return;
-    k_demod_fused32<NSEC, NPCM, HEAD><<<(unsigned)((items + AX_FD_THREADS - 1) / AX_FD_THREADS), AX_FD_THREADS, smem, stream>>>(w, c.win_tab, cfg_id, items);
+    const int per = AX_WS_PAIRS * 32;
+    k_demod_ws<NSEC, NPCM, HEAD><<<(unsigned)((items + per - 1) / per), AX_WS_THREADS, smem, stream>>>(w, c.win_tab, cfg_id, items);
 }
 
 template <int NSEC, int NPCM, bool HEAD>
@@ -695,10 +722,12 @@ static inline bool ax_demod_fused_ok(const AxCfg& c) {
     return ax_sos_is_butter(c) && (c.nsec == 3 || c.nsec == 6) && (c.npcm == 39 || c.npcm == 43) && c.inset == 1;
 }
 template <bool HEAD>
-static inline void ax_launch_demod_fused_any(const AxWave& w, const AxCfg& c, int cfg_id, int64_t n_items, cudaStream_t stream, int rows32) {
-    if (rows32 && c.nsec == 3) {
-        if (c.npcm == 39) ax_launch_demod_fused32<3, 39, HEAD>(w, c, cfg_id, n_items, stream);
-        else ax_launch_demod_fused32<3, 43, HEAD>(w, c, cfg_id, n_items, stream);
+static inline void ax_launch_demod_fused_any(const AxWave& w, const AxCfg& c, int cfg_id, int64_t n_items, cudaStream_t stream, int ws) {
+    if (ws) {
+        if (c.nsec == 3 && c.npcm == 39) ax_launch_demod_ws<3, 39, HEAD>(w, c, cfg_id, n_items, stream);
+        else if (c.nsec == 3 && c.npcm == 43) ax_launch_demod_ws<3, 43, HEAD>(w, c, cfg_id, n_items, stream);
+        else if (c.nsec == 6 && c.npcm == 39) ax_launch_demod_ws<6, 39, HEAD>(w, c, cfg_id, n_items, stream);
+        else ax_launch_demod_ws<6, 43, HEAD>(w, c, cfg_id, n_items, stream);
         return;
     }
     if (c.nsec == 3 && c.npcm == 39) ax_launch_demod_fused<3, 39, HEAD>(w, c, cfg_id, n_items, stream);

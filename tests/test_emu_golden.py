@@ -239,6 +239,27 @@ def test_pipelined_decoder_returns_the_same_results(eng):
         assert np.array_equal(r.rows, g.rows)
 
 
+def test_concurrent_decoder_returns_the_same_results(eng):
+    """batch.ConcurrentDecoder (sub-batches on their own engines and host threads) against a plain batch."""
+    import synth
+    from axctdprocessor_b200 import batch as axbatch
+    specs = [synth.DropSpec(fs=(44100, 48000)[i % 2], duration_s=46.0, seed=920 + i, snr_db=20.0) for i in range(5)]
+    pcms = [np.ascontiguousarray(synth.generate_drop(s)) for s in specs]
+    ref = axbatch.process_drops(eng, pcms, [s.fs for s in specs])
+    for shards in (2, 3):
+        cd = axbatch.ConcurrentDecoder(0, [len(p) for p in pcms], [s.fs for s in specs], shards=shards, engine_factory=emu_engine)
+        assert sorted(i for part in cd.parts for i in part) == list(range(5))
+        for i, p in enumerate(pcms):
+            cd.upload(i, p)
+        timings = cd.run(steps=2)
+        assert len(timings) == shards and all(len(t) == 2 for t in timings)
+        got = cd.results(full=False)
+        cd.close()
+        for r, g in zip(ref, got):
+            assert r.status == 0 and g.status == 0
+            assert np.array_equal(r.rows, g.rows)
+
+
 def test_values_outside_the_compact_row_range_fall_back_to_full_records(eng):
     """A header that announces an absurd depth slope: depth * 100 no longer fits the compact row's int32, the
     row is flagged AXCTD_ROW_WIDE and table() takes the values from the full frame records instead."""

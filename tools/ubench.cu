@@ -44,6 +44,121 @@ static void run(const char* name, int blocks, int threads) {
            fmas / ms / 1e9, fmas / (ms * 1e-3) / 148 / 1.965e9);
     cudaFree(d);
 }
+
+// The fused kernel's cascade pattern: three skewed Butterworth sections per lane (13 FP64-pipe operations per
+// sample), coefficients either in registers (loaded from memory) or as constant-bank operands (kernel parameters).
+struct Coef { double a1[3], a2[3], sg[3], k0, k1; };
+template <bool CONST>
+__global__ void k_casc(double* out, int iters, const __grid_constant__ Coef cc, const Coef* gc) {
+    double a1[3], a2[3], sg[3], k0, k1;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) { a1[s] = CONST ? cc.a1[s] : gc->a1[s]; a2[s] = CONST ? cc.a2[s] : gc->a2[s]; sg[s] = CONST ? cc.sg[s] : gc->sg[s]; }
+    k0 = CONST ? cc.k0 : gc->k0; k1 = CONST ? cc.k1 : gc->k1;
+    double z0[3] = {0, 0, 0}, z1[3] = {0, 0, 0}, pipe[3] = {0, 0, 0};
+    int v = threadIdx.x * 31 + 7;
+    double acc = 0.0;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int n = 0; n < 16; ++n) {
+#pragma unroll
+            for (int s = 2; s >= 0; --s) {
+                double tt;
+                if (s == 0) { v = v * 5 + 1; tt = fma((double)(short)(v >> 8), k0, k1); } else tt = pipe[s];
+                const double y = tt + z0[s];
+                z0[s] = fma(a1[s], y, fma(sg[s], tt, z1[s]));
+                z1[s] = fma(a2[s], y, tt);
+                if (s < 2) pipe[s + 1] = y; else acc += (double)(float)y;
+            }
+        }
+    }
+    if (acc == 12345.678) out[0] = acc;
+}
+template <bool CONST>
+static void run_casc(int threads, int blocks_per_sm) {
+    double* d; cudaMalloc(&d, 64);
+    Coef h;
+    const double A1[3] = {1.6926643005998814, 1.7591969461508574, 1.8877140066455618}, A2[3] = {-0.71770845316494558, -0.78522549575504252, -0.91564405607407828};
+    for (int s = 0; s < 3; ++s) { h.a1[s] = A1[s]; h.a2[s] = A2[s]; h.sg[s] = 2.0; }
+    h.k0 = 2.8447757653552447e-07 / 20000.0; h.k1 = 1e-9;
+    Coef* g; cudaMalloc(&g, sizeof(Coef)); cudaMemcpy(g, &h, sizeof(Coef), cudaMemcpyHostToDevice);
+    const int iters = 512;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    k_casc<CONST><<<148 * blocks_per_sm, threads>>>(d, iters, h, g);
+    cudaEventRecord(e0);
+    k_casc<CONST><<<148 * blocks_per_sm, threads>>>(d, iters, h, g);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    const double wsamp = (double)blocks_per_sm * (threads / 32) * iters * 16 / 4;       // warp-samples per SM sub-partition
+    printf("cascade %s warps/SMSP=%.1f : %.3f ms  %.1f SMSP-cycles per warp-sample (13 FP64 ops; pipe floor 29.1)\n", CONST ? "const-bank coef" : "register coef  ",
+           blocks_per_sm * (threads / 32) / 4.0, ms, ms * 1e-3 * 1.965e9 / wsamp);
+    cudaFree(d); cudaFree(g);
+}
+
+// Cascade warps next to FP32 warps on the same scheduler: does FFMA / LDS traffic slow the FP64 chains?
+__global__ void k_mix(long long* cyc, double* out, int iters, int nf_warps, int fiters, const __grid_constant__ Coef cc) {
+    __shared__ float4 sh[1024];
+    const int warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) sh[i] = make_float4(1.f + i, 0.5f, 0.25f, 2.f);
+    __syncthreads();
+    if (warp < nf_warps) {
+        double z0[3] = {0, 0, 0}, z1[3] = {0, 0, 0}, pipe[3] = {0, 0, 0};
+        int v = threadIdx.x * 31 + 7;
+        double acc = 0.0;
+        const long long t0 = clock64();
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int n = 0; n < 16; ++n) {
+#pragma unroll
+                for (int s = 2; s >= 0; --s) {
+                    double tt;
+                    if (s == 0) { v = v * 5 + 1; tt = fma((double)(short)(v >> 8), cc.k0, cc.k1); } else tt = pipe[s];
+                    const double y = tt + z0[s];
+                    z0[s] = fma(cc.a1[s], y, fma(cc.sg[s], tt, z1[s]));
+                    z1[s] = fma(cc.a2[s], y, tt);
+                    if (s < 2) pipe[s + 1] = y; else acc += (double)(float)y;
+                }
+            }
+        }
+        const long long t1 = clock64();
+        if ((threadIdx.x & 31) == 0) cyc[blockIdx.x * 32 + warp] = t1 - t0;
+        if (acc == 12345.678) out[0] = acc;
+    } else {
+        float a[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = (float)i;
+        for (int it = 0; it < fiters; ++it) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const float4 t = sh[(threadIdx.x + k * 32 + it) & 1023];
+                a[0] = fmaf(a[0], t.x, t.y); a[1] = fmaf(a[1], t.y, t.z); a[2] = fmaf(a[2], t.z, t.w); a[3] = fmaf(a[3], t.w, t.x);
+                a[4] = fmaf(a[4], t.x, t.z); a[5] = fmaf(a[5], t.y, t.w); a[6] = fmaf(a[6], t.z, t.x); a[7] = fmaf(a[7], t.w, t.y);
+            }
+        }
+        float sacc = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sacc += a[i];
+        if (sacc == 12345.678f) out[1] = sacc;
+    }
+}
+static void run_mix(int nf, int nw, int fiters) {
+    double* d; cudaMalloc(&d, 64);
+    long long* c; cudaMalloc(&c, 148 * 32 * 8); cudaMemset(c, 0, 148 * 32 * 8);
+    Coef h;
+    const double A1[3] = {1.6926643005998814, 1.7591969461508574, 1.8877140066455618}, A2[3] = {-0.71770845316494558, -0.78522549575504252, -0.91564405607407828};
+    for (int s = 0; s < 3; ++s) { h.a1[s] = A1[s]; h.a2[s] = A2[s]; h.sg[s] = 2.0; }
+    h.k0 = 2.8447757653552447e-07 / 20000.0; h.k1 = 1e-9;
+    const int iters = 512;
+    for (int rep = 0; rep < 2; ++rep) k_mix<<<148, (nf + nw) * 32>>>(c, d, iters, nf, fiters, h);
+    cudaDeviceSynchronize();
+    static long long hc[148 * 32];
+    cudaMemcpy(hc, c, sizeof(hc), cudaMemcpyDeviceToHost);
+    double mean = 0; int n = 0;
+    for (int b = 0; b < 148; ++b) for (int w2 = 0; w2 < nf; ++w2) { mean += (double)hc[b * 32 + w2]; ++n; }
+    mean /= n;
+    printf("mix: %d cascade + %d fp32/lds warps per SM (fiters %d): %.1f warp-cycles per sample step = %.1f SMSP-cycles per warp-sample\n", nf, nw, fiters,
+           mean / (iters * 16.0), mean / (iters * 16.0) / (nf / 4.0));
+    cudaFree(d); cudaFree(c);
+}
 int main() {
     cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
     printf("%s SMs=%d clock=%d kHz\n", p.name, p.multiProcessorCount, p.clockRate);
@@ -66,5 +181,7 @@ int main() {
         double n = 148.0 * 8 * 256 * 4096 * 8;
         printf("i2f+fadd+imad: %.3f ms, %.1f conv lanes/clk/SM\n", ms, n / (ms * 1e-3) / 148 / 1.965e9);
     }
+    for (int wps = 1; wps <= 4; ++wps) { run_casc<false>(128 * wps, 1); run_casc<true>(128 * wps, 1); }
+    run_mix(8, 0, 0); run_mix(8, 8, 400); run_mix(8, 8, 4000); run_mix(4, 4, 4000); run_mix(8, 4, 4000); run_mix(12, 4, 4000);
     return 0;
 }
