@@ -225,11 +225,18 @@ __global__ void __launch_bounds__(128) k_tone_mag(AxWave w, int i_lo, int i_hi) 
 #define AX_FD_STAGE (32 * AX_FD_ROW)                   // int16 per warp per stage
 #define AX_FD_RINGQ 32                                 // quads (4 samples) per lane ring: two rows
 
-struct AxFdSmem {
+struct AxFdWarp {
     AxF4 tab[AX_WIN_TAPS];                             // phasors of the bit windows (per warp copy: no CTA barrier needed)
     int16_t stage[2][AX_FD_STAGE];
-    float4 yring[AX_FD_RINGQ * 32];                    // [quad][lane]: every lane reads and writes only its own 16-byte column (no bank conflicts)
 };
+// Shared memory of a CTA: the four y rings first ([warp][quad][lane] float4, 16 KB per warp, so that the byte offset
+// of a ring quad is ((quad * 512 + lane * 16) & 0x3ff0) | (warp << 14): one add and one LOP3 per load), then the
+// per-warp phasor tables and staging rows.
+struct AxFdSmem {
+    float4 yring[AX_FD_WARPS][AX_FD_RINGQ * 32];       // every lane reads and writes only its own 16-byte column (no bank conflicts)
+    AxFdWarp wp[AX_FD_WARPS];
+};
+static_assert(AX_FD_RINGQ * 32 * sizeof(float4) == 16384, "ring offsets assume 16 KB per warp");
 
 
 // HEAD = false: lane = segment of the continuous pass.  HEAD = true: lane = run() iteration, filtered from
@@ -240,7 +247,8 @@ template <int NSEC, int NPCM, bool HEAD>
 __global__ void __launch_bounds__(AX_FD_THREADS, 2) k_demod_fused(const __grid_constant__ AxWave w, const __grid_constant__ AxWinTab tab, int cfg_id, int64_t n_items) {
     extern __shared__ __align__(16) unsigned char ax_smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    AxFdSmem& sm = reinterpret_cast<AxFdSmem*>(ax_smem_raw)[warp];
+    AxFdSmem& smem = *reinterpret_cast<AxFdSmem*>(ax_smem_raw);
+    AxFdWarp& sm = smem.wp[warp];
     const int64_t seg = (int64_t)blockIdx.x * AX_FD_THREADS + threadIdx.x;
     int d;
     bool active;
@@ -314,7 +322,8 @@ __global__ void __launch_bounds__(AX_FD_THREADS, 2) k_demod_fused(const __grid_c
     };
     unsigned long long Sprev = 0ull;        // sign bits of row t-1 (bit i = sample i negative)
     int count = 0, unc = 0;
-    float4* myring = sm.yring + lane;                // quad q of this lane's ring: myring[32 * q]
+    float4* myring = smem.yring[warp] + lane;        // quad q of this lane's ring: myring[32 * q]
+    const unsigned ring_hi = (unsigned)warp << 14, ring_lo = (unsigned)lane << 4;
     __syncwarp();
     if (Tmax > 0) issue(0, 0);
     for (int t = 0; t <= Tmax; ++t) {
@@ -389,17 +398,22 @@ __global__ void __launch_bounds__(AX_FD_THREADS, 2) k_demod_fused(const __grid_c
             }
             // every lane works through the crossings of its own row (its own ring: no exchange, no barrier);
             // the warp iterates as often as its busiest lane has crossings
-            while (__any_sync(0xffffffffu, X != 0ull)) {
-                const bool has = X != 0ull;
-                const int p = has ? __ffsll((long long)X) - 1 : 0;
-                if (has) X &= X - 1ull;
+            unsigned Xl = (unsigned)X, Xh = (unsigned)(X >> 32);
+            while (__any_sync(0xffffffffu, (Xl | Xh) != 0u)) {
+                const bool has = (Xl | Xh) != 0u;
+                const bool in_lo = Xl != 0u;
+                const unsigned xs = in_lo ? Xl : Xh;                 // (branch-free 64-bit find-first-set)
+                const int p = has ? __ffs((int)xs) - 1 + (in_lo ? 0 : 32) : 0;
+                const unsigned xc = xs & (xs - 1u);
+                if (in_lo) Xl = xc; else Xh = xc;
                 const int j0 = ((t - 1) & 1) * 64 + p + 1;           // ring position of the first window sample
                 const int o = j0 & 3;
                 constexpr int NQ = (NPCM + 6) >> 2;
                 float yv[NQ * 4];
+                const unsigned q0b = ((unsigned)(j0 >> 2) << 9) + ring_lo;
 #pragma unroll
                 for (int k = 0; k < NQ; ++k) {
-                    const float4 v = myring[32 * (((j0 >> 2) + k) & (AX_FD_RINGQ - 1))];
+                    const float4 v = *reinterpret_cast<const float4*>(ax_smem_raw + ((((q0b + 512u * k) & 0x3ff0u) | ring_hi)));
                     yv[4 * k] = v.x; yv[4 * k + 1] = v.y; yv[4 * k + 2] = v.z; yv[4 * k + 3] = v.w;
                 }
                 float m1, m2;
@@ -709,7 +723,7 @@ static inline void ax_launch_demod_ws(const AxWave& w, const AxCfg& c, int cfg_i
 
 template <int NSEC, int NPCM, bool HEAD>
 static inline void ax_launch_demod_fused(const AxWave& w, const AxCfg& c, int cfg_id, int64_t n_items, cudaStream_t stream) {
-    const size_t smem = AX_FD_WARPS * sizeof(AxFdSmem);
+    const size_t smem = sizeof(AxFdSmem);
     static bool attr_set = false;
     if (!attr_set) { cudaFuncSetAttribute(k_demod_fused<NSEC, NPCM, HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
     const int64_t items = HEAD ? n_items : (int64_t)w.nseg_total;
