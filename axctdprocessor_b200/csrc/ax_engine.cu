@@ -130,6 +130,7 @@ struct axctd_engine {
     double opt_hist_tol = 2e-5;           //   the double-precision re-evaluation (bit decision / calibration histogram)
     int opt_bitfix_all = 0;               // test hook: re-evaluate every window
     int opt_ws = 0;                       // warp-specialised fused kernel (k_demod_ws)
+    int opt_fir_first = 1;                // numerators-first cascade in the continuous low-pass pass (k_demod_fused FAST)
     int opt_heavy_chain = 1;              // engines of one process take turns with the demodulation pass (see ax_heavy_*)
     int opt_scan_only = 0;                // tone levels only (segmentation of long recordings): skip the demodulation pass
 };
@@ -276,6 +277,7 @@ extern "C" int axctd_engine_set_option(axctd_engine* e, const char* name, double
     else if (s == "zc_div") e->opt_zc_div = std::max(2, (int)v);
     else if (s == "inject_misspec") e->opt_inject_misspec = (int)v;
     else if (s == "ws") e->opt_ws = (int)v;
+    else if (s == "fir_first") e->opt_fir_first = (int)v;
     else if (s == "heavy_chain") e->opt_heavy_chain = (int)v;
     else if (s == "scan_only") e->opt_scan_only = (int)v;
     else if (s == "bit_tol") e->opt_bit_tol = v;
@@ -787,7 +789,7 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
     if (scan_only) {
     } else if (fused) {
         // one launch per rate class in use (CTAs of the other classes exit at once)
-        for (int ci : used_cfg) { ax_launch_demod_fused_any<false>(w, e->cfgs[ci], ci, 0, e->stream, e->opt_ws); e->launches++; }
+        for (int ci : used_cfg) { ax_launch_demod_fused_any<false>(w, e->cfgs[ci], ci, 0, e->stream, e->opt_ws, e->opt_fir_first); e->launches++; }
         if (any_dec) { w.only_xf = 1; AX_LAUNCH(e, k_filter, (int64_t)w.nseg_total, w); w.only_xf = 0; }
     } else
 #else
@@ -841,7 +843,7 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
             // heads of the rate classes the fused kernel is instantiated for; the generic form takes the rest
             bool rest = any_dec;
             for (int ci : used_cfg) {
-                if (ax_demod_fused_ok(e->cfgs[ci])) { ax_launch_demod_fused_any<true>(w, e->cfgs[ci], ci, b->chunk_total, e->stream, e->opt_ws); e->launches++; }
+                if (ax_demod_fused_ok(e->cfgs[ci])) { ax_launch_demod_fused_any<true>(w, e->cfgs[ci], ci, b->chunk_total, e->stream, e->opt_ws, 0); e->launches++; }
                 else rest = true;
             }
             if (rest) AX_LAUNCH(e, k_headfilt, b->chunk_total, w, 1);

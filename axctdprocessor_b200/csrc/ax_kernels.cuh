@@ -243,7 +243,16 @@ static_assert(AX_FD_RINGQ * 32 * sizeof(float4) == 16384, "ring offsets assume 1
 // zero state at the chunk start over its first head + npcm + 2 samples (ax_headfilt_item); the lane's
 // stream starts at the chunk start rounded down to 8 samples (16-byte staging) and the samples before the
 // chunk start enter the cascade as zeros, which leaves its state at zero.
-template <int NSEC, int NPCM, bool HEAD>
+// FAST (low-pass, three sections with numerator (1 + z^-1)^2 each, continuous pass only): from the second row of a
+// lane on, the cascade runs "numerators first": u[n] = sum_j C(6,j) x[n-j] is formed exactly in integers (four
+// IDP.2A per sample on the packed int16 words, which also replaces the unpacking), tt = k0 u + 64 k1, and the three
+// sections are all-pole, y_s[n] = in + a1 y_s[n-1] + a2 y_s[n-2] (two DFMA each): 7 FP64-pipe operations per sample
+// instead of 13 -- every one of them costs 2.2 issue cycles on B200 (tools/ubench.cu) -- and one dependent DFMA per
+// step and section instead of two.  The result differs from the reference's operation order by < 1e-14 of full
+// scale (measured 7.5e-15 over 2.6 M samples), two orders below the guard band that flags unreliable signs.  Row 0
+// of every lane runs in the reference's order (the offset term of the first six samples of a stream differs) and
+// its last six outputs give the all-pole states: w3 = y, w2 = A3 w3, w1 = A2 w2.
+template <int NSEC, int NPCM, bool HEAD, bool FAST>
 __global__ void __launch_bounds__(AX_FD_THREADS, 2) k_demod_fused(const __grid_constant__ AxWave w, const __grid_constant__ AxWinTab tab, int cfg_id, int64_t n_items) {
     extern __shared__ __align__(16) unsigned char ax_smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -300,6 +309,8 @@ __global__ void __launch_bounds__(AX_FD_THREADS, 2) k_demod_fused(const __grid_c
         sg[s] = (c.sos[s][1] < 0.0) ? -2.0 : 2.0;
     }
     const double k0 = c.sos[0][0] * st.inv_ampl, k1 = c.sos[0][0] * -(st.dc * st.inv_ampl);
+    const double k1_64 = 64.0 * k1;
+    int3 hist = make_int3(0, 0, 0);         // FAST: the last three packed words of the previous row
     const float guard_f = (float)w.guard;
     const int nb = (int)g.n_begin, nstop = (int)g.n_stop, sstart = (int)g.seg_start, send = (int)g.seg_end;
     const int out_cap = HEAD ? w.head_zc_cap_max : w.seg_cap;
@@ -336,41 +347,90 @@ __global__ void __launch_bounds__(AX_FD_THREADS, 2) k_demod_fused(const __grid_c
                 const int4* rp = reinterpret_cast<const int4*>(&sm.stage[t & 1][lane * AX_FD_ROW]);
                 float4* yo = myring + (t & 1) * (16 * 32);
                 float minabs = 1e30f;
-                // The sections run skewed by one sample each (section s works on sample n - s), so every step
-                // holds NSEC independent recurrences; per sample the arithmetic is exactly AxFilt::filter's.
-                double pipe[NSEC];                   // pipe[s]: output of section s-1 for the sample section s takes next
-                int4 q = rp[0];
                 unsigned sb = 0u;
                 float yf[4];
+                auto emit = [&](const int m, const double y) {
+                    sb = __funnelshift_l((unsigned)__double2hiint(y), sb, 1);   // MSB-first: sample 0 of this half ends at bit 31
+                    const float f = (float)y;
+                    yf[m & 3] = f;
+                    minabs = fminf(minabs, fabsf(f));
+                    if ((m & 3) == 3) yo[32 * (m >> 2)] = make_float4(yf[0], yf[1], yf[2], yf[3]);
+                    if ((m & 31) == 31) { Scur |= (unsigned long long)__brev(sb) << (m & 32); sb = 0u; }
+                };
+                // The sections run skewed by one sample each (section s works on sample n - s), so every step
+                // holds NSEC independent recurrences.
+                double pipe[NSEC];                   // pipe[s]: output of section s-1 for the sample section s takes next
+                int4 q = rp[0];
+                if (!FAST || t == 0) {
+                    // per sample the arithmetic is exactly AxFilt::filter's
+                    double yl[6];                    // FAST: outputs 58..63 of the row
 #pragma unroll
-                for (int n = 0; n < 64 + NSEC - 1; ++n) {
+                    for (int n = 0; n < 64 + NSEC - 1; ++n) {
 #pragma unroll
-                    for (int s = NSEC - 1; s >= 0; --s) {
-                        const int m = n - s;         // sample this section handles in this step
-                        if (m >= 0 && m < 64) {
-                            double tt;
-                            if (s == 0) {
-                                if ((m & 7) == 0 && m > 0) q = rp[m >> 3];
-                                const int wdv = ((m & 7) >> 1) == 0 ? q.x : ((m & 7) >> 1) == 1 ? q.y : ((m & 7) >> 1) == 2 ? q.z : q.w;
-                                const int xi = (m & 1) ? (wdv >> 16) : (int)(short)(wdv & 0xFFFF);
-                                tt = fma((double)xi, k0, k1);
-                                if (HEAD && t == 0 && m < skip) tt = 0.0;      // before the chunk start: keeps the state at zero
-                            } else tt = pipe[s];
-                            const double y = tt + z0[s];
-                            z0[s] = fma(a1[s], y, fma(sg[s], tt, z1[s]));
-                            z1[s] = fma(a2[s], y, tt);
-                            if (s < NSEC - 1) pipe[s + 1] = y;
-                            else {
-                                sb = __funnelshift_l((unsigned)__double2hiint(y), sb, 1);   // MSB-first: sample 0 of this half ends at bit 31
-                                const float f = (float)y;
-                                yf[m & 3] = f;
-                                minabs = fminf(minabs, fabsf(f));
-                                if ((m & 3) == 3) yo[32 * (m >> 2)] = make_float4(yf[0], yf[1], yf[2], yf[3]);
-                                if ((m & 31) == 31) { Scur |= (unsigned long long)__brev(sb) << (m & 32); sb = 0u; }
+                        for (int s = NSEC - 1; s >= 0; --s) {
+                            const int m = n - s;         // sample this section handles in this step
+                            if (m >= 0 && m < 64) {
+                                double tt;
+                                if (s == 0) {
+                                    if ((m & 7) == 0 && m > 0) q = rp[m >> 3];
+                                    const int wdv = ((m & 7) >> 1) == 0 ? q.x : ((m & 7) >> 1) == 1 ? q.y : ((m & 7) >> 1) == 2 ? q.z : q.w;
+                                    const int xi = (m & 1) ? (wdv >> 16) : (int)(short)(wdv & 0xFFFF);
+                                    tt = fma((double)xi, k0, k1);
+                                    if (HEAD && t == 0 && m < skip) tt = 0.0;      // before the chunk start: keeps the state at zero
+                                } else tt = pipe[s];
+                                const double y = tt + z0[s];
+                                z0[s] = fma(a1[s], y, fma(sg[s], tt, z1[s]));
+                                z1[s] = fma(a2[s], y, tt);
+                                if (s < NSEC - 1) pipe[s + 1] = y;
+                                else {
+                                    if (FAST && m >= 58) yl[m - 58] = y;
+                                    emit(m, y);
+                                }
+                            }
+                        }
+                    }
+                    if (FAST) {
+                        // all-pole states after sample 63: z0[s] = y_s[63], z1[s] = y_s[62] (y_s = A_{s+1} y_{s+1}, y_2 = y)
+                        double w2[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) w2[i] = fma(-a1[2], yl[i + 1], fma(-a2[2], yl[i], yl[i + 2]));     // samples 60..63
+                        z0[2] = yl[5]; z1[2] = yl[4];
+                        z0[1] = w2[3]; z1[1] = w2[2];
+                        z0[0] = fma(-a1[1], w2[2], fma(-a2[1], w2[1], w2[3]));
+                        z1[0] = fma(-a1[1], w2[1], fma(-a2[1], w2[0], w2[2]));
+                    }
+                } else {
+                    int4 qp = make_int4(0, hist.x, hist.y, hist.z);          // words -4..-1 of the row (word -4 is not used)
+#pragma unroll
+                    for (int n = 0; n < 64 + NSEC - 1; ++n) {
+#pragma unroll
+                        for (int s = NSEC - 1; s >= 0; --s) {
+                            const int m = n - s;
+                            if (m >= 0 && m < 64) {
+                                double tt;
+                                if (s == 0) {
+                                    if ((m & 7) == 0 && m > 0) { qp = q; q = rp[m >> 3]; }
+                                    // packed words W[k - i], k = m >> 1 (x[2k] low half, x[2k+1] high half)
+                                    const int c = (m >> 1) & 3;
+                                    const int cw[4] = {q.x, q.y, q.z, q.w}, pw[4] = {qp.x, qp.y, qp.z, qp.w};
+                                    const int w0 = cw[c];
+                                    const int w1 = c >= 1 ? cw[c - 1] : pw[c + 3];
+                                    const int w2 = c >= 2 ? cw[c - 2] : pw[c + 2];
+                                    const int w3 = c >= 3 ? cw[c - 3] : pw[c + 1];
+                                    int u;
+                                    if ((m & 1) == 0) u = __dp2a_lo(w3, 0x0601, __dp2a_lo(w2, 0x140F, __dp2a_lo(w1, 0x060F, __dp2a_lo(w0, 0x0001, 0))));
+                                    else u = __dp2a_lo(w3, 0x0100, __dp2a_lo(w2, 0x0F06, __dp2a_lo(w1, 0x0F14, __dp2a_lo(w0, 0x0106, 0))));
+                                    tt = fma((double)u, k0, k1_64);
+                                } else tt = pipe[s];
+                                const double y = fma(a1[s], z0[s], fma(a2[s], z1[s], tt));
+                                z1[s] = z0[s]; z0[s] = y;
+                                if (s < NSEC - 1) pipe[s + 1] = y;
+                                else emit(m, y);
                             }
                         }
                     }
                 }
+                if (FAST) { const int4 ql = rp[7]; hist = make_int3(ql.y, ql.z, ql.w); }
                 // guard band: a filter output this close to zero cannot be signed reliably (AXCTD_DROP_UNCERTAIN)
                 if (minabs < guard_f) {
                     const int base = nb + 64 * t;
@@ -721,14 +781,14 @@ static inline void ax_launch_demod_ws(const AxWave& w, const AxCfg& c, int cfg_i
     k_demod_ws<NSEC, NPCM, HEAD><<<(unsigned)((items + per - 1) / per), AX_WS_THREADS, smem, stream>>>(w, c.win_tab, cfg_id, items);
 }
 
-template <int NSEC, int NPCM, bool HEAD>
+template <int NSEC, int NPCM, bool HEAD, bool FAST = false>
 static inline void ax_launch_demod_fused(const AxWave& w, const AxCfg& c, int cfg_id, int64_t n_items, cudaStream_t stream) {
     const size_t smem = sizeof(AxFdSmem);
     static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(k_demod_fused<NSEC, NPCM, HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+    if (!attr_set) { cudaFuncSetAttribute(k_demod_fused<NSEC, NPCM, HEAD, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
     const int64_t items = HEAD ? n_items : (int64_t)w.nseg_total;
     if (items <= 0) return;
-    k_demod_fused<NSEC, NPCM, HEAD><<<(unsigned)((items + AX_FD_THREADS - 1) / AX_FD_THREADS), AX_FD_THREADS, smem, stream>>>(w, c.win_tab, cfg_id, items);
+    k_demod_fused<NSEC, NPCM, HEAD, FAST><<<(unsigned)((items + AX_FD_THREADS - 1) / AX_FD_THREADS), AX_FD_THREADS, smem, stream>>>(w, c.win_tab, cfg_id, items);
 }
 
 // true if the fused kernel has an instantiation for this rate class
@@ -736,7 +796,13 @@ static inline bool ax_demod_fused_ok(const AxCfg& c) {
     return ax_sos_is_butter(c) && (c.nsec == 3 || c.nsec == 6) && (c.npcm == 39 || c.npcm == 43) && c.inset == 1;
 }
 template <bool HEAD>
-static inline void ax_launch_demod_fused_any(const AxWave& w, const AxCfg& c, int cfg_id, int64_t n_items, cudaStream_t stream, int ws) {
+static inline void ax_launch_demod_fused_any(const AxWave& w, const AxCfg& c, int cfg_id, int64_t n_items, cudaStream_t stream, int ws, int fast) {
+    // numerators-first cascade: continuous pass of the low-pass (every section with numerator g (1 + z^-1)^2) only
+    if (!HEAD && !ws && fast && c.nsec == 3 && c.sos[0][1] > 0.0 && c.sos[1][1] > 0.0 && c.sos[2][1] > 0.0) {
+        if (c.npcm == 39) ax_launch_demod_fused<3, 39, false, true>(w, c, cfg_id, n_items, stream);
+        else ax_launch_demod_fused<3, 43, false, true>(w, c, cfg_id, n_items, stream);
+        return;
+    }
     if (ws) {
         if (c.nsec == 3 && c.npcm == 39) ax_launch_demod_ws<3, 39, HEAD>(w, c, cfg_id, n_items, stream);
         else if (c.nsec == 3 && c.npcm == 43) ax_launch_demod_ws<3, 43, HEAD>(w, c, cfg_id, n_items, stream);

@@ -315,7 +315,7 @@ def run_native(args):
             "roofline": {"bound": "hbm", "kernel": "k_demod_fused (int16 -> SOS IIR f64 -> zero crossings -> mark/space windows f32)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "kernel_ms": f_ms, "tone_kernels_ms": float(np.mean(tone_ms)),
-                         "algorithmic_bytes": alg_bytes, "note": "13 DFMA-pipe ops per sample (3 biquads); FP64 pipe is the binding unit, not HBM"},
+                         "algorithmic_bytes": alg_bytes, "note": "issue-bound: 7 FP64-pipe ops (2.2 issue cycles each on B200) + 4 IDP.2A + ~20 other instructions per sample; HBM is not the binding unit"},
             "decoded": {"frames": frames, "rows": rows, "drops_not_ok": bad}}
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = host_cores()

@@ -159,6 +159,88 @@ static void run_mix(int nf, int nw, int fiters) {
            mean / (iters * 16.0), mean / (iters * 16.0) / (nf / 4.0));
     cudaFree(d); cudaFree(c);
 }
+
+// Issue budget next to the FP64 chains: the cascade plus EXTRA independent FFMAs per sample in the same warp.
+template <int EXTRA>
+__global__ void k_casc_extra(double* out, int iters, const __grid_constant__ Coef cc, float fa, float fb) {
+    double z0[3] = {0, 0, 0}, z1[3] = {0, 0, 0}, pipe[3] = {0, 0, 0};
+    float f[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) f[i] = (float)(threadIdx.x + i);
+    int v = threadIdx.x * 31 + 7;
+    double acc = 0.0;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int n = 0; n < 16; ++n) {
+#pragma unroll
+            for (int s = 2; s >= 0; --s) {
+                double tt;
+                if (s == 0) { v = v * 5 + 1; tt = fma((double)(short)(v >> 8), cc.k0, cc.k1); } else tt = pipe[s];
+                const double y = tt + z0[s];
+                z0[s] = fma(cc.a1[s], y, fma(cc.sg[s], tt, z1[s]));
+                z1[s] = fma(cc.a2[s], y, tt);
+                if (s < 2) pipe[s + 1] = y; else acc += (double)(float)y;
+            }
+#pragma unroll
+            for (int e = 0; e < EXTRA; ++e) f[e & 15] = fmaf(f[e & 15], fa, fb);
+        }
+    }
+    float fs = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) fs += f[i];
+    if (acc == 12345.678 || fs == 12345.678f) out[0] = acc + fs;
+}
+template <int EXTRA>
+static void run_extra(int wps) {
+    double* d; cudaMalloc(&d, 64);
+    Coef h;
+    const double A1[3] = {1.6926643005998814, 1.7591969461508574, 1.8877140066455618}, A2[3] = {-0.71770845316494558, -0.78522549575504252, -0.91564405607407828};
+    for (int s = 0; s < 3; ++s) { h.a1[s] = A1[s]; h.a2[s] = A2[s]; h.sg[s] = 2.0; }
+    h.k0 = 2.8447757653552447e-07 / 20000.0; h.k1 = 1e-9;
+    const int iters = 512;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    k_casc_extra<EXTRA><<<148, 128 * wps>>>(d, iters, h, 1.0000001f, 1e-9f);
+    cudaEventRecord(e0);
+    k_casc_extra<EXTRA><<<148, 128 * wps>>>(d, iters, h, 1.0000001f, 1e-9f);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    printf("cascade + %2d FFMA per sample, %d warps/SMSP: %.1f SMSP-cycles per warp-sample\n", EXTRA, wps, ms * 1e-3 * 1.965e9 / ((double)wps * iters * 16));
+    cudaFree(d);
+}
+
+// FFMA operand forms: three register operands vs two registers and a constant-bank operand (distinct constants)
+struct CTab { float t[64]; };
+template <bool CONST>
+__global__ void k_ffma_form(float* out, const float* in, int iters, const __grid_constant__ CTab ct) {
+    float x[8], y[8], acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { x[i] = in[threadIdx.x + 32 * i]; y[i] = in[threadIdx.x + 32 * i + 256]; acc[i] = 0.f; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = CONST ? fmaf(x[(i + k) & 7], ct.t[8 * k + i], acc[i]) : fmaf(x[(i + k) & 7], y[(i + 3 * k) & 7], acc[i]);
+        }
+    }
+    float sacc = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sacc += acc[i];
+    if (sacc == 12345.678f) out[0] = sacc;
+}
+template <bool CONST>
+static void run_form() {
+    float *d, *in; cudaMalloc(&d, 64); cudaMalloc(&in, 4096); cudaMemset(in, 0, 4096);
+    CTab ct; for (int i = 0; i < 64; ++i) ct.t[i] = 1.0f + i * 1e-3f;
+    const int iters = 2048;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    k_ffma_form<CONST><<<148 * 8, 256>>>(d, in, iters, ct);
+    cudaEventRecord(e0);
+    k_ffma_form<CONST><<<148 * 8, 256>>>(d, in, iters, ct);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    printf("FFMA %s: %.1f lanes/clk/SM\n", CONST ? "reg*const+reg" : "reg*reg+reg  ", 148.0 * 8 * 256 * iters * 64 / (ms * 1e-3) / 148 / 1.965e9);
+    cudaFree(d); cudaFree(in);
+}
 int main() {
     cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
     printf("%s SMs=%d clock=%d kHz\n", p.name, p.multiProcessorCount, p.clockRate);
@@ -182,6 +264,8 @@ int main() {
         printf("i2f+fadd+imad: %.3f ms, %.1f conv lanes/clk/SM\n", ms, n / (ms * 1e-3) / 148 / 1.965e9);
     }
     for (int wps = 1; wps <= 4; ++wps) { run_casc<false>(128 * wps, 1); run_casc<true>(128 * wps, 1); }
+    run_form<false>(); run_form<true>();
+    run_extra<0>(2); run_extra<4>(2); run_extra<8>(2); run_extra<12>(2); run_extra<16>(2); run_extra<24>(2); run_extra<32>(2); run_extra<16>(3); run_extra<32>(3);
     run_mix(8, 0, 0); run_mix(8, 8, 400); run_mix(8, 8, 4000); run_mix(4, 4, 4000); run_mix(8, 4, 4000); run_mix(12, 4, 4000);
     return 0;
 }
