@@ -9,4 +9,4 @@ Drop-in for the entry points of cdens/AXCTDprocessor:
 All signal processing runs in hand-written CUDA kernels (csrc/) behind the C
 ABI of include/axctd.h; there is no CPU fallback.
 """
-__all__ = ["AXCTDprocessor", "processAXCTD", "engine"]
+__all__ = ["AXCTDprocessor", "processAXCTD", "engine", "batch", "segment", "stream"]

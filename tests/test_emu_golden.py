@@ -260,6 +260,30 @@ def test_concurrent_decoder_returns_the_same_results(eng):
             assert np.array_equal(r.rows, g.rows)
 
 
+def test_streaming_decoder_ends_at_the_batch_result(eng):
+    """stream.StreamingDecoder: pushes + polls, then finish() equals the batch decode of the same samples."""
+    import synth
+    from axctdprocessor_b200 import batch as axbatch, stream as axstream
+    spec = synth.DropSpec(fs=44100, duration_s=52.0, seed=930, snr_db=25.0)
+    pcm = np.ascontiguousarray(synth.generate_drop(spec))
+    ref = axbatch.process_drops(eng, [pcm], [spec.fs])[0]
+    sd = axstream.StreamingDecoder(spec.fs, engine=eng, min_new_seconds=1.0)
+    cuts = [0, int(3.0 * spec.fs), int(44.0 * spec.fs), int(44.5 * spec.fs), len(pcm)]
+    polled = []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        sd.push(pcm[a:b])
+        polled.append(sd.poll())
+    assert polled[0] is None                       # 3 s: no pulse yet, nothing decodable
+    assert polled[2] is None                       # less than min_new_seconds of new audio: no decode
+    got = sd.finish()
+    assert got.status == 0 and np.array_equal(got.rows, ref.rows)
+    rows = [p for p in polled if p is not None]
+    assert rows and all((np.diff(p["time_s"]) >= 0).all() for p in rows)
+    assert sum(len(p) for p in rows) <= int((got.table()["keep"] == 1).sum()) + 8
+    sd.stop()
+    assert sd.push(pcm[:10]) == len(pcm)           # ignored after stop()
+
+
 def test_values_outside_the_compact_row_range_fall_back_to_full_records(eng):
     """A header that announces an absurd depth slope: depth * 100 no longer fits the compact row's int32, the
     row is flagged AXCTD_ROW_WIDE and table() takes the values from the full frame records instead."""

@@ -245,3 +245,40 @@ def test_random_batch_matches_oracle(eng):
     b.close()
     for s, p, out in zip(specs, pcms, outs):
         check_against_oracle(out, ao.process_pcm(p, s.fs))
+
+
+def test_streaming_decoder_ends_at_the_batch_result(eng):
+    """stream.StreamingDecoder on the device: provisional polls, finish() = batch decode of the whole recording
+    (which the tests above hold against the oracle and the reference fixtures)."""
+    from axctdprocessor_b200 import batch as axbatch, stream as axstream
+    spec = synth.DropSpec(fs=48000, duration_s=75.0, seed=4242, snr_db=25.0)
+    pcm = np.ascontiguousarray(synth.generate_drop(spec))
+    sd = axstream.StreamingDecoder(spec.fs, engine=eng, min_new_seconds=1.0)
+    seen = 0
+    step = int(5.0 * spec.fs)
+    for a in range(0, len(pcm), step):
+        sd.push(pcm[a:a + step])
+        new = sd.poll()
+        if new is not None:
+            seen += len(new)
+    got = sd.finish()
+    assert seen > 0
+    ref = axbatch.process_drops(eng, [pcm], [spec.fs])[0]
+    assert got.status == 0 and ref.status == 0 and np.array_equal(got.rows, ref.rows) and len(ref.rows) > 500
+
+
+def test_concurrent_decoder_matches_single_batch(eng):
+    """batch.ConcurrentDecoder (sub-batches on their own engines, streams and host threads) against one batch."""
+    from axctdprocessor_b200 import batch as axbatch
+    specs = [synth.DropSpec(fs=(44100, 48000)[i % 2], duration_s=50.0 + i, seed=7000 + i, snr_db=(40.0, 10.0)[i % 2]) for i in range(7)]
+    pcms = [np.ascontiguousarray(synth.generate_drop(s)) for s in specs]
+    ref = axbatch.process_drops(eng, pcms, [s.fs for s in specs])
+    cd = axbatch.ConcurrentDecoder(0, [len(p) for p in pcms], [s.fs for s in specs], shards=3)
+    for i, p in enumerate(pcms):
+        cd.upload(i, p)
+    cd.run(steps=3)
+    got = cd.results(full=False)
+    cd.close()
+    for r, g in zip(ref, got):
+        assert r.status == 0 and g.status == 0
+        assert np.array_equal(r.rows, g.rows)
