@@ -180,7 +180,7 @@ __device__ __forceinline__ void ax_warp_sum6(double* a, int lane) {
 // One warp per power sample: ragged ends + block sums (ax_tonewin_partial); the six sums go to tone_acc and
 // k_tone_mag turns them into magnitudes with one thread per power sample.
 // grid = (warps over the per-drop power-sample range [i_lo, i_hi), drop)
-__global__ void __launch_bounds__(256) k_tone_windows(AxWave w, int i_lo, int i_hi) {
+__global__ void __launch_bounds__(256, 4) k_tone_windows(AxWave w, int i_lo, int i_hi) {
     const int d = blockIdx.y;
     const int32_t i = i_lo + (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (i >= i_hi || i < w.tone_rng[2 * d] || i >= w.tone_rng[2 * d + 1]) return;
