@@ -109,6 +109,10 @@ struct axctd_engine {
     int device = 0;
     axStream stream = 0;
     bool own_stream = true;
+#ifndef AXCTD_EMU
+    cudaStream_t hp_stream = nullptr;     // highest priority: the demodulation pass gets the SMs first when sub-batches share the GPU
+#endif
+    int opt_heavy_prio = 1;
     std::string err;
     std::vector<AxCfg> cfgs;              // host copies (device pointers inside)
     std::vector<AxToneTab> tone_tabs;     // per config: phasors of one tone block (kernel parameter)
@@ -184,6 +188,7 @@ struct axctd_batch {
     double ms_total = 0, ms_filter = 0, ms_tone = 0;
 #ifndef AXCTD_EMU
     cudaEvent_t ev[6];
+    cudaEvent_t evx[2];                   // hand-over to / from the engine's high-priority stream
 #endif
 };
 
@@ -231,6 +236,11 @@ extern "C" int axctd_engine_create(int device, axctd_engine** out) {
         ax_fail(e, cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking), "cudaStreamCreate")) {
         delete e; *out = nullptr; return AXCTD_ERR_CUDA;
     }
+    {
+        int lo = 0, hi = 0;
+        if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess || hi >= lo ||
+            cudaStreamCreateWithPriority(&e->hp_stream, cudaStreamNonBlocking, hi) != cudaSuccess) { e->hp_stream = nullptr; cudaGetLastError(); }
+    }
 #endif
     void* p = nullptr;
     if (ax_alloc(e, &p, sizeof(AxCfg) * e->cfg_cap)) { delete e; *out = nullptr; return AXCTD_ERR_CUDA; }
@@ -245,6 +255,7 @@ extern "C" void axctd_engine_destroy(axctd_engine* e) {
     ax_free(e->d_cfg);
 #ifndef AXCTD_EMU
     if (e->stream && e->own_stream) cudaStreamDestroy(e->stream);
+    if (e->hp_stream) { cudaStreamSynchronize(e->hp_stream); cudaStreamDestroy(e->hp_stream); }
 #endif
     delete e;
 }
@@ -278,6 +289,7 @@ extern "C" int axctd_engine_set_option(axctd_engine* e, const char* name, double
     else if (s == "inject_misspec") e->opt_inject_misspec = (int)v;
     else if (s == "ws") e->opt_ws = (int)v;
     else if (s == "fir_first") e->opt_fir_first = (int)v;
+    else if (s == "heavy_prio") e->opt_heavy_prio = (int)v;
     else if (s == "heavy_chain") e->opt_heavy_chain = (int)v;
     else if (s == "scan_only") e->opt_scan_only = (int)v;
     else if (s == "bit_tol") e->opt_bit_tol = v;
@@ -421,6 +433,7 @@ extern "C" void axctd_batch_destroy(axctd_batch* b) {
 #ifndef AXCTD_EMU
     cudaStreamSynchronize(b->eng->stream);
     for (int i = 0; i < 6; ++i) cudaEventDestroy(b->ev[i]);
+    for (int i = 0; i < 2; ++i) cudaEventDestroy(b->evx[i]);
 #endif
     for (void* p : b->allocs) ax_free(p);
     ax_host_free(b->h_st); ax_host_free(b->h_row); ax_host_free(b->h_chunk);
@@ -436,6 +449,7 @@ extern "C" int axctd_batch_create(axctd_engine* e, int n_drops, const int64_t* n
 #ifndef AXCTD_EMU
     cudaSetDevice(e->device);
     for (int i = 0; i < 6; ++i) cudaEventCreate(&b->ev[i]);
+    for (int i = 0; i < 2; ++i) cudaEventCreateWithFlags(&b->evx[i], cudaEventDisableTiming);
 #endif
     int64_t total = 0;
     int warm_max = 0, head_cap_max = 0, chunk_len_max = 0;
@@ -774,10 +788,23 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
 #ifdef AXCTD_EMU
     AX_LAUNCH(e, k_toneblock, b->tb_total, w);
 #endif
+#ifndef AXCTD_EMU
+    // The demodulation pass runs on the engine's high-priority stream: with several sub-batches in flight its CTAs get
+    // the SMs ahead of the other engines' kernels, which fill in behind it.
+    cudaStream_t main_stream = e->stream;
+    if (e->hp_stream && e->opt_heavy_prio) {
+        cudaEventRecord(b->evx[0], main_stream); cudaStreamWaitEvent(e->hp_stream, b->evx[0], 0);
+        e->stream = e->hp_stream;
+    }
+#define AX_HEAVY_LEAVE() do { if (e->stream != main_stream) { cudaEventRecord(b->evx[1], e->stream); e->stream = main_stream; \
+                                                              cudaStreamWaitEvent(main_stream, b->evx[1], 0); } } while (0)
+#else
+#define AX_HEAVY_LEAVE() ((void)0)
+#endif
     ax_heavy_begin(e);
     AX_EVENT(b, 1);
     const bool scan_only = e->opt_scan_only != 0;     // tone levels only: no crossings are produced
-    if (scan_only) { if (ax_zero(e, w.seg_cnt, sizeof(int32_t) * (size_t)w.nseg_total)) { ax_heavy_end(e); return AXCTD_ERR_CUDA; } }
+    if (scan_only) { if (ax_zero(e, w.seg_cnt, sizeof(int32_t) * (size_t)w.nseg_total)) { ax_heavy_end(e); AX_HEAVY_LEAVE(); return AXCTD_ERR_CUDA; } }
 #ifndef AXCTD_EMU
     bool fused = e->opt_filter_variant == 0;
     std::vector<int> used_cfg;
@@ -798,6 +825,7 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
     { AX_LAUNCH(e, k_filter, (int64_t)w.nseg_total, w); }
     AX_EVENT(b, 2);
     ax_heavy_end(e);
+    AX_HEAVY_LEAVE();
     AX_LAUNCH(e, k_scan_block, (int64_t)w.nseg_total / 128, w);
     AX_LAUNCH1(e, k_scan, n, w);
 #ifndef AXCTD_EMU
