@@ -188,8 +188,68 @@ __global__ void __launch_bounds__(256, 4) k_tone_windows(AxWave w, int i_lo, int
     const AxCfg& c = w.cfg[dr.cfg];
     const int lane = threadIdx.x & 31;
     const int64_t slot = (int64_t)dr.pw_base + i;
+    const int64_t cstart = w.pw_ind[slot];
     double a[6];
-    ax_tonewin_partial(w, dr, c, w.pw_ind[slot], lane, 32, a);
+    // int16 source and ragged ends of at most AX_TB samples each (every window except the last ones of a recording):
+    // all ragged samples of the lane are fetched before the first use -- they come from HBM (the recording is far
+    // larger than L2), and fetched one loop iteration at a time their latency was what bound this kernel.  The
+    // sums themselves are ax_tonewin_partial's, term by term.
+    const int np = c.n_power;
+    int64_t j0 = (cstart + AX_TB - 1) / AX_TB, j1 = (cstart + np) / AX_TB;
+    if (j1 > dr.ntb) j1 = dr.ntb;
+    if (j1 < j0) j1 = j0;
+    const int head_n = (int)(j0 * AX_TB - cstart), tail_off = (int)(j1 * AX_TB - cstart);
+    if (dr.xf_off >= 0 || head_n > AX_TB || np - tail_off > AX_TB) {
+        ax_tonewin_partial(w, dr, c, cstart, lane, 32, a);
+    } else {
+        const int16_t* xs = w.pcm + dr.pcm_off + cstart;
+        int xh[AX_TB / 32], xt[AX_TB / 32];
+#pragma unroll
+        for (int k = 0; k < AX_TB / 32; ++k) {
+            const int m = lane + 32 * k;
+            xh[k] = (m < head_n) ? (int)xs[m] : 0;
+            xt[k] = (tail_off + m < np) ? (int)xs[tail_off + m] : 0;
+        }
+        const double* t0 = c.tone_soa; const double* t1 = t0 + np; const double* t2 = t1 + np;
+        const double* t3 = t2 + np; const double* t4 = t3 + np; const double* t5 = t4 + np;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, a4 = 0.0, a5 = 0.0;
+#pragma unroll
+        for (int k = 0; k < AX_TB / 32; ++k) {
+            const int m = lane + 32 * k;
+            if (m < head_n) {
+                const double xd = (double)xh[k];
+                a0 = fma(xd, t0[m], a0); a1 = fma(xd, t1[m], a1); a2 = fma(xd, t2[m], a2);
+                a3 = fma(xd, t3[m], a3); a4 = fma(xd, t4[m], a4); a5 = fma(xd, t5[m], a5);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < AX_TB / 32; ++k) {
+            const int m = tail_off + lane + 32 * k;
+            if (m < np) {
+                const double xd = (double)xt[k];
+                a0 = fma(xd, t0[m], a0); a1 = fma(xd, t1[m], a1); a2 = fma(xd, t2[m], a2);
+                a3 = fma(xd, t3[m], a3); a4 = fma(xd, t4[m], a4); a5 = fma(xd, t5[m], a5);
+            }
+        }
+        a[0] = a0; a[1] = a1; a[2] = a2; a[3] = a3; a[4] = a4; a[5] = a5;
+        const int nblk = (int)(j1 - j0);
+        const double* B0 = w.tb_sum + (dr.tb_base + j0) * 6;
+        double eh[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) eh[q] = c.tone_soa[(int64_t)q * np + head_n];
+        for (int jj = lane; jj < nblk; jj += 32) {
+            const double* B = B0 + 6 * jj;
+            const double* R = c.tone_rot[jj];
+#pragma unroll
+            for (int f = 0; f < 3; ++f) {
+                const double cr = fma(eh[2 * f], R[2 * f], -(eh[2 * f + 1] * R[2 * f + 1]));
+                const double sn = fma(eh[2 * f], R[2 * f + 1], eh[2 * f + 1] * R[2 * f]);
+                const double br = B[2 * f], bi = B[2 * f + 1];
+                a[2 * f] = fma(br, cr, fma(-bi, sn, a[2 * f]));
+                a[2 * f + 1] = fma(br, sn, fma(bi, cr, a[2 * f + 1]));
+            }
+        }
+    }
     ax_warp_sum6(a, lane);
     if ((lane & 15) == 0) { double* o = w.tone_acc + slot * 6 + (lane ? 3 : 0); o[0] = a[0]; o[1] = a[1]; o[2] = a[2]; }
 }
