@@ -210,16 +210,17 @@ __global__ void __launch_bounds__(256, 4) k_tone_windows(AxWave w, int i_lo, int
             xh[k] = (m < head_n) ? (int)xs[m] : 0;
             xt[k] = (tail_off + m < np) ? (int)xs[tail_off + m] : 0;
         }
-        const double* t0 = c.tone_soa; const double* t1 = t0 + np; const double* t2 = t1 + np;
-        const double* t3 = t2 + np; const double* t4 = t3 + np; const double* t5 = t4 + np;
+        // phasors from the interleaved table (three 16-byte loads per sample instead of six 8-byte ones)
+        const double2* tc = reinterpret_cast<const double2*>(c.tone_cs);
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, a4 = 0.0, a5 = 0.0;
 #pragma unroll
         for (int k = 0; k < AX_TB / 32; ++k) {
             const int m = lane + 32 * k;
             if (m < head_n) {
                 const double xd = (double)xh[k];
-                a0 = fma(xd, t0[m], a0); a1 = fma(xd, t1[m], a1); a2 = fma(xd, t2[m], a2);
-                a3 = fma(xd, t3[m], a3); a4 = fma(xd, t4[m], a4); a5 = fma(xd, t5[m], a5);
+                const double2 p0 = tc[3 * m], p1 = tc[3 * m + 1], p2 = tc[3 * m + 2];
+                a0 = fma(xd, p0.x, a0); a1 = fma(xd, p0.y, a1); a2 = fma(xd, p1.x, a2);
+                a3 = fma(xd, p1.y, a3); a4 = fma(xd, p2.x, a4); a5 = fma(xd, p2.y, a5);
             }
         }
 #pragma unroll
@@ -227,16 +228,17 @@ __global__ void __launch_bounds__(256, 4) k_tone_windows(AxWave w, int i_lo, int
             const int m = tail_off + lane + 32 * k;
             if (m < np) {
                 const double xd = (double)xt[k];
-                a0 = fma(xd, t0[m], a0); a1 = fma(xd, t1[m], a1); a2 = fma(xd, t2[m], a2);
-                a3 = fma(xd, t3[m], a3); a4 = fma(xd, t4[m], a4); a5 = fma(xd, t5[m], a5);
+                const double2 p0 = tc[3 * m], p1 = tc[3 * m + 1], p2 = tc[3 * m + 2];
+                a0 = fma(xd, p0.x, a0); a1 = fma(xd, p0.y, a1); a2 = fma(xd, p1.x, a2);
+                a3 = fma(xd, p1.y, a3); a4 = fma(xd, p2.x, a4); a5 = fma(xd, p2.y, a5);
             }
         }
         a[0] = a0; a[1] = a1; a[2] = a2; a[3] = a3; a[4] = a4; a[5] = a5;
         const int nblk = (int)(j1 - j0);
         const double* B0 = w.tb_sum + (dr.tb_base + j0) * 6;
         double eh[6];
-#pragma unroll
-        for (int q = 0; q < 6; ++q) eh[q] = c.tone_soa[(int64_t)q * np + head_n];
+        { const double2 e0 = tc[3 * head_n], e1 = tc[3 * head_n + 1], e2 = tc[3 * head_n + 2];
+          eh[0] = e0.x; eh[1] = e0.y; eh[2] = e1.x; eh[3] = e1.y; eh[4] = e2.x; eh[5] = e2.y; }
         for (int jj = lane; jj < nblk; jj += 32) {
             const double* B = B0 + 6 * jj;
             const double* R = c.tone_rot[jj];
