@@ -282,3 +282,31 @@ def test_concurrent_decoder_matches_single_batch(eng):
     for r, g in zip(ref, got):
         assert r.status == 0 and g.status == 0
         assert np.array_equal(r.rows, g.rows)
+
+
+def test_config3_full_size_recording(eng):
+    """BASELINE config 3 at full size: a 96 kHz, 1-hour recording holding five drops is halved on the device, cut by
+    the segmentation driver and decoded as one batch; every segment decodes, and the first segment's frames are the
+    oracle's (frame words bit-exact)."""
+    from axctdprocessor_b200 import segment
+    from oracle import axctd_oracle as ao
+    fs = 96000
+    specs = [synth.DropSpec(fs=fs, duration_s=720.0, seed=3300 + i, snr_db=(40.0, 25.0, 10.0)[i % 3]) for i in range(5)]
+    n = [int(round(s.duration_s * s.fs)) for s in specs]
+    gen = eng.batch(n, [eng.config(fs)] * len(n))          # the device twin of synth.generate_drop as a generator
+    parts = []
+    for i, s in enumerate(specs):
+        gen.synth_fill(i, s)
+        parts.append(gen.download(i))
+    gen.close()
+    pcm = np.concatenate(parts)
+    del parts
+    out = segment.process_recording(eng, pcm, fs / 2, decimate=2)
+    assert len(out) == 5 and [a for a, _, _ in out][0] == 0
+    for a, b, r in out:
+        assert r.status == 0 and 16900 < int(r.summary.n_frames) < 17100
+    a, b, r = out[0]
+    op = ao.process_pcm(pcm[a:b], fs)
+    words = np.array([int(h, 16) for h in op.hexframes], dtype=np.uint32)
+    tab = r.table()
+    assert np.array_equal(words, tab["word"][tab["hex_returned"] == 1])

@@ -1,6 +1,7 @@
 """BASELINE config 3 at full size: a 96 kHz, 1-hour recording that holds several drops, halved on the device,
 cut into one segment per drop by the segmentation driver and decoded as one batch on one GPU.
-Prints one JSON line (wall-clock, host buffers in and out); --oracle checks the first segment against the oracle."""
+Prints one JSON line (wall-clock, host buffers in and out).  The parity check of the same workload against the oracle
+is tests/test_gpu_parity.py::test_config3_full_size_recording."""
 import argparse, json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -10,7 +11,6 @@ from axctdprocessor_b200 import engine, segment
 ap = argparse.ArgumentParser()
 ap.add_argument("--drops", type=int, default=5)
 ap.add_argument("--duration", type=float, default=720.0)
-ap.add_argument("--oracle", action="store_true")
 args = ap.parse_args()
 fs = 96000
 eng = engine.Engine(0)
@@ -35,16 +35,5 @@ line = {"workload": f"config 3: {len(pcm) / fs:.0f} s at {fs} Hz, {args.drops} d
                     f"segmented by the engine's own 400 Hz level", "segments": [[int(a), int(b)] for a, b, _ in out],
         "status": [int(r.status) for _, _, r in out], "frames": [int(r.summary.n_frames) for _, _, r in out], "rows_kept": rows,
         "wall_s_first": wall, "wall_s": wall2, "x_realtime": len(pcm) / fs / wall2, "samples": int(len(pcm))}
-if args.oracle:
-    from oracle import axctd_oracle as ao
-    a, b, r = out[0]
-    t0 = time.perf_counter()
-    op = ao.process_pcm(pcm[a:b], fs)
-    line["oracle_s"] = time.perf_counter() - t0
-    words = np.array([int(h, 16) for h in op.hexframes], dtype=np.uint32) if hasattr(op, "hexframes") else None
-    line["oracle_frames"] = int(len(op.hexframes)) if hasattr(op, "hexframes") else None
-    tab = r.table()
-    got = tab["word"][tab["hex_returned"] == 1]
-    line["oracle_words_equal"] = bool(words is not None and len(words) == len(got) and np.array_equal(words, got))
 print(json.dumps(line))
 eng.close()

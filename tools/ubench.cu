@@ -241,6 +241,42 @@ static void run_form() {
     printf("FFMA %s: %.1f lanes/clk/SM\n", CONST ? "reg*const+reg" : "reg*reg+reg  ", 148.0 * 8 * 256 * iters * 64 / (ms * 1e-3) / 148 / 1.965e9);
     cudaFree(d); cudaFree(in);
 }
+
+// Packed FFMA2 (fma.rn.f32x2) with three register-pair operands: FMA lanes per clock
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__global__ void k_ffma2(float* out, const unsigned long long* in, int iters) {
+    unsigned long long x[8], y[8], acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { x[i] = in[threadIdx.x + 32 * i]; y[i] = in[threadIdx.x + 32 * i + 256]; acc[i] = 0ull; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = ffma2(x[(i + k) & 7], y[(i + 3 * k) & 7], acc[i]);
+        }
+    }
+    unsigned long long sacc = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sacc ^= acc[i];
+    if (sacc == 0x1234567812345678ull) out[0] = 1.f;
+}
+static void run_ffma2() {
+    float* d; unsigned long long* in; cudaMalloc(&d, 64); cudaMalloc(&in, 8192); cudaMemset(in, 0, 8192);
+    const int iters = 2048;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    k_ffma2<<<148 * 8, 256>>>(d, in, iters);
+    cudaEventRecord(e0);
+    k_ffma2<<<148 * 8, 256>>>(d, in, iters);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    printf("FFMA2 pair*pair+pair: %.1f FMA lanes/clk/SM (%.1f instruction lanes)\n", 2 * 148.0 * 8 * 256 * iters * 64 / (ms * 1e-3) / 148 / 1.965e9,
+           148.0 * 8 * 256 * iters * 64 / (ms * 1e-3) / 148 / 1.965e9);
+    cudaFree(d); cudaFree(in);
+}
 int main() {
     cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
     printf("%s SMs=%d clock=%d kHz\n", p.name, p.multiProcessorCount, p.clockRate);
@@ -264,7 +300,7 @@ int main() {
         printf("i2f+fadd+imad: %.3f ms, %.1f conv lanes/clk/SM\n", ms, n / (ms * 1e-3) / 148 / 1.965e9);
     }
     for (int wps = 1; wps <= 4; ++wps) { run_casc<false>(128 * wps, 1); run_casc<true>(128 * wps, 1); }
-    run_form<false>(); run_form<true>();
+    run_form<false>(); run_form<true>(); run_ffma2();
     run_extra<0>(2); run_extra<4>(2); run_extra<8>(2); run_extra<12>(2); run_extra<16>(2); run_extra<24>(2); run_extra<32>(2); run_extra<16>(3); run_extra<32>(3);
     run_mix(8, 0, 0); run_mix(8, 8, 400); run_mix(8, 8, 4000); run_mix(4, 4, 4000); run_mix(8, 4, 4000); run_mix(12, 4, 4000);
     return 0;
