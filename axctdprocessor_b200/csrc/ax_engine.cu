@@ -829,9 +829,8 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
     AX_LAUNCH(e, k_scan_block, (int64_t)w.nseg_total / 128, w);
     AX_LAUNCH1(e, k_scan, n, w);
 #ifndef AXCTD_EMU
-    k_compact_warp<<<(unsigned)(((int64_t)w.nseg_total * 32 + 255) / 256), 256, 0, e->stream>>>(w);
-    k_nx_grid<<<dim3(148, (unsigned)n), 256, 0, e->stream>>>(w);
-    e->launches += 2;
+    k_compact_warp<<<(unsigned)(((int64_t)w.nseg_total * 32 + 255) / 256), 256, 0, e->stream>>>(w);     // (+ walk steps)
+    e->launches += 1;
 #else
     AX_LAUNCH(e, k_compact, (int64_t)w.nseg_total, w);
     AX_LAUNCH(e, k_nx, b->zc_total, w);

@@ -4,7 +4,7 @@
 //                     400 / 7500 / dead-frequency DFT sums of every aligned 256-sample block (:358-364)
 //   k_tone_windows    0.1 s window magnitudes from the block sums and the ragged ends
 //   k_demod_fused     SOS cascade, zero crossings, mark / space windows (demodulate.py:74-102)
-//   k_compact_warp / k_nx_grid / k_canon_block   dense crossing arrays, walk steps, canonical walk tables
+//   k_compact_warp / k_canon_block               dense crossing arrays + walk steps, canonical walk tables
 //   k_emit_chunk / k_bits_chunk                  bit edges and bit decisions, one CTA per run() iteration
 #pragma once
 #include <cuda_runtime.h>
@@ -1347,31 +1347,52 @@ __global__ void __launch_bounds__(128) k_qc_warp(AxWave w, double* scratch) {
 }
 
 // ------------------------------------------------------------------ dense crossing arrays
-// ax_compact_item with a warp per segment (coalesced), and the walk steps (ax_nx_item) with a 2-D grid.
+// ax_compact_item with a warp per segment (coalesced) together with the walk steps (ax_nx_item).
 __global__ void __launch_bounds__(256) k_compact_warp(AxWave w) {
     const int64_t seg = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (seg >= w.nseg_total) return;
     const int lane = threadIdx.x & 31;
     const int d = w.seg_drop[seg];
     const AxDrop& dr = w.drop[d];
-    if (w.st[d].zc_count == 0) return;
+    const int64_t M = w.st[d].zc_count;
+    if (M == 0) return;
+    const AxCfg& c = w.cfg[dr.cfg];
     const int64_t src = seg * (int64_t)w.seg_cap, dst = dr.zc_base + w.seg_off[seg] + w.blk_sum[seg / 128];
     const int cnt = w.seg_cnt[seg];
+    if (cnt == 0) return;
+    // the walk step of every crossing (ax_nx_item) is formed here as well: it needs the next four crossings, which
+    // are this segment's own records or, for its last four, the first records of the segments that follow
+    int32_t la[4] = {0, 0, 0, 0};
+    {
+        int got = 0;
+        const int64_t seg_end = (int64_t)dr.seg_base + dr.nseg;
+        for (int64_t s2 = seg + 1; got < 4 && s2 < seg_end; ++s2) {
+            const int c2 = w.seg_cnt[s2];
+            for (int j = 0; j < c2 && got < 4; ++j) la[got++] = w.rec_idx[s2 * (int64_t)w.seg_cap + j];
+        }
+    }
+    const int64_t pos0 = dst - dr.zc_base;
+    const int64_t br2 = 2 * (int64_t)c.bitrate;
     for (int q = lane; q < cnt; q += 32) {
-        w.zc_idx[dst + q] = w.rec_idx[src + q];
+        const int32_t z0 = w.rec_idx[src + q];
+        w.zc_idx[dst + q] = z0;
         w.zc_a1[dst + q] = w.rec_a1[src + q];
         w.zc_a2[dst + q] = w.rec_a2[src + q];
+        uint8_t nx = 0;
+        if (pos0 + q + 4 < M) {                          // as ax_next: nearest to one bit period, first on ties
+            int64_t best = 0; int bj = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int qq = q + 1 + j;
+                const int32_t z = qq < cnt ? w.rec_idx[src + qq] : la[qq - cnt];
+                int64_t dd = ((int64_t)z - z0) * br2 - c.fs2;
+                if (dd < 0) dd = -dd;
+                if (j == 0 || dd < best) { best = dd; bj = j; }
+            }
+            nx = (uint8_t)(1 + bj);
+        }
+        w.zc_nx[dst + q] = nx;
     }
-}
-
-__global__ void __launch_bounds__(256) k_nx_grid(AxWave w) {
-    const int d = blockIdx.y;
-    const AxDrop& dr = w.drop[d];
-    const int64_t M = w.st[d].zc_count;
-    const AxCfg& c = w.cfg[dr.cfg];
-    const int32_t* zi = w.zc_idx + dr.zc_base;
-    for (int64_t pos = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pos < M; pos += (int64_t)gridDim.x * blockDim.x)
-        w.zc_nx[dr.zc_base + pos] = (pos + 4 < M) ? (uint8_t)(ax_next(zi, pos, c.fs2, 2 * (int64_t)c.bitrate) - pos) : (uint8_t)0;
 }
 
 // ------------------------------------------------------------------ canonical walk tables (block per drop)
