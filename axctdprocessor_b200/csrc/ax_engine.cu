@@ -9,6 +9,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <limits>
 #include <string>
 #include <vector>
 
@@ -574,8 +575,8 @@ extern "C" int axctd_batch_create(axctd_engine* e, int n_drops, const int64_t* n
     bad |= ax_alloc_arr(b, &w.tone_acc, 6 * (int64_t)pw_off);
     bad |= ax_alloc_arr(b, &w.tb_sum, tb_off * 6 + 8);
     bad |= ax_alloc_arr(b, &w.edge_idx, edge_off);
-    bad |= ax_alloc_arr(b, &w.lvl400, edge_off);
-    bad |= ax_alloc_arr(b, &w.lvl7500, edge_off);
+    bad |= ax_alloc_arr(b, &w.lvl_slot, edge_off);
+    bad |= ax_alloc_arr(b, &w.r7500m, pw_off);
     bad |= ax_alloc_arr(b, &w.bit, edge_off);
     bad |= ax_alloc_arr(b, &w.a1, edge_off);
     bad |= ax_alloc_arr(b, &w.a2, edge_off);
@@ -1064,9 +1065,21 @@ extern "C" int64_t axctd_batch_edges(axctd_batch* b, int drop, int64_t* edges, d
         if (ax_d2h(b->eng, tmp.data(), b->w.edge_idx + base, sizeof(int32_t) * ne) || ax_sync(b->eng)) return -AXCTD_ERR_CUDA;
         for (int64_t i = 0; i < ne; ++i) edges[i] = tmp[i];
     }
-    if (r400 && ne && ax_d2h(b->eng, r400, b->w.lvl400 + base, sizeof(double) * ne)) return -AXCTD_ERR_CUDA;
-    if (r7500 && ne && ax_d2h(b->eng, r7500, b->w.lvl7500 + base, sizeof(double) * ne)) return -AXCTD_ERR_CUDA;
-    if (ax_sync(b->eng)) return -AXCTD_ERR_CUDA;
+    if ((r400 || r7500) && ne) {
+        // edges hold the index of the power sample whose levels they take: gather on the host
+        const int64_t np = b->drops[drop].pw_cap, pb = b->drops[drop].pw_base;
+        std::vector<int32_t> sl(ne);
+        std::vector<double> l4(np > 0 ? np : 1), l7(np > 0 ? np : 1);
+        if (ax_d2h(b->eng, sl.data(), b->w.lvl_slot + base, sizeof(int32_t) * ne) ||
+            (np > 0 && ax_d2h(b->eng, l4.data(), b->w.r400 + pb, sizeof(double) * np)) ||
+            (np > 0 && ax_d2h(b->eng, l7.data(), b->w.r7500m + pb, sizeof(double) * np)) || ax_sync(b->eng)) return -AXCTD_ERR_CUDA;
+        const double nan = std::numeric_limits<double>::quiet_NaN();
+        for (int64_t i = 0; i < ne; ++i) {
+            const bool ok = sl[i] >= 0 && sl[i] < np;
+            if (r400) r400[i] = ok ? l4[sl[i]] : nan;
+            if (r7500) r7500[i] = ok ? l7[sl[i]] : nan;
+        }
+    }
     return ne;
 }
 

@@ -941,6 +941,7 @@ __global__ void __launch_bounds__(128) k_emit_chunk(AxWave w) {
     if (ne <= 0) return;
     const AxCfg& c = w.cfg[dr.cfg];
     const int nhe = ch.n_head_edges, npre = ch.n_pre;
+    ax_emit_levels(w, dr, ch, (int)threadIdx.x, (int)blockDim.x);
     for (int t = threadIdx.x; t < nhe; t += blockDim.x) ax_emit_edge(w, dr, st, c, ch, cg, k, t, 0);
     if (threadIdx.x == 0 && npre > 0) {
         const uint8_t* nx = w.zc_nx + dr.zc_base;

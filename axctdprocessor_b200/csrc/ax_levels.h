@@ -403,9 +403,22 @@ AX_HD void ax_emit_edge(const AxWave& w, const AxDrop& dr, AxState& st, const Ax
         if (2 * rem > c.d_pcm) ++jj;
         if (jj > ch.np - 1) jj = ch.np - 1;
         if (jj < 0) jj = 0;
-        w.lvl400[eo] = w.r400[dr.pw_base + ch.pw_off + jj];
-        w.lvl7500[eo] = ax_sub(w.r7500[dr.pw_base + ch.pw_off + jj], ch.mean7500);
-    } else { w.lvl400[eo] = ax_nan(); w.lvl7500[eo] = ax_nan(); }
+        w.lvl_slot[eo] = (int32_t)(ch.pw_off + jj);
+    } else w.lvl_slot[eo] = -1;
+}
+// The levels an edge takes (AXCTDprocessor.py:425-429): r400 and r7500 - mean7500pwr of its nearest power sample.
+// Edges store the sample's index only; r7500m holds the difference per power sample (ax_emit_levels).
+AX_HD double ax_lvl400(const AxWave& w, const AxDrop& dr, int64_t e) {
+    const int32_t sl = w.lvl_slot[dr.edge_base + e];
+    return sl < 0 ? ax_nan() : w.r400[dr.pw_base + sl];
+}
+AX_HD double ax_lvl7500(const AxWave& w, const AxDrop& dr, int64_t e) {
+    const int32_t sl = w.lvl_slot[dr.edge_base + e];
+    return sl < 0 ? ax_nan() : w.r7500m[dr.pw_base + sl];
+}
+AX_HD void ax_emit_levels(const AxWave& w, const AxDrop& dr, const AxChunk& ch, int first, int step) {
+    for (int j = first; j < ch.np; j += step)
+        w.r7500m[dr.pw_base + ch.pw_off + j] = ax_sub(w.r7500[dr.pw_base + ch.pw_off + j], ch.mean7500);
 }
 
 // position of the (r+1)-th set bit of m (r < popcount(m))
@@ -439,6 +452,7 @@ AX_HDN inline void ax_emit_item(const AxWave& w, int64_t cg) {
     if (ch.n_edges <= 0) return;
     const AxCfg& c = w.cfg[dr.cfg];
     const uint8_t* nx = w.zc_nx + dr.zc_base;
+    ax_emit_levels(w, dr, ch, 0, 1);
     int64_t pos = ch.g_first;
     for (int t = 0; t < ch.n_edges; ++t) {
         if (t >= ch.n_head_edges + ch.n_pre && ch.merge_pos >= 0) pos = ax_emit_canon_pos(w, dr, ch, t);

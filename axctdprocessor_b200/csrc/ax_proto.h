@@ -118,13 +118,12 @@ AX_HDN inline void ax_valid_item(const AxWave& w, int64_t wg) {
     const int64_t j0 = wg * 32 - dr.edge_base;
     if (st.sm_status < 2 || j0 >= st.nbits_total) { w.validw[wg] = 0; return; }
     const uint32_t* bw = w.bitw + dr.edge_base / 32;
-    const double* l7500 = w.lvl7500 + dr.edge_base;
     uint32_t v = 0;
     for (int q = 0; q < 32; ++q) {
         const int64_t p = j0 + q;
         if (p + 32 > st.nbits_total) break;
         const uint32_t wd = ax_frame_word(bw, p);
-        if ((wd >> 30) == 2u && ax_crc_ok(wd) && l7500[p] > 0.0) v |= 1u << q;
+        if ((wd >> 30) == 2u && ax_crc_ok(wd) && ax_lvl7500(w, dr, p) > 0.0) v |= 1u << q;
     }
     w.validw[wg] = v;
 }
@@ -335,7 +334,7 @@ AX_HDN inline void ax_calib_item(const AxWave& w, int64_t fg) {
         f.word = ax_frame_word(w.bitw + dr.edge_base / 32, p);
         f.edge_index = ei;
         f.time_raw = ax_div((double)(ei - st.profstartind), c.fs);     // AXCTDprocessor.py:554
-        f.r400_raw = w.lvl400[dr.edge_base + p]; f.r7500_raw = w.lvl7500[dr.edge_base + p];
+        f.r400_raw = ax_lvl400(w, dr, p); f.r7500_raw = ax_lvl7500(w, dr, p);
         f.hex_returned = 0;
     }
     f.cint = (int32_t)((f.word >> 18) & 0xFFF);           // bits 2..13  (parse.py:107)
