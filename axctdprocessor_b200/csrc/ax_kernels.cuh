@@ -100,7 +100,8 @@ __global__ void __launch_bounds__(AX_ST_THREADS) k_stats_tones(const __grid_cons
 #pragma unroll
                     for (int h = 0; h < 4; ++h) {
                         s32 = __dp2a_lo(wd[h], 0x0101, s32);
-                        const double x0 = (double)(int)(short)(wd[h] & 0xFFFF), x1 = (double)(wd[h] >> 16);
+                        const short2 xs2 = *reinterpret_cast<const short2*>(&wd[h]);      // I2F.F64.S16 on either half: no unpacking
+                        const double x0 = (double)xs2.x, x1 = (double)xs2.y;
                         const int m = 64 * r + v * 8 + h * 2;
 #pragma unroll
                         for (int q6 = 0; q6 < 6; ++q6) acc[q6] = fma(x0, tab.t[m][q6], acc[q6]);
@@ -436,8 +437,8 @@ __global__ void __launch_bounds__(AX_FD_THREADS, 2) k_demod_fused(const __grid_c
                                 if (s == 0) {
                                     if ((m & 7) == 0 && m > 0) q = rp[m >> 3];
                                     const int wdv = ((m & 7) >> 1) == 0 ? q.x : ((m & 7) >> 1) == 1 ? q.y : ((m & 7) >> 1) == 2 ? q.z : q.w;
-                                    const int xi = (m & 1) ? (wdv >> 16) : (int)(short)(wdv & 0xFFFF);
-                                    tt = fma((double)xi, k0, k1);
+                                    const short2 xs2 = *reinterpret_cast<const short2*>(&wdv);   // I2F.F64.S16 on either half
+                                    tt = fma((m & 1) ? (double)xs2.y : (double)xs2.x, k0, k1);
                                     if (HEAD && t == 0 && m < skip) tt = 0.0;      // before the chunk start: keeps the state at zero
                                 } else tt = pipe[s];
                                 const double y = tt + z0[s];
