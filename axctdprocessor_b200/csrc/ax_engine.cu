@@ -136,6 +136,7 @@ struct axctd_engine {
     int opt_bitfix_all = 0;               // test hook: re-evaluate every window
     int opt_ws = 0;                       // warp-specialised fused kernel (k_demod_ws)
     int opt_fir_first = 1;                // numerators-first cascade in the continuous low-pass pass (k_demod_fused FAST)
+    int opt_tone_mma = 1;                 // tone block sums on the FP64 tensor cores (k_stats_tones_mma)
     int opt_heavy_chain = 1;              // engines of one process take turns with the demodulation pass (see ax_heavy_*)
     int opt_scan_only = 0;                // tone levels only (segmentation of long recordings): skip the demodulation pass
 };
@@ -291,6 +292,7 @@ extern "C" int axctd_engine_set_option(axctd_engine* e, const char* name, double
     else if (s == "ws") e->opt_ws = (int)v;
     else if (s == "fir_first") e->opt_fir_first = (int)v;
     else if (s == "heavy_prio") e->opt_heavy_prio = (int)v;
+    else if (s == "tone_mma") e->opt_tone_mma = (int)v;
     else if (s == "heavy_chain") e->opt_heavy_chain = (int)v;
     else if (s == "scan_only") e->opt_scan_only = (int)v;
     else if (s == "bit_tol") e->opt_bit_tol = v;
@@ -420,6 +422,10 @@ extern "C" int axctd_config_create(axctd_engine* e, const axctd_config_desc* ds,
         for (int m = 0; m < c.n_power; ++m)
             for (int q = 0; q < 6; ++q) soa[(size_t)q * c.n_power + m] = ds->tone_cs[6 * (size_t)m + q];
         if (ax_cfg_upload(e, &c.tone_soa, soa.data(), soa.size())) return AXCTD_ERR_CUDA;
+        std::vector<double> t8(8 * (size_t)AX_TB, 0.0);
+        for (int m = 0; m < AX_TB && m < c.n_power; ++m)
+            for (int q = 0; q < 6; ++q) t8[8 * (size_t)m + q] = ds->tone_cs[6 * (size_t)m + q];
+        if (ax_cfg_upload(e, &c.tone_tab8, t8.data(), t8.size())) return AXCTD_ERR_CUDA;
     }
     e->cfgs.push_back(c);
     e->tone_tabs.push_back(ttab);
@@ -766,7 +772,12 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
     {   // one pass over the PCM: statistics and the tone block sums, one launch per rate class in use
         for (size_t ci = 0; ci < e->cfgs.size(); ++ci) {
             if (!std::any_of(b->drops.begin(), b->drops.end(), [&](const AxDrop& d) { return d.cfg == (int)ci; })) continue;
-            k_stats_tones<<<dim3((unsigned)((w.ntb_max + AX_ST_THREADS - 1) / AX_ST_THREADS), (unsigned)n), AX_ST_THREADS, 0, e->stream>>>(w, e->tone_tabs[ci], (int)ci);
+            if (e->opt_tone_mma) {
+                static bool attr_set = false;
+                if (!attr_set) { cudaFuncSetAttribute(k_stats_tones_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AX_STM_SMEM); attr_set = true; }
+                k_stats_tones_mma<<<dim3((unsigned)((w.ntb_max + AX_STM_GROUPS * AX_ST_THREADS - 1) / (AX_STM_GROUPS * AX_ST_THREADS)), (unsigned)n), AX_ST_THREADS, AX_STM_SMEM, e->stream>>>(w, e->cfgs[ci].tone_tab8, (int)ci);
+            } else
+                k_stats_tones<<<dim3((unsigned)((w.ntb_max + AX_ST_THREADS - 1) / AX_ST_THREADS), (unsigned)n), AX_ST_THREADS, 0, e->stream>>>(w, e->tone_tabs[ci], (int)ci);
             e->launches++;
         }
         if (w.nslab_total > 0) { k_stats_wrap<<<w.nslab_total, 256, 0, e->stream>>>(w); e->launches++; }

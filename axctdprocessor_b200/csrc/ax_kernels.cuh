@@ -142,6 +142,137 @@ __global__ void __launch_bounds__(AX_ST_THREADS) k_stats_tones(const __grid_cons
     }
 }
 
+// The same pass with the block sums on the FP64 tensor cores.  The sums are a tall-skinny product -- (blocks x 256
+// samples) x (256 x 6 phasors) -- and one DMMA m8n8k4 does the work of eight warp-wide DFMAs (eight blocks x four
+// samples x eight columns, six of them used) while holding the issue port for a single cycle: a vector DFMA blocks
+// it for 2.2 cycles, which is what bounds k_stats_tones (tools/ubench.cu: 16.5 cycles per DMMA with up to ~12 other
+// instructions issued underneath).  Lane = tone block for the staging and the statistics as before; for the DMMAs
+// the warp's 32 blocks form four groups of eight rows: A[i][c] = sample 4 ks + c of block 8 g + i (lane = 4 i + c),
+// B[c][n] = phasor n of that sample (shared-memory table, one 8-byte load per k-step, reused by the four groups),
+// C[i][2 (lane & 3) + {0, 1}] accumulates over the 64 k-steps of a block.
+#define AX_STM_GROUPS 4
+#define AX_STM_SMEM (AX_TB * 8 * sizeof(double) + (AX_ST_THREADS / 32) * 2 * 32 * 72 * sizeof(int16_t))
+__device__ __forceinline__ void ax_dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__global__ void __launch_bounds__(AX_ST_THREADS) k_stats_tones_mma(const __grid_constant__ AxWave w, const double* __restrict__ tab8, int cfg_id) {
+    extern __shared__ __align__(16) unsigned char ax_smem_raw[];       // AX_STM_SMEM bytes: phasor table, then the staging rows
+    double* ptab = reinterpret_cast<double*>(ax_smem_raw);
+    int16_t (*stage_all)[2][32 * 72] = reinterpret_cast<int16_t (*)[2][32 * 72]>(ax_smem_raw + AX_TB * 8 * sizeof(double));
+    const int d = blockIdx.y;
+    const AxDrop& dr = w.drop[d];
+    if (dr.cfg != cfg_id) return;
+    const int64_t nsamp = dr.n_raw;                  // statistics are taken over the recording as uploaded
+    const int64_t nblk = (nsamp + AX_TB - 1) / AX_TB;
+    if ((int64_t)blockIdx.x * AX_STM_GROUPS * AX_ST_THREADS >= nblk) return;
+    for (int i = threadIdx.x; i < AX_TB * 8; i += AX_ST_THREADS) ptab[i] = tab8[i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int16_t (*stage)[32 * 72] = stage_all[warp];
+    const int prow = lane >> 3, piece = lane & 7;
+    const int arow = lane >> 2, acol = lane & 3;     // A / C row (block within the group), A column (sample within the k-step)
+    long long sum = 0;
+    int mx2 = (int)0x80008000, mn2 = 0x7fff7fff;        // packed int16 max / min
+    // a CTA takes AX_STM_GROUPS consecutive groups of 128 blocks, so that the table load above is paid once per 128 K samples
+#pragma unroll 1
+    for (int grp = 0; grp < AX_STM_GROUPS; ++grp) {
+    const int64_t jg = ((int64_t)blockIdx.x * AX_STM_GROUPS + grp) * AX_ST_THREADS;
+    if (jg >= nblk) break;
+    const int64_t jb = jg + threadIdx.x;
+    const bool active = jb < nblk;
+    const int64_t n0 = jb * AX_TB;
+    const int T = active ? (int)min((int64_t)4, (nsamp - n0 + 63) >> 6) : 0;
+    const unsigned long long xrow = (unsigned long long)(w.pcm + dr.pcm_off + n0);
+    unsigned long long src[8];
+    int Tr[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        src[i] = __shfl_sync(0xffffffffu, xrow, i * 4 + prow) + (unsigned long long)piece * 16;
+        Tr[i] = __shfl_sync(0xffffffffu, T, i * 4 + prow);
+    }
+    auto issue = [&](int t, int s) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (t < Tr[i]) ax_cp_async16(&stage[s][(i * 4 + prow) * 72 + piece * 8], reinterpret_cast<const void*>(src[i] + (unsigned long long)t * 128));
+        ax_cp_async_commit();
+    };
+    double acc[4][2];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) { acc[g][0] = 0.0; acc[g][1] = 0.0; }
+    issue(0, 0);
+#pragma unroll 1
+    for (int r = 0; r < 4; ++r) {
+        if (r + 1 < 4) { issue(r + 1, (r + 1) & 1); ax_cp_async_wait<1>(); } else ax_cp_async_wait<0>();
+        __syncwarp();
+        // block sums: rows of blocks that do not reach this far hold stale samples; their sums are never stored
+        {
+            const int16_t* st = stage[r & 1];
+            const double* pt = ptab + (64 * r + acol) * 8 + arow;
+#pragma unroll 4
+            for (int ks = 0; ks < 16; ++ks) {
+                const double b = pt[32 * ks];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const double a = (double)st[(8 * g + arow) * 72 + 4 * ks + acol];
+                    ax_dmma884(acc[g][0], acc[g][1], a, b);
+                }
+            }
+        }
+        if (r < T) {
+            const int4* rp = reinterpret_cast<const int4*>(&stage[r & 1][lane * 72]);
+            const int nvalid = (int)min((int64_t)64, nsamp - (n0 + 64 * r));
+            if (nvalid == 64) {
+                int s32 = 0;
+#pragma unroll
+                for (int v = 0; v < 8; ++v) {
+                    const int4 q = rp[v];
+                    mx2 = (int)__vimax3_s16x2((unsigned)mx2, (unsigned)q.x, (unsigned)q.y);
+                    mx2 = (int)__vimax3_s16x2((unsigned)mx2, (unsigned)q.z, (unsigned)q.w);
+                    mn2 = (int)__vimin3_s16x2((unsigned)mn2, (unsigned)q.x, (unsigned)q.y);
+                    mn2 = (int)__vimin3_s16x2((unsigned)mn2, (unsigned)q.z, (unsigned)q.w);
+                    s32 = __dp2a_lo(q.x, 0x0101, s32); s32 = __dp2a_lo(q.y, 0x0101, s32);
+                    s32 = __dp2a_lo(q.z, 0x0101, s32); s32 = __dp2a_lo(q.w, 0x0101, s32);
+                }
+                sum += s32;
+            } else {                                   // ragged end of the recording
+                const int16_t* xs = &stage[r & 1][lane * 72];
+                for (int i = 0; i < nvalid; ++i) {
+                    const int v = xs[i];
+                    sum += v;
+                    const int pk = (v & 0xFFFF) | (v << 16);
+                    mx2 = (int)__vimax3_s16x2((unsigned)mx2, (unsigned)pk, (unsigned)pk);
+                    mn2 = (int)__vimin3_s16x2((unsigned)mn2, (unsigned)pk, (unsigned)pk);
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (dr.xf_off < 0 && acol < 3) {                   // (a decimating drop takes its block sums from the halved signal)
+        const int64_t jw = jg + warp * 32;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const int64_t j = jw + 8 * g + arow;
+            if (j < dr.ntb) {
+                double* out = w.tb_sum + (dr.tb_base + j) * 6 + 2 * acol;
+                out[0] = acc[g][0]; out[1] = acc[g][1];
+            }
+        }
+    }
+    }
+    int mx = max((int)(short)(mx2 & 0xFFFF), mx2 >> 16), mn = min((int)(short)(mn2 & 0xFFFF), mn2 >> 16);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    }
+    if (lane == 0) {
+        atomicAdd((unsigned long long*)&w.st[d].sum, (unsigned long long)sum);
+        atomicMax(&w.st[d].vmax, mx);
+        atomicMin(&w.st[d].vmin, mn);
+    }
+}
+
 // ------------------------------------------------------------------ tone window magnitudes
 // Per-drop power-sample range [lo, hi) of a tone launch (the range test of ax_tone_slot_active, once per drop).
 __global__ void k_tone_range(AxWave w, int phase_b) {

@@ -139,7 +139,7 @@ def test_batch_equals_single_drops(eng):
 
 @pytest.mark.parametrize("opts", [dict(tone_direct=1), dict(force_exact=1), dict(inject_misspec=1),
                                   dict(segment_len=4096), dict(segment_len=32768), dict(filter_variant=1),
-                                  dict(bitfix_all=1), dict(bit_tol=1e-3, hist_tol=1e-3), dict(ws=1), dict(ws=1, segment_len=4096), dict(fir_first=0), dict(fir_first=0, segment_len=4096)])
+                                  dict(bitfix_all=1), dict(bit_tol=1e-3, hist_tol=1e-3), dict(ws=1), dict(ws=1, segment_len=4096), dict(fir_first=0), dict(fir_first=0, segment_len=4096), dict(tone_mma=0)])
 def test_kernel_variants_agree_with_reference(opts):
     g = Golden("g48_25db")
     e = _engine(**opts)

@@ -277,6 +277,50 @@ static void run_ffma2() {
            148.0 * 8 * 256 * iters * 64 / (ms * 1e-3) / 148 / 1.965e9);
     cudaFree(d); cudaFree(in);
 }
+
+// FP64 tensor core (DMMA m8n8k4): FMA rate and issue cost next to the vector FP64 pipe
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+template <int EXTRA>
+__global__ void k_dmma(double* out, int iters, float fa, float fb) {
+    double c[4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { c[i][0] = 0.0; c[i][1] = 0.0; }
+    double a = 1.0 + threadIdx.x * 1e-3, b = 0.5 + threadIdx.x * 1e-4;
+    float f[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) f[i] = (float)(threadIdx.x + i);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            dmma884(c[i][0], c[i][1], a, b);
+#pragma unroll
+            for (int e = 0; e < EXTRA; ++e) f[(4 * i + e) & 15] = fmaf(f[(4 * i + e) & 15], fa, fb);
+        }
+    }
+    double s = 0; float fs = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s += c[i][0] + c[i][1];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) fs += f[i];
+    if (s == 12345.678 || fs == 12345.678f) out[0] = s + fs;
+}
+template <int EXTRA>
+static void run_dmma(int wps) {
+    double* d; cudaMalloc(&d, 64);
+    const int iters = 2048;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    k_dmma<EXTRA><<<148, 128 * wps>>>(d, iters, 1.0000001f, 1e-9f);
+    cudaEventRecord(e0);
+    k_dmma<EXTRA><<<148, 128 * wps>>>(d, iters, 1.0000001f, 1e-9f);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    const double n = 148.0 * 4 * wps * iters * 4;            // DMMA instructions
+    printf("DMMA m8n8k4 + %d FFMA each, %d warps/SMSP: %.2f TFMA/s, %.1f SMSP-cycles per DMMA\n", EXTRA, wps, n * 256 / (ms * 1e-3) / 1e12,
+           ms * 1e-3 * 1.965e9 / (iters * 4.0 * wps));
+    cudaFree(d);
+}
 int main() {
     cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
     printf("%s SMs=%d clock=%d kHz\n", p.name, p.multiProcessorCount, p.clockRate);
@@ -301,6 +345,7 @@ int main() {
     }
     for (int wps = 1; wps <= 4; ++wps) { run_casc<false>(128 * wps, 1); run_casc<true>(128 * wps, 1); }
     run_form<false>(); run_form<true>(); run_ffma2();
+    run_dmma<0>(1); run_dmma<0>(2); run_dmma<0>(4); run_dmma<8>(4); run_dmma<16>(4);
     run_extra<0>(2); run_extra<4>(2); run_extra<8>(2); run_extra<12>(2); run_extra<16>(2); run_extra<24>(2); run_extra<32>(2); run_extra<16>(3); run_extra<32>(3);
     run_mix(8, 0, 0); run_mix(8, 8, 400); run_mix(8, 8, 4000); run_mix(4, 4, 4000); run_mix(8, 4, 4000); run_mix(12, 4, 4000);
     return 0;
