@@ -740,7 +740,10 @@ static int ax_run_tones(axctd_batch* b, int phase_b) {
             }
             if (i_hi > i_lo) {
                 k_tone_range<<<(b->n + 127) / 128, 128, 0, e->stream>>>(w, phase_b);
-                k_tone_windows<<<dim3((unsigned)(((int64_t)(i_hi - i_lo) * 32 + 255) / 256), (unsigned)b->n), 256, 0, e->stream>>>(w, i_lo, i_hi);
+                if (e->opt_tone_mma)
+                    k_tone_windows_mma<<<dim3((unsigned)((i_hi - i_lo + 31) / 32), (unsigned)b->n), 128, 0, e->stream>>>(w, i_lo, i_hi);
+                else
+                    k_tone_windows<<<dim3((unsigned)(((int64_t)(i_hi - i_lo) * 32 + 255) / 256), (unsigned)b->n), 256, 0, e->stream>>>(w, i_lo, i_hi);
                 k_tone_mag<<<dim3((unsigned)((i_hi - i_lo + 127) / 128), (unsigned)b->n), 128, 0, e->stream>>>(w, i_lo, i_hi);
                 e->launches += 3;
             }

@@ -387,6 +387,87 @@ __global__ void __launch_bounds__(256, 4) k_tone_windows(AxWave w, int i_lo, int
     ax_warp_sum6(a, lane);
     if ((lane & 15) == 0) { double* o = w.tone_acc + slot * 6 + (lane ? 3 : 0); o[0] = a[0]; o[1] = a[1]; o[2] = a[2]; }
 }
+// The same sums with the ragged ends on the FP64 tensor cores: a warp takes eight consecutive power samples.  Their
+// ragged heads all use the phasors of window offsets 0 .. 255 and their ragged tails the same phasors relative to the
+// tail's first sample (rotated once by e^{j theta tail_off} afterwards, like the block sums), so both are products
+// (8 windows x 256 samples) x (256 x 6 phasors): A[i][c] = sample 4 ks + c of window i's head (tail), zero past its end,
+// B = the table of k_stats_tones_mma, one DMMA each per k-step, no k-steps past the longest end of the eight.  The
+// result lands with lane (i, f) holding (re, im) of frequency f of window i; that lane adds the window's full blocks
+// and stores -- no warp reduction, one 2-byte load per ragged sample and no per-sample phasor loads.  Windows with a
+// ragged end above AX_TB samples (last windows of a recording) or a double-precision source take the generic sums.
+__global__ void __launch_bounds__(128) k_tone_windows_mma(AxWave w, int i_lo, int i_hi) {
+    const int d = blockIdx.y;
+    const int lo = max(i_lo, w.tone_rng[2 * d]), hi = min(i_hi, w.tone_rng[2 * d + 1]);
+    const int lane = threadIdx.x & 31;
+    const int i0 = i_lo + 8 * (int)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
+    if (i0 >= hi || i0 + 8 <= lo) return;
+    const AxDrop& dr = w.drop[d];
+    const AxCfg& c = w.cfg[dr.cfg];
+    const int arow = lane >> 2, acol = lane & 3;
+    const int np = c.n_power;
+    const int iw = i0 + arow;
+    const bool valid = iw >= lo && iw < hi;
+    const int64_t slot = (int64_t)dr.pw_base + iw;
+    const int64_t cstart = valid ? w.pw_ind[slot] : 0;
+    int64_t j0 = (cstart + AX_TB - 1) / AX_TB, j1 = (cstart + np) / AX_TB;       // full blocks j0 .. j1-1
+    if (j1 > dr.ntb) j1 = dr.ntb;
+    if (j1 < j0) j1 = j0;
+    const int head_n = (int)(j0 * AX_TB - cstart), tail_off = (int)(j1 * AX_TB - cstart);
+    const bool regular = valid && dr.xf_off < 0 && head_n <= AX_TB && np - tail_off <= AX_TB && tail_off <= np;
+    const int hn = regular ? head_n : 0, tn = regular ? np - tail_off : 0;
+    int kmax = max(hn, tn);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+    const int ks_end = (kmax + 3) >> 2;
+    const int16_t* xh = w.pcm + dr.pcm_off + cstart;
+    const int16_t* xt = xh + tail_off;
+    const double* bt = c.tone_tab8 + acol * 8 + arow;
+    double h0 = 0.0, h1 = 0.0, t0 = 0.0, t1 = 0.0;
+#pragma unroll 8
+    for (int ks = 0; ks < ks_end; ++ks) {
+        const int m = 4 * ks + acol;
+        const double b = bt[32 * ks];
+        const double ah = (m < hn) ? (double)xh[m] : 0.0;
+        const double at = (m < tn) ? (double)xt[m] : 0.0;
+        ax_dmma884(h0, h1, ah, b);
+        ax_dmma884(t0, t1, at, b);
+    }
+    if (regular && acol < 3) {
+        const int f = acol;
+        const double* tcs = c.tone_cs;
+        double are, aim;
+        {
+            const double ec = tail_off < np ? tcs[6 * (int64_t)tail_off + 2 * f] : 0.0, es = tail_off < np ? tcs[6 * (int64_t)tail_off + 2 * f + 1] : 0.0;
+            are = h0 + fma(ec, t0, -(es * t1));
+            aim = h1 + fma(ec, t1, es * t0);
+        }
+        const double ehc = tcs[6 * (int64_t)head_n + 2 * f], ehs = tcs[6 * (int64_t)head_n + 2 * f + 1];
+        const int nblk = (int)(j1 - j0);
+        const double* B0 = w.tb_sum + (dr.tb_base + j0) * 6 + 2 * f;
+        for (int jj = 0; jj < nblk; ++jj) {
+            const double rc = c.tone_rot[jj][2 * f], rs = c.tone_rot[jj][2 * f + 1];
+            const double cr = fma(ehc, rc, -(ehs * rs));
+            const double sn = fma(ehc, rs, ehs * rc);
+            const double br = B0[6 * jj], bi = B0[6 * jj + 1];
+            are = fma(br, cr, fma(-bi, sn, are));
+            aim = fma(br, sn, fma(bi, cr, aim));
+        }
+        double* o = w.tone_acc + slot * 6 + 2 * f;
+        o[0] = are; o[1] = aim;
+    }
+    // the windows this form does not cover, one after the other with the whole warp
+    unsigned irr = __ballot_sync(0xffffffffu, valid && !regular && acol == 0);
+    while (irr) {
+        const int L = __ffs((int)irr) - 1;
+        irr &= irr - 1;
+        const int64_t cs = __shfl_sync(0xffffffffu, cstart, L);
+        const int64_t sl = (int64_t)dr.pw_base + i0 + (L >> 2);
+        double a[6];
+        ax_tonewin_partial(w, dr, c, cs, lane, 32, a);
+        ax_warp_sum6(a, lane);
+        if ((lane & 15) == 0) { double* o = w.tone_acc + sl * 6 + (lane ? 3 : 0); o[0] = a[0]; o[1] = a[1]; o[2] = a[2]; }
+    }
+}
 __global__ void __launch_bounds__(128) k_tone_mag(AxWave w, int i_lo, int i_hi) {
     const int d = blockIdx.y;
     const int32_t i = i_lo + (int)(blockIdx.x * blockDim.x + threadIdx.x);
