@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(256, 4) k_tone_windows(AxWave w, int i_lo, int
 // result lands with lane (i, f) holding (re, im) of frequency f of window i; that lane adds the window's full blocks
 // and stores -- no warp reduction, one 2-byte load per ragged sample and no per-sample phasor loads.  Windows with a
 // ragged end above AX_TB samples (last windows of a recording) or a double-precision source take the generic sums.
-__global__ void __launch_bounds__(128) k_tone_windows_mma(AxWave w, int i_lo, int i_hi) {
+__global__ void __launch_bounds__(128, 8) k_tone_windows_mma(AxWave w, int i_lo, int i_hi) {
     const int d = blockIdx.y;
     const int lo = max(i_lo, w.tone_rng[2 * d]), hi = min(i_hi, w.tone_rng[2 * d + 1]);
     const int lane = threadIdx.x & 31;
@@ -441,17 +441,20 @@ __global__ void __launch_bounds__(128) k_tone_windows_mma(AxWave w, int i_lo, in
             are = h0 + fma(ec, t0, -(es * t1));
             aim = h1 + fma(ec, t1, es * t0);
         }
+        // full blocks: sum_j e^{j theta (head_n + AX_TB j)} B_j = e^{j theta head_n} * sum_j e^{j theta AX_TB j} B_j
         const double ehc = tcs[6 * (int64_t)head_n + 2 * f], ehs = tcs[6 * (int64_t)head_n + 2 * f + 1];
         const int nblk = (int)(j1 - j0);
         const double* B0 = w.tb_sum + (dr.tb_base + j0) * 6 + 2 * f;
+        double sr = 0.0, si = 0.0;
+#pragma unroll 4
         for (int jj = 0; jj < nblk; ++jj) {
             const double rc = c.tone_rot[jj][2 * f], rs = c.tone_rot[jj][2 * f + 1];
-            const double cr = fma(ehc, rc, -(ehs * rs));
-            const double sn = fma(ehc, rs, ehs * rc);
             const double br = B0[6 * jj], bi = B0[6 * jj + 1];
-            are = fma(br, cr, fma(-bi, sn, are));
-            aim = fma(br, sn, fma(bi, cr, aim));
+            sr = fma(br, rc, fma(-bi, rs, sr));
+            si = fma(br, rs, fma(bi, rc, si));
         }
+        are += fma(ehc, sr, -(ehs * si));
+        aim += fma(ehc, si, ehs * sr);
         double* o = w.tone_acc + slot * 6 + 2 * f;
         o[0] = are; o[1] = aim;
     }
