@@ -70,6 +70,29 @@ def gather_results(local: dict, world_size: int, rank: int, all_gather_object: C
     return merged
 
 
+def bind_host_thread_to_gpu(device: int) -> bool:
+    """Restrict the calling thread (and the threads it starts later) to the CPUs NVML reports as local to the GPU,
+    so that pinned ingest buffers allocated afterwards sit on the NUMA node the GPU's PCIe link hangs off.  Returns
+    False (and changes nothing) when NVML or the affinity call is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = None
+        try:                                    # CUDA device order need not be NVML's (CUDA_VISIBLE_DEVICES): go by PCI address
+            import torch
+            pr = torch.cuda.get_device_properties(int(device))
+            bus = "%08x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        except Exception:
+            h = None
+        if h is None:
+            h = pynvml.nvmlDeviceGetHandleByIndex(int(device))
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return True
+    except Exception:
+        return False
+
+
 class PipelinedDecoder:
     """Ingest pipeline for a stream of batches on one GPU.
 

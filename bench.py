@@ -186,6 +186,7 @@ def run_native(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from axctdprocessor_b200 import batch as axbatch
+    numa_bound = axbatch.bind_host_thread_to_gpu(local) if world > 1 else False      # (one rank per GPU: keep its pinned buffers local)
     opts = {kv.split("=")[0]: float(kv.split("=")[1]) for kv in args.opt}
     specs = drop_specs(args.drops, args.duration, rank)
     n = [int(round(s.duration_s * s.fs)) for s in specs]
@@ -310,7 +311,7 @@ def run_native(args):
             "config": workload_config(args.drops, args.duration, total_samples, len(streams)),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(d2h_bytes),
-                    "steps": args.e2e_steps, "parts": nparts, "note": "pinned host PCM -> axctd_batch_upload -> run -> compact rows to host, wall clock from an idle pipeline to the last result; the batch goes through batch.PipelinedDecoder in parts so that H2D overlaps decode"},
+                    "steps": args.e2e_steps, "parts": nparts, "host_thread_bound_to_gpu_numa_node": bool(numa_bound), "note": "pinned host PCM -> axctd_batch_upload -> run -> compact rows to host, wall clock from an idle pipeline to the last result; the batch goes through batch.PipelinedDecoder in parts so that H2D overlaps decode"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_demod_fused (int16 -> SOS IIR f64 -> zero crossings -> mark/space windows f32)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
