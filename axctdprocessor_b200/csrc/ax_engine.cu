@@ -921,10 +921,19 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
 #endif
 #ifndef AXCTD_EMU
 #define AX_BITS(phase) do { k_bits_chunk<<<(unsigned)b->chunk_total, 128, 0, e->stream>>>(w, phase); e->launches++; } while (0)
+    {   // phase 0 needs the iterations that overlap [first pulse + 1.8 s, + 3.8 s] (+ margins): the first few after k0
+        int nk = 1;
+        for (int d2 = 0; d2 < n; ++d2) {
+            const AxCfg& c2 = e->cfgs[b->drops[d2].cfg];
+            const double span = (double)c2.h1e + (double)c2.half + 128.0 * c2.fs / c2.bitrate + (double)c2.chunk_len;
+            nk = std::max(nk, (int)(span / (0.9 * (double)c2.chunk_len)) + 3);
+        }
+        k_bits_chunk<<<dim3((unsigned)nk, (unsigned)n), 128, 0, e->stream>>>(w, 0); e->launches++;
+    }
 #else
 #define AX_BITS(phase) AX_LAUNCH(e, k_bits, b->edge_total, w, phase)
-#endif
     AX_BITS(0);
+#endif
 #ifndef AXCTD_EMU
     k_scale_block<<<n, 128, 0, e->stream>>>(w); e->launches++;
 #else

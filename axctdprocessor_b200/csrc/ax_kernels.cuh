@@ -1097,9 +1097,19 @@ static inline void ax_launch_demod_fused_any(const AxWave& w, const AxCfg& c, in
 // ------------------------------------------------------------------ bit decisions with shared window sums
 // As ax_bits_item, one CTA per run() iteration (no per-bit searches); a window that needs double
 // precision is summed by the whole warp.
+// grid (chunks of the batch) for all iterations, or (iterations after the first demodulated one, drops) when only the
+// first few of every drop matter (phase 0: header 1 sits within four seconds of the first pulse)
 __global__ void __launch_bounds__(128) k_bits_chunk(AxWave w, int phase) {
-    const int64_t cg = blockIdx.x;
-    const int d = ax_find_owner(w.drop, w.n_drops, &AxDrop::chunk_base, cg);
+    int d;
+    int64_t cg;
+    if (gridDim.y > 1 || phase == 0) {
+        d = blockIdx.y;
+        cg = (int64_t)w.drop[d].chunk_base + w.st[d].k0 + blockIdx.x;
+        if (w.st[d].k0 + (int)blockIdx.x >= w.drop[d].chunk_cap) return;
+    } else {
+        cg = blockIdx.x;
+        d = ax_find_owner(w.drop, w.n_drops, &AxDrop::chunk_base, cg);
+    }
     const AxDrop& dr = w.drop[d];
     const AxState& st = w.st[d];
     const int k = (int)(cg - dr.chunk_base);
