@@ -14,6 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libaxctd.so")
 
 MAX_SECTIONS = 6
+ABI_VERSION = 2          # AXCTD_ABI_VERSION of include/axctd.h
 
 
 class ConfigDesc(C.Structure):
@@ -49,6 +50,7 @@ class DropSummary(C.Structure):
         ("n_bits", C.c_int64), ("n_edges", C.c_int64), ("n_power", C.c_int64),
         ("n_frames", C.c_int64), ("n_rows", C.c_int64), ("n_hex", C.c_int64), ("n_crossings", C.c_int64),
         ("n_uncertain", C.c_int32), ("n_chain_fixups", C.c_int32),
+        ("n_guard_hits", C.c_int32), ("n_guard_confirmed", C.c_int32),
         ("pcm_sum", C.c_int64), ("pcm_ampl", C.c_int32), ("n_recheck", C.c_int32),
         ("win32_max_rel_err", C.c_float), ("n_frame_respec", C.c_int32),
         ("frame_data", (C.c_uint16 * 72) * 2), ("counter_found", (C.c_uint8 * 72) * 2),
@@ -75,7 +77,7 @@ class Chunk(C.Structure):
     _fields_ = [
         ("s", C.c_int64), ("e", C.c_int64), ("status", C.c_int32), ("n_power_total", C.c_int32),
         ("n_bits", C.c_int32), ("first_edge", C.c_int32), ("last_edge", C.c_int32), ("n_head_edges", C.c_int32),
-        ("n_rows", C.c_int32), ("n_hex", C.c_int32), ("scale", C.c_double),
+        ("n_rows", C.c_int32), ("n_hex", C.c_int32), ("scale", C.c_double), ("profstartind", C.c_int64),
     ]
 
 
@@ -106,7 +108,7 @@ SYMBOLS = [
     "axctd_batch_destroy", "axctd_batch_upload", "axctd_batch_device_pcm", "axctd_batch_run",
     "axctd_batch_run_async", "axctd_batch_finish", "axctd_batch_timing", "axctd_batch_summary",
     "axctd_batch_rows", "axctd_batch_frames", "axctd_batch_chunks", "axctd_batch_bits", "axctd_batch_edges", "axctd_batch_power",
-    "axctd_synth_fill", "axctd_batch_download",
+    "axctd_synth_fill", "axctd_batch_download", "axctd_calib_eval",
 ]
 
 
@@ -142,6 +144,7 @@ def bind(lib: C.CDLL) -> C.CDLL:
         "axctd_batch_power": (i64, [vp, i32, vp, vp, vp, i64]),
         "axctd_synth_fill": (i32, [vp, i32, P(SynthDesc)]),
         "axctd_batch_download": (i32, [vp, i32, vp, i64]),
+        "axctd_calib_eval": (i32, [vp, vp, vp, vp, i32, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -166,7 +169,7 @@ def load() -> C.CDLL:
                 f"{LIB_PATH} not found: build the CUDA extension first (python -c 'import __graft_entry__ as g; "
                 "g.build()').  axctdprocessor_b200 has no CPU fallback.")
         lib = bind(C.CDLL(LIB_PATH))
-        if lib.axctd_abi_version() != 1:
+        if lib.axctd_abi_version() != ABI_VERSION:
             raise ImportError("libaxctd.so ABI version mismatch")
         if not lib.axctd_has_cuda():
             raise ImportError("libaxctd.so was not built with CUDA kernels")

@@ -29,6 +29,19 @@ static inline void ax_host_atomic_max(int* p, int v) {
 #define AX_ATOMIC_MAX32(p, v) ax_host_atomic_max((int*)(p), (int)(v))
 #endif
 
+// ------------------------------------------------------------------ guard band
+// A filter output closer to zero than `guard` cannot be signed reliably by the fast passes (their operation order
+// differs from scipy's by ~1e-14 of full scale).  Such samples are listed here and settled after the chunk chain is
+// final (ax_unc_resolve_item): kp1 = 0 for the continuous pass, chunk + 1 for the zero-state head of that iteration.
+AX_HD void ax_unc_push(const AxWave& w, int d, int64_t n, bool neg, int kp1, int64_t chunk_s) {
+    const int slot = (int)AX_ATOMIC_ADD32(&w.st[d].n_unc_listed, 1);
+    if (slot >= 0 && slot < AX_UNC_CAP) {
+        int64_t* e = w.unc_list + ((int64_t)d * AX_UNC_CAP + slot) * 2;
+        e[0] = (n & 0xffffffffll) | (neg ? (1ll << 32) : 0ll) | ((int64_t)kp1 << 33);
+        e[1] = chunk_s;
+    }
+}
+
 // ------------------------------------------------------------------ lookups
 template <typename T>
 AX_HD int ax_find_owner(const AxDrop* drop, int n_drops, T AxDrop::*base, int64_t v) {
@@ -183,9 +196,11 @@ struct AxFilt {
     double guard;
     const AxWinTab* tab;
     int32_t* rec_idx; float* rec_a1; float* rec_a2;
+    const AxWave* uw; int32_t ud, ukp1; int64_t us;       // where guard-band samples are listed (ax_unc_push)
 
     AX_HD void init(const AxCfg& c, const AxState& st, int32_t s0, int32_t s1, double guard_,
-                    int32_t* ri, float* r1, float* r2, int32_t cap_) {
+                    int32_t* ri, float* r1, float* r2, int32_t cap_, const AxWave* uw_, int ud_, int ukp1_, int64_t us_) {
+        uw = uw_; ud = ud_; ukp1 = ukp1_; us = us_;
         const double kmul = st.inv_ampl, kadd = -(st.dc * st.inv_ampl);
 #pragma unroll
         for (int s = 0; s < NSEC; ++s) {
@@ -262,7 +277,7 @@ struct AxFilt {
             put(i, v1, v2);
             pop();
         }
-        if (fabs(u) < guard && n >= seg_start && n < seg_end) ++unc;
+        if (fabs(u) < guard && n >= seg_start && n < seg_end) { ++unc; ax_unc_push(*uw, ud, n, signbit(u) != 0, ukp1, us); }
         prev_neg = neg; have_prev = true;
     }
 
@@ -287,19 +302,20 @@ AX_HDN inline void ax_filter_segment(const AxWave& w, int64_t seg) {
     const int d = w.seg_drop[seg];
     const AxDrop& dr = w.drop[d];
     const int64_t j = seg - dr.seg_base;
-    if (j >= dr.nseg) { w.seg_cnt[seg] = 0; return; }
+    if (j >= dr.nseg) { w.seg_cnt[seg] = 0; w.seg_unc[seg] = 0; return; }
     const AxCfg& c = w.cfg[dr.cfg];
     AxState& st = w.st[d];
     const AxSegGeom g = ax_seg_geom(dr, c, w.seg_len, j);
     const AxSrc x = ax_src(w, dr);
     const int64_t slot = seg * (int64_t)w.seg_cap;
     AxFilt<NSEC, BUTTER> f;
-    f.init(c, st, (int32_t)g.seg_start, (int32_t)g.seg_end, w.guard, w.rec_idx + slot, w.rec_a1 + slot, w.rec_a2 + slot, w.seg_cap);
+    f.init(c, st, (int32_t)g.seg_start, (int32_t)g.seg_end, w.guard, w.rec_idx + slot, w.rec_a1 + slot, w.rec_a2 + slot, w.seg_cap,
+           &w, d, 0, 0);
     for (int64_t n = g.n_begin; n < g.n_stop; ++n) f.step((int32_t)n, ax_get(x, n));
     f.finish();
-    if (f.cnt > w.seg_cap) { w.flags[AX_FLAG_CAP] = 1; f.cnt = w.seg_cap; }
+    if (f.cnt > w.seg_cap) { w.flags[AX_FLAG_CAP] = 1; ax_raise(st, AXCTD_DROP_CAPACITY, -1); f.cnt = w.seg_cap; }   // crossings were dropped: fail the drop
     w.seg_cnt[seg] = f.cnt;
-    if (f.unc) AX_ATOMIC_ADD32(&st.n_uncertain, f.unc);
+    w.seg_unc[seg] = f.unc;
 }
 
 AX_HDN inline void ax_filter_item(const AxWave& w, int64_t seg) {
@@ -585,19 +601,20 @@ AX_HD AxHeadGeom ax_head_geom(const AxWave& w, const AxDrop& dr, const AxState& 
 // generic form of the head filter (the CUDA build runs k_demod_fused<.., HEAD> for the rate classes it
 // is instantiated for; `only_rest`: skip those)
 template <int NSEC, bool BUTTER>
-AX_HDN inline void ax_headfilt_run(const AxWave& w, int64_t cg, const AxDrop& dr, const AxCfg& c, AxState& st, const AxHeadGeom& g) {
+AX_HDN inline void ax_headfilt_run(const AxWave& w, int64_t cg, int d, const AxDrop& dr, const AxCfg& c, AxState& st, const AxHeadGeom& g) {
     int32_t* hz = w.head_idx + cg * (int64_t)w.head_zc_cap_max;
     float* ha1 = w.head_a1 + cg * (int64_t)w.head_zc_cap_max;
     float* ha2 = w.head_a2 + cg * (int64_t)w.head_zc_cap_max;
     const AxSrc x = ax_src(w, dr);
     AxFilt<NSEC, BUTTER> f;
-    f.init(c, st, (int32_t)(g.s + c.pad), (int32_t)(g.s + g.H - 1), w.guard, hz, ha1, ha2, w.head_zc_cap_max);
+    f.init(c, st, (int32_t)(g.s + c.pad), (int32_t)(g.s + g.H - 1), w.guard, hz, ha1, ha2, w.head_zc_cap_max,
+           &w, d, (int)(cg - dr.chunk_base) + 1, g.s);
     for (int64_t n = g.s; n < g.s + g.ny; ++n) f.step((int32_t)n, ax_get(x, n));
     f.finish();
     const int cnt = f.cnt > w.head_zc_cap_max ? -1 : f.cnt;
     for (int q = 0; q < cnt; ++q) hz[q] -= (int32_t)g.s;               // chunk-relative
     w.head_cnt[cg] = cnt;
-    if (f.unc) AX_ATOMIC_ADD32(&st.n_uncertain, f.unc);
+    w.head_unc[cg] = f.unc;
 }
 AX_HDN inline void ax_headfilt_item(const AxWave& w, int64_t cg, int only_rest) {
     const int d = ax_find_owner(w.drop, w.n_drops, &AxDrop::chunk_base, cg);
@@ -610,12 +627,12 @@ AX_HDN inline void ax_headfilt_item(const AxWave& w, int64_t cg, int only_rest) 
     if (!g.active) return;
     const bool bt = ax_sos_is_butter(c);
     if (only_rest && bt && (c.nsec == 3 || c.nsec == 6) && (c.npcm == 39 || c.npcm == 43) && c.inset == 1 && dr.xf_off < 0) return;
-    if (c.nsec == 3) { if (bt) ax_headfilt_run<3, true>(w, cg, dr, c, st, g); else ax_headfilt_run<3, false>(w, cg, dr, c, st, g); }
-    else if (c.nsec == 6) { if (bt) ax_headfilt_run<6, true>(w, cg, dr, c, st, g); else ax_headfilt_run<6, false>(w, cg, dr, c, st, g); }
-    else if (c.nsec == 1) ax_headfilt_run<1, false>(w, cg, dr, c, st, g);
-    else if (c.nsec == 2) ax_headfilt_run<2, false>(w, cg, dr, c, st, g);
-    else if (c.nsec == 4) ax_headfilt_run<4, false>(w, cg, dr, c, st, g);
-    else ax_headfilt_run<5, false>(w, cg, dr, c, st, g);
+    if (c.nsec == 3) { if (bt) ax_headfilt_run<3, true>(w, cg, d, dr, c, st, g); else ax_headfilt_run<3, false>(w, cg, d, dr, c, st, g); }
+    else if (c.nsec == 6) { if (bt) ax_headfilt_run<6, true>(w, cg, d, dr, c, st, g); else ax_headfilt_run<6, false>(w, cg, d, dr, c, st, g); }
+    else if (c.nsec == 1) ax_headfilt_run<1, false>(w, cg, d, dr, c, st, g);
+    else if (c.nsec == 2) ax_headfilt_run<2, false>(w, cg, d, dr, c, st, g);
+    else if (c.nsec == 4) ax_headfilt_run<4, false>(w, cg, d, dr, c, st, g);
+    else ax_headfilt_run<5, false>(w, cg, d, dr, c, st, g);
 }
 
 // Bit edges of the head (greedy walk over its crossings, demodulate.py:85-93), then join the
@@ -723,6 +740,73 @@ AX_HDN inline void ax_verify_item(const AxWave& w, int64_t d) {
     }
     st.chain_from = st.n_chunks;
     st.chain_end = 1;
+}
+
+// ------------------------------------------------------------------ guard-band samples, settled exactly
+// One listed sample (ax_unc_push) after the chunk chain is final.  The reference signs the output of
+// scipy.signal.sosfilt run from zero state over the slice of ITS iteration (demodulate.py:74-78), so for every
+// demodulated iteration that takes a crossing at this sample -- from the continuous pass past the head, or from the
+// head recomputation of exactly that iteration -- the cascade is run again from the iteration's start in scipy's
+// operation order without contraction (ax_biquad_exact) on the reference's own normalised samples
+// (AXCTDprocessor.py:57), and its sign is compared with the one the fast pass used.  Samples outside every
+// demodulated iteration (the lead-in before the first pulse, recordings without a pulse) do not matter.
+AX_HD bool ax_exact_sign_neg(const AxWave& w, const AxDrop& dr, const AxCfg& c, const AxState& st, int64_t s, int64_t n) {
+    const AxSrc x = ax_src(w, dr);
+    double z[AX_MAXSEC][2];
+    for (int q = 0; q < AX_MAXSEC; ++q) { z[q][0] = 0.0; z[q][1] = 0.0; }
+    double y = 0.0;
+    for (int64_t m = s; m <= n; ++m) {
+        double u = x.xf ? x.xf[m] : ax_div(ax_sub((double)x.x[m], st.dc), st.ampl_d);
+        for (int q = 0; q < c.nsec; ++q) u = ax_biquad_exact(u, c.sos[q], z[q][0], z[q][1]);
+        y = u;
+    }
+    return y < 0.0;                                     // np.sign(y), zeros counted as positive (demodulate.py:77-78)
+}
+AX_HDN inline void ax_unc_resolve_item(const AxWave& w, int64_t item) {
+    const int d = (int)(item / AX_UNC_CAP), j = (int)(item % AX_UNC_CAP);
+    AxState& st = w.st[d];
+    if (st.status != 0 || st.sm_status < 1 || j >= st.n_unc_listed) return;
+    const AxDrop& dr = w.drop[d];
+    const AxCfg& c = w.cfg[dr.cfg];
+    const int64_t* e = w.unc_list + ((int64_t)d * AX_UNC_CAP + j) * 2;
+    const int64_t n = e[0] & 0xffffffffll;
+    const bool neg = (e[0] >> 32) & 1;
+    const int kp1 = (int)(e[0] >> 33);
+    const AxChunk* ch = w.chunk + dr.chunk_base;
+    bool relevant = false, ok = true;
+    if (kp1 > 0) {                                      // head of iteration kp1 - 1, filtered from the start it had then
+        const int k = kp1 - 1;
+        if (k >= st.k0 && k < st.n_chunks && ch[k].s == e[1]) { relevant = true; ok = ax_exact_sign_neg(w, dr, c, st, ch[k].s, n) == neg; }
+    } else {
+        for (int k = st.k0; k < st.n_chunks && k < dr.chunk_cap; ++k) {
+            if (ch[k].s > n) break;
+            const int64_t len = ch[k].e - ch[k].s;
+            const int64_t H = (w.force_exact || c.head > len) ? len : c.head;
+            if (H >= len || n < ch[k].s + H - 1 || n > ch[k].e - 1) continue;      // crossings H-1 .. len-2 come from the continuous pass
+            relevant = true;
+            if (ax_exact_sign_neg(w, dr, c, st, ch[k].s, n) != neg) ok = false;
+        }
+    }
+    if (relevant) {
+        AX_ATOMIC_ADD32(&st.n_unc_relevant, 1);
+        if (ok) AX_ATOMIC_ADD32(&st.n_unc_resolved, 1); else AX_ATOMIC_ADD32(&st.n_uncertain, 1);
+    }
+}
+// More guard-band samples than the list holds: the unlisted ones are only known as counts per segment / per head;
+// any that can lie inside a demodulated iteration stays unconfirmed.
+AX_HDN inline void ax_unc_fin_item(const AxWave& w, int64_t d) {
+    AxState& st = w.st[d];
+    if (st.status != 0 || st.sm_status < 1 || st.n_unc_listed <= AX_UNC_CAP) return;
+    const AxDrop& dr = w.drop[d];
+    const AxCfg& c = w.cfg[dr.cfg];
+    const AxChunk* ch = w.chunk + dr.chunk_base;
+    const int64_t lo = ch[st.k0].s + c.pad;
+    int64_t cnt = 0;
+    for (int j = 0; j < dr.nseg; ++j)
+        if (((int64_t)j + 1) * w.seg_len > lo) cnt += w.seg_unc[dr.seg_base + j];
+    for (int k = st.k0; k < st.n_chunks && k < dr.chunk_cap; ++k) cnt += w.head_unc[dr.chunk_base + k];
+    const int64_t unlisted = cnt - st.n_unc_relevant;
+    if (unlisted > 0) st.n_uncertain += (int32_t)(unlisted > 0x3fffffff ? 0x3fffffff : unlisted);
 }
 
 // ------------------------------------------------------------------ /2 decimation (AXCTDprocessor.py:60-62)

@@ -86,6 +86,8 @@ AX_GLOBAL void k_chain(int64_t n, AxWave w) { AX_FOR_ITEM1(n) ax_chain_item(w, i
 AX_GLOBAL void k_headfilt(int64_t n, AxWave w, int only_rest) { AX_FOR_ITEM(n) ax_headfilt_item(w, item, only_rest); }
 AX_GLOBAL void k_headwalk(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_headwalk_item(w, item); }
 AX_GLOBAL void k_verify(int64_t n, AxWave w) { AX_FOR_ITEM1(n) ax_verify_item(w, item); }
+AX_GLOBAL void k_unc_resolve(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_unc_resolve_item(w, item); }
+AX_GLOBAL void k_unc_fin(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_unc_fin_item(w, item); }
 AX_GLOBAL void k_plan_tones(int64_t n, AxWave w) { AX_FOR_ITEM1(n) ax_plan_tones_item(w, item); }
 AX_GLOBAL void k_offsets(int64_t n, AxWave w) { AX_FOR_ITEM1(n) ax_offsets_item(w, item); }
 AX_GLOBAL void k_emit(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_emit_item(w, item); }
@@ -102,6 +104,12 @@ AX_GLOBAL void k_synth(int64_t n, AxSynth g) { AX_FOR_ITEM(n) ax_synth_item(g, i
 AX_GLOBAL void k_qc(int64_t n, AxWave w, double* scratch) { AX_FOR_ITEM(n) ax_qc_item(w, item, scratch); }
 AX_GLOBAL void k_decim(int64_t n, AxWave w, int pass) { AX_FOR_ITEM(n) ax_decim_item(w, item, pass); }
 AX_GLOBAL void k_decim_fin(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_decim_fin(w, item); }
+AX_GLOBAL void k_calib_eval(int64_t n, const double* in, double* out, int has_coeff) {
+    AX_FOR_ITEM(n) {       // in: [3][n] cond, temp, pres then 4 coefficients; out: [2][n] sp, poly
+        out[item] = ax_sp_from_c(in[item], in[n + item], in[2 * n + item]);
+        out[n + item] = has_coeff ? ax_dataconvert(in[item], in + 3 * n) : 0.0;
+    }
+}
 AX_GLOBAL void k_rows(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_row_item(w, item); }
 AX_GLOBAL void k_chunkout(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_chunkout_item(w, item); }
 
@@ -148,6 +156,8 @@ static int ax_h2d(axctd_engine*, void* d, const void* h, size_t b) { memcpy(d, h
 static int ax_d2h(axctd_engine*, void* h, const void* d, size_t b) { memcpy(h, d, b); return 0; }
 static int ax_zero(axctd_engine*, void* d, size_t b) { memset(d, 0, b); return 0; }
 static int ax_sync(axctd_engine*) { return 0; }
+static int ax_launch_check(axctd_engine*) { return 0; }
+#define AX_DEV(e) ((void)0)
 #else
 static int ax_fail(axctd_engine* e, cudaError_t r, const char* what) {
     if (r == cudaSuccess) return 0;
@@ -159,7 +169,15 @@ static void ax_free(void* p) { if (p) cudaFree(p); }
 static int ax_h2d(axctd_engine* e, void* d, const void* h, size_t b) { return ax_fail(e, cudaMemcpyAsync(d, h, b, cudaMemcpyHostToDevice, e->stream), "H2D"); }
 static int ax_d2h(axctd_engine* e, void* h, const void* d, size_t b) { return ax_fail(e, cudaMemcpyAsync(h, d, b, cudaMemcpyDeviceToHost, e->stream), "D2H"); }
 static int ax_zero(axctd_engine* e, void* d, size_t b) { return ax_fail(e, cudaMemsetAsync(d, 0, b, e->stream), "memset"); }
-static int ax_sync(axctd_engine* e) { return ax_fail(e, cudaStreamSynchronize(e->stream), "sync"); }
+// A bad launch configuration (missing shared-memory opt-in, oversized grid ...) is reported by cudaGetLastError only,
+// never by a later stream synchronisation: every sync point looks at it first, so that a failed launch fails the batch
+// instead of leaving initial values in the results.
+static int ax_launch_check(axctd_engine* e) { return ax_fail(e, cudaGetLastError(), "kernel launch"); }
+static int ax_sync(axctd_engine* e) {
+    if (ax_launch_check(e)) return 1;
+    return ax_fail(e, cudaStreamSynchronize(e->stream), "sync");
+}
+#define AX_DEV(e) cudaSetDevice((e)->device)          /* every ABI entry point that touches CUDA runs on its engine's device */
 #endif
 
 #ifdef AXCTD_EMU
@@ -253,6 +271,7 @@ extern "C" int axctd_engine_create(int device, axctd_engine** out) {
 
 extern "C" void axctd_engine_destroy(axctd_engine* e) {
     if (!e) return;
+    AX_DEV(e);
     for (void* p : e->cfg_allocs) ax_free(p);
     ax_free(e->d_cfg);
 #ifndef AXCTD_EMU
@@ -315,6 +334,7 @@ static int ax_cfg_upload(axctd_engine* e, const T** dst, const T* src, size_t co
 
 extern "C" int axctd_config_create(axctd_engine* e, const axctd_config_desc* ds, int* config_id) {
     if (!e || !ds || !config_id) return AXCTD_ERR_ARG;
+    AX_DEV(e);
     if ((int)e->cfgs.size() >= e->cfg_cap) { e->err = "too many configs"; return AXCTD_ERR_CAPACITY; }
     if (ds->n_sections < 1 || ds->n_sections > AX_MAXSEC || ds->bit_inset != 1 || ds->npcm < 1 ||
         ds->bit_cs_len < ds->npcm + 1 || ds->n_power < 1 || ds->d_pcm < 1 || ds->chunk_len < 1 ||
@@ -437,6 +457,7 @@ extern "C" int axctd_config_create(axctd_engine* e, const axctd_config_desc* ds,
 // ============================================================ C ABI: batch
 extern "C" void axctd_batch_destroy(axctd_batch* b) {
     if (!b) return;
+    AX_DEV(b->eng);
 #ifndef AXCTD_EMU
     cudaStreamSynchronize(b->eng->stream);
     for (int i = 0; i < 6; ++i) cudaEventDestroy(b->ev[i]);
@@ -450,6 +471,8 @@ extern "C" void axctd_batch_destroy(axctd_batch* b) {
 extern "C" int axctd_batch_create(axctd_engine* e, int n_drops, const int64_t* n_samples, const int32_t* config_id,
                                   axctd_batch** out) {
     if (!e || n_drops <= 0 || !n_samples || !config_id || !out) return AXCTD_ERR_ARG;
+    // several kernels put the drop index in gridDim.y (k_stats_tones*, k_tone_*, k_bits_chunk phase 0)
+    if (n_drops > 65535) { e->err = "at most 65535 drops per batch"; return AXCTD_ERR_ARG; }
     axctd_batch* b = new axctd_batch();
     b->eng = e; b->n = n_drops;
     memset(&b->w, 0, sizeof(AxWave));
@@ -555,6 +578,9 @@ extern "C" int axctd_batch_create(axctd_engine* e, int n_drops, const int64_t* n
     bad |= ax_alloc_arr(b, &w.seg_cnt, seg_off);
     bad |= ax_alloc_arr(b, &w.seg_off, seg_off);
     bad |= ax_alloc_arr(b, &w.blk_sum, seg_off / 128 + 1);
+    bad |= ax_alloc_arr(b, &w.seg_unc, seg_off);
+    bad |= ax_alloc_arr(b, &w.head_unc, chunk_off);
+    bad |= ax_alloc_arr(b, &w.unc_list, 2 * (int64_t)AX_UNC_CAP * n_drops);
     const int64_t rec_total = (int64_t)seg_off * w.seg_cap;
     bad |= ax_alloc_arr(b, &w.rec_idx, rec_total);
     bad |= ax_alloc_arr(b, &w.rec_a1, rec_total);
@@ -614,6 +640,7 @@ extern "C" int axctd_batch_create(axctd_engine* e, int n_drops, const int64_t* n
 
 extern "C" int axctd_batch_upload(axctd_batch* b, int drop, const int16_t* pcm, int64_t n) {
     if (!b || drop < 0 || drop >= b->n || !pcm || n != b->drops[drop].n_raw) return AXCTD_ERR_ARG;
+    AX_DEV(b->eng);
     if (ax_h2d(b->eng, b->d_pcm + b->drops[drop].pcm_off, pcm, sizeof(int16_t) * n)) return AXCTD_ERR_CUDA;
     b->ran = false;
     return AXCTD_OK;
@@ -776,8 +803,7 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
         for (size_t ci = 0; ci < e->cfgs.size(); ++ci) {
             if (!std::any_of(b->drops.begin(), b->drops.end(), [&](const AxDrop& d) { return d.cfg == (int)ci; })) continue;
             if (e->opt_tone_mma) {
-                static bool attr_set = false;
-                if (!attr_set) { cudaFuncSetAttribute(k_stats_tones_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AX_STM_SMEM); attr_set = true; }
+                ax_optin_smem<k_stats_tones_mma>(AX_STM_SMEM, e->device);
                 k_stats_tones_mma<<<dim3((unsigned)((w.ntb_max + AX_STM_GROUPS * AX_ST_THREADS - 1) / (AX_STM_GROUPS * AX_ST_THREADS)), (unsigned)n), AX_ST_THREADS, AX_STM_SMEM, e->stream>>>(w, e->cfgs[ci].tone_tab8, (int)ci);
             } else
                 k_stats_tones<<<dim3((unsigned)((w.ntb_max + AX_ST_THREADS - 1) / AX_ST_THREADS), (unsigned)n), AX_ST_THREADS, 0, e->stream>>>(w, e->tone_tabs[ci], (int)ci);
@@ -831,7 +857,7 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
     if (scan_only) {
     } else if (fused) {
         // one launch per rate class in use (CTAs of the other classes exit at once)
-        for (int ci : used_cfg) { ax_launch_demod_fused_any<false>(w, e->cfgs[ci], ci, 0, e->stream, e->opt_ws, e->opt_fir_first); e->launches++; }
+        for (int ci : used_cfg) { ax_launch_demod_fused_any<false>(w, e->cfgs[ci], ci, 0, e->stream, e->device, e->opt_ws, e->opt_fir_first); e->launches++; }
         if (any_dec) { w.only_xf = 1; AX_LAUNCH(e, k_filter, (int64_t)w.nseg_total, w); w.only_xf = 0; }
     } else
 #else
@@ -885,7 +911,7 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
             // heads of the rate classes the fused kernel is instantiated for; the generic form takes the rest
             bool rest = any_dec;
             for (int ci : used_cfg) {
-                if (ax_demod_fused_ok(e->cfgs[ci])) { ax_launch_demod_fused_any<true>(w, e->cfgs[ci], ci, b->chunk_total, e->stream, e->opt_ws, 0); e->launches++; }
+                if (ax_demod_fused_ok(e->cfgs[ci])) { ax_launch_demod_fused_any<true>(w, e->cfgs[ci], ci, b->chunk_total, e->stream, e->device, e->opt_ws, 0); e->launches++; }
                 else rest = true;
             }
             if (rest) AX_LAUNCH(e, k_headfilt, b->chunk_total, w, 1);
@@ -902,6 +928,9 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
         if (it >= e->opt_max_fixups) { e->err = "chunk chain did not converge"; return AXCTD_ERR_STATE; }
         if (ax_zero(e, w.flags, sizeof(int32_t))) return AXCTD_ERR_CUDA;
     }
+    // guard-band samples of the filter passes, now that the iterations are known (almost always none)
+    AX_LAUNCH(e, k_unc_resolve, (int64_t)n * AX_UNC_CAP, w);
+    AX_LAUNCH(e, k_unc_fin, n, w);
 #ifndef AXCTD_EMU
     if (e->opt_filter_variant == 0) { k_plan_tones_warp<<<n, 32, 0, e->stream>>>(w); e->launches++; } else
 #endif
@@ -961,6 +990,7 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
     AX_LAUNCH(e, k_rows, b->frame_total, w);
     AX_LAUNCH(e, k_chunkout, b->chunk_total, w);
     AX_EVENT(b, 5);
+    if (ax_launch_check(e)) return AXCTD_ERR_CUDA;
     b->ran = true;
     return AXCTD_OK;
 }
@@ -971,6 +1001,7 @@ extern "C" int axctd_batch_finish(axctd_batch* b) {
     axctd_engine* e = b->eng;
     AxWave& w = b->w;
     const int n = b->n;
+    AX_DEV(e);
     if (ax_d2h(e, b->h_st, w.st, sizeof(AxState) * n) || ax_sync(e)) return AXCTD_ERR_CUDA;
     memcpy(b->st.data(), b->h_st, sizeof(AxState) * n);
     for (int d = 0; d < n; ++d) {
@@ -1002,6 +1033,7 @@ extern "C" int axctd_batch_finish(axctd_batch* b) {
         sm.n_bits = st.nbits_total; sm.n_edges = st.nedges_total; sm.n_power = st.pcount;
         sm.n_frames = st.n_frames; sm.n_crossings = st.zc_count;
         sm.n_uncertain = st.n_uncertain; sm.n_chain_fixups = st.n_fixups;
+        sm.n_guard_hits = st.n_unc_listed; sm.n_guard_confirmed = st.n_unc_resolved;
         sm.pcm_sum = st.sum; sm.pcm_ampl = st.ampl;
         sm.n_recheck = st.n_recheck; memcpy(&sm.win32_max_rel_err, &st.err32_bits, sizeof(float)); sm.n_frame_respec = st.n_frame_respec;
         memcpy(sm.frame_data, st.frame_data, sizeof(sm.frame_data));
@@ -1047,6 +1079,7 @@ extern "C" int64_t axctd_batch_rows(axctd_batch* b, int drop, axctd_row* out, in
 
 extern "C" int64_t axctd_batch_frames(axctd_batch* b, int drop, axctd_frame* out, int64_t cap) {
     if (!b || !b->finished || drop < 0 || drop >= b->n) return -AXCTD_ERR_ARG;
+    AX_DEV(b->eng);
     const int64_t nf = b->st[drop].n_frames;
     if (!out) return nf;
     if (cap < nf) return -AXCTD_ERR_CAPACITY;
@@ -1066,6 +1099,7 @@ extern "C" int64_t axctd_batch_chunks(axctd_batch* b, int drop, axctd_chunk* out
 
 extern "C" int64_t axctd_batch_bits(axctd_batch* b, int drop, uint8_t* bits, double* conf, int64_t cap) {
     if (!b || !b->finished || drop < 0 || drop >= b->n) return -AXCTD_ERR_ARG;
+    AX_DEV(b->eng);
     const int64_t nb = b->st[drop].nbits_total;
     if (!bits && !conf) return nb;
     if (cap < nb) return -AXCTD_ERR_CAPACITY;
@@ -1079,6 +1113,7 @@ extern "C" int64_t axctd_batch_bits(axctd_batch* b, int drop, uint8_t* bits, dou
 
 extern "C" int64_t axctd_batch_edges(axctd_batch* b, int drop, int64_t* edges, double* r400, double* r7500, int64_t cap) {
     if (!b || !b->finished || drop < 0 || drop >= b->n) return -AXCTD_ERR_ARG;
+    AX_DEV(b->eng);
     const int64_t ne = b->st[drop].nedges_total;
     if (!edges && !r400 && !r7500) return ne;
     if (cap < ne) return -AXCTD_ERR_CAPACITY;
@@ -1108,6 +1143,7 @@ extern "C" int64_t axctd_batch_edges(axctd_batch* b, int drop, int64_t* edges, d
 
 extern "C" int64_t axctd_batch_power(axctd_batch* b, int drop, int64_t* power_inds, double* r400, double* r7500, int64_t cap) {
     if (!b || !b->finished || drop < 0 || drop >= b->n) return -AXCTD_ERR_ARG;
+    AX_DEV(b->eng);
     const int64_t np = b->st[drop].pcount;
     if (!power_inds && !r400 && !r7500) return np;
     if (cap < np) return -AXCTD_ERR_CAPACITY;
@@ -1123,6 +1159,7 @@ extern "C" int64_t axctd_batch_power(axctd_batch* b, int drop, int64_t* power_in
 extern "C" int axctd_synth_fill(axctd_batch* b, int drop, const axctd_synth_desc* ds) {
     if (!b || !ds || drop < 0 || drop >= b->n || ds->n_total != b->drops[drop].n_raw || !ds->bits || !ds->gate || !ds->parity) return AXCTD_ERR_ARG;
     axctd_engine* e = b->eng;
+    AX_DEV(e);
     AxSynth g;
     g.n_total = ds->n_total; g.n0 = ds->n0; g.tone_start = ds->tone_start; g.fs = ds->fs;
     g.key1 = ds->key1; g.key2 = ds->key2; g.nscale = ds->nscale; g.gain = ds->gain; g.tone_amp = ds->tone_amp;
@@ -1142,8 +1179,33 @@ extern "C" int axctd_synth_fill(axctd_batch* b, int drop, const axctd_synth_desc
     return AXCTD_OK;
 }
 
+extern "C" int axctd_calib_eval(axctd_engine* e, const double* cond, const double* temp, const double* pres, int n,
+                                const double* coeff4, double* sp, double* poly) {
+    if (!e || !cond || !temp || !pres || !sp || n <= 0 || (coeff4 && !poly)) return AXCTD_ERR_ARG;
+    AX_DEV(e);
+    std::vector<double> in(3 * (size_t)n + 4, 0.0), out(2 * (size_t)n);
+    memcpy(in.data(), cond, sizeof(double) * n); memcpy(in.data() + n, temp, sizeof(double) * n);
+    memcpy(in.data() + 2 * (size_t)n, pres, sizeof(double) * n);
+    if (coeff4) memcpy(in.data() + 3 * (size_t)n, coeff4, sizeof(double) * 4);
+    void *d_in = nullptr, *d_out = nullptr;
+    int bad = ax_alloc(e, &d_in, in.size() * sizeof(double)) || ax_alloc(e, &d_out, out.size() * sizeof(double));
+    const int64_t launches_before = e->launches;
+    if (!bad) {
+        bad = ax_h2d(e, d_in, in.data(), in.size() * sizeof(double));
+        if (!bad) { AX_LAUNCH(e, k_calib_eval, (int64_t)n, (const double*)d_in, (double*)d_out, coeff4 ? 1 : 0); }
+        bad = bad || ax_d2h(e, out.data(), d_out, out.size() * sizeof(double)) || ax_sync(e);
+    }
+    e->launches = launches_before;          // tooling, not part of the decode path
+    ax_free(d_in); ax_free(d_out);
+    if (bad) return AXCTD_ERR_CUDA;
+    memcpy(sp, out.data(), sizeof(double) * n);
+    if (poly) memcpy(poly, out.data() + n, sizeof(double) * n);
+    return AXCTD_OK;
+}
+
 extern "C" int axctd_batch_download(axctd_batch* b, int drop, int16_t* pcm, int64_t n) {
     if (!b || drop < 0 || drop >= b->n || !pcm || n != b->drops[drop].n_raw) return AXCTD_ERR_ARG;
+    AX_DEV(b->eng);
     if (ax_d2h(b->eng, pcm, b->d_pcm + b->drops[drop].pcm_off, sizeof(int16_t) * n) || ax_sync(b->eng)) return AXCTD_ERR_CUDA;
     return AXCTD_OK;
 }

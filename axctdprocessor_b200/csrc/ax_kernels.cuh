@@ -18,6 +18,19 @@ __device__ __forceinline__ void ax_cp_async_commit() { asm volatile("cp.async.co
 template <int N>
 __device__ __forceinline__ void ax_cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
+// Opt a kernel in to more than 48 KB of dynamic shared memory.  The attribute is per device, so it is tracked per
+// (kernel, device): an engine on a second GPU of the same process sets it again.
+#include <atomic>
+template <auto Kernel>
+static inline cudaError_t ax_optin_smem(size_t bytes, int device) {
+    static std::atomic<unsigned long long> done{0ull};
+    const unsigned long long bit = 1ull << (device & 63);
+    if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    const cudaError_t r = cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (r == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+    return r;
+}
+
 // ------------------------------------------------------------------ stats (exact |x| semantics, fallback)
 // np.max(np.abs(int16)) wraps abs(-32768) to -32768 (AXCTDprocessor.py:56).  k_stats_tones tracks min and max,
 // which decide max|x| unless a sample equals -32768; only then this kernel rescans the drop.
@@ -543,6 +556,7 @@ __global__ void __launch_bounds__(AX_FD_THREADS, 2) k_demod_fused(const __grid_c
     g.seg_start = g.seg_end = g.n_begin = g.n_stop = 0;
     int skip = 0;                                       // HEAD: samples of row 0 that lie before the chunk start
     int64_t chunk_s = 0;
+    int head_k = -1;                                    // HEAD: run() iteration of this lane
     if (!HEAD) {
         d = w.seg_drop[(int64_t)blockIdx.x * AX_FD_THREADS];
         const AxDrop& dr0 = w.drop[d];
@@ -555,6 +569,7 @@ __global__ void __launch_bounds__(AX_FD_THREADS, 2) k_demod_fused(const __grid_c
         d = ax_find_owner(w.drop, w.n_drops, &AxDrop::chunk_base, cg);
         const AxDrop& dr0 = w.drop[d];
         const int k = (int)(cg - dr0.chunk_base);
+        head_k = k;
         active = seg < n_items && k < dr0.chunk_cap && dr0.cfg == cfg_id && dr0.xf_off < 0;
         if (active) {
             const AxHeadGeom hg = ax_head_geom(w, dr0, w.st[d], w.cfg[cfg_id], w.chunk[cg], k);
@@ -714,8 +729,11 @@ __global__ void __launch_bounds__(AX_FD_THREADS, 2) k_demod_fused(const __grid_c
                     const int base = nb + 64 * t;
                     for (int i = 0; i < 64; ++i) {
                         const int n = base + i;
-                        if (n >= sstart && n < send && n < nstop &&
-                            fabsf(reinterpret_cast<const float*>(&yo[32 * (i >> 2)])[i & 3]) < guard_f) ++unc;
+                        const float yv = reinterpret_cast<const float*>(&yo[32 * (i >> 2)])[i & 3];
+                        if (n >= sstart && n < send && n < nstop && fabsf(yv) < guard_f) {
+                            ++unc;
+                            ax_unc_push(w, d, n, (__float_as_uint(yv) >> 31) != 0u, HEAD ? head_k + 1 : 0, chunk_s);
+                        }
                     }
                 }
             }
@@ -780,13 +798,13 @@ __global__ void __launch_bounds__(AX_FD_THREADS, 2) k_demod_fused(const __grid_c
     }
     if (!HEAD) {
         if (active) {
-            if (count > w.seg_cap) { w.flags[AX_FLAG_CAP] = 1; count = w.seg_cap; }
+            if (count > w.seg_cap) { w.flags[AX_FLAG_CAP] = 1; ax_raise(w.st[d], AXCTD_DROP_CAPACITY, -1); count = w.seg_cap; }   // crossings were dropped: fail the drop
             w.seg_cnt[seg] = count;
-            if (unc) atomicAdd(&st.n_uncertain, unc);
-        } else w.seg_cnt[seg] = 0;
+            w.seg_unc[seg] = unc;
+        } else { w.seg_cnt[seg] = 0; w.seg_unc[seg] = 0; }
     } else if (active) {
         w.head_cnt[seg] = count > out_cap ? -1 : count;
-        if (unc) atomicAdd(&st.n_uncertain, unc);
+        w.head_unc[seg] = unc;
     }
 }
 
@@ -852,6 +870,7 @@ __global__ void __launch_bounds__(AX_WS_THREADS, 2) k_demod_ws(const __grid_cons
     g.seg_start = g.seg_end = g.n_begin = g.n_stop = 0;
     int skip = 0;                                       // HEAD: samples of row 0 that lie before the chunk start
     int64_t chunk_s = 0;
+    int head_k = -1;
     if (!HEAD) {
         d = w.seg_drop[seg0];
         const AxDrop& dr0 = w.drop[d];
@@ -864,6 +883,7 @@ __global__ void __launch_bounds__(AX_WS_THREADS, 2) k_demod_ws(const __grid_cons
         d = ax_find_owner(w.drop, w.n_drops, &AxDrop::chunk_base, cg);
         const AxDrop& dr0 = w.drop[d];
         const int k = (int)(cg - dr0.chunk_base);
+        head_k = k;
         active = seg < n_items && k < dr0.chunk_cap && dr0.cfg == cfg_id && dr0.xf_off < 0;
         if (active) {
             const AxHeadGeom hg = ax_head_geom(w, dr0, w.st[d], w.cfg[cfg_id], w.chunk[cg], k);
@@ -967,8 +987,11 @@ __global__ void __launch_bounds__(AX_WS_THREADS, 2) k_demod_ws(const __grid_cons
                     const int base = nb + AX_WS_RS * t;
                     for (int i = 0; i < AX_WS_RS; ++i) {
                         const int n = base + i;
-                        if (n >= sstart && n < send && n < nstop &&
-                            fabsf(reinterpret_cast<const float*>(&yo[32 * (i >> 2)])[i & 3]) < guard_f) ++unc;
+                        const float yv = reinterpret_cast<const float*>(&yo[32 * (i >> 2)])[i & 3];
+                        if (n >= sstart && n < send && n < nstop && fabsf(yv) < guard_f) {
+                            ++unc;
+                            ax_unc_push(w, d, n, (__float_as_uint(yv) >> 31) != 0u, HEAD ? head_k + 1 : 0, chunk_s);
+                        }
                     }
                 }
             }
@@ -976,7 +999,8 @@ __global__ void __launch_bounds__(AX_WS_THREADS, 2) k_demod_ws(const __grid_cons
             ax_mbar_arrive(&sm.full[t & (AX_WS_SLOTS - 1)]);
             __syncwarp();                                // the stage buffer t & 1 is rewritten by issue(t + 2)
         }
-        if (active && unc) atomicAdd(&st.n_uncertain, unc);
+        if (!HEAD) w.seg_unc[seg] = active ? unc : 0;
+        else if (active) w.head_unc[seg] = unc;
         return;
     }
     // ---------------------------------------------------------------- window warp
@@ -1040,7 +1064,7 @@ __global__ void __launch_bounds__(AX_WS_THREADS, 2) k_demod_ws(const __grid_cons
     }
     if (!HEAD) {
         if (active) {
-            if (count > w.seg_cap) { w.flags[AX_FLAG_CAP] = 1; count = w.seg_cap; }
+            if (count > w.seg_cap) { w.flags[AX_FLAG_CAP] = 1; ax_raise(w.st[d], AXCTD_DROP_CAPACITY, -1); count = w.seg_cap; }   // crossings were dropped: fail the drop
             w.seg_cnt[seg] = count;
         } else w.seg_cnt[seg] = 0;
     } else if (active) {
@@ -1049,10 +1073,9 @@ __global__ void __launch_bounds__(AX_WS_THREADS, 2) k_demod_ws(const __grid_cons
 }
 
 template <int NSEC, int NPCM, bool HEAD>
-static inline void ax_launch_demod_ws(const AxWave& w, const AxCfg& c, int cfg_id, int64_t n_items, cudaStream_t stream) {
+static inline void ax_launch_demod_ws(const AxWave& w, const AxCfg& c, int cfg_id, int64_t n_items, cudaStream_t stream, int device) {
     const size_t smem = sizeof(AxWsSmem);
-    static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(k_demod_ws<NSEC, NPCM, HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+    ax_optin_smem<k_demod_ws<NSEC, NPCM, HEAD>>(smem, device);
     const int64_t items = HEAD ? n_items : (int64_t)w.nseg_total;
     if (items <= 0) return;
     const int per = AX_WS_PAIRS * 32;
@@ -1060,10 +1083,9 @@ static inline void ax_launch_demod_ws(const AxWave& w, const AxCfg& c, int cfg_i
 }
 
 template <int NSEC, int NPCM, bool HEAD, bool FAST = false>
-static inline void ax_launch_demod_fused(const AxWave& w, const AxCfg& c, int cfg_id, int64_t n_items, cudaStream_t stream) {
+static inline void ax_launch_demod_fused(const AxWave& w, const AxCfg& c, int cfg_id, int64_t n_items, cudaStream_t stream, int device) {
     const size_t smem = sizeof(AxFdSmem);
-    static bool attr_set = false;
-    if (!attr_set) { cudaFuncSetAttribute(k_demod_fused<NSEC, NPCM, HEAD, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+    ax_optin_smem<k_demod_fused<NSEC, NPCM, HEAD, FAST>>(smem, device);
     const int64_t items = HEAD ? n_items : (int64_t)w.nseg_total;
     if (items <= 0) return;
     k_demod_fused<NSEC, NPCM, HEAD, FAST><<<(unsigned)((items + AX_FD_THREADS - 1) / AX_FD_THREADS), AX_FD_THREADS, smem, stream>>>(w, c.win_tab, cfg_id, items);
@@ -1074,24 +1096,24 @@ static inline bool ax_demod_fused_ok(const AxCfg& c) {
     return ax_sos_is_butter(c) && (c.nsec == 3 || c.nsec == 6) && (c.npcm == 39 || c.npcm == 43) && c.inset == 1;
 }
 template <bool HEAD>
-static inline void ax_launch_demod_fused_any(const AxWave& w, const AxCfg& c, int cfg_id, int64_t n_items, cudaStream_t stream, int ws, int fast) {
+static inline void ax_launch_demod_fused_any(const AxWave& w, const AxCfg& c, int cfg_id, int64_t n_items, cudaStream_t stream, int device, int ws, int fast) {
     // numerators-first cascade: continuous pass of the low-pass (every section with numerator g (1 + z^-1)^2) only
     if (!HEAD && !ws && fast && c.nsec == 3 && c.sos[0][1] > 0.0 && c.sos[1][1] > 0.0 && c.sos[2][1] > 0.0) {
-        if (c.npcm == 39) ax_launch_demod_fused<3, 39, false, true>(w, c, cfg_id, n_items, stream);
-        else ax_launch_demod_fused<3, 43, false, true>(w, c, cfg_id, n_items, stream);
+        if (c.npcm == 39) ax_launch_demod_fused<3, 39, false, true>(w, c, cfg_id, n_items, stream, device);
+        else ax_launch_demod_fused<3, 43, false, true>(w, c, cfg_id, n_items, stream, device);
         return;
     }
     if (ws) {
-        if (c.nsec == 3 && c.npcm == 39) ax_launch_demod_ws<3, 39, HEAD>(w, c, cfg_id, n_items, stream);
-        else if (c.nsec == 3 && c.npcm == 43) ax_launch_demod_ws<3, 43, HEAD>(w, c, cfg_id, n_items, stream);
-        else if (c.nsec == 6 && c.npcm == 39) ax_launch_demod_ws<6, 39, HEAD>(w, c, cfg_id, n_items, stream);
-        else ax_launch_demod_ws<6, 43, HEAD>(w, c, cfg_id, n_items, stream);
+        if (c.nsec == 3 && c.npcm == 39) ax_launch_demod_ws<3, 39, HEAD>(w, c, cfg_id, n_items, stream, device);
+        else if (c.nsec == 3 && c.npcm == 43) ax_launch_demod_ws<3, 43, HEAD>(w, c, cfg_id, n_items, stream, device);
+        else if (c.nsec == 6 && c.npcm == 39) ax_launch_demod_ws<6, 39, HEAD>(w, c, cfg_id, n_items, stream, device);
+        else ax_launch_demod_ws<6, 43, HEAD>(w, c, cfg_id, n_items, stream, device);
         return;
     }
-    if (c.nsec == 3 && c.npcm == 39) ax_launch_demod_fused<3, 39, HEAD>(w, c, cfg_id, n_items, stream);
-    else if (c.nsec == 3 && c.npcm == 43) ax_launch_demod_fused<3, 43, HEAD>(w, c, cfg_id, n_items, stream);
-    else if (c.nsec == 6 && c.npcm == 39) ax_launch_demod_fused<6, 39, HEAD>(w, c, cfg_id, n_items, stream);
-    else ax_launch_demod_fused<6, 43, HEAD>(w, c, cfg_id, n_items, stream);
+    if (c.nsec == 3 && c.npcm == 39) ax_launch_demod_fused<3, 39, HEAD>(w, c, cfg_id, n_items, stream, device);
+    else if (c.nsec == 3 && c.npcm == 43) ax_launch_demod_fused<3, 43, HEAD>(w, c, cfg_id, n_items, stream, device);
+    else if (c.nsec == 6 && c.npcm == 39) ax_launch_demod_fused<6, 39, HEAD>(w, c, cfg_id, n_items, stream, device);
+    else ax_launch_demod_fused<6, 43, HEAD>(w, c, cfg_id, n_items, stream, device);
 }
 
 // ------------------------------------------------------------------ bit decisions with shared window sums

@@ -346,12 +346,13 @@ AX_HDN inline void ax_sm_item(const AxWave& w, int64_t d, int phase_b) {
         }
         q.mean7500 = st.mean7500;
         q.status = st.sm_status;
+        q.profstart = st.profstartind;
         st.next_sm_chunk = k + 1;
         if (!phase_b && st.sm_status >= 1) break;      // hand over to the chunk chain
         if (phase_b && !do_smooth && st.sm_status == 2 && !isnan(st.mean7500) && !(c.trig_to > 0)) {
             // nothing can change any more (status 2 is final unless the timeout branch of :404 is armed):
             // the remaining iterations only record the state
-            for (int k2 = k + 1; k2 < kend; ++k2) { ch[k2].mean7500 = st.mean7500; ch[k2].status = 2; }
+            for (int k2 = k + 1; k2 < kend; ++k2) { ch[k2].mean7500 = st.mean7500; ch[k2].status = 2; ch[k2].profstart = st.profstartind; }
             st.pcount = ch[kend - 1].pw_off + ch[kend - 1].np;
             st.next_sm_chunk = kend;
             break;

@@ -158,8 +158,8 @@ AX_HD int ax_frames_scan(const AxWave& w, const AxDrop& dr, const AxState& st, c
     const uint32_t* vw = w.validw + dr.edge_base / 32;
     const int64_t NI = ch.edge_off + ch.n_edges, NB = ch.bit_off + ch.n_edges - 1;
     int32_t nf = 0;
-    if (cur < NI && (int64_t)I[cur] <= st.profstartind) {              // AXCTDprocessor.py:545-551
-        const int64_t f = ax_first_gt(I, cur, NI, st.profstartind);
+    if (cur < NI && (int64_t)I[cur] <= ch.profstart) {                 // AXCTDprocessor.py:545-551 (profstartind of THIS iteration)
+        const int64_t f = ax_first_gt(I, cur, NI, ch.profstart);
         if (f < 0) return AXCTD_DROP_TRIM_INDEX;
         cur = f;
     }
@@ -333,7 +333,7 @@ AX_HDN inline void ax_calib_item(const AxWave& w, int64_t fg) {
         const int64_t ei = w.edge_idx[dr.edge_base + p];
         f.word = ax_frame_word(w.bitw + dr.edge_base / 32, p);
         f.edge_index = ei;
-        f.time_raw = ax_div((double)(ei - st.profstartind), c.fs);     // AXCTDprocessor.py:554
+        f.time_raw = ax_div((double)(ei - w.chunk[dr.chunk_base + f.chunk].profstart), c.fs);     // AXCTDprocessor.py:554
         f.r400_raw = ax_lvl400(w, dr, p); f.r7500_raw = ax_lvl7500(w, dr, p);
         f.hex_returned = 0;
     }
@@ -450,6 +450,6 @@ AX_HDN inline void ax_chunkout_item(const AxWave& w, int64_t cg) {
     o.n_bits = dem ? c.n_edges - 1 : -1;
     o.first_edge = dem ? (int32_t)(c.first_edge - c.s) : -1; o.last_edge = dem ? (int32_t)(c.true_last - c.s) : -1;
     o.n_head_edges = dem ? c.n_head_edges : 0;
-    o.n_rows = c.n_rows; o.n_hex = c.n_hex; o.scale = c.scale;
+    o.n_rows = c.n_rows; o.n_hex = c.n_hex; o.scale = c.scale; o.profstartind = c.profstart;
     w.chunk_out[cg] = o;
 }

@@ -57,6 +57,7 @@ AX_HD double ax_nan() { return nan(""); }
 #define AX_STAT_SLAB 16384  // samples per stats work item
 #define AX_TB 256           // samples per tone block (ax_toneblock_item)
 #define AX_TONE_ROT 24      // most tone blocks a window can span
+#define AX_UNC_CAP 256      // guard-band samples listed per drop (ax_unc_push); more are only counted
 
 // fp32 phasor table of the bit windows (ax_window32): cos, sin of theta_mark * k and theta_space * k
 #define AX_WIN_TAPS 48
@@ -135,6 +136,8 @@ struct AxChunk {
     int32_t frame_begin, frame_end;   // frames parsed in this iteration
     double scale;
     double mean7500;             // mean7500pwr in force when the chunk was demodulated (NaN before)
+    int64_t profstart;           // self.profstartind after this iteration's detectors (the timeout branch of
+                                 // AXCTDprocessor.py:404-408 can move it after status 2 was reached)
 };
 
 // Sequential per-drop state (the attributes of reference class AXCTD_Processor).
@@ -143,7 +146,10 @@ struct AxState {
     int64_t sum;
     int32_t vmax, vmin;          // max / min sample (k_stats_tones); vmin stays INT_MAX on the generic path
     int32_t ampl;
-    int32_t n_uncertain;
+    int32_t n_uncertain;         // guard-band samples whose sign could not be confirmed (ax_unc_resolve_item / ax_unc_fin_item)
+    int32_t n_unc_listed;        // guard-band samples seen by the filter passes (the first AX_UNC_CAP are listed)
+    int32_t n_unc_relevant;      // listed ones that lie where a demodulated iteration takes crossings
+    int32_t n_unc_resolved;      //   ... and whose sign the exact zero-state recomputation confirmed
     int32_t n_recheck;           // bit windows re-evaluated in double precision (ax_gwin_*)
     int32_t err32_bits;          // max relative |a32 - a64| / a64 seen at re-evaluated windows (float bits)
     double dc, inv_ampl, ampl_d;
@@ -193,6 +199,8 @@ struct AxWave {
     const int32_t* seg_drop;     // segment -> drop
     const int32_t* slab_drop;    // stats slab -> drop
     int32_t* seg_cnt; int64_t* seg_off; int64_t* blk_sum;  // per segment / per block of 128 segments
+    int32_t* seg_unc; int32_t* head_unc;                    // guard-band samples per segment / per chunk head
+    int64_t* unc_list;                                      // [n_drops][AX_UNC_CAP][2]: sample | neg << 32 | (chunk + 1) << 33, chunk start
     int32_t* rec_idx; float* rec_a1; float* rec_a2;         // [nseg_total * seg_cap]
     int32_t* zc_idx; float* zc_a1; float* zc_a2;            // dense, per drop at zc_base
     uint8_t* zc_nx;                                         // per crossing: walk step

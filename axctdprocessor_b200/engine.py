@@ -259,6 +259,22 @@ class Engine:
         self._configs[key] = rc
         return rc
 
+    def calib_eval(self, cond, temp, pres, coeff=None):
+        """Known-answer hook: the device's SP_from_C (parse.py:132) and, with ``coeff``, dataconvert(cond, coeff)
+        (parse.py:297-301) for arrays of points.  Returns (sp, poly or None)."""
+        c = np.ascontiguousarray(cond, dtype=np.float64).reshape(-1)
+        t = np.ascontiguousarray(np.broadcast_to(np.asarray(temp, dtype=np.float64), c.shape))
+        p = np.ascontiguousarray(np.broadcast_to(np.asarray(pres, dtype=np.float64), c.shape))
+        sp = np.empty_like(c)
+        poly = np.empty_like(c) if coeff is not None else None
+        cf = np.ascontiguousarray(coeff, dtype=np.float64) if coeff is not None else None
+        rc = self.lib.axctd_calib_eval(self.h, c.ctypes.data, t.ctypes.data, p.ctypes.data, len(c),
+                                       cf.ctypes.data if cf is not None else None, sp.ctypes.data,
+                                       poly.ctypes.data if poly is not None else None)
+        if rc != 0:
+            raise RuntimeError(f"axctd_calib_eval failed ({rc}): {self.error()}")
+        return sp, poly
+
     def batch(self, n_samples, configs) -> "Batch":
         return Batch(self, n_samples, configs)
 

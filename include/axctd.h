@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define AXCTD_ABI_VERSION 1
+#define AXCTD_ABI_VERSION 2
 #define AXCTD_MAX_SECTIONS 6
 
 /* ---- return codes of API calls ---------------------------------------- */
@@ -113,8 +113,10 @@ typedef struct axctd_drop_summary {
     int64_t n_rows;             /* rows surviving QC + spike filter */
     int64_t n_hex;              /* hexframes returned to the caller (:612 quirk) */
     int64_t n_crossings;        /* zero crossings of the continuous filter pass */
-    int32_t n_uncertain;        /* guard-band hits */
+    int32_t n_uncertain;        /* filter outputs inside the guard band whose sign the exact recomputation did not confirm */
     int32_t n_chain_fixups;     /* mis-speculated chunks repaired */
+    int32_t n_guard_hits;       /* filter outputs inside the guard band seen by the fast passes (anywhere in the recording) */
+    int32_t n_guard_confirmed;  /* those inside demodulated iterations whose sign scipy-order arithmetic confirmed */
     int64_t pcm_sum;            /* integer sum and max|x| of the int16 input (:55-56) */
     int32_t pcm_ampl;
     int32_t n_recheck;          /* fp32 bit windows re-evaluated in double precision (decision within tolerance) */
@@ -169,6 +171,7 @@ typedef struct axctd_chunk {
     int32_t n_head_edges;       /* edges taken from the exact zero-state recomputation */
     int32_t n_rows, n_hex;
     double  scale;              /* high_bit_scale used                :411 */
+    int64_t profstartind;       /* self.profstartind after the iteration (:401, :405), -1 before the trigger */
 } axctd_chunk;
 
 typedef struct axctd_engine axctd_engine;
@@ -246,6 +249,11 @@ typedef struct axctd_synth_desc {
 int  axctd_synth_fill(axctd_batch* b, int drop, const axctd_synth_desc* desc);
 /* Copy one drop's PCM device->host (to hand device-generated audio to the CPU baseline). */
 int  axctd_batch_download(axctd_batch* b, int drop, int16_t* pcm, int64_t n);
+/* Evaluate the device's practical-salinity routine (gsw.SP_from_C as called at parse.py:132) and the cubic
+ * conversion (parse.dataconvert, parse.py:297-301) for n caller-supplied points: sp[i] = SP_from_C(cond[i],
+ * temp[i], pres[i]); poly[i] = dataconvert(cond[i], coeff) when coeff != NULL.  Known-answer tests only. */
+int  axctd_calib_eval(axctd_engine* e, const double* cond, const double* temp, const double* pres, int n,
+                      const double* coeff4, double* sp, double* poly);
 
 #ifdef __cplusplus
 }

@@ -376,6 +376,7 @@ class OracleProcessor:
         self.trace = []
         self.all_bits = []; self.all_edges = []; self.all_conf = []
         self.all_frames = []       # (global edge index, hex, Cint, Tint) of every CRC-valid profile frame
+        self.all_raw = []          # (time, z, T, C, S, r400, r7500) of the same frames BEFORE rounding (parse.py:92)
         self.chunk_starts = []
 
     # -- main loop, AXCTDprocessor.py:267-338
@@ -473,7 +474,7 @@ class OracleProcessor:
         if self.status == 2:
             data = self._profile()
         rec.update(n_power=len(self.power_inds), nrows=(len(data[1]) if len(data) > 1 else 0),
-                   nhex=(len(data[8]) if len(data) > 1 else 0), status=self.status)
+                   nhex=(len(data[8]) if len(data) > 1 else 0), status=self.status, profstart=int(self.profstartind))
         self.trace.append(rec)
         return data
 
@@ -577,6 +578,8 @@ class OracleProcessor:
             if self.keep_trace:
                 for k in range(len(pos)):
                     self.all_frames.append((int(inds[pos[k]]), hexframes[k], int(cint[k]), int(tint[k])))
+                    self.all_raw.append((float(times[k]), float(z[k]), float(T[k]), float(C[k]), float(S[k]),
+                                         float(r400[k]), float(r7500[k])))
         else:
             times = z = T = C = S = r400 = r7500 = np.zeros(0)
         # :560-566

@@ -42,8 +42,24 @@ CASES = {
     "g44_chunk4": (dict(fs=44100, duration_s=60.0, seed=7, snr_db=15.0), {"refreshrate": 4.0}, None, True),
     "g96_decim":  (dict(fs=96000, duration_s=56.0, seed=8, snr_db=30.0), {}, None, True),
     "g44_nopulse": (dict(fs=44100, duration_s=12.0, seed=9, snr_db=30.0, lead_in_s=30.0), {}, None, True),
+    # chunk sizes at both ends of BASELINE config 5's sweep (-l 0.5 .. 8 x fs), wired through 'refreshrate'
+    "g44_chunk05": (dict(fs=44100, duration_s=60.0, seed=10, snr_db=20.0), {"refreshrate": 0.5}, None, True),
+    "g48_chunk8": (dict(fs=48000, duration_s=76.0, seed=11, snr_db=15.0), {"refreshrate": 8.0}, None, True),
+    # custom mark / space (-m / -n): detuned bins on a nominal signal, and a probe that transmits 420 / 780 Hz
+    "g44_marksp": (dict(fs=44100, duration_s=60.0, seed=12, snr_db=25.0),
+                   {"mark_space_freqs": [410.0, 790.0], "deadfreq": 2800.0}, None, True),
+    "g48_marksp_tx": (dict(fs=48000, duration_s=60.0, seed=13, snr_db=30.0, mark_hz=420, space_hz=780),
+                      {"mark_space_freqs": [420.0, 780.0]}, None, True),
+    # latest trigger time (-b): the elif of AXCTDprocessor.py:404-408 only runs once status is already 2 (or while
+    # mean7500pwr is NaN); it then overwrites profstartind while firstpointtime keeps the old value
+    "g44_timeout": (dict(fs=44100, duration_s=64.0, seed=14, snr_db=25.0), {}, [30, 41], True),
+    "g44_timeout_notone": (dict(fs=44100, duration_s=60.0, seed=15, snr_db=25.0, tone_amp=0.0), {}, [30, 36], True),
     "config1_720s": (dict(fs=44100, duration_s=720.0, seed=1, snr_db=40.0), {}, None, False),
     "config2_720s": (dict(fs=44100, duration_s=720.0, seed=1, snr_db=10.0), {}, None, False),
+    # BASELINE config 5 stand-in: a 30-minute recording at 8 dB SNR decoded with a swept parameter point
+    # (chunk 4 x fs, dead frequency 2500 Hz, detuned mark / space)
+    "config5_1800s": (dict(fs=44100, duration_s=1800.0, seed=5, snr_db=8.0),
+                      {"refreshrate": 4.0, "deadfreq": 2500.0, "mark_space_freqs": [405.0, 795.0]}, None, False),
 }
 
 
@@ -97,7 +113,10 @@ def make_case(name: str) -> None:
         arrays["edges_first"] = edges[:1].astype(np.int64)
         arrays["edges_delta"] = np.diff(edges).astype(np.int32)
         arrays["trace"] = np.array([[r.get(k, -1) for k in ("s", "e", "status", "n_power", "nbits", "first_edge",
-                                                            "last_edge", "nrows", "nhex")] for r in trace], dtype=np.int64)
+                                                            "last_edge", "nrows", "nhex", "profstart")] for r in trace], dtype=np.int64)
+        # every CRC-valid profile frame BEFORE rounding and QC (parse.py:92): the 1e-6 bar is held on these
+        for k, v in ap._raw.items():
+            arrays["raw_" + k] = v
         arrays["trace_scale"] = np.array([r.get("scale") or 0.0 for r in trace], dtype=np.float64)
         for k in ("time", "depth", "temperature", "conductivity", "salinity", "r400_prof", "r7500_prof"):
             arrays[k] = np.asarray(getattr(ap, k), dtype=np.float64)

@@ -121,15 +121,25 @@ def run_processor(wav, user_settings=None, triggerrange=None, capture=True, quie
                 data = orig_iter(e)
                 rec = dict(s=s, e=int(e), status=int(ap.status), n_power=len(ap.power_inds),
                            nrows=(len(data[1]) if len(data) > 1 else 0),
-                           nhex=(len(data[8]) if len(data) > 1 else 0))
+                           nhex=(len(data[8]) if len(data) > 1 else 0), profstart=int(ap.profstartind))
                 rec.update(state.get("demod", {}))
                 trace.append(rec)
                 return data
 
             dm.demodulate_axctd = demod_wrap
             ap.iterate_AXCTD_process = iter_wrap
-        # keep every demodulated bit / edge for golden capture
+        # keep every demodulated bit / edge for golden capture, and the UNROUNDED per-frame values
+        # parse.parse_bitstream_to_profile returns (parse.py:92) before AXCTDprocessor.py:559-566 rounds them
         allbits, alledges, allconf = [], [], []
+        raw = {k: [] for k in ("time", "depth", "temperature", "conductivity", "salinity", "r400", "r7500")}
+        orig_parse = ps.parse_bitstream_to_profile
+        if capture:
+            def parse_keep(*a, **k):
+                out = orig_parse(*a, **k)
+                for key, vals in zip(("time", "depth", "temperature", "conductivity", "salinity", "r400", "r7500"), out[1:8]):
+                    raw[key].extend(float(v) for v in vals)
+                return out
+            ps.parse_bitstream_to_profile = parse_keep
         if capture:
             inner = dm.demodulate_axctd
 
@@ -150,6 +160,8 @@ def run_processor(wav, user_settings=None, triggerrange=None, capture=True, quie
         finally:
             if capture:
                 dm.demodulate_axctd = orig_demod
+                ps.parse_bitstream_to_profile = orig_parse
+    ap._raw = {k: np.array(v, dtype=np.float64) for k, v in raw.items()}
     ap._all_bits = np.array(allbits, dtype=np.uint8)
     ap._all_edges = np.array(alledges, dtype=np.int64)
     ap._all_conf = np.array(allconf, dtype=np.float64)

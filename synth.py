@@ -116,6 +116,8 @@ class DropSpec:
     probe_code: int = 0xA000
     spike_every: int = 997       # every n-th data frame carries a temperature spike
     channels: int = 1
+    mark_hz: int = 400           # tone of a 1 bit / of a 0 bit (integers); the defaults keep the PCM of every
+    space_hz: int = 800          #   existing fixture bit-identical, other pairs take the general phase formula
 
 
 @dataclass
@@ -237,6 +239,7 @@ def generate_drop(spec: DropSpec, return_truth: bool = False, block: int = 1 << 
     n_total, truth = build_bitplan(spec)
     par = np.zeros(len(truth.bits) + 1, dtype=np.int64)
     np.cumsum(truth.bits, out=par[1:])
+    ones = par.copy()
     par &= 1
     nscale = noise_sigma(spec) / _IH8_SIGMA
     g = gain(spec)
@@ -260,9 +263,15 @@ def generate_drop(spec: DropSpec, return_truth: bool = False, block: int = 1 << 
         b = numer // fs
         rem = numer - b * fs
         bit = truth.bits[b].astype(np.int64)
-        q = par[b] * fs + np.where(bit == 1, 1, 2) * rem
-        q = q % (2 * fs)
-        fsk = sin_turns(q, 2 * fs)
+        if (spec.mark_hz, spec.space_hz) == (400, 800):
+            q = par[b] * fs + np.where(bit == 1, 1, 2) * rem
+            q = q % (2 * fs)
+            fsk = sin_turns(q, 2 * fs)
+        else:
+            # phase in turns = [(ones before the slot * mark + zeros before it * space) * fs + f * rem] / (BITRATE * fs)
+            done = (ones[b] * spec.mark_hz + (b - ones[b]) * spec.space_hz) % BITRATE
+            q = (done * fs + np.where(bit == 1, spec.mark_hz, spec.space_hz) * rem) % (BITRATE * fs)
+            fsk = sin_turns(q, BITRATE * fs)
         x = x + np.where(on & (truth.gate[b] == 1), fsk, 0.0)
         # profile tone
         relt = n - truth.tone_start_sample

@@ -9,9 +9,10 @@ import synth
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 SMALL_CASES = ["g44_40db", "g44_10db", "g48_25db", "g44_stereo", "g44_bandpass", "g44_wired",
-               "g44_chunk4", "g44_nopulse"]
+               "g44_chunk4", "g44_nopulse", "g44_chunk05", "g48_chunk8", "g44_marksp", "g48_marksp_tx",
+               "g44_timeout", "g44_timeout_notone"]
 DECIM_CASES = ["g96_decim"]
-FULL_CASES = ["config1_720s", "config2_720s"]
+FULL_CASES = ["config1_720s", "config2_720s", "config5_1800s"]
 
 _pcm_cache = {}
 
@@ -50,5 +51,5 @@ class Golden:
         return ["%08x" % v for v in self.z["hexframes"]]
 
     def trace(self):
-        keys = ("s", "e", "status", "n_power", "nbits", "first_edge", "last_edge", "nrows", "nhex")
+        keys = ("s", "e", "status", "n_power", "nbits", "first_edge", "last_edge", "nrows", "nhex", "profstart")
         return [dict(zip(keys, row.tolist())) for row in self.z["trace"]]

@@ -33,6 +33,22 @@ def frames_view(res):
     return kept, hexr
 
 
+RAW_RTOL = 1e-6          # north_star: calibrated T / C / S / depth within 1e-6 relative, on the UNROUNDED values
+
+
+def check_raw(fr, raw):
+    """Every CRC-valid profile frame before rounding and QC (parse.py:92 / axctd_frame.*_raw): time, depth,
+    temperature, conductivity and salinity at 1e-6 relative, signal levels at 1e-4 relative (north_star)."""
+    if not raw:
+        return
+    assert len(fr) == len(raw["time"]), (len(fr), len(raw["time"]))
+    for key, name in (("time_raw", "time"), ("depth_raw", "depth"), ("temperature_raw", "temperature"),
+                      ("conductivity_raw", "conductivity"), ("salinity_raw", "salinity")):
+        np.testing.assert_allclose(fr[key], raw[name], rtol=RAW_RTOL, atol=0, equal_nan=True, err_msg=key)
+    for key, name in (("r400_raw", "r400"), ("r7500_raw", "r7500")):
+        np.testing.assert_allclose(fr[key], raw[name], rtol=1e-4, atol=1e-9, equal_nan=True, err_msg=key)
+
+
 def check_against_golden(out, g, level_rtol=1e-9):
     """Discrete outputs exact; calibrated values 1e-6 relative (north_star)."""
     res, m = out["result"], g.meta
@@ -52,8 +68,11 @@ def check_against_golden(out, g, level_rtol=1e-9):
         got = (c["s"], c["e"], c["status"], c["n_power_total"], c["n_bits"], c["first_edge"], c["last_edge"], c["n_rows"], c["n_hex"])
         exp = (t["s"], t["e"], t["status"], t["n_power"], t["nbits"], t["first_edge"], t["last_edge"], t["nrows"], t["nhex"])
         assert got == exp, (k, got, exp)
+        if "profstart" in t:
+            assert c["profstartind"] == t["profstart"], (k, c["profstartind"], t["profstart"])
     kept, hexr = frames_view(res)
     assert hexr == g.hexframes, "hex frames"
+    check_raw(res.frames, {k[4:]: g.z[k] for k in g.z.files if k.startswith("raw_")})
     for key, gk in (("time_s", "time"), ("depth", "depth"), ("temperature", "temperature"),
                     ("conductivity", "conductivity"), ("salinity", "salinity")):
         assert len(kept[key]) == len(g.z[gk]), gk
@@ -99,8 +118,34 @@ def check_against_oracle(out, op):
         assert (c["s"], c["e"], c["status"], c["n_rows"], c["n_hex"]) == (t["s"], t["e"], t["status"], t["nrows"], t["nhex"])
     kept, hexr = frames_view(res)
     assert hexr == op.hexframes
+    if getattr(op, "all_raw", None) is not None and len(op.all_raw) == len(res.frames):
+        a = np.asarray(op.all_raw, dtype=np.float64).reshape(-1, 7)
+        check_raw(res.frames, dict(time=a[:, 0], depth=a[:, 1], temperature=a[:, 2], conductivity=a[:, 3],
+                                   salinity=a[:, 4], r400=a[:, 5], r7500=a[:, 6]))
+    else:
+        assert len(res.frames) == 0 or not op.keep_trace
     for key, name in (("time_s", "time"), ("depth", "depth"), ("temperature", "temperature"),
                       ("conductivity", "conductivity"), ("salinity", "salinity")):
         np.testing.assert_allclose(kept[key], np.asarray(getattr(op, name), dtype=np.float64), rtol=1e-6, atol=0, equal_nan=True)
     for key, name in (("r400", "r400_prof"), ("r7500", "r7500_prof")):
         np.testing.assert_allclose(kept[key], np.asarray(getattr(op, name), dtype=np.float64), rtol=1e-4, atol=0, equal_nan=True)
+
+
+def check_rows_against_oracle(res, op):
+    """What the reference's API exposes per drop (compact rows + summary, no full frame records): exact hex words,
+    row selection, detector indices and scale; rounded values equal to the oracle's."""
+    s = res.summary
+    assert s.status == 0, (s.status, s.status_chunk)
+    assert s.firstpulse400 == op.firstpulse400 and s.profstartind == op.profstartind
+    assert abs(s.high_bit_scale - op.high_bit_scale) <= 1e-12 * op.high_bit_scale
+    assert s.n_bits == len(op.all_bits) and s.n_edges == len(op.all_edges)
+    tab = res.table()
+    assert ["%08x" % int(w) for w in tab["word"][tab["hex_returned"] == 1]] == op.hexframes
+    kept = tab[tab["keep"] == 1]
+    for key, name in (("time_s", "time"), ("depth", "depth"), ("temperature", "temperature"),
+                      ("conductivity", "conductivity"), ("salinity", "salinity")):
+        assert len(kept) == len(getattr(op, name))
+        np.testing.assert_allclose(kept[key], np.asarray(getattr(op, name), dtype=np.float64), rtol=1e-6, atol=0, equal_nan=True)
+    assert len(res.chunks) == len(op.trace)
+    for c, t in zip(res.chunks, op.trace):
+        assert (c["s"], c["e"], c["status"], c["n_rows"], c["n_hex"]) == (t["s"], t["e"], t["status"], t["nrows"], t["nhex"])

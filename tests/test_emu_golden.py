@@ -306,3 +306,38 @@ def test_values_outside_the_compact_row_range_fall_back_to_full_records(eng):
     assert kept["depth"].max() > 2.2e7
     with pytest.raises(RuntimeError):
         lean.table()
+
+
+def test_calibration_known_answers_on_the_kernel_bodies(eng):
+    """ax_sp_from_c / ax_dataconvert (the bodies k_calib runs) against the GSW documentation's check values for
+    gsw_SP_from_C and against parse.dataconvert's summation order."""
+    from test_oracle_units import GSW_C, GSW_P, GSW_SP, GSW_T
+    from oracle import axctd_oracle as ao
+    cf = [-0.0622192, 1.04584, 3.0e-5, -2.0e-7]
+    sp, poly = eng.calib_eval(GSW_C, GSW_T, GSW_P, coeff=cf)
+    np.testing.assert_allclose(sp, GSW_SP, rtol=1e-13, atol=0)
+    np.testing.assert_array_equal(poly, [ao.dataconvert(c, cf) for c in GSW_C])
+
+
+def test_guard_band_samples_are_settled_by_exact_recomputation():
+    """Filter outputs inside the guard band no longer fail the drop: those inside demodulated iterations are
+    re-signed with scipy-order arithmetic from the iteration start (ax_unc_resolve_item) and only a disagreement
+    (or more hits than can be enumerated) raises AXCTD_DROP_UNCERTAIN; hits in the lead-in are ignored.  The
+    guard is widened here so that the path runs at all (the product's 1e-12 is hit about once per 500 drops)."""
+    g = Golden("g44_10db")
+    e = emu_engine(guard=3e-6)
+    out = run_engine(e, g.pcm(), g.spec.fs)
+    s = out["result"].summary
+    assert s.status == 0 and s.n_uncertain == 0
+    assert s.n_guard_hits > 20 and 0 < s.n_guard_confirmed <= s.n_guard_hits
+    check_against_golden(out, g)
+    e.close()
+    e = emu_engine(guard=1e-3)                      # far more hits than the list holds: cannot be enumerated
+    out = run_engine(e, g.pcm(), g.spec.fs)
+    assert out["result"].summary.status == 33 and out["result"].summary.n_guard_hits > 256
+    e.close()
+    q = Golden("g44_nopulse")                       # no pulse, nothing demodulated: guard hits cannot matter
+    e = emu_engine(guard=1e-3)
+    out = run_engine(e, q.pcm(), q.spec.fs)
+    assert out["result"].summary.status == 0 and out["result"].summary.n_guard_hits > 0
+    e.close()

@@ -11,7 +11,7 @@ import pytest
 
 import synth
 from golden_util import DECIM_CASES, FULL_CASES, SMALL_CASES, Golden
-from parity_util import check_against_golden, check_against_oracle, frames_view, mono, run_engine
+from parity_util import check_against_golden, check_against_oracle, check_rows_against_oracle, frames_view, mono, run_engine
 
 pytestmark = pytest.mark.gpu
 
@@ -41,9 +41,10 @@ def test_matches_reference_small(eng, name):
 
 @pytest.mark.parametrize("name", FULL_CASES)
 def test_matches_reference_full_size(eng, name):
-    """BASELINE configs 1 and 2 (720 s, 44.1 kHz, 40 dB / 10 dB)."""
+    """BASELINE configs 1 and 2 (720 s, 44.1 kHz, 40 dB / 10 dB) and the config-5 stand-in (1800 s at 8 dB, chunk
+    4 x fs, dead frequency 2500 Hz, detuned mark / space)."""
     g = Golden(name)
-    out = run_engine(eng, g.pcm(), g.spec.fs)
+    out = run_engine(eng, g.pcm(), g.spec.fs, settings=g.user_settings, triggerrange=g.triggerrange)
     check_against_golden(out, g)
 
 
@@ -150,6 +151,26 @@ def test_kernel_variants_agree_with_reference(opts):
     if "bitfix_all" in opts:        # every window re-evaluated in double: conf agrees with the reference to fp64 round-off
         np.testing.assert_allclose(out["bits"][1], g.z["conf"], rtol=1e-9, equal_nan=True)
         assert out["result"].summary.n_recheck >= g.meta["n_bits"]
+    e.close()
+
+
+@pytest.mark.parametrize("opts", [dict(), dict(ws=1), dict(filter_variant=1)])
+def test_guard_band_samples_are_settled_by_exact_recomputation(opts):
+    """a filter output inside the guard band must not fail the drop.  With the guard widened to 3e-6 the
+    fast passes flag dozens of samples; the ones inside demodulated iterations are re-signed in scipy's operation
+    order from the iteration start and confirmed, the ones in the lead-in are ignored, and the decode stays exact."""
+    g = Golden("g44_10db")
+    e = _engine(guard=3e-6, **opts)
+    out = run_engine(e, g.pcm(), g.spec.fs)
+    s = out["result"].summary
+    assert s.status == 0 and s.n_uncertain == 0
+    assert s.n_guard_hits > 20 and 0 < s.n_guard_confirmed <= s.n_guard_hits
+    check_against_golden(out, g)
+    e.close()
+    q = Golden("g44_nopulse")
+    e = _engine(guard=1e-3, **opts)
+    out = run_engine(e, q.pcm(), q.spec.fs)
+    assert out["result"].summary.status == 0 and out["result"].summary.n_guard_hits > 0
     e.close()
 
 
@@ -310,3 +331,140 @@ def test_config3_full_size_recording(eng):
     words = np.array([int(h, 16) for h in op.hexframes], dtype=np.uint32)
     tab = r.table()
     assert np.array_equal(words, tab["word"][tab["hex_returned"] == 1])
+
+
+def test_calibration_known_answers_on_the_device(eng):
+    """k_calib's arithmetic (ax_sp_from_c, ax_dataconvert) on the GPU against the GSW documentation's check values
+    for gsw_SP_from_C (the call parse.py:132 makes) and parse.dataconvert's summation order."""
+    from test_oracle_units import GSW_C, GSW_P, GSW_SP, GSW_T
+    from oracle import axctd_oracle as ao, pss78
+    cf = [-0.0622192, 1.04584, 3.0e-5, -2.0e-7]
+    sp, poly = eng.calib_eval(GSW_C, GSW_T, GSW_P, coeff=cf)
+    np.testing.assert_allclose(sp, GSW_SP, rtol=1e-13, atol=0)
+    np.testing.assert_allclose(poly, [ao.dataconvert(c, cf) for c in GSW_C], rtol=1e-15, atol=0)
+    # a sweep over the oceanographic range incl. the Hill (SP < 2) branch and invalid input, against oracle/pss78.py
+    rng = np.random.default_rng(7)
+    c = np.concatenate([rng.uniform(0.0, 70.0, 4000), rng.uniform(0.0, 3.0, 1000), [-1.0, 0.0]])
+    t = np.concatenate([rng.uniform(-2.0, 35.0, 5000), [10.0, 10.0]])
+    p = np.concatenate([rng.uniform(0.0, 2000.0, 5000), [0.0, 0.0]])
+    sp, _ = eng.calib_eval(c, t, p)
+    np.testing.assert_allclose(sp, pss78.SP_from_C(c, t, p), rtol=1e-12, atol=1e-13, equal_nan=True)
+
+
+def test_pipelined_decoder_matches_oracle(eng):
+    """batch.PipelinedDecoder -- the ingest path bench.py's e2e figure goes through (pinned host PCM -> alternating
+    engines -> compact rows) -- held to the oracle drop by drop, and to a reference fixture."""
+    import torch
+    from axctdprocessor_b200 import batch as axbatch
+    from oracle import axctd_oracle as ao
+    g = Golden("g44_10db")
+    specs = [synth.DropSpec(fs=(44100, 48000)[i % 2], duration_s=47.0 + 2 * i, seed=8100 + i, snr_db=(35.0, 12.0, 22.0)[i % 3]) for i in range(5)]
+    pcms = [np.ascontiguousarray(synth.generate_drop(s)) for s in specs] + [np.ascontiguousarray(g.pcm())]
+    fss = [s.fs for s in specs] + [g.spec.fs]
+    pinned = []
+    for p in pcms:
+        t = torch.empty(len(p), dtype=torch.int16).pin_memory()
+        t.numpy()[:] = p
+        pinned.append(t)
+    pipe = axbatch.PipelinedDecoder(0, slots=2)
+    groups = [[0, 1], [2, 3], [4, 5]]
+    got = {}
+
+    def submit(h):
+        pipe.submit([pinned[i].data_ptr() for i in h], [len(pcms[i]) for i in h], [fss[i] for i in h])
+
+    for rep in range(2):                                   # the second pass reuses the cached batches
+        submit(groups[0])
+        for q, h in enumerate(groups):
+            if q + 1 < len(groups):
+                submit(groups[q + 1])
+            for i, r in zip(h, pipe.collect(full=False)):
+                got[(rep, i)] = r
+    pipe.close()
+    ops = [ao.process_pcm(p, fs) for p, fs in zip(pcms, fss)]
+    for rep in range(2):
+        for i, op in enumerate(ops):
+            check_rows_against_oracle(got[(rep, i)], op)
+    r = got[(1, 5)]
+    tab = r.table()
+    assert ["%08x" % int(w) for w in tab["word"][tab["hex_returned"] == 1]] == g.hexframes
+    np.testing.assert_allclose(tab["temperature"][tab["keep"] == 1], g.z["temperature"], rtol=1e-6)
+
+
+def test_concurrent_decoder_matches_oracle(eng):
+    """batch.ConcurrentDecoder (sub-batches in flight on their own engines / streams / host threads: the path
+    bench.py's device-resident figure goes through) held to the oracle drop by drop."""
+    from axctdprocessor_b200 import batch as axbatch
+    from oracle import axctd_oracle as ao
+    specs = [synth.DropSpec(fs=(44100, 48000)[i % 2], duration_s=50.0 + i, seed=7100 + i, snr_db=(40.0, 10.0, 20.0)[i % 3]) for i in range(7)]
+    pcms = [np.ascontiguousarray(synth.generate_drop(s)) for s in specs]
+    cd = axbatch.ConcurrentDecoder(0, [len(p) for p in pcms], [s.fs for s in specs], shards=4)
+    for i, p in enumerate(pcms):
+        cd.upload(i, p)
+    cd.run(steps=2)
+    got = cd.results(full=False)
+    cd.close()
+    for s, p, r in zip(specs, pcms, got):
+        check_rows_against_oracle(r, ao.process_pcm(p, s.fs))
+
+
+def _shard_worker(rank, world, port, q, devices):
+    import torch.distributed as dist
+    sys_path = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    import sys
+    sys.path.insert(0, sys_path)
+    sys.path.insert(0, os.path.join(sys_path, "tests"))
+    import synth as S
+    from axctdprocessor_b200 import batch as B, engine as E
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    specs = _shard_specs()
+    sizes = [int(round(s.duration_s * s.fs)) for s in specs]
+    mine = B.partition_drops(sizes, world)[rank]
+    eng = E.Engine(devices[rank])
+    pcms = [np.ascontiguousarray(S.generate_drop(specs[i])) for i in mine]
+    res = B.process_drops(eng, pcms, [specs[i].fs for i in mine])
+    local = {i: dict(status=r.status, rows=r.rows.copy(), chunks=r.chunks.copy(), firstpulse400=int(r.summary.firstpulse400),
+                     profstartind=int(r.summary.profstartind), scale=float(r.summary.high_bit_scale),
+                     n_bits=int(r.summary.n_bits), n_edges=int(r.summary.n_edges)) for i, r in zip(mine, res)}
+    merged = B.gather_results(local, world, rank)
+    dist.barrier()
+    dist.destroy_process_group()
+    eng.close()
+    if rank == 0:
+        q.put(merged)
+
+
+def _shard_specs():
+    return [synth.DropSpec(fs=(44100, 48000)[i % 2], duration_s=46.0 + 4 * (i % 3), seed=9100 + i, snr_db=(30.0, 14.0)[i % 2]) for i in range(6)]
+
+
+def test_two_rank_sharded_decode_equals_oracle_and_single_gpu(eng):
+    """SURVEY 4.3 item 5 on hardware: batch.partition_drops + gather_results with one process per rank (both on
+    the visible GPUs; a second GPU is used when the box has one) -- every drop of the merged result equals the
+    oracle's decode and the single-process decode of the same drop."""
+    import torch
+    import torch.multiprocessing as mp
+    from axctdprocessor_b200 import batch as axbatch
+    from oracle import axctd_oracle as ao
+    ndev = torch.cuda.device_count()
+    devices = [0, 1 if ndev > 1 else 0]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 400)
+    procs = [ctx.Process(target=_shard_worker, args=(r, 2, port, q, devices)) for r in range(2)]
+    for p in procs:
+        p.start()
+    merged = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    specs = _shard_specs()
+    assert sorted(merged) == list(range(len(specs)))
+    pcms = [np.ascontiguousarray(synth.generate_drop(s)) for s in specs]
+    single = axbatch.process_drops(eng, pcms, [s.fs for s in specs])
+    for i, (s, p) in enumerate(zip(specs, pcms)):
+        m = merged[i]
+        assert m["status"] == 0
+        assert np.array_equal(m["rows"], single[i].rows) and np.array_equal(m["chunks"], single[i].chunks)
+        check_rows_against_oracle(single[i], ao.process_pcm(p, s.fs))
+        assert (m["firstpulse400"], m["profstartind"], m["n_bits"]) == (int(single[i].summary.firstpulse400), int(single[i].summary.profstartind), int(single[i].summary.n_bits))

@@ -100,6 +100,21 @@ def test_pss78_unesco_check_value():
     assert abs(pss78.SP_from_C(42.914, 15.0 / 1.00024, 0.0) - 35.0) < 1e-6
 
 
+# gsw.SP_from_C check values: the six-point example of the GSW toolbox documentation for gsw_SP_from_C
+GSW_C = [34.5487, 34.7275, 34.8605, 34.6810, 34.5680, 34.5600]
+GSW_T = [28.7856, 28.4329, 22.8103, 10.2600, 6.8863, 4.4036]
+GSW_P = [10.0, 50.0, 125.0, 250.0, 600.0, 1000.0]
+GSW_SP = [20.009869599086951, 20.265511864874270, 22.981513062527689, 31.204503263727982, 34.032315787432829,
+          36.400308494388170]
+
+
+def test_pss78_matches_gsw_documented_check_values():
+    got = pss78.SP_from_C(np.array(GSW_C), np.array(GSW_T), np.array(GSW_P))
+    np.testing.assert_allclose(got, GSW_SP, rtol=1e-14, atol=0)
+    for c, t, p, sp in zip(GSW_C, GSW_T, GSW_P, GSW_SP):          # scalar call, as parse.py:132 makes it
+        assert abs(float(pss78.SP_from_C(c, t, p)) - sp) <= 1e-14 * sp
+
+
 def test_pss78_hill_extension_continuous_and_nan():
     for t in (0.0, 10.0, 25.0):
         lo, hi = 0.5, 6.0
