@@ -101,14 +101,39 @@ def _oracle_one(args):
     return time.perf_counter() - t0, len(op.time)
 
 
-def cpu_baseline_run(pcms, fss, durations, cores):
-    """Oracle port (numpy restatement of the reference's path), one process per
-    host core, one drop each; aggregate audio-seconds per wall-second."""
+def _reference_one(args):
+    """The UNMODIFIED reference CLI (processAXCTD.main(), reference processAXCTD.py:47-183: WAV read, normalise,
+    run(), output file) under oracle/ref_shim.py, on a WAV file written beforehand."""
+    wav, out = args
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_shim
+    t0 = time.perf_counter()
+    ref_shim.run_cli(["-i", wav, "-o", out])
+    dt = time.perf_counter() - t0
+    with open(out) as f:
+        rows = sum(1 for _ in f)
+    return dt, rows
+
+
+def reference_available():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_shim
+    return ref_shim.available()
+
+
+def cpu_baseline_run(pcms, fss, durations, cores, kind="port", workdir=None):
+    """One process per host core, one drop each; aggregate audio-seconds per wall-second.  kind "reference": the
+    unmodified reference CLI on WAV files in `workdir`; kind "port": oracle/axctd_oracle.py (numpy restatement)."""
     import multiprocessing as mp
     ctx = mp.get_context("fork")
+    if kind == "reference":
+        jobs = [(os.path.join(workdir, f"drop{i}.wav"), os.path.join(workdir, f"drop{i}.txt")) for i in range(len(pcms))]
+        fn = _reference_one
+    else:
+        jobs, fn = list(zip(pcms, fss)), _oracle_one
     t0 = time.perf_counter()
     with ctx.Pool(processes=cores) as pool:
-        out = pool.map(_oracle_one, list(zip(pcms, fss)))
+        out = pool.map(fn, jobs)
     wall = time.perf_counter() - t0
     return sum(durations) / wall, wall, out
 
@@ -120,54 +145,60 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-def make_pcm_for_cpu(specs):
-    """PCM for the CPU arm: from the GPU generator when a device is present, else numpy."""
-    try:
-        import torch
-        has_gpu = torch.cuda.is_available()
-    except Exception:
-        has_gpu = False
-    if has_gpu:
-        from axctdprocessor_b200 import engine
-        eng = engine.Engine(0)
-        out = []
-        for s in specs:
-            n = int(round(s.duration_s * s.fs))
-            b = eng.batch([n], [eng.config(s.fs)])
-            b.synth_fill(0, s)
-            out.append(b.download(0))
-            b.close()
-        eng.close()
-        return out
-    return [synth.generate_drop(s) for s in specs]
+def write_wavs(pcms, fss, workdir):
+    for i, (p, fs) in enumerate(zip(pcms, fss)):
+        synth.write_wav(os.path.join(workdir, f"drop{i}.wav"), p, fs)
 
 
 def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path on the box's host cores -- the unmodified
+    reference (baseline/_ref, installed by __graft_entry__.build()) when present, else the oracle port.  Nothing of
+    this repository's engine is loaded: the PCM comes from the numpy generator (synth.generate_drop)."""
+    import tempfile
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = min(host_cores(), args.cpu_procs) if args.cpu_procs else host_cores()
-    dur = args.cpu_duration
+    kind = "reference" if reference_available() and not args.cpu_port else "port"
+    if kind == "reference":                   # import the reference's modules once; the forked workers inherit them
+        import ref_shim
+        ref_shim.load_modules()
+    dur = args.cpu_duration if args.cpu_duration > 0 else (120.0 if kind == "reference" else 720.0)
     specs = drop_specs(cores, dur, 0)
-    pcms = make_pcm_for_cpu(specs)
-    fss = [s.fs for s in specs]
-    for _ in range(args.warmup):
-        cpu_baseline_run(pcms[:cores], fss[:cores], [dur] * cores, cores)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        cpu_baseline_run(pcms, fss, [dur] * cores, cores)
-    wall = time.perf_counter() - t0
+    with tempfile.TemporaryDirectory() as td:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(processes=cores) as pool:
+            pcms = pool.map(synth.generate_drop, specs)
+        fss = [s.fs for s in specs]
+        if kind == "reference":
+            write_wavs(pcms, fss, td)
+        for _ in range(args.warmup):
+            cpu_baseline_run(pcms, fss, [dur] * cores, cores, kind, td)
+        t0 = time.perf_counter()
+        rows = 0
+        for _ in range(args.steps):
+            _, _, out = cpu_baseline_run(pcms, fss, [dur] * cores, cores, kind, td)
+            rows = sum(o[1] for o in out)
+        wall = time.perf_counter() - t0
+        port = None
+        if kind == "reference":          # the port beside it, one step, for continuity with round 1
+            v, w, _ = cpu_baseline_run(pcms, fss, [dur] * cores, cores, "port")
+            port = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": f"the same {cores} drops, one step, {w:.1f} s wall"}
     value = args.steps * cores * dur / wall
+    what = ("UNMODIFIED reference CLI (processAXCTD.main() under oracle/ref_shim.py: WAV read + run() + output file)"
+            if kind == "reference" else "oracle/axctd_oracle.py (numpy port of the reference's path; baseline/_ref not installed)")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args.drops, args.duration,
-                                      sum(int(round(sp.duration_s * sp.fs)) for sp in drop_specs(args.drops, args.duration, 0))),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"bounded sample of the workload: {cores} of its drops x {dur:.0f} s per step, one process "
-                                       f"per host core, oracle/axctd_oracle.py (numpy port of the reference's path; the reference "
-                                       f"itself is Python and cannot travel to the GPU box)"},
+                                      sum(int(round(sp.duration_s * sp.fs)) for sp in drop_specs(args.drops, args.duration, 0)), args.shards),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                             "sample": f"bounded sample of the workload per step: {cores} drops of the batch's kind "
+                                       f"(44.1/48 kHz alternating, SNR 40/25/10 dB) cut to {dur:.0f} s each, one process per "
+                                       f"host core, {what}; rows written per step: {rows}"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if port:
+        line["cpu_baseline_port"] = port
     print(json.dumps(line))
 
 
@@ -319,13 +350,23 @@ def run_native(args):
                          "algorithmic_bytes": alg_bytes, "note": "issue-bound: 7 FP64-pipe ops (2.2 issue cycles each on B200) + 4 IDP.2A + ~20 other instructions per sample; HBM is not the binding unit"},
             "decoded": {"frames": frames, "rows": rows, "drops_not_ok": bad}}
     if rank == 0 and world == 1 and not args.no_cpu:
+        import tempfile
         cores = host_cores()
         k = min(cores, len(specs), args.cpu_procs or cores)
-        pcms = [b.download(i) for i in range(k)]
-        v, wall, _ = cpu_baseline_run(pcms, [specs[i].fs for i in range(k)], [specs[i].duration_s for i in range(k)], k)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": k, "kind": "port",
-                                "sample": f"{k} of the batch's drops ({args.duration:.0f} s each), one process per core, "
-                                          f"oracle/axctd_oracle.py, {wall:.1f} s wall"}
+        kind = "reference" if reference_available() and not args.cpu_port else "port"
+        dur = min(args.duration, args.cpu_duration if args.cpu_duration > 0 else (180.0 if kind == "reference" else 720.0))
+        pcms = [b.download(i)[:int(round(dur * specs[i].fs))] for i in range(k)]
+        fss = [specs[i].fs for i in range(k)]
+        with tempfile.TemporaryDirectory() as td:
+            if kind == "reference":
+                import ref_shim
+                ref_shim.load_modules()
+                write_wavs(pcms, fss, td)
+            v, wall, _ = cpu_baseline_run(pcms, fss, [dur] * k, k, kind, td)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": k, "kind": kind,
+                                "sample": f"the first {dur:.0f} s of {k} of the batch's drops, one process per core, "
+                                          + ("UNMODIFIED reference CLI (baseline/_ref under oracle/ref_shim.py)" if kind == "reference"
+                                             else "oracle/axctd_oracle.py (numpy port)") + f", {wall:.1f} s wall"}
     if rank == 0:
         print(json.dumps(line))
     b.close()
@@ -345,7 +386,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--e2e-parts", type=int, default=4, help="parts the batch is cut into for the ingest pipeline")
     ap.add_argument("--cpu-procs", type=int, default=0)
-    ap.add_argument("--cpu-duration", type=float, default=720.0)
+    ap.add_argument("--cpu-duration", type=float, default=0.0, help="seconds per drop in the CPU legs (0: 120 for the real reference, 720 for the port)")
+    ap.add_argument("--cpu-port", action="store_true", help="time the oracle port even when baseline/_ref is installed")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--shards", type=int, default=4, help="sub-batches in flight per GPU (batch.ConcurrentDecoder)")
     ap.add_argument("--opt", action="append", default=[], help="engine option name=value (A/B experiments)")

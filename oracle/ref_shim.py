@@ -23,8 +23,23 @@ import types
 
 import numpy as np
 
-REF_DIR = os.environ.get("AXCTD_REFERENCE_DIR", "/root/reference")
 _HERE = os.path.dirname(os.path.abspath(__file__))
+# /root/reference exists only in the build container; __graft_entry__.build() installs an unmodified copy of its
+# five files under baseline/_ref/ (git-ignored, shipped to the GPU box) so that bench.py --impl reference can time the
+# real reference there.  Tests and fixtures are generated from /root/reference itself.
+_INSTALLED = os.path.join(os.path.dirname(_HERE), "baseline", "_ref")
+
+
+def _default_ref_dir():
+    env = os.environ.get("AXCTD_REFERENCE_DIR")
+    if env:
+        return env
+    if os.path.isfile("/root/reference/AXCTDprocessor.py"):
+        return "/root/reference"
+    return _INSTALLED
+
+
+REF_DIR = _default_ref_dir()
 
 
 def available() -> bool:
