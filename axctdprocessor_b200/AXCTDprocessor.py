@@ -50,9 +50,18 @@ def read_wav_pcm16(path):
     if fmt is None or pcm is None:
         raise ValueError("incomplete WAV file (missing fmt or data chunk)")
     tag, nch, fs, bits = fmt
-    if tag != 1 or bits != 16:
-        raise NotImplementedError(f"only 16-bit PCM WAV is supported by the CUDA engine (format {tag}, {bits} bit)")
-    a = np.frombuffer(pcm, dtype="<i2", count=(len(pcm) // (2 * nch)) * nch)
+    if nch < 1:
+        raise ValueError("malformed WAV file: the fmt chunk declares no channels")
+    if tag == 1 and bits == 8:
+        # scipy.io.wavfile.read returns uint8 for 8-bit PCM (the reference then subtracts the mean, :55-57): every
+        # value fits the engine's int16 input exactly
+        a = np.frombuffer(pcm, dtype=np.uint8, count=(len(pcm) // nch) * nch).astype(np.int16)
+    elif tag == 1 and bits == 16:
+        a = np.frombuffer(pcm, dtype="<i2", count=(len(pcm) // (2 * nch)) * nch)
+    else:
+        # 24 / 32-bit integer and float WAVs (which scipy also reads) do not fit the engine's int16 input without
+        # changing the reference's arithmetic (it normalises the samples as read): see INTEGRATION.md
+        raise NotImplementedError(f"only 8 / 16-bit PCM WAV is supported by the CUDA engine (format {tag}, {bits} bit)")
     if nch > 1:
         a = a.reshape(-1, nch)
     return fs, a
@@ -67,6 +76,14 @@ def _first_channel(snd):
     raise Exception("Too many dimensions for an audio file!")
 
 
+def _frames(snd):
+    """The recording as the engine takes it: mono samples (n,) or interleaved frames (n, channels) -- the first
+    channel of a multi-channel file (AXCTDprocessor.py:50) is picked on the GPU (axctd_batch_upload_interleaved)."""
+    if len(np.shape(snd)) not in (1, 2):
+        raise Exception("Too many dimensions for an audio file!")
+    return np.ascontiguousarray(snd)
+
+
 class RawPCM(np.ndarray):
     """int16 samples as read from the WAV file.  ``decimate`` = 2 marks a recording above 50 kHz: the
     engine halves it on the GPU (reference AXCTDprocessor.py:60-62), and ``len()`` / f_s of the
@@ -79,8 +96,12 @@ def readAXCTDwavfile(inputfile, timerange):
     samples and f_s: normalisation ((x-mean)/max|x|, :55-57) and the /2 decimation of
     recordings above 50 kHz (:60-62, f_s becomes the float f_s/2) happen on the GPU.
     As shipped, any positive time bound raises NameError (:65-70)."""
+    return _read_recording(inputfile, timerange, _first_channel)
+
+
+def _read_recording(inputfile, timerange, pick):
     fs, snd = read_wav_pcm16(inputfile)
-    audiostream = _first_channel(snd).view(RawPCM)
+    audiostream = pick(snd).view(RawPCM)
     if fs > 50000:                                       # :60-62
         audiostream.decimate = 2
         fs /= 2
@@ -135,7 +156,7 @@ class AXCTD_Processor:
         self._device = device
         if mode == "wired":
             fs, snd = read_wav_pcm16(audiofile)
-            a = _first_channel(snd)
+            a = _frames(snd)
             if timerange[1] > 0:
                 a = a[:int(fs * timerange[1])]
             if timerange[0] > 0:
@@ -146,7 +167,7 @@ class AXCTD_Processor:
                 fs /= 2
             self.audiostream, self.f_s = a, fs
         else:
-            self.audiostream, self.f_s = readAXCTDwavfile(audiofile, timerange)
+            self.audiostream, self.f_s = _read_recording(audiofile, timerange, _frames)     # (frames as read: channel 0 is picked on the GPU)
         self._decimate = int(getattr(self.audiostream, "decimate", 1))
         self.numpoints = (len(self.audiostream) + 1) // 2 if self._decimate == 2 else len(self.audiostream)
         self.init_default_AXCTD_settings()

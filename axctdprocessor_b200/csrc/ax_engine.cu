@@ -110,6 +110,27 @@ AX_GLOBAL void k_calib_eval(int64_t n, const double* in, double* out, int has_co
         out[n + item] = has_coeff ? ax_dataconvert(in[item], in + 3 * n) : 0.0;
     }
 }
+// first channel of interleaved frames (AXCTDprocessor.py:50): eight output samples per item, 16-byte loads and stores
+// when the frames allow it
+AX_GLOBAL void k_deinterleave(int64_t n, const int16_t* frames, int16_t* out, int64_t n_frames, int channels) {
+    AX_FOR_ITEM(n) {
+        const int64_t f0 = item * 8;
+        int16_t v[8];
+#if defined(__CUDA_ARCH__)
+        if (channels == 2 && f0 + 8 <= n_frames) {
+            const int4 a = reinterpret_cast<const int4*>(frames)[2 * item], c = reinterpret_cast<const int4*>(frames)[2 * item + 1];
+            int4 o;
+            o.x = __byte_perm(a.x, a.y, 0x5410); o.y = __byte_perm(a.z, a.w, 0x5410);
+            o.z = __byte_perm(c.x, c.y, 0x5410); o.w = __byte_perm(c.z, c.w, 0x5410);
+            reinterpret_cast<int4*>(out)[item] = o;
+        } else
+#endif
+        {
+            for (int q = 0; q < 8; ++q) v[q] = f0 + q < n_frames ? frames[(f0 + q) * channels] : (int16_t)0;
+            for (int q = 0; q < 8 && f0 + q < n_frames; ++q) out[f0 + q] = v[q];
+        }
+    }
+}
 AX_GLOBAL void k_rows(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_row_item(w, item); }
 AX_GLOBAL void k_chunkout(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_chunkout_item(w, item); }
 
@@ -143,6 +164,7 @@ struct axctd_engine {
     double opt_hist_tol = 2e-5;           //   the double-precision re-evaluation (bit decision / calibration histogram)
     int opt_bitfix_all = 0;               // test hook: re-evaluate every window
     int opt_ws = 0;                       // warp-specialised fused kernel (k_demod_ws)
+    int opt_bulk = 0;                     // continuous pass stages its rows with cp.async.bulk (TMA unit) instead of LDGSTS
     int opt_fir_first = 1;                // numerators-first cascade in the continuous low-pass pass (k_demod_fused FAST)
     int opt_tone_mma = 1;                 // tone block sums on the FP64 tensor cores (k_stats_tones_mma)
     int opt_heavy_chain = 1;              // engines of one process take turns with the demodulation pass (see ax_heavy_*)
@@ -195,6 +217,7 @@ struct axctd_batch {
     std::vector<void*> allocs;
     AxWave w;
     int16_t* d_pcm = nullptr;
+    void* d_stage = nullptr; size_t stage_bytes = 0;      // interleaved frames of a multi-channel upload
     double* d_qc = nullptr;
     int64_t tb_total = 0, dseg_total = 0;
     int64_t pcm_total = 0, chunk_total = 0, edge_total = 0, frame_total = 0, zc_total = 0, tile_total = 0;
@@ -310,6 +333,7 @@ extern "C" int axctd_engine_set_option(axctd_engine* e, const char* name, double
     else if (s == "inject_misspec") e->opt_inject_misspec = (int)v;
     else if (s == "ws") e->opt_ws = (int)v;
     else if (s == "fir_first") e->opt_fir_first = (int)v;
+    else if (s == "bulk") e->opt_bulk = (int)v;
     else if (s == "heavy_prio") e->opt_heavy_prio = (int)v;
     else if (s == "tone_mma") e->opt_tone_mma = (int)v;
     else if (s == "heavy_chain") e->opt_heavy_chain = (int)v;
@@ -464,6 +488,7 @@ extern "C" void axctd_batch_destroy(axctd_batch* b) {
     for (int i = 0; i < 2; ++i) cudaEventDestroy(b->evx[i]);
 #endif
     for (void* p : b->allocs) ax_free(p);
+    ax_free(b->d_stage);
     ax_host_free(b->h_st); ax_host_free(b->h_row); ax_host_free(b->h_chunk);
     delete b;
 }
@@ -642,6 +667,27 @@ extern "C" int axctd_batch_upload(axctd_batch* b, int drop, const int16_t* pcm, 
     if (!b || drop < 0 || drop >= b->n || !pcm || n != b->drops[drop].n_raw) return AXCTD_ERR_ARG;
     AX_DEV(b->eng);
     if (ax_h2d(b->eng, b->d_pcm + b->drops[drop].pcm_off, pcm, sizeof(int16_t) * n)) return AXCTD_ERR_CUDA;
+    b->ran = false;
+    return AXCTD_OK;
+}
+
+extern "C" int axctd_batch_upload_interleaved(axctd_batch* b, int drop, const int16_t* frames, int64_t n_frames, int channels) {
+    if (!b || drop < 0 || drop >= b->n || !frames || channels < 1 || n_frames != b->drops[drop].n_raw) return AXCTD_ERR_ARG;
+    if (channels == 1) return axctd_batch_upload(b, drop, frames, n_frames);
+    axctd_engine* e = b->eng;
+    AX_DEV(e);
+    const size_t bytes = sizeof(int16_t) * (size_t)n_frames * channels;
+    if (bytes > b->stage_bytes) {                          // staging area for the interleaved frames, grown on demand
+        if (ax_sync(e)) return AXCTD_ERR_CUDA;             // (an earlier de-interleave may still be reading the old one)
+        ax_free(b->d_stage); b->d_stage = nullptr; b->stage_bytes = 0;
+        if (ax_alloc(e, &b->d_stage, bytes + 64)) return AXCTD_ERR_CUDA;
+        b->stage_bytes = bytes;
+    }
+    if (ax_h2d(e, b->d_stage, frames, bytes)) return AXCTD_ERR_CUDA;
+    const int64_t launches_before = e->launches;
+    AX_LAUNCH(e, k_deinterleave, (n_frames + 7) / 8, (const int16_t*)b->d_stage, b->d_pcm + b->drops[drop].pcm_off, n_frames, channels);
+    e->launches = launches_before + 1;
+    if (ax_launch_check(e)) return AXCTD_ERR_CUDA;
     b->ran = false;
     return AXCTD_OK;
 }
@@ -857,7 +903,7 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
     if (scan_only) {
     } else if (fused) {
         // one launch per rate class in use (CTAs of the other classes exit at once)
-        for (int ci : used_cfg) { ax_launch_demod_fused_any<false>(w, e->cfgs[ci], ci, 0, e->stream, e->device, e->opt_ws, e->opt_fir_first); e->launches++; }
+        for (int ci : used_cfg) { ax_launch_demod_fused_any<false>(w, e->cfgs[ci], ci, 0, e->stream, e->device, e->opt_ws, e->opt_fir_first, e->opt_bulk); e->launches++; }
         if (any_dec) { w.only_xf = 1; AX_LAUNCH(e, k_filter, (int64_t)w.nseg_total, w); w.only_xf = 0; }
     } else
 #else
@@ -911,7 +957,7 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
             // heads of the rate classes the fused kernel is instantiated for; the generic form takes the rest
             bool rest = any_dec;
             for (int ci : used_cfg) {
-                if (ax_demod_fused_ok(e->cfgs[ci])) { ax_launch_demod_fused_any<true>(w, e->cfgs[ci], ci, b->chunk_total, e->stream, e->device, e->opt_ws, 0); e->launches++; }
+                if (ax_demod_fused_ok(e->cfgs[ci])) { ax_launch_demod_fused_any<true>(w, e->cfgs[ci], ci, b->chunk_total, e->stream, e->device, e->opt_ws, 0, 0); e->launches++; }
                 else rest = true;
             }
             if (rest) AX_LAUNCH(e, k_headfilt, b->chunk_total, w, 1);

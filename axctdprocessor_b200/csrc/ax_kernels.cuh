@@ -18,6 +18,36 @@ __device__ __forceinline__ void ax_cp_async_commit() { asm volatile("cp.async.co
 template <int N>
 __device__ __forceinline__ void ax_cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
+// ---- bulk asynchronous copies (the TMA unit's 1-D form: cp.async.bulk, SASS UBLKCP) completing on an mbarrier
+__device__ __forceinline__ unsigned ax_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ax_mbar_init(unsigned long long* b, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(ax_smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void ax_mbar_arrive(unsigned long long* b) {
+    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"(ax_smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void ax_mbar_wait(unsigned long long* b, unsigned parity) {
+    const unsigned a = ax_smem_u32(b);
+    unsigned ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    } while (!ok);
+}
+// one arrival that also announces `bytes` of asynchronous copies to come
+__device__ __forceinline__ void ax_mbar_expect_tx(unsigned long long* b, unsigned bytes) {
+    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}\n" ::"r"(ax_smem_u32(b)), "r"(bytes) : "memory");
+}
+// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completes `bytes` on the mbarrier
+__device__ __forceinline__ void ax_bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(ax_smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(ax_smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void ax_mbar_init_fence() {
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+}
+
 // Opt a kernel in to more than 48 KB of dynamic shared memory.  The attribute is per device, so it is tracked per
 // (kernel, device): an engine on a second GPU of the same process sets it again.
 #include <atomic>
@@ -519,6 +549,7 @@ __global__ void __launch_bounds__(128) k_tone_mag(AxWave w, int i_lo, int i_hi) 
 struct AxFdWarp {
     AxF4 tab[AX_WIN_TAPS];                             // phasors of the bit windows (per warp copy: no CTA barrier needed)
     int16_t stage[2][AX_FD_STAGE];
+    unsigned long long mbar[2];                        // BULK staging: one mbarrier per stage buffer
 };
 // Shared memory of a CTA: the four y rings first ([warp][quad][lane] float4, 16 KB per warp, so that the byte offset
 // of a ring quad is ((quad * 512 + lane * 16) & 0x3ff0) | (warp << 14): one add and one LOP3 per load), then the
@@ -543,7 +574,11 @@ static_assert(AX_FD_RINGQ * 32 * sizeof(float4) == 16384, "ring offsets assume 1
 // scale (measured 7.5e-15 over 2.6 M samples), two orders below the guard band that flags unreliable signs.  Row 0
 // of every lane runs in the reference's order (the offset term of the first six samples of a stream differs) and
 // its last six outputs give the all-pole states: w3 = y, w2 = A3 w3, w1 = A2 w2.
-template <int NSEC, int NPCM, bool HEAD, bool FAST>
+// BULK: the rows are staged by the TMA unit instead of the LSU -- every lane issues ONE 128-byte cp.async.bulk
+// (UBLKCP) per row, straight into its own staging row, completing on the stage's mbarrier (lane 0 announces the
+// bytes with arrive.expect_tx, all lanes wait on the phase parity) -- in place of eight 16-byte LDGSTS per lane with
+// their shuffled source addresses and commit / wait groups.
+template <int NSEC, int NPCM, bool HEAD, bool FAST, bool BULK = false>
 __global__ void __launch_bounds__(AX_FD_THREADS, 2) k_demod_fused(const __grid_constant__ AxWave w, const __grid_constant__ AxWinTab tab, int cfg_id, int64_t n_items) {
     extern __shared__ __align__(16) unsigned char ax_smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -610,19 +645,30 @@ __global__ void __launch_bounds__(AX_FD_THREADS, 2) k_demod_fused(const __grid_c
     const int64_t wslot0 = (seg - lane) * (int64_t)out_cap;          // output slot of the warp's row 0
     // rows this lane helps to stage: r = i*4 + prow, i = 0..7
     const int prow = lane >> 3, piece = lane & 7;
-    unsigned long long src[8];
-    int Tr[8];
+    unsigned long long src[BULK ? 1 : 8];
+    int Tr[BULK ? 1 : 8];
+    if constexpr (!BULK) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        src[i] = __shfl_sync(0xffffffffu, xrow, i * 4 + prow) + (unsigned long long)piece * 16;
-        Tr[i] = __shfl_sync(0xffffffffu, T, i * 4 + prow);
+        for (int i = 0; i < 8; ++i) {
+            src[i] = __shfl_sync(0xffffffffu, xrow, i * 4 + prow) + (unsigned long long)piece * 16;
+            Tr[i] = __shfl_sync(0xffffffffu, T, i * 4 + prow);
+        }
+    } else {
+        if (lane == 0) { ax_mbar_init(&sm.mbar[0], 1u); ax_mbar_init(&sm.mbar[1], 1u); ax_mbar_init_fence(); }
     }
     auto issue = [&](int t, int s) {
+        if constexpr (BULK) {
+            const bool mine = t < T;
+            const unsigned nact = (unsigned)__popc(__ballot_sync(0xffffffffu, mine));
+            if (lane == 0) ax_mbar_expect_tx(&sm.mbar[s], 128u * nact);
+            if (mine) ax_bulk_g2s(&sm.stage[s][lane * AX_FD_ROW], reinterpret_cast<const void*>(xrow + (unsigned long long)t * 128), 128u, &sm.mbar[s]);
+        } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-            if (t < Tr[i]) ax_cp_async16(&sm.stage[s][(i * 4 + prow) * AX_FD_ROW + piece * 8],
-                                         reinterpret_cast<const void*>(src[i] + (unsigned long long)t * 128));
-        ax_cp_async_commit();
+            for (int i = 0; i < 8; ++i)
+                if (t < Tr[i]) ax_cp_async16(&sm.stage[s][(i * 4 + prow) * AX_FD_ROW + piece * 8],
+                                             reinterpret_cast<const void*>(src[i] + (unsigned long long)t * 128));
+            ax_cp_async_commit();
+        }
     };
     unsigned long long Sprev = 0ull;        // sign bits of row t-1 (bit i = sample i negative)
     int count = 0, unc = 0;
@@ -633,7 +679,12 @@ __global__ void __launch_bounds__(AX_FD_THREADS, 2) k_demod_fused(const __grid_c
     for (int t = 0; t <= Tmax; ++t) {
         unsigned long long Scur = 0ull;
         if (t < Tmax) {
-            if (t + 1 < Tmax) { issue(t + 1, (t + 1) & 1); ax_cp_async_wait<1>(); } else ax_cp_async_wait<0>();
+            if constexpr (BULK) {
+                if (t + 1 < Tmax) issue(t + 1, (t + 1) & 1);
+                ax_mbar_wait(&sm.mbar[t & 1], (unsigned)((t >> 1) & 1));
+            } else {
+                if (t + 1 < Tmax) { issue(t + 1, (t + 1) & 1); ax_cp_async_wait<1>(); } else ax_cp_async_wait<0>();
+            }
             __syncwarp();
             // ---------------- phase 1: the cascade over this lane's 64 samples
             if (t < T) {
@@ -837,22 +888,6 @@ struct AxWsSmem {
     AxF4 tab[AX_WIN_TAPS];
     AxWsPair pr[AX_WS_PAIRS];
 };
-__device__ __forceinline__ unsigned ax_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void ax_mbar_init(unsigned long long* b, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(ax_smem_u32(b)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void ax_mbar_arrive(unsigned long long* b) {
-    asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"(ax_smem_u32(b)) : "memory");
-}
-__device__ __forceinline__ void ax_mbar_wait(unsigned long long* b, unsigned parity) {
-    const unsigned a = ax_smem_u32(b);
-    unsigned ok;
-    do {
-        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
-                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
-    } while (!ok);
-}
-
 template <int NSEC, int NPCM, bool HEAD>
 __global__ void __launch_bounds__(AX_WS_THREADS, 2) k_demod_ws(const __grid_constant__ AxWave w, const __grid_constant__ AxWinTab tab, int cfg_id, int64_t n_items) {
     static_assert(NPCM + 2 <= 2 * AX_WS_RS, "window must end inside the row after next");
@@ -1082,13 +1117,13 @@ static inline void ax_launch_demod_ws(const AxWave& w, const AxCfg& c, int cfg_i
     k_demod_ws<NSEC, NPCM, HEAD><<<(unsigned)((items + per - 1) / per), AX_WS_THREADS, smem, stream>>>(w, c.win_tab, cfg_id, items);
 }
 
-template <int NSEC, int NPCM, bool HEAD, bool FAST = false>
+template <int NSEC, int NPCM, bool HEAD, bool FAST = false, bool BULK = false>
 static inline void ax_launch_demod_fused(const AxWave& w, const AxCfg& c, int cfg_id, int64_t n_items, cudaStream_t stream, int device) {
     const size_t smem = sizeof(AxFdSmem);
-    ax_optin_smem<k_demod_fused<NSEC, NPCM, HEAD, FAST>>(smem, device);
+    ax_optin_smem<k_demod_fused<NSEC, NPCM, HEAD, FAST, BULK>>(smem, device);
     const int64_t items = HEAD ? n_items : (int64_t)w.nseg_total;
     if (items <= 0) return;
-    k_demod_fused<NSEC, NPCM, HEAD, FAST><<<(unsigned)((items + AX_FD_THREADS - 1) / AX_FD_THREADS), AX_FD_THREADS, smem, stream>>>(w, c.win_tab, cfg_id, items);
+    k_demod_fused<NSEC, NPCM, HEAD, FAST, BULK><<<(unsigned)((items + AX_FD_THREADS - 1) / AX_FD_THREADS), AX_FD_THREADS, smem, stream>>>(w, c.win_tab, cfg_id, items);
 }
 
 // true if the fused kernel has an instantiation for this rate class
@@ -1096,11 +1131,23 @@ static inline bool ax_demod_fused_ok(const AxCfg& c) {
     return ax_sos_is_butter(c) && (c.nsec == 3 || c.nsec == 6) && (c.npcm == 39 || c.npcm == 43) && c.inset == 1;
 }
 template <bool HEAD>
-static inline void ax_launch_demod_fused_any(const AxWave& w, const AxCfg& c, int cfg_id, int64_t n_items, cudaStream_t stream, int device, int ws, int fast) {
+static inline void ax_launch_demod_fused_any(const AxWave& w, const AxCfg& c, int cfg_id, int64_t n_items, cudaStream_t stream, int device, int ws, int fast, int bulk) {
     // numerators-first cascade: continuous pass of the low-pass (every section with numerator g (1 + z^-1)^2) only
     if (!HEAD && !ws && fast && c.nsec == 3 && c.sos[0][1] > 0.0 && c.sos[1][1] > 0.0 && c.sos[2][1] > 0.0) {
-        if (c.npcm == 39) ax_launch_demod_fused<3, 39, false, true>(w, c, cfg_id, n_items, stream, device);
-        else ax_launch_demod_fused<3, 43, false, true>(w, c, cfg_id, n_items, stream, device);
+        if (bulk) {
+            if (c.npcm == 39) ax_launch_demod_fused<3, 39, false, true, true>(w, c, cfg_id, n_items, stream, device);
+            else ax_launch_demod_fused<3, 43, false, true, true>(w, c, cfg_id, n_items, stream, device);
+        } else {
+            if (c.npcm == 39) ax_launch_demod_fused<3, 39, false, true>(w, c, cfg_id, n_items, stream, device);
+            else ax_launch_demod_fused<3, 43, false, true>(w, c, cfg_id, n_items, stream, device);
+        }
+        return;
+    }
+    if (!HEAD && !ws && bulk) {                          // reference-order cascade (band-pass, fir_first = 0) with bulk staging
+        if (c.nsec == 3 && c.npcm == 39) ax_launch_demod_fused<3, 39, false, false, true>(w, c, cfg_id, n_items, stream, device);
+        else if (c.nsec == 3 && c.npcm == 43) ax_launch_demod_fused<3, 43, false, false, true>(w, c, cfg_id, n_items, stream, device);
+        else if (c.nsec == 6 && c.npcm == 39) ax_launch_demod_fused<6, 39, false, false, true>(w, c, cfg_id, n_items, stream, device);
+        else ax_launch_demod_fused<6, 43, false, false, true>(w, c, cfg_id, n_items, stream, device);
         return;
     }
     if (ws) {

@@ -321,7 +321,13 @@ class Batch:
             raise RuntimeError(f"{what} failed ({rc}): {self.eng.error()}")
 
     def upload(self, i: int, pcm: np.ndarray):
+        """Mono samples (n,), or frames (n, channels) as scipy.io.wavfile.read returns them: the first channel
+        is picked on the device (AXCTDprocessor.py:46-52)."""
         pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+        if pcm.ndim == 2:
+            self._check(self.lib.axctd_batch_upload_interleaved(self.h, i, pcm.ctypes.data, pcm.shape[0], pcm.shape[1]),
+                        "axctd_batch_upload_interleaved")
+            return
         self._check(self.lib.axctd_batch_upload(self.h, i, pcm.ctypes.data, pcm.size), "axctd_batch_upload")
 
     def upload_ptr(self, i: int, host_ptr: int, n: int):

@@ -326,12 +326,28 @@ def run_native(args):
 
     d2h_bytes, e2e_frames = e2e_run(1)
     barrier()
+    # what the box can move host -> device with every rank copying at once (same pinned buffers, copies only):
+    # the ceiling of the end-to-end figure, which carries 2 bytes per sample over these links
+    probe_dev = torch.empty(max(n), dtype=torch.int16, device="cuda")
+    def h2d_only():
+        for i in range(len(specs)):
+            probe_dev[:n[i]].copy_(src[i], non_blocking=True)
+        torch.cuda.synchronize()
+    h2d_only()
+    barrier()
+    t0 = time.perf_counter()
+    h2d_only()
+    h2d_s = reduce_max(time.perf_counter() - t0)
+    h2d_ceiling_gbs = world * h2d_bytes / h2d_s / 1e9
+    del probe_dev
+    barrier()
     t0 = time.perf_counter()
     e2e_run(args.e2e_steps)
     torch.cuda.synchronize()
     barrier()
     e2e_s = reduce_max((time.perf_counter() - t0) / args.e2e_steps)
     e2e_value = world * audio_s / e2e_s
+    e2e_gbs = world * h2d_bytes / e2e_s / 1e9
     # parity guard on the end-to-end leg: every pooled recording decodes to the frames it gave device-resident
     assert e2e_frames == sum(int(stats[j].n_frames) for j in src_idx), (e2e_frames, frames)
     pipe.close()
@@ -342,7 +358,10 @@ def run_native(args):
             "config": workload_config(args.drops, args.duration, total_samples, len(streams)),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(d2h_bytes),
-                    "steps": args.e2e_steps, "parts": nparts, "host_thread_bound_to_gpu_numa_node": bool(numa_bound), "note": "pinned host PCM -> axctd_batch_upload -> run -> compact rows to host, wall clock from an idle pipeline to the last result; the batch goes through batch.PipelinedDecoder in parts so that H2D overlaps decode"},
+                    "steps": args.e2e_steps, "parts": nparts, "host_thread_bound_to_gpu_numa_node": bool(numa_bound),
+                    "h2d_gbs": e2e_gbs, "h2d_ceiling_gbs": h2d_ceiling_gbs, "fraction_of_h2d_ceiling": e2e_gbs / h2d_ceiling_gbs,
+                    "h2d_ceiling_note": "aggregate host->device rate of this box with all ranks copying the same pinned buffers and nothing else, measured in this run (tools/h2d_probe.py, profiles/r2_run2_h2d_probe_n*.json: 55 / 115 / 186 GB/s at 1 / 4 / 8 GPUs on the 32-vCPU single-NUMA guest, whatever the memory type, pool size, streams in flight or CPU binding)",
+                    "host_pool_drops": pool_n, "note": "pinned host PCM -> axctd_batch_upload -> run -> compact rows to host, wall clock from an idle pipeline to the last result; the batch goes through batch.PipelinedDecoder in parts so that H2D overlaps decode"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_demod_fused (int16 -> SOS IIR f64 -> zero crossings -> mark/space windows f32)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
@@ -382,7 +401,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--drops", type=int, default=128, help="drops per GPU (config 4: 1024 drops over 8 GPUs)")
     ap.add_argument("--duration", type=float, default=720.0)
-    ap.add_argument("--host-pool", type=int, default=8, help="distinct pinned host drops cycled by the e2e leg")
+    ap.add_argument("--host-pool", type=int, default=32, help="distinct pinned host drops cycled by the e2e leg (32 = 2.1 GB per rank, well beyond the host's 60 MB L3)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--e2e-parts", type=int, default=4, help="parts the batch is cut into for the ingest pipeline")
     ap.add_argument("--cpu-procs", type=int, default=0)

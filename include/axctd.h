@@ -209,6 +209,10 @@ void axctd_batch_destroy(axctd_batch* b);
 /* Replaces the PCM part of readAXCTDwavfile (AXCTDprocessor.py:41-57): copies
  * one drop's int16 samples host->device (stream ordered). */
 int  axctd_batch_upload(axctd_batch* b, int drop, const int16_t* pcm, int64_t n);
+/* Same for a multi-channel recording as scipy.io.wavfile.read returns it (frames of `channels` interleaved int16
+ * samples): the frames are copied as they are and the first channel is picked on the device
+ * (AXCTDprocessor.py:46-52, `audiostream = snd[:,0]`).  n_frames counts frames. */
+int  axctd_batch_upload_interleaved(axctd_batch* b, int drop, const int16_t* frames, int64_t n_frames, int channels);
 /* Device pointer of a drop's PCM (for callers that fill it on the GPU). */
 int  axctd_batch_device_pcm(axctd_batch* b, int drop, void** dptr);
 /* Replaces AXCTD_Processor.run() (AXCTDprocessor.py:267-338) for every drop

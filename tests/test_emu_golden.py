@@ -341,3 +341,27 @@ def test_guard_band_samples_are_settled_by_exact_recomputation():
     out = run_engine(e, q.pcm(), q.spec.fs)
     assert out["result"].summary.status == 0 and out["result"].summary.n_guard_hits > 0
     e.close()
+
+
+def test_multichannel_frames_are_deinterleaved_by_the_engine(eng, tmp_path):
+    """AXCTDprocessor.py:46-52: only the first channel of a multi-channel file is used.  The frames travel as read
+    (axctd_batch_upload_interleaved) and the engine picks channel 0; checked for 2 and 3 channels (odd frame
+    count: vector and tail paths) against the reference fixture, and through the AXCTD_Processor mirror."""
+    import synth
+    from axctdprocessor_b200 import AXCTDprocessor
+    g = Golden("g44_stereo")
+    frames = g.pcm()
+    assert frames.ndim == 2 and frames.shape[1] == 2
+    check_against_golden(run_engine(eng, frames, g.spec.fs), g)
+    three = np.ascontiguousarray(np.concatenate([frames, frames[:, 1:2] // 2], axis=1))
+    check_against_golden(run_engine(eng, three, g.spec.fs), g)
+    b = eng.batch([len(frames) - 3], [eng.config(g.spec.fs)])
+    b.upload(0, frames[:-3])
+    assert np.array_equal(b.download(0), frames[:-3, 0])
+    b.close()
+    wav = tmp_path / "s.wav"
+    synth.write_wav(str(wav), frames, g.spec.fs)
+    ap = AXCTDprocessor.AXCTD_Processor(str(wav), engine=eng)
+    assert ap.audiostream.ndim == 2
+    ap.run()
+    assert ap.hexframes == g.hexframes and ap.firstpulse400 == g.meta["firstpulse400"]

@@ -174,6 +174,28 @@ def test_guard_band_samples_are_settled_by_exact_recomputation(opts):
     e.close()
 
 
+def test_multichannel_frames_are_deinterleaved_on_the_device(eng, tmp_path):
+    """AXCTDprocessor.py:46-52 on the GPU: interleaved frames are uploaded as read and k_deinterleave picks the
+    first channel (2 channels: the 16-byte path; 3 channels and a ragged tail: the generic path)."""
+    from axctdprocessor_b200 import AXCTDprocessor
+    g = Golden("g44_stereo")
+    frames = g.pcm()
+    check_against_golden(run_engine(eng, frames, g.spec.fs), g)
+    three = np.ascontiguousarray(np.concatenate([frames, frames[:, 1:2] // 2], axis=1))
+    check_against_golden(run_engine(eng, three, g.spec.fs), g)
+    for cut in (1, 3, 8):
+        b = eng.batch([len(frames) - cut], [eng.config(g.spec.fs)])
+        b.upload(0, frames[:-cut])
+        assert np.array_equal(b.download(0), frames[:-cut, 0])
+        b.close()
+    wav = tmp_path / "s.wav"
+    synth.write_wav(str(wav), frames, g.spec.fs)
+    ap = AXCTDprocessor.AXCTD_Processor(str(wav), engine=eng)
+    assert ap.audiostream.ndim == 2
+    ap.run()
+    assert ap.hexframes == g.hexframes and ap.firstpulse400 == g.meta["firstpulse400"]
+
+
 def test_full_size_round_trip_property(eng):
     """12-minute 48 kHz drop generated on the device (fresh seed, 30 dB): every
     decoded frame must be one of the transmitted frames, in order, with no gaps
