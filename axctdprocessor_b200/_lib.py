@@ -105,8 +105,8 @@ class SynthDesc(C.Structure):
 SYMBOLS = [
     "axctd_abi_version", "axctd_has_cuda", "axctd_struct_size", "axctd_engine_create", "axctd_engine_destroy", "axctd_last_error",
     "axctd_engine_set_option", "axctd_engine_set_stream", "axctd_engine_launch_count", "axctd_config_create", "axctd_batch_create",
-    "axctd_batch_destroy", "axctd_batch_upload", "axctd_batch_upload_interleaved", "axctd_batch_device_pcm", "axctd_batch_run",
-    "axctd_batch_run_async", "axctd_batch_finish", "axctd_batch_timing", "axctd_batch_summary",
+    "axctd_batch_destroy", "axctd_batch_upload", "axctd_batch_upload_interleaved", "axctd_batch_copy_from", "axctd_batch_device_pcm", "axctd_batch_run",
+    "axctd_batch_run_async", "axctd_batch_finish", "axctd_batch_timing", "axctd_batch_phase_ms", "axctd_batch_summary",
     "axctd_batch_rows", "axctd_batch_frames", "axctd_batch_chunks", "axctd_batch_bits", "axctd_batch_edges", "axctd_batch_power",
     "axctd_synth_fill", "axctd_batch_download", "axctd_calib_eval",
 ]
@@ -131,11 +131,13 @@ def bind(lib: C.CDLL) -> C.CDLL:
         "axctd_batch_destroy": (None, [vp]),
         "axctd_batch_upload": (i32, [vp, i32, vp, i64]),
         "axctd_batch_upload_interleaved": (i32, [vp, i32, vp, i64, i32]),
+        "axctd_batch_copy_from": (i32, [vp, i32, vp, i32, i64, i64]),
         "axctd_batch_device_pcm": (i32, [vp, i32, P(vp)]),
         "axctd_batch_run": (i32, [vp]),
         "axctd_batch_run_async": (i32, [vp]),
         "axctd_batch_finish": (i32, [vp]),
         "axctd_batch_timing": (i32, [vp, P(dbl), P(dbl), P(dbl)]),
+        "axctd_batch_phase_ms": (i32, [vp, P(dbl)]),
         "axctd_batch_summary": (i32, [vp, i32, P(DropSummary)]),
         "axctd_batch_rows": (i64, [vp, i32, vp, i64]),
         "axctd_batch_frames": (i64, [vp, i32, vp, i64]),

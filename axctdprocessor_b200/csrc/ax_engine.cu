@@ -94,6 +94,7 @@ AX_GLOBAL void k_emit(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_emit_item(w, item
 AX_GLOBAL void k_scale(int64_t n, AxWave w) { AX_FOR_ITEM1(n) ax_scale_item(w, item); }
 AX_GLOBAL void k_bits(int64_t n, AxWave w, int phase) { AX_FOR_ITEM(n) ax_bits_item(w, item, phase); }
 AX_GLOBAL void k_headers(int64_t n, AxWave w) { AX_FOR_ITEM1(n) ax_header_item(w, item); }
+AX_GLOBAL void k_merge(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_merge_item(w, item); }
 AX_GLOBAL void k_pack(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_pack_item(w, item); }
 AX_GLOBAL void k_valid(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_valid_item(w, item); }
 AX_GLOBAL void k_frames_spec(int64_t n, AxWave w) { AX_FOR_ITEM(n) ax_frames_spec_item(w, item); }
@@ -168,6 +169,7 @@ struct axctd_engine {
     int opt_fir_first = 1;                // numerators-first cascade in the continuous low-pass pass (k_demod_fused FAST)
     int opt_tone_mma = 1;                 // tone block sums on the FP64 tensor cores (k_stats_tones_mma)
     int opt_heavy_chain = 1;              // engines of one process take turns with the demodulation pass (see ax_heavy_*)
+    int opt_nosync = 1;                   // enqueue the whole decode without host round trips (see axctd_batch_run_async)
     int opt_scan_only = 0;                // tone levels only (segmentation of long recordings): skip the demodulation pass
 };
 
@@ -227,8 +229,12 @@ struct axctd_batch {
     axctd_row* h_row = nullptr;           // [frame_total], a drop's rows at frame_base
     axctd_chunk* h_chunk = nullptr;       // [chunk_total]
     std::vector<axctd_drop_summary> summary;
+    bool force_sync = false;              // repeat of a run whose fixed schedule did not suffice
     bool ran = false, finished = false;
+    bool ran_nosync = false;              // the last run was enqueued without host round trips: finish() checks the flags
+    int64_t n_fallbacks = 0;              // runs that had to be repeated with the host-driven loops
     double ms_total = 0, ms_filter = 0, ms_tone = 0;
+    double ms_phase[5] = {0, 0, 0, 0, 0};
 #ifndef AXCTD_EMU
     cudaEvent_t ev[6];
     cudaEvent_t evx[2];                   // hand-over to / from the engine's high-priority stream
@@ -338,6 +344,7 @@ extern "C" int axctd_engine_set_option(axctd_engine* e, const char* name, double
     else if (s == "tone_mma") e->opt_tone_mma = (int)v;
     else if (s == "heavy_chain") e->opt_heavy_chain = (int)v;
     else if (s == "scan_only") e->opt_scan_only = (int)v;
+    else if (s == "nosync") e->opt_nosync = (int)v;
     else if (s == "bit_tol") e->opt_bit_tol = v;
     else if (s == "hist_tol") e->opt_hist_tol = v;
     else if (s == "bitfix_all") e->opt_bitfix_all = (int)v;
@@ -456,6 +463,14 @@ extern "C" int axctd_config_create(axctd_engine* e, const axctd_config_desc* ds,
         }
         c.g_len = GL;
         if (ax_cfg_upload(e, &c.gtab, g.data(), g.size()) || ax_cfg_upload(e, &c.gcum, gc.data(), gc.size())) return AXCTD_ERR_CUDA;
+    }
+    {   // python's 10**ex as a float (parse.py:278): int power for ex >= 0, libm pow for ex < 0
+        std::vector<double> p10(AX_POW10_LEN);
+        for (int ex = -99; ex <= 999; ++ex) {
+            if (ex >= 0) { char buf[32]; snprintf(buf, sizeof(buf), "1e%d", ex); p10[ex + 99] = strtod(buf, nullptr); }
+            else p10[ex + 99] = pow(10.0, (double)ex);
+        }
+        if (ax_cfg_upload(e, &c.pow10, p10.data(), p10.size())) return AXCTD_ERR_CUDA;
     }
     if (ax_cfg_upload(e, &c.tone_cs, ds->tone_cs, 6 * (size_t)ds->n_power) ||
         ax_cfg_upload(e, &c.lut, ds->temp_lut, (size_t)ds->lut_len) ||
@@ -692,71 +707,31 @@ extern "C" int axctd_batch_upload_interleaved(axctd_batch* b, int drop, const in
     return AXCTD_OK;
 }
 
+extern "C" int axctd_batch_copy_from(axctd_batch* b, int drop, axctd_batch* src, int src_drop, int64_t src_offset, int64_t n) {
+    if (!b || !src || drop < 0 || drop >= b->n || src_drop < 0 || src_drop >= src->n || n != b->drops[drop].n_raw ||
+        src_offset < 0 || src_offset + n > src->drops[src_drop].n_raw || b->eng->device != src->eng->device) return AXCTD_ERR_ARG;
+    axctd_engine* e = b->eng;
+    AX_DEV(e);
+    const int16_t* from = src->d_pcm + src->drops[src_drop].pcm_off + src_offset;
+    int16_t* to = b->d_pcm + b->drops[drop].pcm_off;
+#ifndef AXCTD_EMU
+    if (src->eng->stream != e->stream) {                      // the source's pending upload / de-interleave must have landed
+        cudaEvent_t ev;
+        if (ax_fail(e, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "event") ) return AXCTD_ERR_CUDA;
+        cudaEventRecord(ev, src->eng->stream); cudaStreamWaitEvent(e->stream, ev, 0); cudaEventDestroy(ev);
+    }
+    if (ax_fail(e, cudaMemcpyAsync(to, from, sizeof(int16_t) * (size_t)n, cudaMemcpyDeviceToDevice, e->stream), "D2D")) return AXCTD_ERR_CUDA;
+#else
+    memcpy(to, from, sizeof(int16_t) * (size_t)n);
+#endif
+    b->ran = false;
+    return AXCTD_OK;
+}
+
 extern "C" int axctd_batch_device_pcm(axctd_batch* b, int drop, void** dptr) {
     if (!b || drop < 0 || drop >= b->n || !dptr) return AXCTD_ERR_ARG;
     *dptr = (void*)(b->d_pcm + b->drops[drop].pcm_off);
     return AXCTD_OK;
-}
-
-// ---- header text -> coefficients, metadata merge (host, python float semantics)
-// parse.py:277-278: int(chex[:9])/1E7 * 10**int(chex[9:]) with B->'+', D->'-'
-static bool ax_py_int(const char* s, int len, long long* out) {
-    int i = 0; int sign = 1;
-    if (i < len && (s[i] == '+' || s[i] == '-')) { if (s[i] == '-') sign = -1; ++i; }
-    if (i >= len) return false;
-    long long v = 0;
-    for (; i < len; ++i) { if (s[i] < '0' || s[i] > '9') return false; v = v * 10 + (s[i] - '0'); }
-    *out = sign * v;
-    return true;
-}
-static bool ax_coeff_from_frames(const uint16_t* f3, double* out) {
-    char hex[13];
-    snprintf(hex, sizeof(hex), "%04X%04X%04X", f3[0], f3[1], f3[2]);
-    for (int i = 0; i < 12; ++i) { if (hex[i] == 'B') hex[i] = '+'; else if (hex[i] == 'D') hex[i] = '-'; }
-    long long mant, ex;
-    if (!ax_py_int(hex, 9, &mant) || !ax_py_int(hex + 9, 3, &ex)) return false;
-    const double a = (double)mant / 1e7;
-    double p;
-    if (ex >= 0) { char buf[32]; snprintf(buf, sizeof(buf), "1e%lld", ex); p = strtod(buf, nullptr); }   // python int 10**ex -> float
-    else p = pow(10.0, (double)ex);                                                                    // python float pow
-    *out = a * p;
-    return true;
-}
-
-static void ax_merge_headers(const AxCfg& c, AxState& st, axctd_drop_summary& sm) {
-    // parse.py:187-192 defaults, then AXCTDprocessor.py:505-535
-    const double zd[4] = {1, 1, 1, 1}, td[4] = {0, 1, 0, 0};
-    for (int q = 0; q < 4; ++q) {
-        sm.zcoeff[q] = zd[q]; sm.tcoeff[q] = td[q]; sm.ccoeff[q] = td[q];
-        sm.zcoeff_valid[q] = sm.tcoeff_valid[q] = sm.ccoeff_valid[q] = 0;
-        st.zc_used[q] = c.zc[q]; st.tc_used[q] = c.tc[q]; st.cc_used[q] = c.cc[q];
-    }
-    bool any = false;
-    for (int slot = 0; slot < 2; ++slot) {
-        if (!st.header_parsed[slot]) continue;
-        any = true;
-        const uint8_t* cf = st.counter_found[slot];
-        const uint16_t* fd = st.frame_data[slot];
-        struct { int top; double* co; int32_t* va; } sets[3] = {
-            {33, sm.tcoeff, sm.tcoeff_valid}, {45, sm.ccoeff, sm.ccoeff_valid}, {21, sm.zcoeff, sm.zcoeff_valid}};
-        for (auto& S : sets) {
-            for (int i = 0; i < 4; ++i) {
-                const int f0 = S.top - 3 * i;                      // parse.py:258-270
-                if (cf[f0] && cf[f0 + 1] && cf[f0 + 2]) {
-                    double v;
-                    if (!ax_coeff_from_frames(fd + f0, &v)) { ax_raise(st, AXCTD_DROP_HEADER_VALUE, st.header_chunk[1 + slot]); return; }
-                    S.co[i] = v; S.va[i] = 1;
-                }
-            }
-        }
-    }
-    if (any) {                                                     // AXCTDprocessor.py:529-535
-        const int tv = sm.tcoeff_valid[0] + sm.tcoeff_valid[1] + sm.tcoeff_valid[2] + sm.tcoeff_valid[3];
-        const int cv = sm.ccoeff_valid[0] + sm.ccoeff_valid[1] + sm.ccoeff_valid[2] + sm.ccoeff_valid[3];
-        if (tv == 4) for (int q = 0; q < 4; ++q) st.tc_used[q] = sm.tcoeff[q];
-        if (cv == 4) for (int q = 0; q < 4; ++q) st.cc_used[q] = sm.ccoeff[q];
-        if (tv == 4) for (int q = 0; q < 4; ++q) st.zc_used[q] = sm.zcoeff[q];      // (sic) guarded by the T flag
-    }
 }
 
 #ifndef AXCTD_EMU
@@ -927,12 +902,22 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
     AX_LAUNCH(e, k_pwfill, b->chunk_total, w, 0);
     AX_EVENT(b, 3);
     int32_t flags[8];
+    // Two data-dependent loops steer a decode: the 400 Hz pulse search (rounds of fixed-grid chunks until every drop has
+    // found its pulse) and the chunk-chain repair (predict / recompute heads / verify until no prediction was wrong).
+    // Host-driven, each iteration ends with a flag read.  Without round trips (nosync, the default) a fixed schedule is
+    // enqueued instead -- two search rounds (the first 32 iterations of the fixed grid: 64 s at the default chunk) and
+    // two chain iterations (one repair), whose kernels do nothing for drops that are already settled -- and
+    // axctd_batch_finish looks at the flags once: a drop that needed more repeats the run with the host-driven loops.
+    const bool nosync = e->opt_nosync != 0 && !b->force_sync;
+    b->ran_nosync = nosync;
     // 400 Hz pulse search on the fixed chunk grid, in rounds of chunks (most drops need one round)
-    for (int lo = 0, hi = 8;; lo = hi, hi = hi * 4) {
+    for (int lo = 0, hi = 8, round = 0;; lo = hi, hi = hi * 4, ++round) {
         w.pa_lo = lo; w.pa_hi = hi;
+        if (nosync && round > 0 && ax_zero(e, w.flags + AX_FLAG_MORE, sizeof(int32_t))) return AXCTD_ERR_CUDA;
         ax_run_tones(b, 0);
         AX_LAUNCH(e, k_levels, (int64_t)w.pw_total, w, 0);
         AX_LAUNCH1(e, k_sm, n, w, 0);
+        if (nosync) { if (round >= 1) break; continue; }
         if (ax_d2h(e, flags, w.flags, sizeof(flags)) || ax_sync(e)) return AXCTD_ERR_CUDA;
         if (!flags[AX_FLAG_MORE]) break;
         flags[AX_FLAG_MORE] = 0;
@@ -947,6 +932,7 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
     AX_LAUNCH1(e, k_canon, n, w);
 #endif
     for (int it = 0;; ++it) {
+        if (nosync && it > 0 && ax_zero(e, w.flags + AX_FLAG_DIRTY, sizeof(int32_t))) return AXCTD_ERR_CUDA;
 #ifndef AXCTD_EMU
         if (e->opt_filter_variant == 0) { k_chain_warp<<<n, 32, 0, e->stream>>>(w); e->launches++; } else
 #endif
@@ -969,6 +955,7 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
         if (e->opt_filter_variant == 0) { k_verify_warp<<<n, 32, 0, e->stream>>>(w); e->launches++; } else
 #endif
         { AX_LAUNCH1(e, k_verify, n, w); }
+        if (nosync) { if (it >= 1) break; continue; }
         if (ax_d2h(e, flags, w.flags, sizeof(flags)) || ax_sync(e)) return AXCTD_ERR_CUDA;
         if (!flags[AX_FLAG_DIRTY]) break;
         if (it >= e->opt_max_fixups) { e->err = "chunk chain did not converge"; return AXCTD_ERR_STATE; }
@@ -1016,10 +1003,7 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
 #endif
     AX_BITS(1);
     AX_LAUNCH1(e, k_headers, 2 * (int64_t)n, w);
-    // header text -> calibration coefficients on the host (python float semantics)
-    if (ax_d2h(e, b->st.data(), w.st, sizeof(AxState) * n) || ax_sync(e)) return AXCTD_ERR_CUDA;
-    for (int d = 0; d < n; ++d) ax_merge_headers(e->cfgs[b->drops[d].cfg], b->st[d], b->summary[d]);
-    if (ax_h2d(e, w.st, b->st.data(), sizeof(AxState) * n)) return AXCTD_ERR_CUDA;
+    AX_LAUNCH(e, k_merge, n, w);          // header text -> calibration coefficients (python float semantics, ax_merge_item)
     AX_LAUNCH(e, k_pack, b->edge_total / 32, w);
     AX_LAUNCH(e, k_valid, b->edge_total / 32, w);
     AX_LAUNCH(e, k_frames_spec, b->chunk_total, w);
@@ -1048,7 +1032,17 @@ extern "C" int axctd_batch_finish(axctd_batch* b) {
     AxWave& w = b->w;
     const int n = b->n;
     AX_DEV(e);
-    if (ax_d2h(e, b->h_st, w.st, sizeof(AxState) * n) || ax_sync(e)) return AXCTD_ERR_CUDA;
+    if (b->ran_nosync) {
+        int32_t flags[8];
+        if (ax_d2h(e, flags, w.flags, sizeof(flags)) || ax_d2h(e, b->h_st, w.st, sizeof(AxState) * n) || ax_sync(e)) return AXCTD_ERR_CUDA;
+        if (flags[AX_FLAG_MORE] || flags[AX_FLAG_DIRTY]) {          // the fixed schedule was not enough for some drop
+            b->force_sync = true; b->n_fallbacks++;
+            const int r = axctd_batch_run_async(b);
+            b->force_sync = false;
+            if (r) return r;
+            if (ax_d2h(e, b->h_st, w.st, sizeof(AxState) * n) || ax_sync(e)) return AXCTD_ERR_CUDA;
+        }
+    } else if (ax_d2h(e, b->h_st, w.st, sizeof(AxState) * n) || ax_sync(e)) return AXCTD_ERR_CUDA;
     memcpy(b->st.data(), b->h_st, sizeof(AxState) * n);
     for (int d = 0; d < n; ++d) {
         const AxDrop& dr = b->drops[d];
@@ -1063,6 +1057,7 @@ extern "C" int axctd_batch_finish(axctd_batch* b) {
     cudaEventElapsedTime(&ms, b->ev[0], b->ev[5]); b->ms_total = ms;
     cudaEventElapsedTime(&ms, b->ev[1], b->ev[2]); b->ms_filter = ms;
     cudaEventElapsedTime(&ms, b->ev[3], b->ev[4]); b->ms_tone = ms;
+    for (int q = 0; q < 5; ++q) { cudaEventElapsedTime(&ms, b->ev[q], b->ev[q + 1]); b->ms_phase[q] = ms; }
 #endif
     for (int d = 0; d < n; ++d) {
         const AxDrop& dr = b->drops[d];
@@ -1085,7 +1080,11 @@ extern "C" int axctd_batch_finish(axctd_batch* b) {
         memcpy(sm.frame_data, st.frame_data, sizeof(sm.frame_data));
         memcpy(sm.counter_found, st.counter_found, sizeof(sm.counter_found));
         sm.header_parsed[0] = st.header_parsed[0]; sm.header_parsed[1] = st.header_parsed[1];
-        for (int q = 0; q < 4; ++q) { sm.zcoeff_used[q] = st.zc_used[q]; sm.tcoeff_used[q] = st.tc_used[q]; sm.ccoeff_used[q] = st.cc_used[q]; }
+        for (int q = 0; q < 4; ++q) {
+            sm.zcoeff_used[q] = st.zc_used[q]; sm.tcoeff_used[q] = st.tc_used[q]; sm.ccoeff_used[q] = st.cc_used[q];
+            sm.zcoeff[q] = st.md_z[q]; sm.tcoeff[q] = st.md_t[q]; sm.ccoeff[q] = st.md_c[q];
+            sm.zcoeff_valid[q] = st.md_zv[q]; sm.tcoeff_valid[q] = st.md_tv[q]; sm.ccoeff_valid[q] = st.md_cv[q];
+        }
         int64_t rows = 0, hex = 0;
         for (int k = 0; k < st.n_chunks && k < dr.chunk_cap; ++k) { rows += b->h_chunk[dr.chunk_base + k].n_rows; hex += b->h_chunk[dr.chunk_base + k].n_hex; }
         sm.n_rows = rows; sm.n_hex = hex;
@@ -1105,6 +1104,12 @@ extern "C" int axctd_batch_timing(axctd_batch* b, double* total_ms, double* filt
     if (total_ms) *total_ms = b->ms_total;
     if (filter_ms) *filter_ms = b->ms_filter;
     if (tone_ms) *tone_ms = b->ms_tone;
+    return AXCTD_OK;
+}
+
+extern "C" int axctd_batch_phase_ms(axctd_batch* b, double* ms5) {
+    if (!b || !b->finished || !ms5) return AXCTD_ERR_STATE;
+    for (int q = 0; q < 5; ++q) ms5[q] = b->ms_phase[q];
     return AXCTD_OK;
 }
 

@@ -79,6 +79,68 @@ AX_HDN inline void ax_header_item(const AxWave& w, int64_t item) {
     }
 }
 
+// ---- header text -> calibration coefficients and their merge (parse.py:272-283, AXCTDprocessor.py:505-535) ----
+// A coefficient is the 12 hex characters of three consecutive frames read as text with B -> '+' and D -> '-':
+// int(chars[0:9]) / 1E7 * 10**int(chars[9:12]) in Python arithmetic.  int() takes an optional sign and at least one
+// decimal digit (any other character -- A, C, E, F or a misplaced sign -- is the ValueError of parse.py:278); the
+// division is one IEEE division; 10**ex is an exact integer turned into a float for ex >= 0 and libm's pow(10., ex)
+// for ex < 0, both tabulated by the host (AxCfg::pow10).
+AX_HD bool ax_py_int_nibbles(const uint8_t* nib, int len, int64_t* out) {
+    int i = 0, sign = 1;
+    if (nib[0] == 0xB || nib[0] == 0xD) { if (nib[0] == 0xD) sign = -1; i = 1; }
+    if (i >= len) return false;
+    int64_t v = 0;
+    for (; i < len; ++i) { if (nib[i] > 9) return false; v = v * 10 + nib[i]; }
+    *out = sign * v;
+    return true;
+}
+AX_HD bool ax_coeff_from_frames(const uint16_t* f3, const double* pow10, double* out) {
+    uint8_t nib[12];
+    for (int q = 0; q < 12; ++q) nib[q] = (uint8_t)((f3[q >> 2] >> (12 - 4 * (q & 3))) & 0xF);
+    int64_t mant, ex;
+    if (!ax_py_int_nibbles(nib, 9, &mant) || !ax_py_int_nibbles(nib + 9, 3, &ex)) return false;
+    *out = ax_mul(ax_div((double)mant, 1e7), pow10[ex + 99]);
+    return true;
+}
+AX_HDN inline void ax_merge_item(const AxWave& w, int64_t d) {
+    const AxDrop& dr = w.drop[d];
+    const AxCfg& c = w.cfg[dr.cfg];
+    AxState& st = w.st[d];
+    const double zd[4] = {1, 1, 1, 1}, td[4] = {0, 1, 0, 0};       // parse.py:187-192 defaults
+    for (int q = 0; q < 4; ++q) {
+        st.md_z[q] = zd[q]; st.md_t[q] = td[q]; st.md_c[q] = td[q];
+        st.md_zv[q] = st.md_tv[q] = st.md_cv[q] = 0;
+        st.zc_used[q] = c.zc[q]; st.tc_used[q] = c.tc[q]; st.cc_used[q] = c.cc[q];
+    }
+    bool any = false;
+    for (int slot = 0; slot < 2; ++slot) {
+        if (!st.header_parsed[slot]) continue;
+        any = true;
+        const uint8_t* cf = st.counter_found[slot];
+        const uint16_t* fd = st.frame_data[slot];
+        for (int set = 0; set < 3; ++set) {                         // parse.py:272: t, c, z
+            const int top = set == 0 ? 33 : set == 1 ? 45 : 21;    // parse.py:258-270
+            double* co = set == 0 ? st.md_t : set == 1 ? st.md_c : st.md_z;
+            uint8_t* va = set == 0 ? st.md_tv : set == 1 ? st.md_cv : st.md_zv;
+            for (int i = 0; i < 4; ++i) {
+                const int f0 = top - 3 * i;
+                if (cf[f0] && cf[f0 + 1] && cf[f0 + 2]) {
+                    double v;
+                    if (!ax_coeff_from_frames(fd + f0, c.pow10, &v)) { ax_raise(st, AXCTD_DROP_HEADER_VALUE, st.header_chunk[1 + slot]); return; }
+                    co[i] = v; va[i] = 1;
+                }
+            }
+        }
+    }
+    if (any) {                                                      // AXCTDprocessor.py:529-535
+        const int tv = st.md_tv[0] + st.md_tv[1] + st.md_tv[2] + st.md_tv[3];
+        const int cv = st.md_cv[0] + st.md_cv[1] + st.md_cv[2] + st.md_cv[3];
+        if (tv == 4) for (int q = 0; q < 4; ++q) st.tc_used[q] = st.md_t[q];
+        if (cv == 4) for (int q = 0; q < 4; ++q) st.cc_used[q] = st.md_c[q];
+        if (tv == 4) for (int q = 0; q < 4; ++q) st.zc_used[q] = st.md_z[q];      // (sic) guarded by the T flag
+    }
+}
+
 // 32 demodulated bits -> one word, bit b of word i = bit 32*i + b of the drop's bitstream
 AX_HDN inline void ax_pack_item(const AxWave& w, int64_t wg) {
     const int d = ax_find_owner(w.drop, w.n_drops, &AxDrop::edge_base, wg * 32);

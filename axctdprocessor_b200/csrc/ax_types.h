@@ -56,7 +56,8 @@ AX_HD double ax_nan() { return nan(""); }
 #define AX_PEND 8           // pending bit-windows per thread in the filter pass
 #define AX_STAT_SLAB 16384  // samples per stats work item
 #define AX_TB 256           // samples per tone block (ax_toneblock_item)
-#define AX_TONE_ROT 24      // most tone blocks a window can span
+#define AX_TONE_ROT 40      // most tone blocks a window can span (0.1 s at 96 kHz is 37.5 blocks)
+#define AX_POW10_LEN 1099
 #define AX_UNC_CAP 256      // guard-band samples listed per drop (ax_unc_push); more are only counted
 
 // fp32 phasor table of the bit windows (ax_window32): cos, sin of theta_mark * k and theta_space * k
@@ -86,6 +87,7 @@ struct AxCfg {
     const double* hist_centers;  // [n_hist_edges-1]
     const double* gtab;          // [g_len][4] mark/space window responses: |S_f(i)| = |sum_d u[i+npcm-d] * G_f[d]| (ax_gwin_*)
     const double* gcum;          // [g_len][4] running sums of gtab (response to the constant -dc/ampl term)
+    const double* pow10;         // [AX_POW10_LEN] python's 10**ex as a float for ex = -99 .. 999 (parse.py:278), entry ex + 99
     int32_t g_len, pad_g;
     int32_t lut_len, n_hist_edges;
     double tone_tsum[6];         // sum over the whole window of tone_cs (response to the constant -dc/ampl term)
@@ -184,6 +186,10 @@ struct AxState {
     uint16_t frame_data[2][72];
     uint8_t counter_found[2][72];
     double zc_used[4], tc_used[4], cc_used[4];
+    // merged header metadata (AXCTDprocessor.py:505-524): metadata['?coeff'] and metadata['?coeff_valid']
+    double md_z[4], md_t[4], md_c[4];
+    uint8_t md_zv[4], md_tv[4], md_cv[4];
+    int32_t pad5;
 };
 
 struct AxWave {

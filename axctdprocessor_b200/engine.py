@@ -333,6 +333,10 @@ class Batch:
     def upload_ptr(self, i: int, host_ptr: int, n: int):
         self._check(self.lib.axctd_batch_upload(self.h, i, host_ptr, n), "axctd_batch_upload")
 
+    def copy_from(self, i: int, src: "Batch", src_drop: int, src_offset: int, n: int):
+        """Fill drop i with n samples of ``src``'s drop ``src_drop`` (already on the device) from ``src_offset`` on."""
+        self._check(self.lib.axctd_batch_copy_from(self.h, i, src.h, src_drop, int(src_offset), int(n)), "axctd_batch_copy_from")
+
     def device_ptr(self, i: int) -> int:
         p = C.c_void_p()
         self._check(self.lib.axctd_batch_device_pcm(self.h, i, C.byref(p)), "axctd_batch_device_pcm")
@@ -350,7 +354,10 @@ class Batch:
     def timing(self):
         a, b, c = C.c_double(), C.c_double(), C.c_double()
         self._check(self.lib.axctd_batch_timing(self.h, C.byref(a), C.byref(b), C.byref(c)), "axctd_batch_timing")
-        return dict(total_ms=a.value, filter_ms=b.value, tone_ms=c.value)
+        ph = (C.c_double * 5)()
+        self._check(self.lib.axctd_batch_phase_ms(self.h, ph), "axctd_batch_phase_ms")
+        return dict(total_ms=a.value, filter_ms=b.value, tone_ms=c.value, ingest_ms=ph[0], demod_ms=ph[1],
+                    crossings_ms=ph[2], search_ms=ph[3], decode_ms=ph[4])
 
     def summary(self, i: int) -> _lib.DropSummary:
         s = _lib.DropSummary()

@@ -25,23 +25,33 @@ import numpy as np
 from . import engine as _engine
 
 
-def scan_levels(eng: _engine.Engine, pcm: np.ndarray, fs: float, settings=None, decimate: int = 1):
-    """(power_inds, r400, r7500) over the whole recording on the fixed chunk grid.
-    ``fs`` is the effective rate (after any /2 decimation); indices refer to the effective signal."""
+def scan_batch(eng: _engine.Engine, pcm, fs_raw: float, settings=None):
+    """Upload the recording once and take its tone levels on the fixed chunk grid at the rate it was recorded at
+    (no demodulation, no decimation: the 400 Hz level is the same signal at either rate).  Returns the batch -- which
+    keeps the recording on the device for the segment decode -- and (power_inds, r400, r7500) in raw sample units.
+    ``pcm``: int16 ndarray, mono or (n, channels) frames."""
     st = dict(settings or {})
     st["minr400"] = 1e300                      # never leaves status 0: every chunk stays on the fixed grid
     eng.set_option("scan_only", 1)
     try:
-        cfg = eng.config(fs, settings=st, decimate=decimate)
+        cfg = eng.config(fs_raw, settings=st)
         b = eng.batch([len(pcm)], [cfg])
         try:
             b.upload(0, pcm)
             b.run()
-            return b.power(0)
-        finally:
+            return b, b.power(0)
+        except Exception:
             b.close()
+            raise
     finally:
         eng.set_option("scan_only", 0)
+
+
+def scan_levels(eng: _engine.Engine, pcm: np.ndarray, fs_raw: float, settings=None):
+    """(power_inds, r400, r7500) over the whole recording at its own rate (see scan_batch)."""
+    b, lv = scan_batch(eng, pcm, fs_raw, settings=settings)
+    b.close()
+    return lv
 
 
 def find_drops(power_inds, r400, fs: float, n_total: int, min_r400: float = 2.0, quiet_s: float = 2.0,
@@ -79,16 +89,29 @@ def find_drops(power_inds, r400, fs: float, n_total: int, min_r400: float = 2.0,
 
 def process_recording(eng: _engine.Engine, pcm: np.ndarray, fs: float, settings=None, triggerrange=None, decimate: int = 1,
                       **find_kw):
-    """Decode every drop of a long recording.  Returns [(start_raw, end_raw, DropResult)] with sample
-    ranges in the units of ``pcm`` (raw samples)."""
+    """Decode every drop of a long recording.  ``fs`` is the effective rate (after any /2 decimation), ``pcm`` the raw
+    samples.  Returns [(start_raw, end_raw, DropResult)] with sample ranges in the units of ``pcm``.
+
+    The recording crosses the PCIe link once: the scan batch keeps it on the device and every segment is filled from
+    there (axctd_batch_copy_from).  Each segment is then normalised, halved (recordings above 50 kHz) and decoded as
+    the stand-alone recording it would be on disk, so its result is the reference's for that file."""
     pcm = np.ascontiguousarray(pcm, dtype=np.int16)
-    p, r400, _ = scan_levels(eng, pcm, fs, settings=settings, decimate=decimate)
-    n_eff = (len(pcm) + 1) // 2 if decimate == 2 else len(pcm)
-    min_r400 = float((settings or {}).get("minr400", _engine.DEFAULT_SETTINGS["minr400"]))
-    segs = find_drops(p, r400, fs, n_eff, min_r400=min_r400, **find_kw)
-    if not segs:
-        return []
-    raw = [(a * decimate, min(b * decimate, len(pcm))) for a, b in segs]
-    cfg = eng.config(fs, settings=settings, triggerrange=triggerrange, decimate=decimate)
-    res = eng.process([pcm[a:b] for a, b in raw], [cfg] * len(raw))
-    return [(a, b, r) for (a, b), r in zip(raw, res)]
+    fs_raw = fs * decimate
+    scan, (p, r400, _) = scan_batch(eng, pcm, fs_raw, settings=settings)
+    try:
+        min_r400 = float((settings or {}).get("minr400", _engine.DEFAULT_SETTINGS["minr400"]))
+        raw = find_drops(p, r400, fs_raw, len(pcm), min_r400=min_r400, **find_kw)
+        if not raw:
+            return []
+        cfg = eng.config(fs, settings=settings, triggerrange=triggerrange, decimate=decimate)
+        b = eng.batch([hi - lo for lo, hi in raw], [cfg] * len(raw))
+        try:
+            for i, (lo, hi) in enumerate(raw):
+                b.copy_from(i, scan, 0, lo, hi - lo)
+            b.run()
+            res = [b.result(i) for i in range(len(raw))]
+        finally:
+            b.close()
+    finally:
+        scan.close()
+    return [(lo, hi, r) for (lo, hi), r in zip(raw, res)]

@@ -202,6 +202,110 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+# ---------------------------------------------------------------- the other BASELINE configs
+def measure_configs(device, opts):
+    """BASELINE configs 1, 2, 3 and 5 next to the headline (config 4), each through the public API with the recording
+    in pinned HOST memory (upload, decode and result download inside the timed region), plus the device time of the
+    decode alone.  Synthetic recordings are generated on the device and moved to the host before anything is timed."""
+    import torch
+    from axctdprocessor_b200 import engine, segment
+    eng = engine.Engine(device)
+    for k, v in opts.items():
+        eng.set_option(k, v)
+    out = {}
+
+    def pinned_drop(spec):
+        n = int(round(spec.duration_s * spec.fs))
+        g = eng.batch([n], [eng.config(spec.fs if spec.fs <= 50000 else spec.fs / 2, decimate=2 if spec.fs > 50000 else 1)])
+        g.synth_fill(0, spec)
+        t = torch.empty(n, dtype=torch.int16).pin_memory()
+        t.numpy()[:] = g.download(0)
+        g.close()
+        return t
+
+    def med(xs):
+        return float(np.median(xs))
+
+    # configs 1 and 2: one 12-minute 44.1 kHz drop (40 dB, default low-pass / 10 dB, band-pass as -u documents it)
+    for name, spec, st in (("config1_single_drop", synth.config_spec("config1"), None),
+                           ("config2_single_drop_bandpass_10db", synth.config_spec("config2"), {"usebandpass": True})):
+        host = pinned_drop(spec)
+        cfg = eng.config(spec.fs, settings=st)
+        b = eng.batch([len(host)], [cfg])
+        e2e, dev, rows = [], [], 0
+        for rep in range(8):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            b.upload_ptr(0, host.data_ptr(), len(host))
+            b.run()
+            r = b.result(0, full=False)
+            dt = time.perf_counter() - t0
+            if rep >= 3:
+                e2e.append(1e3 * dt); dev.append(b.timing())
+            rows = int(r.summary.n_rows)
+        ph = {k: med([d[k] for d in dev]) for k in dev[0]}
+        out[name] = {"e2e_ms": med(e2e), "device_ms": ph["total_ms"], "x_realtime_e2e": spec.duration_s / (1e-3 * med(e2e)),
+                     "x_realtime_device": spec.duration_s / (1e-3 * ph["total_ms"]), "phases_ms": {k: round(v, 4) for k, v in ph.items()},
+                     "status": int(r.summary.status), "frames": int(r.summary.n_frames), "rows": rows,
+                     "h2d_bytes": 2 * len(host)}
+        b.close()
+        del host
+
+    # config 3: 96 kHz, one hour, five drops back to back; cut by the segmentation driver, halved on the device
+    specs = [synth.DropSpec(fs=96000, duration_s=720.0, seed=3300 + i, snr_db=(40.0, 25.0, 10.0)[i % 3]) for i in range(5)]
+    parts = [pinned_drop(s) for s in specs]
+    rec = torch.empty(sum(len(p) for p in parts), dtype=torch.int16).pin_memory()
+    torch.cat(parts, out=rec)
+    del parts
+    t = []
+    for rep in range(4):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        segs = segment.process_recording(eng, rec.numpy(), 48000.0, decimate=2)
+        t.append(time.perf_counter() - t0)
+    out["config3_96k_1h_recording"] = {"e2e_ms": 1e3 * med(t[1:]), "x_realtime_e2e": 3600.0 / med(t[1:]), "segments": len(segs),
+                                       "frames": [int(r.summary.n_frames) for _, _, r in segs],
+                                       "status": [int(r.summary.status) for _, _, r in segs], "h2d_bytes": 2 * len(rec)}
+    del rec
+
+    # config 5: parameter sweep over a 4-hour low-SNR archive (20 drops x 720 s at 44.1 kHz, 8 dB): the archive is
+    # uploaded and cut once, every parameter point decodes every segment (segments x points drops, filled on the device)
+    specs = [synth.DropSpec(fs=44100, duration_s=720.0, seed=5500 + i, snr_db=8.0) for i in range(20)]
+    parts = [pinned_drop(s) for s in specs]
+    rec = torch.empty(sum(len(p) for p in parts), dtype=torch.int16).pin_memory()
+    torch.cat(parts, out=rec)
+    del parts
+    points = [{"refreshrate": rr, "mark_space_freqs": ms, "deadfreq": df}
+              for rr in (0.5, 1.0, 2.0, 4.0, 8.0) for ms in ([400.0, 800.0], [405.0, 795.0]) for df in (3000.0, 2500.0)]
+    t, frames = [], 0
+    for rep in range(2):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        scan, (p, r400, _) = segment.scan_batch(eng, rec.numpy(), 44100.0)
+        cuts = segment.find_drops(p, r400, 44100.0, len(rec))
+        frames = 0
+        wave = 5                                         # parameter points per batch
+        for w0 in range(0, len(points), wave):
+            pts = points[w0:w0 + wave]
+            cfgs = [eng.config(44100.0, settings=pt) for pt in pts for _ in cuts]
+            b = eng.batch([hi - lo for _ in pts for lo, hi in cuts], cfgs)
+            for q in range(len(pts)):
+                for i, (lo, hi) in enumerate(cuts):
+                    b.copy_from(q * len(cuts) + i, scan, 0, lo, hi - lo)
+            b.run()
+            frames += sum(int(b.summary(i).n_frames) for i in range(b.n))
+            b.close()
+        scan.close()
+        t.append(time.perf_counter() - t0)
+    audio = len(points) * len(rec) / 44100.0
+    out["config5_sweep_4h_archive"] = {"e2e_ms": 1e3 * t[-1], "x_realtime_e2e": audio / t[-1], "points": len(points),
+                                       "segments": len(cuts), "drop_decodes": len(points) * len(cuts), "frames": frames,
+                                       "audio_seconds_decoded": audio, "h2d_bytes": 2 * len(rec),
+                                       "note": "chunk 0.5/1/2/4/8 x fs, mark/space (400,800)/(405,795), dead 3000/2500 Hz"}
+    eng.close()
+    return out
+
+
 # ---------------------------------------------------------------- this engine
 def run_native(args):
     import torch
@@ -386,9 +490,12 @@ def run_native(args):
                                 "sample": f"the first {dur:.0f} s of {k} of the batch's drops, one process per core, "
                                           + ("UNMODIFIED reference CLI (baseline/_ref under oracle/ref_shim.py)" if kind == "reference"
                                              else "oracle/axctd_oracle.py (numpy port)") + f", {wall:.1f} s wall"}
+    b.close()
+    if rank == 0 and world == 1 and not args.no_configs:
+        torch.cuda.empty_cache()
+        line["configs"] = measure_configs(local, opts)
     if rank == 0:
         print(json.dumps(line))
-    b.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -408,6 +515,7 @@ def main():
     ap.add_argument("--cpu-duration", type=float, default=0.0, help="seconds per drop in the CPU legs (0: 120 for the real reference, 720 for the port)")
     ap.add_argument("--cpu-port", action="store_true", help="time the oracle port even when baseline/_ref is installed")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the side measurements of BASELINE configs 1, 2, 3 and 5")
     ap.add_argument("--shards", type=int, default=4, help="sub-batches in flight per GPU (batch.ConcurrentDecoder)")
     ap.add_argument("--opt", action="append", default=[], help="engine option name=value (A/B experiments)")
     args = ap.parse_args()

@@ -213,6 +213,10 @@ int  axctd_batch_upload(axctd_batch* b, int drop, const int16_t* pcm, int64_t n)
  * samples): the frames are copied as they are and the first channel is picked on the device
  * (AXCTDprocessor.py:46-52, `audiostream = snd[:,0]`).  n_frames counts frames. */
 int  axctd_batch_upload_interleaved(axctd_batch* b, int drop, const int16_t* frames, int64_t n_frames, int channels);
+/* Fill a drop from samples that are already on the device: n samples of drop src_drop of batch src (same GPU), from
+ * sample src_offset on.  This is how the segments of a long recording (segment.py: one upload, many drops) and the
+ * points of a parameter sweep over one archive reach their batch without a second host->device copy. */
+int  axctd_batch_copy_from(axctd_batch* b, int drop, axctd_batch* src, int src_drop, int64_t src_offset, int64_t n);
 /* Device pointer of a drop's PCM (for callers that fill it on the GPU). */
 int  axctd_batch_device_pcm(axctd_batch* b, int drop, void** dptr);
 /* Replaces AXCTD_Processor.run() (AXCTDprocessor.py:267-338) for every drop
@@ -225,6 +229,10 @@ int  axctd_batch_finish(axctd_batch* b);
  * and of the dominant filter kernel inside it. */
 int  axctd_batch_timing(axctd_batch* b, double* total_ms, double* filter_ms, double* tone_ms);
 
+/* Device milliseconds of the five phases of the last run, in order: ingest (statistics, tone block sums, /2
+ * decimation), demodulation pass, crossing bookkeeping, 400 Hz pulse search, everything after it (chunk chain, bits,
+ * headers, frames, calibration). */
+int  axctd_batch_phase_ms(axctd_batch* b, double* ms5);
 int  axctd_batch_summary(axctd_batch* b, int drop, axctd_drop_summary* out);
 /* Caller-owned buffers; each returns the number of items written or a
  * negative AXCTD_ERR_* code.  cap is the buffer capacity in items. */

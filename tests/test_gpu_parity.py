@@ -140,7 +140,8 @@ def test_batch_equals_single_drops(eng):
 
 @pytest.mark.parametrize("opts", [dict(tone_direct=1), dict(force_exact=1), dict(inject_misspec=1),
                                   dict(segment_len=4096), dict(segment_len=32768), dict(filter_variant=1),
-                                  dict(bitfix_all=1), dict(bit_tol=1e-3, hist_tol=1e-3), dict(ws=1), dict(ws=1, segment_len=4096), dict(fir_first=0), dict(fir_first=0, segment_len=4096), dict(tone_mma=0)])
+                                  dict(bitfix_all=1), dict(bit_tol=1e-3, hist_tol=1e-3), dict(ws=1), dict(ws=1, segment_len=4096), dict(fir_first=0), dict(fir_first=0, segment_len=4096), dict(tone_mma=0),
+                                  dict(bulk=1), dict(bulk=1, fir_first=0), dict(bulk=1, segment_len=4096), dict(bulk=0)])
 def test_kernel_variants_agree_with_reference(opts):
     g = Golden("g48_25db")
     e = _engine(**opts)
@@ -171,6 +172,17 @@ def test_guard_band_samples_are_settled_by_exact_recomputation(opts):
     e = _engine(guard=1e-3, **opts)
     out = run_engine(e, q.pcm(), q.spec.fs)
     assert out["result"].summary.status == 0 and out["result"].summary.n_guard_hits > 0
+    e.close()
+
+
+@pytest.mark.parametrize("name", ["g44_bandpass", "g44_10db", "g48_chunk8", "g44_chunk05"])
+@pytest.mark.parametrize("bulk", [0, 1])
+def test_both_staging_forms_match_reference(name, bulk):
+    """The continuous pass with its rows staged by cp.async.bulk (TMA unit, UBLKCP) and by LDGSTS: band-pass
+    (six sections, reference-order cascade), low-pass at 10 dB, and both ends of the chunk-size sweep."""
+    g = Golden(name)
+    e = _engine(bulk=bulk)
+    check_against_golden(run_engine(e, g.pcm(), g.spec.fs, settings=g.user_settings, triggerrange=g.triggerrange), g)
     e.close()
 
 
