@@ -175,7 +175,7 @@ struct axctd_engine {
 
 #ifdef AXCTD_EMU
 static int ax_alloc(axctd_engine*, void** p, size_t bytes) { *p = calloc(bytes ? bytes : 1, 1); return *p ? 0 : 1; }
-static void ax_free(void* p) { free(p); }
+static void ax_free(axctd_engine*, void* p) { free(p); }
 static int ax_h2d(axctd_engine*, void* d, const void* h, size_t b) { memcpy(d, h, b); return 0; }
 static int ax_d2h(axctd_engine*, void* h, const void* d, size_t b) { memcpy(h, d, b); return 0; }
 static int ax_zero(axctd_engine*, void* d, size_t b) { memset(d, 0, b); return 0; }
@@ -188,8 +188,73 @@ static int ax_fail(axctd_engine* e, cudaError_t r, const char* what) {
     e->err = std::string(what) + ": " + cudaGetErrorString(r);
     return 1;
 }
-static int ax_alloc(axctd_engine* e, void** p, size_t bytes) { return ax_fail(e, cudaMalloc(p, bytes ? bytes : 1), "cudaMalloc"); }
-static void ax_free(void* p) { if (p) cudaFree(p); }
+// ---- block cache.  cudaMalloc / cudaFree / cudaHostAlloc of the gigabyte-sized arrays of a batch cost more than the
+// decode of a one-hour recording (measured: 0.09 s to create and 0.58 s to destroy the two batches of BASELINE config 3
+// against 0.045 s of device work, profiles/r2_run5_config3_phases_before.json), and cudaFree synchronises the whole
+// device.  Blocks of destroyed batches are therefore kept, per device (one list for pinned host memory), and handed
+// to the next batch that asks for about that size; the cache is emptied when the last engine of the process on that
+// device is destroyed, when an allocation fails, or on request (engine option "pool_trim").  A block only enters the
+// cache after its batch's stream has been synchronised (axctd_batch_destroy).
+#include <map>
+#include <mutex>
+#include <unordered_map>
+struct AxBlockCache {
+    std::mutex mu;
+    std::multimap<size_t, void*> idle;             // cached blocks by size
+    std::unordered_map<void*, size_t> live;        // size of every block handed out
+    size_t idle_bytes = 0;
+    int engines = 0;                               // live engines using this cache
+    void* take(size_t bytes) {
+        std::lock_guard<std::mutex> g(mu);
+        auto it = idle.lower_bound(bytes);
+        if (it == idle.end() || it->first > bytes + bytes / 4 + 65536) return nullptr;
+        void* p = it->second;
+        live[p] = it->first; idle_bytes -= it->first;
+        idle.erase(it);
+        return p;
+    }
+    void adopt(void* p, size_t bytes) { std::lock_guard<std::mutex> g(mu); live[p] = bytes; }
+    bool give(void* p) {                           // false: not one of ours
+        std::lock_guard<std::mutex> g(mu);
+        auto it = live.find(p);
+        if (it == live.end()) return false;
+        idle.emplace(it->second, p); idle_bytes += it->second;
+        live.erase(it);
+        return true;
+    }
+    template <typename F> void trim(F release) {
+        std::lock_guard<std::mutex> g(mu);
+        for (auto& kv : idle) release(kv.second);
+        idle.clear(); idle_bytes = 0;
+    }
+};
+static AxBlockCache g_dev_cache[64];
+static AxBlockCache g_host_cache;
+static int g_pool_on = 1, g_pool_poison = 0;
+static AxBlockCache* ax_dev_cache(const axctd_engine* e) { return (g_pool_on && e->device >= 0 && e->device < 64) ? &g_dev_cache[e->device] : nullptr; }
+static void ax_pool_trim(int device) {
+    if (device >= 0 && device < 64) g_dev_cache[device].trim([](void* p) { cudaFree(p); });
+    g_host_cache.trim([](void* p) { cudaFreeHost(p); });
+}
+static int ax_alloc(axctd_engine* e, void** p, size_t bytes) {
+    bytes = ((bytes ? bytes : 1) + 255) & ~(size_t)255;
+    AxBlockCache* c = ax_dev_cache(e);
+    if (c && (*p = c->take(bytes)) != nullptr) {
+        if (g_pool_poison) cudaMemsetAsync(*p, 0xA5, bytes, e->stream);      // test hook: nothing may rely on fresh (zeroed) pages
+        return 0;
+    }
+    cudaError_t r = cudaMalloc(p, bytes);
+    if (r == cudaErrorMemoryAllocation) { cudaGetLastError(); ax_pool_trim(e->device); r = cudaMalloc(p, bytes); }
+    if (r == cudaSuccess && c) c->adopt(*p, bytes);
+    return ax_fail(e, r, "cudaMalloc");
+}
+static void ax_free(axctd_engine* e, void* p) {
+    if (!p) return;
+    AxBlockCache* c = ax_dev_cache(e);
+    if (c && c->give(p)) return;
+    if (e->device >= 0 && e->device < 64) { std::lock_guard<std::mutex> g(g_dev_cache[e->device].mu); g_dev_cache[e->device].live.erase(p); }
+    cudaFree(p);
+}
 static int ax_h2d(axctd_engine* e, void* d, const void* h, size_t b) { return ax_fail(e, cudaMemcpyAsync(d, h, b, cudaMemcpyHostToDevice, e->stream), "H2D"); }
 static int ax_d2h(axctd_engine* e, void* h, const void* d, size_t b) { return ax_fail(e, cudaMemcpyAsync(h, d, b, cudaMemcpyDeviceToHost, e->stream), "D2H"); }
 static int ax_zero(axctd_engine* e, void* d, size_t b) { return ax_fail(e, cudaMemsetAsync(d, 0, b, e->stream), "memset"); }
@@ -208,8 +273,22 @@ static int ax_sync(axctd_engine* e) {
 static void* ax_host_alloc(size_t bytes) { return calloc(bytes ? bytes : 1, 1); }
 static void ax_host_free(void* p) { free(p); }
 #else
-static void* ax_host_alloc(size_t bytes) { void* p = nullptr; return cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) == cudaSuccess ? p : nullptr; }
-static void ax_host_free(void* p) { if (p) cudaFreeHost(p); }
+static void* ax_host_alloc(size_t bytes) {          // pinned, through the block cache
+    bytes = ((bytes ? bytes : 1) + 4095) & ~(size_t)4095;
+    void* p = g_pool_on ? g_host_cache.take(bytes) : nullptr;
+    if (p) return p;
+    cudaError_t r = cudaHostAlloc(&p, bytes, cudaHostAllocDefault);
+    if (r != cudaSuccess) { cudaGetLastError(); g_host_cache.trim([](void* q) { cudaFreeHost(q); }); r = cudaHostAlloc(&p, bytes, cudaHostAllocDefault); }
+    if (r != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (g_pool_on) g_host_cache.adopt(p, bytes);
+    return p;
+}
+static void ax_host_free(void* p) {
+    if (!p) return;
+    if (g_pool_on && g_host_cache.give(p)) return;
+    { std::lock_guard<std::mutex> g(g_host_cache.mu); g_host_cache.live.erase(p); }
+    cudaFreeHost(p);
+}
 #endif
 
 struct axctd_batch {
@@ -231,6 +310,7 @@ struct axctd_batch {
     std::vector<axctd_drop_summary> summary;
     bool force_sync = false;              // repeat of a run whose fixed schedule did not suffice
     bool ran = false, finished = false;
+    bool lent = false;                    // another engine's stream has read this batch's PCM (axctd_batch_copy_from)
     bool ran_nosync = false;              // the last run was enqueued without host round trips: finish() checks the flags
     int64_t n_fallbacks = 0;              // runs that had to be repeated with the host-driven loops
     double ms_total = 0, ms_filter = 0, ms_tone = 0;
@@ -294,6 +374,9 @@ extern "C" int axctd_engine_create(int device, axctd_engine** out) {
     void* p = nullptr;
     if (ax_alloc(e, &p, sizeof(AxCfg) * e->cfg_cap)) { delete e; *out = nullptr; return AXCTD_ERR_CUDA; }
     e->d_cfg = (AxCfg*)p;
+#ifndef AXCTD_EMU
+    if (device >= 0 && device < 64) { std::lock_guard<std::mutex> g(g_dev_cache[device].mu); g_dev_cache[device].engines++; }
+#endif
     *out = e;
     return AXCTD_OK;
 }
@@ -301,11 +384,16 @@ extern "C" int axctd_engine_create(int device, axctd_engine** out) {
 extern "C" void axctd_engine_destroy(axctd_engine* e) {
     if (!e) return;
     AX_DEV(e);
-    for (void* p : e->cfg_allocs) ax_free(p);
-    ax_free(e->d_cfg);
+    for (void* p : e->cfg_allocs) ax_free(e, p);
+    ax_free(e, e->d_cfg);
 #ifndef AXCTD_EMU
     if (e->stream && e->own_stream) cudaStreamDestroy(e->stream);
     if (e->hp_stream) { cudaStreamSynchronize(e->hp_stream); cudaStreamDestroy(e->hp_stream); }
+    if (e->device >= 0 && e->device < 64) {          // the last engine on a device returns the cached blocks
+        bool last;
+        { std::lock_guard<std::mutex> g(g_dev_cache[e->device].mu); last = --g_dev_cache[e->device].engines <= 0; }
+        if (last) ax_pool_trim(e->device);
+    }
 #endif
     delete e;
 }
@@ -348,6 +436,13 @@ extern "C" int axctd_engine_set_option(axctd_engine* e, const char* name, double
     else if (s == "bit_tol") e->opt_bit_tol = v;
     else if (s == "hist_tol") e->opt_hist_tol = v;
     else if (s == "bitfix_all") e->opt_bitfix_all = (int)v;
+#ifndef AXCTD_EMU
+    else if (s == "pool") g_pool_on = v != 0.0;                              // block cache on / off (process-wide)
+    else if (s == "pool_poison") g_pool_poison = v != 0.0;                   // test hook: recycled blocks are filled with 0xA5
+    else if (s == "pool_trim") { AX_DEV(e); cudaStreamSynchronize(e->stream); ax_pool_trim(e->device); }
+#else
+    else if (s == "pool" || s == "pool_trim" || s == "pool_poison") {}
+#endif
     else return AXCTD_ERR_ARG;
     return AXCTD_OK;
 }
@@ -499,11 +594,13 @@ extern "C" void axctd_batch_destroy(axctd_batch* b) {
     AX_DEV(b->eng);
 #ifndef AXCTD_EMU
     cudaStreamSynchronize(b->eng->stream);
+    if (b->eng->hp_stream) cudaStreamSynchronize(b->eng->hp_stream);
+    if (b->lent) cudaDeviceSynchronize();
     for (int i = 0; i < 6; ++i) cudaEventDestroy(b->ev[i]);
     for (int i = 0; i < 2; ++i) cudaEventDestroy(b->evx[i]);
 #endif
-    for (void* p : b->allocs) ax_free(p);
-    ax_free(b->d_stage);
+    for (void* p : b->allocs) ax_free(b->eng, p);
+    ax_free(b->eng, b->d_stage);
     ax_host_free(b->h_st); ax_host_free(b->h_row); ax_host_free(b->h_chunk);
     delete b;
 }
@@ -694,7 +791,7 @@ extern "C" int axctd_batch_upload_interleaved(axctd_batch* b, int drop, const in
     const size_t bytes = sizeof(int16_t) * (size_t)n_frames * channels;
     if (bytes > b->stage_bytes) {                          // staging area for the interleaved frames, grown on demand
         if (ax_sync(e)) return AXCTD_ERR_CUDA;             // (an earlier de-interleave may still be reading the old one)
-        ax_free(b->d_stage); b->d_stage = nullptr; b->stage_bytes = 0;
+        ax_free(e, b->d_stage); b->d_stage = nullptr; b->stage_bytes = 0;
         if (ax_alloc(e, &b->d_stage, bytes + 64)) return AXCTD_ERR_CUDA;
         b->stage_bytes = bytes;
     }
@@ -716,6 +813,7 @@ extern "C" int axctd_batch_copy_from(axctd_batch* b, int drop, axctd_batch* src,
     int16_t* to = b->d_pcm + b->drops[drop].pcm_off;
 #ifndef AXCTD_EMU
     if (src->eng->stream != e->stream) {                      // the source's pending upload / de-interleave must have landed
+        src->lent = true;                                     // (and its blocks must not be recycled under this copy)
         cudaEvent_t ev;
         if (ax_fail(e, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "event") ) return AXCTD_ERR_CUDA;
         cudaEventRecord(ev, src->eng->stream); cudaStreamWaitEvent(e->stream, ev, 0); cudaEventDestroy(ev);
@@ -916,6 +1014,9 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
         if (nosync && round > 0 && ax_zero(e, w.flags + AX_FLAG_MORE, sizeof(int32_t))) return AXCTD_ERR_CUDA;
         ax_run_tones(b, 0);
         AX_LAUNCH(e, k_levels, (int64_t)w.pw_total, w, 0);
+#ifndef AXCTD_EMU
+        k_sm_search_warp<<<n, 32, 0, e->stream>>>(w); e->launches++;
+#endif
         AX_LAUNCH1(e, k_sm, n, w, 0);
         if (nosync) { if (round >= 1) break; continue; }
         if (ax_d2h(e, flags, w.flags, sizeof(flags)) || ax_sync(e)) return AXCTD_ERR_CUDA;
@@ -1247,7 +1348,7 @@ extern "C" int axctd_calib_eval(axctd_engine* e, const double* cond, const doubl
         bad = bad || ax_d2h(e, out.data(), d_out, out.size() * sizeof(double)) || ax_sync(e);
     }
     e->launches = launches_before;          // tooling, not part of the decode path
-    ax_free(d_in); ax_free(d_out);
+    ax_free(e, d_in); ax_free(e, d_out);
     if (bad) return AXCTD_ERR_CUDA;
     memcpy(sp, out.data(), sizeof(double) * n);
     if (poly) memcpy(poly, out.data() + n, sizeof(double) * n);

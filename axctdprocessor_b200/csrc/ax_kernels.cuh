@@ -1368,6 +1368,43 @@ __global__ void __launch_bounds__(32) k_plan_tones_warp(AxWave w) {
     if (__any_sync(0xffffffffu, small) && lane == 0) st.par_levels = 0;
 }
 
+// Pulse search of a detection round (ax_sm_item, phase 0, status 0) with the lanes looking at different power samples:
+// the first sample whose 400 Hz level reaches the threshold decides where the sequential state machine has anything
+// to do; the iterations before it only record "still status 0".  A one-hour recording scanned for its drops
+// (segment.scan_batch) has 90 000 power samples and no pulse the scan accepts: one thread took 4 ms per round.
+__global__ void __launch_bounds__(32) k_sm_search_warp(AxWave w) {
+    const int d = blockIdx.x, lane = threadIdx.x;
+    AxState& st = w.st[d];
+    if (st.status != 0 || st.sm_status != 0 || !st.par_levels) return;
+    int klo, kend;
+    if (!ax_level_range(w, st, 0, &klo, &kend)) return;
+    const AxDrop& dr = w.drop[d];
+    const AxCfg& c = w.cfg[dr.cfg];
+    AxChunk* ch = w.chunk + dr.chunk_base;
+    const int kfrom = st.next_sm_chunk;
+    if (kfrom >= kend) return;
+    const double* r400 = w.r400 + dr.pw_base;
+    const int i0 = ch[kfrom].pw_off, i1 = ch[kend - 1].pw_off + ch[kend - 1].np;
+    int first = i1;
+    for (int ib = i0; ib < i1 && first == i1; ib += 32 * 8) {
+        int mine = i1;
+#pragma unroll
+        for (int u = 7; u >= 0; --u) { const int i = ib + 32 * u + lane; if (i < i1 && r400[i] >= c.min_r400) mine = i; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mine = min(mine, __shfl_xor_sync(0xffffffffu, mine, o));
+        first = mine;
+    }
+    int kf = kend;                                     // iteration that holds the first hit
+    if (first < i1) {
+        int lo = kfrom, hi = kend - 1;                 // last iteration with pw_off <= first
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (ch[mid].pw_off <= first) lo = mid; else hi = mid - 1; }
+        kf = lo;
+    }
+    for (int k = kfrom + lane; k < kf; k += 32) { ch[k].mean7500 = st.mean7500; ch[k].status = 0; ch[k].profstart = st.profstartind; }
+    __syncwarp();
+    if (lane == 0 && kf > kfrom) { st.pcount = ch[kf - 1].pw_off + ch[kf - 1].np; st.next_sm_chunk = kf; }
+}
+
 // ax_chain_item with the lanes fetching in parallel.  Per run() iteration three rounds of loads: the crossings
 // around the predicted end of the chunk (lane i looks at ordinal guess-16+i), the canonical masks of the tiles
 // that can hold the stopping crossing, and the two crossing indices that fix the next start.

@@ -20,6 +20,9 @@ pytestmark = pytest.mark.gpu
 def eng():
     from axctdprocessor_b200 import engine
     e = engine.Engine(0)
+    # recycled device blocks (the engine's block cache) come back filled with 0xA5 instead of whatever the last batch
+    # left: no kernel may rely on freshly allocated memory being zero
+    e.set_option("pool_poison", 1)
     yield e
     e.close()
 
