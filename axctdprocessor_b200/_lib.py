@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libaxctd.so")
 
 MAX_SECTIONS = 6
-ABI_VERSION = 2          # AXCTD_ABI_VERSION of include/axctd.h
+ABI_VERSION = 3          # AXCTD_ABI_VERSION of include/axctd.h
 
 
 class ConfigDesc(C.Structure):
@@ -109,6 +109,7 @@ SYMBOLS = [
     "axctd_batch_run_async", "axctd_batch_finish", "axctd_batch_timing", "axctd_batch_phase_ms", "axctd_batch_summary",
     "axctd_batch_rows", "axctd_batch_frames", "axctd_batch_chunks", "axctd_batch_bits", "axctd_batch_edges", "axctd_batch_power",
     "axctd_synth_fill", "axctd_batch_download", "axctd_calib_eval",
+    "axctd_batch_stream_begin", "axctd_batch_stream_append", "axctd_batch_stream_run",
 ]
 
 
@@ -148,6 +149,9 @@ def bind(lib: C.CDLL) -> C.CDLL:
         "axctd_synth_fill": (i32, [vp, i32, P(SynthDesc)]),
         "axctd_batch_download": (i32, [vp, i32, vp, i64]),
         "axctd_calib_eval": (i32, [vp, vp, vp, vp, i32, vp, vp, vp]),
+        "axctd_batch_stream_begin": (i32, [vp, P(dbl), P(dbl)]),
+        "axctd_batch_stream_append": (i32, [vp, i32, vp, i64]),
+        "axctd_batch_stream_run": (i32, [vp, i32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -305,6 +305,7 @@ AX_HDN inline void ax_filter_segment(const AxWave& w, int64_t seg) {
     if (j >= dr.nseg) { w.seg_cnt[seg] = 0; w.seg_unc[seg] = 0; return; }
     const AxCfg& c = w.cfg[dr.cfg];
     AxState& st = w.st[d];
+    if (w.streaming && j < st.seg_done) return;          // its records are final (an earlier run of the growing recording)
     const AxSegGeom g = ax_seg_geom(dr, c, w.seg_len, j);
     const AxSrc x = ax_src(w, dr);
     const int64_t slot = seg * (int64_t)w.seg_cap;
@@ -561,7 +562,8 @@ AX_HDN inline void ax_chain_item(const AxWave& w, int64_t d) {
     else s = ch[k - 1].true_last - 1 - c.pad;          // s + (last_edge - 1) - pad
     int64_t entry = -1, span = (int64_t)c.chunk_len / 37;
     for (;; ++k) {
-        if (dr.n - s < 4 * (int64_t)c.n_power) { st.n_chunks = k; break; }          // :295
+        if (w.streaming == 1) { if (s + c.chunk_len >= dr.n) { st.n_chunks = k; break; } }   // not complete yet: a later run takes it
+        else if (dr.n - s < 4 * (int64_t)c.n_power) { st.n_chunks = k; break; }     // :295
         if (k >= dr.chunk_cap) { ax_raise(st, AXCTD_DROP_CAPACITY, k); w.flags[AX_FLAG_CAP] = 1; st.n_chunks = k; break; }
         int64_t e = s + c.chunk_len;                                               // :293
         if (e >= dr.n) e = dr.n - 1;                                               // :299-300
@@ -727,6 +729,7 @@ AX_HDN inline void ax_verify_item(const AxWave& w, int64_t d) {
             // if the end-of-file test (:295) stops it first.
             const double sf = (double)ch[k].s + c.fs / (double)c.bitrate;
             if (!((double)dr.n - sf < 4.0 * c.n_power)) ax_raise(st, AXCTD_DROP_FLOAT_INDEX, k + 1);
+            else if (w.streaming == 1) { st.n_chunks = k; st.chain_from = k; st.chain_end = 1; return; }   // the file may end here: decided by a later run
             st.n_chunks = k + 1; st.chain_from = k + 1; st.chain_end = 1;
             return;
         }

@@ -57,6 +57,36 @@ AX_GLOBAL void k_init(int64_t n, AxWave w) {
         for (int q = 0; q < 4; ++q) { st.zc_used[q] = c.zc[q]; st.tc_used[q] = c.tc[q]; st.cc_used[q] = c.cc[q]; }
     }
 }
+// ---- streaming decode of a growing recording (axctd_batch_stream_*)
+// normalisation fixed by the caller instead of the whole-file statistics of AXCTDprocessor.py:55-57 (ax_stats_fin)
+AX_GLOBAL void k_stream_begin(int64_t n, AxWave w, const double* norm) {
+    AX_FOR_ITEM(n) {
+        AxState& st = w.st[item];
+        st.dc = norm[2 * item]; st.ampl_d = norm[2 * item + 1];
+        st.ampl = (int32_t)st.ampl_d; st.inv_ampl = ax_div(1.0, st.ampl_d);
+    }
+}
+// a later run: the state of the iterations already decoded stays; only what a run re-derives is re-armed
+AX_GLOBAL void k_stream_resume(int64_t n, AxWave w) {
+    AX_FOR_ITEM(n) {
+        AxState& st = w.st[item];
+        st.chain_end = 0; st.chain_dirty = 0;
+        st.n_unc_relevant = 0; st.n_unc_resolved = 0; st.n_uncertain = 0;      // (ax_unc_resolve_item goes through the whole list again)
+    }
+}
+// end of a run: what it leaves final for the next one
+AX_GLOBAL void k_stream_commit(int64_t n, AxWave w) {
+    AX_FOR_ITEM(n) {
+        AxState& st = w.st[item];
+        const AxDrop& dr = w.drop[item];
+        const AxCfg& c = w.cfg[dr.cfg];
+        if (st.status == 0) st.k_done = st.n_chunks;
+        int64_t sd = dr.n > c.npcm ? (dr.n - c.npcm) / w.seg_len : 0;        // segments whose last window lies inside the data
+        if (sd > dr.nseg) sd = dr.nseg;
+        st.seg_done = (int32_t)sd;
+        st.tb_done = dr.ntb;
+    }
+}
 AX_GLOBAL void k_inject(int64_t n, AxWave w) {     // test hook: pretend the first prediction was off by 3 samples
     AX_FOR_ITEM(n) {
         AxState& s = w.st[item];
@@ -311,6 +341,12 @@ struct axctd_batch {
     bool force_sync = false;              // repeat of a run whose fixed schedule did not suffice
     bool ran = false, finished = false;
     bool lent = false;                    // another engine's stream has read this batch's PCM (axctd_batch_copy_from)
+    // streaming decode (axctd_batch_stream_*): drops hold growing recordings, `drops` carries their current lengths
+    bool streaming = false, stream_closed = false, in_stream_run = false;
+    int stream_runs = 0;
+    std::vector<int64_t> cap_n;           // samples each drop was created for
+    std::vector<int64_t> rows_done;       // rows already on the host
+    double* d_norm = nullptr;
     bool ran_nosync = false;              // the last run was enqueued without host round trips: finish() checks the flags
     int64_t n_fallbacks = 0;              // runs that had to be repeated with the host-driven loops
     double ms_total = 0, ms_filter = 0, ms_tone = 0;
@@ -776,7 +812,7 @@ extern "C" int axctd_batch_create(axctd_engine* e, int n_drops, const int64_t* n
 }
 
 extern "C" int axctd_batch_upload(axctd_batch* b, int drop, const int16_t* pcm, int64_t n) {
-    if (!b || drop < 0 || drop >= b->n || !pcm || n != b->drops[drop].n_raw) return AXCTD_ERR_ARG;
+    if (!b || b->streaming || drop < 0 || drop >= b->n || !pcm || n != b->drops[drop].n_raw) return AXCTD_ERR_ARG;
     AX_DEV(b->eng);
     if (ax_h2d(b->eng, b->d_pcm + b->drops[drop].pcm_off, pcm, sizeof(int16_t) * n)) return AXCTD_ERR_CUDA;
     b->ran = false;
@@ -784,7 +820,7 @@ extern "C" int axctd_batch_upload(axctd_batch* b, int drop, const int16_t* pcm, 
 }
 
 extern "C" int axctd_batch_upload_interleaved(axctd_batch* b, int drop, const int16_t* frames, int64_t n_frames, int channels) {
-    if (!b || drop < 0 || drop >= b->n || !frames || channels < 1 || n_frames != b->drops[drop].n_raw) return AXCTD_ERR_ARG;
+    if (!b || b->streaming || drop < 0 || drop >= b->n || !frames || channels < 1 || n_frames != b->drops[drop].n_raw) return AXCTD_ERR_ARG;
     if (channels == 1) return axctd_batch_upload(b, drop, frames, n_frames);
     axctd_engine* e = b->eng;
     AX_DEV(e);
@@ -805,7 +841,7 @@ extern "C" int axctd_batch_upload_interleaved(axctd_batch* b, int drop, const in
 }
 
 extern "C" int axctd_batch_copy_from(axctd_batch* b, int drop, axctd_batch* src, int src_drop, int64_t src_offset, int64_t n) {
-    if (!b || !src || drop < 0 || drop >= b->n || src_drop < 0 || src_drop >= src->n || n != b->drops[drop].n_raw ||
+    if (!b || !src || b->streaming || drop < 0 || drop >= b->n || src_drop < 0 || src_drop >= src->n || n != b->drops[drop].n_raw ||
         src_offset < 0 || src_offset + n > src->drops[src_drop].n_raw || b->eng->device != src->eng->device) return AXCTD_ERR_ARG;
     axctd_engine* e = b->eng;
     AX_DEV(e);
@@ -914,9 +950,13 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
     cudaSetDevice(e->device);
 #endif
     b->finished = false;
+    const bool streaming = b->streaming;
+    if (streaming && !b->in_stream_run) { e->err = "a streaming batch runs through axctd_batch_stream_run"; return AXCTD_ERR_STATE; }
     AX_EVENT(b, 0);
     if (ax_zero(e, w.flags, sizeof(int32_t) * 8)) return AXCTD_ERR_CUDA;
-    AX_LAUNCH(e, k_init, n, w);
+    if (!streaming) { AX_LAUNCH(e, k_init, n, w); }
+    else if (b->stream_runs == 0) { AX_LAUNCH(e, k_init, n, w); AX_LAUNCH(e, k_stream_begin, n, w, (const double*)b->d_norm); }
+    else { AX_LAUNCH(e, k_stream_resume, n, w); }
 #ifndef AXCTD_EMU
     {   // one pass over the PCM: statistics and the tone block sums, one launch per rate class in use
         for (size_t ci = 0; ci < e->cfgs.size(); ++ci) {
@@ -928,12 +968,12 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
                 k_stats_tones<<<dim3((unsigned)((w.ntb_max + AX_ST_THREADS - 1) / AX_ST_THREADS), (unsigned)n), AX_ST_THREADS, 0, e->stream>>>(w, e->tone_tabs[ci], (int)ci);
             e->launches++;
         }
-        if (w.nslab_total > 0) { k_stats_wrap<<<w.nslab_total, 256, 0, e->stream>>>(w); e->launches++; }
+        if (w.nslab_total > 0 && !streaming) { k_stats_wrap<<<w.nslab_total, 256, 0, e->stream>>>(w); e->launches++; }
     }
 #else
-    AX_LAUNCH(e, k_stats, (int64_t)w.nslab_total, w);
+    if (!streaming) { AX_LAUNCH(e, k_stats, (int64_t)w.nslab_total, w); }
 #endif
-    AX_LAUNCH(e, k_stats_fin, n, w);
+    if (!streaming) { AX_LAUNCH(e, k_stats_fin, n, w); }        // (streaming: the normalisation was fixed by the caller)
     const bool any_dec = b->dseg_total > 0;
     if (any_dec) {       // recordings above 50 kHz: halve them on the device (AXCTDprocessor.py:60-62)
         AX_LAUNCH(e, k_decim, b->dseg_total, w, 0);
@@ -1006,10 +1046,16 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
     // enqueued instead -- two search rounds (the first 32 iterations of the fixed grid: 64 s at the default chunk) and
     // two chain iterations (one repair), whose kernels do nothing for drops that are already settled -- and
     // axctd_batch_finish looks at the flags once: a drop that needed more repeats the run with the host-driven loops.
-    const bool nosync = e->opt_nosync != 0 && !b->force_sync;
+    const bool nosync = e->opt_nosync != 0 && !b->force_sync && !streaming;
     b->ran_nosync = nosync;
-    // 400 Hz pulse search on the fixed chunk grid, in rounds of chunks (most drops need one round)
-    for (int lo = 0, hi = 8, round = 0;; lo = hi, hi = hi * 4, ++round) {
+    // 400 Hz pulse search on the fixed chunk grid, in rounds of chunks (most drops need one round); a streaming run looks
+    // at the iterations that are new since the previous run, in one round
+    int lo0 = 0, hi0 = 8;
+    if (streaming) {
+        hi0 = 1 << 28; lo0 = hi0;
+        for (int d2 = 0; d2 < n; ++d2) if (b->stream_runs == 0 || b->st[d2].sm_status == 0) lo0 = std::min(lo0, b->stream_runs == 0 ? 0 : (int)b->st[d2].next_sm_chunk);
+    }
+    for (int lo = lo0, hi = hi0, round = 0; lo < hi; lo = hi, hi = hi * 4, ++round) {
         w.pa_lo = lo; w.pa_hi = hi;
         if (nosync && round > 0 && ax_zero(e, w.flags + AX_FLAG_MORE, sizeof(int32_t))) return AXCTD_ERR_CUDA;
         ax_run_tones(b, 0);
@@ -1120,6 +1166,7 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
     { AX_LAUNCH(e, k_qc, b->chunk_total, w, b->d_qc); }
     AX_LAUNCH(e, k_rows, b->frame_total, w);
     AX_LAUNCH(e, k_chunkout, b->chunk_total, w);
+    if (streaming) { AX_LAUNCH(e, k_stream_commit, n, w); }
     AX_EVENT(b, 5);
     if (ax_launch_check(e)) return AXCTD_ERR_CUDA;
     b->ran = true;
@@ -1149,7 +1196,10 @@ extern "C" int axctd_batch_finish(axctd_batch* b) {
         const AxDrop& dr = b->drops[d];
         const int64_t nf = b->st[d].status == 0 ? b->st[d].n_frames : 0;
         const int64_t nc = std::min<int64_t>(b->st[d].n_chunks, dr.chunk_cap);
-        if (nf > 0 && ax_d2h(e, b->h_row + dr.frame_base, w.row + dr.frame_base, sizeof(axctd_row) * nf)) return AXCTD_ERR_CUDA;
+        // (streaming: the rows of iterations closed by earlier runs are on the host already and do not change)
+        const int64_t f0 = b->streaming ? std::min<int64_t>(b->rows_done[d], nf) : 0;
+        if (nf > f0 && ax_d2h(e, b->h_row + dr.frame_base + f0, w.row + dr.frame_base + f0, sizeof(axctd_row) * (nf - f0))) return AXCTD_ERR_CUDA;
+        if (b->streaming) b->rows_done[d] = nf;
         if (nc > 0 && ax_d2h(e, b->h_chunk + dr.chunk_base, w.chunk_out + dr.chunk_base, sizeof(axctd_chunk) * nc)) return AXCTD_ERR_CUDA;
     }
     if (ax_sync(e)) return AXCTD_ERR_CUDA;
@@ -1198,6 +1248,68 @@ extern "C" int axctd_batch_run(axctd_batch* b) {
     int r = axctd_batch_run_async(b);
     if (r) return r;
     return axctd_batch_finish(b);
+}
+
+// ============================================================ C ABI: streaming
+// A growing recording decoded one run at a time (the shape of the reference's own loop: AXCTDprocessor.py:283-338 is
+// written per 2 s iteration with a `keepgoing` flag).  Each drop of the batch was created with the most samples it can
+// take; samples are appended as they arrive and every run decodes the iterations that have become complete
+// (s + pointsperloop inside the data, so that :299-300 cannot cut them short), on top of the device state the previous
+// runs left: per-sample work (tone block sums, filter, crossings, windows) covers the new samples only, per-bit work
+// the new iterations only.  The normalisation of AXCTDprocessor.py:55-57 needs the whole file, so the caller fixes
+// (dc, ampl) up front; the result equals the reference's for the recording normalised with those two numbers.
+static void ax_stream_set_len(axctd_batch* b, int d, int64_t n) {
+    AxDrop& dr = b->drops[d];
+    dr.n = n; dr.n_raw = n;
+    dr.nseg = (int32_t)((n + b->w.seg_len - 1) / b->w.seg_len);
+    dr.nslab = (int32_t)((n + AX_STAT_SLAB - 1) / AX_STAT_SLAB);
+    dr.ntb = (int32_t)(n / AX_TB);
+}
+extern "C" int axctd_batch_stream_begin(axctd_batch* b, const double* dc, const double* ampl) {
+    if (!b || !dc || !ampl) return AXCTD_ERR_ARG;
+    axctd_engine* e = b->eng;
+    if (b->streaming || b->ran) { e->err = "axctd_batch_stream_begin on a batch already in use"; return AXCTD_ERR_STATE; }
+    for (int d = 0; d < b->n; ++d) {
+        if (b->drops[d].xf_off >= 0) { e->err = "a recording that has to be halved cannot be streamed (sosfiltfilt runs backwards over the whole file)"; return AXCTD_ERR_ARG; }
+        if (!(ampl[d] > 0.0) || !(dc[d] == dc[d])) { e->err = "bad normalisation"; return AXCTD_ERR_ARG; }
+    }
+    AX_DEV(e);
+    std::vector<double> norm(2 * (size_t)b->n);
+    for (int d = 0; d < b->n; ++d) { norm[2 * d] = dc[d]; norm[2 * d + 1] = ampl[d]; }
+    if (ax_alloc_arr(b, &b->d_norm, 2 * (int64_t)b->n) || ax_h2d(e, b->d_norm, norm.data(), sizeof(double) * norm.size()) ||
+        ax_zero(e, b->w.seg_cnt, sizeof(int32_t) * (size_t)b->w.nseg_total) || ax_zero(e, b->w.seg_unc, sizeof(int32_t) * (size_t)b->w.nseg_total) ||
+        ax_sync(e)) return AXCTD_ERR_CUDA;
+    b->cap_n.resize(b->n); b->rows_done.assign(b->n, 0);
+    for (int d = 0; d < b->n; ++d) { b->cap_n[d] = b->drops[d].n_raw; ax_stream_set_len(b, d, 0); }
+    b->streaming = true; b->stream_runs = 0; b->stream_closed = false;
+    b->w.streaming = 1;
+    return AXCTD_OK;
+}
+extern "C" int axctd_batch_stream_append(axctd_batch* b, int drop, const int16_t* pcm, int64_t n) {
+    if (!b || !b->streaming || b->stream_closed || drop < 0 || drop >= b->n || n < 0 || (n > 0 && !pcm)) return AXCTD_ERR_ARG;
+    axctd_engine* e = b->eng;
+    const int64_t have = b->drops[drop].n_raw;
+    if (have + n > b->cap_n[drop]) { e->err = "recording longer than the batch was created for"; return AXCTD_ERR_CAPACITY; }
+    AX_DEV(e);
+    if (n > 0 && ax_h2d(e, b->d_pcm + b->drops[drop].pcm_off + have, pcm, sizeof(int16_t) * (size_t)n)) return AXCTD_ERR_CUDA;
+    ax_stream_set_len(b, drop, have + n);
+    return AXCTD_OK;
+}
+extern "C" int axctd_batch_stream_run(axctd_batch* b, int final_run) {
+    if (!b || !b->streaming) return AXCTD_ERR_ARG;
+    axctd_engine* e = b->eng;
+    if (b->stream_closed) { e->err = "the recording was closed by an earlier final run"; return AXCTD_ERR_STATE; }
+    AX_DEV(e);
+    b->w.streaming = final_run ? 2 : 1;
+    if (ax_h2d(e, (void*)b->w.drop, b->drops.data(), sizeof(AxDrop) * (size_t)b->n)) return AXCTD_ERR_CUDA;
+    b->in_stream_run = true;
+    int r = axctd_batch_run_async(b);
+    b->in_stream_run = false;
+    if (!r) r = axctd_batch_finish(b);
+    if (r) return r;
+    b->stream_runs++;
+    if (final_run) b->stream_closed = true;
+    return AXCTD_OK;
 }
 
 extern "C" int axctd_batch_timing(axctd_batch* b, double* total_ms, double* filter_ms, double* tone_ms) {

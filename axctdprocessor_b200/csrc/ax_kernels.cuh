@@ -98,6 +98,7 @@ __global__ void __launch_bounds__(AX_ST_THREADS) k_stats_tones(const __grid_cons
     const int64_t nsamp = dr.n_raw;                  // statistics are taken over the recording as uploaded
     const int64_t nblk = (nsamp + AX_TB - 1) / AX_TB;
     if ((int64_t)blockIdx.x * AX_ST_THREADS >= nblk) return;
+    if (w.streaming && ((int64_t)blockIdx.x + 1) * AX_ST_THREADS <= w.st[d].tb_done) return;     // summed by an earlier run
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int16_t (*stage)[32 * 72] = stage_all[warp];
     const int64_t jb = (int64_t)blockIdx.x * AX_ST_THREADS + threadIdx.x;
@@ -208,6 +209,7 @@ __global__ void __launch_bounds__(AX_ST_THREADS) k_stats_tones_mma(const __grid_
     const int64_t nsamp = dr.n_raw;                  // statistics are taken over the recording as uploaded
     const int64_t nblk = (nsamp + AX_TB - 1) / AX_TB;
     if ((int64_t)blockIdx.x * AX_STM_GROUPS * AX_ST_THREADS >= nblk) return;
+    if (w.streaming && ((int64_t)blockIdx.x + 1) * AX_STM_GROUPS * AX_ST_THREADS <= w.st[d].tb_done) return;   // summed by an earlier run
     for (int i = threadIdx.x; i < AX_TB * 8; i += AX_ST_THREADS) ptab[i] = tab8[i];
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -331,6 +333,7 @@ __global__ void k_tone_range(AxWave w, int phase_b) {
             if (st.searching && kb > ka) { lo = ch[ka].pw_off; hi = ch[kb - 1].pw_off + ch[kb - 1].np; }
         } else if (st.sm_status >= 1 && st.n_chunks > st.k0 + 1) {
             lo = ch[st.k0].pw_off + ch[st.k0].np; hi = ch[st.n_chunks - 1].pw_off + ch[st.n_chunks - 1].np;
+            if (w.streaming && st.next_sm_chunk > st.k0 + 1) lo = st.next_sm_chunk < st.n_chunks ? ch[st.next_sm_chunk].pw_off : hi;
         }
     }
     w.tone_rng[2 * d] = lo; w.tone_rng[2 * d + 1] = hi;
@@ -586,7 +589,7 @@ __global__ void __launch_bounds__(AX_FD_THREADS, 2) k_demod_fused(const __grid_c
     AxFdWarp& sm = smem.wp[warp];
     const int64_t seg = (int64_t)blockIdx.x * AX_FD_THREADS + threadIdx.x;
     int d;
-    bool active;
+    bool active, kept = false;
     AxSegGeom g;
     g.seg_start = g.seg_end = g.n_begin = g.n_stop = 0;
     int skip = 0;                                       // HEAD: samples of row 0 that lie before the chunk start
@@ -597,7 +600,10 @@ __global__ void __launch_bounds__(AX_FD_THREADS, 2) k_demod_fused(const __grid_c
         const AxDrop& dr0 = w.drop[d];
         if (dr0.cfg != cfg_id || dr0.xf_off >= 0) return;   // another launch handles this rate class / the generic kernel the halved signals
         const int64_t j = seg - dr0.seg_base;
-        active = j < dr0.nseg;
+        // streaming: segments whose records an earlier run of the growing recording left final are skipped
+        kept = w.streaming && j < w.st[d].seg_done;
+        if (w.streaming && (int64_t)blockIdx.x * AX_FD_THREADS + AX_FD_THREADS - 1 - dr0.seg_base < w.st[d].seg_done) return;
+        active = j < dr0.nseg && !kept;
         if (active) g = ax_seg_geom(dr0, w.cfg[cfg_id], w.seg_len, j);
     } else {
         const int64_t cg = seg < n_items ? seg : n_items - 1;
@@ -852,7 +858,7 @@ __global__ void __launch_bounds__(AX_FD_THREADS, 2) k_demod_fused(const __grid_c
             if (count > w.seg_cap) { w.flags[AX_FLAG_CAP] = 1; ax_raise(w.st[d], AXCTD_DROP_CAPACITY, -1); count = w.seg_cap; }   // crossings were dropped: fail the drop
             w.seg_cnt[seg] = count;
             w.seg_unc[seg] = unc;
-        } else { w.seg_cnt[seg] = 0; w.seg_unc[seg] = 0; }
+        } else if (!kept) { w.seg_cnt[seg] = 0; w.seg_unc[seg] = 0; }
     } else if (active) {
         w.head_cnt[seg] = count > out_cap ? -1 : count;
         w.head_unc[seg] = unc;
@@ -1183,6 +1189,7 @@ __global__ void __launch_bounds__(128) k_bits_chunk(AxWave w, int phase) {
     const AxState& st = w.st[d];
     const int k = (int)(cg - dr.chunk_base);
     if (st.sm_status < 1 || st.nedges_total == 0 || k < st.k0 || k >= st.n_chunks || k >= dr.chunk_cap) return;
+    if (w.streaming && k < st.k_done && (phase == 1 || ax_scale_is_final(w, st))) return;     // decided by an earlier run
     const AxChunk& ch = w.chunk[cg];
     const int nb = ch.n_edges - 1;
     if (nb <= 0) return;
@@ -1302,8 +1309,10 @@ __global__ void __launch_bounds__(32) k_verify_warp(AxWave w) {
                 if (code == 1) { ax_raise(st, ch[k].err, k); st.n_chunks = k + 1; st.chain_from = k + 1; st.chain_end = 1; }
                 else if (code == 2) {
                     const double sf = (double)ch[k].s + c.fs / (double)c.bitrate;       // AXCTDprocessor.py:331
-                    if (!((double)dr.n - sf < 4.0 * c.n_power)) ax_raise(st, AXCTD_DROP_FLOAT_INDEX, k + 1);
-                    st.n_chunks = k + 1; st.chain_from = k + 1; st.chain_end = 1;
+                    const bool ends = (double)dr.n - sf < 4.0 * c.n_power;
+                    if (!ends) ax_raise(st, AXCTD_DROP_FLOAT_INDEX, k + 1);
+                    if (ends && w.streaming == 1) { st.n_chunks = k; st.chain_from = k; st.chain_end = 1; }   // the file may end here: a later run decides
+                    else { st.n_chunks = k + 1; st.chain_from = k + 1; st.chain_end = 1; }
                 } else { st.n_fixups++; st.chain_from = k + 1; st.chain_dirty = 1; w.flags[AX_FLAG_DIRTY] = 1; }
             }
             return;
@@ -1343,6 +1352,7 @@ __global__ void __launch_bounds__(32) k_plan_tones_warp(AxWave w) {
     const AxCfg& c = w.cfg[dr.cfg];
     AxChunk* ch = w.chunk + dr.chunk_base;
     const int k0 = st.k0 + 1, k1 = st.n_chunks;
+    const int nsm = st.next_sm_chunk;          // (iterations the state machine has been through keep their records: streaming)
     int32_t pc = ch[st.k0].pw_off + ch[st.k0].np;
     bool small = false;
     for (int kb = k0; kb < k1; kb += 32) {
@@ -1356,7 +1366,7 @@ __global__ void __launch_bounds__(32) k_plan_tones_warp(AxWave w) {
         if (k < k1 && lane <= stop) {
             AxChunk& q = ch[k];
             q.pw_off = pc + pre; q.np = lane == stop ? 0 : np;
-            q.status = 0; q.n_rows = 0; q.n_hex = 0; q.frame_begin = q.frame_end = 0; q.scale = c.scale0; q.mean7500 = ax_nan();
+            if (k >= nsm) { q.status = 0; q.n_rows = 0; q.n_hex = 0; q.frame_begin = q.frame_end = 0; q.scale = c.scale0; q.mean7500 = ax_nan(); }
             if (lane < stop && np < 10) small = true;
         }
         if (ball) {
@@ -1426,7 +1436,8 @@ __global__ void __launch_bounds__(32) k_chain_warp(AxWave w) {
     int64_t entry = -1, span = (int64_t)c.chunk_len / 37;
     int n_chunks_out = -1;
     for (;; ++k) {
-        if (dr.n - s < 4 * (int64_t)c.n_power) { n_chunks_out = k; break; }
+        if (w.streaming == 1) { if (s + c.chunk_len >= dr.n) { n_chunks_out = k; break; } }      // not complete yet: a later run takes it
+        else if (dr.n - s < 4 * (int64_t)c.n_power) { n_chunks_out = k; break; }
         if (k >= dr.chunk_cap) { if (lane == 0) { ax_raise(st, AXCTD_DROP_CAPACITY, k); w.flags[AX_FLAG_CAP] = 1; } n_chunks_out = k; break; }
         int64_t e = s + c.chunk_len;
         if (e >= dr.n) e = dr.n - 1;
@@ -1567,6 +1578,7 @@ __global__ void __launch_bounds__(128) k_scale_block(AxWave w) {
     __shared__ int s_found, s_k;
     __shared__ int64_t s_a, s_hi;
     const int nbins = c.n_hist_edges - 1;
+    if (ax_scale_is_final(w, st)) { ax_scale_spread(w, d, threadIdx.x, blockDim.x); return; }      // (uniform over the CTA)
     if (threadIdx.x == 0) {
         ax_scale_reset(w, d);
         int k = -1; int64_t a = 0, hi = 0;

@@ -24,8 +24,16 @@ AX_HDN inline void ax_plan0_item(const AxWave& w, int64_t d) {
     int64_t s = 0;
     int32_t pc = 0;
     int par = 1;
+    if (w.streaming) {
+        // a growing recording: the grid is extended by the iterations that have become complete; once the pulse is
+        // found the chunk chain owns the iterations from k0 on
+        if (st.sm_status >= 1 || st.status != 0) return;
+        k = st.n_fixed;
+        if (k > 0) { s = ch[k - 1].e; pc = ch[k - 1].pw_off + ch[k - 1].np; par = st.par_levels; }
+    }
     while (true) {
-        if (dr.n - s < 4 * (int64_t)c.n_power) break;
+        if (w.streaming == 1) { if (s + c.chunk_len >= dr.n) break; }      // :299 would cut it short: not complete yet
+        else if (dr.n - s < 4 * (int64_t)c.n_power) break;
         if (k >= dr.chunk_cap) { ax_raise(st, AXCTD_DROP_CAPACITY, k); w.flags[AX_FLAG_CAP] = 1; break; }
         int64_t e = s + c.chunk_len;
         if (e >= dr.n) e = dr.n - 1;
@@ -44,6 +52,7 @@ AX_HDN inline void ax_plan0_item(const AxWave& w, int64_t d) {
     st.n_chunks = k;
     st.par_levels = par;
     st.searching = k > 0 ? 1 : 0;
+    if (w.streaming && st.next_sm_chunk >= k) st.searching = 0;      // nothing new to look at in this run
 }
 
 // power_inds of one chunk (AXCTDprocessor.py:357)
@@ -71,7 +80,9 @@ AX_HDN inline void ax_plan_tones_item(const AxWave& w, int64_t d) {
     for (int k = st.k0 + 1; k < st.n_chunks; ++k) {
         AxChunk& q = ch[k];
         q.pw_off = pc; q.np = ax_grid_count(q.s, q.e, c);
-        q.status = 0; q.n_rows = 0; q.n_hex = 0; q.frame_begin = q.frame_end = 0; q.scale = c.scale0; q.mean7500 = ax_nan();
+        if (k >= st.next_sm_chunk) {                      // (iterations the state machine has been through keep their records: streaming)
+            q.status = 0; q.n_rows = 0; q.n_hex = 0; q.frame_begin = q.frame_end = 0; q.scale = c.scale0; q.mean7500 = ax_nan();
+        }
         if (pc + q.np > dr.pw_cap) { ax_raise(st, AXCTD_DROP_CAPACITY, k); w.flags[AX_FLAG_CAP] = 1; q.np = 0; st.n_chunks = k; break; }
         if (q.np < 10) st.par_levels = 0;
         pc += q.np;
@@ -97,6 +108,7 @@ AX_HD bool ax_tone_slot_active(const AxWave& w, int64_t slot, int phase_b, int* 
     else {
         if (st.sm_status < 1 || st.n_chunks <= st.k0 + 1) return false;
         lo = ch[st.k0].pw_off + ch[st.k0].np; hi = ch[st.n_chunks - 1].pw_off + ch[st.n_chunks - 1].np;
+        if (w.streaming && st.next_sm_chunk > st.k0 + 1) lo = st.next_sm_chunk < st.n_chunks ? ch[st.next_sm_chunk].pw_off : hi;
     }
     return i >= lo && i < hi;
 }
@@ -136,6 +148,7 @@ AX_HDN inline void ax_toneblock_item(const AxWave& w, int64_t tbg) {
     const AxDrop& dr = w.drop[d];
     const int64_t j = tbg - dr.tb_base;
     if (j >= dr.ntb || (w.only_xf && dr.xf_off < 0)) return;       // (k_stats_tones already did the int16 drops)
+    if (w.streaming && j < w.st[d].tb_done) return;                // summed by an earlier run of the growing recording
     const AxCfg& c = w.cfg[dr.cfg];
     const AxSrc x = ax_src(w, dr);
     double a[6] = {0, 0, 0, 0, 0, 0};
@@ -228,6 +241,7 @@ AX_HD bool ax_level_range(const AxWave& w, const AxState& st, int phase_b, int* 
         return st.searching && *khi > *klo;
     }
     *klo = st.k0 + 1; *khi = st.n_chunks;
+    if (w.streaming && st.next_sm_chunk > *klo) *klo = st.next_sm_chunk;      // a growing recording: the new iterations only
     return st.sm_status >= 1 && *khi > *klo;
 }
 
@@ -439,6 +453,7 @@ AX_HD int64_t ax_emit_canon_pos(const AxWave& w, const AxDrop& dr, const AxChunk
 }
 
 AX_HD bool ax_emit_active(const AxWave& w, const AxDrop& dr, const AxState& st, int k) {
+    if (w.streaming && k < st.k_done) return false;      // edges of an earlier run of the growing recording: final
     return !(st.sm_status < 1 || k < st.k0 || k >= st.n_chunks || k >= dr.chunk_cap || st.nedges_total == 0);
 }
 
@@ -540,6 +555,10 @@ AX_HD bool ax_scale_threshold(const AxCfg& c, const int* hist, int64_t npts, dou
     *thr = ax_div(ax_add(ctr[first], ctr[last]), 2.0);
     return true;
 }
+// streaming: the calibration was made in an iteration that an earlier run already closed
+AX_HD bool ax_scale_is_final(const AxWave& w, const AxState& st) {
+    return w.streaming && st.header_read[0] && st.k1 >= 0 && st.k1 < st.k_done;
+}
 AX_HD void ax_scale_reset(const AxWave& w, int d) {
     AxState& st = w.st[d];
     st.scale = w.cfg[w.drop[d].cfg].scale0; st.k1 = -1; st.header_read[0] = 0; st.header_chunk[0] = -1; st.scale_switch_bit = st.nbits_total;
@@ -559,6 +578,7 @@ AX_HDN inline void ax_scale_item(const AxWave& w, int64_t d) {
     const AxDrop& dr = w.drop[d];
     const AxCfg& c = w.cfg[dr.cfg];
     AxState& st = w.st[d];
+    if (ax_scale_is_final(w, st)) { ax_scale_spread(w, (int)d, 0, 1); return; }
     ax_scale_reset(w, (int)d);
     if (st.sm_status < 1 || st.nedges_total == 0) return;
     int k = -1; int64_t a = 0, hi = 0;
@@ -681,6 +701,7 @@ AX_HDN inline void ax_bits_item(const AxWave& w, int64_t slot, int phase) {
     const int64_t j = slot - dr0.edge_base;
     if (j >= st.nbits_total || st.sm_status < 1) return;
     const int k = ax_chunk_of_bit(w.chunk + dr0.chunk_base, st.k0, st.n_chunks, j);
+    if (w.streaming && (k < st.k_done) && (phase == 1 || ax_scale_is_final(w, st))) return;     // decided by an earlier run
     AxBitFix fx;
     if (ax_bits_need(w, d, k, slot, phase, &fx)) {
         const AxDrop& dr = w.drop[fx.d];

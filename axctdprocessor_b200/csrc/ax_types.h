@@ -190,6 +190,10 @@ struct AxState {
     double md_z[4], md_t[4], md_c[4];
     uint8_t md_zv[4], md_tv[4], md_cv[4];
     int32_t pad5;
+    // streaming decode (axctd_batch_stream_*): what the previous run left final
+    int32_t seg_done;            // leading segments of the continuous pass whose crossing records are final
+    int32_t k_done;              // leading run() iterations whose edges / bits are final
+    int64_t tb_done;             // leading tone blocks whose sums are final
 };
 
 struct AxWave {
@@ -244,6 +248,8 @@ struct AxWave {
     int32_t tone_direct;
     int32_t pa_lo, pa_hi;        // fixed-grid chunk range of the current detection round
     int32_t force_exact;
+    int32_t streaming;           // 0: whole recordings; 1: a growing recording, only iterations that are complete are
+                                 // decoded (AXCTDprocessor.py:293-304 with the end of the file still unknown); 2: its last run
     int32_t* flags;              // [0] = any chain dirty, [1] = any capacity error
 };
 

@@ -337,6 +337,21 @@ class Batch:
         """Fill drop i with n samples of ``src``'s drop ``src_drop`` (already on the device) from ``src_offset`` on."""
         self._check(self.lib.axctd_batch_copy_from(self.h, i, src.h, src_drop, int(src_offset), int(n)), "axctd_batch_copy_from")
 
+    # ---- a growing recording (include/axctd.h, "decoded as it arrives")
+    def stream_begin(self, dc, ampl):
+        """Switch the batch to streaming: every drop starts empty (its length at creation is the most it can take)
+        and is normalised with the given (dc, ampl) instead of whole-file statistics."""
+        dc = np.ascontiguousarray(np.broadcast_to(np.asarray(dc, dtype=np.float64), (self.n,)))
+        am = np.ascontiguousarray(np.broadcast_to(np.asarray(ampl, dtype=np.float64), (self.n,)))
+        self._check(self.lib.axctd_batch_stream_begin(self.h, _dptr(dc), _dptr(am)), "axctd_batch_stream_begin")
+
+    def stream_append(self, i: int, pcm: np.ndarray):
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16).reshape(-1)
+        self._check(self.lib.axctd_batch_stream_append(self.h, i, pcm.ctypes.data, pcm.size), "axctd_batch_stream_append")
+
+    def stream_run(self, final: bool = False):
+        self._check(self.lib.axctd_batch_stream_run(self.h, 1 if final else 0), "axctd_batch_stream_run")
+
     def device_ptr(self, i: int) -> int:
         p = C.c_void_p()
         self._check(self.lib.axctd_batch_device_pcm(self.h, i, C.byref(p)), "axctd_batch_device_pcm")

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define AXCTD_ABI_VERSION 2
+#define AXCTD_ABI_VERSION 3
 #define AXCTD_MAX_SECTIONS 6
 
 /* ---- return codes of API calls ---------------------------------------- */
@@ -225,6 +225,23 @@ int  axctd_batch_run(axctd_batch* b);
 /* Same, but returns after enqueueing the device work; pair with _finish. */
 int  axctd_batch_run_async(axctd_batch* b);
 int  axctd_batch_finish(axctd_batch* b);
+/* ---- a growing recording, decoded as it arrives ------------------------------------------------------------
+ * The reference's run() is a loop over 2 s iterations with a `keepgoing` flag and per-iteration result lists
+ * (AXCTDprocessor.py:119, :283-338, :612), the shape a live receiver needs.  These three calls run that loop one
+ * batch of new iterations at a time: the drops of `b` were created with the most samples they can take
+ * (axctd_batch_create), _append adds samples as they arrive (only these cross the PCIe link), and every _run decodes
+ * the iterations that have become complete -- start + pointsperloop inside the data, so the end-of-file cut of
+ * :299-300 cannot apply to them -- on top of the device state the earlier runs left: tone block sums, filtering,
+ * crossings and bit windows cover the new samples only, edges and bit decisions the new iterations only.  The last
+ * run (final_run != 0) applies the end-of-file rules of :295-300 to what is left.  After each run the usual getters
+ * (axctd_batch_summary / _rows / _chunks / _frames / _bits / _edges / _power) report everything decoded so far.
+ * readAXCTDwavfile normalises with the mean and the peak of the WHOLE file (AXCTDprocessor.py:55-57), which a live
+ * decoder cannot know: the caller fixes them (dc[i], ampl[i] per drop, e.g. from the first seconds or from the
+ * receiver's scaling), and the result is the reference's for the recording normalised with those two numbers.
+ * Recordings above 50 kHz (config decimate == 2) cannot be streamed: AXCTDprocessor.py:60-62 filters backwards. */
+int  axctd_batch_stream_begin(axctd_batch* b, const double* dc, const double* ampl);
+int  axctd_batch_stream_append(axctd_batch* b, int drop, const int16_t* pcm, int64_t n);
+int  axctd_batch_stream_run(axctd_batch* b, int final_run);
 /* Device milliseconds of the last run (CUDA events on the engine stream),
  * and of the dominant filter kernel inside it. */
 int  axctd_batch_timing(axctd_batch* b, double* total_ms, double* filter_ms, double* tone_ms);

@@ -149,3 +149,60 @@ def check_rows_against_oracle(res, op):
     assert len(res.chunks) == len(op.trace)
     for c, t in zip(res.chunks, op.trace):
         assert (c["s"], c["e"], c["status"], c["n_rows"], c["n_hex"]) == (t["s"], t["e"], t["status"], t["nrows"], t["nhex"])
+
+
+def oracle_prefix_normalised(pcm, fs, norm_seconds=2.0, settings=None, triggerrange=None):
+    """The oracle over a recording normalised with the mean and the peak of its first norm_seconds (the streaming
+    decoder's fixed normalisation) instead of the whole file's (AXCTDprocessor.py:55-57)."""
+    from axctdprocessor_b200.stream import prefix_normalisation
+    from oracle import axctd_oracle as ao
+    dc, ampl = prefix_normalisation(pcm[:int(norm_seconds * fs)])
+    x = (np.asarray(pcm, dtype=np.float64) - dc) / ampl
+    return ao.OracleProcessor(x, fs, settings=settings, triggerrange=triggerrange).run(), (dc, ampl)
+
+
+def check_streaming_against_oracle(eng, pcm, fs, seed=0, settings=None, triggerrange=None, piece_s=(0.3, 3.1), norm_seconds=2.0):
+    """Feed the recording to StreamingDecoder in pieces of random length, poll after every piece and hold
+    (a) every poll's rows to the oracle's per-iteration lists (AXCTDprocessor.py:612) of exactly the iterations that
+    poll closed, (b) the finished result to the oracle as a whole.  Returns the decoder's per-run records."""
+    from axctdprocessor_b200.stream import StreamingDecoder
+    op, _ = oracle_prefix_normalised(pcm, fs, norm_seconds, settings, triggerrange)
+    cum = np.concatenate([[0], np.cumsum([t["nrows"] for t in op.trace])]).astype(int)     # kept rows before iteration k
+    sd = StreamingDecoder(fs, settings=settings, triggerrange=triggerrange, engine=eng, max_seconds=len(pcm) / fs + 5.0,
+                          norm_seconds=norm_seconds)
+    rng = np.random.default_rng(seed)
+    pos, k_prev, polls_with_rows = 0, 0, 0
+    try:
+        while pos < len(pcm):
+            n = int(rng.integers(int(piece_s[0] * fs), int(piece_s[1] * fs)))
+            sd.push(pcm[pos:pos + n]); pos += n
+            new = sd.poll()
+            if sd.last is None:
+                assert new is None
+                continue
+            k_now = int(sd.last.summary.n_chunks)
+            assert k_prev <= k_now <= len(op.trace)
+            # only complete iterations are decoded, and they are the oracle's
+            for k in range(k_prev, k_now):
+                c, t = sd.last.chunks[k], op.trace[k]
+                assert (c["s"], c["e"], c["status"], c["n_rows"], c["n_hex"]) == (t["s"], t["e"], t["status"], t["nrows"], t["nhex"]), k
+                assert c["e"] < sd.batch.summary(0).numpoints
+            lo, hi = cum[k_prev], cum[k_now]
+            assert (0 if new is None else len(new)) == hi - lo, (k_prev, k_now)
+            if new is not None:
+                polls_with_rows += 1
+                for key, name in (("time_s", "time"), ("depth", "depth"), ("temperature", "temperature"),
+                                  ("conductivity", "conductivity"), ("salinity", "salinity")):
+                    np.testing.assert_allclose(new[key], np.asarray(getattr(op, name)[lo:hi], dtype=np.float64), rtol=1e-6, atol=0, equal_nan=True)
+            k_prev = k_now
+        r, rest = sd.finish_rows()
+        assert len(rest) == cum[-1] - cum[k_prev]
+        out = dict(result=r, bits=sd.batch.bits(0), edges=sd.batch.edges(0), power=sd.batch.power(0))
+        check_against_oracle(out, op)
+        assert polls_with_rows >= 3
+        return sd.runs
+    finally:
+        eng_keep = sd.eng
+        sd._own = False
+        sd.close()
+        assert eng_keep is eng

@@ -305,24 +305,48 @@ def test_random_batch_matches_oracle(eng):
         check_against_oracle(out, ao.process_pcm(p, s.fs))
 
 
-def test_streaming_decoder_ends_at_the_batch_result(eng):
-    """stream.StreamingDecoder on the device: provisional polls, finish() = batch decode of the whole recording
-    (which the tests above hold against the oracle and the reference fixtures)."""
-    from axctdprocessor_b200 import batch as axbatch, stream as axstream
-    spec = synth.DropSpec(fs=48000, duration_s=75.0, seed=4242, snr_db=25.0)
-    pcm = np.ascontiguousarray(synth.generate_drop(spec))
-    sd = axstream.StreamingDecoder(spec.fs, engine=eng, min_new_seconds=1.0)
-    seen = 0
-    step = int(5.0 * spec.fs)
+@pytest.mark.parametrize("kw,settings,trig", [
+    (dict(fs=44100, duration_s=64.0, seed=77, snr_db=15.0), None, None),
+    (dict(fs=48000, duration_s=75.0, seed=4242, snr_db=25.0), None, None),
+    (dict(fs=48000, duration_s=56.0, seed=78, snr_db=25.0), {"usebandpass": True, "refreshrate": 1.0}, None),
+    (dict(fs=44100, duration_s=64.0, seed=14, snr_db=25.0), None, [30, 41]),
+])
+def test_streaming_polls_match_oracle(eng, kw, settings, trig):
+    """stream.StreamingDecoder on the device (axctd_batch_stream_*): the recording arrives in pieces of random
+    length; every poll decodes only the iterations that became complete and its rows are held to the oracle's
+    per-iteration lists on the prefix-normalised recording; the finished result is held to the oracle as a whole
+    (bits, edges, chunk chain, frames, unrounded values)."""
+    from parity_util import check_streaming_against_oracle
+    spec = synth.DropSpec(**kw)
+    check_streaming_against_oracle(eng, np.ascontiguousarray(synth.generate_drop(spec)), spec.fs, seed=spec.seed, settings=settings,
+                                   triggerrange=trig)
+
+
+def test_streaming_work_per_poll_does_not_grow_with_the_prefix(eng):
+    """A 10-minute drop polled once a second: the filter pass of a poll covers the new second only, so its device
+    time late in the recording stays what it was early on (a whole-prefix re-decode grows linearly), and the finished
+    result equals the oracle's on the prefix-normalised recording."""
+    from axctdprocessor_b200.stream import StreamingDecoder
+    from parity_util import oracle_prefix_normalised
+    spec = synth.DropSpec(fs=44100, duration_s=600.0, seed=4711, snr_db=25.0)
+    g = eng.batch([int(round(spec.duration_s * spec.fs))], [eng.config(spec.fs)])
+    g.synth_fill(0, spec)
+    pcm = g.download(0)
+    g.close()
+    sd = StreamingDecoder(spec.fs, engine=eng, max_seconds=620.0, norm_seconds=2.0)
+    step = spec.fs
     for a in range(0, len(pcm), step):
         sd.push(pcm[a:a + step])
-        new = sd.poll()
-        if new is not None:
-            seen += len(new)
-    got = sd.finish()
-    assert seen > 0
-    ref = axbatch.process_drops(eng, [pcm], [spec.fs])[0]
-    assert got.status == 0 and ref.status == 0 and np.array_equal(got.rows, ref.rows) and len(ref.rows) > 500
+        sd.poll()
+    r = sd.finish()
+    runs = sd.runs
+    early = np.median([x["filter_ms"] for x in runs[60:120]])
+    late = np.median([x["filter_ms"] for x in runs[-61:-1]])
+    assert late < 2.0 * early + 0.05, (early, late)
+    op, _ = oracle_prefix_normalised(pcm, spec.fs)
+    check_rows_against_oracle(r, op)
+    sd._own = False
+    sd.close()
 
 
 def test_concurrent_decoder_matches_single_batch(eng):
