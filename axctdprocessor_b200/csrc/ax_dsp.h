@@ -821,7 +821,8 @@ AX_HDN inline void ax_unc_fin_item(const AxWave& w, int64_t d) {
 AX_HD double ax_decim_ext(const AxWave& w, const AxDrop& dr, const AxCfg& c, const AxState& st, int64_t e) {
     const int16_t* x = w.pcm + dr.pcm_off;
     const int64_t N = dr.n_raw, P = c.dpad;
-#define AX_U(n) ax_div(ax_sub((double)x[(n)], st.dc), st.ampl_d)
+    // (x - dc) / ampl of AXCTDprocessor.py:57 as one FMA with the reciprocal, the form the staged kernel uses as well
+#define AX_U(n) ax_fma((double)x[(n)], st.inv_ampl, -ax_mul(st.dc, st.inv_ampl))
     if (e < P) return ax_sub(ax_mul(2.0, AX_U(0)), AX_U(P - e));                 // 2 x[0] - x[P-e]
     if (e < P + N) return AX_U(e - P);
     return ax_sub(ax_mul(2.0, AX_U(N - 1)), AX_U(N - 2 - (e - P - N)));         // 2 x[N-1] - x[N-2-i]

@@ -701,7 +701,21 @@ extern "C" int axctd_batch_create(axctd_engine* e, int n_drops, const int64_t* n
     b->drops.resize(n_drops);
     int64_t pcm_off = 0, zc_off = 0, edge_off = 0, tb_off = 0, xf_off = 0, fwd_off = 0;
     int32_t ntb_max = 0, dseg_off = 0;
-    const int64_t DL = 8192;                       // samples per decimation segment
+    // samples per decimation segment: one wave of (SMs x 8 warps x 32) lanes over the recordings that are halved, but
+    // not below 2048 (the warm-up overlap is some 650 samples)
+    int64_t DL = 8192;
+    {
+        int64_t dec_total = 0;
+        for (int d = 0; d < n_drops; ++d) if (e->cfgs[config_id[d]].decimate == 2) dec_total += n_samples[d];
+        int sms = 148;
+#ifndef AXCTD_EMU
+        { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, e->device) == cudaSuccess && v > 0) sms = v; }
+#endif
+        const int64_t lanes = (int64_t)sms * 8 * 32;
+        DL = ((dec_total / lanes + 1 + 63) / 64) * 64;
+        if (DL < 2048) DL = 2048;
+        if (DL > 65536) DL = 65536;
+    }
     w.dseg_len = (int32_t)DL;
     int32_t seg_off = 0, slab_off = 0, tile_off = 0, chunk_off = 0, pw_off = 0, frame_off = 0;
     for (int d = 0; d < n_drops; ++d) {
@@ -717,8 +731,8 @@ extern "C" int axctd_batch_create(axctd_engine* e, int n_drops, const int64_t* n
             if (n_raw < 2 * (int64_t)c.dpad + 2) { e->err = "recording too short to decimate"; axctd_batch_destroy(b); return AXCTD_ERR_ARG; }
             const int64_t E = n_raw + 2 * (int64_t)c.dpad;
             dr.xf_off = xf_off; xf_off += ((n + 63) / 64) * 64 + 64;
-            dr.fwd_off = fwd_off; fwd_off += E + 8;
-            dr.ndseg = (int32_t)((E + DL - 1) / DL); dseg_off += dr.ndseg;
+            dr.fwd_off = fwd_off; fwd_off += ((E + 8 + 1) / 2) * 2;                  // (even: 16-byte rows of the backward pass)
+            dr.ndseg = (int32_t)((E + DL - 1) / DL); dseg_off += ((dr.ndseg + 31) / 32) * 32;   // a warp of k_decim_fused stays inside one drop
         }
         dr.seg_base = seg_off; dr.nseg = (int32_t)((n + L - 1) / L); seg_off += ((dr.nseg + 127) / 128) * 128;
         dr.slab_base = slab_off; dr.nslab = (int32_t)((n_raw + AX_STAT_SLAB - 1) / AX_STAT_SLAB); slab_off += dr.nslab;
@@ -976,8 +990,24 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
     if (!streaming) { AX_LAUNCH(e, k_stats_fin, n, w); }        // (streaming: the normalisation was fixed by the caller)
     const bool any_dec = b->dseg_total > 0;
     if (any_dec) {       // recordings above 50 kHz: halve them on the device (AXCTDprocessor.py:60-62)
-        AX_LAUNCH(e, k_decim, b->dseg_total, w, 0);
-        AX_LAUNCH(e, k_decim, b->dseg_total, w, 1);
+#ifndef AXCTD_EMU
+        bool dfused = e->opt_filter_variant == 0;
+        int dpar = -1;
+        for (const AxDrop& dr : b->drops) if (dr.xf_off >= 0) {
+            const AxCfg& c = e->cfgs[dr.cfg];
+            if (!ax_decim_fused_ok(c) || (dpar >= 0 && dpar != (c.dpad & 1))) dfused = false;
+            dpar = c.dpad & 1;
+        }
+        if (dfused) {
+            ax_launch_decim_fused<0>(w, b->dseg_total, dpar, e->stream, e->device);
+            ax_launch_decim_fused<1>(w, b->dseg_total, dpar, e->stream, e->device);
+            e->launches += 2;
+        } else
+#endif
+        {
+            AX_LAUNCH(e, k_decim, b->dseg_total, w, 0);
+            AX_LAUNCH(e, k_decim, b->dseg_total, w, 1);
+        }
         AX_LAUNCH(e, k_decim_fin, n, w);
 #ifndef AXCTD_EMU
         w.only_xf = 1;
@@ -1016,8 +1046,12 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
     if (scan_only) {
     } else if (fused) {
         // one launch per rate class in use (CTAs of the other classes exit at once)
-        for (int ci : used_cfg) { ax_launch_demod_fused_any<false>(w, e->cfgs[ci], ci, 0, e->stream, e->device, e->opt_ws, e->opt_fir_first, e->opt_bulk); e->launches++; }
-        if (any_dec) { w.only_xf = 1; AX_LAUNCH(e, k_filter, (int64_t)w.nseg_total, w); w.only_xf = 0; }
+        for (int ci : used_cfg) {
+            const bool has_i16 = std::any_of(b->drops.begin(), b->drops.end(), [&](const AxDrop& d) { return d.cfg == ci && d.xf_off < 0; });
+            const bool has_f64 = std::any_of(b->drops.begin(), b->drops.end(), [&](const AxDrop& d) { return d.cfg == ci && d.xf_off >= 0; });
+            if (has_i16) { ax_launch_demod_fused_any<false>(w, e->cfgs[ci], ci, 0, e->stream, e->device, e->opt_ws, e->opt_fir_first, e->opt_bulk); e->launches++; }
+            if (has_f64) { ax_launch_demod_fused_f64(w, e->cfgs[ci], ci, e->stream, e->device); e->launches++; }      // halved recordings
+        }
     } else
 #else
     if (!scan_only)

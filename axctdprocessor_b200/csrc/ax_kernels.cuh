@@ -581,7 +581,11 @@ static_assert(AX_FD_RINGQ * 32 * sizeof(float4) == 16384, "ring offsets assume 1
 // (UBLKCP) per row, straight into its own staging row, completing on the stage's mbarrier (lane 0 announces the
 // bytes with arrive.expect_tx, all lanes wait on the phase parity) -- in place of eight 16-byte LDGSTS per lane with
 // their shuffled source addresses and commit / wait groups.
-template <int NSEC, int NPCM, bool HEAD, bool FAST, bool BULK = false>
+// F64: the drop's samples are the halved double-precision signal (w.xf, recordings above 50 kHz) instead of int16:
+// every lane reads its own 512-byte row straight from global memory, two samples per 16-byte load (whole lines are
+// consumed, and the next row's four lines are prefetched), because staging 512 bytes per lane and stage would not
+// leave room for two CTAs per SM; everything after the sample fetch is the same code.
+template <int NSEC, int NPCM, bool HEAD, bool FAST, bool BULK = false, bool F64 = false>
 __global__ void __launch_bounds__(AX_FD_THREADS, 2) k_demod_fused(const __grid_constant__ AxWave w, const __grid_constant__ AxWinTab tab, int cfg_id, int64_t n_items) {
     extern __shared__ __align__(16) unsigned char ax_smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -598,7 +602,7 @@ __global__ void __launch_bounds__(AX_FD_THREADS, 2) k_demod_fused(const __grid_c
     if (!HEAD) {
         d = w.seg_drop[(int64_t)blockIdx.x * AX_FD_THREADS];
         const AxDrop& dr0 = w.drop[d];
-        if (dr0.cfg != cfg_id || dr0.xf_off >= 0) return;   // another launch handles this rate class / the generic kernel the halved signals
+        if (dr0.cfg != cfg_id || (dr0.xf_off >= 0) != F64) return;   // another launch handles this rate class / the halved signals
         const int64_t j = seg - dr0.seg_base;
         // streaming: segments whose records an earlier run of the growing recording left final are skipped
         kept = w.streaming && j < w.st[d].seg_done;
@@ -633,6 +637,7 @@ __global__ void __launch_bounds__(AX_FD_THREADS, 2) k_demod_fused(const __grid_c
     for (int o = 16; o > 0; o >>= 1) Tmax = max(Tmax, __shfl_xor_sync(0xffffffffu, Tmax, o));
     const int16_t* xdrop = w.pcm + dr.pcm_off;
     const unsigned long long xrow = (unsigned long long)(xdrop + g.n_begin);      // 16-byte aligned
+    const double* xfrow = F64 ? w.xf + dr.xf_off + g.n_begin : nullptr;           // (n_begin and xf_off are multiples of 64)
     for (int k = lane; k < AX_WIN_TAPS; k += 32) sm.tab[k] = tab.t[k];
     // ---- cascade constants (Butterworth form, see AxFilt::filter)
     double z0[NSEC], z1[NSEC], a1[NSEC], a2[NSEC], sg[NSEC];
@@ -663,7 +668,12 @@ __global__ void __launch_bounds__(AX_FD_THREADS, 2) k_demod_fused(const __grid_c
         if (lane == 0) { ax_mbar_init(&sm.mbar[0], 1u); ax_mbar_init(&sm.mbar[1], 1u); ax_mbar_init_fence(); }
     }
     auto issue = [&](int t, int s) {
-        if constexpr (BULK) {
+        if constexpr (F64) {
+            if (t < T) {
+#pragma unroll
+                for (int l = 0; l < 4; ++l) asm volatile("prefetch.global.L1 [%0];" ::"l"(xfrow + 64 * (long long)t + 16 * l));
+            }
+        } else if constexpr (BULK) {
             const bool mine = t < T;
             const unsigned nact = (unsigned)__popc(__ballot_sync(0xffffffffu, mine));
             if (lane == 0) ax_mbar_expect_tx(&sm.mbar[s], 128u * nact);
@@ -685,7 +695,9 @@ __global__ void __launch_bounds__(AX_FD_THREADS, 2) k_demod_fused(const __grid_c
     for (int t = 0; t <= Tmax; ++t) {
         unsigned long long Scur = 0ull;
         if (t < Tmax) {
-            if constexpr (BULK) {
+            if constexpr (F64) {
+                if (t + 1 < Tmax) issue(t + 1, 0);
+            } else if constexpr (BULK) {
                 if (t + 1 < Tmax) issue(t + 1, (t + 1) & 1);
                 ax_mbar_wait(&sm.mbar[t & 1], (unsigned)((t >> 1) & 1));
             } else {
@@ -710,7 +722,8 @@ __global__ void __launch_bounds__(AX_FD_THREADS, 2) k_demod_fused(const __grid_c
                 // The sections run skewed by one sample each (section s works on sample n - s), so every step
                 // holds NSEC independent recurrences.
                 double pipe[NSEC];                   // pipe[s]: output of section s-1 for the sample section s takes next
-                int4 q = rp[0];
+                int4 q = F64 ? make_int4(0, 0, 0, 0) : rp[0];
+                double2 xq = make_double2(0.0, 0.0);
                 if (!FAST || t == 0) {
                     // per sample the arithmetic is exactly AxFilt::filter's
                     double yl[6];                    // FAST: outputs 58..63 of the row
@@ -722,11 +735,16 @@ __global__ void __launch_bounds__(AX_FD_THREADS, 2) k_demod_fused(const __grid_c
                             if (m >= 0 && m < 64) {
                                 double tt;
                                 if (s == 0) {
+                                    if constexpr (F64) {
+                                        if ((m & 1) == 0) xq = __ldg(reinterpret_cast<const double2*>(xfrow + 64 * (long long)t + m));
+                                        tt = fma((m & 1) ? xq.y : xq.x, k0, k1);
+                                    } else {
                                     if ((m & 7) == 0 && m > 0) q = rp[m >> 3];
                                     const int wdv = ((m & 7) >> 1) == 0 ? q.x : ((m & 7) >> 1) == 1 ? q.y : ((m & 7) >> 1) == 2 ? q.z : q.w;
                                     const short2 xs2 = *reinterpret_cast<const short2*>(&wdv);   // I2F.F64.S16 on either half
                                     tt = fma((m & 1) ? (double)xs2.y : (double)xs2.x, k0, k1);
                                     if (HEAD && t == 0 && m < skip) tt = 0.0;      // before the chunk start: keeps the state at zero
+                                    }
                                 } else tt = pipe[s];
                                 const double y = tt + z0[s];
                                 z0[s] = fma(a1[s], y, fma(sg[s], tt, z1[s]));
@@ -1123,13 +1141,20 @@ static inline void ax_launch_demod_ws(const AxWave& w, const AxCfg& c, int cfg_i
     k_demod_ws<NSEC, NPCM, HEAD><<<(unsigned)((items + per - 1) / per), AX_WS_THREADS, smem, stream>>>(w, c.win_tab, cfg_id, items);
 }
 
-template <int NSEC, int NPCM, bool HEAD, bool FAST = false, bool BULK = false>
+template <int NSEC, int NPCM, bool HEAD, bool FAST = false, bool BULK = false, bool F64 = false>
 static inline void ax_launch_demod_fused(const AxWave& w, const AxCfg& c, int cfg_id, int64_t n_items, cudaStream_t stream, int device) {
     const size_t smem = sizeof(AxFdSmem);
-    ax_optin_smem<k_demod_fused<NSEC, NPCM, HEAD, FAST, BULK>>(smem, device);
+    ax_optin_smem<k_demod_fused<NSEC, NPCM, HEAD, FAST, BULK, F64>>(smem, device);
     const int64_t items = HEAD ? n_items : (int64_t)w.nseg_total;
     if (items <= 0) return;
-    k_demod_fused<NSEC, NPCM, HEAD, FAST, BULK><<<(unsigned)((items + AX_FD_THREADS - 1) / AX_FD_THREADS), AX_FD_THREADS, smem, stream>>>(w, c.win_tab, cfg_id, items);
+    k_demod_fused<NSEC, NPCM, HEAD, FAST, BULK, F64><<<(unsigned)((items + AX_FD_THREADS - 1) / AX_FD_THREADS), AX_FD_THREADS, smem, stream>>>(w, c.win_tab, cfg_id, items);
+}
+// continuous pass over the halved (double-precision) signals of rate class cfg_id
+static inline void ax_launch_demod_fused_f64(const AxWave& w, const AxCfg& c, int cfg_id, cudaStream_t stream, int device) {
+    if (c.nsec == 3 && c.npcm == 39) ax_launch_demod_fused<3, 39, false, false, false, true>(w, c, cfg_id, 0, stream, device);
+    else if (c.nsec == 3 && c.npcm == 43) ax_launch_demod_fused<3, 43, false, false, false, true>(w, c, cfg_id, 0, stream, device);
+    else if (c.nsec == 6 && c.npcm == 39) ax_launch_demod_fused<6, 39, false, false, false, true>(w, c, cfg_id, 0, stream, device);
+    else ax_launch_demod_fused<6, 43, false, false, false, true>(w, c, cfg_id, 0, stream, device);
 }
 
 // true if the fused kernel has an instantiation for this rate class
@@ -1167,6 +1192,208 @@ static inline void ax_launch_demod_fused_any(const AxWave& w, const AxCfg& c, in
     else if (c.nsec == 3 && c.npcm == 43) ax_launch_demod_fused<3, 43, HEAD>(w, c, cfg_id, n_items, stream, device);
     else if (c.nsec == 6 && c.npcm == 39) ax_launch_demod_fused<6, 39, HEAD>(w, c, cfg_id, n_items, stream, device);
     else ax_launch_demod_fused<6, 43, HEAD>(w, c, cfg_id, n_items, stream, device);
+}
+
+// ------------------------------------------------------------------ /2 decimation, staged (AXCTDprocessor.py:60-62)
+// k_decim_fused<PASS, PAR>: the two passes of ax_decim_item (forward over the odd-extended recording -> fwd, backward
+// over fwd -> every second sample of the unpadded range -> xf) with the layout of the demodulation pass: one lane per
+// decimation segment, 32 samples ("a row") per iteration, rows staged by the warp with 16-byte cp.async (coalesced:
+// the thread-per-segment form read 2 or 8 bytes per thread from 32 different lines per instruction and kept its
+// filter state in local memory), the four Chebyshev sections skewed by one sample each so that a lane holds four
+// independent recurrences, and the row's outputs transposed through shared memory so that the warp stores whole
+// 256-byte (pass 0) / 128-byte (pass 1) runs.  Per sample and section the arithmetic is ax_decim_step's.  A drop's
+// segments are padded to a multiple of 32 (axctd_batch_create), so a warp never spans two drops and the geometry of
+// lane q is lane 0's shifted by q segments; rows that touch the padding of the extension or the ends of the
+// recording (first / last rows of a drop) take a per-sample path that reads global memory directly.
+#define AX_DC_WARPS 4
+#define AX_DC_THREADS (AX_DC_WARPS * 32)
+#define AX_DC_R 32
+struct AxDc0Warp { int16_t stage[2][32 * 40]; double tile[32 * 33]; };      // 80-byte staging rows (conflict-free LDS.128), 33-double tile rows
+struct AxDc1Warp { double stage[2][32 * 34]; double tile[32 * 17]; };       // 272-byte staging rows, 17-double tile rows
+__device__ __forceinline__ long long ax_floor_div(long long a, long long b) { long long q = a / b; if ((a % b != 0) && ((a < 0) != (b < 0))) --q; return q; }
+__device__ __forceinline__ double ax_dc_section(double u, const double* k, double& z0, double& z1) {
+    const double y = fma(k[0], u, z0);
+    z0 = fma(k[1], u, fma(k[3], y, z1));
+    z1 = fma(k[2], u, -__dmul_rn(k[4], y));
+    return y;
+}
+template <int PASS, int PAR>
+__global__ void __launch_bounds__(AX_DC_THREADS) k_decim_fused(const __grid_constant__ AxWave w, int64_t n_items) {
+    extern __shared__ __align__(16) unsigned char ax_smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t sg0 = (int64_t)blockIdx.x * AX_DC_THREADS + warp * 32;
+    if (sg0 >= n_items) return;
+    const int d = ax_find_owner(w.drop, w.n_drops, &AxDrop::dseg_base, sg0);
+    const AxDrop& dr = w.drop[d];
+    const long long j0 = sg0 - dr.dseg_base;
+    if (dr.xf_off < 0 || j0 >= dr.ndseg) return;
+    const AxCfg& c = w.cfg[dr.cfg];
+    const AxState& st = w.st[d];
+    const long long N = dr.n_raw, P = c.dpad, E = N + 2 * P, DL = w.dseg_len, DR = DL / AX_DC_R;
+    const long long j = j0 + lane;
+    const bool active = j < dr.ndseg;
+    double k[4][5], z[4][2];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        k[q][0] = c.dsos[q][0]; k[q][1] = c.dsos[q][1]; k[q][2] = c.dsos[q][2]; k[q][3] = -c.dsos[q][4]; k[q][4] = c.dsos[q][5];
+        z[q][0] = 0.0; z[q][1] = 0.0;
+    }
+    double* fwd = w.fwd + dr.fwd_off;
+    if (PASS == 0) {
+        AxDc0Warp& sm = reinterpret_cast<AxDc0Warp*>(ax_smem_raw)[warp];
+        const int16_t* x = w.pcm + dr.pcm_off;
+        const double kmul = st.inv_ampl, kadd = -(st.dc * st.inv_ampl);
+        // lane q: rows rA0 + q DR .. of 32 samples in recording coordinates n = e - P; its outputs are e in [(j0+q) DL, ...)
+        const long long rA0 = ax_floor_div(j0 * DL - c.dwarm - P, AX_DC_R);
+        const long long e1 = active ? ((j + 1) * DL < E ? (j + 1) * DL : E) : 0;
+        const int T = active ? (int)(ax_floor_div(e1 - P + AX_DC_R - 1, AX_DC_R) - (rA0 + lane * DR)) : 0;
+        int Tmax = T;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) Tmax = max(Tmax, __shfl_xor_sync(0xffffffffu, Tmax, o));
+        const int prow = lane >> 2, piece = lane & 3;
+        auto issue = [&](int t, int sbuf) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int q = i * 8 + prow;
+                const long long nr = AX_DC_R * (rA0 + q * DR + t);
+                if (j0 + q < dr.ndseg && nr >= 0 && nr + AX_DC_R <= N)
+                    ax_cp_async16(&sm.stage[sbuf][q * 40 + piece * 8], x + nr + piece * 8);
+            }
+            ax_cp_async_commit();
+        };
+        if (Tmax > 0) issue(0, 0);
+        for (int t = 0; t < Tmax; ++t) {
+            if (t + 1 < Tmax) { issue(t + 1, (t + 1) & 1); ax_cp_async_wait<1>(); } else ax_cp_async_wait<0>();
+            __syncwarp();
+            if (t < T) {
+                const long long nr = AX_DC_R * (rA0 + lane * DR + t);
+                double* to = sm.tile + lane * 33;
+                if (nr >= 0 && nr + AX_DC_R <= N) {
+                    const int4* rp = reinterpret_cast<const int4*>(&sm.stage[t & 1][lane * 40]);
+                    double pipe[4];
+                    int4 qd = rp[0];
+#pragma unroll
+                    for (int nn = 0; nn < AX_DC_R + 3; ++nn) {
+#pragma unroll
+                        for (int sct = 3; sct >= 0; --sct) {
+                            const int m = nn - sct;
+                            if (m >= 0 && m < AX_DC_R) {
+                                double u;
+                                if (sct == 0) {
+                                    if ((m & 7) == 0 && m > 0) qd = rp[m >> 3];
+                                    const int wdv = ((m & 7) >> 1) == 0 ? qd.x : ((m & 7) >> 1) == 1 ? qd.y : ((m & 7) >> 1) == 2 ? qd.z : qd.w;
+                                    const short2 xs2 = *reinterpret_cast<const short2*>(&wdv);
+                                    u = fma((m & 1) ? (double)xs2.y : (double)xs2.x, kmul, kadd);
+                                } else u = pipe[sct];
+                                const double y = ax_dc_section(u, k[sct], z[sct][0], z[sct][1]);
+                                if (sct < 3) pipe[sct + 1] = y; else to[m] = y;
+                            }
+                        }
+                    }
+                } else {
+                    for (int i = 0; i < AX_DC_R; ++i) {
+                        const long long e = nr + i + P;
+                        if (e < 0 || e >= E) continue;
+                        double u = ax_decim_ext(w, dr, c, st, e);
+                        if (e == 0) for (int q = 0; q < 4; ++q) { z[q][0] = ax_mul(c.dzi[q][0], u); z[q][1] = ax_mul(c.dzi[q][1], u); }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) u = ax_dc_section(u, k[q], z[q][0], z[q][1]);
+                        to[i] = u;
+                    }
+                }
+            }
+            __syncwarp();
+            const long long erow0 = AX_DC_R * (rA0 + t) + P;
+#pragma unroll 4
+            for (int q = 0; q < 32; ++q) {
+                const long long e = erow0 + q * DL + lane, lo = (j0 + q) * DL;
+                long long hi = lo + DL; if (hi > E) hi = E;
+                if (j0 + q < dr.ndseg && e >= lo && e < hi) fwd[e] = sm.tile[q * 33 + lane];
+            }
+            __syncwarp();
+        }
+    } else {
+        AxDc1Warp& sm = reinterpret_cast<AxDc1Warp*>(ax_smem_raw)[warp];
+        double* xf = w.xf + dr.xf_off;
+        // reversed segment j covers e' = E-1-e in [j DL, (j+1) DL): lane q walks rows rT0 - q DR - t of 32 samples, downwards
+        const long long rT0 = ax_floor_div(E - 1 - j0 * DL + c.dwarm, AX_DC_R);
+        const long long e1r = active ? ((j + 1) * DL < E ? (j + 1) * DL : E) : 0;
+        const int T = active ? (int)((rT0 - lane * DR) - ax_floor_div(E - e1r, AX_DC_R) + 1) : 0;
+        int Tmax = T;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) Tmax = max(Tmax, __shfl_xor_sync(0xffffffffu, Tmax, o));
+        const int prow = lane >> 4, piece = lane & 15;
+        auto issue = [&](int t, int sbuf) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int q = i * 2 + prow;
+                const long long er = AX_DC_R * (rT0 - q * DR - t);
+                if (j0 + q < dr.ndseg && er >= 0 && er + AX_DC_R <= E)
+                    ax_cp_async16(&sm.stage[sbuf][q * 34 + piece * 2], fwd + er + piece * 2);
+            }
+            ax_cp_async_commit();
+        };
+        if (Tmax > 0) issue(0, 0);
+        for (int t = 0; t < Tmax; ++t) {
+            if (t + 1 < Tmax) { issue(t + 1, (t + 1) & 1); ax_cp_async_wait<1>(); } else ax_cp_async_wait<0>();
+            __syncwarp();
+            if (t < T) {
+                const long long er = AX_DC_R * (rT0 - lane * DR - t);
+                double* to = sm.tile + lane * 17;
+                if (er >= 0 && er + AX_DC_R <= E) {
+                    const double2* rp = reinterpret_cast<const double2*>(&sm.stage[t & 1][lane * 34]);
+                    double pipe[4];
+                    double2 qd = rp[15];
+#pragma unroll
+                    for (int nn = 0; nn < AX_DC_R + 3; ++nn) {
+#pragma unroll
+                        for (int sct = 3; sct >= 0; --sct) {
+                            const int m = nn - sct;
+                            if (m >= 0 && m < AX_DC_R) {
+                                const int i = AX_DC_R - 1 - m;         // sample of the row (descending)
+                                double u;
+                                if (sct == 0) {
+                                    if ((i & 1) == 1 && i < AX_DC_R - 1) qd = rp[i >> 1];
+                                    u = (i & 1) ? qd.y : qd.x;
+                                } else u = pipe[sct];
+                                const double y = ax_dc_section(u, k[sct], z[sct][0], z[sct][1]);
+                                if (sct < 3) pipe[sct + 1] = y;
+                                else if (((i ^ PAR) & 1) == 0) to[(i - PAR) >> 1] = y;
+                            }
+                        }
+                    }
+                } else {
+                    for (int i = AX_DC_R - 1; i >= 0; --i) {
+                        const long long e = er + i;
+                        if (e < 0 || e >= E) continue;
+                        double u = fwd[e];
+                        if (e == E - 1) for (int q = 0; q < 4; ++q) { z[q][0] = ax_mul(c.dzi[q][0], u); z[q][1] = ax_mul(c.dzi[q][1], u); }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) u = ax_dc_section(u, k[q], z[q][0], z[q][1]);
+                        if (((i ^ PAR) & 1) == 0) to[(i - PAR) >> 1] = u;
+                    }
+                }
+            }
+            __syncwarp();
+#pragma unroll 4
+            for (int q2 = 0; q2 < 16; ++q2) {
+                const int q = 2 * q2 + (lane >> 4), uu = lane & 15;
+                const long long e = AX_DC_R * (rT0 - q * DR - t) + PAR + 2 * uu, m = e - P;
+                long long hi = (j0 + q + 1) * DL; if (hi > E) hi = E;
+                // outputs of reversed segment j0+q: e' = E-1-e in [(j0+q) DL, hi)
+                if (j0 + q < dr.ndseg && E - 1 - e >= (j0 + q) * DL && E - 1 - e < hi && m >= 0 && m < N) xf[m >> 1] = sm.tile[q * 17 + uu];
+            }
+            __syncwarp();
+        }
+    }
+}
+static inline bool ax_decim_fused_ok(const AxCfg& c) { return c.decimate == 2 && c.dnsec == 4; }
+template <int PASS>
+static inline void ax_launch_decim_fused(const AxWave& w, int64_t n_items, int par, cudaStream_t stream, int device) {
+    const size_t smem = AX_DC_WARPS * (PASS == 0 ? sizeof(AxDc0Warp) : sizeof(AxDc1Warp));
+    const unsigned grid = (unsigned)((n_items + AX_DC_THREADS - 1) / AX_DC_THREADS);
+    if (par) { ax_optin_smem<k_decim_fused<PASS, 1>>(smem, device); k_decim_fused<PASS, 1><<<grid, AX_DC_THREADS, smem, stream>>>(w, n_items); }
+    else { ax_optin_smem<k_decim_fused<PASS, 0>>(smem, device); k_decim_fused<PASS, 0><<<grid, AX_DC_THREADS, smem, stream>>>(w, n_items); }
 }
 
 // ------------------------------------------------------------------ bit decisions with shared window sums
