@@ -15,66 +15,70 @@ import os
 from . import AXCTDprocessor
 
 
+# flag, long name, default, help -- the flags and defaults of the reference CLI (processAXCTD.py:52-66); the help
+# texts are this package's own
+_VALUE_FLAGS = (
+    ("-i", "--input", "ERROR_NO_FILE_SPECIFIED", "WAV recording to decode"),
+    ("-o", "--output", "output.txt", "text file the profile is written to"),
+    ("-s", "--starttime", "0", "where the drop starts in the recording (seconds, or [HH:]MM:SS)"),
+    ("-e", "--endtime", "-1", "where the drop ends in the recording (-1: end of file)"),
+    ("-a", "--autodetect-start", "30", "earliest profile start the 7500 Hz detector accepts, seconds after the first 400 Hz pulse"),
+    ("-b", "--autodetect-end", "-1", "latest profile start: the profile is taken to begin here if no 7500 Hz tone was seen (-1: never)"),
+    ("-p", "--sig-threshold-400", "2", "400 Hz level (log10 ratio to the dead frequency) that marks a header pulse"),
+    ("-t", "--sig-threshold-7500", "1.5", "rise of the 7500 Hz level that marks the profile start"),
+    ("-d", "--dead-freq", "3000", "quiet reference frequency of the signal levels (Hz)"),
+    ("-l", "--pointsperloop", "100000", "samples per processing iteration"),
+    ("-m", "--mark-freq", "400", "frequency of a 1 bit (Hz)"),
+    ("-n", "--space-freq", "800", "frequency of a 0 bit (Hz)"),
+)
+
+
 def main(argv=None):
-    parser = argparse.ArgumentParser(description='Demodulate an audio file to text')
-    parser.add_argument('-i', '--input', default='ERROR_NO_FILE_SPECIFIED', help='Input WAV filename')
-    parser.add_argument('-o', '--output', default='output.txt', help='Output filename')
-    parser.add_argument('-s', '--starttime', default='0', help='AXCTD start time in WAV file')
-    parser.add_argument('-e', '--endtime', default='-1', help='AXCTD end time in WAV file')
-    parser.add_argument('-a', '--autodetect-start', default='30', help='Point at which autodetect algorithm starts scanning for profile transmission start')
-    parser.add_argument('-b', '--autodetect-end', default='-1', help='Point at which autodetect algorithm stops scanning for profile transmission start')
-    parser.add_argument('-p', '--sig-threshold-400', default='2', help='Threshold for normalized 400 Hz signal level to detect profile transmission')
-    parser.add_argument('-t', '--sig-threshold-7500', default='1.5', help='Threshold for normalized 7500 Hz signal level to detect profile transmission')
-    parser.add_argument('-d', '--dead-freq', default='3000', help='"Dead" (quiet) frequency used to calculate normalized signal levels (Hz)')
-    parser.add_argument('-l', '--pointsperloop', default='100000', help='Number of PCM audio data points processed per iteration')
-    parser.add_argument('-m', '--mark-freq', default='400', help='Mark (bit 1) frequency (Hz)')
-    parser.add_argument('-n', '--space-freq', default='800', help='Space (bit 0) frequency (Hz)')
-    parser.add_argument('-u', '--use-bandpass', action='store_true', help='Apply this flag to use a bandpass filter (100 Hz to 1200 Hz) rather than a 1200 Hz lowpass filter before demodulation')
-    parser.add_argument('--wired', action='store_true', help='make the documented flags act (not reference behaviour)')
-    parser.add_argument('--device', type=int, default=0, help='CUDA device index')
+    parser = argparse.ArgumentParser(description="AXCTD audio recording -> profile text file (B200 engine)")
+    for short, long_name, default, text in _VALUE_FLAGS:
+        parser.add_argument(short, long_name, default=default, help=text)
+    parser.add_argument("-u", "--use-bandpass", action="store_true", help="band-pass 100-1200 Hz instead of the 1200 Hz low-pass")
+    parser.add_argument("--wired", action="store_true", help="make the documented flags act (not reference behaviour)")
+    parser.add_argument("--device", type=int, default=0, help="CUDA device index")
     args = parser.parse_args(argv)
 
-    if args.input == 'ERROR_NO_FILE_SPECIFIED':
+    # processAXCTD.py:71-76: the two messages and the silent exit are part of the interface
+    if args.input == "ERROR_NO_FILE_SPECIFIED":
         print("[!] Error- no input WAV file specified! Terminating")
         exit()
     elif not os.path.exists(args.input):
         print("[!] Specified input file does not exist! Terminating")
         exit()
 
-    timerange = [parse_times(args.starttime), parse_times(args.endtime)]      # processAXCTD.py:80-84
-    if timerange[1] <= 0:
-        timerange[1] = -1
-    triggerrange = [parse_times(args.autodetect_start), parse_times(args.autodetect_end)]   # :87-91
-    if triggerrange[1] <= 0:
-        triggerrange[1] = -1
+    def window(lo_text, hi_text):                # :80-91: a non-positive end means "open"
+        lo, hi = parse_times(lo_text), parse_times(hi_text)
+        return [lo, hi if hi > 0 else -1]
 
-    settings = {'triggerrange': triggerrange,                                # :93-99
-                'minR400': float(args.sig_threshold_400),
-                'mindR7500': float(args.sig_threshold_7500),
-                'deadfreq': float(args.dead_freq),
-                'pointsperloop': int(args.pointsperloop),
-                'mark_space_freqs': [float(args.mark_freq), float(args.space_freq)],
-                'use_bandpass': args.use_bandpass}
+    timerange = window(args.starttime, args.endtime)
+    triggerrange = window(args.autodetect_start, args.autodetect_end)
+    settings = {"triggerrange": triggerrange,                                # keys and types of :93-99
+                "minR400": float(args.sig_threshold_400),
+                "mindR7500": float(args.sig_threshold_7500),
+                "deadfreq": float(args.dead_freq),
+                "pointsperloop": int(args.pointsperloop),
+                "mark_space_freqs": [float(args.mark_freq), float(args.space_freq)],
+                "use_bandpass": args.use_bandpass}
     return processAXCTD(args.input, args.output, timerange, settings,
                         mode="wired" if args.wired else "faithful", device=args.device)
 
 
 def parse_times(time_string):
-    """processAXCTD.py:106-121."""
+    """Seconds from "SS", "MM:SS" or "HH:MM:SS" (same results as processAXCTD.py:106-121: fields beyond the hours are
+    dropped with a log message, anything that is not an integer gives -2)."""
+    fields = time_string.split(":")
+    if len(fields) > 3:
+        logging.info("[!] time fields beyond HH:MM:SS are ignored")
     try:
-        if ":" in time_string:
-            t = 0
-            for i, val in enumerate(reversed(time_string.split(":"))):
-                if i <= 2:
-                    t += int(val) * 60 ** i
-                else:
-                    logging.info("[!] Warning- ignoring all end time information past the hours place (HH:MM:SS)")
-        else:
-            t = int(time_string)
-        return t
+        values = [int(f) for f in fields[::-1][:3]]          # seconds, minutes, hours; the ignored fields are not looked at
     except ValueError:
-        logging.info("[!] Unable to interpret specified start time- defaulting to 00:00")
+        logging.info("[!] time not understood, taking -2 (treated as unset)")
         return -2
+    return sum(v * 60 ** i for i, v in enumerate(values))
 
 
 def wired_settings(settings, f_s):

@@ -366,10 +366,18 @@ def test_concurrent_decoder_matches_single_batch(eng):
         assert np.array_equal(r.rows, g.rows)
 
 
+def _oracle_words_and_rows(args):
+    from oracle import axctd_oracle as ao
+    pcm, fs = args
+    op = ao.process_pcm(pcm, fs)
+    return (np.array([int(h, 16) for h in op.hexframes], dtype=np.uint32), np.asarray(op.time, dtype=np.float64),
+            np.asarray(op.temperature, dtype=np.float64))
+
+
 def test_config3_full_size_recording(eng):
     """BASELINE config 3 at full size: a 96 kHz, 1-hour recording holding five drops is halved on the device, cut by
-    the segmentation driver and decoded as one batch; every segment decodes, and the first segment's frames are the
-    oracle's (frame words bit-exact)."""
+    the segmentation driver and decoded as one batch; every segment's frames are the oracle's for that segment
+    (frame words bit-exact, times and temperatures of the kept rows)."""
     from axctdprocessor_b200 import segment
     from oracle import axctd_oracle as ao
     fs = 96000
@@ -387,11 +395,16 @@ def test_config3_full_size_recording(eng):
     assert len(out) == 5 and [a for a, _, _ in out][0] == 0
     for a, b, r in out:
         assert r.status == 0 and 16900 < int(r.summary.n_frames) < 17100
-    a, b, r = out[0]
-    op = ao.process_pcm(pcm[a:b], fs)
-    words = np.array([int(h, 16) for h in op.hexframes], dtype=np.uint32)
-    tab = r.table()
-    assert np.array_equal(words, tab["word"][tab["hex_returned"] == 1])
+    # every segment against the oracle run on that segment as a stand-alone recording (one process per segment)
+    import multiprocessing as mp
+    with mp.get_context("fork").Pool(processes=len(out)) as pool:
+        ops = pool.map(_oracle_words_and_rows, [(pcm[a:b], fs) for a, b, _ in out])
+    for (a, b, r), (words, times, temps) in zip(out, ops):
+        tab = r.table()
+        assert np.array_equal(words, tab["word"][tab["hex_returned"] == 1]), (a, b)
+        kept = tab[tab["keep"] == 1]
+        np.testing.assert_allclose(kept["time_s"], times, rtol=1e-6, atol=0)
+        np.testing.assert_allclose(kept["temperature"], temps, rtol=1e-6, atol=0)
 
 
 def test_calibration_known_answers_on_the_device(eng):
