@@ -1070,7 +1070,11 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
     AX_LAUNCH(e, k_nx, b->zc_total, w);
 #endif
     AX_LAUNCH(e, k_tiles, b->tile_total, w);
+#ifndef AXCTD_EMU
+    k_plan0_block<<<n, 128, 0, e->stream>>>(w); e->launches++;
+#else
     AX_LAUNCH1(e, k_plan0, n, w);
+#endif
     AX_LAUNCH(e, k_pwfill, b->chunk_total, w, 0);
     AX_EVENT(b, 3);
     int32_t flags[8];
@@ -1183,7 +1187,11 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
     AX_LAUNCH1(e, k_scale, n, w);
 #endif
     AX_BITS(1);
+#ifndef AXCTD_EMU
+    k_headers_warp<<<2 * n, 32, 0, e->stream>>>(w); e->launches++;
+#else
     AX_LAUNCH1(e, k_headers, 2 * (int64_t)n, w);
+#endif
     AX_LAUNCH(e, k_merge, n, w);          // header text -> calibration coefficients (python float semantics, ax_merge_item)
     AX_LAUNCH(e, k_pack, b->edge_total / 32, w);
     AX_LAUNCH(e, k_valid, b->edge_total / 32, w);

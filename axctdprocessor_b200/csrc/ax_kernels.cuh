@@ -1642,6 +1642,92 @@ __global__ void __launch_bounds__(32) k_sm_search_warp(AxWave w) {
     if (lane == 0 && kf > kfrom) { st.pcount = ch[kf - 1].pw_off + ch[kf - 1].np; st.next_sm_chunk = kf; }
 }
 
+// ax_header_item with the window's bits staged in shared memory by the warp (one thread read up to 4 400 bits from
+// global memory one byte at a time); the parse itself stays with lane 0.  grid = 2 x drops (header slots)
+#define AX_HDR_STAGE 8192
+__global__ void __launch_bounds__(32) k_headers_warp(AxWave w) {
+    __shared__ uint8_t sb[AX_HDR_STAGE];
+    const int d = (int)(blockIdx.x >> 1), slot = (int)(blockIdx.x & 1), lane = threadIdx.x;
+    const AxDrop& dr = w.drop[d];
+    const AxCfg& c = w.cfg[dr.cfg];
+    AxState& st = w.st[d];
+    ax_header_reset(st, slot, lane, 32);
+    __syncwarp();
+    if (st.sm_status < 1 || st.nedges_total == 0) return;
+    const uint8_t* B = w.bit + dr.edge_base;
+    const int klast = (st.k2 >= 0) ? st.k2 : st.n_chunks - 1;
+    for (int k = st.k0; k <= klast && k < st.n_chunks; ++k) {
+        int64_t a = 0, n = 0;
+        int r = 0;
+        if (lane == 0) r = ax_header_window(w, dr, c, st, slot, k, &a, &n);
+        r = __shfl_sync(0xffffffffu, r, 0);
+        if (r < 0) { if (lane == 0) ax_raise(st, -r, k); return; }
+        if (r == 0) continue;
+        a = __shfl_sync(0xffffffffu, a, 0); n = __shfl_sync(0xffffffffu, n, 0);
+        const bool staged = n <= AX_HDR_STAGE;
+        if (staged) for (int64_t i = lane; i < n; i += 32) sb[i] = B[a + i];
+        __syncwarp();
+        int done = 0;
+        if (lane == 0) done = ax_header_parse(st, slot, k, staged ? sb : B + a, n) ? 1 : 0;
+        done = __shfl_sync(0xffffffffu, done, 0);
+        if (done) return;
+        __syncwarp();
+    }
+}
+
+// ax_plan0_item in closed form, a CTA per drop: while the status is 0 the iterations tile the recording
+// (start k * chunk, AXCTDprocessor.py:333), so their number and every field follow from k alone.
+__global__ void __launch_bounds__(128) k_plan0_block(AxWave w) {
+    const int d = blockIdx.x;
+    const AxDrop& dr = w.drop[d];
+    const AxCfg& c = w.cfg[dr.cfg];
+    AxState& st = w.st[d];
+    AxChunk* ch = w.chunk + dr.chunk_base;
+    __shared__ int s_viol, s_small;
+    int kfrom = 0, par0 = 1;
+    if (w.streaming) {
+        if (st.sm_status >= 1 || st.status != 0) return;
+        kfrom = st.n_fixed;
+        if (kfrom > 0) par0 = st.par_levels;
+    }
+    const int64_t CL = c.chunk_len, n = dr.n;
+    int64_t K;
+    if (w.streaming == 1) K = n > 0 ? (n - 1) / CL : 0;                     // iterations with start + chunk inside the data
+    else K = n >= 4 * (int64_t)c.n_power ? (n - 4 * (int64_t)c.n_power) / CL + 1 : 0;     // :295
+    bool cap_hit = false;
+    if (K > dr.chunk_cap) { K = dr.chunk_cap; cap_hit = true; }
+    const int32_t np0 = ax_grid_count(0, CL, c);
+    if (threadIdx.x == 0) { s_viol = 0x7fffffff; s_small = 0; }
+    __syncthreads();
+    for (int64_t k = kfrom + threadIdx.x; k < K; k += blockDim.x) {
+        const int64_t s = k * CL;
+        int64_t e = s + CL; if (e >= n) e = n - 1;
+        const int32_t np = ax_grid_count(s, e, c);
+        if (k * (int64_t)np0 + np > dr.pw_cap) atomicMin(&s_viol, (int)k);
+    }
+    __syncthreads();
+    const int64_t Kf = s_viol < K ? s_viol : K;
+    for (int64_t k = kfrom + threadIdx.x; k < Kf; k += blockDim.x) {
+        const int64_t s = k * CL;
+        int64_t e = s + CL; if (e >= n) e = n - 1;
+        AxChunk& q = ch[k];
+        q.s = s; q.e = e; q.pw_off = (int32_t)(k * np0); q.np = ax_grid_count(s, e, c);
+        q.n_edges = 0; q.n_head_edges = 0; q.err = 0; q.status = 0; q.n_rows = 0; q.n_hex = 0;
+        q.frame_begin = q.frame_end = 0; q.scale = c.scale0; q.mean7500 = ax_nan();
+        q.spec_last = q.true_last = -1; q.g_first = -1; q.q_last = -1; q.bit_off = q.edge_off = 0; q.first_edge = -1;
+        if (q.np < 10) atomicOr(&s_small, 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_viol < K) { ax_raise(st, AXCTD_DROP_CAPACITY, s_viol); w.flags[AX_FLAG_CAP] = 1; }
+        else if (cap_hit) { ax_raise(st, AXCTD_DROP_CAPACITY, (int)K); w.flags[AX_FLAG_CAP] = 1; }
+        st.n_fixed = (int32_t)Kf; st.n_chunks = (int32_t)Kf;
+        st.par_levels = (par0 && !s_small) ? 1 : 0;
+        st.searching = Kf > 0 ? 1 : 0;
+        if (w.streaming && st.next_sm_chunk >= Kf) st.searching = 0;
+    }
+}
+
 // ax_chain_item with the lanes fetching in parallel.  Per run() iteration three rounds of loads: the crossings
 // around the predicted end of the chunk (lane i looks at ordinal guess-16+i), the canonical masks of the tiles
 // that can hold the stopping crossing, and the two crossing indices that fix the next start.

@@ -20,62 +20,76 @@ AX_HD uint32_t ax_word32(const uint8_t* b) {
     return wd;
 }
 
-// One header slot (0 = second transmission, 1 = third) of one drop.
+// One header slot (0 = second transmission, 1 = third) of one drop, in three steps so that the CUDA build can stage
+// the bit window in shared memory (k_headers_warp): reset, the window of one candidate iteration, trim + parse.
+AX_HD void ax_header_reset(AxState& st, int slot, int first, int step) {
+    if (first == 0) { st.header_read[1 + slot] = 0; st.header_chunk[1 + slot] = -1; st.header_parsed[slot] = 0; }
+    for (int q = first; q < 72; q += step) { st.frame_data[slot][q] = 0; st.counter_found[slot][q] = 0; }
+}
+// iteration k: 0 = its buffer does not span the header yet, 1 = bits [a, a + n) of the drop are the window
+// (AXCTDprocessor.py:472-478), < 0 = -AXCTD_DROP_* (the reference's IndexError)
+AX_HD int ax_header_window(const AxWave& w, const AxDrop& dr, const AxCfg& c, const AxState& st, int slot, int k, int64_t* a_out, int64_t* n_out) {
+    const AxChunk* ch = w.chunk + dr.chunk_base;
+    const int32_t* I = w.edge_idx + dr.edge_base;
+    const int64_t ps = st.firstpulse400 + (slot ? c.h3s : c.h2s), pe = st.firstpulse400 + (slot ? c.h3e : c.h2e);
+    if (ch[k].n_edges <= 0) return 0;
+    const int64_t ni = ch[k].edge_off + ch[k].n_edges, nb = ch[k].bit_off + ch[k].n_edges - 1;
+    if (!((int64_t)I[0] <= ps && (int64_t)I[ni - 1] >= pe)) return 0;
+    const int64_t a = ax_first_ge(I, ni, ps - c.half), b = ax_last_le(I, ni, pe + c.half);
+    if (a < 0 || b < 0) return -AXCTD_DROP_TRIM_INDEX;
+    const int64_t hi = b < nb ? b : nb;
+    *a_out = a; *n_out = hi > a ? hi - a : 0;
+    return 1;
+}
+// trim_header (parse.py:157-183) and parse_header (parse.py:197-245) on the window's bits; false: fewer than 72 frames
+// are left after the trim, the next iteration tries again (AXCTDprocessor.py:481)
+AX_HD bool ax_header_parse(AxState& st, int slot, int k, const uint8_t* bits, int64_t n) {
+    int64_t last_pulse = 0; int ones25 = 0; int run = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const int bv = (i < 25) ? 1 : bits[i];
+        if (bv) { ++ones25; ++run; if (i > 10 && run >= 8) last_pulse = i; } else run = 0;
+        if (i > 24) {
+            const int back = (i - 25 < 25) ? 1 : bits[i - 25];
+            if (back) --ones25;
+            if (i >= 400 && ones25 <= 20) break;
+        }
+    }
+    int64_t hn = n - last_pulse;
+    if (hn > 32 * 75) hn = 32 * 75;
+    if (hn < 72 * 32) return false;
+    int lastframe = -1; int64_t s = 0;
+    uint8_t fb[32];
+    while (lastframe < 71 && s < hn - 32) {
+        for (int q = 0; q < 32; ++q) { const int64_t p = last_pulse + s + q; fb[q] = (p < 25) ? 1 : bits[p]; }
+        if (!(fb[0] == 1 && fb[1] == 0) || !ax_crc_ok(ax_word32(fb))) { ++s; continue; }
+        int cur = 0;
+        if (fb[2] & fb[3] & fb[4] & fb[5] & fb[6]) { cur = (fb[7] << 2 | fb[8] << 1 | fb[9]) + 64; }
+        else { for (int q = 2; q < 10; ++q) cur = (cur << 1) | fb[q]; }
+        if (cur <= 71) {
+            st.counter_found[slot][cur] = 1; lastframe = cur;
+            uint16_t v = 0; for (int q = 10; q < 26; ++q) v = (uint16_t)((v << 1) | fb[q]);
+            st.frame_data[slot][cur] = v;
+        }
+        s += 32;
+    }
+    st.header_parsed[slot] = 1; st.header_read[1 + slot] = 1; st.header_chunk[1 + slot] = k;
+    return true;
+}
 AX_HDN inline void ax_header_item(const AxWave& w, int64_t item) {
     const int d = (int)(item >> 1), slot = (int)(item & 1);
     const AxDrop& dr = w.drop[d];
     const AxCfg& c = w.cfg[dr.cfg];
     AxState& st = w.st[d];
-    st.header_read[1 + slot] = 0; st.header_chunk[1 + slot] = -1; st.header_parsed[slot] = 0;
-    for (int q = 0; q < 72; ++q) { st.frame_data[slot][q] = 0; st.counter_found[slot][q] = 0; }
+    ax_header_reset(st, slot, 0, 1);
     if (st.sm_status < 1 || st.nedges_total == 0) return;
-    const AxChunk* ch = w.chunk + dr.chunk_base;
-    const int32_t* I = w.edge_idx + dr.edge_base;
     const uint8_t* B = w.bit + dr.edge_base;
-    const int64_t ps = st.firstpulse400 + (slot ? c.h3s : c.h2s), pe = st.firstpulse400 + (slot ? c.h3e : c.h2e);
-    const int64_t firstbin = I[0];
     const int klast = (st.k2 >= 0) ? st.k2 : st.n_chunks - 1;
     for (int k = st.k0; k <= klast && k < st.n_chunks; ++k) {
-        if (ch[k].n_edges <= 0) continue;
-        const int64_t ni = ch[k].edge_off + ch[k].n_edges, nb = ch[k].bit_off + ch[k].n_edges - 1;
-        if (!(firstbin <= ps && (int64_t)I[ni - 1] >= pe)) continue;
-        const int64_t a = ax_first_ge(I, ni, ps - c.half), b = ax_last_le(I, ni, pe + c.half);
-        if (a < 0 || b < 0) { ax_raise(st, AXCTD_DROP_TRIM_INDEX, k); return; }
-        const int64_t hi = b < nb ? b : nb;
-        const int64_t n = hi > a ? hi - a : 0;
-        const uint8_t* bits = B + a;
-        // ---- trim_header, parse.py:157-183
-        int64_t last_pulse = 0; int ones25 = 0; int run = 0;
-        for (int64_t i = 0; i < n; ++i) {
-            const int bv = (i < 25) ? 1 : bits[i];
-            if (bv) { ++ones25; ++run; if (i > 10 && run >= 8) last_pulse = i; } else run = 0;
-            if (i > 24) {
-                const int back = (i - 25 < 25) ? 1 : bits[i - 25];
-                if (back) --ones25;
-                if (i >= 400 && ones25 <= 20) break;
-            }
-        }
-        int64_t hn = n - last_pulse;
-        if (hn > 32 * 75) hn = 32 * 75;
-        if (hn < 72 * 32) continue;                       // AXCTDprocessor.py:481: try again next iteration
-        // ---- parse_header, parse.py:197-245
-        int lastframe = -1; int64_t s = 0;
-        uint8_t fb[32];
-        while (lastframe < 71 && s < hn - 32) {
-            for (int q = 0; q < 32; ++q) { const int64_t p = last_pulse + s + q; fb[q] = (p < 25) ? 1 : bits[p]; }
-            if (!(fb[0] == 1 && fb[1] == 0) || !ax_crc_ok(ax_word32(fb))) { ++s; continue; }
-            int cur = 0;
-            if (fb[2] & fb[3] & fb[4] & fb[5] & fb[6]) { cur = (fb[7] << 2 | fb[8] << 1 | fb[9]) + 64; }
-            else { for (int q = 2; q < 10; ++q) cur = (cur << 1) | fb[q]; }
-            if (cur <= 71) {
-                st.counter_found[slot][cur] = 1; lastframe = cur;
-                uint16_t v = 0; for (int q = 10; q < 26; ++q) v = (uint16_t)((v << 1) | fb[q]);
-                st.frame_data[slot][cur] = v;
-            }
-            s += 32;
-        }
-        st.header_parsed[slot] = 1; st.header_read[1 + slot] = 1; st.header_chunk[1 + slot] = k;
-        return;
+        int64_t a = 0, n = 0;
+        const int r = ax_header_window(w, dr, c, st, slot, k, &a, &n);
+        if (r < 0) { ax_raise(st, -r, k); return; }
+        if (r == 0) continue;
+        if (ax_header_parse(st, slot, k, B + a, n)) return;
     }
 }
 
