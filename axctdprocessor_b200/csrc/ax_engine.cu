@@ -737,7 +737,7 @@ extern "C" int axctd_batch_create(axctd_engine* e, int n_drops, const int64_t* n
         dr.seg_base = seg_off; dr.nseg = (int32_t)((n + L - 1) / L); seg_off += ((dr.nseg + 127) / 128) * 128;
         dr.slab_base = slab_off; dr.nslab = (int32_t)((n_raw + AX_STAT_SLAB - 1) / AX_STAT_SLAB); slab_off += dr.nslab;
         dr.tb_base = tb_off; dr.ntb = (int32_t)(n / AX_TB); tb_off += dr.ntb; ntb_max = std::max(ntb_max, (int32_t)((n_raw + AX_TB - 1) / AX_TB));
-        dr.zc_base = zc_off; dr.zc_cap = n / e->opt_zc_div + 4096; zc_off += dr.zc_cap + 8;
+        dr.zc_base = zc_off; dr.zc_cap = n / e->opt_zc_div + 4096; zc_off += ((dr.zc_cap + 8 + 63) / 64) * 64;   // (64-aligned: k_tiles_reg loads a tile's walk steps as four 16-byte words)
         dr.tile_base = tile_off; dr.tile_cap = (int32_t)(dr.zc_cap / AX_TILE + 1); tile_off += dr.tile_cap;
         dr.chunk_base = chunk_off; dr.chunk_cap = (int32_t)(2 * (n / c.chunk_len) + 16); chunk_off += dr.chunk_cap;
         dr.edge_base = edge_off; dr.edge_cap = n / 24 + 8 * (int64_t)dr.chunk_cap; edge_off += ((dr.edge_cap + 64 + 63) / 64) * 64;
@@ -775,7 +775,7 @@ extern "C" int axctd_batch_create(axctd_engine* e, int n_drops, const int64_t* n
     bad |= ax_alloc_arr(b, &w.zc_idx, zc_off);
     bad |= ax_alloc_arr(b, &w.zc_a1, zc_off);
     bad |= ax_alloc_arr(b, &w.zc_a2, zc_off);
-    bad |= ax_alloc_arr(b, &w.zc_nx, zc_off);
+    bad |= ax_alloc_arr(b, &w.zc_nx, zc_off + 64);
     bad |= ax_alloc_arr(b, &w.tile_mask, (int64_t)tile_off * 4);
     bad |= ax_alloc_arr(b, &w.tile_map, tile_off);
     bad |= ax_alloc_arr(b, &w.cmask, (int64_t)tile_off + 8);
@@ -799,7 +799,6 @@ extern "C" int axctd_batch_create(axctd_engine* e, int n_drops, const int64_t* n
     bad |= ax_alloc_arr(b, &w.bit, edge_off);
     bad |= ax_alloc_arr(b, &w.a1, edge_off);
     bad |= ax_alloc_arr(b, &w.a2, edge_off);
-    bad |= ax_alloc_arr(b, &w.conf, edge_off);
     bad |= ax_alloc_arr(b, &w.bitw, edge_off / 32 + 4);
     bad |= ax_alloc_arr(b, &w.validw, edge_off / 32 + 4);
     bad |= ax_alloc_arr(b, &w.frame, frame_off);
@@ -1069,7 +1068,11 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
     AX_LAUNCH(e, k_compact, (int64_t)w.nseg_total, w);
     AX_LAUNCH(e, k_nx, b->zc_total, w);
 #endif
+#ifndef AXCTD_EMU
+    if (b->tile_total > 0) { k_tiles_reg<<<(unsigned)((b->tile_total + 127) / 128), 128, 0, e->stream>>>(b->tile_total, w); e->launches++; }
+#else
     AX_LAUNCH(e, k_tiles, b->tile_total, w);
+#endif
 #ifndef AXCTD_EMU
     k_plan0_block<<<n, 128, 0, e->stream>>>(w); e->launches++;
 #else
@@ -1412,7 +1415,16 @@ extern "C" int64_t axctd_batch_bits(axctd_batch* b, int drop, uint8_t* bits, dou
     const int64_t base = b->drops[drop].edge_base;
     // bits of chunk k sit at bit_off[k]: contiguous over the drop
     if (bits && nb && ax_d2h(b->eng, bits, b->w.bit + base, (size_t)nb)) return -AXCTD_ERR_CUDA;
-    if (conf && nb && ax_d2h(b->eng, conf, b->w.conf + base, sizeof(double) * nb)) return -AXCTD_ERR_CUDA;
+    if (conf && nb) {
+        // demodulate.py:102,110: conf = |S2| * high_bit_scale / |S1| with the scale in force when the bit was demodulated
+        // (ax_bits_decide's arithmetic, on the magnitudes the decision was made from)
+        std::vector<double> p1((size_t)nb), p2((size_t)nb);
+        if (ax_d2h(b->eng, p1.data(), b->w.a1 + base, sizeof(double) * nb) || ax_d2h(b->eng, p2.data(), b->w.a2 + base, sizeof(double) * nb) ||
+            ax_sync(b->eng)) return -AXCTD_ERR_CUDA;
+        const AxState& st = b->st[drop];
+        const double s0 = b->eng->cfgs[b->drops[drop].cfg].scale0;
+        for (int64_t j = 0; j < nb; ++j) conf[j] = ax_div(ax_mul(p2[j], j >= st.scale_switch_bit ? st.scale : s0), p1[j]);
+    }
     if (ax_sync(b->eng)) return -AXCTD_ERR_CUDA;
     return nb;
 }

@@ -689,7 +689,7 @@ AX_HD void ax_bits_decide(const AxWave& w, int d, int64_t slot) {
     const double scale = (j >= st.scale_switch_bit) ? st.scale : w.cfg[dr.cfg].scale0;
     const double p1 = w.a1[slot];
     const double p2 = ax_mul(w.a2[slot], scale);
-    w.conf[slot] = ax_div(p2, p1);
+    // (the confidence p2 / p1 of demodulate.py:110 is not stored: axctd_batch_bits forms it from a1, a2 and the scale)
     w.bit[slot] = (p1 >= p2) ? 1 : 0;
 }
 

@@ -234,7 +234,7 @@ struct AxWave {
     // bits / edges
     int32_t* edge_idx; int32_t* lvl_slot;                   // per edge: PCM index; power sample whose levels it takes (-1: none)
     double* r7500m;                                         // [pw_total] r7500 - mean7500pwr of the iteration the sample belongs to
-    uint8_t* bit; double* a1; double* a2; double* conf;     // per bit
+    uint8_t* bit; double* a1; double* a2;                   // per bit
     uint32_t* bitw; uint32_t* validw;                       // packed bits / frame-candidate mask (32 per word)
     // frames
     axctd_frame* frame;
