@@ -47,14 +47,7 @@ AX_GLOBAL void k_init(int64_t n, AxWave w) {
     AX_FOR_ITEM(n) {
         AxState& st = w.st[item];
         memset(&st, 0, sizeof(AxState));
-        st.ampl = -2147483647 - 1; st.vmax = -2147483647 - 1; st.vmin = 0x7fffffff;
-        st.k0 = st.k2 = st.km = st.k1 = -1;
-        st.firstpulse400 = -1; st.profstartind = -1; st.firstpointtime = -1.0; st.mean7500 = ax_nan();
-        st.status_chunk = -1;
-        for (int q = 0; q < 3; ++q) st.header_chunk[q] = -1;
-        const AxCfg& c = w.cfg[w.drop[item].cfg];
-        st.scale = c.scale0;
-        for (int q = 0; q < 4; ++q) { st.zc_used[q] = c.zc[q]; st.tc_used[q] = c.tc[q]; st.cc_used[q] = c.cc[q]; }
+        ax_state_defaults(st, w.cfg[w.drop[item].cfg]);
     }
 }
 // ---- streaming decode of a growing recording (axctd_batch_stream_*)
@@ -967,8 +960,13 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
     if (streaming && !b->in_stream_run) { e->err = "a streaming batch runs through axctd_batch_stream_run"; return AXCTD_ERR_STATE; }
     AX_EVENT(b, 0);
     if (ax_zero(e, w.flags, sizeof(int32_t) * 8)) return AXCTD_ERR_CUDA;
-    if (!streaming) { AX_LAUNCH(e, k_init, n, w); }
-    else if (b->stream_runs == 0) { AX_LAUNCH(e, k_init, n, w); AX_LAUNCH(e, k_stream_begin, n, w, (const double*)b->d_norm); }
+#ifndef AXCTD_EMU
+#define AX_INIT() do { k_init_warp<<<n, 32, 0, e->stream>>>(w); e->launches++; } while (0)
+#else
+#define AX_INIT() AX_LAUNCH(e, k_init, n, w)
+#endif
+    if (!streaming) { AX_INIT(); }
+    else if (b->stream_runs == 0) { AX_INIT(); AX_LAUNCH(e, k_stream_begin, n, w, (const double*)b->d_norm); }
     else { AX_LAUNCH(e, k_stream_resume, n, w); }
 #ifndef AXCTD_EMU
     {   // one pass over the PCM: statistics and the tone block sums, one launch per rate class in use
@@ -981,7 +979,7 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
                 k_stats_tones<<<dim3((unsigned)((w.ntb_max + AX_ST_THREADS - 1) / AX_ST_THREADS), (unsigned)n), AX_ST_THREADS, 0, e->stream>>>(w, e->tone_tabs[ci], (int)ci);
             e->launches++;
         }
-        if (w.nslab_total > 0 && !streaming) { k_stats_wrap<<<w.nslab_total, 256, 0, e->stream>>>(w); e->launches++; }
+        if (w.nslab_total > 0 && !streaming) { k_stats_wrap<<<dim3(AX_WRAP_CTAS, (unsigned)n), 256, 0, e->stream>>>(w); e->launches++; }
     }
 #else
     if (!streaming) { AX_LAUNCH(e, k_stats, (int64_t)w.nslab_total, w); }

@@ -64,24 +64,36 @@ static inline cudaError_t ax_optin_smem(size_t bytes, int device) {
 // ------------------------------------------------------------------ stats (exact |x| semantics, fallback)
 // np.max(np.abs(int16)) wraps abs(-32768) to -32768 (AXCTDprocessor.py:56).  k_stats_tones tracks min and max,
 // which decide max|x| unless a sample equals -32768; only then this kernel rescans the drop.
+// grid (AX_WRAP_CTAS, drops): the CTAs of a drop share its slabs; almost always they only look at vmin and leave
+#define AX_WRAP_CTAS 16
 __global__ void __launch_bounds__(256) k_stats_wrap(AxWave w) {
-    const int64_t slab = blockIdx.x;
-    const int d = w.slab_drop[slab];
+    const int d = blockIdx.y;
     if (w.st[d].vmin != -32768) return;
     const AxDrop& dr = w.drop[d];
-    const int64_t j = slab - dr.slab_base;
-    const int64_t a = j * AX_STAT_SLAB;
-    int64_t b = a + AX_STAT_SLAB;
-    if (b > dr.n_raw) b = dr.n_raw;
-    const int16_t* x = w.pcm + dr.pcm_off + a;
     int mx = -32768;
-    for (int t = threadIdx.x; t < (int)(b - a); t += blockDim.x) {
-        const int v = x[t];
-        mx = max(mx, (v == -32768) ? -32768 : abs(v));
+    for (int64_t j = blockIdx.x; j < dr.nslab; j += gridDim.x) {
+        const int64_t a = j * AX_STAT_SLAB;
+        int64_t b = a + AX_STAT_SLAB;
+        if (b > dr.n_raw) b = dr.n_raw;
+        const int16_t* x = w.pcm + dr.pcm_off + a;
+        for (int t = threadIdx.x; t < (int)(b - a); t += blockDim.x) {
+            const int v = x[t];
+            mx = max(mx, (v == -32768) ? -32768 : abs(v));
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     if ((threadIdx.x & 31) == 0) atomicMax(&w.st[d].ampl, mx);
+}
+// k_init with a warp per drop: the state record (1.3 KB) is cleared with 16-byte stores by all lanes
+__global__ void __launch_bounds__(32) k_init_warp(AxWave w) {
+    const int d = blockIdx.x, lane = threadIdx.x;
+    AxState& st = w.st[d];
+    static_assert(sizeof(AxState) % 8 == 0, "AxState is cleared in 8-byte words");
+    unsigned long long* p = reinterpret_cast<unsigned long long*>(&st);
+    for (int i = lane; i < (int)(sizeof(AxState) / 8); i += 32) p[i] = 0ull;
+    __syncwarp();
+    if (lane == 0) ax_state_defaults(st, w.cfg[w.drop[d].cfg]);
 }
 
 // ------------------------------------------------------------------ stats + tone block sums (one PCM pass)
@@ -1761,6 +1773,14 @@ __global__ void __launch_bounds__(32) k_chain_warp(AxWave w) {
         const int64_t g0 = entry + span - 15;
         const int64_t mine = g0 + lane;
         const int32_t zmine = (mine >= 0 && mine < M) ? zi[mine] : 0;
+        {   // the next iteration will look one span further on: fetch those lines into L2 while this iteration's loads are
+            // under way (the crossing arrays of a batch are far larger than L2, and the chain is one dependent DRAM
+            // round trip per iteration otherwise)
+            const int64_t pf = g0 + span + 32 * (int64_t)(lane - 2);
+            if (lane < 8 && pf >= 0 && pf < M) asm volatile("prefetch.global.L2 [%0];" ::"l"(zi + pf));
+            const int64_t tpf = (entry + 2 * span - 4) / AX_TILE + (lane - 8);
+            if (lane >= 8 && lane < 11 && tpf >= 0 && tpf * AX_TILE < M) asm volatile("prefetch.global.L2 [%0];" ::"l"(cmask + tpf));
+        }
         const int64_t tg = (entry + span - 4) / AX_TILE;                        // predicted tile of X
         const int64_t tl = lane == 0 ? entry / AX_TILE : tg + (lane - 1);
         const uint64_t mv = (lane < 3 && tl >= 0) ? cmask[tl] : 0ull;

@@ -268,6 +268,17 @@ AX_HD AxSrc ax_src(const AxWave& w, const AxDrop& dr) {
     return s;
 }
 
+// the non-zero fields of a fresh state record (k_init clears the rest)
+AX_HD void ax_state_defaults(AxState& st, const AxCfg& c) {
+    st.ampl = -2147483647 - 1; st.vmax = -2147483647 - 1; st.vmin = 0x7fffffff;
+    st.k0 = st.k2 = st.km = st.k1 = -1;
+    st.firstpulse400 = -1; st.profstartind = -1; st.firstpointtime = -1.0; st.mean7500 = ax_nan();
+    st.status_chunk = -1;
+    for (int q = 0; q < 3; ++q) st.header_chunk[q] = -1;
+    st.scale = c.scale0;
+    for (int q = 0; q < 4; ++q) { st.zc_used[q] = c.zc[q]; st.tc_used[q] = c.tc[q]; st.cc_used[q] = c.cc[q]; }
+}
+
 #define AX_FLAG_DIRTY 0
 #define AX_FLAG_CAP 1
 #define AX_FLAG_MORE 2
