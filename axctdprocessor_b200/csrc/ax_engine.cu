@@ -692,7 +692,7 @@ extern "C" int axctd_batch_create(axctd_engine* e, int n_drops, const int64_t* n
     w.bit_tol = e->opt_bit_tol; w.hist_tol = e->opt_hist_tol; w.bitfix_all = e->opt_bitfix_all;
     w.head_zc_cap_max = head_cap_max;
     b->drops.resize(n_drops);
-    int64_t pcm_off = 0, zc_off = 0, edge_off = 0, tb_off = 0, xf_off = 0, fwd_off = 0;
+    int64_t pcm_off = 0, zc_off = 0, edge_off = 0, tb_off = 0, xf_off = 0, fwd_off = 0, zq_off = 0;
     int32_t ntb_max = 0, dseg_off = 0;
     // samples per decimation segment: one wave of (SMs x 8 warps x 32) lanes over the recordings that are halved, but
     // not below 2048 (the warm-up overlap is some 650 samples)
@@ -731,6 +731,7 @@ extern "C" int axctd_batch_create(axctd_engine* e, int n_drops, const int64_t* n
         dr.slab_base = slab_off; dr.nslab = (int32_t)((n_raw + AX_STAT_SLAB - 1) / AX_STAT_SLAB); slab_off += dr.nslab;
         dr.tb_base = tb_off; dr.ntb = (int32_t)(n / AX_TB); tb_off += dr.ntb; ntb_max = std::max(ntb_max, (int32_t)((n_raw + AX_TB - 1) / AX_TB));
         dr.zc_base = zc_off; dr.zc_cap = n / e->opt_zc_div + 4096; zc_off += ((dr.zc_cap + 8 + 63) / 64) * 64;   // (64-aligned: k_tiles_reg loads a tile's walk steps as four 16-byte words)
+        dr.zq_base = zq_off; zq_off += n / AX_ZQ + 2;
         dr.tile_base = tile_off; dr.tile_cap = (int32_t)(dr.zc_cap / AX_TILE + 1); tile_off += dr.tile_cap;
         dr.chunk_base = chunk_off; dr.chunk_cap = (int32_t)(2 * (n / c.chunk_len) + 16); chunk_off += dr.chunk_cap;
         dr.edge_base = edge_off; dr.edge_cap = n / 24 + 8 * (int64_t)dr.chunk_cap; edge_off += ((dr.edge_cap + 64 + 63) / 64) * 64;
@@ -769,6 +770,7 @@ extern "C" int axctd_batch_create(axctd_engine* e, int n_drops, const int64_t* n
     bad |= ax_alloc_arr(b, &w.zc_a1, zc_off);
     bad |= ax_alloc_arr(b, &w.zc_a2, zc_off);
     bad |= ax_alloc_arr(b, &w.zc_nx, zc_off + 64);
+    bad |= ax_alloc_arr(b, &w.zc_q, zq_off + 8);
     bad |= ax_alloc_arr(b, &w.tile_mask, (int64_t)tile_off * 4);
     bad |= ax_alloc_arr(b, &w.tile_map, tile_off);
     bad |= ax_alloc_arr(b, &w.cmask, (int64_t)tile_off + 8);

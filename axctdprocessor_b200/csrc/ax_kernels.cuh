@@ -1760,6 +1760,13 @@ __global__ void __launch_bounds__(32) k_chain_warp(AxWave w) {
     else s = ch[k - 1].true_last - 1 - c.pad;
     int64_t entry = -1, span = (int64_t)c.chunk_len / 37;
     int n_chunks_out = -1;
+    // the crossing that ends an iteration is found through the coarse index zq (crossings below every AX_ZQ-th sample,
+    // k_compact_warp): the 64 crossings from zq[(e - 2) / AX_ZQ] - 9 on hold it, its four predecessors and the crossings
+    // that fix the next start.  The entries the NEXT iteration can need are fetched in the same round of loads
+    // (tq_lo .. tq_lo + 2), so that an iteration costs one dependent memory round trip.
+    const int32_t* zq = w.zc_q + dr.zq_base;
+    const int64_t nzq = dr.n / AX_ZQ + 2;
+    int64_t tq_lo = -1; int32_t tq_val = 0;              // lane i < 3 holds zq[tq_lo + i]
     for (;; ++k) {
         if (w.streaming == 1) { if (s + c.chunk_len >= dr.n) { n_chunks_out = k; break; } }      // not complete yet: a later run takes it
         else if (dr.n - s < 4 * (int64_t)c.n_power) { n_chunks_out = k; break; }
@@ -1770,26 +1777,32 @@ __global__ void __launch_bounds__(32) k_chain_warp(AxWave w) {
         if (entry < 0) entry = ax_lower_bound(zi, M, s + c.pad);            // (all lanes: same result)
         // ---- one round of loads: the 32 crossings around the predicted end of the chunk, and (lanes 0..2) the
         // canonical masks of the entry tile and of the two tiles that should hold the stopping crossing
-        const int64_t g0 = entry + span - 15;
-        const int64_t mine = g0 + lane;
+        const int64_t jq = (e - 2) >> AX_ZQ_SHIFT;
+        int64_t t0;
+        if (jq >= tq_lo && jq < tq_lo + 3 && tq_lo >= 0) t0 = __shfl_sync(0xffffffffu, tq_val, (int)(jq - tq_lo));
+        else t0 = zq[jq < nzq ? jq : nzq - 1];
+        const int64_t g0 = t0 - 9;
+        const int64_t mine = g0 + lane, mine2 = mine + 32;
         const int32_t zmine = (mine >= 0 && mine < M) ? zi[mine] : 0;
-        {   // the next iteration will look one span further on: fetch those lines into L2 while this iteration's loads are
-            // under way (the crossing arrays of a batch are far larger than L2, and the chain is one dependent DRAM
-            // round trip per iteration otherwise)
-            const int64_t pf = g0 + span + 32 * (int64_t)(lane - 2);
-            if (lane < 8 && pf >= 0 && pf < M) asm volatile("prefetch.global.L2 [%0];" ::"l"(zi + pf));
-            const int64_t tpf = (entry + 2 * span - 4) / AX_TILE + (lane - 8);
-            if (lane >= 8 && lane < 11 && tpf >= 0 && tpf * AX_TILE < M) asm volatile("prefetch.global.L2 [%0];" ::"l"(cmask + tpf));
+        const int32_t zmine2 = (mine2 >= 0 && mine2 < M) ? zi[mine2] : 0;
+        {   // entries of the coarse index the next iteration can ask for: its end lies one chunk (less the pad and the
+            // few crossings the walk stops short) after this one's
+            tq_lo = (e - 2 + c.chunk_len - c.pad - 512 - AX_ZQ) >> AX_ZQ_SHIFT;
+            if (tq_lo < 0) tq_lo = 0;
+            const int64_t jn = tq_lo + lane;
+            tq_val = (lane < 3) ? zq[jn < nzq ? jn : nzq - 1] : 0;
         }
-        const int64_t tg = (entry + span - 4) / AX_TILE;                        // predicted tile of X
+        const int64_t tg = (t0 - 4) / AX_TILE;                                  // likely tile of X
         const int64_t tl = lane == 0 ? entry / AX_TILE : tg + (lane - 1);
         const uint64_t mv = (lane < 3 && tl >= 0) ? cmask[tl] : 0ull;
         int64_t q;
         {
             const bool le = mine < 0 ? true : (mine >= M ? false : (int64_t)zmine <= e - 2);
-            const unsigned ball = __ballot_sync(0xffffffffu, le);
-            if (ball != 0u && ball != 0xffffffffu) q = g0 + (31 - __clz((int)ball));        // zi is ascending: le is a prefix
-            else q = ax_upper_bound_from(zi, M, e - 2, entry + span) - 1;
+            const bool le2 = mine2 < 0 ? true : (mine2 >= M ? false : (int64_t)zmine2 <= e - 2);
+            const unsigned ball = __ballot_sync(0xffffffffu, le), ball2 = __ballot_sync(0xffffffffu, le2);
+            if (ball2 != 0u && ball2 != 0xffffffffu) q = g0 + 32 + (31 - __clz((int)ball2));   // zi is ascending: le is a prefix
+            else if (ball2 == 0u && ball != 0u) q = g0 + (31 - __clz((int)ball));
+            else q = ax_upper_bound_from(zi, M, e - 2, t0 + 54) - 1;
         }
         if (entry > q) { n_chunks_out = k + 1; break; }
         span = q - entry;
@@ -1820,9 +1833,12 @@ __global__ void __launch_bounds__(32) k_chain_warp(AxWave w) {
         }
         // ---- the crossing indices that fix the next start: from the window when they are in it
         int64_t zpos, zprev;
-        if (pos - 1 >= g0 && pos < g0 + 32 && pos - 1 >= 0 && pos < M) {
-            zpos = __shfl_sync(0xffffffffu, zmine, (int)(pos - g0));
-            zprev = __shfl_sync(0xffffffffu, zmine, (int)(pos - 1 - g0));
+        if (pos - 1 >= g0 && pos < g0 + 64 && pos - 1 >= 0 && pos < M) {
+            const int ia = (int)(pos - g0), ib = ia - 1;                     // window positions (two registers of 32)
+            const int32_t a0 = __shfl_sync(0xffffffffu, zmine, ia & 31), a1 = __shfl_sync(0xffffffffu, zmine2, ia & 31);
+            const int32_t b0 = __shfl_sync(0xffffffffu, zmine, ib & 31), b1 = __shfl_sync(0xffffffffu, zmine2, ib & 31);
+            zpos = ia < 32 ? a0 : a1;
+            zprev = ib < 32 ? b0 : b1;
         } else {
             const int64_t pl = pos - (lane & 1);
             const int32_t zv = (lane < 2 && pl >= 0) ? zi[pl] : 0;
@@ -2037,7 +2053,25 @@ __global__ void __launch_bounds__(256) k_compact_warp(AxWave w) {
     const AxCfg& c = w.cfg[dr.cfg];
     const int64_t src = seg * (int64_t)w.seg_cap, dst = dr.zc_base + w.seg_off[seg] + w.blk_sum[seg / 128];
     const int cnt = w.seg_cnt[seg];
-    if (cnt == 0) return;
+    auto fill_zq = [&]() {   // coarse index (k_chain_warp): zq[j] = number of crossings of the drop with index below AX_ZQ * j.  A segment
+        // owns the boundaries inside its own sample range (its records are exactly the crossings in that range, so the
+        // entry is its dense offset plus the number of its records below the boundary); the last one also closes the table
+        const int64_t jseg = seg - dr.seg_base;
+        if (jseg < dr.nseg) {
+            const int64_t lo_s = jseg * (int64_t)w.seg_len;
+            const int64_t j0 = (lo_s + AX_ZQ - 1) >> AX_ZQ_SHIFT;
+            const int64_t j1 = jseg == dr.nseg - 1 ? dr.n / AX_ZQ + 2 : (lo_s + w.seg_len + AX_ZQ - 1) >> AX_ZQ_SHIFT;    // exclusive
+            int32_t* zq = w.zc_q + dr.zq_base;
+            const int32_t base = (int32_t)(dst - dr.zc_base);
+            for (int64_t j = j0 + lane; j < j1; j += 32) {
+                const int64_t bnd = j << AX_ZQ_SHIFT;
+                int lo = 0, hi = cnt;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if ((int64_t)w.rec_idx[src + mid] < bnd) lo = mid + 1; else hi = mid; }
+                zq[j] = base + lo;
+            }
+        }
+    };
+    if (cnt == 0) { fill_zq(); return; }
     // the walk step of every crossing (ax_nx_item) is formed here as well: it needs the next four crossings, which
     // are this segment's own records or, for its last four, the first records of the segments that follow.
     // 128 records per warp and round, all their loads issued before the first use (the kernel is bound by memory
@@ -2086,6 +2120,7 @@ __global__ void __launch_bounds__(256) k_compact_warp(AxWave w) {
             w.zc_nx[dst + q] = nx;
         }
     }
+    fill_zq();                                           // (after the copy: the records are in cache by now)
 }
 
 // ------------------------------------------------------------------ walk tiles from registers

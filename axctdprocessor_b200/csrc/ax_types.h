@@ -52,6 +52,8 @@ AX_HD double ax_fma(double a, double b, double c) { return fma(a, b, c); }
 AX_HD double ax_nan() { return nan(""); }
 
 #define AX_TILE 64          // crossings per walk tile
+#define AX_ZQ 1024          // samples per entry of the coarse crossing index
+#define AX_ZQ_SHIFT 10
 #define AX_MAXSEC AXCTD_MAX_SECTIONS
 #define AX_PEND 8           // pending bit-windows per thread in the filter pass
 #define AX_STAT_SLAB 16384  // samples per stats work item
@@ -108,6 +110,7 @@ struct AxDrop {
     int32_t slab_base, nslab;    // stats work items
     int64_t tb_base; int32_t ntb, pad_tb;   // tone blocks: floor(n / AX_TB) full blocks
     int64_t zc_base, zc_cap;     // dense crossing arrays
+    int64_t zq_base;             // coarse index of the dense crossings (AxWave::zc_q), n / AX_ZQ + 2 entries
     int32_t tile_base, tile_cap;
     int32_t chunk_base, chunk_cap;
     int64_t edge_base, edge_cap; // bit / edge arrays
@@ -214,6 +217,7 @@ struct AxWave {
     int32_t* rec_idx; float* rec_a1; float* rec_a2;         // [nseg_total * seg_cap]
     int32_t* zc_idx; float* zc_a1; float* zc_a2;            // dense, per drop at zc_base
     uint8_t* zc_nx;                                         // per crossing: walk step
+    int32_t* zc_q;                                          // per AX_ZQ samples: crossings with index below AX_ZQ * j (k_compact_warp -> k_chain_warp)
     uint64_t* tile_mask; uint32_t* tile_map;                // [tile][4] visited masks, [tile] exit offsets (ax_tiles_item)
     uint64_t* cmask; int32_t* crank;                        // [tile] canonical walk: visited mask, visited count before the tile
     // chunks
