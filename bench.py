@@ -375,6 +375,7 @@ def run_native(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # NCCL's own banner ("NCCL version ...") goes to stdout otherwise: stdout carries the JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from axctdprocessor_b200 import batch as axbatch
     numa_bound = axbatch.bind_host_thread_to_gpu(local) if world > 1 else False      # (one rank per GPU: keep its pinned buffers local)
