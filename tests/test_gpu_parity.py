@@ -542,3 +542,32 @@ def test_two_rank_sharded_decode_equals_oracle_and_single_gpu(eng):
         assert np.array_equal(m["rows"], single[i].rows) and np.array_equal(m["chunks"], single[i].chunks)
         check_rows_against_oracle(single[i], ao.process_pcm(p, s.fs))
         assert (m["firstpulse400"], m["profstartind"], m["n_bits"]) == (int(single[i].summary.firstpulse400), int(single[i].summary.profstartind), int(single[i].summary.n_bits))
+
+
+def test_engines_on_two_devices_in_one_process():
+    """Two engines on two GPUs of one process, used alternately (per-device shared-memory opt-in, device guards of
+    every ABI entry point, per-device block cache): both decode to the oracle's result."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from axctdprocessor_b200 import engine
+    from oracle import axctd_oracle as ao
+    spec = synth.DropSpec(fs=44100, duration_s=52.0, seed=616, snr_db=18.0)
+    pcm = synth.generate_drop(spec)
+    op = ao.process_pcm(pcm, spec.fs)
+    e0, e1 = engine.Engine(0), engine.Engine(1)
+    try:
+        c0, c1 = e0.config(spec.fs), e1.config(spec.fs)          # interleaved on purpose: each call must land on its own device
+        b1 = e1.batch([len(pcm)], [c1]); b0 = e0.batch([len(pcm)], [c0])
+        b0.upload(0, pcm); b1.upload(0, pcm)
+        b1.run(); b0.run()
+        for b in (b0, b1):
+            out = dict(result=b.result(0), bits=b.bits(0), edges=b.edges(0), power=b.power(0))
+            check_against_oracle(out, op)
+        b0.close(); b1.close()
+        # recycled blocks stay on their device
+        b0 = e0.batch([len(pcm)], [c0]); b0.upload(0, pcm); b0.run()
+        check_rows_against_oracle(b0.result(0, full=False), op)
+        b0.close()
+    finally:
+        e0.close(); e1.close()
