@@ -974,9 +974,14 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
     {   // one pass over the PCM: statistics and the tone block sums, one launch per rate class in use
         for (size_t ci = 0; ci < e->cfgs.size(); ++ci) {
             if (!std::any_of(b->drops.begin(), b->drops.end(), [&](const AxDrop& d) { return d.cfg == (int)ci; })) continue;
-            if (e->opt_tone_mma) {
+            const dim3 stm_grid((unsigned)((w.ntb_max + AX_STM_GROUPS * AX_ST_THREADS - 1) / (AX_STM_GROUPS * AX_ST_THREADS)), (unsigned)n);
+#define AX_HYB(KD) do { ax_optin_smem<k_stats_tones_hyb<KD>>(AX_STM_SMEM, e->device); \
+                        k_stats_tones_hyb<KD><<<stm_grid, AX_ST_THREADS, AX_STM_SMEM, e->stream>>>(w, e->cfgs[ci].tone_tab8, e->tone_tabs[ci], (int)ci); } while (0)
+            if (e->opt_tone_mma >= 2) {           // block sums split between the tensor cores and the vector pipe: 4 * (value) of every 64 samples on the tensor cores
+                if (e->opt_tone_mma <= 8) AX_HYB(8); else if (e->opt_tone_mma <= 10) AX_HYB(10); else if (e->opt_tone_mma <= 12) AX_HYB(12); else AX_HYB(14);
+            } else if (e->opt_tone_mma) {
                 ax_optin_smem<k_stats_tones_mma>(AX_STM_SMEM, e->device);
-                k_stats_tones_mma<<<dim3((unsigned)((w.ntb_max + AX_STM_GROUPS * AX_ST_THREADS - 1) / (AX_STM_GROUPS * AX_ST_THREADS)), (unsigned)n), AX_ST_THREADS, AX_STM_SMEM, e->stream>>>(w, e->cfgs[ci].tone_tab8, (int)ci);
+                k_stats_tones_mma<<<stm_grid, AX_ST_THREADS, AX_STM_SMEM, e->stream>>>(w, e->cfgs[ci].tone_tab8, (int)ci);
             } else
                 k_stats_tones<<<dim3((unsigned)((w.ntb_max + AX_ST_THREADS - 1) / AX_ST_THREADS), (unsigned)n), AX_ST_THREADS, 0, e->stream>>>(w, e->tone_tabs[ci], (int)ci);
             e->launches++;

@@ -330,6 +330,149 @@ __global__ void __launch_bounds__(AX_ST_THREADS) k_stats_tones_mma(const __grid_
     }
 }
 
+// The same pass with the block sums split between the FP64 tensor cores and the vector FP64 pipe.
+template <int KD>
+__global__ void __launch_bounds__(AX_ST_THREADS) k_stats_tones_hyb(const __grid_constant__ AxWave w, const double* __restrict__ tab8, const __grid_constant__ AxToneTab tab, int cfg_id) {
+    extern __shared__ __align__(16) unsigned char ax_smem_raw[];       // AX_STM_SMEM bytes: phasor table, then the staging rows
+    double* ptab = reinterpret_cast<double*>(ax_smem_raw);
+    int16_t (*stage_all)[2][32 * 72] = reinterpret_cast<int16_t (*)[2][32 * 72]>(ax_smem_raw + AX_TB * 8 * sizeof(double));
+    const int d = blockIdx.y;
+    const AxDrop& dr = w.drop[d];
+    if (dr.cfg != cfg_id) return;
+    const int64_t nsamp = dr.n_raw;                  // statistics are taken over the recording as uploaded
+    const int64_t nblk = (nsamp + AX_TB - 1) / AX_TB;
+    if ((int64_t)blockIdx.x * AX_STM_GROUPS * AX_ST_THREADS >= nblk) return;
+    if (w.streaming && ((int64_t)blockIdx.x + 1) * AX_STM_GROUPS * AX_ST_THREADS <= w.st[d].tb_done) return;   // summed by an earlier run
+    for (int i = threadIdx.x; i < AX_TB * 8; i += AX_ST_THREADS) ptab[i] = tab8[i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int16_t (*stage)[32 * 72] = stage_all[warp];
+    const int prow = lane >> 3, piece = lane & 7;
+    const int arow = lane >> 2, acol = lane & 3;     // A / C row (block within the group), A column (sample within the k-step)
+    long long sum = 0;
+    int mx2 = (int)0x80008000, mn2 = 0x7fff7fff;        // packed int16 max / min
+    // a CTA takes AX_STM_GROUPS consecutive groups of 128 blocks, so that the table load above is paid once per 128 K samples
+#pragma unroll 1
+    for (int grp = 0; grp < AX_STM_GROUPS; ++grp) {
+    const int64_t jg = ((int64_t)blockIdx.x * AX_STM_GROUPS + grp) * AX_ST_THREADS;
+    if (jg >= nblk) break;
+    const int64_t jb = jg + threadIdx.x;
+    const bool active = jb < nblk;
+    const int64_t n0 = jb * AX_TB;
+    const int T = active ? (int)min((int64_t)4, (nsamp - n0 + 63) >> 6) : 0;
+    const unsigned long long xrow = (unsigned long long)(w.pcm + dr.pcm_off + n0);
+    unsigned long long src[8];
+    int Tr[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        src[i] = __shfl_sync(0xffffffffu, xrow, i * 4 + prow) + (unsigned long long)piece * 16;
+        Tr[i] = __shfl_sync(0xffffffffu, T, i * 4 + prow);
+    }
+    auto issue = [&](int t, int s) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (t < Tr[i]) ax_cp_async16(&stage[s][(i * 4 + prow) * 72 + piece * 8], reinterpret_cast<const void*>(src[i] + (unsigned long long)t * 128));
+        ax_cp_async_commit();
+    };
+    double acc[4][2];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) { acc[g][0] = 0.0; acc[g][1] = 0.0; }
+    double vac[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};      // this lane's block, samples 4 KD .. 63 of every row
+    issue(0, 0);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        if (r + 1 < 4) { issue(r + 1, (r + 1) & 1); ax_cp_async_wait<1>(); } else ax_cp_async_wait<0>();
+        __syncwarp();
+        // block sums: rows of blocks that do not reach this far hold stale samples; their sums are never stored.
+        // The first KD k-steps (4 KD samples) of the row go to the tensor cores, the rest to the vector FP64 pipe
+        // (lane = block, phasors as constant operands): the DMMA pipe was 80 % busy and the issue port 35 %, so the
+        // two run side by side.
+        {
+            const int16_t* st = stage[r & 1];
+            const double* pt = ptab + (64 * r + acol) * 8 + arow;
+#pragma unroll 2
+            for (int ks = 0; ks < KD; ++ks) {
+                const double b = pt[32 * ks];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const double a = (double)st[(8 * g + arow) * 72 + 4 * ks + acol];
+                    ax_dmma884(acc[g][0], acc[g][1], a, b);
+                }
+            }
+            const int* rw = reinterpret_cast<const int*>(&st[lane * 72]);
+#pragma unroll
+            for (int m = 4 * KD; m < 64; m += 2) {
+                const int wd = rw[m >> 1];
+                const short2 xs2 = *reinterpret_cast<const short2*>(&wd);
+                const double x0 = (double)xs2.x, x1 = (double)xs2.y;
+#pragma unroll
+                for (int q6 = 0; q6 < 6; ++q6) vac[q6] = fma(x0, tab.t[64 * r + m][q6], vac[q6]);
+#pragma unroll
+                for (int q6 = 0; q6 < 6; ++q6) vac[q6] = fma(x1, tab.t[64 * r + m + 1][q6], vac[q6]);
+            }
+        }
+        if (r < T) {
+            const int4* rp = reinterpret_cast<const int4*>(&stage[r & 1][lane * 72]);
+            const int nvalid = (int)min((int64_t)64, nsamp - (n0 + 64 * r));
+            if (nvalid == 64) {
+                int s32 = 0;
+#pragma unroll
+                for (int v = 0; v < 8; ++v) {
+                    const int4 q = rp[v];
+                    mx2 = (int)__vimax3_s16x2((unsigned)mx2, (unsigned)q.x, (unsigned)q.y);
+                    mx2 = (int)__vimax3_s16x2((unsigned)mx2, (unsigned)q.z, (unsigned)q.w);
+                    mn2 = (int)__vimin3_s16x2((unsigned)mn2, (unsigned)q.x, (unsigned)q.y);
+                    mn2 = (int)__vimin3_s16x2((unsigned)mn2, (unsigned)q.z, (unsigned)q.w);
+                    s32 = __dp2a_lo(q.x, 0x0101, s32); s32 = __dp2a_lo(q.y, 0x0101, s32);
+                    s32 = __dp2a_lo(q.z, 0x0101, s32); s32 = __dp2a_lo(q.w, 0x0101, s32);
+                }
+                sum += s32;
+            } else {                                   // ragged end of the recording
+                const int16_t* xs = &stage[r & 1][lane * 72];
+                for (int i = 0; i < nvalid; ++i) {
+                    const int v = xs[i];
+                    sum += v;
+                    const int pk = (v & 0xFFFF) | (v << 16);
+                    mx2 = (int)__vimax3_s16x2((unsigned)mx2, (unsigned)pk, (unsigned)pk);
+                    mn2 = (int)__vimin3_s16x2((unsigned)mn2, (unsigned)pk, (unsigned)pk);
+                }
+            }
+        }
+        __syncwarp();
+    }
+    // the vector-pipe part of every block joins the tensor-core part through shared memory (the staging rows are free now)
+    double* vx = reinterpret_cast<double*>(stage[0]);            // [32 blocks][6]
+    __syncwarp();
+#pragma unroll
+    for (int q6 = 0; q6 < 6; ++q6) vx[lane * 6 + q6] = vac[q6];
+    __syncwarp();
+    if (dr.xf_off < 0 && acol < 3) {                   // (a decimating drop takes its block sums from the halved signal)
+        const int64_t jw = jg + warp * 32;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const int64_t j = jw + 8 * g + arow;
+            if (j < dr.ntb) {
+                double* out = w.tb_sum + (dr.tb_base + j) * 6 + 2 * acol;
+                out[0] = acc[g][0] + vx[(8 * g + arow) * 6 + 2 * acol]; out[1] = acc[g][1] + vx[(8 * g + arow) * 6 + 2 * acol + 1];
+            }
+        }
+    }
+    __syncwarp();
+    }
+    int mx = max((int)(short)(mx2 & 0xFFFF), mx2 >> 16), mn = min((int)(short)(mn2 & 0xFFFF), mn2 >> 16);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    }
+    if (lane == 0) {
+        atomicAdd((unsigned long long*)&w.st[d].sum, (unsigned long long)sum);
+        atomicMax(&w.st[d].vmax, mx);
+        atomicMin(&w.st[d].vmin, mn);
+    }
+}
+
 // ------------------------------------------------------------------ tone window magnitudes
 // Per-drop power-sample range [lo, hi) of a tone launch (the range test of ax_tone_slot_active, once per drop).
 __global__ void k_tone_range(AxWave w, int phase_b) {
@@ -1758,7 +1901,7 @@ __global__ void __launch_bounds__(32) k_chain_warp(AxWave w) {
     int64_t s;
     if (k == st.k0) s = ch[k].s;
     else s = ch[k - 1].true_last - 1 - c.pad;
-    int64_t entry = -1, span = (int64_t)c.chunk_len / 37;
+    int64_t entry = -1;
     int n_chunks_out = -1;
     // the crossing that ends an iteration is found through the coarse index zq (crossings below every AX_ZQ-th sample,
     // k_compact_warp): the 64 crossings from zq[(e - 2) / AX_ZQ] - 9 on hold it, its four predecessors and the crossings
@@ -1805,7 +1948,6 @@ __global__ void __launch_bounds__(32) k_chain_warp(AxWave w) {
             else q = ax_upper_bound_from(zi, M, e - 2, t0 + 54) - 1;
         }
         if (entry > q) { n_chunks_out = k + 1; break; }
-        span = q - entry;
         // ---- where the walk stops (ax_walk_end without the step count)
         const int64_t X = q - 4;
         int64_t pos = entry;
