@@ -13,8 +13,11 @@ known-answer frame of reference README.md:87 and the constants of SURVEY.md
 section 4.2 (tests/test_oracle_units.py) and (b) outputs of the UNMODIFIED
 reference run in the build container through oracle/ref_shim.py, committed as
 fixtures under tests/golden/ by oracle/make_golden.py (tests/test_oracle_golden.py).
-Salinity (gsw.SP_from_C) is restated from the published PSS-78 algorithm in
-oracle/pss78.py and is PARITY UNPINNED (gsw is not available here).
+Salinity (gsw.SP_from_C, gsw==3.3.1 in the reference's requirements.txt) is not available
+here; it is restated from the published PSS-78 algorithm in oracle/pss78.py and pinned to the
+UNESCO check value and to the six check values of the GSW documentation for gsw_SP_from_C
+(tests/test_oracle_units.py); the Hill extension below SP = 2 has no published vector and
+stays PARITY UNPINNED.
 
 Differences from the reference that do not change results: the per-bit and
 per-window single-bin DFTs, the nearest-power-sample lookup and the CRC scan are

@@ -7,10 +7,12 @@ this image, so its published algorithm (GSW-C ``gsw_sp_from_c`` and
 ``gsw_hill_ratio_at_sp2``: PSS-78 with the Hill et al. 1986 extension below
 SP = 2) is restated here from the public description.
 
-PARITY UNPINNED for salinity: the reference ships no test or golden vector for
-this call and gsw itself cannot be run here.  The only external anchor is the
-UNESCO 1983 check value (R=1.888091, t68=40, p=10000 -> S=40.00000), which is
-asserted in tests/test_oracle_units.py.
+Pinning: the reference ships no test or golden vector for this call and gsw
+itself cannot be run here.  External anchors, asserted in
+tests/test_oracle_units.py: the UNESCO 1983 check value (R=1.888091, t68=40,
+p=10000 -> S=40.00000) and the six-point example of the GSW documentation for
+gsw_SP_from_C (matched to the last bit).  The Hill extension below SP = 2 has
+no published vector: that branch stays PARITY UNPINNED.
 
 Works on python floats and numpy arrays alike (used (a) as the ``gsw`` stand-in
 when the real reference is run under oracle/ref_shim.py and (b) by the numpy
