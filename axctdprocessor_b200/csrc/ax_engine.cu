@@ -194,6 +194,7 @@ struct axctd_engine {
     int opt_heavy_chain = 1;              // engines of one process take turns with the demodulation pass (see ax_heavy_*)
     int opt_nosync = 1;                   // enqueue the whole decode without host round trips (see axctd_batch_run_async)
     int opt_scan_only = 0;                // tone levels only (segmentation of long recordings): skip the demodulation pass
+    int opt_fuse_bits = 1;                // bits decided while the edges are emitted (k_emit_chunk mode 2)
 };
 
 #ifdef AXCTD_EMU
@@ -332,6 +333,8 @@ struct axctd_batch {
     axctd_chunk* h_chunk = nullptr;       // [chunk_total]
     std::vector<axctd_drop_summary> summary;
     bool force_sync = false;              // repeat of a run whose fixed schedule did not suffice
+    bool force_nofuse = false;            // repeat of a run whose list of bits to re-evaluate overflowed
+    bool ran_fused = false, mags_full = true;   // the last run decided bits in k_emit_chunk; magnitudes of every bit are on the device
     bool ran = false, finished = false;
     bool lent = false;                    // another engine's stream has read this batch's PCM (axctd_batch_copy_from)
     // streaming decode (axctd_batch_stream_*): drops hold growing recordings, `drops` carries their current lengths
@@ -462,6 +465,7 @@ extern "C" int axctd_engine_set_option(axctd_engine* e, const char* name, double
     else if (s == "heavy_chain") e->opt_heavy_chain = (int)v;
     else if (s == "scan_only") e->opt_scan_only = (int)v;
     else if (s == "nosync") e->opt_nosync = (int)v;
+    else if (s == "fuse_bits") e->opt_fuse_bits = (int)v;
     else if (s == "bit_tol") e->opt_bit_tol = v;
     else if (s == "hist_tol") e->opt_hist_tol = v;
     else if (s == "bitfix_all") e->opt_bitfix_all = (int)v;
@@ -805,6 +809,8 @@ extern "C" int axctd_batch_create(axctd_engine* e, int n_drops, const int64_t* n
     if (!b->h_st || !b->h_row || !b->h_chunk) bad = 1;
     bad |= ax_alloc_arr(b, &b->d_qc, 2 * (int64_t)frame_off + 16);
     bad |= ax_alloc_arr(b, &w.flags, 8);
+    w.fix_cap = edge_off / 8 + 1024;
+    bad |= ax_alloc_arr(b, &w.fix_list, w.fix_cap);
     if (bad) { axctd_batch_destroy(b); return AXCTD_ERR_CUDA; }
     w.drop = d_drop; w.st = d_st; w.pcm = b->d_pcm; w.seg_drop = d_seg_drop; w.slab_drop = d_slab_drop;
     bad |= ax_h2d(e, d_drop, b->drops.data(), sizeof(AxDrop) * n_drops);
@@ -1170,31 +1176,39 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
 #endif
     { AX_LAUNCH1(e, k_offsets, n, w); }
 #ifndef AXCTD_EMU
-    k_emit_chunk<<<(unsigned)b->chunk_total, 128, 0, e->stream>>>(w); e->launches++;
-#else
-    AX_LAUNCH(e, k_emit, b->chunk_total, w);
-#endif
-#ifndef AXCTD_EMU
-#define AX_BITS(phase) do { k_bits_chunk<<<(unsigned)b->chunk_total, 128, 0, e->stream>>>(w, phase); e->launches++; } while (0)
-    {   // phase 0 needs the iterations that overlap [first pulse + 1.8 s, + 3.8 s] (+ margins): the first few after k0
+    {
+        // The scale calibration reads the mark / space magnitudes of the iterations that overlap [first pulse + 1.8 s,
+        // + 3.8 s] (+ margins): the first nk after k0.  Those keep the two-step form (edges + magnitudes, phase-0
+        // re-evaluation, calibration, decisions); every later iteration has its bits decided while its edges are
+        // emitted (k_emit_chunk mode 2) and stores magnitudes only for the bits listed for a double-precision window
+        // (k_bits_recheck) -- 16 B per bit less written and read back.  A caller that asks for the magnitudes
+        // (axctd_batch_bits: conf) has them materialised then (ax_materialise_magnitudes).
         int nk = 1;
         for (int d2 = 0; d2 < n; ++d2) {
             const AxCfg& c2 = e->cfgs[b->drops[d2].cfg];
             const double span = (double)c2.h1e + (double)c2.half + 128.0 * c2.fs / c2.bitrate + (double)c2.chunk_len;
             nk = std::max(nk, (int)(span / (0.9 * (double)c2.chunk_len)) + 3);
         }
-        k_bits_chunk<<<dim3((unsigned)nk, (unsigned)n), 128, 0, e->stream>>>(w, 0); e->launches++;
+        const bool fuse = e->opt_fuse_bits != 0 && !streaming && !w.bitfix_all && !b->force_nofuse;
+        b->ran_fused = fuse; b->mags_full = !fuse;
+        w.nk_full = nk;
+        const dim3 region_a((unsigned)nk, (unsigned)n);
+        k_emit_chunk<<<(unsigned)b->chunk_total, 128, 0, e->stream>>>(w, fuse ? 1 : 0); e->launches++;
+        k_bits_chunk<<<region_a, 128, 0, e->stream>>>(w, 0, 1); e->launches++;
+        k_scale_block<<<n, 128, 0, e->stream>>>(w); e->launches++;
+        if (fuse) {
+            k_bits_chunk<<<region_a, 128, 0, e->stream>>>(w, 1, 1);
+            k_emit_chunk<<<(unsigned)b->chunk_total, 128, 0, e->stream>>>(w, 2);
+            k_bits_recheck<<<592, 128, 0, e->stream>>>(w);
+            e->launches += 3;
+        } else { k_bits_chunk<<<(unsigned)b->chunk_total, 128, 0, e->stream>>>(w, 1, 0); e->launches++; }
     }
 #else
-#define AX_BITS(phase) AX_LAUNCH(e, k_bits, b->edge_total, w, phase)
-    AX_BITS(0);
-#endif
-#ifndef AXCTD_EMU
-    k_scale_block<<<n, 128, 0, e->stream>>>(w); e->launches++;
-#else
+    AX_LAUNCH(e, k_emit, b->chunk_total, w);
+    AX_LAUNCH(e, k_bits, b->edge_total, w, 0);
     AX_LAUNCH1(e, k_scale, n, w);
+    AX_LAUNCH(e, k_bits, b->edge_total, w, 1);
 #endif
-    AX_BITS(1);
 #ifndef AXCTD_EMU
     k_headers_warp<<<2 * n, 32, 0, e->stream>>>(w); e->launches++;
 #else
@@ -1230,13 +1244,15 @@ extern "C" int axctd_batch_finish(axctd_batch* b) {
     AxWave& w = b->w;
     const int n = b->n;
     AX_DEV(e);
-    if (b->ran_nosync) {
+    if (b->ran_nosync || b->ran_fused) {
         int32_t flags[8];
         if (ax_d2h(e, flags, w.flags, sizeof(flags)) || ax_d2h(e, b->h_st, w.st, sizeof(AxState) * n) || ax_sync(e)) return AXCTD_ERR_CUDA;
-        if (flags[AX_FLAG_MORE] || flags[AX_FLAG_DIRTY]) {          // the fixed schedule was not enough for some drop
-            b->force_sync = true; b->n_fallbacks++;
+        const bool more = b->ran_nosync && (flags[AX_FLAG_MORE] || flags[AX_FLAG_DIRTY]);     // the fixed schedule was not enough for some drop
+        const bool ovf = b->ran_fused && flags[AX_FLAG_FIXOVF];                              // more bits to re-evaluate than the list holds
+        if (more || ovf) {
+            b->force_sync = more || !b->ran_nosync; b->force_nofuse = ovf; b->n_fallbacks++;
             const int r = axctd_batch_run_async(b);
-            b->force_sync = false;
+            b->force_sync = false; b->force_nofuse = false;
             if (r) return r;
             if (ax_d2h(e, b->h_st, w.st, sizeof(AxState) * n) || ax_sync(e)) return AXCTD_ERR_CUDA;
         }
@@ -1421,6 +1437,14 @@ extern "C" int64_t axctd_batch_bits(axctd_batch* b, int drop, uint8_t* bits, dou
     // bits of chunk k sit at bit_off[k]: contiguous over the drop
     if (bits && nb && ax_d2h(b->eng, bits, b->w.bit + base, (size_t)nb)) return -AXCTD_ERR_CUDA;
     if (conf && nb) {
+#ifndef AXCTD_EMU
+        if (!b->mags_full) {      // the run kept magnitudes only where it needed them: produce the rest now (two-step form of the later iterations)
+            k_emit_chunk<<<(unsigned)b->chunk_total, 128, 0, b->eng->stream>>>(b->w, 3);
+            k_bits_chunk<<<(unsigned)b->chunk_total, 128, 0, b->eng->stream>>>(b->w, 1, 2);
+            if (ax_sync(b->eng)) return -AXCTD_ERR_CUDA;
+            b->mags_full = true;
+        }
+#endif
         // demodulate.py:102,110: conf = |S2| * high_bit_scale / |S1| with the scale in force when the bit was demodulated
         // (ax_bits_decide's arithmetic, on the magnitudes the decision was made from)
         std::vector<double> p1((size_t)nb), p2((size_t)nb);

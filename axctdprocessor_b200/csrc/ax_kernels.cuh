@@ -1556,16 +1556,19 @@ static inline void ax_launch_decim_fused(const AxWave& w, int64_t n_items, int p
 // precision is summed by the whole warp.
 // grid (chunks of the batch) for all iterations, or (iterations after the first demodulated one, drops) when only the
 // first few of every drop matter (phase 0: header 1 sits within four seconds of the first pulse)
-__global__ void __launch_bounds__(128) k_bits_chunk(AxWave w, int phase) {
+// region 0: grid = all iterations of the batch; 1: grid (iterations after k0, drops), the first nk_full of every drop;
+// 2: grid = all iterations, those from k0 + nk_full on only
+__global__ void __launch_bounds__(128) k_bits_chunk(AxWave w, int phase, int region) {
     int d;
     int64_t cg;
-    if (gridDim.y > 1 || phase == 0) {
+    if (region == 1) {
         d = blockIdx.y;
         cg = (int64_t)w.drop[d].chunk_base + w.st[d].k0 + blockIdx.x;
         if (w.st[d].k0 + (int)blockIdx.x >= w.drop[d].chunk_cap) return;
     } else {
         cg = blockIdx.x;
         d = ax_find_owner(w.drop, w.n_drops, &AxDrop::chunk_base, cg);
+        if (region == 2 && (int)(cg - w.drop[d].chunk_base) < w.st[d].k0 + w.nk_full) return;
     }
     const AxDrop& dr = w.drop[d];
     const AxState& st = w.st[d];
@@ -1608,29 +1611,62 @@ __global__ void __launch_bounds__(128) k_bits_chunk(AxWave w, int phase) {
     }
 }
 
+// The bits that k_emit_chunk (fused) listed: a warp per bit sums the double-precision window (ax_gwin_*), replaces the
+// magnitudes and decides again.  The list length is only known on the device: a fixed grid strides over it.
+__global__ void __launch_bounds__(128) k_bits_recheck(AxWave w) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    int64_t cnt = w.flags[AX_FLAG_FIXCNT];
+    if (cnt > w.fix_cap) cnt = w.fix_cap;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < cnt; i += nwarps) {
+        const int64_t slot = w.fix_list[i];
+        const int d = ax_find_owner(w.drop, w.n_drops, &AxDrop::edge_base, slot);
+        const AxDrop& dr = w.drop[d];
+        const AxState& st = w.st[d];
+        const int64_t j = slot - dr.edge_base;
+        const int k = ax_chunk_of_bit(w.chunk + dr.chunk_base, st.k0, st.n_chunks, j);
+        const AxChunk& ch = w.chunk[dr.chunk_base + k];
+        AxBitFix f;
+        f.d = d; f.i = w.edge_idx[dr.edge_base + ch.edge_off + (j - ch.bit_off)]; f.q0 = ch.s;
+        double acc[4];
+        ax_gwin_partial(ax_src(w, dr), f.i, f.q0, w.cfg[dr.cfg], lane, 32, acc);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+        if (lane == 0) { ax_bits_fix(w, slot, f, acc); ax_bits_decide(w, d, slot); }
+    }
+}
+
 // ------------------------------------------------------------------ bit edges (CTA per run() iteration)
 // ax_emit_item in parallel: head edges one per thread; the continuous part of the chunk's walk is read
 // off the canonical walk tile by tile (a warp per tile, a lane per crossing: the edge number is the tile's
 // running count plus the popcount below the lane's bit, no search); only the few edges stepped
 // explicitly before the walk joins the canonical one are produced by one thread.
-__global__ void __launch_bounds__(128) k_emit_chunk(AxWave w) {
+// mode 0: every iteration, magnitudes stored (the bit decisions follow in k_bits_chunk); 1: the same for the iterations
+// before k0 + nk_full only; 2: the later iterations with the bit decided on the spot (ax_emit_edge, fused); 3: the later
+// iterations in the two-step form (materialises the magnitudes when a caller asks for them: axctd_batch_bits)
+__global__ void __launch_bounds__(128) k_emit_chunk(AxWave w, int mode) {
     const int64_t cg = blockIdx.x;
     const int d = ax_find_owner(w.drop, w.n_drops, &AxDrop::chunk_base, cg);
     const AxDrop& dr = w.drop[d];
     AxState& st = w.st[d];
     const int k = (int)(cg - dr.chunk_base);
     if (!ax_emit_active(w, dr, st, k)) return;
+    if (mode == 1 && k >= st.k0 + w.nk_full) return;
+    if (mode >= 2 && k < st.k0 + w.nk_full) return;
+    const bool fused = mode == 2;
     AxChunk& ch = w.chunk[cg];
     const int ne = ch.n_edges;
     if (ne <= 0) return;
     const AxCfg& c = w.cfg[dr.cfg];
     const int nhe = ch.n_head_edges, npre = ch.n_pre;
     ax_emit_levels(w, dr, ch, (int)threadIdx.x, (int)blockDim.x);
-    for (int t = threadIdx.x; t < nhe; t += blockDim.x) ax_emit_edge(w, dr, st, c, ch, cg, k, t, 0);
+    for (int t = threadIdx.x; t < nhe; t += blockDim.x) ax_emit_edge(w, dr, st, c, ch, cg, k, t, 0, fused);
     if (threadIdx.x == 0 && npre > 0) {
         const uint8_t* nx = w.zc_nx + dr.zc_base;
         int64_t pos = ch.g_first;
-        for (int q = 0; q < npre; ++q) { ax_emit_edge(w, dr, st, c, ch, cg, k, nhe + q, pos); if (q < npre - 1) pos += nx[pos]; }
+        for (int q = 0; q < npre; ++q) { ax_emit_edge(w, dr, st, c, ch, cg, k, nhe + q, pos, fused); if (q < npre - 1) pos += nx[pos]; }
     }
     if (ch.merge_pos < 0) return;
     const uint64_t* cmask = w.cmask + dr.tile_base;
@@ -1649,7 +1685,7 @@ __global__ void __launch_bounds__(128) k_emit_chunk(AxWave w) {
             const int bit = lane + 32 * h;
             if ((m >> bit) & 1ull) {
                 const int64_t t = base + __popcll(cmask[tt] & ((1ull << bit) - 1ull));
-                if (t < ne) ax_emit_edge(w, dr, st, c, ch, cg, k, (int)t, tt * AX_TILE + bit);
+                if (t < ne) ax_emit_edge(w, dr, st, c, ch, cg, k, (int)t, tt * AX_TILE + bit, fused);
             }
         }
     }

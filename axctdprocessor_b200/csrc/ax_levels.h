@@ -398,7 +398,7 @@ AX_HDN inline void ax_offsets_item(const AxWave& w, int64_t d) {
 // AXCTDprocessor.py:413-429: bit edges of one chunk and the signal level of the
 // nearest power sample of THIS chunk for every edge.
 // One edge: t < n_head_edges comes from the exact head, otherwise `pos` is its dense crossing ordinal.
-AX_HD void ax_emit_edge(const AxWave& w, const AxDrop& dr, AxState& st, const AxCfg& c, AxChunk& ch, int64_t cg, int k, int t, int64_t pos) {
+AX_HD void ax_emit_edge(const AxWave& w, const AxDrop& dr, AxState& st, const AxCfg& c, AxChunk& ch, int64_t cg, int k, int t, int64_t pos, bool fused = false) {
     int64_t idx; double v1, v2;
     if (t < ch.n_head_edges) {
         idx = ch.s + w.head_idx[cg * (int64_t)w.head_zc_cap_max + t];
@@ -409,7 +409,25 @@ AX_HD void ax_emit_edge(const AxWave& w, const AxDrop& dr, AxState& st, const Ax
     }
     const int64_t eo = dr.edge_base + ch.edge_off + t;
     w.edge_idx[eo] = (int32_t)idx;
-    if (t < ch.n_edges - 1) { w.a1[dr.edge_base + ch.bit_off + t] = v1; w.a2[dr.edge_base + ch.bit_off + t] = v2; }
+    if (t < ch.n_edges - 1) {
+        const int64_t slot = dr.edge_base + ch.bit_off + t;
+        if (!fused) { w.a1[slot] = v1; w.a2[slot] = v2; }
+        else {
+            // the decision of ax_bits_decide right here (demodulate.py:109-114 with this iteration's scale); a bit whose
+            // two tones are within bit_tol of each other is listed for a double-precision window (k_bits_recheck), and only
+            // such bits keep their magnitudes
+            const double p2 = ax_mul(v2, ch.scale);
+            const double m = v1 > p2 ? v1 : p2;
+            w.bit[slot] = (v1 >= p2) ? 1 : 0;
+            if (fabs(v1 - p2) <= w.bit_tol * m) {
+                w.a1[slot] = v1; w.a2[slot] = v2;
+#if defined(__CUDA_ARCH__)
+                const int pos_l = atomicAdd(&w.flags[AX_FLAG_FIXCNT], 1);
+                if (pos_l < w.fix_cap) w.fix_list[pos_l] = slot; else w.flags[AX_FLAG_FIXOVF] = 1;
+#endif
+            }
+        }
+    }
     // np.argmin(np.abs(recent_pwrinds - ci)): nearest grid point, first on ties (:425,:428)
     if (ch.np > 0) {
         const int64_t off = idx - ch.s;

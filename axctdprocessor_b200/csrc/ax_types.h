@@ -254,7 +254,12 @@ struct AxWave {
     int32_t force_exact;
     int32_t streaming;           // 0: whole recordings; 1: a growing recording, only iterations that are complete are
                                  // decoded (AXCTDprocessor.py:293-304 with the end of the file still unknown); 2: its last run
-    int32_t* flags;              // [0] = any chain dirty, [1] = any capacity error
+    int32_t* flags;              // [0] = any chain dirty, [1] = any capacity error, [2] = another search round, [3] = fix list full, [4] = fix list length
+    // bit decisions made while the edges are emitted (k_emit_chunk, fused modes): iterations before k0 + nk_full keep
+    // the two-step form (they feed the scale calibration); later ones write bits directly and list the few bits whose
+    // decision needs a double-precision window (k_bits_recheck)
+    int32_t nk_full, pad_nk;
+    int64_t* fix_list; int64_t fix_cap;
 };
 
 // cos, sin of theta400, theta7500, thetadead for the AX_TB taps of a tone block (kernel parameter of k_stats_tones)
@@ -286,6 +291,8 @@ AX_HD void ax_state_defaults(AxState& st, const AxCfg& c) {
 #define AX_FLAG_DIRTY 0
 #define AX_FLAG_CAP 1
 #define AX_FLAG_MORE 2
+#define AX_FLAG_FIXOVF 3
+#define AX_FLAG_FIXCNT 4
 
 AX_HD void ax_raise(AxState& st, int code, int chunk) {
     if (st.status == 0) { st.status = code; st.status_chunk = chunk; }
