@@ -575,3 +575,44 @@ def test_engines_on_two_devices_in_one_process():
         b0.close()
     finally:
         e0.close(); e1.close()
+
+
+def test_random_parameter_sweep_matches_oracle(eng):
+    """BASELINE config 5 in miniature: sixteen drops decoded as ONE batch, every one with its own randomly drawn
+    parameter point (chunk 0.5-8 s, low-pass / band-pass, dead frequency, mark / space pair with a matching
+    transmitter, detector thresholds, trigger window) -- each compared with the oracle run with the same settings,
+    including the cases in which the reference raises."""
+    from axctdprocessor_b200 import engine as axengine
+    from oracle import axctd_oracle as ao
+    rng = np.random.default_rng(55)
+    cases = []
+    for i in range(16):
+        ms = [(400, 800), (405, 795), (420, 780)][int(rng.integers(0, 3))]
+        st = {"refreshrate": float(rng.choice([0.5, 0.75, 1.0, 2.0, 3.0, 4.0, 8.0])), "usebandpass": bool(rng.integers(0, 2)),
+              "deadfreq": float(rng.choice([2500.0, 2800.0, 3000.0, 3500.0])), "mark_space_freqs": [float(ms[0]), float(ms[1])],
+              "minr400": float(rng.choice([1.5, 2.0, 2.5])), "mindr7500": float(rng.choice([1.0, 1.5, 2.0]))}
+        trig = [[30, -1], [30, 40], [32, -1]][int(rng.integers(0, 3))]
+        spec = synth.DropSpec(fs=int(rng.choice([44100, 48000])), duration_s=float(rng.uniform(50.0, 72.0)), seed=5600 + i,
+                              snr_db=float(rng.uniform(8.0, 35.0)), mark_hz=ms[0], space_hz=ms[1],
+                              tone_after_pulse_s=float(rng.uniform(33.0, 37.0)))
+        cases.append((spec, st, trig))
+    pcms = [synth.generate_drop(s) for s, _, _ in cases]
+    cfgs = [eng.config(s.fs, settings=st, triggerrange=trig) for s, st, trig in cases]
+    b = eng.batch([len(p) for p in pcms], cfgs)
+    for i, p in enumerate(pcms):
+        b.upload(i, p)
+    b.run()
+    outs = [dict(result=b.result(i), bits=b.bits(i), edges=b.edges(i), power=b.power(i)) for i in range(len(cases))]
+    b.close()
+    n_ok = 0
+    for (spec, st, trig), p, out in zip(cases, pcms, outs):
+        try:
+            op = ao.process_pcm(p, spec.fs, settings=st, triggerrange=trig)
+        except Exception as exc:                       # the reference crashes on this point: the engine reports the same exception
+            code = out["result"].status
+            assert code != 0, (st, trig, type(exc))
+            assert issubclass(axengine.STATUS_EXCEPTIONS[code][0], type(exc)) or issubclass(type(exc), axengine.STATUS_EXCEPTIONS[code][0]), (code, type(exc))
+            continue
+        check_against_oracle(out, op)
+        n_ok += 1
+    assert n_ok >= 10
