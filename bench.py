@@ -439,7 +439,11 @@ def run_native(args):
 
     # ---- roofline of the dominant kernel (continuous filter / crossing / bit-DFT pass)
     peak, peak_src = measured_peak_gbs()
-    alg_bytes = 2.0 * total_samples + 12.0 * crossings            # int16 in, (idx i32, |S1| f32, |S2| f32) per crossing out
+    # 2 B per input sample + outputs (one byte per bit, 48 B per frame).  The kernel's own output
+    # is larger (12 B per crossing: index i32, |S1| f32, |S2| f32 -- intermediate records); that figure is kept beside it.
+    bits_total = int(sum(s.n_bits for s in stats))
+    alg_bytes = 2.0 * total_samples + 1.0 * bits_total + 48.0 * frames
+    alg_bytes_kernel = 2.0 * total_samples + 12.0 * crossings
     f_ms = float(np.mean(filt_ms))
     achieved = alg_bytes / (f_ms * 1e-3) / 1e9
     traffic = None
@@ -528,7 +532,10 @@ def run_native(args):
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "traffic_source": "profiles/filter_traffic.json: dram__bytes_read + dram__bytes_write of k_demod_fused per sample from one ncu --set full capture, scaled to this run's sample count (static, not re-measured here)",
                          "peak_source": peak_src, "kernel_ms": f_ms, "tone_kernels_ms": float(np.mean(tone_ms)),
-                         "algorithmic_bytes": alg_bytes, "note": "issue-bound: 7 FP64-pipe ops (2.2 issue cycles each on B200) + 4 IDP.2A + ~20 other instructions per sample; HBM is not the binding unit"},
+                         "algorithmic_bytes": alg_bytes,
+                         "algorithmic_bytes_definition": "SURVEY 8(d): 2 B x samples + 1 B x bits + 48 B x frames",
+                         "achieved_incl_crossing_records": alg_bytes_kernel / (f_ms * 1e-3) / 1e9,
+                         "frac_incl_crossing_records": alg_bytes_kernel / (f_ms * 1e-3) / 1e9 / peak, "note": "issue-bound: 7 FP64-pipe ops (2.2 issue cycles each on B200) + 4 IDP.2A + ~20 other instructions per sample; HBM is not the binding unit"},
             "decoded": {"frames": frames, "rows": rows, "drops_not_ok": bad}}
     if rank == 0 and world == 1 and not args.no_cpu:
         import tempfile
