@@ -120,28 +120,38 @@ AX_HD bool ax_sos_is_butter(const AxCfg& c) {
 // ------------------------------------------------------------------ bit windows
 // demodulate.py:99-102: |sum_m y[i+1+m] e^{j theta_f m}| for the mark and space tones over the
 // npcm samples after crossing i.  Only the magnitude is used, so the phase reference is free:
-// the window is evaluated over the aligned quads of samples that cover it, tap k of the first
-// quad carrying e^{j theta_f k}, with the taps outside the window masked to zero.  The samples
-// are the float roundings of the double-precision filter output and the sums run in fp32 (eight
-// chains); a decision that this precision cannot make is re-made from ax_gwin_* in double.
+// the window is evaluated over the nt = 4 * ax_win_quads(npcm) samples of the aligned quads that
+// cover it, the samples outside the window masked to zero, with the phase reference in the MIDDLE
+// of those nt taps: taps k and nt-1-k then carry conjugate phasors e^{-+j phi_k}, phi_k =
+// theta_f (nt/2 - 1/2 - k), so that
+//   Re S = sum_{k < nt/2} (y[k] + y[nt-1-k]) cos phi_k,   Im S = sum_{k < nt/2} (y[nt-1-k] - y[k]) sin phi_k:
+// two additions and four FMAs per PAIR of samples for both tones (the sum and the difference serve
+// both) instead of eight FMAs, and half the phasor loads.  tab[k], k < nt/2, holds (cos phi_k,
+// sin phi_k) of the mark and of the space tone (axctd_config_create).  The samples are the float
+// roundings of the double-precision filter output and the sums run in fp32 (eight chains); a
+// decision that this precision cannot make is re-made from ax_gwin_* in double.
 AX_HD int ax_win_quads(int npcm) { return (npcm + 6) >> 2; }     // quads covering offset o <= 3 plus npcm taps
 
 // yv[k], k < 4*ax_win_quads(npcm): samples of the aligned quads; o = (i + 1) & 3
 AX_HD void ax_window32(const float* yv, int o, int npcm, const AxF4* tab, float* a1, float* a2) {
     float r1a = 0.f, i1a = 0.f, r2a = 0.f, i2a = 0.f, r1b = 0.f, i1b = 0.f, r2b = 0.f, i2b = 0.f;
-    const int nt = 4 * ax_win_quads(npcm);
+    const int nt = 4 * ax_win_quads(npcm), nh = nt >> 1;        // nh is even
+    // tap k lies inside the window iff o <= k < o + npcm (o <= 3: only the first three and the last few taps can fall outside)
+#define AX_WIN_TAP(k) ((((k) >= 3 || (k) >= o) && ((k) < npcm || (k) < o + npcm)) ? yv[(k)] : 0.f)
 #pragma unroll
-    for (int k = 0; k < AX_WIN_TAPS; k += 2) {
-        if (k < nt) {
-            const float ya = (k >= o && k < o + npcm) ? yv[k] : 0.f;
-            const float yb = (k + 1 >= o && k + 1 < o + npcm) ? yv[k + 1] : 0.f;
+    for (int k = 0; k < AX_WIN_TAPS / 2; k += 2) {
+        if (k < nh) {
+            const float la = AX_WIN_TAP(k), ua = AX_WIN_TAP(nt - 1 - k);
+            const float lb = AX_WIN_TAP(k + 1), ub = AX_WIN_TAP(nt - 2 - k);
+            const float sa = la + ua, da = ua - la, sb = lb + ub, db = ub - lb;
             const AxF4 ta = tab[k], tb = tab[k + 1];                   // 16-byte broadcast loads (shared memory in k_demod_fused)
-            r1a = fmaf(ya, ta.x, r1a); i1a = fmaf(ya, ta.y, i1a);
-            r2a = fmaf(ya, ta.z, r2a); i2a = fmaf(ya, ta.w, i2a);
-            r1b = fmaf(yb, tb.x, r1b); i1b = fmaf(yb, tb.y, i1b);
-            r2b = fmaf(yb, tb.z, r2b); i2b = fmaf(yb, tb.w, i2b);
+            r1a = fmaf(sa, ta.x, r1a); i1a = fmaf(da, ta.y, i1a);
+            r2a = fmaf(sa, ta.z, r2a); i2a = fmaf(da, ta.w, i2a);
+            r1b = fmaf(sb, tb.x, r1b); i1b = fmaf(db, tb.y, i1b);
+            r2b = fmaf(sb, tb.z, r2b); i2b = fmaf(db, tb.w, i2b);
         }
     }
+#undef AX_WIN_TAP
     const float r1 = r1a + r1b, i1 = i1a + i1b, r2 = r2a + r2b, i2 = i2a + i2b;
     *a1 = sqrtf(fmaf(r1, r1, i1 * i1));
     *a2 = sqrtf(fmaf(r2, r2, i2 * i2));

@@ -187,6 +187,7 @@ struct axctd_engine {
     double opt_bit_tol = 2e-5;            // fp32 bit windows: relative distance to a decision boundary that triggers
     double opt_hist_tol = 2e-5;           //   the double-precision re-evaluation (bit decision / calibration histogram)
     int opt_bitfix_all = 0;               // test hook: re-evaluate every window
+    int opt_demod_probe = 0;              // timing probe (AxWave::probe)
     int opt_ws = 0;                       // warp-specialised fused kernel (k_demod_ws)
     int opt_bulk = 0;                     // continuous pass stages its rows with cp.async.bulk (TMA unit) instead of LDGSTS
     int opt_fir_first = 1;                // numerators-first cascade in the continuous low-pass pass (k_demod_fused FAST)
@@ -469,6 +470,7 @@ extern "C" int axctd_engine_set_option(axctd_engine* e, const char* name, double
     else if (s == "bit_tol") e->opt_bit_tol = v;
     else if (s == "hist_tol") e->opt_hist_tol = v;
     else if (s == "bitfix_all") e->opt_bitfix_all = (int)v;
+    else if (s == "demod_probe") e->opt_demod_probe = (int)v;
 #ifndef AXCTD_EMU
     else if (s == "pool") g_pool_on = v != 0.0;                              // block cache on / off (process-wide)
     else if (s == "pool_poison") g_pool_poison = v != 0.0;                   // test hook: recycled blocks are filled with 0xA5
@@ -556,9 +558,17 @@ extern "C" int axctd_config_create(axctd_engine* e, const axctd_config_desc* ds,
     c.half = (int64_t)(fs * 0.5);
     c.lut_len = ds->lut_len; c.n_hist_edges = ds->n_hist_edges;
     if (ds->bit_cs_len < AX_WIN_TAPS) { e->err = "bit_cs table shorter than 48 entries"; return AXCTD_ERR_ARG; }
-    for (int k = 0; k < AX_WIN_TAPS; ++k) {
-        const double* t4 = ds->bit_cs + 4 * (size_t)k;
-        c.win_tab.t[k].x = (float)t4[0]; c.win_tab.t[k].y = (float)t4[1]; c.win_tab.t[k].z = (float)t4[2]; c.win_tab.t[k].w = (float)t4[3];
+    {   // ax_window32: phase reference in the middle of the nt aligned taps, tab[k] = (cos, sin)(theta_f (nt/2 - 1/2 - k))
+        // for the mark and the space tone, k < nt/2; theta_f from entry 1 of the caller's table (= 2 pi f / f_s)
+        const double th1 = atan2(ds->bit_cs[4 + 1], ds->bit_cs[4 + 0]), th2 = atan2(ds->bit_cs[4 + 3], ds->bit_cs[4 + 2]);
+        // (a window longer than the table serves scan-only configurations: axctd_batch_run_async refuses to demodulate with it)
+        const int nh = ax_win_quads(c.npcm) * 4 <= AX_WIN_TAPS ? ax_win_quads(c.npcm) * 2 : 0;
+        for (int k = 0; k < AX_WIN_TAPS; ++k) {
+            const double ph = (double)nh - 0.5 - (double)k;
+            const bool in = k < nh;
+            c.win_tab.t[k].x = in ? (float)cos(th1 * ph) : 0.f; c.win_tab.t[k].y = in ? (float)sin(th1 * ph) : 0.f;
+            c.win_tab.t[k].z = in ? (float)cos(th2 * ph) : 0.f; c.win_tab.t[k].w = in ? (float)sin(th2 * ph) : 0.f;
+        }
     }
     {   // window responses G_f[d] = sum_m e^{j theta_f m} h[d - (npcm-1-m)] (ax_gwin_*): impulse response h of the
         // cascade in long double, long enough for its tail to fall below 1e-18
@@ -694,6 +704,7 @@ extern "C" int axctd_batch_create(axctd_engine* e, int n_drops, const int64_t* n
     w.seg_len = (int32_t)L; w.seg_cap = (int32_t)(L / 8 + 32);
     w.guard = e->opt_guard; w.tone_direct = e->opt_tone_direct; w.force_exact = e->opt_force_exact;
     w.bit_tol = e->opt_bit_tol; w.hist_tol = e->opt_hist_tol; w.bitfix_all = e->opt_bitfix_all;
+    w.probe = e->opt_demod_probe;
     w.head_zc_cap_max = head_cap_max;
     b->drops.resize(n_drops);
     int64_t pcm_off = 0, zc_off = 0, edge_off = 0, tb_off = 0, xf_off = 0, fwd_off = 0, zq_off = 0;
@@ -1044,6 +1055,13 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
     ax_heavy_begin(e);
     AX_EVENT(b, 1);
     const bool scan_only = e->opt_scan_only != 0;     // tone levels only: no crossings are produced
+    if (!scan_only)
+        for (const AxDrop& dr : b->drops)
+            if (ax_win_quads(e->cfgs[dr.cfg].npcm) * 4 > AX_WIN_TAPS) {
+                e->err = "bit window longer than the window table (npcm > 45): this rate can only be scanned, not demodulated";
+                ax_heavy_end(e); AX_HEAVY_LEAVE();
+                return AXCTD_ERR_ARG;
+            }
     if (scan_only) { if (ax_zero(e, w.seg_cnt, sizeof(int32_t) * (size_t)w.nseg_total)) { ax_heavy_end(e); AX_HEAVY_LEAVE(); return AXCTD_ERR_CUDA; } }
 #ifndef AXCTD_EMU
     bool fused = e->opt_filter_variant == 0;

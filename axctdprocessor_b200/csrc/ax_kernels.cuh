@@ -981,6 +981,9 @@ __global__ void __launch_bounds__(AX_FD_THREADS, 2) k_demod_fused(const __grid_c
                 unsigned long long m = 0ull;
                 if (hi > lo) m = ((hi >= 64) ? ~0ull : ((1ull << hi) - 1ull)) & ~((1ull << lo) - 1ull);
                 X &= m;
+#ifdef AX_DEMOD_PROBE
+                if (w.probe == 2) X = 0ull;
+#endif
             }
             // every lane works through the crossings of its own row (its own ring: no exchange, no barrier);
             // the warp iterates as often as its busiest lane has crossings
@@ -1002,8 +1005,13 @@ __global__ void __launch_bounds__(AX_FD_THREADS, 2) k_demod_fused(const __grid_c
                     const float4 v = *reinterpret_cast<const float4*>(ax_smem_raw + ((((q0b + 512u * k) & 0x3ff0u) | ring_hi)));
                     yv[4 * k] = v.x; yv[4 * k + 1] = v.y; yv[4 * k + 2] = v.z; yv[4 * k + 3] = v.w;
                 }
+#ifdef AX_DEMOD_PROBE
+                float m1 = yv[0], m2 = yv[NQ * 4 - 1];
+                if (w.probe != 1) ax_window32(yv, o, NPCM, sm.tab, &m1, &m2);
+#else
                 float m1, m2;
                 ax_window32(yv, o, NPCM, sm.tab, &m1, &m2);
+#endif
                 if (has) {
                     const int idx = base + p;
                     const bool complete = idx + NPCM < nstop;
@@ -2256,6 +2264,9 @@ __global__ void __launch_bounds__(256) k_compact_warp(AxWave w) {
     // latency: one round of 32 records at a time left two thirds of the bandwidth unused).
     const int64_t pos0 = dst - dr.zc_base;
     const int64_t br2 = 2 * (int64_t)c.bitrate;
+    // (2^20 * br2 stays below 2^31 and beyond 2 * fs2: every real rate)
+    const bool narrow = br2 > 0 && br2 < 2048 && c.fs2 > 0 && c.fs2 < (1 << 28) && (br2 << 20) > 2 * c.fs2;
+    const int32_t br2n = (int32_t)br2, fs2n = (int32_t)c.fs2;
     int32_t la[4] = {0, 0, 0, 0};
     bool have_la = false;
     for (int b0 = 0; b0 < cnt; b0 += 128) {
@@ -2284,14 +2295,28 @@ __global__ void __launch_bounds__(256) k_compact_warp(AxWave w) {
             w.zc_a2[dst + q] = v2[u];
             uint8_t nx = 0;
             if (pos0 + q + 4 < M) {                      // as ax_next: nearest to one bit period, first on ties
-                int64_t best = 0; int bj = 0;
+                int bj = 0;
+                if (narrow) {
+                    // 32-bit form: distances are capped at 2^20 samples, far beyond the bit period, where |d * br2 - fs2|
+                    // only grows with d (a capped candidate never beats an earlier one, capped or not: same choice)
+                    int32_t best = 0;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int qq = q + 1 + j;
-                    const int32_t z = qq < cnt ? w.rec_idx[src + qq] : la[qq - cnt];
-                    int64_t dd = ((int64_t)z - z0[u]) * br2 - c.fs2;
-                    if (dd < 0) dd = -dd;
-                    if (j == 0 || dd < best) { best = dd; bj = j; }
+                    for (int j = 0; j < 4; ++j) {
+                        const int qq = q + 1 + j;
+                        const int32_t z = qq < cnt ? w.rec_idx[src + qq] : la[qq - cnt];
+                        const int32_t dd = abs(min(z - z0[u], 1 << 20) * br2n - fs2n);
+                        if (j == 0 || dd < best) { best = dd; bj = j; }
+                    }
+                } else {
+                    int64_t best = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int qq = q + 1 + j;
+                        const int32_t z = qq < cnt ? w.rec_idx[src + qq] : la[qq - cnt];
+                        int64_t dd = ((int64_t)z - z0[u]) * br2 - c.fs2;
+                        if (dd < 0) dd = -dd;
+                        if (j == 0 || dd < best) { best = dd; bj = j; }
+                    }
                 }
                 nx = (uint8_t)(1 + bj);
             }

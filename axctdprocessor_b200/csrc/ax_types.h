@@ -248,7 +248,7 @@ struct AxWave {
     double bit_tol;              // |p1 - p2| <= bit_tol * max(p1, p2): the bit is re-decided from a double-precision window
     double hist_tol;             // conf within hist_tol (relative) of a histogram bin edge: re-evaluated before the scale calibration
     int32_t bitfix_all;          // test hook: re-evaluate every bit window in double precision
-    int32_t pad3;
+    int32_t probe;               // timing probe of k_demod_fused (builds with -DAX_DEMOD_PROBE only; option "demod_probe", results are wrong): 1 = window sums skipped, 2 = crossings not processed at all
     int32_t tone_direct;
     int32_t pa_lo, pa_hi;        // fixed-grid chunk range of the current detection round
     int32_t force_exact;
