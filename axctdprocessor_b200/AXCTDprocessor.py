@@ -26,10 +26,10 @@ def default_engine(device: int = 0) -> _engine.Engine:
     return _default_engines[device]
 
 
-def read_wav_pcm16(path):
-    """RIFF/WAVE reader for 16-bit PCM (what scipy.io.wavfile.read returns for
-    the recordings this processor handles, reference AXCTDprocessor.py:41):
-    (fs, int16 array of shape (n,) or (n, channels))."""
+def read_wav(path):
+    """RIFF/WAVE reader returning what scipy.io.wavfile.read returns (reference AXCTDprocessor.py:41): (fs, array
+    of shape (n,) or (n, channels)) with dtype uint8 -> widened to int16 here (exact), int16, int32 for 24-bit
+    (left-justified, as scipy stores it) and 32-bit PCM, int64 for 64-bit PCM, float32 / float64 for IEEE files."""
     with open(path, "rb") as f:
         data = f.read()
     if len(data) < 12 or data[0:4] != b"RIFF" or data[8:12] != b"WAVE":
@@ -52,19 +52,51 @@ def read_wav_pcm16(path):
     tag, nch, fs, bits = fmt
     if nch < 1:
         raise ValueError("malformed WAV file: the fmt chunk declares no channels")
+    bps = bits // 8
+    nval = (len(pcm) // (bps * nch)) * nch if bps else 0
     if tag == 1 and bits == 8:
         # scipy.io.wavfile.read returns uint8 for 8-bit PCM (the reference then subtracts the mean, :55-57): every
         # value fits the engine's int16 input exactly
-        a = np.frombuffer(pcm, dtype=np.uint8, count=(len(pcm) // nch) * nch).astype(np.int16)
+        a = np.frombuffer(pcm, dtype=np.uint8, count=nval).astype(np.int16)
     elif tag == 1 and bits == 16:
-        a = np.frombuffer(pcm, dtype="<i2", count=(len(pcm) // (2 * nch)) * nch)
+        a = np.frombuffer(pcm, dtype="<i2", count=nval)
+    elif tag == 1 and bits == 24:
+        raw = np.frombuffer(pcm, dtype=np.uint8, count=3 * nval).reshape(-1, 3)
+        wide = np.zeros((nval, 4), dtype=np.uint8)
+        wide[:, 1:] = raw                               # left-justified in 32 bits, as scipy stores 24-bit samples
+        a = wide.view("<i4").reshape(-1)
+    elif tag == 1 and bits in (32, 64):
+        a = np.frombuffer(pcm, dtype="<i4" if bits == 32 else "<i8", count=nval)
+    elif tag == 3 and bits in (32, 64):
+        a = np.frombuffer(pcm, dtype="<f4" if bits == 32 else "<f8", count=nval)
     else:
-        # 24 / 32-bit integer and float WAVs (which scipy also reads) do not fit the engine's int16 input without
-        # changing the reference's arithmetic (it normalises the samples as read): see INTEGRATION.md
-        raise NotImplementedError(f"only 8 / 16-bit PCM WAV is supported by the CUDA engine (format {tag}, {bits} bit)")
+        raise ValueError(f"Unknown wave file format: format tag {tag}, {bits} bit")
     if nch > 1:
         a = a.reshape(-1, nch)
     return fs, a
+
+
+read_wav_pcm16 = read_wav          # (name of earlier rounds)
+
+
+def normalised_signal(audiostream, fs):
+    """AXCTDprocessor.py:55-62 on the host, for recordings whose samples are not 8 / 16-bit integers: the same numpy
+    expressions as the reference ((x - mean) / max|x| in double precision; scipy.signal.decimate(pcm, 2) above
+    50 kHz).  The engine takes the result as it is (axctd_batch_upload_f64) -- int16 recordings never come here,
+    their normalisation and halving run on the GPU."""
+    from scipy import signal
+    pcm_dc = np.mean(audiostream)
+    pcm_ampl = np.max(np.abs(audiostream))
+    pcm = (audiostream.astype(np.float64) - pcm_dc) / pcm_ampl
+    if fs > 50000:
+        pcm = signal.decimate(pcm, 2)
+        fs /= 2
+    return np.ascontiguousarray(pcm, dtype=np.float64), fs
+
+
+class WidePCM(np.ndarray):
+    """Normalised double-precision signal of a recording with wide samples (what the reference's audiostream holds)."""
+    decimate = 3
 
 
 def _first_channel(snd):
@@ -100,7 +132,12 @@ def readAXCTDwavfile(inputfile, timerange):
 
 
 def _read_recording(inputfile, timerange, pick):
-    fs, snd = read_wav_pcm16(inputfile)
+    fs, snd = read_wav(inputfile)
+    if snd.dtype != np.int16:                            # 24 / 32-bit, float: normalised (and halved) on the host
+        pcm, fs = normalised_signal(_first_channel(snd), fs)
+        if timerange[1] > 0 or timerange[0] > 0:
+            raise NameError("name 'self' is not defined")    # :66 / :69
+        return pcm.view(WidePCM), fs
     audiostream = pick(snd).view(RawPCM)
     if fs > 50000:                                       # :60-62
         audiostream.decimate = 2
@@ -155,16 +192,20 @@ class AXCTD_Processor:
         self._engine = engine
         self._device = device
         if mode == "wired":
-            fs, snd = read_wav_pcm16(audiofile)
+            fs, snd = read_wav(audiofile)
             a = _frames(snd)
             if timerange[1] > 0:
                 a = a[:int(fs * timerange[1])]
             if timerange[0] > 0:
                 a = a[int(fs * timerange[0]):]
-            a = np.ascontiguousarray(a).view(RawPCM)
-            if fs > 50000:
-                a.decimate = 2
-                fs /= 2
+            if snd.dtype != np.int16:
+                a, fs = normalised_signal(_first_channel(a), fs)
+                a = a.view(WidePCM)
+            else:
+                a = np.ascontiguousarray(a).view(RawPCM)
+                if fs > 50000:
+                    a.decimate = 2
+                    fs /= 2
             self.audiostream, self.f_s = a, fs
         else:
             self.audiostream, self.f_s = _read_recording(audiofile, timerange, _frames)     # (frames as read: channel 0 is picked on the GPU)

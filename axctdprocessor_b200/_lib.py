@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libaxctd.so")
 
 MAX_SECTIONS = 6
-ABI_VERSION = 3          # AXCTD_ABI_VERSION of include/axctd.h
+ABI_VERSION = 4          # AXCTD_ABI_VERSION of include/axctd.h
 
 
 class ConfigDesc(C.Structure):
@@ -105,7 +105,7 @@ class SynthDesc(C.Structure):
 SYMBOLS = [
     "axctd_abi_version", "axctd_has_cuda", "axctd_struct_size", "axctd_engine_create", "axctd_engine_destroy", "axctd_last_error",
     "axctd_engine_set_option", "axctd_engine_set_stream", "axctd_engine_launch_count", "axctd_config_create", "axctd_batch_create",
-    "axctd_batch_destroy", "axctd_batch_upload", "axctd_batch_upload_interleaved", "axctd_batch_copy_from", "axctd_batch_device_pcm", "axctd_batch_run",
+    "axctd_batch_destroy", "axctd_batch_upload", "axctd_batch_upload_interleaved", "axctd_batch_upload_f64", "axctd_batch_copy_from", "axctd_batch_device_pcm", "axctd_batch_run",
     "axctd_batch_run_async", "axctd_batch_finish", "axctd_batch_timing", "axctd_batch_phase_ms", "axctd_batch_summary",
     "axctd_batch_rows", "axctd_batch_frames", "axctd_batch_chunks", "axctd_batch_bits", "axctd_batch_edges", "axctd_batch_power",
     "axctd_synth_fill", "axctd_batch_download", "axctd_calib_eval",
@@ -132,6 +132,7 @@ def bind(lib: C.CDLL) -> C.CDLL:
         "axctd_batch_destroy": (None, [vp]),
         "axctd_batch_upload": (i32, [vp, i32, vp, i64]),
         "axctd_batch_upload_interleaved": (i32, [vp, i32, vp, i64, i32]),
+        "axctd_batch_upload_f64": (i32, [vp, i32, vp, i64]),
         "axctd_batch_copy_from": (i32, [vp, i32, vp, i32, i64, i64]),
         "axctd_batch_device_pcm": (i32, [vp, i32, P(vp)]),
         "axctd_batch_run": (i32, [vp]),

@@ -337,6 +337,7 @@ struct axctd_batch {
     bool force_nofuse = false;            // repeat of a run whose list of bits to re-evaluate overflowed
     bool ran_fused = false, mags_full = true;   // the last run decided bits in k_emit_chunk; magnitudes of every bit are on the device
     bool ran = false, finished = false;
+    bool any_f64in = false;               // a drop takes its samples through axctd_batch_upload_f64 (config decimate = 3)
     bool lent = false;                    // another engine's stream has read this batch's PCM (axctd_batch_copy_from)
     // streaming decode (axctd_batch_stream_*): drops hold growing recordings, `drops` carries their current lengths
     bool streaming = false, stream_closed = false, in_stream_run = false;
@@ -519,7 +520,7 @@ extern "C" int axctd_config_create(axctd_engine* e, const axctd_config_desc* ds,
     c.head = e->opt_exact_head > 0 ? e->opt_exact_head : warm;
     if (c.head < c.pad + 8) c.head = c.pad + 8;
     c.head_zc_cap = c.head / 4 + 64;
-    c.decimate = ds->decimate == 2 ? 2 : 1;
+    c.decimate = ds->decimate == 2 ? 2 : ds->decimate == 3 ? 3 : 1;      // 3: the samples arrive as the normalised double-precision signal
     if (c.decimate == 2) {
         if (ds->decim_sections < 1 || ds->decim_sections > AX_MAXSEC || ds->decim_padlen < 1 ||
             !(ds->decim_pole_radius > 0.0 && ds->decim_pole_radius < 1.0)) { e->err = "bad decimator description"; return AXCTD_ERR_ARG; }
@@ -731,10 +732,12 @@ extern "C" int axctd_batch_create(axctd_engine* e, int n_drops, const int64_t* n
         AxDrop& dr = b->drops[d];
         const int64_t n_raw = n_samples[d];
         const bool dec = c.decimate == 2;
+        const bool f64in = c.decimate == 3;                           // axctd_batch_upload_f64: no int16 samples at all
         const int64_t n = dec ? (n_raw + 1) / 2 : n_raw;              // len(y[::2])
-        dr.pcm_off = pcm_off; dr.n = n; dr.n_raw = n_raw; dr.cfg = config_id[d];
-        pcm_off += ((n_raw + 63) / 64) * 64 + 64;
+        dr.pcm_off = pcm_off; dr.n = n; dr.n_raw = f64in ? 0 : n_raw; dr.cfg = config_id[d];
+        pcm_off += f64in ? 64 : ((n_raw + 63) / 64) * 64 + 64;
         dr.xf_off = -1; dr.fwd_off = -1; dr.dseg_base = dseg_off; dr.ndseg = 0;
+        if (f64in) { dr.xf_off = xf_off; xf_off += ((n + 63) / 64) * 64 + 64; b->any_f64in = true; }
         if (dec) {
             if (n_raw < 2 * (int64_t)c.dpad + 2) { e->err = "recording too short to decimate"; axctd_batch_destroy(b); return AXCTD_ERR_ARG; }
             const int64_t E = n_raw + 2 * (int64_t)c.dpad;
@@ -743,8 +746,8 @@ extern "C" int axctd_batch_create(axctd_engine* e, int n_drops, const int64_t* n
             dr.ndseg = (int32_t)((E + DL - 1) / DL); dseg_off += ((dr.ndseg + 31) / 32) * 32;   // a warp of k_decim_fused stays inside one drop
         }
         dr.seg_base = seg_off; dr.nseg = (int32_t)((n + L - 1) / L); seg_off += ((dr.nseg + 127) / 128) * 128;
-        dr.slab_base = slab_off; dr.nslab = (int32_t)((n_raw + AX_STAT_SLAB - 1) / AX_STAT_SLAB); slab_off += dr.nslab;
-        dr.tb_base = tb_off; dr.ntb = (int32_t)(n / AX_TB); tb_off += dr.ntb; ntb_max = std::max(ntb_max, (int32_t)((n_raw + AX_TB - 1) / AX_TB));
+        dr.slab_base = slab_off; dr.nslab = (int32_t)(((f64in ? 0 : n_raw) + AX_STAT_SLAB - 1) / AX_STAT_SLAB); slab_off += dr.nslab;
+        dr.tb_base = tb_off; dr.ntb = (int32_t)(n / AX_TB); tb_off += dr.ntb; ntb_max = std::max(ntb_max, (int32_t)(((f64in ? 0 : n_raw) + AX_TB - 1) / AX_TB));
         dr.zc_base = zc_off; dr.zc_cap = n / e->opt_zc_div + 4096; zc_off += ((dr.zc_cap + 8 + 63) / 64) * 64;   // (64-aligned: k_tiles_reg loads a tile's walk steps as four 16-byte words)
         dr.zq_base = zq_off; zq_off += n / AX_ZQ + 2;
         dr.tile_base = tile_off; dr.tile_cap = (int32_t)(dr.zc_cap / AX_TILE + 1); tile_off += dr.tile_cap;
@@ -837,15 +840,26 @@ extern "C" int axctd_batch_create(axctd_engine* e, int n_drops, const int64_t* n
 }
 
 extern "C" int axctd_batch_upload(axctd_batch* b, int drop, const int16_t* pcm, int64_t n) {
-    if (!b || b->streaming || drop < 0 || drop >= b->n || !pcm || n != b->drops[drop].n_raw) return AXCTD_ERR_ARG;
+    if (!b || b->streaming || drop < 0 || drop >= b->n || !pcm || n != b->drops[drop].n_raw ||
+        b->eng->cfgs[b->drops[drop].cfg].decimate == 3) return AXCTD_ERR_ARG;
     AX_DEV(b->eng);
     if (ax_h2d(b->eng, b->d_pcm + b->drops[drop].pcm_off, pcm, sizeof(int16_t) * n)) return AXCTD_ERR_CUDA;
     b->ran = false;
     return AXCTD_OK;
 }
 
+extern "C" int axctd_batch_upload_f64(axctd_batch* b, int drop, const double* samples, int64_t n) {
+    if (!b || b->streaming || drop < 0 || drop >= b->n || !samples || b->eng->cfgs[b->drops[drop].cfg].decimate != 3 ||
+        n != b->drops[drop].n) return AXCTD_ERR_ARG;
+    AX_DEV(b->eng);
+    if (ax_h2d(b->eng, b->w.xf + b->drops[drop].xf_off, samples, sizeof(double) * n)) return AXCTD_ERR_CUDA;
+    b->ran = false;
+    return AXCTD_OK;
+}
+
 extern "C" int axctd_batch_upload_interleaved(axctd_batch* b, int drop, const int16_t* frames, int64_t n_frames, int channels) {
-    if (!b || b->streaming || drop < 0 || drop >= b->n || !frames || channels < 1 || n_frames != b->drops[drop].n_raw) return AXCTD_ERR_ARG;
+    if (!b || b->streaming || drop < 0 || drop >= b->n || !frames || channels < 1 || n_frames != b->drops[drop].n_raw ||
+        b->eng->cfgs[b->drops[drop].cfg].decimate == 3) return AXCTD_ERR_ARG;
     if (channels == 1) return axctd_batch_upload(b, drop, frames, n_frames);
     axctd_engine* e = b->eng;
     AX_DEV(e);
@@ -867,7 +881,8 @@ extern "C" int axctd_batch_upload_interleaved(axctd_batch* b, int drop, const in
 
 extern "C" int axctd_batch_copy_from(axctd_batch* b, int drop, axctd_batch* src, int src_drop, int64_t src_offset, int64_t n) {
     if (!b || !src || b->streaming || drop < 0 || drop >= b->n || src_drop < 0 || src_drop >= src->n || n != b->drops[drop].n_raw ||
-        src_offset < 0 || src_offset + n > src->drops[src_drop].n_raw || b->eng->device != src->eng->device) return AXCTD_ERR_ARG;
+        src_offset < 0 || src_offset + n > src->drops[src_drop].n_raw || b->eng->device != src->eng->device ||
+        b->eng->cfgs[b->drops[drop].cfg].decimate == 3) return AXCTD_ERR_ARG;
     axctd_engine* e = b->eng;
     AX_DEV(e);
     const int16_t* from = src->d_pcm + src->drops[src_drop].pcm_off + src_offset;
@@ -991,6 +1006,7 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
     {   // one pass over the PCM: statistics and the tone block sums, one launch per rate class in use
         for (size_t ci = 0; ci < e->cfgs.size(); ++ci) {
             if (!std::any_of(b->drops.begin(), b->drops.end(), [&](const AxDrop& d) { return d.cfg == (int)ci; })) continue;
+            if (e->cfgs[ci].decimate == 3 || w.ntb_max <= 0) continue;      // drops given as a double-precision signal hold no int16 samples
             const dim3 stm_grid((unsigned)((w.ntb_max + AX_STM_GROUPS * AX_ST_THREADS - 1) / (AX_STM_GROUPS * AX_ST_THREADS)), (unsigned)n);
 #define AX_HYB(KD) do { ax_optin_smem<k_stats_tones_hyb<KD>>(AX_STM_SMEM, e->device); \
                         k_stats_tones_hyb<KD><<<stm_grid, AX_ST_THREADS, AX_STM_SMEM, e->stream>>>(w, e->cfgs[ci].tone_tab8, e->tone_tabs[ci], (int)ci); } while (0)
@@ -1009,8 +1025,8 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
     if (!streaming) { AX_LAUNCH(e, k_stats, (int64_t)w.nslab_total, w); }
 #endif
     if (!streaming) { AX_LAUNCH(e, k_stats_fin, n, w); }        // (streaming: the normalisation was fixed by the caller)
-    const bool any_dec = b->dseg_total > 0;
-    if (any_dec) {       // recordings above 50 kHz: halve them on the device (AXCTDprocessor.py:60-62)
+    const bool any_dec = b->dseg_total > 0 || b->any_f64in;      // drops whose samples are doubles (w.xf)
+    if (b->dseg_total > 0) {       // recordings above 50 kHz: halve them on the device (AXCTDprocessor.py:60-62)
 #ifndef AXCTD_EMU
         bool dfused = e->opt_filter_variant == 0;
         int dpar = -1;
@@ -1029,6 +1045,8 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
             AX_LAUNCH(e, k_decim, b->dseg_total, w, 0);
             AX_LAUNCH(e, k_decim, b->dseg_total, w, 1);
         }
+    }
+    if (any_dec) {
         AX_LAUNCH(e, k_decim_fin, n, w);
 #ifndef AXCTD_EMU
         w.only_xf = 1;

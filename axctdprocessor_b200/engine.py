@@ -210,6 +210,10 @@ class Engine:
 
     def close(self):
         if getattr(self, "h", None):
+            # batches that are still open hold device blocks of this engine: release them first (a Batch that is
+            # garbage-collected after its engine would otherwise hand a dangling engine pointer to the library)
+            for b in list(getattr(self, "_live_batches", ())):
+                b.close()
             self.lib.axctd_engine_destroy(self.h)
             self.h = None
 
@@ -304,6 +308,10 @@ class Batch:
             raise RuntimeError(f"axctd_batch_create failed ({rc}): {eng.error()}")
         self.h = h
         self.n_samples = [int(x) for x in n_samples]
+        if not hasattr(eng, "_live_batches"):
+            import weakref
+            eng._live_batches = weakref.WeakSet()
+        eng._live_batches.add(self)
 
     def close(self):
         if getattr(self, "h", None):
@@ -323,6 +331,11 @@ class Batch:
     def upload(self, i: int, pcm: np.ndarray):
         """Mono samples (n,), or frames (n, channels) as scipy.io.wavfile.read returns them: the first channel
         is picked on the device (AXCTDprocessor.py:46-52)."""
+        if isinstance(pcm, np.ndarray) and pcm.dtype == np.float64 and self.configs[i].decimate == 3:
+            # the normalised signal of a recording with wide samples (24 / 32-bit, float: AXCTDprocessor.normalised_signal)
+            pcm = np.ascontiguousarray(pcm)
+            self._check(self.lib.axctd_batch_upload_f64(self.h, i, pcm.ctypes.data, pcm.size), "axctd_batch_upload_f64")
+            return
         pcm = np.ascontiguousarray(pcm, dtype=np.int16)
         if pcm.ndim == 2:
             self._check(self.lib.axctd_batch_upload_interleaved(self.h, i, pcm.ctypes.data, pcm.shape[0], pcm.shape[1]),

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define AXCTD_ABI_VERSION 3
+#define AXCTD_ABI_VERSION 4
 #define AXCTD_MAX_SECTIONS 6
 
 /* ---- return codes of API calls ---------------------------------------- */
@@ -82,7 +82,8 @@ typedef struct axctd_config_desc {
     int32_t n_hist_edges;
     /* /2 decimation of recordings above 50 kHz (AXCTDprocessor.py:60-62): scipy.signal.decimate(pcm, 2) =
      * sosfiltfilt(cheby1(8, 0.05, 0.4, output='sos'), pcm)[::2] with odd padding; fs above is then f_s/2. */
-    int32_t decimate;           /* 0 / 1: none, 2: the batch is given the raw recording and halves it on the device */
+    int32_t decimate;           /* 0 / 1: none, 2: the batch is given the raw recording and halves it on the device,
+                                   3: the batch is given the normalised double-precision signal (axctd_batch_upload_f64) */
     int32_t decim_sections;     /* rows of decim_sos (4) */
     int32_t decim_padlen;       /* sosfiltfilt's default padlen (27) */
     double  decim_sos[AXCTD_MAX_SECTIONS][6];
@@ -213,6 +214,12 @@ int  axctd_batch_upload(axctd_batch* b, int drop, const int16_t* pcm, int64_t n)
  * samples): the frames are copied as they are and the first channel is picked on the device
  * (AXCTDprocessor.py:46-52, `audiostream = snd[:,0]`).  n_frames counts frames. */
 int  axctd_batch_upload_interleaved(axctd_batch* b, int drop, const int16_t* frames, int64_t n_frames, int channels);
+/* Recordings whose samples are not 8 / 16-bit integers (24 / 32-bit PCM and float WAV files, which
+ * scipy.io.wavfile.read also returns, AXCTDprocessor.py:41): the host forms (x - mean) / max|x| in double precision
+ * exactly as AXCTDprocessor.py:55-57 does (and halves recordings above 50 kHz as :60-62 does) and hands the result
+ * over; the drop's config must have decimate == 3 and n is the length of that signal.  The int16 statistics
+ * (pcm_sum, pcm_ampl) of such a drop are not defined. */
+int  axctd_batch_upload_f64(axctd_batch* b, int drop, const double* samples, int64_t n);
 /* Fill a drop from samples that are already on the device: n samples of drop src_drop of batch src (same GPU), from
  * sample src_offset on.  This is how the segments of a long recording (segment.py: one upload, many drops) and the
  * points of a parameter sweep over one archive reach their batch without a second host->device copy. */

@@ -54,6 +54,10 @@ CASES = {
     # mean7500pwr is NaN); it then overwrites profstartind while firstpointtime keeps the old value
     "g44_timeout": (dict(fs=44100, duration_s=64.0, seed=14, snr_db=25.0), {}, [30, 41], True),
     "g44_timeout_notone": (dict(fs=44100, duration_s=60.0, seed=15, snr_db=25.0, tone_amp=0.0), {}, [30, 36], True),
+    # sample formats other than 16-bit PCM (scipy reads them too, AXCTDprocessor.py:41): WIDE below names the format
+    "g44_pcm24": (dict(fs=44100, duration_s=52.0, seed=16, snr_db=20.0), {}, None, True),
+    "g48_float32": (dict(fs=48000, duration_s=52.0, seed=17, snr_db=30.0), {}, None, True),
+    "g96_pcm24_decim": (dict(fs=96000, duration_s=52.0, seed=18, snr_db=25.0), {}, None, True),
     "config1_720s": (dict(fs=44100, duration_s=720.0, seed=1, snr_db=40.0), {}, None, False),
     "config2_720s": (dict(fs=44100, duration_s=720.0, seed=1, snr_db=10.0), {}, None, False),
     # BASELINE config 5 stand-in: a 30-minute recording at 8 dB SNR decoded with a swept parameter point
@@ -61,6 +65,10 @@ CASES = {
     "config5_1800s": (dict(fs=44100, duration_s=1800.0, seed=5, snr_db=8.0),
                       {"refreshrate": 4.0, "deadfreq": 2500.0, "mark_space_freqs": [405.0, 795.0]}, None, False),
 }
+
+
+# cases whose WAV file holds synth.widen(pcm, format, seed) instead of the int16 drop
+WIDE = {"g44_pcm24": "pcm24", "g48_float32": "float32", "g96_pcm24_decim": "pcm24"}
 
 
 def _sha(a) -> str:
@@ -85,7 +93,10 @@ def make_case(name: str) -> None:
     pcm = synth.generate_drop(spec)
     with tempfile.TemporaryDirectory() as td:
         wav = os.path.join(td, name + ".wav")
-        synth.write_wav(wav, pcm, spec.fs)
+        if name in WIDE:
+            synth.write_wav_wide(wav, synth.widen(pcm, WIDE[name], spec.seed), spec.fs, WIDE[name])
+        else:
+            synth.write_wav(wav, pcm, spec.fs)
         t0 = time.time()
         err = None
         try:
@@ -96,7 +107,7 @@ def make_case(name: str) -> None:
         dt = time.time() - t0
     meta = dict(name=name, spec=spec_kw, user_settings=user_settings, triggerrange=trig,
                 pcm_sha256=synth.pcm_sha256(pcm), reference_seconds=dt, error=err,
-                generator="oracle/make_golden.py", numpy=np.__version__)
+                generator="oracle/make_golden.py", numpy=np.__version__, wav_format=WIDE.get(name))
     arrays = {}
     if ap is not None:
         edges = ap._all_edges

@@ -308,6 +308,50 @@ def write_wav(path: str, pcm: np.ndarray, fs: int) -> None:
         f.write(data)
 
 
+# Sample formats other than 16-bit PCM (scipy.io.wavfile.read, reference AXCTDprocessor.py:41, returns int32 for 24 /
+# 32-bit PCM -- 24-bit left-justified -- and float32 / float64 for IEEE files)
+WIDE_FORMATS = ("pcm24", "pcm32", "float32", "float64")
+
+
+def widen(pcm: np.ndarray, fmt: str, seed: int = 0) -> np.ndarray:
+    """The int16 drop re-quantised to a wider sample format with seeded low-order detail, so that the samples are
+    not representable in 16 bits: what a 24-bit / float recorder would have stored."""
+    rng = np.random.default_rng(777000 + seed)
+    x = np.ascontiguousarray(pcm).astype(np.int64)
+    if fmt == "pcm24":
+        return (x * 256 + rng.integers(-128, 128, size=x.shape)).astype(np.int32)          # 24-bit values
+    if fmt == "pcm32":
+        return (x * 65536 + rng.integers(-32768, 32768, size=x.shape)).astype(np.int32)
+    if fmt == "float32":
+        return ((x + rng.uniform(-0.5, 0.5, size=x.shape)) / 32768.0).astype(np.float32)
+    if fmt == "float64":
+        return (x + rng.uniform(-0.5, 0.5, size=x.shape)) / 32768.0
+    raise KeyError(fmt)
+
+
+def write_wav_wide(path: str, samples: np.ndarray, fs: int, fmt: str) -> None:
+    """RIFF/WAVE writer for widen()'s formats: 24-bit PCM (three bytes per sample), 32-bit PCM, IEEE float 32 / 64."""
+    a = np.ascontiguousarray(samples)
+    nch = 1 if a.ndim == 1 else a.shape[1]
+    if fmt == "pcm24":
+        b = a.astype("<i4").reshape(-1, 1).view(np.uint8).reshape(-1, 4)[:, :3].tobytes()
+        tag, bits = 1, 24
+    elif fmt == "pcm32":
+        b, tag, bits = a.astype("<i4").tobytes(), 1, 32
+    elif fmt == "float32":
+        b, tag, bits = a.astype("<f4").tobytes(), 3, 32
+    elif fmt == "float64":
+        b, tag, bits = a.astype("<f8").tobytes(), 3, 64
+    else:
+        raise KeyError(fmt)
+    bps = bits // 8
+    with open(path, "wb") as f:
+        f.write(b"RIFF" + struct.pack("<I", 36 + len(b)) + b"WAVE")
+        f.write(b"fmt " + struct.pack("<IHHIIHH", 16, tag, nch, fs, fs * nch * bps, nch * bps, bits))
+        f.write(b"data" + struct.pack("<I", len(b)))
+        f.write(b)
+
+
 # Named workloads (BASELINE.json configs)
 def config_spec(name: str, seed: int = 1) -> DropSpec:
     if name == "config1":      # 44.1 kHz, 12 min, 40 dB, default lowpass

@@ -12,6 +12,7 @@ SMALL_CASES = ["g44_40db", "g44_10db", "g48_25db", "g44_stereo", "g44_bandpass",
                "g44_chunk4", "g44_nopulse", "g44_chunk05", "g48_chunk8", "g44_marksp", "g48_marksp_tx",
                "g44_timeout", "g44_timeout_notone"]
 DECIM_CASES = ["g96_decim"]
+WIDE_CASES = ["g44_pcm24", "g48_float32", "g96_pcm24_decim"]      # 24-bit PCM / IEEE float WAV files
 FULL_CASES = ["config1_720s", "config2_720s", "config5_1800s"]
 
 _pcm_cache = {}
@@ -35,6 +36,11 @@ class Golden:
             _pcm_cache.clear()
             _pcm_cache[self.name] = p
         return _pcm_cache[self.name]
+
+    def wide(self):
+        """(samples, format) of a WIDE_CASES fixture's WAV file: the drop re-quantised as oracle/make_golden.py did."""
+        fmt = self.meta["wav_format"]
+        return synth.widen(self.pcm(), fmt, self.spec.seed), fmt
 
     @property
     def bits(self):

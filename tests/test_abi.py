@@ -36,7 +36,7 @@ def test_struct_sizes_agree(lib):
     from axctdprocessor_b200 import _lib
     for which, st in enumerate((_lib.ConfigDesc, _lib.DropSummary, _lib.Frame, _lib.Chunk)):
         assert lib.axctd_struct_size(which) == C.sizeof(st)
-    assert lib.axctd_abi_version() == _lib.ABI_VERSION == 3 and lib.axctd_has_cuda() == 1
+    assert lib.axctd_abi_version() == _lib.ABI_VERSION == 4 and lib.axctd_has_cuda() == 1
 
 
 def test_no_cpu_fallback_without_gpu(lib):
