@@ -192,6 +192,7 @@ struct axctd_engine {
     int opt_bulk = 0;                     // continuous pass stages its rows with cp.async.bulk (TMA unit) instead of LDGSTS
     int opt_fir_first = 1;                // numerators-first cascade in the continuous low-pass pass (k_demod_fused FAST)
     int opt_tone_mma = 1;                 // tone block sums on the FP64 tensor cores (k_stats_tones_mma)
+    int opt_tone_int8 = 1;                // ... as exact integer products on the int8 tensor cores instead (k_stats_tones_imma); 0: FP64 tensor cores
     int opt_heavy_chain = 1;              // engines of one process take turns with the demodulation pass (see ax_heavy_*)
     int opt_nosync = 1;                   // enqueue the whole decode without host round trips (see axctd_batch_run_async)
     int opt_scan_only = 0;                // tone levels only (segmentation of long recordings): skip the demodulation pass
@@ -464,6 +465,7 @@ extern "C" int axctd_engine_set_option(axctd_engine* e, const char* name, double
     else if (s == "bulk") e->opt_bulk = (int)v;
     else if (s == "heavy_prio") e->opt_heavy_prio = (int)v;
     else if (s == "tone_mma") e->opt_tone_mma = (int)v;
+    else if (s == "tone_int8") e->opt_tone_int8 = (int)v;
     else if (s == "heavy_chain") e->opt_heavy_chain = (int)v;
     else if (s == "scan_only") e->opt_scan_only = (int)v;
     else if (s == "nosync") e->opt_nosync = (int)v;
@@ -624,6 +626,23 @@ extern "C" int axctd_config_create(axctd_engine* e, const axctd_config_desc* ds,
         for (int m = 0; m < AX_TB && m < c.n_power; ++m)
             for (int q = 0; q < 6; ++q) t8[8 * (size_t)m + q] = ds->tone_cs[6 * (size_t)m + q];
         if (ax_cfg_upload(e, &c.tone_tab8, t8.data(), t8.size())) return AXCTD_ERR_CUDA;
+#ifndef AXCTD_EMU
+        // k_stats_tones_imma: P = round(p * 2^45) = sum_j d_j 256^j with signed digits; word layout [k-step][digit][lane][2]:
+        // lane = 4 g + t holds column g, samples 32 ks + 4 t + i (word 0) and 32 ks + 16 + 4 t + i (word 1) in byte i
+        std::vector<uint32_t> ti(AX_STI_TAB_WORDS, 0u);
+        for (int m = 0; m < AX_TB && m < c.n_power; ++m)
+            for (int q = 0; q < 6; ++q) {
+                long long P = llround(ldexp(t8[8 * (size_t)m + q], AX_STI_SHIFT));
+                const int ks = m >> 5, kk = m & 31, half = kk >> 4, tt = (kk & 15) >> 2, bi = kk & 3;
+                for (int j = 0; j < AX_STI_DIGITS; ++j) {
+                    const int dg = (int)(((P & 0xff) ^ 0x80) - 0x80);
+                    P = (P - dg) >> 8;
+                    ti[(((size_t)ks * AX_STI_DIGITS + j) * 32 + 4 * q + tt) * 2 + half] |= (uint32_t)(dg & 0xff) << (8 * bi);
+                }
+                if (P != 0) { e->err = "tone phasor outside the digit range"; return AXCTD_ERR_ARG; }
+            }
+        if (ax_cfg_upload(e, &c.tone_tabi, ti.data(), ti.size())) return AXCTD_ERR_CUDA;
+#endif
     }
     e->cfgs.push_back(c);
     e->tone_tabs.push_back(ttab);
@@ -1012,6 +1031,10 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
                         k_stats_tones_hyb<KD><<<stm_grid, AX_ST_THREADS, AX_STM_SMEM, e->stream>>>(w, e->cfgs[ci].tone_tab8, e->tone_tabs[ci], (int)ci); } while (0)
             if (e->opt_tone_mma >= 2) {           // block sums split between the tensor cores and the vector pipe: 4 * (value) of every 64 samples on the tensor cores
                 if (e->opt_tone_mma <= 8) AX_HYB(8); else if (e->opt_tone_mma <= 10) AX_HYB(10); else if (e->opt_tone_mma <= 12) AX_HYB(12); else AX_HYB(14);
+            } else if (e->opt_tone_mma && e->opt_tone_int8) {
+                ax_optin_smem<k_stats_tones_imma>(AX_STI_SMEM, e->device);
+                const dim3 sti_grid((unsigned)((w.ntb_max + AX_STI_GROUPS * AX_ST_THREADS - 1) / (AX_STI_GROUPS * AX_ST_THREADS)), (unsigned)n);
+                k_stats_tones_imma<<<sti_grid, AX_ST_THREADS, AX_STI_SMEM, e->stream>>>(w, e->cfgs[ci].tone_tabi, (int)ci);
             } else if (e->opt_tone_mma) {
                 ax_optin_smem<k_stats_tones_mma>(AX_STM_SMEM, e->device);
                 k_stats_tones_mma<<<stm_grid, AX_ST_THREADS, AX_STM_SMEM, e->stream>>>(w, e->cfgs[ci].tone_tab8, (int)ci);

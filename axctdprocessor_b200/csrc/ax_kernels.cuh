@@ -330,6 +330,186 @@ __global__ void __launch_bounds__(AX_ST_THREADS) k_stats_tones_mma(const __grid_
     }
 }
 
+// The same pass with the block sums as EXACT INTEGER products on the int8 tensor cores (IMMA.16832, 8.4 cycles per
+// instruction and scheduler on B200 against 16.5 for a DMMA that does a sixteenth of the multiply-adds:
+// tools/ubench_imma.cu).  A sample is two 8-bit slices, x = 256 xh + xl (xh signed, xl unsigned); a phasor is
+// quantised to P = round(p * 2^45) and written with six signed base-256 digits, P = sum_j d_j 256^j, d_j in
+// [-128, 127] (axctd_config_create).  Every product slice x digit is an m16n8k32 tile product -- 16 tone blocks x 32
+// samples x 8 columns (six used) -- accumulated exactly in int32 over the block's 256 samples (|sum| < 2^24); slices
+// of equal weight share an accumulator (xh d_(e-1) and xl d_e both weigh 256^e), and the block sum is
+// sum_e acc_e 256^e * 2^-45, formed in double at the end.  The result is the exact sum of x[n] P[n]: it differs from
+// the double-precision sum only by the quantisation of the phasors, <= 2^-46 each, i.e. <= 1.2e-7 on a block sum of
+// full-scale samples (relative 1e-13; the FP64 sum itself rounds at 1e-10 absolute on such a block).  Twelve IMMAs per
+// tile and k-step = 0.023 per sample: 0.7 ms of tensor time for the 128-drop batch, below the 1.3 ms its PCM takes to
+// stream from HBM -- the pass becomes bandwidth-bound.
+// Fragments (PTX m16n8k32, lane = 4 g + t): A rows g and g + 8 of the tile, bytes k = 4 t .. 4 t + 3 and 16 + 4 t ..
+// (one 8-byte shared-memory load of four staged int16 samples per register, split into low and high bytes with two
+// PRMT); B column g, same k (digit table in shared memory, laid out per lane); C rows g, g + 8, columns 2 t, 2 t + 1.
+#define AX_STI_DIGITS 6
+#define AX_STI_SHIFT 45
+#define AX_STI_STAGES 2                                 // staging rows per warp: one in flight while one is consumed (three were measured: no gain)
+#define AX_STI_GROUPS 8                                 // groups of 128 tone blocks per CTA (the digit table is loaded once per CTA)
+#define AX_STI_TAB_WORDS ((AX_TB / 32) * AX_STI_DIGITS * 32 * 2)
+#define AX_STI_SMEM (AX_STI_TAB_WORDS * sizeof(uint32_t) + (AX_ST_THREADS / 32) * AX_STI_STAGES * 32 * 72 * sizeof(int16_t))
+__device__ __forceinline__ void ax_imma_u8s8(int (&c)[4], const unsigned (&a)[4], const uint2 b) {
+    asm("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y));
+}
+__device__ __forceinline__ void ax_imma_s8s8(int (&c)[4], const unsigned (&a)[4], const uint2 b) {
+    asm("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y));
+}
+// A CTA takes AX_STI_GROUPS consecutive groups of 128 tone blocks (a warp: 32 blocks of each group, lane = block for the
+// staging and the statistics); the 4 x AX_STI_GROUPS row steps of a warp form ONE software pipeline -- the rows of the
+// next group are already in flight while the last rows of a group are consumed -- with AX_STI_STAGES - 1 rows ahead.
+__global__ void __launch_bounds__(AX_ST_THREADS, 4) k_stats_tones_imma(const __grid_constant__ AxWave w, const uint32_t* __restrict__ tabi, int cfg_id) {
+    extern __shared__ __align__(16) unsigned char ax_smem_raw[];       // AX_STI_SMEM bytes: digit table, then the staging rows
+    const uint2* btab = reinterpret_cast<const uint2*>(ax_smem_raw);   // [k-step of the block][digit][lane]
+    int16_t (*stage_all)[AX_STI_STAGES][32 * 72] = reinterpret_cast<int16_t (*)[AX_STI_STAGES][32 * 72]>(ax_smem_raw + AX_STI_TAB_WORDS * sizeof(uint32_t));
+    const int d = blockIdx.y;
+    const AxDrop& dr = w.drop[d];
+    if (dr.cfg != cfg_id) return;
+    const int64_t nsamp = dr.n_raw;                  // statistics are taken over the recording as uploaded
+    const int64_t nblk = (nsamp + AX_TB - 1) / AX_TB;
+    if ((int64_t)blockIdx.x * AX_STI_GROUPS * AX_ST_THREADS >= nblk) return;
+    if (w.streaming && ((int64_t)blockIdx.x + 1) * AX_STI_GROUPS * AX_ST_THREADS <= w.st[d].tb_done) return;   // summed by an earlier run
+    // digit table: asynchronous 16-byte copies that land together with the first staged row (first commit group)
+    for (int i = threadIdx.x; i < AX_STI_TAB_WORDS / 4; i += AX_ST_THREADS) ax_cp_async16(ax_smem_raw + 16 * i, tabi + 4 * i);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int16_t (*stage)[32 * 72] = stage_all[warp];
+    const int prow = lane >> 3, piece = lane & 7;
+    const int fg = lane >> 2, ft = lane & 3;         // fragment row / column group
+    long long sum = 0;
+    int mx2 = (int)0x80008000, mn2 = 0x7fff7fff;        // packed int16 max / min
+    const int16_t* xdrop = w.pcm + dr.pcm_off;
+    const int64_t jw0 = (int64_t)blockIdx.x * AX_STI_GROUPS * AX_ST_THREADS + warp * 32;      // first block of this warp in group 0
+    // row step s = 4 grp + r: row r (64 samples) of the warp's 32 blocks of group grp; a lane copies the 16-byte piece
+    // `piece` of the rows of blocks 4 i + prow, i < 8 (blocks are 512 bytes apart: no address exchange needed)
+    auto issue = [&](int s, int slot) {
+        const int64_t jw = jw0 + (int64_t)(s >> 2) * AX_ST_THREADS;
+        const int r = s & 3;
+        const int64_t rem = nsamp - (jw + prow) * AX_TB - 64 * r;        // samples left from this row's start, block prow
+        const int16_t* src = xdrop + (jw + prow) * AX_TB + 64 * r + piece * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (rem - (int64_t)i * 4 * AX_TB > 0) ax_cp_async16(&stage[slot][(i * 4 + prow) * 72 + piece * 8], src + (int64_t)i * 4 * AX_TB);
+        ax_cp_async_commit();
+    };
+    int nsteps = 0;
+#pragma unroll
+    for (int grp = 0; grp < AX_STI_GROUPS; ++grp)
+        if (((int64_t)blockIdx.x * AX_STI_GROUPS + grp) * AX_ST_THREADS < nblk) nsteps = 4 * (grp + 1);
+    int acc[2][AX_STI_DIGITS + 1][4];                // [tile of 16 blocks][weight 256^e][C fragment]
+#pragma unroll
+    for (int pre = 0; pre < AX_STI_STAGES - 1; ++pre) { if (pre < nsteps) issue(pre, pre); else ax_cp_async_commit(); }
+    int slot = 0, slot_next = AX_STI_STAGES - 1;
+#pragma unroll 1
+    for (int s = 0; s < nsteps; ++s) {
+        const int r = s & 3;
+        const int64_t jw = jw0 + (int64_t)(s >> 2) * AX_ST_THREADS;
+        if (r == 0) {
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int e = 0; e <= AX_STI_DIGITS; ++e) { acc[mt][e][0] = 0; acc[mt][e][1] = 0; acc[mt][e][2] = 0; acc[mt][e][3] = 0; }
+        }
+        if (s + AX_STI_STAGES - 1 < nsteps) issue(s + AX_STI_STAGES - 1, slot_next); else ax_cp_async_commit();
+        ax_cp_async_wait<AX_STI_STAGES - 1>();
+        if (s == 0) __syncthreads(); else __syncwarp();      // (step 0: the digit table, copied by all warps, has landed too)
+        // block sums: rows of blocks that do not reach this far hold stale samples; their sums are never stored
+        {
+            const int16_t* st = stage[slot];
+#pragma unroll
+            for (int k2 = 0; k2 < 2; ++k2) {
+                const uint2* bt = btab + ((2 * r + k2) * AX_STI_DIGITS) * 32 + lane;
+                uint2 bd[AX_STI_DIGITS];
+#pragma unroll
+                for (int j = 0; j < AX_STI_DIGITS; ++j) bd[j] = bt[32 * j];
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    const int16_t* p0 = st + (16 * mt + fg) * 72 + 32 * k2 + 4 * ft;
+                    const uint2 w00 = *reinterpret_cast<const uint2*>(p0), w01 = *reinterpret_cast<const uint2*>(p0 + 16);
+                    const uint2 w10 = *reinterpret_cast<const uint2*>(p0 + 8 * 72), w11 = *reinterpret_cast<const uint2*>(p0 + 8 * 72 + 16);
+                    unsigned al[4], ah[4];
+                    al[0] = __byte_perm(w00.x, w00.y, 0x6420); ah[0] = __byte_perm(w00.x, w00.y, 0x7531);
+                    al[1] = __byte_perm(w10.x, w10.y, 0x6420); ah[1] = __byte_perm(w10.x, w10.y, 0x7531);
+                    al[2] = __byte_perm(w01.x, w01.y, 0x6420); ah[2] = __byte_perm(w01.x, w01.y, 0x7531);
+                    al[3] = __byte_perm(w11.x, w11.y, 0x6420); ah[3] = __byte_perm(w11.x, w11.y, 0x7531);
+                    // (the two products that meet in one accumulator are issued six instructions apart)
+#pragma unroll
+                    for (int j = 0; j < AX_STI_DIGITS; ++j) ax_imma_u8s8(acc[mt][j], al, bd[j]);
+#pragma unroll
+                    for (int j = 0; j < AX_STI_DIGITS; ++j) ax_imma_s8s8(acc[mt][j + 1], ah, bd[j]);
+                }
+            }
+        }
+        {   // statistics of this lane's own block
+            const int64_t n0 = (jw + lane) * AX_TB + 64 * r;
+            const int64_t left = nsamp - n0;
+            if (left > 0) {
+                const int4* rp = reinterpret_cast<const int4*>(&stage[slot][lane * 72]);
+                if (left >= 64) {
+                    int s32 = 0;
+#pragma unroll
+                    for (int v = 0; v < 8; ++v) {
+                        const int4 q = rp[v];
+                        mx2 = (int)__vimax3_s16x2((unsigned)mx2, (unsigned)q.x, (unsigned)q.y);
+                        mx2 = (int)__vimax3_s16x2((unsigned)mx2, (unsigned)q.z, (unsigned)q.w);
+                        mn2 = (int)__vimin3_s16x2((unsigned)mn2, (unsigned)q.x, (unsigned)q.y);
+                        mn2 = (int)__vimin3_s16x2((unsigned)mn2, (unsigned)q.z, (unsigned)q.w);
+                        s32 = __dp2a_lo(q.x, 0x0101, s32); s32 = __dp2a_lo(q.y, 0x0101, s32);
+                        s32 = __dp2a_lo(q.z, 0x0101, s32); s32 = __dp2a_lo(q.w, 0x0101, s32);
+                    }
+                    sum += s32;
+                } else {                                   // ragged end of the recording
+                    const int16_t* xs = &stage[slot][lane * 72];
+                    for (int i = 0; i < (int)left; ++i) {
+                        const int v = xs[i];
+                        sum += v;
+                        const int pk = (v & 0xFFFF) | (v << 16);
+                        mx2 = (int)__vimax3_s16x2((unsigned)mx2, (unsigned)pk, (unsigned)pk);
+                        mn2 = (int)__vimin3_s16x2((unsigned)mn2, (unsigned)pk, (unsigned)pk);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (r == 3 && dr.xf_off < 0 && ft < 3) {       // (a decimating drop takes its block sums from the halved signal)
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {          // rows fg and fg + 8 of the tile
+                    const int64_t j = jw + 16 * mt + fg + 8 * h;
+                    if (j < dr.ntb) {
+                        double v0 = 0.0, v1 = 0.0;
+#pragma unroll
+                        for (int e = AX_STI_DIGITS; e >= 0; --e) {      // exact conversions, weights 2^(8 e - shift)
+                            const double wgt = __longlong_as_double((long long)(1023 + 8 * e - AX_STI_SHIFT) << 52);
+                            v0 = fma((double)acc[mt][e][2 * h], wgt, v0);
+                            v1 = fma((double)acc[mt][e][2 * h + 1], wgt, v1);
+                        }
+                        double* out = w.tb_sum + (dr.tb_base + j) * 6 + 2 * ft;
+                        out[0] = v0; out[1] = v1;
+                    }
+                }
+        }
+        slot_next = slot;
+        slot = (slot + 1 == AX_STI_STAGES) ? 0 : slot + 1;
+    }
+    int mx = max((int)(short)(mx2 & 0xFFFF), mx2 >> 16), mn = min((int)(short)(mn2 & 0xFFFF), mn2 >> 16);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    }
+    if (lane == 0) {
+        atomicAdd((unsigned long long*)&w.st[d].sum, (unsigned long long)sum);
+        atomicMax(&w.st[d].vmax, mx);
+        atomicMin(&w.st[d].vmin, mn);
+    }
+}
+
 // The same pass with the block sums split between the FP64 tensor cores and the vector FP64 pipe.
 template <int KD>
 __global__ void __launch_bounds__(AX_ST_THREADS) k_stats_tones_hyb(const __grid_constant__ AxWave w, const double* __restrict__ tab8, const __grid_constant__ AxToneTab tab, int cfg_id) {

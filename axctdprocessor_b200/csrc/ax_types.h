@@ -83,6 +83,7 @@ struct AxCfg {
     int64_t h1s, h1e, h2s, h2e, h3s, h3e, half;                    // AXCTDprocessor.py:447-456
     const double* tone_cs;       // [n_power][6]
     const double* tone_tab8;     // [AX_TB][8] phasors of a tone block, columns 6 and 7 zero (B operand of k_stats_tones_mma)
+    const uint32_t* tone_tabi;   // the same phasors as signed base-256 digits of round(p * 2^45), in the B-fragment layout of k_stats_tones_imma
     const double* tone_soa;      // [6][n_power] the same table, one array per component (coalesced reads in ax_tonewin_partial)
     const double* lut;           // [lut_len]
     const double* hist_edges;    // [n_hist_edges]
