@@ -193,6 +193,7 @@ struct axctd_engine {
     int opt_fir_first = 1;                // numerators-first cascade in the continuous low-pass pass (k_demod_fused FAST)
     int opt_tone_mma = 1;                 // tone block sums on the FP64 tensor cores (k_stats_tones_mma)
     int opt_tone_int8 = 1;                // ... as exact integer products on the int8 tensor cores instead (k_stats_tones_imma); 0: FP64 tensor cores
+    int opt_pair_launch = 1;              // two rate classes (window lengths 39 / 43) demodulated by one launch (k_demod_fused_pair)
     int opt_heavy_chain = 1;              // engines of one process take turns with the demodulation pass (see ax_heavy_*)
     int opt_nosync = 1;                   // enqueue the whole decode without host round trips (see axctd_batch_run_async)
     int opt_scan_only = 0;                // tone levels only (segmentation of long recordings): skip the demodulation pass
@@ -467,6 +468,7 @@ extern "C" int axctd_engine_set_option(axctd_engine* e, const char* name, double
     else if (s == "tone_mma") e->opt_tone_mma = (int)v;
     else if (s == "tone_int8") e->opt_tone_int8 = (int)v;
     else if (s == "heavy_chain") e->opt_heavy_chain = (int)v;
+    else if (s == "pair_launch") e->opt_pair_launch = (int)v;
     else if (s == "scan_only") e->opt_scan_only = (int)v;
     else if (s == "nosync") e->opt_nosync = (int)v;
     else if (s == "fuse_bits") e->opt_fuse_bits = (int)v;
@@ -1114,6 +1116,20 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
         }
     if (scan_only) {
     } else if (fused) {
+        // two low-pass rate classes with window lengths 39 and 43 (a batch of 44.1 and 48 kHz drops): one launch for both
+        int pair39 = -1, pair43 = -1;
+        if (e->opt_pair_launch && !e->opt_ws && !e->opt_bulk && e->opt_fir_first && used_cfg.size() == 2) {
+            const AxCfg& ca = e->cfgs[used_cfg[0]]; const AxCfg& cb = e->cfgs[used_cfg[1]];
+            const bool i16_only = std::none_of(b->drops.begin(), b->drops.end(), [&](const AxDrop& d) { return d.xf_off >= 0; });
+            if (i16_only && ax_demod_fast_ok(ca) && ax_demod_fast_ok(cb) && ca.npcm + cb.npcm == 82 && (ca.npcm == 39 || ca.npcm == 43)) {
+                pair39 = ca.npcm == 39 ? used_cfg[0] : used_cfg[1];
+                pair43 = ca.npcm == 39 ? used_cfg[1] : used_cfg[0];
+            }
+        }
+        if (pair39 >= 0) {
+            ax_launch_demod_fused_pair<3, true>(w, e->cfgs[pair39], pair39, e->cfgs[pair43], pair43, e->stream, e->device);
+            e->launches++;
+        } else
         // one launch per rate class in use (CTAs of the other classes exit at once)
         for (int ci : used_cfg) {
             const bool has_i16 = std::any_of(b->drops.begin(), b->drops.end(), [&](const AxDrop& d) { return d.cfg == ci && d.xf_off < 0; });

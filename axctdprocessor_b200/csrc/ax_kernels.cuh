@@ -921,7 +921,7 @@ static_assert(AX_FD_RINGQ * 32 * sizeof(float4) == 16384, "ring offsets assume 1
 // consumed, and the next row's four lines are prefetched), because staging 512 bytes per lane and stage would not
 // leave room for two CTAs per SM; everything after the sample fetch is the same code.
 template <int NSEC, int NPCM, bool HEAD, bool FAST, bool BULK = false, bool F64 = false>
-__global__ void __launch_bounds__(AX_FD_THREADS, 2) k_demod_fused(const __grid_constant__ AxWave w, const __grid_constant__ AxWinTab tab, int cfg_id, int64_t n_items) {
+__device__ __forceinline__ void ax_demod_fused_body(const AxWave& w, const AxWinTab& tab, int cfg_id, int64_t n_items) {
     extern __shared__ __align__(16) unsigned char ax_smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     AxFdSmem& smem = *reinterpret_cast<AxFdSmem*>(ax_smem_raw);
@@ -1226,6 +1226,21 @@ __global__ void __launch_bounds__(AX_FD_THREADS, 2) k_demod_fused(const __grid_c
     }
 }
 
+template <int NSEC, int NPCM, bool HEAD, bool FAST, bool BULK = false, bool F64 = false>
+__global__ void __launch_bounds__(AX_FD_THREADS, 2) k_demod_fused(const __grid_constant__ AxWave w, const __grid_constant__ AxWinTab tab, int cfg_id, int64_t n_items) {
+    ax_demod_fused_body<NSEC, NPCM, HEAD, FAST, BULK, F64>(w, tab, cfg_id, n_items);
+}
+// Both rate classes of a batch (window lengths 39 and 43 samples: 44.1 and 48 kHz) in ONE launch: a CTA takes the body
+// of its drop's class.  The segment length of a batch is chosen so that ALL its segments fill a whole number of waves
+// of (SMs x 8 warps x 32) lanes; one launch per class broke that fit (2.1 + 1.9 waves ran as 3 + 2 rounds).
+template <int NSEC, bool FAST>
+__global__ void __launch_bounds__(AX_FD_THREADS, 2) k_demod_fused_pair(const __grid_constant__ AxWave w, const __grid_constant__ AxWinTab tab39, const __grid_constant__ AxWinTab tab43,
+                                                                        int cfg39, int cfg43, int64_t n_items) {
+    const int cfg = w.drop[w.seg_drop[(int64_t)blockIdx.x * AX_FD_THREADS]].cfg;
+    if (cfg == cfg39) ax_demod_fused_body<NSEC, 39, false, FAST>(w, tab39, cfg39, n_items);
+    else if (cfg == cfg43) ax_demod_fused_body<NSEC, 43, false, FAST>(w, tab43, cfg43, n_items);
+}
+
 // ------------------------------------------------------------------ fused demodulation pass, warp-specialised
 // k_demod_ws: the computation of k_demod_fused split over two kinds of warps so that the FP64 cascade and the
 // FP32 windows overlap instead of alternating.  A CTA holds AX_WS_PAIRS pairs of warps; pair p owns 32
@@ -1498,6 +1513,19 @@ static inline void ax_launch_demod_fused_f64(const AxWave& w, const AxCfg& c, in
     else if (c.nsec == 3 && c.npcm == 43) ax_launch_demod_fused<3, 43, false, false, false, true>(w, c, cfg_id, 0, stream, device);
     else if (c.nsec == 6 && c.npcm == 39) ax_launch_demod_fused<6, 39, false, false, false, true>(w, c, cfg_id, 0, stream, device);
     else ax_launch_demod_fused<6, 43, false, false, false, true>(w, c, cfg_id, 0, stream, device);
+}
+
+// continuous pass of two low-pass rate classes (npcm 39 and 43) in one launch
+template <int NSEC, bool FAST>
+static inline void ax_launch_demod_fused_pair(const AxWave& w, const AxCfg& c39, int cfg39, const AxCfg& c43, int cfg43, cudaStream_t stream, int device) {
+    const size_t smem = sizeof(AxFdSmem);
+    ax_optin_smem<k_demod_fused_pair<NSEC, FAST>>(smem, device);
+    const int64_t items = (int64_t)w.nseg_total;
+    if (items <= 0) return;
+    k_demod_fused_pair<NSEC, FAST><<<(unsigned)((items + AX_FD_THREADS - 1) / AX_FD_THREADS), AX_FD_THREADS, smem, stream>>>(w, c39.win_tab, c43.win_tab, cfg39, cfg43, items);
+}
+static inline bool ax_demod_fast_ok(const AxCfg& c) {       // numerators-first cascade: low-pass, every section with numerator g (1 + z^-1)^2
+    return c.nsec == 3 && c.sos[0][1] > 0.0 && c.sos[1][1] > 0.0 && c.sos[2][1] > 0.0;
 }
 
 // true if the fused kernel has an instantiation for this rate class
