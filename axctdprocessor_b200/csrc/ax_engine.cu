@@ -193,7 +193,7 @@ struct axctd_engine {
     int opt_fir_first = 1;                // numerators-first cascade in the continuous low-pass pass (k_demod_fused FAST)
     int opt_tone_mma = 1;                 // tone block sums on the FP64 tensor cores (k_stats_tones_mma)
     int opt_tone_int8 = 1;                // ... as exact integer products on the int8 tensor cores instead (k_stats_tones_imma); 0: FP64 tensor cores
-    int opt_pair_launch = 1;              // two rate classes (window lengths 39 / 43) demodulated by one launch (k_demod_fused_pair)
+    int opt_pair_launch = 0;              // two rate classes (window lengths 39 / 43) demodulated by one launch (k_demod_fused_pair): measured, no gain
     int opt_heavy_chain = 1;              // engines of one process take turns with the demodulation pass (see ax_heavy_*)
     int opt_nosync = 1;                   // enqueue the whole decode without host round trips (see axctd_batch_run_async)
     int opt_scan_only = 0;                // tone levels only (segmentation of long recordings): skip the demodulation pass
