@@ -339,6 +339,7 @@ struct axctd_batch {
     bool force_nofuse = false;            // repeat of a run whose list of bits to re-evaluate overflowed
     bool ran_fused = false, mags_full = true;   // the last run decided bits in k_emit_chunk; magnitudes of every bit are on the device
     bool ran = false, finished = false;
+    int32_t chunk_cap_max = 0;            // largest per-drop iteration capacity (grid of k_emit_chunk)
     bool any_f64in = false;               // a drop takes its samples through axctd_batch_upload_f64 (config decimate = 3)
     bool lent = false;                    // another engine's stream has read this batch's PCM (axctd_batch_copy_from)
     // streaming decode (axctd_batch_stream_*): drops hold growing recordings, `drops` carries their current lengths
@@ -773,6 +774,7 @@ extern "C" int axctd_batch_create(axctd_engine* e, int n_drops, const int64_t* n
         dr.zq_base = zq_off; zq_off += n / AX_ZQ + 2;
         dr.tile_base = tile_off; dr.tile_cap = (int32_t)(dr.zc_cap / AX_TILE + 1); tile_off += dr.tile_cap;
         dr.chunk_base = chunk_off; dr.chunk_cap = (int32_t)(2 * (n / c.chunk_len) + 16); chunk_off += dr.chunk_cap;
+        b->chunk_cap_max = std::max(b->chunk_cap_max, dr.chunk_cap);
         dr.edge_base = edge_off; dr.edge_cap = n / 24 + 8 * (int64_t)dr.chunk_cap; edge_off += ((dr.edge_cap + 64 + 63) / 64) * 64;
         dr.pw_base = pw_off; dr.pw_cap = (int32_t)(n / c.d_pcm + 2 * (int64_t)dr.chunk_cap + 8); pw_off += dr.pw_cap;
         dr.frame_base = frame_off; dr.frame_cap = (int32_t)(dr.edge_cap / 32 + 64); frame_off += dr.frame_cap;
@@ -1268,12 +1270,12 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
         b->ran_fused = fuse; b->mags_full = !fuse;
         w.nk_full = nk;
         const dim3 region_a((unsigned)nk, (unsigned)n);
-        k_emit_chunk<<<(unsigned)b->chunk_total, 128, 0, e->stream>>>(w, fuse ? 1 : 0); e->launches++;
+        k_emit_chunk<<<dim3((unsigned)b->chunk_cap_max, (unsigned)b->n), 128, 0, e->stream>>>(w, fuse ? 1 : 0); e->launches++;
         k_bits_chunk<<<region_a, 128, 0, e->stream>>>(w, 0, 1); e->launches++;
         k_scale_block<<<n, 128, 0, e->stream>>>(w); e->launches++;
         if (fuse) {
             k_bits_chunk<<<region_a, 128, 0, e->stream>>>(w, 1, 1);
-            k_emit_chunk<<<(unsigned)b->chunk_total, 128, 0, e->stream>>>(w, 2);
+            k_emit_chunk<<<dim3((unsigned)b->chunk_cap_max, (unsigned)b->n), 128, 0, e->stream>>>(w, 2);
             k_bits_recheck<<<592, 128, 0, e->stream>>>(w);
             e->launches += 3;
         } else { k_bits_chunk<<<(unsigned)b->chunk_total, 128, 0, e->stream>>>(w, 1, 0); e->launches++; }
@@ -1514,7 +1516,7 @@ extern "C" int64_t axctd_batch_bits(axctd_batch* b, int drop, uint8_t* bits, dou
     if (conf && nb) {
 #ifndef AXCTD_EMU
         if (!b->mags_full) {      // the run kept magnitudes only where it needed them: produce the rest now (two-step form of the later iterations)
-            k_emit_chunk<<<(unsigned)b->chunk_total, 128, 0, b->eng->stream>>>(b->w, 3);
+            k_emit_chunk<<<dim3((unsigned)b->chunk_cap_max, (unsigned)b->n), 128, 0, b->eng->stream>>>(b->w, 3);
             k_bits_chunk<<<(unsigned)b->chunk_total, 128, 0, b->eng->stream>>>(b->w, 1, 2);
             if (ax_sync(b->eng)) return -AXCTD_ERR_CUDA;
             b->mags_full = true;

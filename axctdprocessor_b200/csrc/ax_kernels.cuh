@@ -1862,12 +1862,14 @@ __global__ void __launch_bounds__(128) k_bits_recheck(AxWave w) {
 // mode 0: every iteration, magnitudes stored (the bit decisions follow in k_bits_chunk); 1: the same for the iterations
 // before k0 + nk_full only; 2: the later iterations with the bit decided on the spot (ax_emit_edge, fused); 3: the later
 // iterations in the two-step form (materialises the magnitudes when a caller asks for them: axctd_batch_bits)
+// grid (iterations, drops): no search for the owner of an iteration
 __global__ void __launch_bounds__(128) k_emit_chunk(AxWave w, int mode) {
-    const int64_t cg = blockIdx.x;
-    const int d = ax_find_owner(w.drop, w.n_drops, &AxDrop::chunk_base, cg);
+    const int d = blockIdx.y;
     const AxDrop& dr = w.drop[d];
     AxState& st = w.st[d];
-    const int k = (int)(cg - dr.chunk_base);
+    const int k = (int)blockIdx.x;
+    if (k >= dr.chunk_cap) return;
+    const int64_t cg = (int64_t)dr.chunk_base + k;
     if (!ax_emit_active(w, dr, st, k)) return;
     if (mode == 1 && k >= st.k0 + w.nk_full) return;
     if (mode >= 2 && k < st.k0 + w.nk_full) return;
@@ -1891,17 +1893,31 @@ __global__ void __launch_bounds__(128) k_emit_chunk(AxWave w, int mode) {
     const int64_t t0 = mp / AX_TILE, t1 = ch.q_last / AX_TILE;
     const int64_t r0 = ax_canon_rank(cmask, crank, mp) - (nhe + npre);       // edge number = canonical rank - r0
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // The tile's mask and running count and the records of all its 64 crossings are fetched in ONE round of loads (the
+    // records before the mask says which of them are edges: whole lines, and no second round of dependent loads -- the
+    // kernel was bound by that latency); the dense arrays are padded to whole tiles.
+    const int32_t* zi = w.zc_idx + dr.zc_base;
+    const float* za1 = w.zc_a1 + dr.zc_base;
+    const float* za2 = w.zc_a2 + dr.zc_base;
     for (int64_t tt = t0 + warp; tt <= t1; tt += blockDim.x >> 5) {
-        uint64_t m = cmask[tt];
+        const uint64_t cm = cmask[tt];
+        const int32_t cr = crank[tt];
+        int32_t ri[2]; float r1[2], r2[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int64_t pos = tt * AX_TILE + lane + 32 * h;
+            ri[h] = zi[pos]; r1[h] = za1[pos]; r2[h] = za2[pos];
+        }
+        uint64_t m = cm;
         if (tt == t0) m &= ~((1ull << (mp - t0 * AX_TILE)) - 1ull);
-        const int64_t base = (int64_t)crank[tt] - r0;
+        const int64_t base = (int64_t)cr - r0;
         if (base >= ne) break;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int bit = lane + 32 * h;
             if ((m >> bit) & 1ull) {
-                const int64_t t = base + __popcll(cmask[tt] & ((1ull << bit) - 1ull));
-                if (t < ne) ax_emit_edge(w, dr, st, c, ch, cg, k, (int)t, tt * AX_TILE + bit, fused);
+                const int64_t t = base + __popcll(cm & ((1ull << bit) - 1ull));
+                if (t < ne) ax_emit_edge_vals(w, dr, st, c, ch, cg, k, (int)t, (int64_t)ri[h], (double)r1[h], (double)r2[h], fused);
             }
         }
     }

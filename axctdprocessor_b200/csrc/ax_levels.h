@@ -398,6 +398,9 @@ AX_HDN inline void ax_offsets_item(const AxWave& w, int64_t d) {
 // AXCTDprocessor.py:413-429: bit edges of one chunk and the signal level of the
 // nearest power sample of THIS chunk for every edge.
 // One edge: t < n_head_edges comes from the exact head, otherwise `pos` is its dense crossing ordinal.
+// edge t of iteration k from a crossing whose record (sample index, |S1|, |S2|) the caller has already fetched
+AX_HD void ax_emit_edge_vals(const AxWave& w, const AxDrop& dr, AxState& st, const AxCfg& c, AxChunk& ch, int64_t cg, int k, int t,
+                             int64_t idx, double v1, double v2, bool fused);
 AX_HD void ax_emit_edge(const AxWave& w, const AxDrop& dr, AxState& st, const AxCfg& c, AxChunk& ch, int64_t cg, int k, int t, int64_t pos, bool fused = false) {
     int64_t idx; double v1, v2;
     if (t < ch.n_head_edges) {
@@ -405,8 +408,12 @@ AX_HD void ax_emit_edge(const AxWave& w, const AxDrop& dr, AxState& st, const Ax
         v1 = w.head_a1[cg * (int64_t)w.head_zc_cap_max + t]; v2 = w.head_a2[cg * (int64_t)w.head_zc_cap_max + t];
     } else {
         idx = w.zc_idx[dr.zc_base + pos]; v1 = w.zc_a1[dr.zc_base + pos]; v2 = w.zc_a2[dr.zc_base + pos];
-        if (t < ch.n_edges - 1 && idx + c.inset + c.npcm > ch.e) ax_raise(st, AXCTD_DROP_SHORT_WINDOW, k);   // demodulate.py:100-101
     }
+    ax_emit_edge_vals(w, dr, st, c, ch, cg, k, t, idx, v1, v2, fused);
+}
+AX_HD void ax_emit_edge_vals(const AxWave& w, const AxDrop& dr, AxState& st, const AxCfg& c, AxChunk& ch, int64_t cg, int k, int t,
+                             int64_t idx, double v1, double v2, bool fused) {
+    if (t >= ch.n_head_edges && t < ch.n_edges - 1 && idx + c.inset + c.npcm > ch.e) ax_raise(st, AXCTD_DROP_SHORT_WINDOW, k);   // demodulate.py:100-101
     const int64_t eo = dr.edge_base + ch.edge_off + t;
     w.edge_idx[eo] = (int32_t)idx;
     if (t < ch.n_edges - 1) {

@@ -141,7 +141,7 @@ def test_batch_equals_single_drops(eng):
     b.close()
 
 
-@pytest.mark.parametrize("opts", [dict(tone_direct=1), dict(force_exact=1), dict(inject_misspec=1), dict(tone_mma=10), dict(tone_mma=1), dict(fuse_bits=0), dict(fuse_bits=1, bit_tol=1e-2), dict(fuse_bits=1, bit_tol=0.9, expect_fallback=1),
+@pytest.mark.parametrize("opts", [dict(tone_direct=1), dict(force_exact=1), dict(inject_misspec=1), dict(tone_mma=10), dict(tone_mma=1), dict(tone_int8=0), dict(fuse_bits=0), dict(fuse_bits=1, bit_tol=1e-2), dict(fuse_bits=1, bit_tol=0.9, expect_fallback=1),
                                   dict(segment_len=4096), dict(segment_len=32768), dict(filter_variant=1),
                                   dict(bitfix_all=1), dict(bit_tol=1e-3, hist_tol=1e-3), dict(ws=1), dict(ws=1, segment_len=4096), dict(fir_first=0), dict(fir_first=0, segment_len=4096), dict(tone_mma=0),
                                   dict(bulk=1), dict(bulk=1, fir_first=0), dict(bulk=1, segment_len=4096), dict(bulk=0)])
@@ -159,6 +159,22 @@ def test_kernel_variants_agree_with_reference(opts):
     if "bitfix_all" in opts:        # every window re-evaluated in double: conf agrees with the reference to fp64 round-off
         np.testing.assert_allclose(out["bits"][1], g.z["conf"], rtol=1e-9, equal_nan=True)
         assert out["result"].summary.n_recheck >= g.meta["n_bits"]
+    e.close()
+
+
+@pytest.mark.parametrize("pair", [0, 1])
+def test_mixed_rate_batch_in_one_or_two_demodulation_launches(pair):
+    """A batch holding both rate classes (44.1 and 48 kHz: window lengths 39 and 43): one launch per class, or both in
+    one launch (k_demod_fused_pair, option pair_launch)."""
+    ga, gb = Golden("g44_40db"), Golden("g48_25db")
+    e = _engine(pair_launch=pair)
+    pa, pb = ga.pcm(), gb.pcm()
+    b = e.batch([len(pa), len(pb), len(pa)], [e.config(ga.spec.fs), e.config(gb.spec.fs), e.config(ga.spec.fs)])
+    b.upload(0, pa); b.upload(1, pb); b.upload(2, pa)
+    b.run()
+    for i, g in enumerate((ga, gb, ga)):
+        check_against_golden(dict(result=b.result(i), bits=b.bits(i), edges=b.edges(i), power=b.power(i)), g)
+    b.close()
     e.close()
 
 
