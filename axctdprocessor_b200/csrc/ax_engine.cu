@@ -192,6 +192,7 @@ struct axctd_engine {
     int opt_bulk = 0;                     // continuous pass stages its rows with cp.async.bulk (TMA unit) instead of LDGSTS
     int opt_fir_first = 1;                // numerators-first cascade in the continuous low-pass pass (k_demod_fused FAST)
     int opt_tone_mma = 1;                 // tone block sums on the FP64 tensor cores (k_stats_tones_mma)
+    int opt_tone_complement = 1;          // ragged window ends above half a tone block as the block minus its complement (k_tone_windows_mma)
     int opt_tone_int8 = 1;                // ... as exact integer products on the int8 tensor cores instead (k_stats_tones_imma); 0: FP64 tensor cores
     int opt_pair_launch = 0;              // two rate classes (window lengths 39 / 43) demodulated by one launch (k_demod_fused_pair): measured, no gain
     int opt_heavy_chain = 1;              // engines of one process take turns with the demodulation pass (see ax_heavy_*)
@@ -468,6 +469,7 @@ extern "C" int axctd_engine_set_option(axctd_engine* e, const char* name, double
     else if (s == "heavy_prio") e->opt_heavy_prio = (int)v;
     else if (s == "tone_mma") e->opt_tone_mma = (int)v;
     else if (s == "tone_int8") e->opt_tone_int8 = (int)v;
+    else if (s == "tone_complement") e->opt_tone_complement = (int)v;
     else if (s == "heavy_chain") e->opt_heavy_chain = (int)v;
     else if (s == "pair_launch") e->opt_pair_launch = (int)v;
     else if (s == "scan_only") e->opt_scan_only = (int)v;
@@ -728,6 +730,7 @@ extern "C" int axctd_batch_create(axctd_engine* e, int n_drops, const int64_t* n
     w.guard = e->opt_guard; w.tone_direct = e->opt_tone_direct; w.force_exact = e->opt_force_exact;
     w.bit_tol = e->opt_bit_tol; w.hist_tol = e->opt_hist_tol; w.bitfix_all = e->opt_bitfix_all;
     w.probe = e->opt_demod_probe;
+    w.tone_complement = e->opt_tone_complement;
     w.head_zc_cap_max = head_cap_max;
     b->drops.resize(n_drops);
     int64_t pcm_off = 0, zc_off = 0, edge_off = 0, tb_off = 0, xf_off = 0, fwd_off = 0, zq_off = 0;

@@ -796,20 +796,30 @@ __global__ void __launch_bounds__(128, 8) k_tone_windows_mma(AxWave w, int i_lo,
     const int head_n = (int)(j0 * AX_TB - cstart), tail_off = (int)(j1 * AX_TB - cstart);
     const bool regular = valid && dr.xf_off < 0 && head_n <= AX_TB && np - tail_off <= AX_TB && tail_off <= np;
     const int hn = regular ? head_n : 0, tn = regular ? np - tail_off : 0;
-    int kmax = max(hn, tn);
+    // A ragged end longer than half a block is taken as the block that contains it minus its complement (option
+    // tone_complement): the head as e^{-j theta nc} (B_(j0-1) - C), C = the first nc = AX_TB - hn samples of block j0-1
+    // against the table; the tail as B_j1 - e^{j theta (AX_TB-1)} conj(R), R = the last nc = AX_TB - tn samples of block
+    // j1 read backwards against the table.  No end then needs more than AX_TB / 2 samples: half the k-steps, half the
+    // 2-byte sample loads.
+    const bool hcomp = w.tone_complement && regular && hn > AX_TB / 2 && j0 >= 1;
+    const bool tcomp = w.tone_complement && regular && tn > AX_TB / 2 && j1 < dr.ntb;
+    const int hm = hcomp ? AX_TB - hn : hn, tm = tcomp ? AX_TB - tn : tn;
+    int kmax = max(hm, tm);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
     const int ks_end = (kmax + 3) >> 2;
-    const int16_t* xh = w.pcm + dr.pcm_off + cstart;
-    const int16_t* xt = xh + tail_off;
+    const int16_t* xbase = w.pcm + dr.pcm_off;
+    const int16_t* xh = hcomp ? xbase + (j0 - 1) * AX_TB : xbase + cstart;           // forwards from here
+    const int16_t* xt = tcomp ? xbase + j1 * AX_TB + (AX_TB - 1) : xbase + cstart + tail_off;     // complement: backwards from the block's last sample
+    const int tstep = tcomp ? -1 : 1;
     const double* bt = c.tone_tab8 + acol * 8 + arow;
     double h0 = 0.0, h1 = 0.0, t0 = 0.0, t1 = 0.0;
 #pragma unroll 8
     for (int ks = 0; ks < ks_end; ++ks) {
         const int m = 4 * ks + acol;
         const double b = bt[32 * ks];
-        const double ah = (m < hn) ? (double)xh[m] : 0.0;
-        const double at = (m < tn) ? (double)xt[m] : 0.0;
+        const double ah = (m < hm) ? (double)xh[m] : 0.0;
+        const double at = (m < tm) ? (double)xt[tstep * m] : 0.0;
         ax_dmma884(h0, h1, ah, b);
         ax_dmma884(t0, t1, at, b);
     }
@@ -818,6 +828,19 @@ __global__ void __launch_bounds__(128, 8) k_tone_windows_mma(AxWave w, int i_lo,
         const double* tcs = c.tone_cs;
         double are, aim;
         {
+            if (hcomp) {
+                const double* Bp = w.tb_sum + (dr.tb_base + j0 - 1) * 6 + 2 * f;
+                const double dr_ = Bp[0] - h0, di_ = Bp[1] - h1;
+                const double cc = tcs[6 * (int64_t)hm + 2 * f], ss = tcs[6 * (int64_t)hm + 2 * f + 1];
+                h0 = fma(dr_, cc, di_ * ss);               // (dr + j di) (cc - j ss)
+                h1 = fma(di_, cc, -(dr_ * ss));
+            }
+            if (tcomp) {
+                const double* Bp = w.tb_sum + (dr.tb_base + j1) * 6 + 2 * f;
+                const double c5 = tcs[6 * (int64_t)(AX_TB - 1) + 2 * f], s5 = tcs[6 * (int64_t)(AX_TB - 1) + 2 * f + 1];
+                const double er = fma(t0, c5, t1 * s5), ei = fma(t0, s5, -(t1 * c5));      // (t0 - j t1) (c5 + j s5)
+                t0 = Bp[0] - er; t1 = Bp[1] - ei;
+            }
             const double ec = tail_off < np ? tcs[6 * (int64_t)tail_off + 2 * f] : 0.0, es = tail_off < np ? tcs[6 * (int64_t)tail_off + 2 * f + 1] : 0.0;
             are = h0 + fma(ec, t0, -(es * t1));
             aim = h1 + fma(ec, t1, es * t0);

@@ -251,6 +251,7 @@ struct AxWave {
     int32_t bitfix_all;          // test hook: re-evaluate every bit window in double precision
     int32_t probe;               // timing probe of k_demod_fused (builds with -DAX_DEMOD_PROBE only; option "demod_probe", results are wrong): 1 = window sums skipped, 2 = crossings not processed at all
     int32_t tone_direct;
+    int32_t tone_complement;     // k_tone_windows_mma: ragged ends above half a block as the block minus its complement
     int32_t pa_lo, pa_hi;        // fixed-grid chunk range of the current detection round
     int32_t force_exact;
     int32_t streaming;           // 0: whole recordings; 1: a growing recording, only iterations that are complete are

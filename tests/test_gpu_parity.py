@@ -141,7 +141,7 @@ def test_batch_equals_single_drops(eng):
     b.close()
 
 
-@pytest.mark.parametrize("opts", [dict(tone_direct=1), dict(force_exact=1), dict(inject_misspec=1), dict(tone_mma=10), dict(tone_mma=1), dict(tone_int8=0), dict(fuse_bits=0), dict(fuse_bits=1, bit_tol=1e-2), dict(fuse_bits=1, bit_tol=0.9, expect_fallback=1),
+@pytest.mark.parametrize("opts", [dict(tone_direct=1), dict(force_exact=1), dict(inject_misspec=1), dict(tone_mma=10), dict(tone_mma=1), dict(tone_int8=0), dict(tone_complement=0), dict(fuse_bits=0), dict(fuse_bits=1, bit_tol=1e-2), dict(fuse_bits=1, bit_tol=0.9, expect_fallback=1),
                                   dict(segment_len=4096), dict(segment_len=32768), dict(filter_variant=1),
                                   dict(bitfix_all=1), dict(bit_tol=1e-3, hist_tol=1e-3), dict(ws=1), dict(ws=1, segment_len=4096), dict(fir_first=0), dict(fir_first=0, segment_len=4096), dict(tone_mma=0),
                                   dict(bulk=1), dict(bulk=1, fir_first=0), dict(bulk=1, segment_len=4096), dict(bulk=0)])
