@@ -192,6 +192,7 @@ struct axctd_engine {
     int opt_bulk = 0;                     // continuous pass stages its rows with cp.async.bulk (TMA unit) instead of LDGSTS
     int opt_fir_first = 1;                // numerators-first cascade in the continuous low-pass pass (k_demod_fused FAST)
     int opt_tone_mma = 1;                 // tone block sums on the FP64 tensor cores (k_stats_tones_mma)
+    int opt_seg_target = 16384;           // segment length the number of waves of the demodulation pass is sized for (8192: 15.3 ms per step, 16384: 14.7)
     int opt_tone_complement = 1;          // ragged window ends above half a tone block as the block minus its complement (k_tone_windows_mma)
     int opt_tone_int8 = 1;                // ... as exact integer products on the int8 tensor cores instead (k_stats_tones_imma); 0: FP64 tensor cores
     int opt_pair_launch = 0;              // two rate classes (window lengths 39 / 43) demodulated by one launch (k_demod_fused_pair): measured, no gain
@@ -470,6 +471,7 @@ extern "C" int axctd_engine_set_option(axctd_engine* e, const char* name, double
     else if (s == "tone_mma") e->opt_tone_mma = (int)v;
     else if (s == "tone_int8") e->opt_tone_int8 = (int)v;
     else if (s == "tone_complement") e->opt_tone_complement = (int)v;
+    else if (s == "seg_target") e->opt_seg_target = (int)v;
     else if (s == "heavy_chain") e->opt_heavy_chain = (int)v;
     else if (s == "pair_launch") e->opt_pair_launch = (int)v;
     else if (s == "scan_only") e->opt_scan_only = (int)v;
@@ -704,8 +706,10 @@ extern "C" int axctd_batch_create(axctd_engine* e, int n_drops, const int64_t* n
     if (L > 0) L = ((L + 63) / 64) * 64;
     if (L <= 0) {
         // Every lane of the demodulation pass does the same amount of work, so the pass runs in waves of
-        // (SMs x 8 warps x 32) segments: take the number of waves that segments of about 8192 samples need (warm-up
-        // overlap near 1/8) and then the shortest segment length whose padded segment count still fits them.
+        // (SMs x 8 warps x 32) segments: take the number of waves that segments of about seg_target samples need and then
+        // the shortest segment length whose padded segment count still fits them.  seg_target = 16384 (a 32-drop sub-batch
+        // of 12-minute drops runs as two waves of ~14 k-sample segments, warm-up overlap 5 %): measured 14.7 ms per step
+        // against 15.3 at 8192 (four waves, overlap 10 %) and 14.3 .. 14.9 for a single wave (runs 42, 43).
         int sms = 148;
 #ifndef AXCTD_EMU
         { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, e->device) == cudaSuccess && v > 0) sms = v; }
@@ -719,9 +723,10 @@ extern "C" int axctd_batch_create(axctd_engine* e, int n_drops, const int64_t* n
             }
             return s;
         };
-        const int64_t waves = std::max<int64_t>(1, (total + 8192 * lanes - 1) / (8192 * lanes));
+        const int64_t tgt = e->opt_seg_target > 0 ? e->opt_seg_target : 16384;
+        const int64_t waves = std::max<int64_t>(1, (total + tgt * lanes - 1) / (tgt * lanes));
         L = 2048;
-        while (L < 16384 && nseg_for(L) > waves * lanes) L += 64;
+        while (L < 2 * tgt && nseg_for(L) > waves * lanes) L += 64;
         while (L < 2 * (int64_t)warm_max) L <<= 1;
     }
     AxWave& w = b->w;
