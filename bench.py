@@ -362,6 +362,20 @@ def measure_configs(device, opts):
     return out
 
 
+_REAL_STDOUT = None
+
+
+def emit_line(line):
+    """The one JSON line, on the process's real stdout (see run_native: under torchrun descriptor 1 is handed to stderr)."""
+    text = json.dumps(line) + "\n"
+    if _REAL_STDOUT is None:
+        sys.stdout.write(text)
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, text.encode())
+
+
 # ---------------------------------------------------------------- this engine
 def run_native(args):
     import torch
@@ -375,7 +389,12 @@ def run_native(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # NCCL's own banner ("NCCL version ...") goes to stdout otherwise: stdout carries the JSON line only
+        # NCCL prints its banner ("NCCL version ...") on file descriptor 1 from C code (NCCL_DEBUG_FILE does not move it): from
+        # here on descriptor 1 is stderr, and the JSON line goes to the saved real stdout -- stdout carries that line only
+        sys.stdout.flush()
+        global _REAL_STDOUT
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from axctdprocessor_b200 import batch as axbatch
     numa_bound = axbatch.bind_host_thread_to_gpu(local) if world > 1 else False      # (one rank per GPU: keep its pinned buffers local)
@@ -560,7 +579,7 @@ def run_native(args):
         torch.cuda.empty_cache()
         line["configs"] = measure_configs(local, opts)
     if rank == 0:
-        print(json.dumps(line))
+        emit_line(line)
     if world > 1:
         dist.destroy_process_group()
 
