@@ -1278,7 +1278,9 @@ extern "C" int axctd_batch_run_async(axctd_batch* b) {
         b->ran_fused = fuse; b->mags_full = !fuse;
         w.nk_full = nk;
         const dim3 region_a((unsigned)nk, (unsigned)n);
-        k_emit_chunk<<<dim3((unsigned)b->chunk_cap_max, (unsigned)b->n), 128, 0, e->stream>>>(w, fuse ? 1 : 0); e->launches++;
+        if (fuse) k_emit_chunk<<<region_a, 128, 0, e->stream>>>(w, 1);            // only the nk iterations after the first demodulated one
+        else k_emit_chunk<<<dim3((unsigned)b->chunk_cap_max, (unsigned)b->n), 128, 0, e->stream>>>(w, 0);
+        e->launches++;
         k_bits_chunk<<<region_a, 128, 0, e->stream>>>(w, 0, 1); e->launches++;
         k_scale_block<<<n, 128, 0, e->stream>>>(w); e->launches++;
         if (fuse) {

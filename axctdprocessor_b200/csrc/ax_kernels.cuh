@@ -1885,13 +1885,14 @@ __global__ void __launch_bounds__(128) k_bits_recheck(AxWave w) {
 // mode 0: every iteration, magnitudes stored (the bit decisions follow in k_bits_chunk); 1: the same for the iterations
 // before k0 + nk_full only; 2: the later iterations with the bit decided on the spot (ax_emit_edge, fused); 3: the later
 // iterations in the two-step form (materialises the magnitudes when a caller asks for them: axctd_batch_bits)
-// grid (iterations, drops): no search for the owner of an iteration
+// grid (iterations, drops): no search for the owner of an iteration; mode 1: grid (nk_full, drops), iterations counted
+// from the drop's first demodulated one (a full grid spent 0.05 ms per launch on CTAs that only exit)
 __global__ void __launch_bounds__(128) k_emit_chunk(AxWave w, int mode) {
     const int d = blockIdx.y;
     const AxDrop& dr = w.drop[d];
     AxState& st = w.st[d];
-    const int k = (int)blockIdx.x;
-    if (k >= dr.chunk_cap) return;
+    const int k = (mode == 1 ? st.k0 : 0) + (int)blockIdx.x;
+    if (k < 0 || k >= dr.chunk_cap) return;
     const int64_t cg = (int64_t)dr.chunk_base + k;
     if (!ax_emit_active(w, dr, st, k)) return;
     if (mode == 1 && k >= st.k0 + w.nk_full) return;
