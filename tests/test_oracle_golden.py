@@ -3,7 +3,7 @@
 import numpy as np
 import pytest
 
-from golden_util import DECIM_CASES, FULL_CASES, SMALL_CASES, Golden
+from golden_util import DECIM_CASES, FULL_CASES, SMALL_CASES, WIDE_CASES, Golden
 from oracle import axctd_oracle as ao
 
 
@@ -54,6 +54,15 @@ def _check(g, op, full=True):
 def test_oracle_matches_reference_small(name):
     g = Golden(name)
     _check(g, _run_oracle(g))
+
+
+@pytest.mark.parametrize("name", WIDE_CASES)
+def test_oracle_matches_reference_on_wide_samples(name):
+    """24-bit PCM / IEEE float WAV files (int32 / float32 arrays from scipy.io.wavfile.read): the oracle's
+    normalisation is the reference's numpy expression for any sample type (AXCTDprocessor.py:55-62)."""
+    g = Golden(name)
+    wide, _ = g.wide()
+    _check(g, ao.process_pcm(wide, g.spec.fs, settings=g.user_settings, triggerrange=g.triggerrange))
 
 
 @pytest.mark.parametrize("name", [FULL_CASES[0], FULL_CASES[2]])
