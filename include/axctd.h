@@ -187,9 +187,13 @@ int  axctd_struct_size(int which);
 int  axctd_engine_create(int device, axctd_engine** out);
 void axctd_engine_destroy(axctd_engine* e);
 const char* axctd_last_error(axctd_engine* e);
-/* Tunables: "segment_len", "exact_head", "guard", "force_exact", "tone_direct", "max_fixups",
- * "filter_variant", "zc_div", "bit_tol", "hist_tol", "bitfix_all", "inject_misspec".
- * Unknown names return AXCTD_ERR_ARG. */
+/* Tunables (set before the configs / batches they are to affect).  Decomposition: "segment_len" (samples per lane of the
+ * continuous pass, 0 = sized for whole waves), "seg_target" (segment length that sizing aims at, 16384), "exact_head",
+ * "zc_div".  Numerics: "guard", "bit_tol", "hist_tol", "force_exact", "bitfix_all".  Kernel variants, all held to the
+ * reference by the tests: "filter_variant", "ws", "fir_first", "bulk", "pair_launch" (demodulation pass); "tone_direct",
+ * "tone_mma", "tone_int8", "tone_complement" (tone levels); "fuse_bits", "nosync", "max_fixups", "scan_only".
+ * Scheduling of several engines on one GPU: "heavy_chain", "heavy_prio".  Block cache: "pool", "pool_trim",
+ * "pool_poison".  Test hooks: "inject_misspec", "demod_probe".  Unknown names return AXCTD_ERR_ARG. */
 int  axctd_engine_set_option(axctd_engine* e, const char* name, double value);
 /* Run all engine work on a caller-owned CUDA stream (cudaStream_t passed as void*), so that the
  * caller can bracket it with its own events.  The engine does not take ownership. */
