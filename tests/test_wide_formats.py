@@ -162,3 +162,32 @@ def test_engine_close_releases_batches_that_are_still_open():
     e.close()
     assert b.h is None
     b.close()
+
+
+@pytest.mark.parametrize("bits,tag", [(16, 1), (24, 1), (32, 3)])
+def test_reader_handles_extensible_headers_and_extra_chunks(tmp_path, bits, tag):
+    """WAVE_FORMAT_EXTENSIBLE (the sub-format carries the real tag), a LIST chunk before the data and an odd-sized
+    chunk with its pad byte: the reader walks the chunks as scipy does."""
+    import struct
+    from scipy.io import wavfile
+    from axctdprocessor_b200.AXCTDprocessor import read_wav
+    rng = np.random.default_rng(bits)
+    nch, fs, n = 2, 48000, 1001
+    bps = bits // 8
+    if tag == 3:
+        payload = rng.uniform(-1, 1, size=(n, nch)).astype("<f4").tobytes()
+    elif bits == 16:
+        payload = rng.integers(-32768, 32768, size=(n, nch)).astype("<i2").tobytes()
+    else:
+        payload = rng.integers(0, 256, size=n * nch * 3, dtype=np.uint8).tobytes()
+    guid_tail = bytes.fromhex("000000001000800000aa00389b71")
+    fmt = struct.pack("<HHIIHH", 0xFFFE, nch, fs, fs * nch * bps, nch * bps, bits) + struct.pack("<HHI", 22, bits, 3) + struct.pack("<H", tag) + guid_tail
+    info = b"INFOISFT" + struct.pack("<I", 5) + b"test\0" + b"\0"      # odd-sized sub-chunk + pad byte
+    body = (b"WAVE" + b"fmt " + struct.pack("<I", len(fmt)) + fmt + b"LIST" + struct.pack("<I", len(info)) + info
+            + b"data" + struct.pack("<I", len(payload)) + payload)
+    path = str(tmp_path / "ext.wav")
+    with open(path, "wb") as f:
+        f.write(b"RIFF" + struct.pack("<I", len(body)) + body)
+    fs_ref, a_ref = wavfile.read(path)
+    fs_got, a = read_wav(path)
+    assert fs_got == fs_ref and a.dtype == a_ref.dtype and a.shape == a_ref.shape and np.array_equal(a, a_ref)
